@@ -1,0 +1,197 @@
+/* pgk.h -- C ABI of libpgk.so: the sm_100a kernels behind the Progressive-GAN
+ * G + D + WGAN-GP training step.
+ *
+ * The reference (deepsound-project/pggan-pytorch) has no FFI of its own: all of
+ * its arithmetic is PyTorch library calls made from network.py / wgan_gp_loss.py.
+ * Each entry point below replaces the library call(s) named in its comment
+ * (file:line into the reference); INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every function ENQUEUES work on `stream` (a cudaStream_t) and returns
+ *    immediately: no allocation, no hidden synchronisation, no host<->device copy.
+ *  - return value 0 = ok; non-zero = error code, text via pgk_last_error().
+ *  - all pointers are DEVICE pointers owned by the caller for the duration of
+ *    the call.
+ *  - "planes" tensors are the internal activation format: P planes (1 or 2) of
+ *    bfloat16 in N,H,W,C order (channels innermost, C % 8 == 0).  value =
+ *    plane0 (+ plane1).  P = 2 is the fp32-faithful mode (hi + lo split keeps
+ *    ~16 mantissa bits and feeds the 3-product tensor-core scheme), P = 1 is
+ *    the bf16 mode.  `*_ps` arguments are the plane stride in ELEMENTS.
+ *  - "image" tensors are the reference's own surface format: fp32, N,C,H,W.
+ *  - LeakyReLU slope is 0.2 (network.py:27); lrelu'(v) = v > 0 ? 1 : 0.2.
+ */
+#ifndef PGK_H
+#define PGK_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* pgk_stream_t; /* cudaStream_t */
+
+#define PGK_OK 0
+#define PGK_ERR_ARG 1
+#define PGK_ERR_CUDA 2
+#define PGK_ERR_ARCH 3
+
+/* weight layouts (`kind`) understood by pgk_prep_weight / pgk_unprep_grad */
+#define PGK_W_CONV 0   /* KSxKS "same" conv, KS in {1,3}   (network.py:16,34)            */
+#define PGK_W_GFIRST 1 /* G's 4x4 pad-3 conv on a 1x1 input = dense GEMM (network.py:47)  */
+#define PGK_W_DLAST 2  /* D's 4x4 valid conv on a 4x4 input = dense GEMM (network.py:163) */
+
+int pgk_version(void);
+const char* pgk_last_error(void);
+/* 0 iff `device` is compute capability 10.x (the library carries sm_100a SASS only). */
+int pgk_arch_check(int device);
+/* number of kernels launched by this library since load / since the last reset (bench's gpu_launches). */
+long long pgk_launch_count(void);
+void pgk_reset_launch_count(void);
+
+/* ---- equalised-LR weights: fold c into the weight, re-lay for the kernels --------------
+ * replaces `h = x * self.c` (network.py:33) + the cuDNN filter transform.
+ * w: (Cout, cin_stride, KH, KW) fp32 as PyTorch stores it; only input channels [0, cin) are used.
+ * wf: forward operand  [K][Cout]   K = taps*cin  (PGK_W_CONV), cin (GFIRST, Cout' = 16*cout), 16*cin (DLAST)
+ * wb: backward operand [K'][cin']  the transposed / tap-flipped operand for the data gradient. */
+int pgk_prep_weight(const float* w, float c, int kind, int cin, int cin_stride, int cout, int ks,
+                    float* wf, float* wb, pgk_stream_t stream);
+/* inverse map for weight gradients: dw (PyTorch layout) (+)= c * dwp (wf layout). */
+int pgk_unprep_grad(const float* dwp, float c, int kind, int cin, int cin_stride, int cout, int ks,
+                    float* dw, int accumulate, pgk_stream_t stream);
+
+/* ---- the convolution (network.py:34, F.conv2d through cuDNN) ---------------------------
+ * out[n,y,x,co] = E( sum_{tap,ci} X[n, y+dy, x+dx, ci] * wf[tap*Cin+ci][co] ), zero padded, stride 1.
+ *   ups = 1: X is the nearest-neighbour 2x upsample of x (x has H/2 x W/2)  (network.py:127,129)
+ *   E(v) = v + bias[co] + pos_s[n] * posT[(y*W+x)*Cout + co]   (each term optional)
+ *          then LeakyReLU if act == 1                          (network.py:36)
+ *          then * lrelu'(mask_ref[n,y,x,co]) if mask_ref       (the backward of network.py:36)
+ *          then * out_scale
+ * The same entry point computes data gradients (x = output gradient, wf = wb of the layer,
+ * mask_ref = the stored input activation of the layer) and the gradient-penalty's second chain. */
+int pgk_conv(const void* x, int P, long long x_ps, int N, int H, int W, int Cin, int Cout, int KS, int ups,
+             const float* wf, const float* bias, const float* posT, const float* pos_s, int act,
+             const void* mask_ref, long long mask_ps, float out_scale, void* out, long long out_ps,
+             pgk_stream_t stream);
+
+/* ---- weight gradient (cuDNN convolution_backward, weight part) --------------------------
+ * dwp[tap*Cin+ci][co] += sum over the listed sample groups of X[..., ci] (shifted by tap) * g[..., co].
+ * Groups: ngroups (<= 4) groups of group_n samples; group i reads x samples starting at xoff[i] and g samples
+ * starting at goff[i].  dwp must be zeroed by the caller (fp32, wf layout). */
+int pgk_wgrad(const void* x, long long x_ps, const void* g, long long g_ps, int P, int H, int W, int Cin, int Cout,
+              int KS, int ups, int ngroups, int group_n, const int* xoff, const int* goff, float* dwp,
+              pgk_stream_t stream);
+/* db[co] (+)= scale * sum over pixels of the listed sample groups of g[..., co]. */
+int pgk_bias_grad(const void* g, long long g_ps, int P, int HW, int Cout, int ngroups, int group_n, const int* goff,
+                  float scale, float* db, int accumulate, pgk_stream_t stream);
+
+/* ---- 1x1 convs against the image surface ------------------------------------------------
+ * fromRGB (network.py:145,160): out[n,y,x,co] = E(sum_c c*w[co][c] * img[n,c,y,x]); E as in pgk_conv
+ * (bias, act, mask_ref).  w is the PyTorch (Cout, C, 1, 1) tensor, scale c applied here. */
+int pgk_from_rgb(const float* img, int N, int C, int H, int W, int Cout, const float* w, float c, const float* bias,
+                 int act, const void* mask_ref, long long mask_ps, void* out, int P, long long out_ps,
+                 pgk_stream_t stream);
+/* data gradient of fromRGB to the image: dimg[n,c,y,x] (+)= scale * sum_co c*w[co][c] * g[n,y,x,co];
+ * ups = 1: g has H/2 x W/2 and is read at (y/2, x/2) (the avg-pooled low-res branch, network.py:231-232). */
+int pgk_from_rgb_dgrad(const void* g, int P, long long g_ps, int N, int C, int H, int W, int Cout, const float* w,
+                       float c, float scale, int ups, int accumulate, float* dimg, pgk_stream_t stream);
+/* toRGB (network.py:49,65) with the generator's fade-in (network.py:131-138):
+ * img[n,c,y,x] = a_hi * (sum_k c_hi*w_hi[c][k]*h[n,y,x,k] + b_hi[c])
+ *              + a_lo * (sum_k c_lo*w_lo[c][k]*h_lo[n,y/2,x/2,k] + b_lo[c])     (second term iff h_lo != NULL) */
+int pgk_to_rgb(const void* h, int P, long long h_ps, int N, int H, int W, int Cin, const float* w_hi, float c_hi,
+               const float* b_hi, float a_hi, const void* h_lo, long long hlo_ps, int Cin_lo, const float* w_lo,
+               float c_lo, const float* b_lo, float a_lo, int C, float* img, pgk_stream_t stream);
+/* data gradient of toRGB: dh[n,y,x,k] = scale * sum_c c*w[c][k] * dimg(n,c,y,x); pool = 1: dimg is summed over the
+ * 2x2 block (2y..2y+1, 2x..2x+1) of a 2H x 2W image (the backward of toRGB_prev(upsample(h))). */
+int pgk_to_rgb_dgrad(const float* dimg, int N, int C, int H, int W, int Cin, const float* w, float c, float scale,
+                     int pool, void* dh, int P, long long dh_ps, pgk_stream_t stream);
+/* weight/bias gradients of both 1x1 families in one pass over pixels:
+ * dw[a*sa + k*sk] += scale_w * sum_{n,pix} IMG(n,a,pix) * t[n,pix,k];  d_colsum[k] += scale_b*sum t;  d_imgsum[a] += scale_b*sum IMG
+ * IMG = img, or its 2x2 block sum when pool = 1 (img is then 2H x 2W).  Any output pointer may be NULL. */
+int pgk_rgb_wgrad(const float* img, int img_n0, const void* t, int P, long long t_ps, int t_n0, int N, int C, int H,
+                  int W, int K, int pool, float scale_w, float scale_b, float* dw, int sa, int sk, float* d_colsum,
+                  float* d_imgsum, pgk_stream_t stream);
+
+/* ---- elementwise / reductions on planes ------------------------------------------------- */
+/* out = a * pool2x2(src) [+ b * other]; avg = 1: mean of the block (F.avg_pool2d, network.py:229,238),
+ * avg = 0: sum (backward of the nearest upsample).  src is N x 2H x 2W x C, out/other N x H x W x C. */
+int pgk_pool2(const void* src, long long src_ps, int P, int N, int H, int W, int C, int avg, float a,
+              const void* other, long long other_ps, float b, void* out, long long out_ps, pgk_stream_t stream);
+/* out[n,y,x,c] = scale * src[n, y>>ups, x>>ups, c] * lrelu'(ref[n,y,x,c]) (ref optional) */
+int pgk_mask_mul(const void* src, long long src_ps, int P, int N, int H, int W, int C, int ups, float scale,
+                 const void* ref, long long ref_ps, void* out, long long out_ps, pgk_stream_t stream);
+/* out = a*x + b*y (y optional) on planes with `count` elements per plane */
+int pgk_axpby(const void* x, long long x_ps, float a, const void* y, long long y_ps, float b, int P, long long count,
+              void* out, long long out_ps, pgk_stream_t stream);
+/* pixel norm (network.py:37-40): y = h * r, r = rsqrt(mean_c(h^2) + 1e-8); in place allowed; r (fp32 per pixel) stored. */
+int pgk_pixelnorm(const void* h, long long h_ps, int P, long long npix, int C, void* y, long long y_ps, float* r,
+                  pgk_stream_t stream);
+/* backward of LeakyReLU -> pixel norm: da = r * (dy - y * mean_c(dy*y)) * lrelu'(y)  */
+int pgk_pixelnorm_bwd(const void* dy, long long dy_ps, const void* y, long long y_ps, const float* r, int P,
+                      long long npix, int C, void* da, long long da_ps, pgk_stream_t stream);
+/* latent normalisation (network.py:119-123): fp32 (N, L) -> planes (N,1,1,L) */
+int pgk_latent_norm(const float* z, int N, int L, int normalize, void* out, int P, long long out_ps,
+                    pgk_stream_t stream);
+
+/* ---- minibatch stddev (network.py:174-187) and its first / second derivatives ------------
+ * stats[g*4 + {0,1,2,3}] = {mean, s, 1/(n*s), n} over group g (group_n samples x HWC values each);
+ * svec[g*group_n + i] = s_g (the per-sample scalar pgk_conv's pos_s wants; optional). */
+int pgk_stddev_stats(const void* h, long long h_ps, int P, int ngroups, long long group_count, float* stats,
+                     float* svec, int group_n, pgk_stream_t stream);
+/* q[g] = sum over group g of ua[n,y,x,co] * posT[(y*W+x)*C + co]   (the gradient arriving at the stddev scalar) */
+int pgk_group_dot_pos(const void* ua, long long ua_ps, int P, int ngroups, int group_n, int HW, int C,
+                      const float* posT, float* q, pgk_stream_t stream);
+/* first-order backward: dh += q[g] * (h - mean_g) / (n s_g) */
+int pgk_stddev_bwd(const void* h, long long h_ps, const float* stats, const float* q, int P, int ngroups,
+                   long long group_count, void* dh, long long dh_ps, pgk_stream_t stream);
+/* second-order terms for ONE group (the mixed samples): given v (cotangent of the data-gradient at h),
+ *   e  = <v, (h-mean)/(n s)>                       -> ev[0..ev_n)  (value of the extra channel in the v-chain)
+ *   wh = q/(n s) * (v - mean(v)) - q*e*(h-mean)/(n s^2)        (cotangent entering the forward graph at h) */
+int pgk_stddev_bwd2(const void* h, long long h_ps, const void* v, long long v_ps, const float* stats,
+                    const float* q, int P, long long group_count, float* ev, int ev_n, void* wh, long long wh_ps,
+                    float* scratch, pgk_stream_t stream);
+/* gradient of the extra (stddev) input channel's filter taps of D's last 3x3 conv:
+ * dw[co][ch][ky][kx] += c * sum_{n,y,x : (y+ky-1,x+kx-1) inside} coef[n] * ua[n,y,x,co];   dw has cin_stride channels */
+int pgk_posbias_wgrad(const void* ua, long long ua_ps, int P, int N, int H, int W, int Cout, const float* coef,
+                      float c, int cin_stride, int ch, float* dw, pgk_stream_t stream);
+/* posT[(y*W+x)*Cout+co] = c * sum_{taps inside at (y,x)} w[co][ch][ky][kx] */
+int pgk_prep_posbias(const float* w, float c, int cin_stride, int ch, int Cout, int H, int W, float* posT,
+                     pgk_stream_t stream);
+
+/* ---- head: nn.Linear(512,1) (network.py:219,239) ------------------------------------------ */
+int pgk_linear_fwd(const void* h, long long h_ps, int P, int N, int K, const float* w, const float* b, float* scores,
+                   pgk_stream_t stream);
+/* ua[n,k] = seed[n] * w[k] * lrelu'(h[n,k]);  dw[k] += sum_n wseed[n]*h[n,k];  db += sum_n wseed[n]  (wseed optional) */
+int pgk_linear_bwd(const void* h, long long h_ps, int P, int N, int K, const float* w, const float* seed,
+                   const float* wseed, void* ua, long long ua_ps, float* dw, float* db, pgk_stream_t stream);
+/* dw[k] += sum_n v[n,k]   (gradient-penalty term of the head's weight) */
+int pgk_colsum(const void* v, long long v_ps, int P, int N, int K, float scale, float* dw, pgk_stream_t stream);
+
+/* ---- WGAN-GP algebra (wgan_gp_loss.py) ---------------------------------------------------- */
+/* mixed = real*(1-eps_n) + fake*eps_n per sample (wgan_gp_loss.py:8-10,19); per = C*H*W */
+int pgk_interpolate(const float* real, const float* fake, const float* eps, int N, long long per, float* mixed,
+                    pgk_stream_t stream);
+/* scores: [real N | fake N | mixed N].  Writes (wgan_gp_loss.py:48,55; trainer.py:98):
+ *   d_real_loss[n] = -Dr + eps_drift*Dr^2 ; d_fake_loss[n] = Df
+ *   seed[3N]: d cost / d score = {(-1 + 2 eps_drift Dr)/N, 1/N, 1 (the grad_outputs of wgan_gp_loss.py:21-23)}
+ *   wseed[3N]: the same with 0 for the mixed samples (their scores do not enter the cost directly) */
+int pgk_d_loss_seed(const float* scores, int N, float eps_drift, float* d_real_loss, float* d_fake_loss, float* seed,
+                    float* wseed, pgk_stream_t stream);
+/* out[0] = scale * mean(x[0..n))   (wgan_gp_loss.py:72-73: G_cost = mean(-D(G(z)))) */
+int pgk_mean_scale(const float* x, int n, float scale, float* out, pgk_stream_t stream);
+/* per-sample ||g||_2 of an image-shaped gradient, the penalty (wgan_gp_loss.py:29-31) and the cotangent
+ *   v0 = (1/N) * 2*lambda*(nrm - T)/(T^2 * nrm) * g ; also writes cost = mean(real)+mean(fake)+mean(gp).
+ * `norms` must hold 2N floats: [0,N) receives the norms, [N,2N) is scratch. */
+int pgk_gp_penalty(const float* g, int N, long long per, float lambda, float target, const float* d_real_loss,
+                   const float* d_fake_loss, float* norms, float* gp, float* v0, float* cost, pgk_stream_t stream);
+/* generic fp32 helpers */
+int pgk_fill(float* p, long long n, float v, pgk_stream_t stream);
+/* out[n,c,y,x] = scale * (mean | sum) of the 2x2 block of img; H, W are the OUTPUT sizes (img is 2H x 2W) */
+int pgk_pool_img(const float* img, int N, int C, int H, int W, int avg, float scale, float* out, pgk_stream_t stream);
+/* dst[n,c,y,x] (+)= scale * src[n,c,y>>1,x>>1] (fp32 images; H, W are dst sizes) */
+int pgk_unpool_img_add(const float* src, int N, int C, int H, int W, float scale, int accumulate, float* dst,
+                       pgk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGK_H */

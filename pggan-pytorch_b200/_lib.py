@@ -1,0 +1,124 @@
+"""ctypes binding of libpgk.so (include/pgk.h).
+
+There is no fallback: if the shared library is missing or the device is not
+sm_100, importing the compute path raises.  Build with
+``python -c "import __graft_entry__ as g; g.build()"`` or ``make -C pggan-pytorch_b200/csrc``.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libpgk.so')
+
+P, I, L, F = c_void_p, c_int, c_longlong, c_float
+
+# name -> argument ctypes, in the order of include/pgk.h (the trailing stream argument is appended automatically)
+SIGNATURES = {
+    'pgk_prep_weight': [P, F, I, I, I, I, I, P, P],
+    'pgk_unprep_grad': [P, F, I, I, I, I, I, P, I],
+    'pgk_conv': [P, I, L, I, I, I, I, I, I, I, P, P, P, P, I, P, L, F, P, L],
+    'pgk_wgrad': [P, L, P, L, I, I, I, I, I, I, I, I, I, P, P, P],
+    'pgk_bias_grad': [P, L, I, I, I, I, I, P, F, P, I],
+    'pgk_from_rgb': [P, I, I, I, I, I, P, F, P, I, P, L, P, I, L],
+    'pgk_from_rgb_dgrad': [P, I, L, I, I, I, I, I, P, F, F, I, I, P],
+    'pgk_to_rgb': [P, I, L, I, I, I, I, P, F, P, F, P, L, I, P, F, P, F, I, P],
+    'pgk_to_rgb_dgrad': [P, I, I, I, I, I, P, F, F, I, P, I, L],
+    'pgk_rgb_wgrad': [P, I, P, I, L, I, I, I, I, I, I, I, F, F, P, I, I, P, P],
+    'pgk_pool2': [P, L, I, I, I, I, I, I, F, P, L, F, P, L],
+    'pgk_mask_mul': [P, L, I, I, I, I, I, I, F, P, L, P, L],
+    'pgk_axpby': [P, L, F, P, L, F, I, L, P, L],
+    'pgk_pixelnorm': [P, L, I, L, I, P, L, P],
+    'pgk_pixelnorm_bwd': [P, L, P, L, P, I, L, I, P, L],
+    'pgk_latent_norm': [P, I, I, I, P, I, L],
+    'pgk_stddev_stats': [P, L, I, I, L, P, P, I],
+    'pgk_group_dot_pos': [P, L, I, I, I, I, I, P, P],
+    'pgk_stddev_bwd': [P, L, P, P, I, I, L, P, L],
+    'pgk_stddev_bwd2': [P, L, P, L, P, P, I, L, P, I, P, L, P],
+    'pgk_posbias_wgrad': [P, L, I, I, I, I, I, P, F, I, I, P],
+    'pgk_prep_posbias': [P, F, I, I, I, I, I, P],
+    'pgk_linear_fwd': [P, L, I, I, I, P, P, P],
+    'pgk_linear_bwd': [P, L, I, I, I, P, P, P, P, L, P, P],
+    'pgk_colsum': [P, L, I, I, I, F, P],
+    'pgk_interpolate': [P, P, P, I, L, P],
+    'pgk_d_loss_seed': [P, I, F, P, P, P, P],
+    'pgk_mean_scale': [P, I, F, P],
+    'pgk_gp_penalty': [P, I, L, F, F, P, P, P, P, P, P],
+    'pgk_fill': [P, L, F],
+    'pgk_pool_img': [P, I, I, I, I, I, F, P],
+    'pgk_unpool_img_add': [P, I, I, I, I, F, I, P],
+}
+
+_lib = None
+
+
+class PgkError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libpgk.so once; raise loudly if it is absent (no CPU / PyTorch fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PgkError('libpgk.so not found at %s -- build it first (__graft_entry__.build() or '
+                       '`make -C pggan-pytorch_b200/csrc`); there is no fallback path' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.pgk_last_error.restype = c_char_p
+    lib.pgk_last_error.argtypes = []
+    lib.pgk_version.restype = c_int
+    lib.pgk_arch_check.argtypes = [c_int]
+    lib.pgk_arch_check.restype = c_int
+    lib.pgk_launch_count.restype = c_longlong
+    lib.pgk_reset_launch_count.restype = None
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = list(args) + [c_void_p]
+        fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return ['pgk_version', 'pgk_last_error', 'pgk_arch_check', 'pgk_launch_count', 'pgk_reset_launch_count'] + \
+        list(SIGNATURES)
+
+
+_checked_devices = set()
+
+
+def check_device(device):
+    lib = load()
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx in _checked_devices:
+        return
+    rc = lib.pgk_arch_check(idx)
+    if rc != 0:
+        raise PgkError(lib.pgk_last_error().decode())
+    _checked_devices.add(idx)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def call(name, *args):
+    """Enqueue one libpgk call on torch's current CUDA stream."""
+    lib = load()
+    rc = getattr(lib, name)(*args, torch.cuda.current_stream().cuda_stream)
+    if rc != 0:
+        raise PgkError('%s failed (%d): %s' % (name, rc, lib.pgk_last_error().decode()))
+
+
+def launch_count():
+    return int(load().pgk_launch_count())
+
+
+def reset_launch_count():
+    load().pgk_reset_launch_count()

@@ -1,0 +1,161 @@
+// pgk_common.cuh -- shared device helpers for libpgk (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pgk.h"
+
+#define PGK_LRELU 0.2f
+
+extern "C" void pgk_set_error(const char* fmt, ...);
+extern "C" void pgk_count_launch(int n);
+
+#define PGK_REQUIRE(cond, ...)                                  \
+    do {                                                        \
+        if (!(cond)) {                                          \
+            pgk_set_error(__VA_ARGS__);                         \
+            return PGK_ERR_ARG;                                 \
+        }                                                       \
+    } while (0)
+
+#define PGK_LAUNCH_CHECK(name)                                                          \
+    do {                                                                                \
+        cudaError_t e__ = cudaGetLastError();                                           \
+        if (e__ != cudaSuccess) {                                                       \
+            pgk_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));      \
+            return PGK_ERR_CUDA;                                                        \
+        }                                                                               \
+        pgk_count_launch(1);                                                            \
+    } while (0)
+
+typedef __nv_bfloat16 bf16;
+
+// A planes tensor: value = p[i] (+ p[i + ps] when P == 2)
+struct Planes {
+    bf16* p;
+    long long ps;
+    int P;
+};
+static inline Planes make_planes(const void* p, long long ps, int P) {
+    Planes t;
+    t.p = (bf16*)p;
+    t.ps = ps;
+    t.P = P;
+    return t;
+}
+
+__device__ __forceinline__ float bf16_bits_to_f(uint32_t b) { return __uint_as_float(b << 16); }
+
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+    f[0] = __uint_as_float(q.x << 16);
+    f[1] = __uint_as_float(q.x & 0xffff0000u);
+    f[2] = __uint_as_float(q.y << 16);
+    f[3] = __uint_as_float(q.y & 0xffff0000u);
+    f[4] = __uint_as_float(q.z << 16);
+    f[5] = __uint_as_float(q.z & 0xffff0000u);
+    f[6] = __uint_as_float(q.w << 16);
+    f[7] = __uint_as_float(q.w & 0xffff0000u);
+}
+
+// load 8 consecutive channels starting at element index i (i % 8 == 0)
+__device__ __forceinline__ void ld8(const Planes& t, long long i, float* f) {
+    uint4 q = __ldg(reinterpret_cast<const uint4*>(t.p + i));
+    unpack8(q, f);
+    if (t.P == 2) {
+        float g[8];
+        uint4 r = __ldg(reinterpret_cast<const uint4*>(t.p + t.ps + i));
+        unpack8(r, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += g[j];
+    }
+}
+
+__device__ __forceinline__ float ld1(const Planes& t, long long i) {
+    float v = __bfloat162float(t.p[i]);
+    if (t.P == 2) v += __bfloat162float(t.p[t.ps + i]);
+    return v;
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// split v into hi (bf16 RN) and lo = bf16(v - hi)
+__device__ __forceinline__ void split_store8(const Planes& t, long long i, const float* f) {
+    uint4 q;
+    q.x = pack2(f[0], f[1]);
+    q.y = pack2(f[2], f[3]);
+    q.z = pack2(f[4], f[5]);
+    q.w = pack2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(t.p + i) = q;
+    if (t.P == 2) {
+        float h[8];
+        unpack8(q, h);
+        uint4 r;
+        r.x = pack2(f[0] - h[0], f[1] - h[1]);
+        r.y = pack2(f[2] - h[2], f[3] - h[3]);
+        r.z = pack2(f[4] - h[4], f[5] - h[5]);
+        r.w = pack2(f[6] - h[6], f[7] - h[7]);
+        *reinterpret_cast<uint4*>(t.p + t.ps + i) = r;
+    }
+}
+
+__device__ __forceinline__ void split_store4(const Planes& t, long long i, const float* f) {
+    uint2 q;
+    q.x = pack2(f[0], f[1]);
+    q.y = pack2(f[2], f[3]);
+    *reinterpret_cast<uint2*>(t.p + i) = q;
+    if (t.P == 2) {
+        float h0 = __uint_as_float(q.x << 16), h1 = __uint_as_float(q.x & 0xffff0000u);
+        float h2 = __uint_as_float(q.y << 16), h3 = __uint_as_float(q.y & 0xffff0000u);
+        uint2 r;
+        r.x = pack2(f[0] - h0, f[1] - h1);
+        r.y = pack2(f[2] - h2, f[3] - h3);
+        *reinterpret_cast<uint2*>(t.p + t.ps + i) = r;
+    }
+}
+
+__device__ __forceinline__ void st1(const Planes& t, long long i, float v) {
+    bf16 h = __float2bfloat16_rn(v);
+    t.p[i] = h;
+    if (t.P == 2) t.p[t.ps + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+__device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : PGK_LRELU * v; }
+__device__ __forceinline__ float lrelu_grad(float v) { return v > 0.f ? 1.f : PGK_LRELU; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum; result valid in thread 0 (and broadcast through smem to all when bcast)
+__device__ __forceinline__ float block_sum(float v, float* sh /* >= 33 floats */) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        float t = lane < nw ? sh[lane] : 0.f;
+        t = warp_sum(t);
+        if (lane == 0) sh[32] = t;
+    }
+    __syncthreads();
+    return sh[32];
+}
+
+static inline int pgk_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}

@@ -1,0 +1,1216 @@
+// pgk_elem.cu -- the non-GEMM part of the step: weight re-layout, 1x1 convs against the NCHW image surface,
+// pooling / masks / pixel norm, minibatch-stddev (with first and second derivative), the head and the WGAN-GP
+// algebra.  All HBM-bound: 16-byte vector access on the channel-innermost planes, warp-shuffle reductions.
+#include <stdarg.h>
+
+#include "pgk_common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// library state
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static long long g_launches = 0;
+
+extern "C" void pgk_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" void pgk_count_launch(int n) { g_launches += n; }
+extern "C" const char* pgk_last_error(void) { return g_err; }
+extern "C" int pgk_version(void) { return 100; }
+extern "C" long long pgk_launch_count(void) { return g_launches; }
+extern "C" void pgk_reset_launch_count(void) { g_launches = 0; }
+extern "C" int pgk_arch_check(int device) {
+    int major = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (e != cudaSuccess) {
+        pgk_set_error("pgk_arch_check: %s", cudaGetErrorString(e));
+        return PGK_ERR_CUDA;
+    }
+    if (major != 10) {
+        pgk_set_error("pgk_arch_check: device %d has compute capability %d.x; libpgk carries sm_100a code only", device,
+                      major);
+        return PGK_ERR_ARCH;
+    }
+    return PGK_OK;
+}
+
+namespace {
+
+constexpr int MAXC = 4;  // image channels supported by the 1x1 image-surface kernels
+
+inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 1) / per); }
+
+// ------------------------------------------------------------------------------------------
+// weight re-layout
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void weight_index(int kind, int cin, int cout, int ks, int co, int ci, int ky, int kx,
+                                             long long& fi, long long& bi) {
+    if (kind == PGK_W_CONV) {
+        int tap = ky * ks + kx, tapf = (ks - 1 - ky) * ks + (ks - 1 - kx);
+        fi = ((long long)tap * cin + ci) * cout + co;
+        bi = ((long long)tapf * cout + co) * cin + ci;
+    } else if (kind == PGK_W_GFIRST) {  // out pixel (y,x) = (3-ky, 3-kx)
+        int p = (3 - ky) * 4 + (3 - kx);
+        fi = (long long)ci * (16 * cout) + (long long)p * cout + co;
+        bi = ((long long)p * cout + co) * cin + ci;
+    } else {  // PGK_W_DLAST: in pixel (y,x) = (ky,kx)
+        int p = ky * 4 + kx;
+        fi = ((long long)p * cin + ci) * cout + co;
+        bi = (long long)co * (16 * cin) + (long long)p * cin + ci;
+    }
+}
+
+__global__ void prep_weight_kernel(const float* __restrict__ w, float c, int kind, int cin, int cin_stride, int cout,
+                                   int ks, float* __restrict__ wf, float* __restrict__ wb) {
+    long long total = (long long)cout * cin * ks * ks;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        int kx = (int)(e % ks);
+        long long r = e / ks;
+        int ky = (int)(r % ks);
+        r /= ks;
+        int ci = (int)(r % cin);
+        int co = (int)(r / cin);
+        float v = c * w[(((long long)co * cin_stride + ci) * ks + ky) * ks + kx];
+        long long fi, bi;
+        weight_index(kind, cin, cout, ks, co, ci, ky, kx, fi, bi);
+        if (wf) wf[fi] = v;
+        if (wb) wb[bi] = v;
+    }
+}
+
+__global__ void unprep_grad_kernel(const float* __restrict__ dwp, float c, int kind, int cin, int cin_stride, int cout,
+                                   int ks, float* __restrict__ dw, int accumulate) {
+    long long total = (long long)cout * cin * ks * ks;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        int kx = (int)(e % ks);
+        long long r = e / ks;
+        int ky = (int)(r % ks);
+        r /= ks;
+        int ci = (int)(r % cin);
+        int co = (int)(r / cin);
+        long long fi, bi;
+        weight_index(kind, cin, cout, ks, co, ci, ky, kx, fi, bi);
+        long long o = (((long long)co * cin_stride + ci) * ks + ky) * ks + kx;
+        float v = c * dwp[fi];
+        dw[o] = accumulate ? dw[o] + v : v;
+    }
+}
+
+__global__ void prep_posbias_kernel(const float* __restrict__ w, float c, int cin_stride, int ch, int Cout, int H,
+                                    int W, float* __restrict__ posT) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= H * W * Cout) return;
+    int co = idx % Cout, p = idx / Cout;
+    int y = p / W, x = p % W;
+    float s = 0.f;
+    for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+            int iy = y + ky - 1, ix = x + kx - 1;
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) s += w[(((long long)co * cin_stride + ch) * 3 + ky) * 3 + kx];
+        }
+    posT[idx] = c * s;
+}
+
+// dw[co][ch][ky][kx] += c * sum_{n, (y,x) with (y+ky-1, x+kx-1) inside} coef[n] * ua[n,y,x,co]
+__global__ void posbias_wgrad_kernel(Planes ua, int N, int H, int W, int Cout, const float* __restrict__ coef, float c,
+                                     int cin_stride, int ch, float* __restrict__ dw, int n_per_cta) {
+    int co = blockIdx.x * blockDim.x + threadIdx.x;
+    int tap = blockIdx.y;
+    int ky = tap / 3, kx = tap % 3;
+    int nb = blockIdx.z * n_per_cta, ne = min(N, nb + n_per_cta);
+    if (co >= Cout) return;
+    float s = 0.f;
+    for (int n = nb; n < ne; ++n) {
+        float cf = coef[n];
+        float t = 0.f;
+        for (int y = 0; y < H; ++y) {
+            int iy = y + ky - 1;
+            if (iy < 0 || iy >= H) continue;
+            for (int x = 0; x < W; ++x) {
+                int ix = x + kx - 1;
+                if (ix < 0 || ix >= W) continue;
+                t += ld1(ua, (((long long)n * H + y) * W + x) * Cout + co);
+            }
+        }
+        s = fmaf(cf, t, s);
+    }
+    atomicAdd(dw + (((long long)co * cin_stride + ch) * 3 + ky) * 3 + kx, c * s);
+}
+
+// ------------------------------------------------------------------------------------------
+// 1x1 convs against the image surface
+// ------------------------------------------------------------------------------------------
+// "expand": image (few channels) -> planes (K channels):  out[n,y,x,k] = E(scale * sum_c Wm[c][k] * IMG(n,c,y,x))
+struct ExpandArgs {
+    const float* img;
+    int N, C, H, W, K;
+    const float* w;
+    int sc, sk;  // weight element (c,k) at w[c*sc + k*sk]
+    float wscale;
+    const float* bias;
+    int act;
+    Planes mask;
+    int has_mask;
+    int pool;  // IMG = 2x2 block sum of a 2H x 2W image
+    Planes out;
+};
+
+__global__ void __launch_bounds__(256) rgb_expand_kernel(ExpandArgs a) {
+    extern __shared__ float wsm[];  // [C][K]
+    for (int i = threadIdx.x; i < a.C * a.K; i += blockDim.x) {
+        int c = i / a.K, k = i - c * a.K;
+        wsm[i] = a.wscale * a.w[(long long)c * a.sc + (long long)k * a.sk];
+    }
+    __syncthreads();
+    const int nch = a.K >> 3;
+    const long long total = (long long)a.N * a.H * a.W * nch;
+    const int HW = a.H * a.W;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int chunk = (int)(idx % nch);
+        long long pix = idx / nch;
+        int n = (int)(pix / HW);
+        int r = (int)(pix - (long long)n * HW);
+        float iv[MAXC];
+        if (!a.pool) {
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c)
+                if (c < a.C) iv[c] = __ldg(a.img + ((long long)n * a.C + c) * HW + r);
+        } else {
+            int y = r / a.W, x = r - y * a.W;
+            int W2 = a.W * 2;
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c)
+                if (c < a.C) {
+                    const float* p = a.img + (((long long)n * a.C + c) * (a.H * 2) + 2 * y) * W2 + 2 * x;
+                    iv[c] = (__ldg(p) + __ldg(p + 1)) + (__ldg(p + W2) + __ldg(p + W2 + 1));
+                }
+        }
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c)
+                if (c < a.C) s = fmaf(iv[c], wsm[c * a.K + chunk * 8 + j], s);
+            if (a.bias) s += __ldg(a.bias + chunk * 8 + j);
+            if (a.act) s = lrelu(s);
+            v[j] = s;
+        }
+        long long o = pix * a.K + chunk * 8;
+        if (a.has_mask) {
+            float m[8];
+            ld8(a.mask, o, m);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] *= lrelu_grad(m[j]);
+        }
+        split_store8(a.out, o, v);
+    }
+}
+
+// "reduce": planes (K channels) -> image (few channels), up to two sources (the generator's fade-in):
+//   img[n,c,y,x] (+)= sum_s a_s * (sum_k Wm_s[c][k] * T_s[n, y>>u_s, x>>u_s, k] + b_s[c])
+struct ReduceSrc {
+    Planes t;
+    int K, ups;
+    const float* w;
+    int sc, sk;
+    float wscale;
+    const float* bias;
+    float a;
+};
+struct ReduceArgs {
+    ReduceSrc s[2];
+    int nsrc;
+    int N, C, H, W;
+    int L;  // lanes per pixel (power of two <= 32)
+    int accumulate;
+    float* img;
+};
+
+__global__ void __launch_bounds__(256) rgb_reduce_kernel(ReduceArgs a) {
+    extern __shared__ float wsm[];  // source 0: [C][K0], then source 1: [C][K1]
+    int off1 = a.C * a.s[0].K;
+    for (int s = 0; s < a.nsrc; ++s) {
+        int K = a.s[s].K;
+        float* dst = wsm + (s ? off1 : 0);
+        for (int i = threadIdx.x; i < a.C * K; i += blockDim.x) {
+            int c = i / K, k = i - c * K;
+            dst[i] = a.s[s].wscale * a.s[s].w[(long long)c * a.s[s].sc + (long long)k * a.s[s].sk];
+        }
+    }
+    __syncthreads();
+    const int L = a.L;
+    const int sub = threadIdx.x & (L - 1);
+    const long long npix = (long long)a.N * a.H * a.W;
+    const int HW = a.H * a.W;
+    const long long gstride = ((long long)gridDim.x * blockDim.x) / L;
+    // loop bound must be uniform inside each lane group (it is: all lanes of a group share pix)
+    const long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long pix = t0 / L;
+    for (long long wpix = (t0 & ~31ll) / L; wpix < npix; wpix += gstride, pix += gstride) {
+        const bool valid = pix < npix;  // whole warps iterate together: the shuffles below use the full mask
+        const long long pc = valid ? pix : 0;
+        int n = (int)(pc / HW);
+        int r = (int)(pc - (long long)n * HW);
+        int y = r / a.W, x = r - y * a.W;
+        float acc[MAXC] = {0.f, 0.f, 0.f, 0.f};
+        for (int s = 0; s < a.nsrc; ++s) {
+            const ReduceSrc& S = a.s[s];
+            const float* wm = wsm + (s ? off1 : 0);
+            int Hs = a.H >> S.ups, Ws = a.W >> S.ups;
+            long long base = (((long long)n * Hs + (y >> S.ups)) * Ws + (x >> S.ups)) * S.K;
+            float part[MAXC] = {0.f, 0.f, 0.f, 0.f};
+            for (int ch = sub; valid && ch < (S.K >> 3); ch += L) {
+                float f[8];
+                ld8(S.t, base + ch * 8, f);
+#pragma unroll
+                for (int c = 0; c < MAXC; ++c)
+                    if (c < a.C) {
+                        const float* wr = wm + c * S.K + ch * 8;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) part[c] = fmaf(f[j], wr[j], part[c]);
+                    }
+            }
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) acc[c] = fmaf(S.a, part[c], acc[c]);
+        }
+        for (int o = L >> 1; o > 0; o >>= 1) {
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+        }
+        if (sub == 0 && valid) {
+            for (int c = 0; c < a.C; ++c) {
+                float v = acc[c];
+                for (int s = 0; s < a.nsrc; ++s)
+                    if (a.s[s].bias) v = fmaf(a.s[s].a, __ldg(a.s[s].bias + c), v);
+                long long o = ((long long)n * a.C + c) * HW + r;
+                a.img[o] = a.accumulate ? a.img[o] + v : v;
+            }
+        }
+    }
+}
+
+// weight / bias gradients of the 1x1 families:
+//   dw[a*sa + k*sk] += scale * sum IMG(n,a,pix) * t[n,pix,k]; colsum[k] += scale * sum t; imgsum[a] += scale * sum IMG
+struct RgbWgradArgs {
+    const float* img;
+    int img_n0;
+    Planes t;
+    int t_n0;
+    int N, C, H, W, K, pool;
+    float scale, scale_b;
+    float* dw;
+    int sa, sk;
+    float* colsum;
+    float* imgsum;
+    long long R, r_per_cta;
+};
+
+__global__ void __launch_bounds__(256) rgb_wgrad_kernel(RgbWgradArgs a) {
+    __shared__ float red[256][MAXC * 8 + 8 + 1];
+    __shared__ float isum[MAXC];
+    const int nch = a.K >> 3;
+    const int t = threadIdx.x;
+    const int lanes = 256 / nch;
+    const int ch = t % nch, pl = t / nch;
+    const int HW = a.H * a.W;
+    float acc[MAXC][8];
+    float cs[8];
+    float is[MAXC] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        cs[j] = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) acc[c][j] = 0.f;
+    }
+    if (t < MAXC) isum[t] = 0.f;
+    long long r_begin = (long long)blockIdx.x * a.r_per_cta, r_end = r_begin + a.r_per_cta;
+    if (r_end > a.R) r_end = a.R;
+    if (pl < lanes) {
+        for (long long rr = r_begin + pl; rr < r_end; rr += lanes) {
+            int n = (int)(rr / HW);
+            int r = (int)(rr - (long long)n * HW);
+            float iv[MAXC] = {0.f, 0.f, 0.f, 0.f};
+            if (!a.pool) {
+#pragma unroll
+                for (int c = 0; c < MAXC; ++c)
+                    if (c < a.C) iv[c] = __ldg(a.img + ((long long)(a.img_n0 + n) * a.C + c) * HW + r);
+            } else {
+                int y = r / a.W, x = r - y * a.W;
+                int W2 = a.W * 2;
+#pragma unroll
+                for (int c = 0; c < MAXC; ++c)
+                    if (c < a.C) {
+                        const float* p = a.img + (((long long)(a.img_n0 + n) * a.C + c) * (a.H * 2) + 2 * y) * W2 + 2 * x;
+                        iv[c] = (__ldg(p) + __ldg(p + 1)) + (__ldg(p + W2) + __ldg(p + W2 + 1));
+                    }
+            }
+            float f[8];
+            ld8(a.t, ((long long)(a.t_n0 + n) * HW + r) * a.K + ch * 8, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                cs[j] += f[j];
+#pragma unroll
+                for (int c = 0; c < MAXC; ++c) acc[c][j] = fmaf(iv[c], f[j], acc[c][j]);
+            }
+            if (ch == 0) {
+#pragma unroll
+                for (int c = 0; c < MAXC; ++c) is[c] += iv[c];
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        red[t][MAXC * 8 + j] = cs[j];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) red[t][c * 8 + j] = acc[c][j];
+    }
+    __syncthreads();
+    if (ch == 0 && pl < lanes && a.imgsum) {
+        for (int c = 0; c < a.C; ++c) atomicAdd(&isum[c], is[c]);
+    }
+    if (t < nch) {
+        for (int q = 0; q < MAXC * 8 + 8; ++q) {
+            float tot = 0.f;
+            for (int l = 0; l < lanes; ++l) tot += red[l * nch + t][q];
+            int j = q & 7, c = q >> 3;
+            if (c < MAXC) {
+                if (c < a.C && a.dw) atomicAdd(a.dw + (long long)c * a.sa + (long long)(t * 8 + j) * a.sk, a.scale * tot);
+            } else if (a.colsum) {
+                atomicAdd(a.colsum + t * 8 + j, a.scale_b * tot);
+            }
+        }
+    }
+    __syncthreads();
+    if (t < a.C && a.imgsum) atomicAdd(a.imgsum + t, a.scale_b * isum[t]);
+}
+
+// ------------------------------------------------------------------------------------------
+// planes elementwise
+// ------------------------------------------------------------------------------------------
+__global__ void pool2_kernel(Planes src, int N, int H, int W, int C, float a, Planes other, int has_other, float b,
+                             Planes out) {
+    const int nch = C >> 3;
+    const long long total = (long long)N * H * W * nch;
+    const float sa = a;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int chunk = (int)(idx % nch);
+        long long pix = idx / nch;
+        int x = (int)(pix % W);
+        long long r = pix / W;
+        int y = (int)(r % H);
+        int n = (int)(r / H);
+        long long b00 = ((((long long)n * 2 * H + 2 * y) * 2 * W) + 2 * x) * C + chunk * 8;
+        float f0[8], f1[8], f2[8], f3[8], v[8];
+        ld8(src, b00, f0);
+        ld8(src, b00 + C, f1);
+        ld8(src, b00 + (long long)2 * W * C, f2);
+        ld8(src, b00 + (long long)2 * W * C + C, f3);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = sa * ((f0[j] + f1[j]) + (f2[j] + f3[j]));
+        long long o = pix * C + chunk * 8;
+        if (has_other) {
+            float g[8];
+            ld8(other, o, g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(b, g[j], v[j]);
+        }
+        split_store8(out, o, v);
+    }
+}
+
+__global__ void mask_mul_kernel(Planes src, int N, int H, int W, int C, int ups, float scale, Planes ref, int has_ref,
+                                Planes out) {
+    const int nch = C >> 3;
+    const long long total = (long long)N * H * W * nch;
+    const int Hs = H >> ups, Ws = W >> ups;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int chunk = (int)(idx % nch);
+        long long pix = idx / nch;
+        int x = (int)(pix % W);
+        long long r = pix / W;
+        int y = (int)(r % H);
+        int n = (int)(r / H);
+        float f[8];
+        ld8(src, ((((long long)n * Hs + (y >> ups)) * Ws) + (x >> ups)) * C + chunk * 8, f);
+        long long o = pix * C + chunk * 8;
+        if (has_ref) {
+            float m[8];
+            ld8(ref, o, m);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] *= scale * lrelu_grad(m[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] *= scale;
+        }
+        split_store8(out, o, f);
+    }
+}
+
+__global__ void axpby_kernel(Planes x, float a, Planes y, int has_y, float b, long long count, Planes out) {
+    const long long total = count >> 3;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        float f[8];
+        ld8(x, idx * 8, f);
+        if (has_y) {
+            float g[8];
+            ld8(y, idx * 8, g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = a * f[j] + b * g[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] *= a;
+        }
+        split_store8(out, idx * 8, f);
+    }
+}
+
+// pixel norm: L lanes per pixel, each lane owns up to 4 chunks of 8 channels
+__global__ void __launch_bounds__(256) pixelnorm_kernel(Planes h, long long npix, int C, int L, Planes y, float* r) {
+    const int nch = C >> 3;
+    const int sub = threadIdx.x & (L - 1);
+    const long long gstride = ((long long)gridDim.x * blockDim.x) / L;
+    const long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long pix = t0 / L;
+    for (long long wpix = (t0 & ~31ll) / L; wpix < npix; wpix += gstride, pix += gstride) {
+        const bool valid = pix < npix;
+        float f[4][8];
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int ch = sub + i * L;
+            if (valid && ch < nch) {
+                ld8(h, pix * C + ch * 8, f[i]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ss = fmaf(f[i][j], f[i][j], ss);
+            }
+        }
+        for (int o = L >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        float rs = rsqrtf(ss / (float)C + 1e-8f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int ch = sub + i * L;
+            if (valid && ch < nch) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[i][j] *= rs;
+                split_store8(y, pix * C + ch * 8, f[i]);
+            }
+        }
+        if (sub == 0 && valid && r) r[pix] = rs;
+    }
+}
+
+__global__ void __launch_bounds__(256) pixelnorm_bwd_kernel(Planes dy, Planes y, const float* __restrict__ r,
+                                                            long long npix, int C, int L, Planes da) {
+    const int nch = C >> 3;
+    const int sub = threadIdx.x & (L - 1);
+    const long long gstride = ((long long)gridDim.x * blockDim.x) / L;
+    const long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long pix = t0 / L;
+    for (long long wpix = (t0 & ~31ll) / L; wpix < npix; wpix += gstride, pix += gstride) {
+        const bool valid = pix < npix;
+        float g[4][8], v[4][8];
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int ch = sub + i * L;
+            if (valid && ch < nch) {
+                ld8(dy, pix * C + ch * 8, g[i]);
+                ld8(y, pix * C + ch * 8, v[i]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dot = fmaf(g[i][j], v[i][j], dot);
+            }
+        }
+        for (int o = L >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        float mean = dot / (float)C;
+        float rs = valid ? r[pix] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int ch = sub + i * L;
+            if (valid && ch < nch) {
+                float o8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o8[j] = rs * (g[i][j] - v[i][j] * mean) * lrelu_grad(v[i][j]);
+                split_store8(da, pix * C + ch * 8, o8);
+            }
+        }
+    }
+}
+
+__global__ void latent_norm_kernel(const float* __restrict__ z, int L, int normalize, Planes out) {
+    __shared__ float sh[33];
+    int n = blockIdx.x;
+    float ss = 0.f;
+    for (int k = threadIdx.x; k < L; k += blockDim.x) {
+        float v = z[(long long)n * L + k];
+        ss = fmaf(v, v, ss);
+    }
+    float tot = block_sum(ss, sh);
+    float rs = normalize ? rsqrtf(tot / (float)L + 1e-8f) : 1.f;
+    for (int k = threadIdx.x; k < L; k += blockDim.x) st1(out, (long long)n * L + k, z[(long long)n * L + k] * rs);
+}
+
+// ------------------------------------------------------------------------------------------
+// minibatch stddev
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) stddev_stats_kernel(Planes h, long long count, float* stats, float* svec,
+                                                            int group_n) {
+    __shared__ float sh[33];
+    int g = blockIdx.x;
+    long long base = (long long)g * count;
+    float s = 0.f;
+    for (long long i = threadIdx.x * 8ll; i < count; i += blockDim.x * 8ll) {
+        float f[8];
+        ld8(h, base + i, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += f[j];
+    }
+    float mean = block_sum(s, sh) / (float)count;
+    float v = 0.f;
+    for (long long i = threadIdx.x * 8ll; i < count; i += blockDim.x * 8ll) {
+        float f[8];
+        ld8(h, base + i, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float d = f[j] - mean;
+            v = fmaf(d, d, v);
+        }
+    }
+    float var = block_sum(v, sh) / (float)count;
+    if (threadIdx.x == 0) {
+        float sd = sqrtf(var + 1.0e-8f);
+        stats[g * 4 + 0] = mean;
+        stats[g * 4 + 1] = sd;
+        stats[g * 4 + 2] = 1.f / ((float)count * sd);
+        stats[g * 4 + 3] = (float)count;
+        sh[0] = sd;
+    }
+    __syncthreads();
+    if (svec)
+        for (int i = threadIdx.x; i < group_n; i += blockDim.x) svec[g * group_n + i] = sh[0];
+}
+
+__global__ void __launch_bounds__(256) group_dot_pos_kernel(Planes ua, long long group_count, int HWC,
+                                                            const float* __restrict__ posT, float* q,
+                                                            int ctas_per_group) {
+    __shared__ float sh[33];
+    int g = blockIdx.x / ctas_per_group, part = blockIdx.x % ctas_per_group;
+    long long base = (long long)g * group_count;
+    float s = 0.f;
+    for (long long i = (part * 256ll + threadIdx.x) * 8; i < group_count; i += ctas_per_group * 256ll * 8) {
+        float f[8];
+        ld8(ua, base + i, f);
+        const float* p = posT + (i % HWC);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s = fmaf(f[j], __ldg(p + j), s);
+    }
+    float tot = block_sum(s, sh);
+    if (threadIdx.x == 0) atomicAdd(q + g, tot);
+}
+
+__global__ void stddev_bwd_kernel(Planes h, const float* __restrict__ stats, const float* __restrict__ q,
+                                  long long group_count, int ngroups, Planes dh) {
+    const long long total = (group_count * ngroups) >> 3;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        long long i = idx * 8;
+        int g = (int)(i / group_count);
+        float mean = stats[g * 4], k = q[g] * stats[g * 4 + 2];
+        float f[8], d[8];
+        ld8(h, i, f);
+        ld8(dh, i, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = fmaf(k, f[j] - mean, d[j]);
+        split_store8(dh, i, d);
+    }
+}
+
+// scratch[0] = sum v*(h-mean), scratch[1] = sum v   (scratch zeroed by the caller wrapper)
+__global__ void __launch_bounds__(256) stddev_bwd2_reduce_kernel(Planes h, Planes v, const float* __restrict__ stats,
+                                                                 long long count, float* scratch) {
+    __shared__ float sh[33];
+    float mean = stats[0];
+    float s0 = 0.f, s1 = 0.f;
+    for (long long i = (blockIdx.x * 256ll + threadIdx.x) * 8; i < count; i += gridDim.x * 256ll * 8) {
+        float f[8], w[8];
+        ld8(h, i, f);
+        ld8(v, i, w);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s0 = fmaf(w[j], f[j] - mean, s0);
+            s1 += w[j];
+        }
+    }
+    float t0 = block_sum(s0, sh);
+    float t1 = block_sum(s1, sh);
+    if (threadIdx.x == 0) {
+        atomicAdd(scratch, t0);
+        atomicAdd(scratch + 1, t1);
+    }
+}
+
+__global__ void stddev_bwd2_apply_kernel(Planes h, Planes v, const float* __restrict__ stats,
+                                         const float* __restrict__ q, const float* __restrict__ scratch,
+                                         long long count, float* ev, int ev_n, Planes wh) {
+    const float mean = stats[0], sd = stats[1], inv_ns = stats[2];
+    const float e = scratch[0] * inv_ns;
+    const float vmean = scratch[1] / (float)count;
+    const float qq = q[0];
+    const float k1 = qq * inv_ns;            // q/(n s)
+    const float k2 = qq * e * inv_ns / sd;   // q e /(n s^2)
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < ev_n; i += blockDim.x) ev[i] = e;
+    const long long total = count >> 3;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        float f[8], w[8], o[8];
+        ld8(h, idx * 8, f);
+        ld8(v, idx * 8, w);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = k1 * (w[j] - vmean) - k2 * (f[j] - mean);
+        split_store8(wh, idx * 8, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// head
+// ------------------------------------------------------------------------------------------
+__global__ void linear_fwd_kernel(Planes h, int N, int K, const float* __restrict__ w, const float* __restrict__ b,
+                                  float* scores) {
+    int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    float s = 0.f;
+    for (int ch = lane; ch < (K >> 3); ch += 32) {
+        float f[8];
+        ld8(h, (long long)n * K + ch * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s = fmaf(f[j], __ldg(w + ch * 8 + j), s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) scores[n] = s + b[0];
+}
+
+__global__ void linear_bwd_kernel(Planes h, int N, int K, const float* __restrict__ w, const float* __restrict__ seed,
+                                  const float* __restrict__ wseed, Planes ua, float* dw, float* db) {
+    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch < (K >> 3)) {
+        float wv[8], acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            wv[j] = w[ch * 8 + j];
+            acc[j] = 0.f;
+        }
+        for (int n = 0; n < N; ++n) {
+            float f[8], o[8];
+            ld8(h, (long long)n * K + ch * 8, f);
+            float sd = seed[n];
+            float ws = wseed ? wseed[n] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                o[j] = sd * wv[j] * lrelu_grad(f[j]);
+                acc[j] = fmaf(ws, f[j], acc[j]);
+            }
+            split_store8(ua, (long long)n * K + ch * 8, o);
+        }
+        if (dw && wseed) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(dw + ch * 8 + j, acc[j]);
+        }
+    }
+    if (db && wseed && blockIdx.x == 0 && threadIdx.x == 0) {
+        float s = 0.f;
+        for (int n = 0; n < N; ++n) s += wseed[n];
+        atomicAdd(db, s);
+    }
+}
+
+__global__ void colsum_kernel(Planes v, int N, int K, float scale, float* dw) {
+    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= (K >> 3)) return;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int n = 0; n < N; ++n) {
+        float f[8];
+        ld8(v, (long long)n * K + ch * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(dw + ch * 8 + j, scale * acc[j]);
+}
+
+// ------------------------------------------------------------------------------------------
+// WGAN-GP algebra
+// ------------------------------------------------------------------------------------------
+__global__ void interpolate_kernel(const float* __restrict__ real, const float* __restrict__ fake,
+                                   const float* __restrict__ eps, long long per, long long total, float* mixed) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        float e = eps[i / per];
+        mixed[i] = real[i] * (1.f - e) + fake[i] * e;
+    }
+}
+
+__global__ void d_loss_seed_kernel(const float* __restrict__ scores, int N, float eps_drift, float* d_real_loss,
+                                   float* d_fake_loss, float* seed, float* wseed) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float dr = scores[n], df = scores[N + n];
+    d_real_loss[n] = -dr + dr * dr * eps_drift;
+    d_fake_loss[n] = df;
+    float inv = 1.f / (float)N;
+    seed[n] = (-1.f + 2.f * eps_drift * dr) * inv;
+    seed[N + n] = inv;
+    seed[2 * N + n] = 1.f;
+    wseed[n] = seed[n];
+    wseed[N + n] = inv;
+    wseed[2 * N + n] = 0.f;
+}
+
+__global__ void mean_scale_kernel(const float* __restrict__ x, int n, float scale, float* out) {
+    __shared__ float sh[33];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+    float tot = block_sum(s, sh);
+    if (threadIdx.x == 0) out[0] = scale * tot / (float)n;
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long per, int ctas_per_sample,
+                                                    float* norms2) {
+    __shared__ float sh[33];
+    int n = blockIdx.x / ctas_per_sample, part = blockIdx.x % ctas_per_sample;
+    const float* p = g + (long long)n * per;
+    float s = 0.f;
+    for (long long i = part * 256ll + threadIdx.x; i < per; i += ctas_per_sample * 256ll) s = fmaf(p[i], p[i], s);
+    float tot = block_sum(s, sh);
+    if (threadIdx.x == 0) atomicAdd(norms2 + n, tot);
+}
+
+__global__ void gp_finalize_kernel(const float* __restrict__ g, int N, long long per, float lambda, float target,
+                                   const float* __restrict__ d_real_loss, const float* __restrict__ d_fake_loss,
+                                   const float* __restrict__ norms2, float* norms, float* gp, float* v0, float* cost) {
+    const long long total = (long long)N * per;
+    const float inv_n = 1.f / (float)N, t2 = target * target;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        float c = 0.f;
+        for (int n = 0; n < N; ++n) {
+            float nr = sqrtf(norms2[n]);
+            float p = (nr - target) * (nr - target) * lambda / t2;
+            norms[n] = nr;
+            gp[n] = p;
+            c += p + d_real_loss[n] + d_fake_loss[n];
+        }
+        cost[0] = c * inv_n;
+    }
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int n = (int)(i / per);
+        float nr = sqrtf(norms2[n]);
+        float coef = nr > 0.f ? inv_n * 2.f * lambda * (nr - target) / (t2 * nr) : 0.f;
+        v0[i] = coef * g[i];
+    }
+}
+
+__global__ void fill_kernel(float* p, long long n, float v) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+__global__ void pool_img_kernel(const float* __restrict__ img, long long planes, int H, int W, float scale,
+                                float* out) {
+    const long long total = planes * H * W;  // H, W = output sizes
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int x = (int)(i % W);
+        long long r = i / W;
+        int y = (int)(r % H);
+        long long pl = r / H;
+        const float* p = img + (pl * 2 * H + 2 * y) * 2 * W + 2 * x;
+        out[i] = scale * ((p[0] + p[1]) + (p[2 * W] + p[2 * W + 1]));
+    }
+}
+
+__global__ void unpool_img_add_kernel(const float* __restrict__ src, long long planes, int H, int W, float scale,
+                                      int accumulate, float* dst) {
+    const long long total = planes * H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int x = (int)(i % W);
+        long long r = i / W;
+        int y = (int)(r % H);
+        long long pl = r / H;
+        float v = scale * src[(pl * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)];
+        dst[i] = accumulate ? dst[i] + v : v;
+    }
+}
+
+inline int lanes_for(int nch) {
+    int L = 1;
+    while (L < nch && L < 32) L <<= 1;
+    return L;
+}
+
+inline unsigned grid_cap(long long blocks) {
+    long long cap = 16ll * pgk_num_sms();
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+}  // namespace
+
+#define ST (cudaStream_t) stream
+
+extern "C" int pgk_prep_weight(const float* w, float c, int kind, int cin, int cin_stride, int cout, int ks, float* wf,
+                               float* wb, pgk_stream_t stream) {
+    PGK_REQUIRE(kind >= 0 && kind <= 2, "pgk_prep_weight: bad kind %d", kind);
+    PGK_REQUIRE(kind == PGK_W_CONV ? (ks == 1 || ks == 3) : ks == 4, "pgk_prep_weight: bad ks %d for kind %d", ks, kind);
+    PGK_REQUIRE(cin_stride >= cin, "pgk_prep_weight: cin_stride < cin");
+    long long total = (long long)cout * cin * ks * ks;
+    prep_weight_kernel<<<grid_cap((total + 255) / 256), 256, 0, ST>>>(w, c, kind, cin, cin_stride, cout, ks, wf, wb);
+    PGK_LAUNCH_CHECK("pgk_prep_weight");
+    return PGK_OK;
+}
+
+extern "C" int pgk_unprep_grad(const float* dwp, float c, int kind, int cin, int cin_stride, int cout, int ks,
+                               float* dw, int accumulate, pgk_stream_t stream) {
+    PGK_REQUIRE(kind >= 0 && kind <= 2, "pgk_unprep_grad: bad kind %d", kind);
+    long long total = (long long)cout * cin * ks * ks;
+    unprep_grad_kernel<<<grid_cap((total + 255) / 256), 256, 0, ST>>>(dwp, c, kind, cin, cin_stride, cout, ks, dw,
+                                                                      accumulate);
+    PGK_LAUNCH_CHECK("pgk_unprep_grad");
+    return PGK_OK;
+}
+
+extern "C" int pgk_prep_posbias(const float* w, float c, int cin_stride, int ch, int Cout, int H, int W, float* posT,
+                                pgk_stream_t stream) {
+    int total = H * W * Cout;
+    prep_posbias_kernel<<<blocks_for(total, 256), 256, 0, ST>>>(w, c, cin_stride, ch, Cout, H, W, posT);
+    PGK_LAUNCH_CHECK("pgk_prep_posbias");
+    return PGK_OK;
+}
+
+extern "C" int pgk_posbias_wgrad(const void* ua, long long ua_ps, int P, int N, int H, int W, int Cout,
+                                 const float* coef, float c, int cin_stride, int ch, float* dw, pgk_stream_t stream) {
+    int n_per = 16;
+    dim3 grid(blocks_for(Cout, 128), 9, blocks_for(N, n_per));
+    posbias_wgrad_kernel<<<grid, 128, 0, ST>>>(make_planes(ua, ua_ps, P), N, H, W, Cout, coef, c, cin_stride, ch, dw,
+                                               n_per);
+    PGK_LAUNCH_CHECK("pgk_posbias_wgrad");
+    return PGK_OK;
+}
+
+static int launch_expand(ExpandArgs& a, pgk_stream_t stream, const char* name) {
+    PGK_REQUIRE(a.C >= 1 && a.C <= MAXC, "%s: image channels must be 1..%d (got %d)", name, MAXC, a.C);
+    PGK_REQUIRE(a.K % 8 == 0, "%s: feature channels must be a multiple of 8 (got %d)", name, a.K);
+    size_t smem = sizeof(float) * a.C * a.K;
+    PGK_REQUIRE(smem <= 48 * 1024, "%s: weight does not fit shared memory", name);
+    long long total = (long long)a.N * a.H * a.W * (a.K >> 3);
+    rgb_expand_kernel<<<grid_cap((total + 255) / 256), 256, smem, ST>>>(a);
+    PGK_LAUNCH_CHECK(name);
+    return PGK_OK;
+}
+
+extern "C" int pgk_from_rgb(const float* img, int N, int C, int H, int W, int Cout, const float* w, float c,
+                            const float* bias, int act, const void* mask_ref, long long mask_ps, void* out, int P,
+                            long long out_ps, pgk_stream_t stream) {
+    ExpandArgs a;
+    a.img = img, a.N = N, a.C = C, a.H = H, a.W = W, a.K = Cout;
+    a.w = w, a.sc = 1, a.sk = C, a.wscale = c, a.bias = bias, a.act = act;
+    a.mask = make_planes(mask_ref, mask_ps, P);
+    a.has_mask = mask_ref != nullptr;
+    a.pool = 0;
+    a.out = make_planes(out, out_ps, P);
+    return launch_expand(a, stream, "pgk_from_rgb");
+}
+
+extern "C" int pgk_to_rgb_dgrad(const float* dimg, int N, int C, int H, int W, int Cin, const float* w, float c,
+                                float scale, int pool, void* dh, int P, long long dh_ps, pgk_stream_t stream) {
+    ExpandArgs a;
+    a.img = dimg, a.N = N, a.C = C, a.H = H, a.W = W, a.K = Cin;
+    a.w = w, a.sc = Cin, a.sk = 1, a.wscale = c * scale, a.bias = nullptr, a.act = 0;
+    a.mask = make_planes(nullptr, 0, P);
+    a.has_mask = 0;
+    a.pool = pool;
+    a.out = make_planes(dh, dh_ps, P);
+    return launch_expand(a, stream, "pgk_to_rgb_dgrad");
+}
+
+static int launch_reduce(ReduceArgs& a, pgk_stream_t stream, const char* name) {
+    PGK_REQUIRE(a.C >= 1 && a.C <= MAXC, "%s: image channels must be 1..%d (got %d)", name, MAXC, a.C);
+    size_t smem = 0;
+    int maxch = 0;
+    for (int s = 0; s < a.nsrc; ++s) {
+        PGK_REQUIRE(a.s[s].K % 8 == 0, "%s: feature channels must be a multiple of 8", name);
+        smem += sizeof(float) * a.C * a.s[s].K;
+        if ((a.s[s].K >> 3) > maxch) maxch = a.s[s].K >> 3;
+    }
+    PGK_REQUIRE(smem <= 48 * 1024, "%s: weights do not fit shared memory", name);
+    a.L = lanes_for(maxch);
+    long long threads = (long long)a.N * a.H * a.W * a.L;
+    rgb_reduce_kernel<<<grid_cap((threads + 255) / 256), 256, smem, ST>>>(a);
+    PGK_LAUNCH_CHECK(name);
+    return PGK_OK;
+}
+
+extern "C" int pgk_to_rgb(const void* h, int P, long long h_ps, int N, int H, int W, int Cin, const float* w_hi,
+                          float c_hi, const float* b_hi, float a_hi, const void* h_lo, long long hlo_ps, int Cin_lo,
+                          const float* w_lo, float c_lo, const float* b_lo, float a_lo, int C, float* img,
+                          pgk_stream_t stream) {
+    ReduceArgs a;
+    a.nsrc = h_lo ? 2 : 1;
+    a.s[0].t = make_planes(h, h_ps, P), a.s[0].K = Cin, a.s[0].ups = 0, a.s[0].w = w_hi, a.s[0].sc = Cin, a.s[0].sk = 1;
+    a.s[0].wscale = c_hi, a.s[0].bias = b_hi, a.s[0].a = a_hi;
+    a.s[1].t = make_planes(h_lo, hlo_ps, P), a.s[1].K = Cin_lo, a.s[1].ups = 1, a.s[1].w = w_lo, a.s[1].sc = Cin_lo;
+    a.s[1].sk = 1, a.s[1].wscale = c_lo, a.s[1].bias = b_lo, a.s[1].a = a_lo;
+    a.N = N, a.C = C, a.H = H, a.W = W, a.accumulate = 0, a.img = img;
+    PGK_REQUIRE(!h_lo || (H % 2 == 0 && W % 2 == 0), "pgk_to_rgb: fade-in needs even H, W");
+    return launch_reduce(a, stream, "pgk_to_rgb");
+}
+
+extern "C" int pgk_from_rgb_dgrad(const void* g, int P, long long g_ps, int N, int C, int H, int W, int Cout,
+                                  const float* w, float c, float scale, int ups, int accumulate, float* dimg,
+                                  pgk_stream_t stream) {
+    ReduceArgs a;
+    a.nsrc = 1;
+    a.s[0].t = make_planes(g, g_ps, P), a.s[0].K = Cout, a.s[0].ups = ups, a.s[0].w = w, a.s[0].sc = 1, a.s[0].sk = C;
+    a.s[0].wscale = c, a.s[0].bias = nullptr, a.s[0].a = scale;
+    a.s[1] = a.s[0];
+    a.N = N, a.C = C, a.H = H, a.W = W, a.accumulate = accumulate, a.img = dimg;
+    return launch_reduce(a, stream, "pgk_from_rgb_dgrad");
+}
+
+extern "C" int pgk_rgb_wgrad(const float* img, int img_n0, const void* t, int P, long long t_ps, int t_n0, int N,
+                             int C, int H, int W, int K, int pool, float scale_w, float scale_b, float* dw, int sa,
+                             int sk, float* d_colsum, float* d_imgsum, pgk_stream_t stream) {
+    PGK_REQUIRE(C >= 1 && C <= MAXC, "pgk_rgb_wgrad: image channels must be 1..%d", MAXC);
+    PGK_REQUIRE(K % 8 == 0 && K / 8 <= 256, "pgk_rgb_wgrad: K must be a multiple of 8 and <= 2048");
+    RgbWgradArgs a;
+    a.img = img, a.img_n0 = img_n0, a.t = make_planes(t, t_ps, P), a.t_n0 = t_n0;
+    a.N = N, a.C = C, a.H = H, a.W = W, a.K = K, a.pool = pool, a.scale = scale_w, a.scale_b = scale_b;
+    a.dw = dw, a.sa = sa, a.sk = sk, a.colsum = d_colsum, a.imgsum = d_imgsum;
+    a.R = (long long)N * H * W;
+    long long ctas = (a.R + 255) / 256;
+    long long cap = 4ll * pgk_num_sms();
+    if (ctas > cap) ctas = cap;
+    if (ctas < 1) ctas = 1;
+    a.r_per_cta = (a.R + ctas - 1) / ctas;
+    rgb_wgrad_kernel<<<(unsigned)ctas, 256, 0, ST>>>(a);
+    PGK_LAUNCH_CHECK("pgk_rgb_wgrad");
+    return PGK_OK;
+}
+
+extern "C" int pgk_pool2(const void* src, long long src_ps, int P, int N, int H, int W, int C, int avg, float a,
+                         const void* other, long long other_ps, float b, void* out, long long out_ps,
+                         pgk_stream_t stream) {
+    PGK_REQUIRE(C % 8 == 0, "pgk_pool2: C must be a multiple of 8");
+    long long total = (long long)N * H * W * (C >> 3);
+    pool2_kernel<<<grid_cap((total + 255) / 256), 256, 0, ST>>>(make_planes(src, src_ps, P), N, H, W, C,
+                                                                avg ? 0.25f * a : a, make_planes(other, other_ps, P),
+                                                                other != nullptr, b, make_planes(out, out_ps, P));
+    PGK_LAUNCH_CHECK("pgk_pool2");
+    return PGK_OK;
+}
+
+extern "C" int pgk_mask_mul(const void* src, long long src_ps, int P, int N, int H, int W, int C, int ups, float scale,
+                            const void* ref, long long ref_ps, void* out, long long out_ps, pgk_stream_t stream) {
+    PGK_REQUIRE(C % 8 == 0, "pgk_mask_mul: C must be a multiple of 8");
+    PGK_REQUIRE(!ups || (H % 2 == 0 && W % 2 == 0), "pgk_mask_mul: ups needs even H, W");
+    long long total = (long long)N * H * W * (C >> 3);
+    mask_mul_kernel<<<grid_cap((total + 255) / 256), 256, 0, ST>>>(make_planes(src, src_ps, P), N, H, W, C, ups, scale,
+                                                                   make_planes(ref, ref_ps, P), ref != nullptr,
+                                                                   make_planes(out, out_ps, P));
+    PGK_LAUNCH_CHECK("pgk_mask_mul");
+    return PGK_OK;
+}
+
+extern "C" int pgk_axpby(const void* x, long long x_ps, float a, const void* y, long long y_ps, float b, int P,
+                         long long count, void* out, long long out_ps, pgk_stream_t stream) {
+    PGK_REQUIRE(count % 8 == 0, "pgk_axpby: count must be a multiple of 8");
+    axpby_kernel<<<grid_cap((count / 8 + 255) / 256), 256, 0, ST>>>(make_planes(x, x_ps, P), a, make_planes(y, y_ps, P),
+                                                                    y != nullptr, b, count, make_planes(out, out_ps, P));
+    PGK_LAUNCH_CHECK("pgk_axpby");
+    return PGK_OK;
+}
+
+extern "C" int pgk_pixelnorm(const void* h, long long h_ps, int P, long long npix, int C, void* y, long long y_ps,
+                             float* r, pgk_stream_t stream) {
+    PGK_REQUIRE(C % 8 == 0 && C <= 1024, "pgk_pixelnorm: C must be a multiple of 8 and <= 1024");
+    int L = lanes_for(C >> 3);
+    pixelnorm_kernel<<<grid_cap((npix * L + 255) / 256), 256, 0, ST>>>(make_planes(h, h_ps, P), npix, C, L,
+                                                                       make_planes(y, y_ps, P), r);
+    PGK_LAUNCH_CHECK("pgk_pixelnorm");
+    return PGK_OK;
+}
+
+extern "C" int pgk_pixelnorm_bwd(const void* dy, long long dy_ps, const void* y, long long y_ps, const float* r, int P,
+                                 long long npix, int C, void* da, long long da_ps, pgk_stream_t stream) {
+    PGK_REQUIRE(C % 8 == 0 && C <= 1024, "pgk_pixelnorm_bwd: C must be a multiple of 8 and <= 1024");
+    int L = lanes_for(C >> 3);
+    pixelnorm_bwd_kernel<<<grid_cap((npix * L + 255) / 256), 256, 0, ST>>>(
+        make_planes(dy, dy_ps, P), make_planes(y, y_ps, P), r, npix, C, L, make_planes(da, da_ps, P));
+    PGK_LAUNCH_CHECK("pgk_pixelnorm_bwd");
+    return PGK_OK;
+}
+
+extern "C" int pgk_latent_norm(const float* z, int N, int L, int normalize, void* out, int P, long long out_ps,
+                               pgk_stream_t stream) {
+    latent_norm_kernel<<<N, 128, 0, ST>>>(z, L, normalize, make_planes(out, out_ps, P));
+    PGK_LAUNCH_CHECK("pgk_latent_norm");
+    return PGK_OK;
+}
+
+extern "C" int pgk_stddev_stats(const void* h, long long h_ps, int P, int ngroups, long long group_count, float* stats,
+                                float* svec, int group_n, pgk_stream_t stream) {
+    PGK_REQUIRE(group_count % 8 == 0, "pgk_stddev_stats: group size must be a multiple of 8");
+    stddev_stats_kernel<<<ngroups, 1024, 0, ST>>>(make_planes(h, h_ps, P), group_count, stats, svec, group_n);
+    PGK_LAUNCH_CHECK("pgk_stddev_stats");
+    return PGK_OK;
+}
+
+extern "C" int pgk_group_dot_pos(const void* ua, long long ua_ps, int P, int ngroups, int group_n, int HW, int C,
+                                 const float* posT, float* q, pgk_stream_t stream) {
+    cudaError_t e = cudaMemsetAsync(q, 0, sizeof(float) * ngroups, ST);
+    if (e != cudaSuccess) {
+        pgk_set_error("pgk_group_dot_pos: memset failed: %s", cudaGetErrorString(e));
+        return PGK_ERR_CUDA;
+    }
+    long long count = (long long)group_n * HW * C;
+    int per = (int)((count / 8 + 256 * 8 - 1) / (256 * 8));
+    if (per < 1) per = 1;
+    if (per > 64) per = 64;
+    group_dot_pos_kernel<<<ngroups * per, 256, 0, ST>>>(make_planes(ua, ua_ps, P), count, HW * C, posT, q, per);
+    PGK_LAUNCH_CHECK("pgk_group_dot_pos");
+    return PGK_OK;
+}
+
+extern "C" int pgk_stddev_bwd(const void* h, long long h_ps, const float* stats, const float* q, int P, int ngroups,
+                              long long group_count, void* dh, long long dh_ps, pgk_stream_t stream) {
+    long long total = group_count * ngroups / 8;
+    stddev_bwd_kernel<<<grid_cap((total + 255) / 256), 256, 0, ST>>>(make_planes(h, h_ps, P), stats, q, group_count,
+                                                                     ngroups, make_planes(dh, dh_ps, P));
+    PGK_LAUNCH_CHECK("pgk_stddev_bwd");
+    return PGK_OK;
+}
+
+extern "C" int pgk_stddev_bwd2(const void* h, long long h_ps, const void* v, long long v_ps, const float* stats,
+                               const float* q, int P, long long group_count, float* ev, int ev_n, void* wh,
+                               long long wh_ps, float* scratch, pgk_stream_t stream) {
+    cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(float) * 2, ST);
+    if (e != cudaSuccess) {
+        pgk_set_error("pgk_stddev_bwd2: memset failed: %s", cudaGetErrorString(e));
+        return PGK_ERR_CUDA;
+    }
+    long long total = group_count / 8;
+    unsigned nb = grid_cap((total + 255) / 256);
+    if (nb > 128) nb = 128;
+    stddev_bwd2_reduce_kernel<<<nb, 256, 0, ST>>>(make_planes(h, h_ps, P), make_planes(v, v_ps, P), stats, group_count,
+                                                  scratch);
+    PGK_LAUNCH_CHECK("pgk_stddev_bwd2(reduce)");
+    stddev_bwd2_apply_kernel<<<grid_cap((total + 255) / 256), 256, 0, ST>>>(
+        make_planes(h, h_ps, P), make_planes(v, v_ps, P), stats, q, scratch, group_count, ev, ev_n,
+        make_planes(wh, wh_ps, P));
+    PGK_LAUNCH_CHECK("pgk_stddev_bwd2(apply)");
+    return PGK_OK;
+}
+
+extern "C" int pgk_linear_fwd(const void* h, long long h_ps, int P, int N, int K, const float* w, const float* b,
+                              float* scores, pgk_stream_t stream) {
+    linear_fwd_kernel<<<blocks_for(N, 4), 128, 0, ST>>>(make_planes(h, h_ps, P), N, K, w, b, scores);
+    PGK_LAUNCH_CHECK("pgk_linear_fwd");
+    return PGK_OK;
+}
+
+extern "C" int pgk_linear_bwd(const void* h, long long h_ps, int P, int N, int K, const float* w, const float* seed,
+                              const float* wseed, void* ua, long long ua_ps, float* dw, float* db,
+                              pgk_stream_t stream) {
+    linear_bwd_kernel<<<blocks_for(K / 8, 32), 32, 0, ST>>>(make_planes(h, h_ps, P), N, K, w, seed, wseed,
+                                                            make_planes(ua, ua_ps, P), dw, db);
+    PGK_LAUNCH_CHECK("pgk_linear_bwd");
+    return PGK_OK;
+}
+
+extern "C" int pgk_colsum(const void* v, long long v_ps, int P, int N, int K, float scale, float* dw,
+                          pgk_stream_t stream) {
+    colsum_kernel<<<blocks_for(K / 8, 32), 32, 0, ST>>>(make_planes(v, v_ps, P), N, K, scale, dw);
+    PGK_LAUNCH_CHECK("pgk_colsum");
+    return PGK_OK;
+}
+
+extern "C" int pgk_interpolate(const float* real, const float* fake, const float* eps, int N, long long per,
+                               float* mixed, pgk_stream_t stream) {
+    long long total = (long long)N * per;
+    interpolate_kernel<<<grid_cap((total + 255) / 256), 256, 0, ST>>>(real, fake, eps, per, total, mixed);
+    PGK_LAUNCH_CHECK("pgk_interpolate");
+    return PGK_OK;
+}
+
+extern "C" int pgk_d_loss_seed(const float* scores, int N, float eps_drift, float* d_real_loss, float* d_fake_loss,
+                               float* seed, float* wseed, pgk_stream_t stream) {
+    d_loss_seed_kernel<<<blocks_for(N, 128), 128, 0, ST>>>(scores, N, eps_drift, d_real_loss, d_fake_loss, seed,
+                                                          wseed);
+    PGK_LAUNCH_CHECK("pgk_d_loss_seed");
+    return PGK_OK;
+}
+
+extern "C" int pgk_mean_scale(const float* x, int n, float scale, float* out, pgk_stream_t stream) {
+    PGK_REQUIRE(n > 0, "pgk_mean_scale: empty input");
+    mean_scale_kernel<<<1, 256, 0, ST>>>(x, n, scale, out);
+    PGK_LAUNCH_CHECK("pgk_mean_scale");
+    return PGK_OK;
+}
+
+extern "C" int pgk_gp_penalty(const float* g, int N, long long per, float lambda, float target,
+                              const float* d_real_loss, const float* d_fake_loss, float* norms, float* gp, float* v0,
+                              float* cost, pgk_stream_t stream) {
+    // norms is 2N floats: [0,N) receives the norms, [N,2N) is the sum-of-squares scratch.
+    float* norms2 = norms + N;
+    cudaError_t e = cudaMemsetAsync(norms2, 0, sizeof(float) * N, ST);
+    if (e != cudaSuccess) {
+        pgk_set_error("pgk_gp_penalty: memset failed: %s", cudaGetErrorString(e));
+        return PGK_ERR_CUDA;
+    }
+    int per_sample = (int)((per + 256 * 16 - 1) / (256 * 16));
+    if (per_sample < 1) per_sample = 1;
+    if (per_sample > 256) per_sample = 256;
+    sumsq_kernel<<<N * per_sample, 256, 0, ST>>>(g, per, per_sample, norms2);
+    PGK_LAUNCH_CHECK("pgk_gp_penalty(sumsq)");
+    long long total = (long long)N * per;
+    gp_finalize_kernel<<<grid_cap((total + 255) / 256), 256, 0, ST>>>(g, N, per, lambda, target, d_real_loss,
+                                                                      d_fake_loss, norms2, norms, gp, v0, cost);
+    PGK_LAUNCH_CHECK("pgk_gp_penalty(finalize)");
+    return PGK_OK;
+}
+
+extern "C" int pgk_fill(float* p, long long n, float v, pgk_stream_t stream) {
+    fill_kernel<<<grid_cap((n + 255) / 256), 256, 0, ST>>>(p, n, v);
+    PGK_LAUNCH_CHECK("pgk_fill");
+    return PGK_OK;
+}
+
+extern "C" int pgk_pool_img(const float* img, int N, int C, int H, int W, int avg, float scale, float* out,
+                            pgk_stream_t stream) {
+    long long total = (long long)N * C * H * W;
+    pool_img_kernel<<<grid_cap((total + 255) / 256), 256, 0, ST>>>(img, (long long)N * C, H, W,
+                                                                   avg ? 0.25f * scale : scale, out);
+    PGK_LAUNCH_CHECK("pgk_pool_img");
+    return PGK_OK;
+}
+
+extern "C" int pgk_unpool_img_add(const float* src, int N, int C, int H, int W, float scale, int accumulate, float* dst,
+                                  pgk_stream_t stream) {
+    long long total = (long long)N * C * H * W;
+    unpool_img_add_kernel<<<grid_cap((total + 255) / 256), 256, 0, ST>>>(src, (long long)N * C, H, W, scale, accumulate,
+                                                                         dst);
+    PGK_LAUNCH_CHECK("pgk_unpool_img_add");
+    return PGK_OK;
+}

@@ -1,0 +1,650 @@
+"""Kernel sequencing for the G + D + WGAN-GP step (host side, Python; all arithmetic is in libpgk.so).
+
+Everything here is stream-ordered enqueueing of libpgk kernels on torch's current stream -- no host
+synchronisation, no torch arithmetic on activations.  Tensors are allocated through torch's caching
+allocator (plumbing) and handed to the C ABI as raw pointers.
+
+Notation used below (see DESIGN.md "the gradient-penalty double backward"):
+  x_l   activation after layer l (post LeakyReLU)            -- "planes" tensors, N,H,W,C
+  ua_l  gradient w.r.t. the PRE-activation of layer l         = (incoming gradient) * lrelu'(x_l)
+  u-chain  the ordinary data-gradient chain through D (network.py:225-240 backwards).  For the mixed samples it
+           is the `autograd.grad(..., create_graph=True)` of wgan_gp_loss.py:25-28.
+  v-chain  the adjoint of the u-chain: D's forward applied to v0 = dPenalty/dg with biases dropped and
+           LeakyReLU replaced by the stored masks.  Gives dPenalty/dW as wgrad(v_{l-1}, ua_l).
+  w-chain  the second-order term that enters the forward graph through MinibatchStddev (network.py:174-187).
+"""
+import ctypes
+from types import SimpleNamespace
+
+import torch
+
+from . import _lib
+
+call = _lib.call
+BF16 = torch.bfloat16
+W_CONV, W_GFIRST, W_DLAST = 0, 1, 2
+
+
+def _ints(vals):
+    vals = list(vals)
+    return (ctypes.c_int * 4)(*(vals + [0] * (4 - len(vals))))
+
+
+class PT(object):
+    """A 'planes' tensor: P planes of bf16 in N,H,W,C order; value = plane0 (+ plane1)."""
+    __slots__ = ('t', 'N', 'H', 'W', 'C', 'P', 'off', 'ntot')
+
+    def __init__(self, t, N, H, W, C, P, off, ntot):
+        self.t, self.N, self.H, self.W, self.C, self.P, self.off, self.ntot = t, N, H, W, C, P, off, ntot
+
+    @staticmethod
+    def empty(N, H, W, C, P, device):
+        t = torch.empty((P, N, H, W, C), dtype=BF16, device=device)
+        return PT(t, N, H, W, C, P, 0, N)
+
+    @property
+    def per(self):
+        return self.H * self.W * self.C
+
+    @property
+    def ps(self):
+        return self.ntot * self.per
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr() + 2 * self.off * self.per
+
+    def sl(self, n0, n1):
+        return PT(self.t, n1 - n0, self.H, self.W, self.C, self.P, self.off + n0, self.ntot)
+
+    def view(self, H, W, C):
+        assert H * W * C == self.per
+        return PT(self.t, self.N, H, W, C, self.P, self.off, self.ntot)
+
+    def float(self):
+        """fp32 N,C,H,W copy (tests / debugging only)."""
+        v = self.t.view(self.P, self.ntot, self.H, self.W, self.C)[:, self.off:self.off + self.N].float().sum(0)
+        return v.permute(0, 3, 1, 2).contiguous()
+
+    @staticmethod
+    def from_float(x, P):
+        """fp32 N,C,H,W -> planes (tests only; the product path never converts through torch)."""
+        n, c, h, w = x.shape
+        v = x.permute(0, 2, 3, 1).contiguous().float()
+        hi = v.to(BF16)
+        out = PT.empty(n, h, w, c, P, x.device)
+        out.t[0] = hi
+        if P == 2:
+            out.t[1] = (v - hi.float()).to(BF16)
+        return out
+
+
+def _mask(m):
+    return (m.ptr, m.ps) if m is not None else (None, 0)
+
+
+# ---------------------------------------------------------------------------------------------
+# thin op wrappers (argument marshalling only)
+# ---------------------------------------------------------------------------------------------
+def conv(x, wf, cout, ks, out, ups=0, bias=None, posT=None, pos_s=None, act=0, mask=None, scale=1.0):
+    """out <- pgk_conv(x); H, W are taken from `out`."""
+    mp, mps = _mask(mask)
+    call('pgk_conv', x.ptr, x.P, x.ps, out.N, out.H, out.W, x.C, cout, ks, ups, wf.data_ptr(),
+         None if bias is None else bias.data_ptr(), None if posT is None else posT.data_ptr(),
+         None if pos_s is None else pos_s.data_ptr(), act, mp, mps, scale, out.ptr, out.ps)
+    return out
+
+
+def wgrad(x, g, H, W, cin, cout, ks, ups, groups, group_n, dwp):
+    xoff, goff = _ints([a for a, _ in groups]), _ints([b for _, b in groups])
+    call('pgk_wgrad', x.ptr, x.ps, g.ptr, g.ps, x.P, H, W, cin, cout, ks, ups, len(groups), group_n, xoff, goff,
+         dwp.data_ptr())
+
+
+def bias_grad(g, hw, cout, goffs, group_n, db, scale=1.0, accumulate=0):
+    call('pgk_bias_grad', g.ptr, g.ps, g.P, hw, cout, len(goffs), group_n, _ints(goffs), scale, db.data_ptr(),
+         accumulate)
+
+
+def from_rgb(img, mod, out, act=1, bias=True, mask=None):
+    n, c, h, w = img.shape
+    mp, mps = _mask(mask)
+    call('pgk_from_rgb', img.data_ptr(), n, c, h, w, out.C, mod.conv.weight.data_ptr(), mod.cf,
+         mod.conv.bias.data_ptr() if bias else None, act, mp, mps, out.ptr, out.P, out.ps)
+    return out
+
+
+def from_rgb_dgrad(g, mod, dimg, scale=1.0, ups=0, accumulate=0):
+    n, c, h, w = dimg.shape
+    call('pgk_from_rgb_dgrad', g.ptr, g.P, g.ps, n, c, h, w, g.C, mod.conv.weight.data_ptr(), mod.cf, scale, ups,
+         accumulate, dimg.data_ptr())
+
+
+def rgb_wgrad(img, img_n0, t, n, c, h, w, pool, scale_w, scale_b, dw, sa, sk, colsum, imgsum):
+    call('pgk_rgb_wgrad', img.data_ptr(), img_n0, t.ptr, t.P, t.ps, 0, n, c, h, w, t.C, pool, scale_w, scale_b,
+         None if dw is None else dw.data_ptr(), sa, sk, None if colsum is None else colsum.data_ptr(),
+         None if imgsum is None else imgsum.data_ptr())
+
+
+def pool2(src, out, avg=1, a=1.0, other=None, b=0.0):
+    op, ops = _mask(other)
+    call('pgk_pool2', src.ptr, src.ps, src.P, out.N, out.H, out.W, out.C, avg, a, op, ops, b, out.ptr, out.ps)
+    return out
+
+
+def mask_mul(src, out, ref=None, ups=0, scale=1.0):
+    rp, rps = _mask(ref)
+    call('pgk_mask_mul', src.ptr, src.ps, src.P, out.N, out.H, out.W, out.C, ups, scale, rp, rps, out.ptr, out.ps)
+    return out
+
+
+def pool_img(img, avg=1, scale=1.0):
+    n, c, h, w = img.shape
+    out = torch.empty((n, c, h // 2, w // 2), dtype=torch.float32, device=img.device)
+    call('pgk_pool_img', img.data_ptr(), n, c, h // 2, w // 2, avg, scale, out.data_ptr())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# prepared weights
+# ---------------------------------------------------------------------------------------------
+class ConvW(object):
+    """Kernel-side operands of one equalised-LR conv (network.py:8-41): c folded in, re-laid for the GEMMs."""
+
+    def __init__(self, mod, kind, cin, cout, ks, cin_stride=None, pos_hw=None, need_wb=True):
+        self.mod, self.kind, self.cin, self.cout, self.ks = mod, kind, cin, cout, ks
+        self.cin_stride = cin_stride if cin_stride is not None else cin
+        self.pos_hw, self.need_wb = pos_hw, need_wb
+        self.wf = self.wb = self.posT = self.bias16 = self.dwp = None
+        self.version = None
+
+    @property
+    def weight(self):
+        return self.mod.conv.weight
+
+    @property
+    def bias(self):
+        return self.mod.conv.bias
+
+    def ensure(self):
+        w = self.weight
+        ver = (w._version, w.data_ptr(), self.bias._version, self.mod.cf)
+        if ver == self.version:
+            return self
+        dev = w.device
+        n = self.cout * self.cin * self.ks * self.ks
+        if self.wf is None or self.wf.device != dev:
+            self.wf = torch.empty(n, dtype=torch.float32, device=dev)
+            self.wb = torch.empty(n, dtype=torch.float32, device=dev) if self.need_wb else None
+            if self.pos_hw is not None:
+                self.posT = torch.empty(self.pos_hw[0] * self.pos_hw[1] * self.cout, dtype=torch.float32, device=dev)
+        call('pgk_prep_weight', w.data_ptr(), self.mod.cf, self.kind, self.cin, self.cin_stride, self.cout, self.ks,
+             self.wf.data_ptr(), None if self.wb is None else self.wb.data_ptr())
+        if self.pos_hw is not None:
+            call('pgk_prep_posbias', w.data_ptr(), self.mod.cf, self.cin_stride, self.cin, self.cout, self.pos_hw[0],
+                 self.pos_hw[1], self.posT.data_ptr())
+        if self.kind == W_GFIRST:
+            self.bias16 = self.bias.detach().repeat(16)
+        self.version = ver
+        return self
+
+    def scratch(self):
+        if self.dwp is None or self.dwp.device != self.wf.device:
+            self.dwp = torch.empty_like(self.wf)
+        return self.dwp
+
+    def wgrad_into(self, grad, x, g, H, W, ups, groups, group_n):
+        """grad (PyTorch layout, fp32) <- c * sum_groups x (*) g."""
+        dwp = self.scratch()
+        dwp.zero_()
+        if self.kind == W_CONV:
+            wgrad(x, g, H, W, self.cin, self.cout, self.ks, ups, groups, group_n, dwp)
+        elif self.kind == W_GFIRST:   # x: (n,1,1,cin), g: (n,1,1,16*cout)
+            wgrad(x, g, 1, 1, self.cin, 16 * self.cout, 1, 0, groups, group_n, dwp)
+        else:                          # x: (n,1,1,16*cin), g: (n,1,1,cout)
+            wgrad(x, g, 1, 1, 16 * self.cin, self.cout, 1, 0, groups, group_n, dwp)
+        call('pgk_unprep_grad', dwp.data_ptr(), self.mod.cf, self.kind, self.cin, self.cin_stride, self.cout, self.ks,
+             grad.data_ptr(), 0)
+
+
+class GradSet(object):
+    """One flat fp32 buffer holding the gradients of the parameters that take part in a step (the active set
+    depends only on (depth, alpha < 1)); `views[param]` are the per-parameter views handed to autograd.  A single
+    flat buffer = a single NCCL all-reduce per optimizer step under data parallelism."""
+
+    def __init__(self, params, device):
+        self.params = list(params)
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.views = {}
+        o = 0
+        for p in self.params:
+            self.views[id(p)] = self.flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+
+    def __getitem__(self, p):
+        return self.views[id(p)]
+
+    def grads(self):
+        return [self.views[id(p)] for p in self.params]
+
+
+# ---------------------------------------------------------------------------------------------
+# Discriminator
+# ---------------------------------------------------------------------------------------------
+class DEngine(object):
+    """Forward / backward chains of Discriminator.forward (network.py:225-240) at the current (depth, alpha)."""
+
+    def __init__(self, D):
+        self.D = D
+        self._cw = {}
+
+    def blk(self, k):
+        """blocks[-k] (network.py:227,231,236)."""
+        return self.D.blocks[len(self.D.blocks) - k]
+
+    def cw(self, mod, kind=W_CONV):
+        key = id(mod)
+        if key not in self._cw:
+            w = mod.conv.weight
+            cout, cin_stride, ks = w.shape[0], w.shape[1], w.shape[2]
+            if kind == W_DLAST:
+                self._cw[key] = ConvW(mod, W_DLAST, cin_stride, cout, 4)
+            elif cin_stride % 8 == 1:   # the stddev layer: 512 real channels + 1 constant channel
+                self._cw[key] = ConvW(mod, W_CONV, cin_stride - 1, cout, ks, cin_stride=cin_stride, pos_hw=(4, 4))
+            else:
+                self._cw[key] = ConvW(mod, W_CONV, cin_stride, cout, ks)
+        return self._cw[key].ensure()
+
+    def active_params(self, depth, fade):
+        ps = []
+        top = self.blk(depth + 1)
+        ps += [top.fromRGB.conv.weight, top.fromRGB.conv.bias]
+        if fade:
+            lo = self.blk(depth)
+            ps += [lo.fromRGB.conv.weight, lo.fromRGB.conv.bias]
+        for k in range(depth + 1, 0, -1):
+            b = self.blk(k)
+            ps += [b.c1.conv.weight, b.c1.conv.bias, b.c2.conv.weight, b.c2.conv.bias]
+        ps += [self.D.linear.weight, self.D.linear.bias]
+        return ps
+
+    # -- forward ---------------------------------------------------------------------------
+    def forward(self, ximg, ngroups, group_n, P, slots=0):
+        """ximg: fp32 (B,C,r,r), B = ngroups*group_n, r = 4*2^depth.  Activations are allocated with B+slots
+        samples so that the v-chain can live next to them (D step).  Returns the tape."""
+        D = self.D
+        depth, alpha = int(D.depth), float(D.alpha)
+        fade = depth > 0 and alpha < 1.0
+        B = ximg.shape[0]
+        Bt = B + slots
+        dev = ximg.device
+        r = ximg.shape[-1]
+        assert B == ngroups * group_n and r == 4 * 2 ** depth, 'input resolution must match the current depth'
+        T = SimpleNamespace(depth=depth, alpha=alpha, fade=fade, B=B, Bt=Bt, P=P, ngroups=ngroups, group_n=group_n,
+                            ximg=ximg, blocks=[])
+        new = lambda res, c: PT.empty(Bt, res, res, c, P, dev)
+        top = self.blk(depth + 1)
+        ctop = top.fromRGB.conv.weight.shape[0]
+        T.t0 = new(r, ctop)
+        from_rgb(ximg, top.fromRGB, T.t0.sl(0, B))
+        if depth == 0:
+            hin = T.t0
+        else:
+            w1, w2 = self.cw(top.c1), self.cw(top.c2)
+            T.t1 = new(r, w1.cout)
+            conv(T.t0.sl(0, B), w1.wf, w1.cout, 3, T.t1.sl(0, B), bias=w1.bias, act=1)
+            T.t2 = new(r, w2.cout)
+            conv(T.t1.sl(0, B), w2.wf, w2.cout, 3, T.t2.sl(0, B), bias=w2.bias, act=1)
+            h = new(r // 2, w2.cout)
+            if fade:
+                T.xlow = pool_img(ximg)
+                T.f = new(r // 2, w2.cout)
+                from_rgb(T.xlow, self.blk(depth).fromRGB, T.f.sl(0, B))
+                pool2(T.t2.sl(0, B), h.sl(0, B), avg=1, a=alpha, other=T.f.sl(0, B), b=1.0 - alpha)
+            else:
+                pool2(T.t2.sl(0, B), h.sl(0, B), avg=1)
+            res = r // 2
+            for k in range(depth, 1, -1):
+                b = self.blk(k)
+                w1, w2 = self.cw(b.c1), self.cw(b.c2)
+                a_ = new(res, w1.cout)
+                conv(h.sl(0, B), w1.wf, w1.cout, 3, a_.sl(0, B), bias=w1.bias, act=1)
+                b_ = new(res, w2.cout)
+                conv(a_.sl(0, B), w2.wf, w2.cout, 3, b_.sl(0, B), bias=w2.bias, act=1)
+                hn = new(res // 2, w2.cout)
+                pool2(b_.sl(0, B), hn.sl(0, B), avg=1)
+                T.blocks.append(SimpleNamespace(mod=b, hin=h, a=a_, b=b_, res=res))
+                h, res = hn, res // 2
+            hin = h
+        T.hin = hin
+        last = self.blk(1)
+        wl1, wl2 = self.cw(last.c1), self.cw(last.c2, W_DLAST)
+        C = hin.C
+        T.stats = torch.empty(ngroups * 4, dtype=torch.float32, device=dev)
+        T.svec = torch.empty(B, dtype=torch.float32, device=dev)
+        call('pgk_stddev_stats', hin.ptr, hin.ps, P, ngroups, group_n * 16 * C, T.stats.data_ptr(), T.svec.data_ptr(),
+             group_n)
+        T.l1 = new(4, wl1.cout)
+        conv(hin.sl(0, B), wl1.wf, wl1.cout, 3, T.l1.sl(0, B), bias=wl1.bias, posT=wl1.posT, pos_s=T.svec, act=1)
+        T.l2 = PT.empty(Bt, 1, 1, wl2.cout, P, dev)
+        conv(T.l1.sl(0, B).view(1, 1, 16 * wl1.cout), wl2.wf, wl2.cout, 1, T.l2.sl(0, B), bias=wl2.bias, act=1)
+        T.scores = torch.empty(B, dtype=torch.float32, device=dev)
+        call('pgk_linear_fwd', T.l2.ptr, T.l2.ps, P, B, wl2.cout, D.linear.weight.data_ptr(), D.linear.bias.data_ptr(),
+             T.scores.data_ptr())
+        return T
+
+    # -- u-chain: head -> hin ---------------------------------------------------------------
+    def backward_head(self, T, seed, wseed, gs):
+        """Fills T.ua_l2, T.ua_l1, T.q and T.d_hin (gradient w.r.t. the last block's input, stddev term included)
+        for all B samples.  gs: GradSet receiving linear.weight/bias grads (None = no parameter grads)."""
+        D, B, P = self.D, T.B, T.P
+        dev = T.scores.device
+        last = self.blk(1)
+        wl1, wl2 = self.cw(last.c1), self.cw(last.c2, W_DLAST)
+        T.ua_l2 = PT.empty(T.Bt, 1, 1, wl2.cout, P, dev)
+        call('pgk_linear_bwd', T.l2.ptr, T.l2.ps, P, B, wl2.cout, D.linear.weight.data_ptr(), seed.data_ptr(),
+             None if wseed is None else wseed.data_ptr(), T.ua_l2.ptr, T.ua_l2.ps,
+             None if gs is None else gs[D.linear.weight].data_ptr(),
+             None if gs is None else gs[D.linear.bias].data_ptr())
+        T.ua_l1 = PT.empty(T.Bt, 4, 4, wl1.cout, P, dev)
+        conv(T.ua_l2.sl(0, B), wl2.wb, 16 * wl1.cout, 1, T.ua_l1.sl(0, B).view(1, 1, 16 * wl1.cout),
+             mask=T.l1.sl(0, B).view(1, 1, 16 * wl1.cout))
+        T.q = torch.empty(T.ngroups, dtype=torch.float32, device=dev)
+        call('pgk_group_dot_pos', T.ua_l1.ptr, T.ua_l1.ps, P, T.ngroups, T.group_n, 16, wl1.cout, wl1.posT.data_ptr(),
+             T.q.data_ptr())
+        C = T.hin.C
+        T.d_hin = PT.empty(B, 4, 4, C, P, dev)
+        conv(T.ua_l1.sl(0, B), wl1.wb, C, 3, T.d_hin)
+        call('pgk_stddev_bwd', T.hin.ptr, T.hin.ps, T.stats.data_ptr(), T.q.data_ptr(), P, T.ngroups,
+             T.group_n * 16 * C, T.d_hin.ptr, T.d_hin.ps)
+
+    # -- the part of the backward chain below the last block (shared by the u- and w-chains) -----
+    def backward_body(self, T, d_hin, n0, n1, g0):
+        """d_hin: gradient at the last block's input for tape samples [n0, n1).  Writes the pre-activation gradients
+        into the `ua` tensors of the tape at sample offset g0 (allocating them with Bt slots on first use)."""
+        P, dev, n = T.P, d_hin.t.device, n1 - n0
+        depth, alpha, fade = T.depth, T.alpha, T.fade
+        top = self.blk(depth + 1)
+
+        def ua_of(name, like):
+            if not hasattr(T, name):
+                setattr(T, name, PT.empty(T.Bt, like.H, like.W, like.C, P, dev))
+            return getattr(T, name).sl(g0, g0 + n)
+
+        if depth == 0:
+            ua_t0 = mask_mul(d_hin, ua_of('ua_t0', T.t0), ref=T.t0.sl(n0, n1))
+        else:
+            d_h = d_hin
+            for i, rec in enumerate(reversed(T.blocks)):
+                w1, w2 = self.cw(rec.mod.c1), self.cw(rec.mod.c2)
+                name = 'ua_blk%d' % (len(T.blocks) - 1 - i)
+                ua_b = mask_mul(d_h, ua_of(name + 'b', rec.b), ref=rec.b.sl(n0, n1), ups=1, scale=0.25)
+                ua_a = conv(ua_b, w2.wb, w1.cout, 3, ua_of(name + 'a', rec.a), mask=rec.a.sl(n0, n1))
+                d_h = conv(ua_a, w1.wb, w1.cin, 3, PT.empty(n, rec.res, rec.res, w1.cin, P, dev))
+            w1, w2 = self.cw(top.c1), self.cw(top.c2)
+            ua_t2 = mask_mul(d_h, ua_of('ua_t2', T.t2), ref=T.t2.sl(n0, n1), ups=1,
+                             scale=0.25 * (alpha if fade else 1.0))
+            ua_t1 = conv(ua_t2, w2.wb, w1.cout, 3, ua_of('ua_t1', T.t1), mask=T.t1.sl(n0, n1))
+            ua_t0 = conv(ua_t1, w1.wb, w1.cin, 3, ua_of('ua_t0', T.t0), mask=T.t0.sl(n0, n1))
+            if fade:
+                ua_f = mask_mul(d_h, ua_of('ua_f', T.f), ref=T.f.sl(n0, n1), scale=1.0 - alpha)
+
+    def image_grad(self, T, g0, n, dimg):
+        """dimg (fp32 n,C,r,r) <- gradient w.r.t. the input image from the ua tensors at sample offset g0
+        (fromRGB backwards, plus the avg-pooled low-res branch during a fade, network.py:230-233)."""
+        top = self.blk(T.depth + 1)
+        from_rgb_dgrad(T.ua_t0.sl(g0, g0 + n), top.fromRGB, dimg)
+        if T.fade:
+            from_rgb_dgrad(T.ua_f.sl(g0, g0 + n), self.blk(T.depth).fromRGB, dimg, scale=0.25, ups=1, accumulate=1)
+
+    # -- v-chain ------------------------------------------------------------------------------
+    def v_chain(self, T, v0, m0, vs):
+        """D's forward applied to v0 (fp32 n,C,r,r) with biases dropped and LeakyReLU replaced by the masks of the
+        tape samples [m0, m0+n) (the mixed samples).  The v tensors are written into slot `vs` of the tape's
+        activation buffers.  Returns the extra-channel value ev and w_h (the w-chain seed)."""
+        P, dev = T.P, v0.device
+        n = v0.shape[0]
+        depth, alpha, fade = T.depth, T.alpha, T.fade
+        top = self.blk(depth + 1)
+        m = lambda t: t.sl(m0, m0 + n)
+        v = lambda t: t.sl(vs, vs + n)
+        from_rgb(v0, top.fromRGB, v(T.t0), act=0, bias=False, mask=m(T.t0))
+        if depth == 0:
+            vh = v(T.t0)
+        else:
+            w1, w2 = self.cw(top.c1), self.cw(top.c2)
+            conv(v(T.t0), w1.wf, w1.cout, 3, v(T.t1), mask=m(T.t1))
+            conv(v(T.t1), w2.wf, w2.cout, 3, v(T.t2), mask=m(T.t2))
+            res = T.t2.H // 2
+            if fade:
+                T.v0low = pool_img(v0)
+                from_rgb(T.v0low, self.blk(depth).fromRGB, v(T.f), act=0, bias=False, mask=m(T.f))
+                dst = T.blocks[0].hin if T.blocks else T.hin
+                pool2(v(T.t2), v(dst), avg=1, a=alpha, other=v(T.f), b=1.0 - alpha)
+            else:
+                dst = T.blocks[0].hin if T.blocks else T.hin
+                pool2(v(T.t2), v(dst), avg=1)
+            for i, rec in enumerate(T.blocks):
+                w1, w2 = self.cw(rec.mod.c1), self.cw(rec.mod.c2)
+                conv(v(rec.hin), w1.wf, w1.cout, 3, v(rec.a), mask=m(rec.a))
+                conv(v(rec.a), w2.wf, w2.cout, 3, v(rec.b), mask=m(rec.b))
+                dst = T.blocks[i + 1].hin if i + 1 < len(T.blocks) else T.hin
+                pool2(v(rec.b), v(dst), avg=1)
+            vh = v(T.hin)
+        last = self.blk(1)
+        wl1, wl2 = self.cw(last.c1), self.cw(last.c2, W_DLAST)
+        C = T.hin.C
+        g = m0 // T.group_n
+        T.ev = torch.empty(n, dtype=torch.float32, device=dev)
+        T.w_h = PT.empty(n, 4, 4, C, P, dev)
+        scratch = torch.empty(2, dtype=torch.float32, device=dev)
+        hm = m(T.hin)
+        call('pgk_stddev_bwd2', hm.ptr, hm.ps, vh.ptr, vh.ps, T.stats[4 * g:].data_ptr(), T.q[g:].data_ptr(), P,
+             n * 16 * C, T.ev.data_ptr(), n, T.w_h.ptr, T.w_h.ps, scratch.data_ptr())
+        conv(vh, wl1.wf, wl1.cout, 3, v(T.l1), posT=wl1.posT, pos_s=T.ev, mask=m(T.l1))
+        conv(v(T.l1).view(1, 1, 16 * wl1.cout), wl2.wf, wl2.cout, 1, v(T.l2), mask=m(T.l2))
+
+    # -- parameter gradients -------------------------------------------------------------------
+    def param_grads(self, T, gs, groups, bias_goffs, head_groups, head_bias_goffs, img_pairs, ev_pair=None):
+        """groups: (x sample offset, ua sample offset) pairs of group_n samples each for the layers below the last
+        block; head_groups: the same for the last block's c1 / c2.  img_pairs: (image tensor, img_n0, ua offset)
+        triples for fromRGB.  ev_pair = (coef vector (n), ua offset) adds the v-chain's extra-channel term."""
+        n, P = T.group_n, T.P
+        depth, alpha, fade = T.depth, T.alpha, T.fade
+        top = self.blk(depth + 1)
+        C = T.ximg.shape[1]
+        r = T.ximg.shape[-1]
+
+        def rgb(mod, t_ua, res, pairs_):
+            gw, gb = gs[mod.conv.weight], gs[mod.conv.bias]
+            for img, img_n0, goff, with_bias in pairs_:
+                rgb_wgrad(img, img_n0, t_ua.sl(goff, goff + n), n, C, res, res, 0, mod.cf, 1.0, gw, 1, C,
+                          gb if with_bias else None, None)
+
+        rgb(top.fromRGB, T.ua_t0, r, img_pairs['top'])
+        if fade:
+            rgb(self.blk(depth).fromRGB, T.ua_f, r // 2, img_pairs['low'])
+
+        def conv_layer(mod, x, ua, res):
+            w = self.cw(mod)
+            w.wgrad_into(gs[mod.conv.weight], x, ua, res, res, 0, groups, n)
+            bias_grad(ua, res * res, w.cout, bias_goffs, n, gs[mod.conv.bias])
+
+        if depth > 0:
+            conv_layer(top.c1, T.t0, T.ua_t1, r)
+            conv_layer(top.c2, T.t1, T.ua_t2, r)
+            for i, rec in enumerate(T.blocks):
+                conv_layer(rec.mod.c1, rec.hin, getattr(T, 'ua_blk%da' % i), rec.res)
+                conv_layer(rec.mod.c2, rec.a, getattr(T, 'ua_blk%db' % i), rec.res)
+        last = self.blk(1)
+        wl1, wl2 = self.cw(last.c1), self.cw(last.c2, W_DLAST)
+        g1 = gs[last.c1.conv.weight]
+        wl1.wgrad_into(g1, T.hin, T.ua_l1, 4, 4, 0, head_groups, n)
+        # the constant (stddev) input channel of c1: coefficient s_g for the ordinary terms, e for the v-chain
+        for xo, go in head_groups:
+            if ev_pair is not None and go == ev_pair[1] and xo == ev_pair[2]:
+                coef = ev_pair[0]
+            else:
+                coef = T.svec[xo:xo + n]
+            u = T.ua_l1.sl(go, go + n)
+            call('pgk_posbias_wgrad', u.ptr, u.ps, P, n, 4, 4, wl1.cout, coef.data_ptr(), last.c1.cf, wl1.cin_stride,
+                 wl1.cin, g1.data_ptr())
+        bias_grad(T.ua_l1, 16, wl1.cout, head_bias_goffs, n, gs[last.c1.conv.bias])
+        wl2.wgrad_into(gs[last.c2.conv.weight], T.l1.view(1, 1, 16 * wl1.cout), T.ua_l2, 1, 1, 0, head_groups, n)
+        bias_grad(T.ua_l2, 1, wl2.cout, head_bias_goffs, n, gs[last.c2.conv.bias])
+
+
+# ---------------------------------------------------------------------------------------------
+# Generator
+# ---------------------------------------------------------------------------------------------
+class GEngine(object):
+    """Generator.forward (network.py:118-139) and its backward."""
+
+    def __init__(self, G):
+        self.G = G
+        self._cw = {}
+
+    def block(self, i):
+        return self.G.block0 if i == 0 else self.G.blocks[i - 1]
+
+    def cw(self, mod, kind=W_CONV):
+        key = id(mod)
+        if key not in self._cw:
+            w = mod.conv.weight
+            if kind == W_GFIRST:
+                self._cw[key] = ConvW(mod, W_GFIRST, w.shape[1], w.shape[0], 4, need_wb=False)
+            else:
+                self._cw[key] = ConvW(mod, W_CONV, w.shape[1], w.shape[0], w.shape[2])
+        return self._cw[key].ensure()
+
+    def active_params(self, depth, fade):
+        ps = []
+        for i in range(depth + 1):
+            b = self.block(i)
+            ps += [b.c1.conv.weight, b.c1.conv.bias, b.c2.conv.weight, b.c2.conv.bias]
+        ps += [self.block(depth).toRGB.conv.weight, self.block(depth).toRGB.conv.bias]
+        if fade:
+            ps += [self.block(depth - 1).toRGB.conv.weight, self.block(depth - 1).toRGB.conv.bias]
+        return ps
+
+    def _post(self, h, T, name):
+        """LeakyReLU has been applied by the conv; apply the pixel norm in place (network.py:37-40)."""
+        if self.G.pixelnorm:
+            r = torch.empty(h.N * h.H * h.W, dtype=torch.float32, device=h.t.device)
+            call('pgk_pixelnorm', h.ptr, h.ps, h.P, h.N * h.H * h.W, h.C, h.ptr, h.ps, r.data_ptr())
+            if T is not None:
+                setattr(T, 'r_' + name, r)
+
+    def forward(self, z, P, out=None, tape=False):
+        """z: fp32 (N, latent).  Returns (image fp32 N,C,r,r, tape or None); `out` lets the caller place the image
+        (e.g. straight into the fake slot of D's input batch)."""
+        G = self.G
+        depth, alpha = int(G.depth), float(G.alpha)
+        fade = depth > 0 and alpha < 1.0
+        n, dev = z.shape[0], z.device
+        T = SimpleNamespace(depth=depth, alpha=alpha, fade=fade, n=n, P=P, acts=[]) if tape else None
+        zn = PT.empty(n, 1, 1, z.shape[1], P, dev)
+        call('pgk_latent_norm', z.data_ptr(), n, z.shape[1], 1 if G.normalize_latents else 0, zn.ptr, P, zn.ps)
+        b0 = G.block0
+        w1, w2 = self.cw(b0.c1, W_GFIRST), self.cw(b0.c2)
+        h1 = PT.empty(n, 4, 4, w1.cout, P, dev)
+        conv(zn, w1.wf, 16 * w1.cout, 1, h1.view(1, 1, 16 * w1.cout), bias=w1.bias16, act=1)
+        self._post(h1, T, 'b0c1')
+        h2 = PT.empty(n, 4, 4, w2.cout, P, dev)
+        conv(h1, w2.wf, w2.cout, 3, h2, bias=w2.bias, act=1)
+        self._post(h2, T, 'b0c2')
+        if tape:
+            T.zn = zn
+            T.acts.append((None, h1, h2))
+        h, res = h2, 4
+        hprev = None
+        for i in range(1, depth + 1):
+            b = self.block(i)
+            w1, w2 = self.cw(b.c1), self.cw(b.c2)
+            res *= 2
+            u1 = PT.empty(n, res, res, w1.cout, P, dev)
+            conv(h, w1.wf, w1.cout, 3, u1, ups=1, bias=w1.bias, act=1)
+            self._post(u1, T, 'b%dc1' % i)
+            u2 = PT.empty(n, res, res, w2.cout, P, dev)
+            conv(u1, w2.wf, w2.cout, 3, u2, bias=w2.bias, act=1)
+            self._post(u2, T, 'b%dc2' % i)
+            if tape:
+                T.acts.append((h, u1, u2))
+            hprev, h = h, u2
+        C = self.block(depth).toRGB.conv.weight.shape[0]
+        img = out if out is not None else torch.empty((n, C, res, res), dtype=torch.float32, device=dev)
+        hi = self.block(depth).toRGB
+        if fade:
+            lo = self.block(depth - 1).toRGB
+            call('pgk_to_rgb', h.ptr, P, h.ps, n, res, res, h.C, hi.conv.weight.data_ptr(), hi.cf,
+                 hi.conv.bias.data_ptr(), alpha, hprev.ptr, hprev.ps, hprev.C, lo.conv.weight.data_ptr(), lo.cf,
+                 lo.conv.bias.data_ptr(), 1.0 - alpha, C, img.data_ptr())
+        else:
+            # depth 0 returns toRGB(h); depth > 0 with alpha >= 1 returns 0*(1-alpha) + ult*alpha (network.py:136-138)
+            a_hi = 1.0 if depth == 0 else alpha
+            call('pgk_to_rgb', h.ptr, P, h.ps, n, res, res, h.C, hi.conv.weight.data_ptr(), hi.cf,
+                 hi.conv.bias.data_ptr(), a_hi, None, 0, 0, None, 0.0, None, 0.0, C, img.data_ptr())
+        return img, T
+
+    def backward(self, T, dimg, gs):
+        """dimg: fp32 gradient w.r.t. the generated image; fills gs with every active parameter's gradient."""
+        G = self.G
+        depth, alpha, fade, n, P = T.depth, T.alpha, T.fade, T.n, T.P
+        dev = dimg.device
+        C = dimg.shape[1]
+        res = dimg.shape[-1]
+        groups = [(0, 0)]
+        hi = self.block(depth).toRGB
+        hprev, u1, u2 = T.acts[depth]
+        a_hi = 1.0 if depth == 0 else alpha
+        # toRGB (network.py:49,65) and the fade-in lerp (network.py:138)
+        rgb_wgrad(dimg, 0, u2, n, C, res, res, 0, hi.cf * a_hi, a_hi, gs[hi.conv.weight], u2.C, 1, None,
+                  gs[hi.conv.bias])
+        d = PT.empty(n, res, res, u2.C, P, dev)
+        call('pgk_to_rgb_dgrad', dimg.data_ptr(), n, C, res, res, u2.C, hi.conv.weight.data_ptr(), hi.cf, a_hi, 0,
+             d.ptr, P, d.ps)
+        d_lo = None
+        if fade:
+            lo = self.block(depth - 1).toRGB
+            rgb_wgrad(dimg, 0, hprev, n, C, res // 2, res // 2, 1, lo.cf * (1.0 - alpha), 1.0 - alpha,
+                      gs[lo.conv.weight], hprev.C, 1, None, gs[lo.conv.bias])
+            d_lo = PT.empty(n, res // 2, res // 2, hprev.C, P, dev)
+            call('pgk_to_rgb_dgrad', dimg.data_ptr(), n, C, res // 2, res // 2, hprev.C, lo.conv.weight.data_ptr(),
+                 lo.cf, 1.0 - alpha, 1, d_lo.ptr, P, d_lo.ps)
+        for i in range(depth, -1, -1):
+            b = self.block(i)
+            hprev, u1, u2 = T.acts[i]
+            w2 = self.cw(b.c2)
+            da2 = self._act_bwd(d, u2, T, 'b%dc2' % i)
+            w2.wgrad_into(gs[b.c2.conv.weight], u1, da2, res, res, 0, groups, n)
+            bias_grad(da2, res * res, w2.cout, [0], n, gs[b.c2.conv.bias])
+            d1 = conv(da2, w2.wb, w2.cin, 3, PT.empty(n, res, res, w2.cin, P, dev))
+            da1 = self._act_bwd(d1, u1, T, 'b%dc1' % i)
+            if i == 0:
+                w1 = self.cw(b.c1, W_GFIRST)
+                w1.wgrad_into(gs[b.c1.conv.weight], T.zn, da1.view(1, 1, 16 * w1.cout), 1, 1, 0, groups, n)
+                bias_grad(da1, 16, w1.cout, [0], n, gs[b.c1.conv.bias])
+                break
+            w1 = self.cw(b.c1)
+            w1.wgrad_into(gs[b.c1.conv.weight], hprev, da1, res, res, 1, groups, n)
+            bias_grad(da1, res * res, w1.cout, [0], n, gs[b.c1.conv.bias])
+            d_up = conv(da1, w1.wb, w1.cin, 3, PT.empty(n, res, res, w1.cin, P, dev))
+            res //= 2
+            d = PT.empty(n, res, res, w1.cin, P, dev)
+            if d_lo is not None:
+                pool2(d_up, d, avg=0, a=1.0, other=d_lo, b=1.0)
+                d_lo = None
+            else:
+                pool2(d_up, d, avg=0, a=1.0)
+
+    def _act_bwd(self, d, y, T, name):
+        """gradient w.r.t. the conv output given the gradient w.r.t. the (lrelu -> pixelnorm) output y."""
+        out = PT.empty(y.N, y.H, y.W, y.C, y.P, y.t.device)
+        if self.G.pixelnorm:
+            r = getattr(T, 'r_' + name)
+            call('pgk_pixelnorm_bwd', d.ptr, d.ps, y.ptr, y.ps, r.data_ptr(), y.P, y.N * y.H * y.W, y.C, out.ptr,
+                 out.ps)
+        else:
+            mask_mul(d, out, ref=y)
+        return out

@@ -1,0 +1,126 @@
+"""WGAN-GP losses with the reference's signatures (wgan_gp_loss.py:36-74), computed by the fused libpgk chains.
+
+Both functions run forward AND backward immediately (Trainer.train() always calls ``.backward()`` on the returned
+scalar, trainer.py:98,111) and return a scalar whose ``grad_fn`` deposits the pre-computed parameter gradients, so
+``loss.backward(); optimizer.step()`` behaves exactly as with the reference.
+
+Data parallel: when torch.distributed is initialised with world_size > 1, the flat gradient buffer of the step is
+all-reduced (ONE NCCL call per optimizer step) and averaged before it is handed to autograd.
+"""
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .engine import GradSet
+
+call = _lib.call
+
+# test hook: a (N,1) tensor used instead of drawing U(0,1) mixing factors (wgan_gp_loss.py:15-17)
+mixing_factors_override = None
+# last step's auxiliary outputs (per-sample gradient norms, penalty) for monitoring / tests
+last_aux = {}
+
+
+class _Deposit(torch.autograd.Function):
+    """value -> value, with d(value)/d(param_i) := grads_i (already computed by the kernels)."""
+
+    @staticmethod
+    def forward(ctx, value, n, *params_and_grads):
+        ctx.n = n
+        ctx.grads = params_and_grads[n:]
+        return value.clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        grads = torch._foreach_mul(list(ctx.grads), gout)
+        return (None, None) + tuple(grads) + (None,) * ctx.n
+
+
+def _deposit(value, gs):
+    return _Deposit.apply(value, len(gs.params), *(gs.params + gs.grads()))
+
+
+def _allreduce(gs):
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(gs.flat)
+        gs.flat.div_(dist.get_world_size())
+
+
+def wgan_gp_D_loss(D, G, real_images_in, fake_latents_in, iwass_lambda=10.0, iwass_epsilon=0.001, iwass_target=1.0,
+                   return_all=True):
+    D.zero_grad()
+    G.zero_grad()
+    real = D._input(real_images_in)
+    z = G._input(fake_latents_in)
+    n, C, r = real.shape[0], real.shape[1], real.shape[-1]
+    dev = real.device
+    P = D.planes
+    ed, eg = D.engine, G.engine
+    per = C * r * r
+
+    # input batch of D: [real | fake | mixed]
+    ximg = torch.empty((3 * n, C, r, r), dtype=torch.float32, device=dev)
+    ximg[:n].copy_(real)
+    eg.forward(z, G.planes, out=ximg[n:2 * n])                      # fake = G(z), no graph (wgan_gp_loss.py:51-52)
+    if mixing_factors_override is not None:
+        eps = mixing_factors_override.to(dev, torch.float32).contiguous().view(-1)
+    else:
+        eps = torch.rand(n, device=dev, dtype=torch.float32)
+    call('pgk_interpolate', ximg.data_ptr(), ximg[n:].data_ptr(), eps.data_ptr(), n, per, ximg[2 * n:].data_ptr())
+
+    T = ed.forward(ximg, 3, n, P, slots=n)
+    f32 = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+    d_real_loss, d_fake_loss, seed, wseed = f32(n), f32(n), f32(3 * n), f32(3 * n)
+    call('pgk_d_loss_seed', T.scores.data_ptr(), n, iwass_epsilon, d_real_loss.data_ptr(), d_fake_loss.data_ptr(),
+         seed.data_ptr(), wseed.data_ptr())
+
+    gs = GradSet(ed.active_params(T.depth, T.fade), dev)
+    # u-chain for all three groups at once; the mixed group's chain is the create_graph gradient of the penalty
+    ed.backward_head(T, seed, wseed, gs)
+    ed.backward_body(T, T.d_hin, 0, 3 * n, 0)
+    g_img = f32(n, C, r, r)
+    ed.image_grad(T, 2 * n, n, g_img)
+    norms, gp, v0, cost = f32(2 * n), f32(n), f32(n, C, r, r), f32(1)
+    call('pgk_gp_penalty', g_img.data_ptr(), n, per, iwass_lambda, iwass_target, d_real_loss.data_ptr(),
+         d_fake_loss.data_ptr(), norms.data_ptr(), gp.data_ptr(), v0.data_ptr(), cost.data_ptr())
+    # second order: v-chain (adjoint of the u-chain) and the w-chain entering through MinibatchStddev
+    ed.v_chain(T, v0, 2 * n, 3 * n)
+    v_l2 = T.l2.sl(3 * n, 4 * n)
+    call('pgk_colsum', v_l2.ptr, v_l2.ps, P, n, v_l2.C, 1.0, gs[D.linear.weight].data_ptr())
+    ed.backward_body(T, T.w_h, 2 * n, 3 * n, 3 * n)
+    top_pairs = [(ximg, 0, 0, True), (ximg, n, n, True), (ximg, 2 * n, 3 * n, True), (v0, 0, 2 * n, False)]
+    low_pairs = None
+    if T.fade:
+        low_pairs = [(T.xlow, 0, 0, True), (T.xlow, n, n, True), (T.xlow, 2 * n, 3 * n, True),
+                     (T.v0low, 0, 2 * n, False)]
+    ed.param_grads(T, gs,
+                   groups=[(0, 0), (n, n), (2 * n, 3 * n), (3 * n, 2 * n)], bias_goffs=[0, n, 3 * n],
+                   head_groups=[(0, 0), (n, n), (3 * n, 2 * n)], head_bias_goffs=[0, n],
+                   img_pairs=dict(top=top_pairs, low=low_pairs), ev_pair=(T.ev, 2 * n, 3 * n))
+    _allreduce(gs)
+    last_aux.update(grad_norms=norms[:n], gradient_penalty=gp, mixing=eps)
+    D_cost = _deposit(cost.view(()), gs)
+    if return_all:
+        return D_cost, d_real_loss.view(n, 1), d_fake_loss.view(n, 1)
+    return D_cost
+
+
+def wgan_gp_G_loss(G, D, fake_latents_in):
+    G.zero_grad()
+    z = G._input(fake_latents_in)
+    n, dev = z.shape[0], z.device
+    ed, eg = D.engine, G.engine
+    img, TG = eg.forward(z, G.planes, tape=True)
+    T = ed.forward(img, 1, n, D.planes)
+    seed = torch.empty(n, dtype=torch.float32, device=dev)
+    call('pgk_fill', seed.data_ptr(), n, -1.0 / n)
+    ed.backward_head(T, seed, None, None)
+    ed.backward_body(T, T.d_hin, 0, n, 0)
+    dimg = torch.empty_like(img)
+    ed.image_grad(T, 0, n, dimg)
+    gs = GradSet(eg.active_params(TG.depth, TG.fade), dev)
+    eg.backward(TG, dimg, gs)
+    cost = torch.empty(1, dtype=torch.float32, device=dev)
+    call('pgk_mean_scale', T.scores.data_ptr(), n, -1.0, cost.data_ptr())
+    _allreduce(gs)
+    return _deposit(cost.view(()), gs)

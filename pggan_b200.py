@@ -1,0 +1,11 @@
+"""Import alias: the package directory is named ``pggan-pytorch_b200`` (not a valid identifier), so
+``import pggan_b200`` resolves to it."""
+import importlib
+import os
+import sys
+
+_root = os.path.dirname(os.path.abspath(__file__))
+if _root not in sys.path:
+    sys.path.insert(0, _root)
+_pkg = importlib.import_module('pggan-pytorch_b200')
+sys.modules[__name__] = _pkg

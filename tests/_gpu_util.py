@@ -1,0 +1,39 @@
+"""Helpers for the -m gpu tests: build the CUDA-path modules from golden / oracle parameter dictionaries."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+
+import pggan_b200 as pg  # noqa: E402
+import pggan_oracle as O  # noqa: E402
+
+
+def load_params(module, params):
+    """params: reference state_dict names + '<conv>.c'."""
+    sd = {k: v for k, v in params.items() if not k.endswith('.c')}
+    module.load_state_dict(sd)
+    module.set_wscale({k[:-2]: float(v) for k, v in params.items() if k.endswith('.c')})
+
+
+def build_pair(g, precision='fp32', device='cuda'):
+    """g: a golden dict (tests/_util.load_step) or any dict with resolution/channels/fmap_base/fmap_max/latent/pg/pd."""
+    shape = (1000, g['channels'], g['resolution'], g['resolution'])
+    G = pg.Generator(shape, fmap_base=g['fmap_base'], fmap_max=g['fmap_max'], latent_size=g['latent'])
+    D = pg.Discriminator(shape, fmap_base=g['fmap_base'], fmap_max=g['fmap_max'])
+    load_params(G, g['pg'])
+    load_params(D, g['pd'])
+    G.cuda()
+    D.cuda()
+    G.precision = D.precision = precision
+    if 'depth' in g:
+        G.depth = D.depth = g['depth']
+        G.alpha = D.alpha = g['alpha']
+    return G, D
+
+
+def named_grads(module):
+    return {k: p.grad.detach().float().cpu() for k, p in module.named_parameters() if p.grad is not None}

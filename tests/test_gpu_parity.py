@@ -1,0 +1,167 @@
+"""-m gpu: the CUDA path (through the C ABI) against the golden vectors produced by the reference and against
+the oracle on fresh seeded inputs.  Tolerance (SURVEY.md 8c / BASELINE.json north_star): per-tensor
+||a-b||_2 / ||b||_2 <= 1e-3 in the fp32-faithful mode; bf16 mode tolerances are stated per test."""
+import pytest
+import torch
+
+from _util import STEP_CASES, load_step, load_trainer, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+@pytest.fixture(scope='module')
+def gpu():
+    from _gpu_util import O, build_pair, named_grads, pg
+    return dict(O=O, build_pair=build_pair, named_grads=named_grads, pg=pg)
+
+
+@pytest.mark.parametrize('case', STEP_CASES)
+def test_forward_golden(gpu, case):
+    g = load_step(case)
+    G, D = gpu['build_pair'](g)
+    assert rel_err(G(g['z1'].cuda()), g['fake']) < TOL
+    assert rel_err(D(g['real'].cuda()), g['d_real_scores']) < TOL
+    assert rel_err(D(g['fake'].cuda()), g['d_fake_scores']) < TOL
+
+
+@pytest.mark.parametrize('case', STEP_CASES)
+def test_d_step_golden(gpu, case):
+    g = load_step(case)
+    pg = gpu['pg']
+    G, D = gpu['build_pair'](g)
+    pg.wgan_gp_loss.mixing_factors_override = g['mixing']
+    try:
+        cost, rl, fl = pg.wgan_gp_D_loss(D, G, g['real'].cuda(), g['z1'].cuda())
+        cost.backward()
+    finally:
+        pg.wgan_gp_loss.mixing_factors_override = None
+    assert rel_err(cost, g['d_cost']) < TOL
+    assert rl.shape == (g['n'], 1) and rel_err(rl, g['d_real_loss']) < TOL
+    assert fl.shape == (g['n'], 1) and rel_err(fl, g['d_fake_loss']) < TOL
+    grads = gpu['named_grads'](D)
+    assert set(grads) == set(g['dgrad']), 'same parameters receive a gradient as in the reference'
+    for k, v in g['dgrad'].items():
+        assert rel_err(grads[k], v) < TOL, k
+    assert all(p.grad is None for p in G.parameters()), 'G gets no gradient in the D step'
+
+
+@pytest.mark.parametrize('case', STEP_CASES)
+def test_g_step_golden(gpu, case):
+    g = load_step(case)
+    pg = gpu['pg']
+    G, D = gpu['build_pair'](g)
+    cost = pg.wgan_gp_G_loss(G, D, g['z2'].cuda())
+    cost.backward()
+    assert rel_err(cost, g['g_cost']) < TOL
+    grads = gpu['named_grads'](G)
+    assert set(grads) == set(g['ggrad'])
+    for k, v in g['ggrad'].items():
+        assert rel_err(grads[k], v) < TOL, k
+
+
+def test_two_trainer_iterations_golden(gpu):
+    """Trainer.train() twice with torch Adam(betas=(0,.99)) -- parameters match the reference's after the same."""
+    g = load_trainer()
+    pg = gpu['pg']
+    g2 = dict(g, pg=g['G0'], pd=g['D0'])
+    G, D = gpu['build_pair'](g2)
+    G.depth = D.depth = g['depth']
+    G.alpha = D.alpha = g['alpha']
+    opt_g = torch.optim.Adam(G.parameters(), 1e-3, betas=(0.0, 0.99))
+    opt_d = torch.optim.Adam(D.parameters(), 1e-3, betas=(0.0, 0.99))
+    lats = iter(list(g['latents']))
+    t = pg.Trainer(D, G, pg.wgan_gp_D_loss, pg.wgan_gp_G_loss, opt_d, opt_g, None, iter(list(g['reals'])),
+                   lambda: next(lats))
+    for it in range(2):
+        pg.wgan_gp_loss.mixing_factors_override = g['mixing'][it]
+        t.train()
+    pg.wgan_gp_loss.mixing_factors_override = None
+    assert t.cur_nimg == g['cur_nimg']
+    sd_d = {k: v.detach().cpu() for k, v in D.state_dict().items()}
+    sd_g = {k: v.detach().cpu() for k, v in G.state_dict().items()}
+    # Adam with beta1=0 normalises every gradient to +-lr on the first steps, so parameter agreement is a
+    # sign-level check of all gradients: ||dp|| ~ lr*sqrt(numel).  Compare the UPDATE, not the parameter.
+    for k, v in g['D2'].items():
+        if k.endswith('.c'):
+            continue
+        upd_ref = v - g['D0'][k]
+        upd = sd_d[k] - g['D0'][k]
+        if float(upd_ref.norm()) > 0:
+            assert rel_err(upd, upd_ref) < 5e-2, k
+        else:
+            assert float(upd.norm()) == 0, k
+    for k, v in g['G2'].items():
+        if k.endswith('.c'):
+            continue
+        upd_ref = v - g['G0'][k]
+        upd = sd_g[k] - g['G0'][k]
+        if float(upd_ref.norm()) > 0:
+            assert rel_err(upd, upd_ref) < 5e-2, k
+        else:
+            assert float(upd.norm()) == 0, k
+
+
+@pytest.mark.parametrize('depth,alpha,n,ch', [(3, 0.5, 4, 3), (3, 1.0, 3, 3), (2, 0.0, 5, 1)])
+def test_step_vs_oracle_fresh_inputs(gpu, depth, alpha, n, ch):
+    """Larger channel counts / other depths than the golden files: CUDA path vs the oracle on the same seeded inputs."""
+    O, pg = gpu['O'], gpu['pg']
+    res, fb, fm, lat = 32, 512, 64, 64
+    pgp = O.make_generator_params(res, ch, fmap_base=fb, fmap_max=fm, latent_size=lat, seed=3)
+    pdp = O.make_discriminator_params(res, ch, fmap_base=fb, fmap_max=fm, seed=4)
+    g = dict(resolution=res, channels=ch, fmap_base=fb, fmap_max=fm, latent=lat, pg=pgp, pd=pdp, depth=depth,
+             alpha=alpha)
+    G, D = gpu['build_pair'](g)
+    gen = torch.Generator().manual_seed(99)
+    r = 4 * 2 ** depth
+    z1, z2 = torch.randn(n, lat, generator=gen), torch.randn(n, lat, generator=gen)
+    real = torch.randn(n, ch, r, r, generator=gen)
+    mix = torch.rand(n, 1, generator=gen)
+    nb = O.n_blocks_for(res)
+    cost_o, rl_o, fl_o, gd_o = O.d_step_grads(pdp, pgp, real, z1, mix, depth, alpha, nb)
+    gcost_o, gg_o = O.g_step_grads(pgp, pdp, z2, depth, alpha, nb)
+    pg.wgan_gp_loss.mixing_factors_override = mix
+    try:
+        cost, rl, fl = pg.wgan_gp_D_loss(D, G, real.cuda(), z1.cuda())
+        cost.backward()
+    finally:
+        pg.wgan_gp_loss.mixing_factors_override = None
+    assert rel_err(cost, cost_o) < TOL and rel_err(rl, rl_o) < TOL and rel_err(fl, fl_o) < TOL
+    grads = gpu['named_grads'](D)
+    assert set(grads) == set(gd_o)
+    for k, v in gd_o.items():
+        assert rel_err(grads[k], v) < TOL, k
+    gcost = pg.wgan_gp_G_loss(G, D, z2.cuda())
+    gcost.backward()
+    assert rel_err(gcost, gcost_o) < TOL
+    grads = gpu['named_grads'](G)
+    assert set(grads) == set(gg_o)
+    for k, v in gg_o.items():
+        assert rel_err(grads[k], v) < TOL, k
+
+
+def test_bf16_mode_close_to_oracle(gpu):
+    """bf16 mode (one plane): activations and gradients are rounded to 8 mantissa bits at every layer boundary, so
+    the tolerance against the fp32 oracle is 5e-2 on losses / outputs and 1e-1 on gradients."""
+    g = load_step('tiny3_d2_a03')
+    pg = gpu['pg']
+    G, D = gpu['build_pair'](g, precision='bf16')
+    assert rel_err(G(g['z1'].cuda()), g['fake']) < 5e-2
+    pg.wgan_gp_loss.mixing_factors_override = g['mixing']
+    try:
+        cost, rl, fl = pg.wgan_gp_D_loss(D, G, g['real'].cuda(), g['z1'].cuda())
+        cost.backward()
+    finally:
+        pg.wgan_gp_loss.mixing_factors_override = None
+    assert rel_err(cost, g['d_cost']) < 5e-2
+    grads = gpu['named_grads'](D)
+    for k, v in g['dgrad'].items():
+        assert rel_err(grads[k], v) < 1e-1, k
+
+
+def test_no_cpu_path(gpu):
+    g = load_step('tiny3_d0_a1')
+    G, D = gpu['build_pair'](g)
+    with pytest.raises(RuntimeError):
+        G.cpu()(g['z1'])

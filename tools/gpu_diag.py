@@ -1,0 +1,76 @@
+"""Prints a table of relative errors (CUDA path vs golden vectors / oracle) for every golden case.
+Development aid for the GPU box:  python tools/gpu_diag.py [case ...]"""
+import os
+import sys
+import traceback
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+from _util import STEP_CASES, load_step, rel_err  # noqa: E402
+from _gpu_util import O, build_pair, named_grads, pg  # noqa: E402
+
+
+def row(name, a, b):
+    e = rel_err(a, b)
+    flag = '' if e < 1e-3 else '   <-- FAIL'
+    print('  %-40s %.3e%s' % (name, e, flag))
+    return e
+
+
+def run_case(case, precision):
+    g = load_step(case)
+    print('== %s  precision=%s  depth=%d alpha=%g N=%d' % (case, precision, g['depth'], g['alpha'], g['n']))
+    G, D = build_pair(g, precision)
+    worst = 0.0
+    try:
+        fake = G(g['z1'].cuda())
+        worst = max(worst, row('G(z1)', fake, g['fake']))
+        worst = max(worst, row('D(real)', D(g['real'].cuda()), g['d_real_scores']))
+        worst = max(worst, row('D(fake_ref)', D(g['fake'].cuda()), g['d_fake_scores']))
+    except Exception:
+        traceback.print_exc()
+    try:
+        pg.wgan_gp_loss.mixing_factors_override = g['mixing']
+        cost, rl, fl = pg.wgan_gp_D_loss(D, G, g['real'].cuda(), g['z1'].cuda())
+        cost.backward()
+        torch.cuda.synchronize()
+        worst = max(worst, row('D_cost', cost, g['d_cost']))
+        worst = max(worst, row('D_real_loss', rl, g['d_real_loss']))
+        worst = max(worst, row('D_fake_loss', fl, g['d_fake_loss']))
+        grads = named_grads(D)
+        missing = set(g['dgrad']) - set(grads)
+        extra = set(grads) - set(g['dgrad'])
+        if missing or extra:
+            print('  grad set mismatch: missing %s extra %s' % (sorted(missing), sorted(extra)))
+        for k in sorted(g['dgrad']):
+            if k in grads:
+                worst = max(worst, row('dD/' + k, grads[k], g['dgrad'][k]))
+    except Exception:
+        traceback.print_exc()
+    try:
+        cost = pg.wgan_gp_G_loss(G, D, g['z2'].cuda())
+        cost.backward()
+        torch.cuda.synchronize()
+        worst = max(worst, row('G_cost', cost, g['g_cost']))
+        grads = named_grads(G)
+        missing = set(g['ggrad']) - set(grads)
+        extra = set(grads) - set(g['ggrad'])
+        if missing or extra:
+            print('  grad set mismatch: missing %s extra %s' % (sorted(missing), sorted(extra)))
+        for k in sorted(g['ggrad']):
+            if k in grads:
+                worst = max(worst, row('dG/' + k, grads[k], g['ggrad'][k]))
+    except Exception:
+        traceback.print_exc()
+    print('  worst: %.3e' % worst)
+    return worst
+
+
+if __name__ == '__main__':
+    cases = sys.argv[1:] or STEP_CASES
+    print(torch.cuda.get_device_name(0), torch.__version__)
+    for prec in ('fp32',):
+        for c in cases:
+            run_case(c, prec)
