@@ -1,0 +1,334 @@
+"""bench.py -- images/sec of one Progressive-GAN training iteration (D step with gradient penalty + G step +
+both Adam updates; reference trainer.py:85-115) on synthetic data.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One JSON line on rank 0.  `value` = whole-job images/sec with inputs resident in HBM; `e2e` = the same through
+Trainer.train() with pinned HOST inputs (H2D inside the timed region) and a D2H read of the loss every step;
+`roofline` = the dominant kernel family (pgk_conv: forward conv / data gradient) timed per launch with CUDA events on
+the launching stream; `cpu_baseline` = the CPU oracle (a port of the reference's step) on a bounded sample.
+`--impl reference` times that CPU path alone with all host threads.
+
+Configs (BASELINE.json): c1 depth 0 N16 fp32 | c2 depth 4 alpha .5 N128 fp32 (default: the metric's 1-GPU config) |
+c3 depth 6 N32 bf16 | c4 depth 8 alpha .3 N4 bf16 | c5 depth 5, 1-channel 128x128 model, N64 bf16.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    'c1': dict(depth=0, alpha=1.0, n=16, precision='fp32', res=1024, ch=3),
+    'c2': dict(depth=4, alpha=0.5, n=128, precision='fp32', res=1024, ch=3),
+    'c3': dict(depth=6, alpha=1.0, n=32, precision='bf16', res=1024, ch=3),
+    'c4': dict(depth=8, alpha=0.3, n=4, precision='bf16', res=1024, ch=3),
+    'c5': dict(depth=5, alpha=1.0, n=64, precision='bf16', res=128, ch=1),
+}
+DTYPE = {'fp32': 'bf16x3 (hi+lo bf16 planes, fp32 accumulate; fp32-faithful)', 'bf16': 'bf16 (fp32 accumulate)'}
+
+
+def nf(stage, fmap_base=4096, fmap_max=512):
+    return min(int(fmap_base / (2.0 ** stage)), fmap_max)
+
+
+def flops_per_image(depth, ch, fade):
+    """Algorithmic FLOPs of one iteration per image: 2*(14*MAC_D + 4*MAC_G) (SURVEY.md 8d / BASELINE.md 3), the
+    4x4 first-G / last-D convs counted as the dense GEMMs they are."""
+    mac_g = nf(0) * nf(1) * 16 + 16 * nf(1) * nf(1) * 9
+    mac_d = 16 * nf(1) * nf(1) * 9 + 16 * nf(1) * nf(0) + nf(0)
+    for j in range(1, depth + 1):
+        px = (4 * 2 ** j) ** 2
+        mac_g += px * 9 * (nf(j) * nf(j + 1) + nf(j + 1) * nf(j + 1))
+        mac_d += px * 9 * (nf(j + 1) * nf(j + 1) + nf(j + 1) * nf(j))
+    px = (4 * 2 ** depth) ** 2
+    mac_g += px * nf(depth + 1) * ch
+    mac_d += px * nf(depth + 1) * ch
+    if fade:
+        mac_g += (px // 4) * nf(depth) * ch
+        mac_d += (px // 4) * nf(depth) * ch
+    return 2.0 * (14 * mac_d + 4 * mac_g)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(',')])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [nm for i, nm in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == 'Active' for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx[0] if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+def cpu_reference_leg(cfg, steps, warmup, budget_s=25.0):
+    """The reference's algorithm for the step on the host CPU: oracle/pggan_oracle.py (a functional port of
+    network.py / wgan_gp_loss.py / trainer.py:85-115 on torch CPU ops, all host threads), D step + Adam + G step +
+    Adam, on a bounded sample (a small batch of the same depth / alpha / resolution).  Returns img/s."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import pggan_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    depth, alpha, ch, res = cfg['depth'], cfg['alpha'], cfg['ch'], cfg['res']
+    n = max(1, min(cfg['n'], {0: 16, 1: 16, 2: 8, 3: 4, 4: 2}.get(depth, 1)))
+    pgp = O.make_generator_params(res, ch, seed=1337)
+    pdp = O.make_discriminator_params(res, ch, seed=1338)
+    nb = O.n_blocks_for(res)
+    gen = torch.Generator().manual_seed(1337)
+    r = 4 * 2 ** depth
+    sd, sg = {}, {}
+
+    def step():
+        nonlocal pgp, pdp
+        real = torch.randn(n, ch, r, r, generator=gen)
+        z1, z2 = torch.randn(n, 512, generator=gen), torch.randn(n, 512, generator=gen)
+        mix = torch.rand(n, 1, generator=gen)
+        _, _, _, gd = O.d_step_grads(pdp, pgp, real, z1, mix, depth, alpha, nb)
+        pdp = O.adam_step(dict(pdp), gd, sd, 1e-3)
+        _, gg = O.g_step_grads(pgp, pdp, z2, depth, alpha, nb)
+        pgp = O.adam_step(dict(pgp), gg, sg, 1e-3)
+
+    t_first = time.perf_counter()
+    step()
+    t_first = time.perf_counter() - t_first
+    # bound the whole leg: as many warm-up / timed steps as requested, but never beyond the budget
+    k = max(1, min(steps, int(budget_s / max(t_first, 1e-3))))
+    w = max(0, min(warmup - 1, int(0.3 * budget_s / max(t_first, 1e-3))))
+    for _ in range(w):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(k):
+        step()
+    dt = (time.perf_counter() - t0) / k
+    return dict(value=n / dt, unit='images/sec', cores=cores, kind='port',
+                sample='%d timed iteration(s) of batch %d at depth %d (%dx%d), alpha %g, fp32, torch CPU ops on %d threads'
+                       % (k, n, depth, r, r, alpha, cores)), dt, k, w
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch of the config')
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.batch:
+        cfg['n'] = args.batch
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    depth, alpha, n, ch = cfg['depth'], cfg['alpha'], cfg['n'], cfg['ch']
+    fade = depth > 0 and alpha < 1.0
+    r = 4 * 2 ** depth
+    workload = {'workload': '%s: depth %d (%dx%d), alpha %g, batch %d/GPU, %s, D step (WGAN-GP) + G step + 2x Adam'
+                            % (args.config, depth, r, r, alpha, n, cfg['precision']),
+                'global_batch': n * max(world, 1), 'parallelism': 'dp%d' % max(world, 1),
+                'model_resolution': cfg['res'], 'channels': ch}
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        base, dt, k, w = cpu_reference_leg(cfg, args.steps, args.warmup, budget_s=60.0)
+        print(json.dumps({'impl': 'reference', 'metric': 'images/sec (G+D+GP step)', 'value': base['value'],
+                          'unit': 'images/sec', 'n_gpus': 0, 'steps': k, 'warmup': w, 'ms_per_step': dt * 1e3,
+                          'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                          'data': 'synthetic', 'config': workload, 'cpu_baseline': base,
+                          'e2e': {'value': base['value'], 'unit': 'images/sec', 'h2d_bytes_per_step': 0,
+                                  'd2h_bytes_per_step': 0}}))
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import pggan_b200 as pg
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU path)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    torch.manual_seed(1337)
+    np.random.seed(1337 + rank)
+    shape = (1000, ch, cfg['res'], cfg['res'])
+    G, D = pg.Generator(shape).to(dev), pg.Discriminator(shape).to(dev)
+    G.precision = D.precision = cfg['precision']
+    G.depth = D.depth = depth
+    G.alpha = D.alpha = alpha
+    opt_g = torch.optim.Adam(G.parameters(), 1e-3, betas=(0.0, 0.99))
+    opt_d = torch.optim.Adam(D.parameters(), 1e-3, betas=(0.0, 0.99))
+    gen = torch.Generator(device=dev).manual_seed(1337 + rank)
+    nbuf = 4
+    reals = [torch.randn(n, ch, r, r, device=dev, generator=gen) for _ in range(nbuf)]
+    lats = [torch.randn(n, 512, device=dev, generator=gen) for _ in range(2 * nbuf)]
+
+    def step_device(i):
+        """inputs already resident in HBM"""
+        cost, _, _ = pg.wgan_gp_D_loss(D, G, reals[i % nbuf], lats[(2 * i) % (2 * nbuf)])
+        cost.backward()
+        opt_d.step()
+        gcost = pg.wgan_gp_G_loss(G, D, lats[(2 * i + 1) % (2 * nbuf)])
+        gcost.backward()
+        opt_g.step()
+        return gcost
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        sync_all()
+        return float(ms)
+
+    for i in range(args.warmup):
+        step_device(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    pg._lib.reset_launch_count()
+    ms = timed(step_device, args.steps)
+    launches = pg._lib.launch_count()
+    clocks = sampler.finish() if rank == 0 else None
+    peak_mem = torch.cuda.max_memory_allocated(dev)
+
+    # ---- end to end: Trainer.train() fed from pinned host memory, loss read back every step ----------------
+    host_reals = [torch.randn(n, ch, r, r).pin_memory() for _ in range(2)]
+    host_lats = [torch.from_numpy(np.random.randn(n, 512).astype(np.float32)).pin_memory() for _ in range(4)]
+    cnt = {'r': 0, 'l': 0}
+
+    def next_real():
+        while True:
+            cnt['r'] += 1
+            yield host_reals[cnt['r'] % 2]
+
+    def next_lat():
+        cnt['l'] += 1
+        return host_lats[cnt['l'] % 4]
+
+    got = {}
+
+    class Grab(pg.Plugin):
+        def __init__(self):
+            super().__init__([(1, 'iteration')])
+
+        def register(self, trainer):
+            pass
+
+        def iteration(self, it, g_cost, d_cost, *rest):
+            got['v'] = (float(g_cost), float(d_cost))          # D2H read of both losses (2 x 4 bytes)
+
+    tr = pg.Trainer(D, G, pg.wgan_gp_D_loss, pg.wgan_gp_G_loss, opt_d, opt_g, None, next_real(), next_lat)
+    tr.register_plugin(Grab())
+    import heapq
+    for q in tr.plugin_queues.values():
+        heapq.heapify(q)
+    for _ in range(2):
+        tr.train()
+    ms_e2e = timed(lambda i: tr.train(), args.steps)
+    h2d = n * ch * r * r * 4 + 2 * n * 512 * 4
+    d2h = 8
+
+    # ---- roofline leg: per-launch CUDA-event timing of the conv kernels over the same steps -----------------
+    pg._lib.prof_reset()
+    pg._lib.prof_enable(True)
+    sync_all()
+    ksteps = min(args.steps, 3)
+    for i in range(ksteps):
+        step_device(i)
+    torch.cuda.synchronize()
+    pg._lib.prof_enable(False)
+    cf, cms, cn = pg._lib.prof_read(0)
+    wf_, wms, wn = pg._lib.prof_read(1)
+    pg._lib.prof_reset()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_tf = float(peaks.get('bf16_tflops_sustained', 1400.0))
+    peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'
+    step_s = ms / 1e3 / args.steps
+    value = n * world / step_s
+    fimg = flops_per_image(depth, ch, fade)
+    ach = cf / (cms * 1e-3) / 1e12 if cms > 0 else 0.0
+    out = {
+        'metric': 'images/sec (G+D+GP step)', 'value': value, 'unit': 'images/sec', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': step_s * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': DTYPE[cfg['precision']], 'data': 'synthetic',
+        'config': dict(workload, l2='no flush needed: activations written per step (%.1f GB peak allocated) >> 126 MB L2'
+                       % (peak_mem / 1e9)),
+        'e2e': {'value': n * world / (ms_e2e / 1e3 / args.steps), 'unit': 'images/sec', 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': d2h, 'api': 'Trainer.train() with pinned host reals/latents'},
+        'gpu_launches': launches,
+        'clocks': clocks,
+        'roofline': {'bound': 'tensor', 'kernel': 'pgk_conv (3x3/1x1 implicit-GEMM forward + data gradient)',
+                     'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': None,
+                     'peak_source': peak_src, 'launches_timed': cn, 'kernel_ms_per_step': cms / ksteps,
+                     'wgrad': {'achieved': wf_ / (wms * 1e-3) / 1e12 if wms > 0 else 0.0, 'launches_timed': wn,
+                               'kernel_ms_per_step': wms / ksteps},
+                     'step_algorithmic': {'gflop_per_image': fimg / 1e9,
+                                          'achieved': fimg * n / step_s / 1e12,
+                                          'frac': fimg * n / step_s / 1e12 / peak_tf}},
+    }
+    if not args.no_cpu_baseline:
+        base, _, _, _ = cpu_reference_leg(cfg, 3, 1, budget_s=20.0)
+        out['cpu_baseline'] = base
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -13,11 +13,13 @@
  *  - return value 0 = ok; non-zero = error code, text via pgk_last_error().
  *  - all pointers are DEVICE pointers owned by the caller for the duration of
  *    the call.
- *  - "planes" tensors are the internal activation format: P planes (1 or 2) of
- *    bfloat16 in N,H,W,C order (channels innermost, C % 8 == 0).  value =
- *    plane0 (+ plane1).  P = 2 is the fp32-faithful mode (hi + lo split keeps
- *    ~16 mantissa bits and feeds the 3-product tensor-core scheme), P = 1 is
- *    the bf16 mode.  `*_ps` arguments are the plane stride in ELEMENTS.
+ *  - "planes" tensors are the internal activation format: P planes (1, 2 or 3)
+ *    of bfloat16 in N,H,W,C order (channels innermost, C % 8 == 0).  value =
+ *    plane0 + plane1 + plane2, plane k = bf16(value - earlier planes).  P = 3 is
+ *    the fp32-faithful mode (24 mantissa bits; the tensor-core kernels form the
+ *    six products of planes i, j with i + j <= 2), P = 2 keeps 16 bits (three
+ *    products), P = 1 is the bf16 mode.  `*_ps` arguments are the plane stride
+ *    in ELEMENTS.
  *  - "image" tensors are the reference's own surface format: fp32, N,C,H,W.
  *  - LeakyReLU slope is 0.2 (network.py:27); lrelu'(v) = v > 0 ? 1 : 0.2.
  */
@@ -47,6 +49,15 @@ int pgk_arch_check(int device);
 /* number of kernels launched by this library since load / since the last reset (bench's gpu_launches). */
 long long pgk_launch_count(void);
 void pgk_reset_launch_count(void);
+/* per-launch device timing of the GEMM-shaped kernels (bench.py's roofline): while enabled, pgk_conv / pgk_wgrad
+ * bracket their launch with CUDA events on `stream`.  pgk_prof_read synchronises on the recorded events and returns
+ * the summed algorithmic FLOPs (2*M*N*K of each launch), the summed device milliseconds and the launch count of one
+ * kernel family; pgk_prof_reset drops the records. */
+#define PGK_PROF_CONV 0  /* forward conv / data gradient (pgk_conv) */
+#define PGK_PROF_WGRAD 1 /* weight gradient (pgk_wgrad)             */
+void pgk_prof_enable(int on);
+int pgk_prof_read(int family, double* flops, double* ms, long long* launches);
+void pgk_prof_reset(void);
 
 /* ---- equalised-LR weights: fold c into the weight, re-lay for the kernels --------------
  * replaces `h = x * self.c` (network.py:33) + the cuDNN filter transform.

@@ -74,6 +74,12 @@ def load():
     lib.pgk_arch_check.restype = c_int
     lib.pgk_launch_count.restype = c_longlong
     lib.pgk_reset_launch_count.restype = None
+    lib.pgk_prof_enable.argtypes = [c_int]
+    lib.pgk_prof_enable.restype = None
+    lib.pgk_prof_read.argtypes = [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                  ctypes.POINTER(c_longlong)]
+    lib.pgk_prof_read.restype = c_int
+    lib.pgk_prof_reset.restype = None
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = list(args) + [c_void_p]
@@ -83,8 +89,8 @@ def load():
 
 
 def exported_symbols():
-    return ['pgk_version', 'pgk_last_error', 'pgk_arch_check', 'pgk_launch_count', 'pgk_reset_launch_count'] + \
-        list(SIGNATURES)
+    return ['pgk_version', 'pgk_last_error', 'pgk_arch_check', 'pgk_launch_count', 'pgk_reset_launch_count',
+            'pgk_prof_enable', 'pgk_prof_read', 'pgk_prof_reset'] + list(SIGNATURES)
 
 
 _checked_devices = set()
@@ -122,3 +128,21 @@ def launch_count():
 
 def reset_launch_count():
     load().pgk_reset_launch_count()
+
+
+def prof_enable(on):
+    load().pgk_prof_enable(1 if on else 0)
+
+
+def prof_read(family):
+    """(algorithmic FLOPs, device ms, launches) of one kernel family since the last prof_reset()."""
+    lib = load()
+    f, t, n = ctypes.c_double(), ctypes.c_double(), c_longlong()
+    rc = lib.pgk_prof_read(family, ctypes.byref(f), ctypes.byref(t), ctypes.byref(n))
+    if rc != 0:
+        raise PgkError('pgk_prof_read failed: %s' % lib.pgk_last_error().decode())
+    return f.value, t.value, n.value
+
+
+def prof_reset():
+    load().pgk_prof_reset()

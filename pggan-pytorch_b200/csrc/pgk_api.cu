@@ -1,7 +1,10 @@
-// pgk_api.cu -- shape dispatch for the two GEMM-shaped entry points.  The tcgen05 path (pgk_conv_tc.cu) serves
-// the tensor-core friendly layers; everything else runs on the CUDA-core implicit GEMM.  Both are this library's
-// own sm_100a kernels -- there is no library or CPU fallback.
+// pgk_api.cu -- shape dispatch for the two GEMM-shaped entry points, and the per-launch timing hooks bench.py uses
+// for the roofline.  The tcgen05 path (pgk_conv_tc.cu) serves the tensor-core friendly layers; everything else runs
+// on the CUDA-core implicit GEMM.  Both are this library's own sm_100a kernels -- there is no library or CPU
+// fallback.
 #include <stdlib.h>
+
+#include <vector>
 
 #include "pgk_common.cuh"
 
@@ -13,10 +16,70 @@ extern "C" int pgk_wgrad_simt(const void* x, long long x_ps, const void* g, long
                               int Cin, int Cout, int KS, int ups, int ngroups, int group_n, const int* xoff,
                               const int* goff, float* dwp, pgk_stream_t stream);
 
+// ---- per-launch timing (off by default; bench.py's roofline leg turns it on) --------------------------------
+namespace {
+struct ProfRec {
+    cudaEvent_t e0, e1;
+    double flops;
+    int family;
+};
+bool g_prof = false;
+std::vector<ProfRec> g_recs;
+
+struct ProfScope {
+    bool on;
+    cudaStream_t s;
+    ProfRec r;
+    ProfScope(int family, double flops, pgk_stream_t stream) : on(g_prof), s((cudaStream_t)stream) {
+        if (!on) return;
+        r.family = family, r.flops = flops;
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e0, s);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(r.e1, s);
+        g_recs.push_back(r);
+    }
+};
+}  // namespace
+
+extern "C" void pgk_prof_enable(int on) { g_prof = on != 0; }
+
+extern "C" int pgk_prof_read(int family, double* flops, double* ms, long long* launches) {
+    double f = 0.0, t = 0.0;
+    long long n = 0;
+    for (auto& r : g_recs) {
+        if (r.family != family) continue;
+        cudaError_t e = cudaEventSynchronize(r.e1);
+        float dt = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&dt, r.e0, r.e1);
+        if (e != cudaSuccess) {
+            pgk_set_error("pgk_prof_read: %s", cudaGetErrorString(e));
+            return PGK_ERR_CUDA;
+        }
+        f += r.flops, t += dt, ++n;
+    }
+    if (flops) *flops = f;
+    if (ms) *ms = t;
+    if (launches) *launches = n;
+    return PGK_OK;
+}
+
+extern "C" void pgk_prof_reset(void) {
+    for (auto& r : g_recs) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    g_recs.clear();
+}
+
 extern "C" int pgk_conv(const void* x, int P, long long x_ps, int N, int H, int W, int Cin, int Cout, int KS, int ups,
                         const float* wf, const float* bias, const float* posT, const float* pos_s, int act,
                         const void* mask_ref, long long mask_ps, float out_scale, void* out, long long out_ps,
                         pgk_stream_t stream) {
+    ProfScope prof(PGK_PROF_CONV, 2.0 * N * H * W * (double)Cout * KS * KS * Cin, stream);
     return pgk_conv_simt(x, P, x_ps, N, H, W, Cin, Cout, KS, ups, wf, bias, posT, pos_s, act, mask_ref, mask_ps,
                          out_scale, out, out_ps, stream);
 }
@@ -24,5 +87,6 @@ extern "C" int pgk_conv(const void* x, int P, long long x_ps, int N, int H, int 
 extern "C" int pgk_wgrad(const void* x, long long x_ps, const void* g, long long g_ps, int P, int H, int W, int Cin,
                          int Cout, int KS, int ups, int ngroups, int group_n, const int* xoff, const int* goff,
                          float* dwp, pgk_stream_t stream) {
+    ProfScope prof(PGK_PROF_WGRAD, 2.0 * ngroups * group_n * H * W * (double)Cout * KS * KS * Cin, stream);
     return pgk_wgrad_simt(x, x_ps, g, g_ps, P, H, W, Cin, Cout, KS, ups, ngroups, group_n, xoff, goff, dwp, stream);
 }

@@ -32,7 +32,7 @@ extern "C" void pgk_count_launch(int n);
 
 typedef __nv_bfloat16 bf16;
 
-// A planes tensor: value = p[i] (+ p[i + ps] when P == 2)
+// A planes tensor: value = sum over k < P of p[i + k * ps]   (P = 1, 2 or 3)
 struct Planes {
     bf16* p;
     long long ps;
@@ -59,23 +59,53 @@ __device__ __forceinline__ void unpack8(const uint4& q, float* f) {
     f[7] = __uint_as_float(q.w & 0xffff0000u);
 }
 
-// load 8 consecutive channels starting at element index i (i % 8 == 0)
+// load 8 consecutive channels starting at element index i (i % 8 == 0); planes are summed smallest first
 __device__ __forceinline__ void ld8(const Planes& t, long long i, float* f) {
     uint4 q = __ldg(reinterpret_cast<const uint4*>(t.p + i));
-    unpack8(q, f);
-    if (t.P == 2) {
-        float g[8];
-        uint4 r = __ldg(reinterpret_cast<const uint4*>(t.p + t.ps + i));
-        unpack8(r, g);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] += g[j];
+    if (t.P == 1) {
+        unpack8(q, f);
+        return;
     }
+    float h[8], g[8];
+    unpack8(q, h);
+    uint4 r = __ldg(reinterpret_cast<const uint4*>(t.p + t.ps + i));
+    unpack8(r, g);
+    if (t.P == 3) {
+        float e[8];
+        uint4 u = __ldg(reinterpret_cast<const uint4*>(t.p + 2 * t.ps + i));
+        unpack8(u, e);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] += e[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = h[j] + g[j];
+}
+
+__device__ __forceinline__ void ld4(const Planes& t, long long i, float* f) {
+    uint2 q = __ldg(reinterpret_cast<const uint2*>(t.p + i));
+    f[0] = __uint_as_float(q.x << 16);
+    f[1] = __uint_as_float(q.x & 0xffff0000u);
+    f[2] = __uint_as_float(q.y << 16);
+    f[3] = __uint_as_float(q.y & 0xffff0000u);
+    if (t.P == 1) return;
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int pl = t.P - 1; pl >= 1; --pl) {
+        uint2 r = __ldg(reinterpret_cast<const uint2*>(t.p + pl * t.ps + i));
+        g[0] += __uint_as_float(r.x << 16);
+        g[1] += __uint_as_float(r.x & 0xffff0000u);
+        g[2] += __uint_as_float(r.y << 16);
+        g[3] += __uint_as_float(r.y & 0xffff0000u);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) f[j] += g[j];
 }
 
 __device__ __forceinline__ float ld1(const Planes& t, long long i) {
     float v = __bfloat162float(t.p[i]);
-    if (t.P == 2) v += __bfloat162float(t.p[t.ps + i]);
-    return v;
+    if (t.P == 1) return v;
+    float lo = __bfloat162float(t.p[t.ps + i]);
+    if (t.P == 3) lo += __bfloat162float(t.p[2 * t.ps + i]);
+    return v + lo;
 }
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -83,45 +113,49 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// split v into hi (bf16 RN) and lo = bf16(v - hi)
+// split v into P bf16 planes: plane k = bf16_rn(v - sum of the earlier planes)   (8 / 16 / 24 mantissa bits)
 __device__ __forceinline__ void split_store8(const Planes& t, long long i, const float* f) {
-    uint4 q;
-    q.x = pack2(f[0], f[1]);
-    q.y = pack2(f[2], f[3]);
-    q.z = pack2(f[4], f[5]);
-    q.w = pack2(f[6], f[7]);
-    *reinterpret_cast<uint4*>(t.p + i) = q;
-    if (t.P == 2) {
-        float h[8];
-        unpack8(q, h);
-        uint4 r;
-        r.x = pack2(f[0] - h[0], f[1] - h[1]);
-        r.y = pack2(f[2] - h[2], f[3] - h[3]);
-        r.z = pack2(f[4] - h[4], f[5] - h[5]);
-        r.w = pack2(f[6] - h[6], f[7] - h[7]);
-        *reinterpret_cast<uint4*>(t.p + t.ps + i) = r;
+    float res[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) res[j] = f[j];
+    for (int pl = 0; pl < t.P; ++pl) {
+        uint4 q;
+        q.x = pack2(res[0], res[1]);
+        q.y = pack2(res[2], res[3]);
+        q.z = pack2(res[4], res[5]);
+        q.w = pack2(res[6], res[7]);
+        *reinterpret_cast<uint4*>(t.p + pl * t.ps + i) = q;
+        if (pl + 1 < t.P) {
+            float h[8];
+            unpack8(q, h);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) res[j] -= h[j];
+        }
     }
 }
 
 __device__ __forceinline__ void split_store4(const Planes& t, long long i, const float* f) {
-    uint2 q;
-    q.x = pack2(f[0], f[1]);
-    q.y = pack2(f[2], f[3]);
-    *reinterpret_cast<uint2*>(t.p + i) = q;
-    if (t.P == 2) {
-        float h0 = __uint_as_float(q.x << 16), h1 = __uint_as_float(q.x & 0xffff0000u);
-        float h2 = __uint_as_float(q.y << 16), h3 = __uint_as_float(q.y & 0xffff0000u);
-        uint2 r;
-        r.x = pack2(f[0] - h0, f[1] - h1);
-        r.y = pack2(f[2] - h2, f[3] - h3);
-        *reinterpret_cast<uint2*>(t.p + t.ps + i) = r;
+    float res[4] = {f[0], f[1], f[2], f[3]};
+    for (int pl = 0; pl < t.P; ++pl) {
+        uint2 q;
+        q.x = pack2(res[0], res[1]);
+        q.y = pack2(res[2], res[3]);
+        *reinterpret_cast<uint2*>(t.p + pl * t.ps + i) = q;
+        if (pl + 1 < t.P) {
+            res[0] -= __uint_as_float(q.x << 16);
+            res[1] -= __uint_as_float(q.x & 0xffff0000u);
+            res[2] -= __uint_as_float(q.y << 16);
+            res[3] -= __uint_as_float(q.y & 0xffff0000u);
+        }
     }
 }
 
 __device__ __forceinline__ void st1(const Planes& t, long long i, float v) {
-    bf16 h = __float2bfloat16_rn(v);
-    t.p[i] = h;
-    if (t.P == 2) t.p[t.ps + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    for (int pl = 0; pl < t.P; ++pl) {
+        bf16 h = __float2bfloat16_rn(v);
+        t.p[pl * t.ps + i] = h;
+        v -= __bfloat162float(h);
+    }
 }
 
 __device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : PGK_LRELU * v; }

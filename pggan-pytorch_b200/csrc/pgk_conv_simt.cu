@@ -28,21 +28,6 @@ struct ConvArgs {
     int M, K;
 };
 
-__device__ __forceinline__ void ld4(const Planes& t, long long i, float* f) {
-    uint2 q = __ldg(reinterpret_cast<const uint2*>(t.p + i));
-    f[0] = __uint_as_float(q.x << 16);
-    f[1] = __uint_as_float(q.x & 0xffff0000u);
-    f[2] = __uint_as_float(q.y << 16);
-    f[3] = __uint_as_float(q.y & 0xffff0000u);
-    if (t.P == 2) {
-        uint2 r = __ldg(reinterpret_cast<const uint2*>(t.p + t.ps + i));
-        f[0] += __uint_as_float(r.x << 16);
-        f[1] += __uint_as_float(r.x & 0xffff0000u);
-        f[2] += __uint_as_float(r.y << 16);
-        f[3] += __uint_as_float(r.y & 0xffff0000u);
-    }
-}
-
 __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
     __shared__ __align__(16) float As[2][BK][BM + 4];
     __shared__ __align__(16) float Bs[2][BK][BN];
@@ -362,7 +347,7 @@ extern "C" int pgk_conv_simt(const void* x, int P, long long x_ps, int N, int H,
                              int ups, const float* wf, const float* bias, const float* posT, const float* pos_s,
                              int act, const void* mask_ref, long long mask_ps, float out_scale, void* out,
                              long long out_ps, pgk_stream_t stream) {
-    PGK_REQUIRE(P == 1 || P == 2, "pgk_conv: P must be 1 or 2 (got %d)", P);
+    PGK_REQUIRE(P >= 1 && P <= 3, "pgk_conv: P must be 1, 2 or 3 (got %d)", P);
     PGK_REQUIRE(KS == 1 || KS == 3, "pgk_conv: KS must be 1 or 3 (got %d)", KS);
     PGK_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0, "pgk_conv: channels must be multiples of 8 (Cin %d Cout %d)", Cin, Cout);
     PGK_REQUIRE(!ups || (H % 2 == 0 && W % 2 == 0), "pgk_conv: ups needs even H, W");
@@ -389,7 +374,7 @@ extern "C" int pgk_conv_simt(const void* x, int P, long long x_ps, int N, int H,
 extern "C" int pgk_wgrad_simt(const void* x, long long x_ps, const void* g, long long g_ps, int P, int H, int W,
                               int Cin, int Cout, int KS, int ups, int ngroups, int group_n, const int* xoff,
                               const int* goff, float* dwp, pgk_stream_t stream) {
-    PGK_REQUIRE(P == 1 || P == 2, "pgk_wgrad: P must be 1 or 2");
+    PGK_REQUIRE(P >= 1 && P <= 3, "pgk_wgrad: P must be 1, 2 or 3");
     PGK_REQUIRE(KS == 1 || KS == 3, "pgk_wgrad: KS must be 1 or 3");
     PGK_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0, "pgk_wgrad: channels must be multiples of 8");
     PGK_REQUIRE(ngroups >= 1 && ngroups <= 4 && group_n > 0, "pgk_wgrad: 1..4 groups");
@@ -424,7 +409,7 @@ extern "C" int pgk_wgrad_simt(const void* x, long long x_ps, const void* g, long
 
 extern "C" int pgk_bias_grad(const void* g, long long g_ps, int P, int HW, int Cout, int ngroups, int group_n,
                              const int* goff, float scale, float* db, int accumulate, pgk_stream_t stream) {
-    PGK_REQUIRE(P == 1 || P == 2, "pgk_bias_grad: P must be 1 or 2");
+    PGK_REQUIRE(P >= 1 && P <= 3, "pgk_bias_grad: P must be 1, 2 or 3");
     PGK_REQUIRE(Cout % 8 == 0 && Cout / 8 <= 256, "pgk_bias_grad: Cout must be a multiple of 8 and <= 2048");
     PGK_REQUIRE(ngroups >= 1 && ngroups <= 4 && group_n > 0, "pgk_bias_grad: 1..4 groups");
     if (!accumulate) {

@@ -13,7 +13,10 @@ from torch import nn
 
 from . import _lib
 
-PRECISIONS = {'fp32': 2, 'bf16': 1}   # number of bf16 planes per activation tensor (see include/pgk.h)
+# number of bf16 planes per activation / weight tensor (see include/pgk.h).  'fp32' keeps 24 mantissa bits (three
+# planes, six tensor-core products): LeakyReLU masks make the gradients discontinuous in the forward values, so the
+# reference's fp32 results are only reproduced to 1e-3 when the forward pass carries (almost) fp32 precision.
+PRECISIONS = {'fp32': 3, 'bf16x2': 2, 'bf16': 1}
 
 
 def nf_fn(fmap_base, fmap_decay, fmap_max):

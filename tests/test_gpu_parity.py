@@ -113,14 +113,23 @@ def test_step_vs_oracle_fresh_inputs(gpu, depth, alpha, n, ch):
     g = dict(resolution=res, channels=ch, fmap_base=fb, fmap_max=fm, latent=lat, pg=pgp, pd=pdp, depth=depth,
              alpha=alpha)
     G, D = gpu['build_pair'](g)
-    gen = torch.Generator().manual_seed(99)
     r = 4 * 2 ** depth
-    z1, z2 = torch.randn(n, lat, generator=gen), torch.randn(n, lat, generator=gen)
-    real = torch.randn(n, ch, r, r, generator=gen)
-    mix = torch.rand(n, 1, generator=gen)
     nb = O.n_blocks_for(res)
-    cost_o, rl_o, fl_o, gd_o = O.d_step_grads(pdp, pgp, real, z1, mix, depth, alpha, nb)
-    gcost_o, gg_o = O.g_step_grads(pgp, pdp, z2, depth, alpha, nb)
+    from _gpu_util import relu_margin
+    for seed in range(99, 140):   # first seed whose LeakyReLU margins are clear of float noise (see relu_margin)
+        gen = torch.Generator().manual_seed(seed)
+        z1, z2 = torch.randn(n, lat, generator=gen), torch.randn(n, lat, generator=gen)
+        real = torch.randn(n, ch, r, r, generator=gen)
+        mix = torch.rand(n, 1, generator=gen)
+        res_o = {}
+
+        def run_oracle():
+            res_o['d'] = O.d_step_grads(pdp, pgp, real, z1, mix, depth, alpha, nb)
+            res_o['g'] = O.g_step_grads(pgp, pdp, z2, depth, alpha, nb)
+        if relu_margin(run_oracle) > 2e-5:
+            break
+    cost_o, rl_o, fl_o, gd_o = res_o['d']
+    gcost_o, gg_o = res_o['g']
     pg.wgan_gp_loss.mixing_factors_override = mix
     try:
         cost, rl, fl = pg.wgan_gp_D_loss(D, G, real.cuda(), z1.cuda())

@@ -19,8 +19,34 @@ def row(name, a, b):
     return e
 
 
+def oracle_case(spec):
+    """'o:depth,alpha,n,ch[,res,fmap_base,fmap_max,latent]' -> a golden-like dict computed by the oracle (fp64 when
+    the spec ends in ',64')."""
+    v = spec[2:].split(',')
+    depth, alpha, n, ch = int(v[0]), float(v[1]), int(v[2]), int(v[3])
+    res, fb, fm, lat = (int(x) for x in (v[4:8] if len(v) >= 8 else (32, 512, 64, 64)))
+    dt = torch.float64 if len(v) > 8 and v[8] == '64' else torch.float32
+    pgp = O.make_generator_params(res, ch, fmap_base=fb, fmap_max=fm, latent_size=lat, seed=3)
+    pdp = O.make_discriminator_params(res, ch, fmap_base=fb, fmap_max=fm, seed=4)
+    gen = torch.Generator().manual_seed(99)
+    r = 4 * 2 ** depth
+    z1, z2 = torch.randn(n, lat, generator=gen), torch.randn(n, lat, generator=gen)
+    real = torch.randn(n, ch, r, r, generator=gen)
+    mix = torch.rand(n, 1, generator=gen)
+    nb = O.n_blocks_for(res)
+    c = lambda d: {k: t.to(dt) for k, t in d.items()}
+    cost, rl, fl, gd = O.d_step_grads(c(pdp), c(pgp), real.to(dt), z1.to(dt), mix.to(dt), depth, alpha, nb)
+    gcost, gg = O.g_step_grads(c(pgp), c(pdp), z2.to(dt), depth, alpha, nb)
+    fake = O.generator_forward(c(pgp), z1.to(dt), depth, alpha)
+    return dict(resolution=res, channels=ch, fmap_base=fb, fmap_max=fm, latent=lat, n=n, depth=depth, alpha=alpha,
+                pg=pgp, pd=pdp, z1=z1, z2=z2, real=real, mixing=mix, fake=fake,
+                d_real_scores=O.discriminator_forward(c(pdp), real.to(dt), depth, alpha, nb),
+                d_fake_scores=O.discriminator_forward(c(pdp), fake, depth, alpha, nb),
+                d_cost=cost, d_real_loss=rl, d_fake_loss=fl, dgrad=gd, g_cost=gcost, ggrad=gg)
+
+
 def run_case(case, precision):
-    g = load_step(case)
+    g = oracle_case(case) if case.startswith('o:') else load_step(case)
     print('== %s  precision=%s  depth=%d alpha=%g N=%d' % (case, precision, g['depth'], g['alpha'], g['n']))
     G, D = build_pair(g, precision)
     worst = 0.0
@@ -28,7 +54,7 @@ def run_case(case, precision):
         fake = G(g['z1'].cuda())
         worst = max(worst, row('G(z1)', fake, g['fake']))
         worst = max(worst, row('D(real)', D(g['real'].cuda()), g['d_real_scores']))
-        worst = max(worst, row('D(fake_ref)', D(g['fake'].cuda()), g['d_fake_scores']))
+        worst = max(worst, row('D(fake_ref)', D(g['fake'].float().cuda()), g['d_fake_scores']))
     except Exception:
         traceback.print_exc()
     try:
