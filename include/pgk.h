@@ -53,11 +53,15 @@ void pgk_reset_launch_count(void);
  * bracket their launch with CUDA events on `stream`.  pgk_prof_read synchronises on the recorded events and returns
  * the summed algorithmic FLOPs (2*M*N*K of each launch), the summed device milliseconds and the launch count of one
  * kernel family; pgk_prof_reset drops the records. */
-#define PGK_PROF_CONV 0  /* forward conv / data gradient (pgk_conv) */
-#define PGK_PROF_WGRAD 1 /* weight gradient (pgk_wgrad)             */
+#define PGK_PROF_CONV 0       /* forward conv / data gradient on tcgen05 (pgk_conv)  */
+#define PGK_PROF_WGRAD 1      /* weight gradient on tcgen05 (pgk_wgrad)              */
+#define PGK_PROF_CONV_SIMT 2  /* pgk_conv launches served by the CUDA-core kernel    */
+#define PGK_PROF_WGRAD_SIMT 3 /* pgk_wgrad launches served by the CUDA-core kernel   */
 void pgk_prof_enable(int on);
 int pgk_prof_read(int family, double* flops, double* ms, long long* launches);
 void pgk_prof_reset(void);
+/* 0 routes every shape to the CUDA-core kernels (A/B comparisons; also PGK_TC=0 in the environment). */
+void pgk_set_tc(int on);
 
 /* ---- equalised-LR weights: fold c into the weight, re-lay for the kernels --------------
  * replaces `h = x * self.c` (network.py:33) + the cuDNN filter transform.
@@ -66,6 +70,9 @@ void pgk_prof_reset(void);
  * wb: backward operand [K'][cin']  the transposed / tap-flipped operand for the data gradient. */
 int pgk_prep_weight(const float* w, float c, int kind, int cin, int cin_stride, int cout, int ks,
                     float* wf, float* wb, pgk_stream_t stream);
+/* tensor-core operand: out[p][n][k] = bf16 plane p of w[k][n]  (w = wf or wb above, fp32 [K][Nn]; out: P planes,
+ * out_ps elements apart, each [Nn][K] K-major -- what the TMA descriptors of pgk_conv read). */
+int pgk_pack_operand(const float* w, int K, int Nn, void* out, long long out_ps, int P, pgk_stream_t stream);
 /* inverse map for weight gradients: dw (PyTorch layout) (+)= c * dwp (wf layout). */
 int pgk_unprep_grad(const float* dwp, float c, int kind, int cin, int cin_stride, int cout, int ks,
                     float* dw, int accumulate, pgk_stream_t stream);
@@ -78,11 +85,14 @@ int pgk_unprep_grad(const float* dwp, float c, int kind, int cin, int cin_stride
  *          then * lrelu'(mask_ref[n,y,x,co]) if mask_ref       (the backward of network.py:36)
  *          then * out_scale
  * The same entry point computes data gradients (x = output gradient, wf = wb of the layer,
- * mask_ref = the stored input activation of the layer) and the gradient-penalty's second chain. */
+ * mask_ref = the stored input activation of the layer) and the gradient-penalty's second chain.
+ * wt / wt_ps: the same operand packed by pgk_pack_operand (3 planes).  Shapes with Cin % 64 == 0, Cout % 16 == 0,
+ * power-of-two H, W and ups == 0 run on the TMA + tcgen05 kernel and read wt; all others run on the CUDA-core
+ * implicit GEMM and read wf.  Either pointer may be NULL if the shape never takes that path. */
 int pgk_conv(const void* x, int P, long long x_ps, int N, int H, int W, int Cin, int Cout, int KS, int ups,
-             const float* wf, const float* bias, const float* posT, const float* pos_s, int act,
-             const void* mask_ref, long long mask_ps, float out_scale, void* out, long long out_ps,
-             pgk_stream_t stream);
+             const float* wf, const void* wt, long long wt_ps, const float* bias, const float* posT,
+             const float* pos_s, int act, const void* mask_ref, long long mask_ps, float out_scale, void* out,
+             long long out_ps, pgk_stream_t stream);
 
 /* ---- weight gradient (cuDNN convolution_backward, weight part) --------------------------
  * dwp[tap*Cin+ci][co] += sum over the listed sample groups of X[..., ci] (shifted by tap) * g[..., co].

@@ -19,7 +19,8 @@ P, I, L, F = c_void_p, c_int, c_longlong, c_float
 SIGNATURES = {
     'pgk_prep_weight': [P, F, I, I, I, I, I, P, P],
     'pgk_unprep_grad': [P, F, I, I, I, I, I, P, I],
-    'pgk_conv': [P, I, L, I, I, I, I, I, I, I, P, P, P, P, I, P, L, F, P, L],
+    'pgk_pack_operand': [P, I, I, P, L, I],
+    'pgk_conv': [P, I, L, I, I, I, I, I, I, I, P, P, L, P, P, P, I, P, L, F, P, L],
     'pgk_wgrad': [P, L, P, L, I, I, I, I, I, I, I, I, I, P, P, P],
     'pgk_bias_grad': [P, L, I, I, I, I, I, P, F, P, I],
     'pgk_from_rgb': [P, I, I, I, I, I, P, F, P, I, P, L, P, I, L],
@@ -80,6 +81,8 @@ def load():
                                   ctypes.POINTER(c_longlong)]
     lib.pgk_prof_read.restype = c_int
     lib.pgk_prof_reset.restype = None
+    lib.pgk_set_tc.argtypes = [c_int]
+    lib.pgk_set_tc.restype = None
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = list(args) + [c_void_p]
@@ -90,7 +93,7 @@ def load():
 
 def exported_symbols():
     return ['pgk_version', 'pgk_last_error', 'pgk_arch_check', 'pgk_launch_count', 'pgk_reset_launch_count',
-            'pgk_prof_enable', 'pgk_prof_read', 'pgk_prof_reset'] + list(SIGNATURES)
+            'pgk_prof_enable', 'pgk_prof_read', 'pgk_prof_reset', 'pgk_set_tc'] + list(SIGNATURES)
 
 
 _checked_devices = set()

@@ -16,6 +16,27 @@ extern "C" int pgk_wgrad_simt(const void* x, long long x_ps, const void* g, long
                               int Cin, int Cout, int KS, int ups, int ngroups, int group_n, const int* xoff,
                               const int* goff, float* dwp, pgk_stream_t stream);
 
+extern "C" int pgk_conv_tc_supported(int N, int H, int W, int Cin, int Cout, int KS, int ups);
+extern "C" int pgk_conv_tc(const void* x, int P, long long x_ps, int N, int H, int W, int Cin, int Cout, int KS,
+                           const void* wt, long long wt_ps, const float* bias, const float* posT, const float* pos_s,
+                           int act, const void* mask_ref, long long mask_ps, float out_scale, void* out,
+                           long long out_ps, pgk_stream_t stream);
+extern "C" int pgk_wgrad_tc_supported(int H, int W, int Cin, int Cout, int KS, int ups, int ngroups, int group_n);
+extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long long g_ps, int P, int H, int W, int Cin,
+                            int Cout, int KS, int ngroups, int group_n, const int* xoff, const int* goff, float* dwp,
+                            pgk_stream_t stream);
+
+// PGK_TC=0 in the environment (or pgk_set_tc(0)) routes every shape to the CUDA-core kernels (A/B comparisons)
+static int g_tc = -1;
+static bool tc_enabled() {
+    if (g_tc < 0) {
+        const char* e = getenv("PGK_TC");
+        g_tc = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_tc != 0;
+}
+extern "C" void pgk_set_tc(int on) { g_tc = on ? 1 : 0; }
+
 // ---- per-launch timing (off by default; bench.py's roofline leg turns it on) --------------------------------
 namespace {
 struct ProfRec {
@@ -76,10 +97,17 @@ extern "C" void pgk_prof_reset(void) {
 }
 
 extern "C" int pgk_conv(const void* x, int P, long long x_ps, int N, int H, int W, int Cin, int Cout, int KS, int ups,
-                        const float* wf, const float* bias, const float* posT, const float* pos_s, int act,
-                        const void* mask_ref, long long mask_ps, float out_scale, void* out, long long out_ps,
-                        pgk_stream_t stream) {
-    ProfScope prof(PGK_PROF_CONV, 2.0 * N * H * W * (double)Cout * KS * KS * Cin, stream);
+                        const float* wf, const void* wt, long long wt_ps, const float* bias, const float* posT,
+                        const float* pos_s, int act, const void* mask_ref, long long mask_ps, float out_scale, void* out,
+                        long long out_ps, pgk_stream_t stream) {
+    const double flops = 2.0 * N * H * W * (double)Cout * KS * KS * Cin;
+    if (wt && tc_enabled() && pgk_conv_tc_supported(N, H, W, Cin, Cout, KS, ups)) {
+        ProfScope prof(PGK_PROF_CONV, flops, stream);
+        return pgk_conv_tc(x, P, x_ps, N, H, W, Cin, Cout, KS, wt, wt_ps, bias, posT, pos_s, act, mask_ref, mask_ps,
+                           out_scale, out, out_ps, stream);
+    }
+    PGK_REQUIRE(wf != nullptr, "pgk_conv: this shape runs on the CUDA-core kernel, which needs the fp32 operand wf");
+    ProfScope prof(PGK_PROF_CONV_SIMT, flops, stream);
     return pgk_conv_simt(x, P, x_ps, N, H, W, Cin, Cout, KS, ups, wf, bias, posT, pos_s, act, mask_ref, mask_ps,
                          out_scale, out, out_ps, stream);
 }
@@ -87,6 +115,11 @@ extern "C" int pgk_conv(const void* x, int P, long long x_ps, int N, int H, int 
 extern "C" int pgk_wgrad(const void* x, long long x_ps, const void* g, long long g_ps, int P, int H, int W, int Cin,
                          int Cout, int KS, int ups, int ngroups, int group_n, const int* xoff, const int* goff,
                          float* dwp, pgk_stream_t stream) {
-    ProfScope prof(PGK_PROF_WGRAD, 2.0 * ngroups * group_n * H * W * (double)Cout * KS * KS * Cin, stream);
+    const double flops = 2.0 * ngroups * group_n * H * W * (double)Cout * KS * KS * Cin;
+    if (tc_enabled() && pgk_wgrad_tc_supported(H, W, Cin, Cout, KS, ups, ngroups, group_n)) {
+        ProfScope prof(PGK_PROF_WGRAD, flops, stream);
+        return pgk_wgrad_tc(x, x_ps, g, g_ps, P, H, W, Cin, Cout, KS, ngroups, group_n, xoff, goff, dwp, stream);
+    }
+    ProfScope prof(PGK_PROF_WGRAD_SIMT, flops, stream);
     return pgk_wgrad_simt(x, x_ps, g, g_ps, P, H, W, Cin, Cout, KS, ups, ngroups, group_n, xoff, goff, dwp, stream);
 }

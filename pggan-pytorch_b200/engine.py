@@ -71,11 +71,10 @@ class PT(object):
         """fp32 N,C,H,W -> planes (tests only; the product path never converts through torch)."""
         n, c, h, w = x.shape
         v = x.permute(0, 2, 3, 1).contiguous().float()
-        hi = v.to(BF16)
         out = PT.empty(n, h, w, c, P, x.device)
-        out.t[0] = hi
-        if P == 2:
-            out.t[1] = (v - hi.float()).to(BF16)
+        for p in range(P):
+            out.t[p] = v.to(BF16)
+            v = v - out.t[p].float()
         return out
 
 
@@ -86,11 +85,12 @@ def _mask(m):
 # ---------------------------------------------------------------------------------------------
 # thin op wrappers (argument marshalling only)
 # ---------------------------------------------------------------------------------------------
-def conv(x, wf, cout, ks, out, ups=0, bias=None, posT=None, pos_s=None, act=0, mask=None, scale=1.0):
-    """out <- pgk_conv(x); H, W are taken from `out`."""
+def conv(x, w, cout, ks, out, ups=0, bias=None, posT=None, pos_s=None, act=0, mask=None, scale=1.0):
+    """out <- pgk_conv(x); H, W are taken from `out`.  w = (fp32 [K][Cout] operand, bf16 planes [3][Cout][K] operand)."""
     mp, mps = _mask(mask)
-    call('pgk_conv', x.ptr, x.P, x.ps, out.N, out.H, out.W, x.C, cout, ks, ups, wf.data_ptr(),
-         None if bias is None else bias.data_ptr(), None if posT is None else posT.data_ptr(),
+    wf, wt = w
+    call('pgk_conv', x.ptr, x.P, x.ps, out.N, out.H, out.W, x.C, cout, ks, ups, wf.data_ptr(), wt.data_ptr(),
+         wt.stride(0), None if bias is None else bias.data_ptr(), None if posT is None else posT.data_ptr(),
          None if pos_s is None else pos_s.data_ptr(), act, mp, mps, scale, out.ptr, out.ps)
     return out
 
@@ -156,6 +156,7 @@ class ConvW(object):
         self.cin_stride = cin_stride if cin_stride is not None else cin
         self.pos_hw, self.need_wb = pos_hw, need_wb
         self.wf = self.wb = self.posT = self.bias16 = self.dwp = None
+        self.F = self.B = None   # (fp32 [K][N], bf16 planes [3][N][K]) operand pairs: forward / data gradient
         self.version = None
 
     @property
@@ -180,6 +181,20 @@ class ConvW(object):
                 self.posT = torch.empty(self.pos_hw[0] * self.pos_hw[1] * self.cout, dtype=torch.float32, device=dev)
         call('pgk_prep_weight', w.data_ptr(), self.mod.cf, self.kind, self.cin, self.cin_stride, self.cout, self.ks,
              self.wf.data_ptr(), None if self.wb is None else self.wb.data_ptr())
+        # tensor-core operands: [plane][output channel][K], K-major
+        taps = self.ks * self.ks
+        if self.kind == W_CONV:
+            kf, nf_, kb, nb = taps * self.cin, self.cout, taps * self.cout, self.cin
+        elif self.kind == W_GFIRST:
+            kf, nf_, kb, nb = self.cin, 16 * self.cout, 16 * self.cout, self.cin
+        else:
+            kf, nf_, kb, nb = 16 * self.cin, self.cout, self.cout, 16 * self.cin
+        if self.F is None or self.F[1].device != dev:
+            self.F = (self.wf, torch.empty((3, nf_, kf), dtype=BF16, device=dev))
+            self.B = (self.wb, torch.empty((3, nb, kb), dtype=BF16, device=dev)) if self.need_wb else None
+        call('pgk_pack_operand', self.wf.data_ptr(), kf, nf_, self.F[1].data_ptr(), self.F[1].stride(0), 3)
+        if self.need_wb:
+            call('pgk_pack_operand', self.wb.data_ptr(), kb, nb, self.B[1].data_ptr(), self.B[1].stride(0), 3)
         if self.pos_hw is not None:
             call('pgk_prep_posbias', w.data_ptr(), self.mod.cf, self.cin_stride, self.cin, self.cout, self.pos_hw[0],
                  self.pos_hw[1], self.posT.data_ptr())
@@ -293,9 +308,9 @@ class DEngine(object):
         else:
             w1, w2 = self.cw(top.c1), self.cw(top.c2)
             T.t1 = new(r, w1.cout)
-            conv(T.t0.sl(0, B), w1.wf, w1.cout, 3, T.t1.sl(0, B), bias=w1.bias, act=1)
+            conv(T.t0.sl(0, B), w1.F, w1.cout, 3, T.t1.sl(0, B), bias=w1.bias, act=1)
             T.t2 = new(r, w2.cout)
-            conv(T.t1.sl(0, B), w2.wf, w2.cout, 3, T.t2.sl(0, B), bias=w2.bias, act=1)
+            conv(T.t1.sl(0, B), w2.F, w2.cout, 3, T.t2.sl(0, B), bias=w2.bias, act=1)
             h = new(r // 2, w2.cout)
             if fade:
                 T.xlow = pool_img(ximg)
@@ -309,9 +324,9 @@ class DEngine(object):
                 b = self.blk(k)
                 w1, w2 = self.cw(b.c1), self.cw(b.c2)
                 a_ = new(res, w1.cout)
-                conv(h.sl(0, B), w1.wf, w1.cout, 3, a_.sl(0, B), bias=w1.bias, act=1)
+                conv(h.sl(0, B), w1.F, w1.cout, 3, a_.sl(0, B), bias=w1.bias, act=1)
                 b_ = new(res, w2.cout)
-                conv(a_.sl(0, B), w2.wf, w2.cout, 3, b_.sl(0, B), bias=w2.bias, act=1)
+                conv(a_.sl(0, B), w2.F, w2.cout, 3, b_.sl(0, B), bias=w2.bias, act=1)
                 hn = new(res // 2, w2.cout)
                 pool2(b_.sl(0, B), hn.sl(0, B), avg=1)
                 T.blocks.append(SimpleNamespace(mod=b, hin=h, a=a_, b=b_, res=res))
@@ -326,9 +341,9 @@ class DEngine(object):
         call('pgk_stddev_stats', hin.ptr, hin.ps, P, ngroups, group_n * 16 * C, T.stats.data_ptr(), T.svec.data_ptr(),
              group_n)
         T.l1 = new(4, wl1.cout)
-        conv(hin.sl(0, B), wl1.wf, wl1.cout, 3, T.l1.sl(0, B), bias=wl1.bias, posT=wl1.posT, pos_s=T.svec, act=1)
+        conv(hin.sl(0, B), wl1.F, wl1.cout, 3, T.l1.sl(0, B), bias=wl1.bias, posT=wl1.posT, pos_s=T.svec, act=1)
         T.l2 = PT.empty(Bt, 1, 1, wl2.cout, P, dev)
-        conv(T.l1.sl(0, B).view(1, 1, 16 * wl1.cout), wl2.wf, wl2.cout, 1, T.l2.sl(0, B), bias=wl2.bias, act=1)
+        conv(T.l1.sl(0, B).view(1, 1, 16 * wl1.cout), wl2.F, wl2.cout, 1, T.l2.sl(0, B), bias=wl2.bias, act=1)
         T.scores = torch.empty(B, dtype=torch.float32, device=dev)
         call('pgk_linear_fwd', T.l2.ptr, T.l2.ps, P, B, wl2.cout, D.linear.weight.data_ptr(), D.linear.bias.data_ptr(),
              T.scores.data_ptr())
@@ -348,14 +363,14 @@ class DEngine(object):
              None if gs is None else gs[D.linear.weight].data_ptr(),
              None if gs is None else gs[D.linear.bias].data_ptr())
         T.ua_l1 = PT.empty(T.Bt, 4, 4, wl1.cout, P, dev)
-        conv(T.ua_l2.sl(0, B), wl2.wb, 16 * wl1.cout, 1, T.ua_l1.sl(0, B).view(1, 1, 16 * wl1.cout),
+        conv(T.ua_l2.sl(0, B), wl2.B, 16 * wl1.cout, 1, T.ua_l1.sl(0, B).view(1, 1, 16 * wl1.cout),
              mask=T.l1.sl(0, B).view(1, 1, 16 * wl1.cout))
         T.q = torch.empty(T.ngroups, dtype=torch.float32, device=dev)
         call('pgk_group_dot_pos', T.ua_l1.ptr, T.ua_l1.ps, P, T.ngroups, T.group_n, 16, wl1.cout, wl1.posT.data_ptr(),
              T.q.data_ptr())
         C = T.hin.C
         T.d_hin = PT.empty(B, 4, 4, C, P, dev)
-        conv(T.ua_l1.sl(0, B), wl1.wb, C, 3, T.d_hin)
+        conv(T.ua_l1.sl(0, B), wl1.B, C, 3, T.d_hin)
         call('pgk_stddev_bwd', T.hin.ptr, T.hin.ps, T.stats.data_ptr(), T.q.data_ptr(), P, T.ngroups,
              T.group_n * 16 * C, T.d_hin.ptr, T.d_hin.ps)
 
@@ -380,13 +395,13 @@ class DEngine(object):
                 w1, w2 = self.cw(rec.mod.c1), self.cw(rec.mod.c2)
                 name = 'ua_blk%d' % (len(T.blocks) - 1 - i)
                 ua_b = mask_mul(d_h, ua_of(name + 'b', rec.b), ref=rec.b.sl(n0, n1), ups=1, scale=0.25)
-                ua_a = conv(ua_b, w2.wb, w1.cout, 3, ua_of(name + 'a', rec.a), mask=rec.a.sl(n0, n1))
-                d_h = conv(ua_a, w1.wb, w1.cin, 3, PT.empty(n, rec.res, rec.res, w1.cin, P, dev))
+                ua_a = conv(ua_b, w2.B, w1.cout, 3, ua_of(name + 'a', rec.a), mask=rec.a.sl(n0, n1))
+                d_h = conv(ua_a, w1.B, w1.cin, 3, PT.empty(n, rec.res, rec.res, w1.cin, P, dev))
             w1, w2 = self.cw(top.c1), self.cw(top.c2)
             ua_t2 = mask_mul(d_h, ua_of('ua_t2', T.t2), ref=T.t2.sl(n0, n1), ups=1,
                              scale=0.25 * (alpha if fade else 1.0))
-            ua_t1 = conv(ua_t2, w2.wb, w1.cout, 3, ua_of('ua_t1', T.t1), mask=T.t1.sl(n0, n1))
-            ua_t0 = conv(ua_t1, w1.wb, w1.cin, 3, ua_of('ua_t0', T.t0), mask=T.t0.sl(n0, n1))
+            ua_t1 = conv(ua_t2, w2.B, w1.cout, 3, ua_of('ua_t1', T.t1), mask=T.t1.sl(n0, n1))
+            ua_t0 = conv(ua_t1, w1.B, w1.cin, 3, ua_of('ua_t0', T.t0), mask=T.t0.sl(n0, n1))
             if fade:
                 ua_f = mask_mul(d_h, ua_of('ua_f', T.f), ref=T.f.sl(n0, n1), scale=1.0 - alpha)
 
@@ -414,8 +429,8 @@ class DEngine(object):
             vh = v(T.t0)
         else:
             w1, w2 = self.cw(top.c1), self.cw(top.c2)
-            conv(v(T.t0), w1.wf, w1.cout, 3, v(T.t1), mask=m(T.t1))
-            conv(v(T.t1), w2.wf, w2.cout, 3, v(T.t2), mask=m(T.t2))
+            conv(v(T.t0), w1.F, w1.cout, 3, v(T.t1), mask=m(T.t1))
+            conv(v(T.t1), w2.F, w2.cout, 3, v(T.t2), mask=m(T.t2))
             res = T.t2.H // 2
             if fade:
                 T.v0low = pool_img(v0)
@@ -427,8 +442,8 @@ class DEngine(object):
                 pool2(v(T.t2), v(dst), avg=1)
             for i, rec in enumerate(T.blocks):
                 w1, w2 = self.cw(rec.mod.c1), self.cw(rec.mod.c2)
-                conv(v(rec.hin), w1.wf, w1.cout, 3, v(rec.a), mask=m(rec.a))
-                conv(v(rec.a), w2.wf, w2.cout, 3, v(rec.b), mask=m(rec.b))
+                conv(v(rec.hin), w1.F, w1.cout, 3, v(rec.a), mask=m(rec.a))
+                conv(v(rec.a), w2.F, w2.cout, 3, v(rec.b), mask=m(rec.b))
                 dst = T.blocks[i + 1].hin if i + 1 < len(T.blocks) else T.hin
                 pool2(v(rec.b), v(dst), avg=1)
             vh = v(T.hin)
@@ -442,8 +457,8 @@ class DEngine(object):
         hm = m(T.hin)
         call('pgk_stddev_bwd2', hm.ptr, hm.ps, vh.ptr, vh.ps, T.stats[4 * g:].data_ptr(), T.q[g:].data_ptr(), P,
              n * 16 * C, T.ev.data_ptr(), n, T.w_h.ptr, T.w_h.ps, scratch.data_ptr())
-        conv(vh, wl1.wf, wl1.cout, 3, v(T.l1), posT=wl1.posT, pos_s=T.ev, mask=m(T.l1))
-        conv(v(T.l1).view(1, 1, 16 * wl1.cout), wl2.wf, wl2.cout, 1, v(T.l2), mask=m(T.l2))
+        conv(vh, wl1.F, wl1.cout, 3, v(T.l1), posT=wl1.posT, pos_s=T.ev, mask=m(T.l1))
+        conv(v(T.l1).view(1, 1, 16 * wl1.cout), wl2.F, wl2.cout, 1, v(T.l2), mask=m(T.l2))
 
     # -- parameter gradients -------------------------------------------------------------------
     def param_grads(self, T, gs, groups, bias_goffs, head_groups, head_bias_goffs, img_pairs, ev_pair=None):
@@ -549,28 +564,31 @@ class GEngine(object):
         b0 = G.block0
         w1, w2 = self.cw(b0.c1, W_GFIRST), self.cw(b0.c2)
         h1 = PT.empty(n, 4, 4, w1.cout, P, dev)
-        conv(zn, w1.wf, 16 * w1.cout, 1, h1.view(1, 1, 16 * w1.cout), bias=w1.bias16, act=1)
+        conv(zn, w1.F, 16 * w1.cout, 1, h1.view(1, 1, 16 * w1.cout), bias=w1.bias16, act=1)
         self._post(h1, T, 'b0c1')
         h2 = PT.empty(n, 4, 4, w2.cout, P, dev)
-        conv(h1, w2.wf, w2.cout, 3, h2, bias=w2.bias, act=1)
+        conv(h1, w2.F, w2.cout, 3, h2, bias=w2.bias, act=1)
         self._post(h2, T, 'b0c2')
         if tape:
             T.zn = zn
-            T.acts.append((None, h1, h2))
+            T.acts.append((None, None, h1, h2))
         h, res = h2, 4
         hprev = None
         for i in range(1, depth + 1):
             b = self.block(i)
             w1, w2 = self.cw(b.c1), self.cw(b.c2)
             res *= 2
+            # nearest-neighbour 2x upsample (network.py:127,129), materialised once: the tensor-core conv and the
+            # weight gradient both read it through plain TMA boxes
+            hu = mask_mul(h, PT.empty(n, res, res, h.C, P, dev), ups=1)
             u1 = PT.empty(n, res, res, w1.cout, P, dev)
-            conv(h, w1.wf, w1.cout, 3, u1, ups=1, bias=w1.bias, act=1)
+            conv(hu, w1.F, w1.cout, 3, u1, bias=w1.bias, act=1)
             self._post(u1, T, 'b%dc1' % i)
             u2 = PT.empty(n, res, res, w2.cout, P, dev)
-            conv(u1, w2.wf, w2.cout, 3, u2, bias=w2.bias, act=1)
+            conv(u1, w2.F, w2.cout, 3, u2, bias=w2.bias, act=1)
             self._post(u2, T, 'b%dc2' % i)
             if tape:
-                T.acts.append((h, u1, u2))
+                T.acts.append((h, hu, u1, u2))
             hprev, h = h, u2
         C = self.block(depth).toRGB.conv.weight.shape[0]
         img = out if out is not None else torch.empty((n, C, res, res), dtype=torch.float32, device=dev)
@@ -596,7 +614,7 @@ class GEngine(object):
         res = dimg.shape[-1]
         groups = [(0, 0)]
         hi = self.block(depth).toRGB
-        hprev, u1, u2 = T.acts[depth]
+        hprev, _, u1, u2 = T.acts[depth]
         a_hi = 1.0 if depth == 0 else alpha
         # toRGB (network.py:49,65) and the fade-in lerp (network.py:138)
         rgb_wgrad(dimg, 0, u2, n, C, res, res, 0, hi.cf * a_hi, a_hi, gs[hi.conv.weight], u2.C, 1, None,
@@ -614,12 +632,12 @@ class GEngine(object):
                  lo.cf, 1.0 - alpha, 1, d_lo.ptr, P, d_lo.ps)
         for i in range(depth, -1, -1):
             b = self.block(i)
-            hprev, u1, u2 = T.acts[i]
+            hprev, hup, u1, u2 = T.acts[i]
             w2 = self.cw(b.c2)
             da2 = self._act_bwd(d, u2, T, 'b%dc2' % i)
             w2.wgrad_into(gs[b.c2.conv.weight], u1, da2, res, res, 0, groups, n)
             bias_grad(da2, res * res, w2.cout, [0], n, gs[b.c2.conv.bias])
-            d1 = conv(da2, w2.wb, w2.cin, 3, PT.empty(n, res, res, w2.cin, P, dev))
+            d1 = conv(da2, w2.B, w2.cin, 3, PT.empty(n, res, res, w2.cin, P, dev))
             da1 = self._act_bwd(d1, u1, T, 'b%dc1' % i)
             if i == 0:
                 w1 = self.cw(b.c1, W_GFIRST)
@@ -627,9 +645,9 @@ class GEngine(object):
                 bias_grad(da1, 16, w1.cout, [0], n, gs[b.c1.conv.bias])
                 break
             w1 = self.cw(b.c1)
-            w1.wgrad_into(gs[b.c1.conv.weight], hprev, da1, res, res, 1, groups, n)
+            w1.wgrad_into(gs[b.c1.conv.weight], hup, da1, res, res, 0, groups, n)
             bias_grad(da1, res * res, w1.cout, [0], n, gs[b.c1.conv.bias])
-            d_up = conv(da1, w1.wb, w1.cin, 3, PT.empty(n, res, res, w1.cin, P, dev))
+            d_up = conv(da1, w1.B, w1.cin, 3, PT.empty(n, res, res, w1.cin, P, dev))
             res //= 2
             d = PT.empty(n, res, res, w1.cin, P, dev)
             if d_lo is not None:

@@ -1,0 +1,125 @@
+"""Development aid (GPU box): tensor-core kernels vs the CUDA-core kernels of the same library on random operands.
+   python tools/tc_test.py [conv|wgrad|all]"""
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import pggan_b200 as pg  # noqa: E402
+from importlib import import_module  # noqa: E402
+
+E = import_module('pggan-pytorch_b200.engine')
+lib = pg._lib.load()
+call = pg._lib.call
+BF16 = torch.bfloat16
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+REF = torch.float32
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def conv_case(N, H, W, Cin, Cout, KS, P, act=1, mask=False, bias=True, scale=1.0, pos=False):
+    g = torch.Generator(device='cuda').manual_seed(N * 1000 + H + Cin + Cout)
+    x = torch.randn(N, Cin, H, W, device='cuda', generator=g)
+    K = KS * KS * Cin
+    wf = (torch.randn(K, Cout, device='cuda', generator=g) / K ** 0.5).contiguous()
+    wt = torch.empty(3, Cout, K, dtype=BF16, device='cuda')
+    call('pgk_pack_operand', wf.data_ptr(), K, Cout, wt.data_ptr(), wt.stride(0), 3)
+    b = torch.randn(Cout, device='cuda', generator=g) if bias else None
+    xp = E.PT.from_float(x, P)
+    m = E.PT.from_float(torch.randn(N, Cout, H, W, device='cuda', generator=g), P) if mask else None
+    posT = torch.randn(H * W * Cout, device='cuda', generator=g) if pos else None
+    pos_s = torch.randn(N, device='cuda', generator=g) if pos else None
+    outs = []
+    for tcon in (0, 1):
+        lib.pgk_set_tc(tcon)
+        o = E.PT.empty(N, H, W, Cout, P, 'cuda')
+        o.t.fill_(float('nan'))
+        E.conv(xp, (wf, wt), Cout, KS, o, bias=b, posT=posT, pos_s=pos_s, act=act, mask=m, scale=scale)
+        torch.cuda.synchronize()
+        outs.append(o.float())
+    lib.pgk_set_tc(1)
+    # fp64 reference
+    w4 = wf.view(KS, KS, Cin, Cout).permute(3, 2, 0, 1).to(REF)
+    ref = torch.nn.functional.conv2d(xp.float().to(REF), w4, b.to(REF) if bias else None, padding=KS // 2)
+    if pos:
+        ref = ref + pos_s.to(REF).view(N, 1, 1, 1) * posT.to(REF).view(H, W, Cout).permute(2, 0, 1)
+    if act:
+        ref = torch.nn.functional.leaky_relu(ref, 0.2)
+    if mask:
+        ref = ref * torch.where(m.float().to(REF) > 0, 1.0, 0.2)
+    ref = ref * scale
+    e_tc, e_simt = rel(outs[1], ref), rel(outs[0], ref)
+    tol = {1: 2e-2, 2: 1e-4, 3: 2e-5}[P]
+    flag = 'ok ' if e_tc < tol else 'BAD'
+    print('%s conv N%d %dx%d %d->%d k%d P%d act%d mask%d pos%d: tc %.2e simt %.2e' % (flag, N, H, W, Cin, Cout, KS, P, act, mask, pos, e_tc, e_simt))
+    return e_tc < tol
+
+
+def wgrad_case(N, H, W, Cin, Cout, KS, P, ngroups=1):
+    g = torch.Generator(device='cuda').manual_seed(N * 1000 + H + Cin + Cout)
+    ntot = N * ngroups + 2
+    x = torch.randn(ntot, Cin, H, W, device='cuda', generator=g)
+    gg = torch.randn(ntot, Cout, H, W, device='cuda', generator=g)
+    xp, gp = E.PT.from_float(x, P), E.PT.from_float(gg, P)
+    K = KS * KS * Cin
+    groups = [(1 + i * N, (ngroups - 1 - i) * N) for i in range(ngroups)]
+    outs = []
+    for tcon in (0, 1):
+        lib.pgk_set_tc(tcon)
+        dwp = torch.zeros(K, Cout, device='cuda')
+        E.wgrad(xp, gp, H, W, Cin, Cout, KS, 0, groups, N, dwp)
+        torch.cuda.synchronize()
+        outs.append(dwp)
+    lib.pgk_set_tc(1)
+    xd, gd = xp.float().to(REF), gp.float().to(REF)
+    ref = torch.zeros(K, Cout, dtype=REF, device='cuda')
+    for xo, go in groups:
+        xs = torch.nn.functional.pad(xd[xo:xo + N], (KS // 2,) * 4)
+        gs = gd[go:go + N]
+        for ky in range(KS):
+            for kx in range(KS):
+                patch = xs[:, :, ky:ky + H, kx:kx + W]
+                tap = ky * KS + kx
+                ref[tap * Cin:(tap + 1) * Cin] += torch.einsum('nchw,nohw->co', patch, gs)
+    e_tc, e_simt = rel(outs[1], ref), rel(outs[0], ref)
+    tol = {1: 2e-2, 2: 1e-4, 3: 2e-5}[P]
+    flag = 'ok ' if e_tc < tol else 'BAD'
+    print('%s wgrad N%d x%d groups %dx%d %d->%d k%d P%d: tc %.2e simt %.2e' % (flag, N, ngroups, H, W, Cin, Cout, KS, P, e_tc, e_simt))
+    return e_tc < tol
+
+
+def main():
+    what = sys.argv[1] if len(sys.argv) > 1 else 'all'
+    ok = True
+    if what in ('conv', 'all'):
+        ok &= conv_case(2, 16, 16, 64, 64, 3, 1)
+        ok &= conv_case(2, 16, 16, 64, 64, 3, 3)
+        ok &= conv_case(3, 4, 4, 128, 64, 3, 2, pos=True)
+        ok &= conv_case(5, 8, 8, 64, 128, 3, 3, mask=True, act=0, bias=False, scale=0.25)
+        ok &= conv_case(2, 32, 32, 128, 256, 3, 3)
+        ok &= conv_case(1, 64, 64, 256, 512, 3, 1)
+        ok &= conv_case(1, 64, 64, 256, 512, 3, 3)
+        ok &= conv_case(2, 128, 128, 64, 16, 3, 3)
+        ok &= conv_case(1, 256, 256, 64, 32, 3, 1, mask=True)
+        ok &= conv_case(130, 1, 1, 512, 2048, 1, 3)
+        ok &= conv_case(7, 1, 1, 1024, 64, 1, 3, mask=True, act=0)
+    if what in ('wgrad', 'all'):
+        ok &= wgrad_case(4, 16, 16, 64, 64, 3, 1)
+        ok &= wgrad_case(4, 16, 16, 64, 64, 3, 3)
+        ok &= wgrad_case(16, 4, 4, 128, 64, 3, 3, ngroups=2)
+        ok &= wgrad_case(8, 8, 8, 64, 128, 3, 2, ngroups=3)
+        ok &= wgrad_case(2, 32, 32, 128, 256, 3, 3, ngroups=4)
+        ok &= wgrad_case(2, 64, 64, 256, 512, 3, 1)
+        ok &= wgrad_case(1, 128, 128, 64, 64, 3, 3, ngroups=2)
+    print('ALL OK' if ok else 'FAILURES')
+
+
+if __name__ == '__main__':
+    main()
