@@ -131,7 +131,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
     }
-    const unsigned ncols = tmem_cols(a.NT);
+    // With P > 1 the plane-0 x plane-0 products go to one accumulator and all correction products (2^-8 and smaller)
+    // to a second one, added in the epilogue: the tensor core truncates the accumulator on every add, so keeping
+    // the adds into the large accumulator to K/16 (instead of 3x / 6x that) is what holds fp32-level accuracy.
+    const unsigned ncols = tmem_cols(P > 1 ? 2 * a.NT : a.NT);
     if (warp == 5) tmem_alloc(tptr, ncols);
     fence_before();
     __syncthreads();
@@ -159,7 +162,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t layout = a.bkb == 128 ? 2u : 4u;
             const uint32_t sbo = 8u * a.bkb;
             const int ksteps = a.bkb / 32;
-            uint32_t acc = 0;
+            uint32_t acc = 0, acc_corr = 0;
             for (int kc = 0; kc < nk; ++kc) {
                 const int s = kc % a.stages;
                 mbar_wait(full(s), (kc / a.stages) & 1);
@@ -170,8 +173,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint64_t ad = smem_desc(abase + i * a_bytes + ks * 32, 16, sbo, layout);
                         for (int j = 0; i + j < P; ++j) {
                             const uint64_t bd = smem_desc(bbase + j * b_bytes + ks * 32, 16, sbo, layout);
-                            mma_bf16(tmem, ad, bd, idesc, acc);
-                            acc = 1;
+                            if (i + j == 0) {
+                                mma_bf16(tmem, ad, bd, idesc, acc);
+                                acc = 1;
+                            } else {
+                                mma_bf16(tmem + a.NT, ad, bd, idesc, acc_corr);
+                                acc_corr = 1;
+                            }
                         }
                     }
                 }
@@ -197,6 +205,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int c = 0; c < a.NT; c += 16) {
             float v[16];
             tmem_ld16(trow + c, v);
+            if (P > 1) {
+                float w[16];
+                tmem_ld16(trow + a.NT + c, w);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += w[j];
+            }
             if (!valid) continue;
             const int co = co0 + c;
 #pragma unroll
