@@ -1,0 +1,138 @@
+"""CPU: host-side logic of the product package -- C ABI surface, schedule, module surface, trainer plumbing and the
+data-parallel gradient exchange (gloo, world_size 2).  No kernels are launched here."""
+import os
+import pickle
+import re
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from _util import load_schedule
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+import pggan_b200 as pg  # noqa: E402
+
+
+def test_library_exports_every_declared_symbol():
+    """include/pgk.h is the contract: every function it declares is exported by libpgk.so and bound in _lib.py."""
+    hdr = open(os.path.join(ROOT, 'include', 'pgk.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(pgk_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) > 30
+    lib = pg._lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), '%s declared in pgk.h but not exported' % name
+    assert declared == set(pg._lib.exported_symbols()), declared ^ set(pg._lib.exported_symbols())
+    assert lib.pgk_version() >= 100
+
+
+def test_no_cpu_fallback():
+    G = pg.Generator((1, 3, 16, 16), fmap_base=64, fmap_max=16, latent_size=16)
+    D = pg.Discriminator((1, 3, 16, 16), fmap_base=64, fmap_max=16)
+    with pytest.raises(RuntimeError):
+        G(torch.randn(2, 16))
+    with pytest.raises(RuntimeError):
+        D(torch.randn(2, 3, 4, 4))
+    with pytest.raises(RuntimeError):
+        pg.wgan_gp_G_loss(G, D, torch.randn(2, 16))
+
+
+def test_module_surface_matches_reference():
+    """constructor kwargs / attributes / state_dict keys of network.py:75-116,190-223 (names from SURVEY.md 5)."""
+    G = pg.Generator((1, 3, 32, 32))
+    D = pg.Discriminator((1, 3, 32, 32))
+    assert (G.depth, G.alpha, G.latent_size, G.max_depth) == (0, 1.0, 512, 3)
+    assert (D.depth, D.alpha, D.max_depth) == (0, 1.0, 3)
+    gk, dk = set(G.state_dict()), set(D.state_dict())
+    assert {'block0.c1.conv.weight', 'block0.toRGB.conv.bias', 'blocks.2.c2.conv.weight'} <= gk
+    assert {'blocks.0.fromRGB.conv.weight', 'blocks.3.c1.conv.weight', 'linear.weight', 'linear.bias'} <= dk
+    assert G.block0.c1.conv.weight.shape == (512, 512, 4, 4)
+    assert D.blocks[3].c1.conv.weight.shape == (512, 513, 3, 3)
+    assert D.blocks[3].c2.conv.weight.shape == (512, 512, 4, 4)
+    assert not any(k.endswith('.c') for k in gk | dk), 'c is a plain attribute, not in the state_dict (network.py:19)'
+    # 1024x1024 parameter counts probed on the reference
+    assert sum(p.numel() for p in pg.Generator((1, 3, 1024, 1024)).parameters()) == 18359731
+    assert sum(p.numel() for p in pg.Discriminator((1, 3, 1024, 1024)).parameters()) == 18367369
+    # SaverPlugin pickles whole modules (plugins.py:158-166)
+    G2 = pickle.loads(pickle.dumps(G))
+    assert set(G2.state_dict()) == gk and abs(G2.block0.c1.c - G.block0.c1.c) == 0
+
+
+def test_depth_manager_drives_modules_like_the_reference():
+    pts = [p for p in load_schedule()['points'] if p['max_depth'] == 8]
+    G = pg.Generator((1, 3, 1024, 1024), fmap_base=4096, fmap_max=8, latent_size=8)
+    D = pg.Discriminator((1, 3, 1024, 1024), fmap_base=4096, fmap_max=8)
+    assert G.max_depth == D.max_depth == 8
+
+    class DS(object):
+        model_depth, alpha = 0, 1.0
+
+    made = []
+    t = pg.Trainer(D, G, None, None, None, None, DS(), None, None)
+    dm = pg.DepthManager(lambda mb: made.append(mb) or iter(()), lambda mb: (lambda: None), G.max_depth)
+    t.register_plugin(dm)
+    assert (G.depth, G.alpha, D.depth, D.alpha) == (0, 1.0, 0, 1.0) and made == [16]
+    for p in pts:
+        t.cur_nimg = p['cur_nimg']
+        dm.iteration()
+        assert (G.depth, D.depth, t.dataset.model_depth) == (p['depth'],) * 3
+        assert repr(G.alpha) == p['alpha'] and D.alpha == G.alpha == t.dataset.alpha      # bit exact (repr of the float)
+        assert t.tick_duration_nimg == p['tick_nimg']
+        assert t.stats['minibatch_size'] == p['minibatch']
+    assert len(pts) > 10
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dp_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from importlib import import_module
+        engine = import_module('pggan-pytorch_b200.engine')
+        torch.manual_seed(0)
+        params = [torch.nn.Parameter(torch.zeros(3, 5)), torch.nn.Parameter(torch.zeros(7))]
+        gs = engine.GradSet(params, 'cpu')
+        gs[params[0]].fill_(float(rank + 1))
+        gs[params[1]].copy_(torch.arange(7.0) * (rank + 1))
+        pg.wgan_gp_loss._allreduce(gs)          # ONE all-reduce of the flat buffer, averaged
+        loss = pg.wgan_gp_loss._deposit(torch.tensor(2.0), gs)
+        loss.backward()
+        out[rank] = (params[0].grad.clone(), params[1].grad.clone(), float(loss))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_exchange_gloo_world2():
+    """Exact DP oracle: every rank ends with the mean over ranks of the per-rank gradients."""
+    world = 2
+    port = _free_port()
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_dp_worker, args=(world, port, out), nprocs=world, join=True)
+        res = dict(out)
+    for rank in range(world):
+        g0, g1, loss = res[rank]
+        assert torch.equal(g0, torch.full((3, 5), 1.5))
+        assert torch.equal(g1, torch.arange(7.0) * 1.5)
+        assert loss == 2.0
+
+
+def test_deposit_scales_with_upstream_gradient():
+    from importlib import import_module
+    engine = import_module('pggan-pytorch_b200.engine')
+    p = torch.nn.Parameter(torch.zeros(4))
+    gs = engine.GradSet([p], 'cpu')
+    gs[p].copy_(torch.tensor([1.0, 2.0, 3.0, 4.0]))
+    (pg.wgan_gp_loss._deposit(torch.tensor(1.0), gs) * 0.5).backward()
+    assert torch.equal(p.grad, torch.tensor([0.5, 1.0, 1.5, 2.0]))
