@@ -88,8 +88,11 @@ int pgk_unprep_grad(const float* dwp, float c, int kind, int cin, int cin_stride
  * mask_ref = the stored input activation of the layer) and the gradient-penalty's second chain.
  * wt / wt_ps: the same operand packed by pgk_pack_operand (3 planes).  Shapes with Cin % 64 == 0, Cout % 16 == 0,
  * power-of-two H, W and ups == 0 run on the TMA + tcgen05 kernel and read wt; all others run on the CUDA-core
- * implicit GEMM and read wf.  Either pointer may be NULL if the shape never takes that path. */
-int pgk_conv(const void* x, int P, long long x_ps, int N, int H, int W, int Cin, int Cout, int KS, int ups,
+ * implicit GEMM and read wf.  Either pointer may be NULL if the shape never takes that path.
+ * Pr (1 <= Pr <= P): how many planes of x and wt the tensor-core kernel READS (products of planes i + j < Pr).
+ * Forward passes, whose values decide the LeakyReLU masks, use Pr = P; the gradient chains use Pr = min(P, 2)
+ * (16 mantissa bits, three products instead of six) -- gradients are continuous in these operands. */
+int pgk_conv(const void* x, int P, int Pr, long long x_ps, int N, int H, int W, int Cin, int Cout, int KS, int ups,
              const float* wf, const void* wt, long long wt_ps, const float* bias, const float* posT,
              const float* pos_s, int act, const void* mask_ref, long long mask_ps, float out_scale, void* out,
              long long out_ps, pgk_stream_t stream);
@@ -98,8 +101,8 @@ int pgk_conv(const void* x, int P, long long x_ps, int N, int H, int W, int Cin,
  * dwp[tap*Cin+ci][co] += sum over the listed sample groups of X[..., ci] (shifted by tap) * g[..., co].
  * Groups: ngroups (<= 4) groups of group_n samples; group i reads x samples starting at xoff[i] and g samples
  * starting at goff[i].  dwp must be zeroed by the caller (fp32, wf layout). */
-int pgk_wgrad(const void* x, long long x_ps, const void* g, long long g_ps, int P, int H, int W, int Cin, int Cout,
-              int KS, int ups, int ngroups, int group_n, const int* xoff, const int* goff, float* dwp,
+int pgk_wgrad(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W, int Cin,
+              int Cout, int KS, int ups, int ngroups, int group_n, const int* xoff, const int* goff, float* dwp,
               pgk_stream_t stream);
 /* db[co] (+)= scale * sum over pixels of the listed sample groups of g[..., co]. */
 int pgk_bias_grad(const void* g, long long g_ps, int P, int HW, int Cout, int ngroups, int group_n, const int* goff,

@@ -17,14 +17,14 @@ extern "C" int pgk_wgrad_simt(const void* x, long long x_ps, const void* g, long
                               const int* goff, float* dwp, pgk_stream_t stream);
 
 extern "C" int pgk_conv_tc_supported(int N, int H, int W, int Cin, int Cout, int KS, int ups);
-extern "C" int pgk_conv_tc(const void* x, int P, long long x_ps, int N, int H, int W, int Cin, int Cout, int KS,
+extern "C" int pgk_conv_tc(const void* x, int P, int Pr, long long x_ps, int N, int H, int W, int Cin, int Cout, int KS,
                            const void* wt, long long wt_ps, const float* bias, const float* posT, const float* pos_s,
                            int act, const void* mask_ref, long long mask_ps, float out_scale, void* out,
                            long long out_ps, pgk_stream_t stream);
 extern "C" int pgk_wgrad_tc_supported(int H, int W, int Cin, int Cout, int KS, int ups, int ngroups, int group_n);
-extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long long g_ps, int P, int H, int W, int Cin,
-                            int Cout, int KS, int ngroups, int group_n, const int* xoff, const int* goff, float* dwp,
-                            pgk_stream_t stream);
+extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W,
+                            int Cin, int Cout, int KS, int ngroups, int group_n, const int* xoff, const int* goff,
+                            float* dwp, pgk_stream_t stream);
 
 // PGK_TC=0 in the environment (or pgk_set_tc(0)) routes every shape to the CUDA-core kernels (A/B comparisons)
 static int g_tc = -1;
@@ -96,14 +96,16 @@ extern "C" void pgk_prof_reset(void) {
     g_recs.clear();
 }
 
-extern "C" int pgk_conv(const void* x, int P, long long x_ps, int N, int H, int W, int Cin, int Cout, int KS, int ups,
+extern "C" int pgk_conv(const void* x, int P, int Pr, long long x_ps, int N, int H, int W, int Cin, int Cout, int KS,
+                        int ups,
                         const float* wf, const void* wt, long long wt_ps, const float* bias, const float* posT,
                         const float* pos_s, int act, const void* mask_ref, long long mask_ps, float out_scale, void* out,
                         long long out_ps, pgk_stream_t stream) {
+    PGK_REQUIRE(Pr >= 1 && Pr <= P, "pgk_conv: need 1 <= Pr <= P");
     const double flops = 2.0 * N * H * W * (double)Cout * KS * KS * Cin;
     if (wt && tc_enabled() && pgk_conv_tc_supported(N, H, W, Cin, Cout, KS, ups)) {
         ProfScope prof(PGK_PROF_CONV, flops, stream);
-        return pgk_conv_tc(x, P, x_ps, N, H, W, Cin, Cout, KS, wt, wt_ps, bias, posT, pos_s, act, mask_ref, mask_ps,
+        return pgk_conv_tc(x, P, Pr, x_ps, N, H, W, Cin, Cout, KS, wt, wt_ps, bias, posT, pos_s, act, mask_ref, mask_ps,
                            out_scale, out, out_ps, stream);
     }
     PGK_REQUIRE(wf != nullptr, "pgk_conv: this shape runs on the CUDA-core kernel, which needs the fp32 operand wf");
@@ -112,13 +114,13 @@ extern "C" int pgk_conv(const void* x, int P, long long x_ps, int N, int H, int 
                          out_scale, out, out_ps, stream);
 }
 
-extern "C" int pgk_wgrad(const void* x, long long x_ps, const void* g, long long g_ps, int P, int H, int W, int Cin,
-                         int Cout, int KS, int ups, int ngroups, int group_n, const int* xoff, const int* goff,
+extern "C" int pgk_wgrad(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W,
+                         int Cin, int Cout, int KS, int ups, int ngroups, int group_n, const int* xoff, const int* goff,
                          float* dwp, pgk_stream_t stream) {
     const double flops = 2.0 * ngroups * group_n * H * W * (double)Cout * KS * KS * Cin;
     if (tc_enabled() && pgk_wgrad_tc_supported(H, W, Cin, Cout, KS, ups, ngroups, group_n)) {
         ProfScope prof(PGK_PROF_WGRAD, flops, stream);
-        return pgk_wgrad_tc(x, x_ps, g, g_ps, P, H, W, Cin, Cout, KS, ngroups, group_n, xoff, goff, dwp, stream);
+        return pgk_wgrad_tc(x, x_ps, g, g_ps, P, Pr, H, W, Cin, Cout, KS, ngroups, group_n, xoff, goff, dwp, stream);
     }
     ProfScope prof(PGK_PROF_WGRAD_SIMT, flops, stream);
     return pgk_wgrad_simt(x, x_ps, g, g_ps, P, H, W, Cin, Cout, KS, ups, ngroups, group_n, xoff, goff, dwp, stream);

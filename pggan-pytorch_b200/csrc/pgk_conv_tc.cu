@@ -427,14 +427,14 @@ extern "C" int pgk_conv_tc_supported(int N, int H, int W, int Cin, int Cout, int
     return N > 0;
 }
 
-extern "C" int pgk_conv_tc(const void* x, int P, long long x_ps, int N, int H, int W, int Cin, int Cout, int KS,
+extern "C" int pgk_conv_tc(const void* x, int P, int Pr, long long x_ps, int N, int H, int W, int Cin, int Cout, int KS,
                            const void* wt, long long wt_ps, const float* bias, const float* posT, const float* pos_s,
                            int act, const void* mask_ref, long long mask_ps, float out_scale, void* out,
                            long long out_ps, pgk_stream_t stream) {
     PGK_REQUIRE(pgk_conv_tc_supported(N, H, W, Cin, Cout, KS, 0), "pgk_conv_tc: unsupported shape");
-    PGK_REQUIRE(P >= 1 && P <= 3, "pgk_conv_tc: P must be 1, 2 or 3");
+    PGK_REQUIRE(P >= 1 && P <= 3 && Pr >= 1 && Pr <= P, "pgk_conv_tc: need 1 <= Pr <= P <= 3");
     ConvTcArgs a;
-    a.N = N, a.H = H, a.W = W, a.Cin = Cin, a.Cout = Cout, a.KS = KS, a.P = P;
+    a.N = N, a.H = H, a.W = W, a.Cin = Cin, a.Cout = Cout, a.KS = KS, a.P = Pr;   // the kernel's P = planes READ
     const int TW = W < 128 ? W : 128;
     const int TH = H < 128 / TW ? H : 128 / TW;
     a.TN = 128 / (TW * TH);
@@ -443,12 +443,17 @@ extern "C" int pgk_conv_tc(const void* x, int P, long long x_ps, int N, int H, i
     const int tiles_n = (N + a.TN - 1) / a.TN;
     a.NT = Cout < 256 ? Cout : 256;
     a.bkb = 128;
-    int stage_bytes = P * (128 * a.bkb + a.NT * a.bkb);
+    int stage_bytes = Pr * (128 * a.bkb + a.NT * a.bkb);
     if (2 * stage_bytes + 2048 > kSmemLimit && Cin % 32 == 0) {   // three planes of a 256-wide tile: halve the K slice
         a.bkb = 64;
-        stage_bytes = P * (128 * a.bkb + a.NT * a.bkb);
+        stage_bytes = Pr * (128 * a.bkb + a.NT * a.bkb);
     }
-    a.stages = (kSmemLimit - 2048) / stage_bytes;
+    // several CTAs per SM (bounded by TMEM columns and by >= 3 smem stages each): one tile's prologue / epilogue
+    // overlaps another tile's main loop
+    int ctas = 512 / (int)tmem_cols(Pr > 1 ? 2 * a.NT : a.NT);
+    if (ctas > 4) ctas = 4;
+    while (ctas > 1 && (kSmemLimit / ctas - 2048) / stage_bytes < 3) --ctas;
+    a.stages = (kSmemLimit / ctas - 2048) / stage_bytes;
     if (a.stages > 8) a.stages = 8;
     PGK_REQUIRE(a.stages >= 1, "pgk_conv_tc: tile does not fit in shared memory");
     a.bias = bias, a.posT = posT, a.pos_s = pos_s, a.act = act;
@@ -502,14 +507,14 @@ extern "C" int pgk_wgrad_tc_supported(int H, int W, int Cin, int Cout, int KS, i
     return 1;
 }
 
-extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long long g_ps, int P, int H, int W, int Cin,
-                            int Cout, int KS, int ngroups, int group_n, const int* xoff, const int* goff, float* dwp,
-                            pgk_stream_t stream) {
+extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W,
+                            int Cin, int Cout, int KS, int ngroups, int group_n, const int* xoff, const int* goff,
+                            float* dwp, pgk_stream_t stream) {
     PGK_REQUIRE(pgk_wgrad_tc_supported(H, W, Cin, Cout, KS, 0, ngroups, group_n), "pgk_wgrad_tc: unsupported shape");
-    PGK_REQUIRE(P >= 1 && P <= 3, "pgk_wgrad_tc: P must be 1, 2 or 3");
+    PGK_REQUIRE(P >= 1 && P <= 3 && Pr >= 1 && Pr <= P, "pgk_wgrad_tc: need 1 <= Pr <= P <= 3");
     PGK_REQUIRE(ngroups >= 1 && ngroups <= 4, "pgk_wgrad_tc: 1..4 groups");
     WgradTcArgs a;
-    a.H = H, a.W = W, a.Cin = Cin, a.Cout = Cout, a.KS = KS, a.P = P;
+    a.H = H, a.W = W, a.Cin = Cin, a.Cout = Cout, a.KS = KS, a.P = Pr;   // the kernel's P = planes READ
     a.PXS = 32;
     const int TW = W < a.PXS ? W : a.PXS;
     const int TH = H < a.PXS / TW ? H : a.PXS / TW;
@@ -532,17 +537,29 @@ extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long l
     const int sgroups = (slabs + smax - 1) / smax;
     a.S = (slabs + sgroups - 1) / sgroups;
     const int box_bytes = a.PXS * 128;
-    const int stage_bytes = P * (2 * a.S + a.NT / 64) * box_bytes;
-    a.stages = (kSmemLimit - 2048) / stage_bytes;
+    const int stage_bytes = Pr * (2 * a.S + a.NT / 64) * box_bytes;
+    int ctas = 512 / (int)tmem_cols(a.S * a.NT);
+    if (ctas > 4) ctas = 4;
+    while (ctas > 1 && (kSmemLimit / ctas - 2048) / stage_bytes < 3) --ctas;
+    a.stages = (kSmemLimit / ctas - 2048) / stage_bytes;
     if (a.stages > 8) a.stages = 8;
     PGK_REQUIRE(a.stages >= 1, "pgk_wgrad_tc: stage does not fit in shared memory");
     a.tiles_per_group = (long long)group_n * H * W / a.PXS;
     a.tiles_total = a.tiles_per_group * ngroups;
+    // split the pixel range so that the grid is (just under) one or two full waves of the SMs
     const int base = sgroups * (Cout / a.NT);
-    long long split = (2ll * pgk_num_sms() + base - 1) / base;
+    const int sms = pgk_num_sms();
     long long max_split = (a.tiles_total + 15) / 16;
-    if (split > max_split) split = max_split;
-    if (split < 1) split = 1;
+    long long split = 1;
+    double best = -1.0;
+    for (int w = 1; w <= 2; ++w) {
+        long long sp = (long long)w * sms / base;
+        if (sp < 1) sp = 1;
+        if (sp > max_split) sp = max_split;
+        const long long ctas = sp * base;
+        const double util = (double)ctas / (double)(((ctas + sms - 1) / sms) * sms);
+        if (util > best + 0.02) best = util, split = sp;
+    }
     if (split > 65535) split = 65535;
     a.tiles_per_cta = (a.tiles_total + split - 1) / split;
     split = (a.tiles_total + a.tiles_per_cta - 1) / a.tiles_per_cta;

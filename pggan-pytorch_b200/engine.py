@@ -85,11 +85,15 @@ def _mask(m):
 # ---------------------------------------------------------------------------------------------
 # thin op wrappers (argument marshalling only)
 # ---------------------------------------------------------------------------------------------
-def conv(x, w, cout, ks, out, ups=0, bias=None, posT=None, pos_s=None, act=0, mask=None, scale=1.0):
-    """out <- pgk_conv(x); H, W are taken from `out`.  w = (fp32 [K][Cout] operand, bf16 planes [3][Cout][K] operand)."""
+GRAD_PLANES = 2   # planes read by the gradient chains (see include/pgk.h, pgk_conv: Pr)
+
+
+def conv(x, w, cout, ks, out, ups=0, bias=None, posT=None, pos_s=None, act=0, mask=None, scale=1.0, fwd=False):
+    """out <- pgk_conv(x); H, W are taken from `out`.  w = (fp32 [K][Cout] operand, bf16 planes [3][Cout][K] operand).
+    fwd=True: a forward pass whose values decide LeakyReLU masks -- all planes are read."""
     mp, mps = _mask(mask)
     wf, wt = w
-    call('pgk_conv', x.ptr, x.P, x.ps, out.N, out.H, out.W, x.C, cout, ks, ups, wf.data_ptr(), wt.data_ptr(),
+    call('pgk_conv', x.ptr, x.P, x.P if fwd else min(x.P, GRAD_PLANES), x.ps, out.N, out.H, out.W, x.C, cout, ks, ups, wf.data_ptr(), wt.data_ptr(),
          wt.stride(0), None if bias is None else bias.data_ptr(), None if posT is None else posT.data_ptr(),
          None if pos_s is None else pos_s.data_ptr(), act, mp, mps, scale, out.ptr, out.ps)
     return out
@@ -97,7 +101,7 @@ def conv(x, w, cout, ks, out, ups=0, bias=None, posT=None, pos_s=None, act=0, ma
 
 def wgrad(x, g, H, W, cin, cout, ks, ups, groups, group_n, dwp):
     xoff, goff = _ints([a for a, _ in groups]), _ints([b for _, b in groups])
-    call('pgk_wgrad', x.ptr, x.ps, g.ptr, g.ps, x.P, H, W, cin, cout, ks, ups, len(groups), group_n, xoff, goff,
+    call('pgk_wgrad', x.ptr, x.ps, g.ptr, g.ps, x.P, min(x.P, GRAD_PLANES), H, W, cin, cout, ks, ups, len(groups), group_n, xoff, goff,
          dwp.data_ptr())
 
 
@@ -308,9 +312,9 @@ class DEngine(object):
         else:
             w1, w2 = self.cw(top.c1), self.cw(top.c2)
             T.t1 = new(r, w1.cout)
-            conv(T.t0.sl(0, B), w1.F, w1.cout, 3, T.t1.sl(0, B), bias=w1.bias, act=1)
+            conv(T.t0.sl(0, B), w1.F, w1.cout, 3, T.t1.sl(0, B), bias=w1.bias, act=1, fwd=True)
             T.t2 = new(r, w2.cout)
-            conv(T.t1.sl(0, B), w2.F, w2.cout, 3, T.t2.sl(0, B), bias=w2.bias, act=1)
+            conv(T.t1.sl(0, B), w2.F, w2.cout, 3, T.t2.sl(0, B), bias=w2.bias, act=1, fwd=True)
             h = new(r // 2, w2.cout)
             if fade:
                 T.xlow = pool_img(ximg)
@@ -324,9 +328,9 @@ class DEngine(object):
                 b = self.blk(k)
                 w1, w2 = self.cw(b.c1), self.cw(b.c2)
                 a_ = new(res, w1.cout)
-                conv(h.sl(0, B), w1.F, w1.cout, 3, a_.sl(0, B), bias=w1.bias, act=1)
+                conv(h.sl(0, B), w1.F, w1.cout, 3, a_.sl(0, B), bias=w1.bias, act=1, fwd=True)
                 b_ = new(res, w2.cout)
-                conv(a_.sl(0, B), w2.F, w2.cout, 3, b_.sl(0, B), bias=w2.bias, act=1)
+                conv(a_.sl(0, B), w2.F, w2.cout, 3, b_.sl(0, B), bias=w2.bias, act=1, fwd=True)
                 hn = new(res // 2, w2.cout)
                 pool2(b_.sl(0, B), hn.sl(0, B), avg=1)
                 T.blocks.append(SimpleNamespace(mod=b, hin=h, a=a_, b=b_, res=res))
@@ -341,9 +345,9 @@ class DEngine(object):
         call('pgk_stddev_stats', hin.ptr, hin.ps, P, ngroups, group_n * 16 * C, T.stats.data_ptr(), T.svec.data_ptr(),
              group_n)
         T.l1 = new(4, wl1.cout)
-        conv(hin.sl(0, B), wl1.F, wl1.cout, 3, T.l1.sl(0, B), bias=wl1.bias, posT=wl1.posT, pos_s=T.svec, act=1)
+        conv(hin.sl(0, B), wl1.F, wl1.cout, 3, T.l1.sl(0, B), bias=wl1.bias, posT=wl1.posT, pos_s=T.svec, act=1, fwd=True)
         T.l2 = PT.empty(Bt, 1, 1, wl2.cout, P, dev)
-        conv(T.l1.sl(0, B).view(1, 1, 16 * wl1.cout), wl2.F, wl2.cout, 1, T.l2.sl(0, B), bias=wl2.bias, act=1)
+        conv(T.l1.sl(0, B).view(1, 1, 16 * wl1.cout), wl2.F, wl2.cout, 1, T.l2.sl(0, B), bias=wl2.bias, act=1, fwd=True)
         T.scores = torch.empty(B, dtype=torch.float32, device=dev)
         call('pgk_linear_fwd', T.l2.ptr, T.l2.ps, P, B, wl2.cout, D.linear.weight.data_ptr(), D.linear.bias.data_ptr(),
              T.scores.data_ptr())
@@ -564,10 +568,10 @@ class GEngine(object):
         b0 = G.block0
         w1, w2 = self.cw(b0.c1, W_GFIRST), self.cw(b0.c2)
         h1 = PT.empty(n, 4, 4, w1.cout, P, dev)
-        conv(zn, w1.F, 16 * w1.cout, 1, h1.view(1, 1, 16 * w1.cout), bias=w1.bias16, act=1)
+        conv(zn, w1.F, 16 * w1.cout, 1, h1.view(1, 1, 16 * w1.cout), bias=w1.bias16, act=1, fwd=True)
         self._post(h1, T, 'b0c1')
         h2 = PT.empty(n, 4, 4, w2.cout, P, dev)
-        conv(h1, w2.F, w2.cout, 3, h2, bias=w2.bias, act=1)
+        conv(h1, w2.F, w2.cout, 3, h2, bias=w2.bias, act=1, fwd=True)
         self._post(h2, T, 'b0c2')
         if tape:
             T.zn = zn
@@ -582,10 +586,10 @@ class GEngine(object):
             # weight gradient both read it through plain TMA boxes
             hu = mask_mul(h, PT.empty(n, res, res, h.C, P, dev), ups=1)
             u1 = PT.empty(n, res, res, w1.cout, P, dev)
-            conv(hu, w1.F, w1.cout, 3, u1, bias=w1.bias, act=1)
+            conv(hu, w1.F, w1.cout, 3, u1, bias=w1.bias, act=1, fwd=True)
             self._post(u1, T, 'b%dc1' % i)
             u2 = PT.empty(n, res, res, w2.cout, P, dev)
-            conv(u1, w2.F, w2.cout, 3, u2, bias=w2.bias, act=1)
+            conv(u1, w2.F, w2.cout, 3, u2, bias=w2.bias, act=1, fwd=True)
             self._post(u2, T, 'b%dc2' % i)
             if tape:
                 T.acts.append((h, hu, u1, u2))

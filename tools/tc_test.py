@@ -41,7 +41,7 @@ def conv_case(N, H, W, Cin, Cout, KS, P, act=1, mask=False, bias=True, scale=1.0
         lib.pgk_set_tc(tcon)
         o = E.PT.empty(N, H, W, Cout, P, 'cuda')
         o.t.fill_(float('nan'))
-        E.conv(xp, (wf, wt), Cout, KS, o, bias=b, posT=posT, pos_s=pos_s, act=act, mask=m, scale=scale)
+        E.conv(xp, (wf, wt), Cout, KS, o, bias=b, posT=posT, pos_s=pos_s, act=act, mask=m, scale=scale, fwd=True)
         torch.cuda.synchronize()
         outs.append(o.float())
     lib.pgk_set_tc(1)
