@@ -15,6 +15,8 @@
 // Warp roles (192 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMA producer, warp 5 TMEM
 // allocation + MMA issue.  smem ring of `stages` {A planes, B planes}; full/empty mbarriers; tcgen05.commit releases
 // a stage back to the producer and, after the last k-step, hands the accumulator to the epilogue.
+#include <stdlib.h>
+
 #include "pgk_tc.cuh"
 
 using namespace tc;
@@ -77,13 +79,24 @@ __host__ __device__ inline unsigned tmem_cols(int n) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// forward conv / data gradient
+// forward conv / data gradient: persistent CTAs (one per SM), tiles = (128-pixel block, NT-channel slice).
+// Warps 0-7 epilogue (TMEM lane quarter = warp % 4, column half = warp / 4), warp 8 TMA producer, warp 9 MMA issue.
+// Two TMEM accumulator buffers: the epilogue of tile i overlaps the main loop of tile i + 1.
 // ------------------------------------------------------------------------------------------------------------
+constexpr int kConvThreads = 320;
+constexpr int kEpiWarps = 8;
+
 struct ConvTcArgs {
-    int N, H, W, Cin, Cout, KS, P;
+    int N, H, W, Cin, Cout, KS, P;   // P = planes READ (products of planes i + j < P)
     int lw, lh, TN;        // pixel block = TN samples x 2^lh rows x 2^lw columns = 128 pixels
     int tiles_x, tiles_y;
-    int NT, stages, bkb;   // channels per CTA, ring depth, bytes per K row of a stage (128 or 64)
+    int ntiles_n;          // Cout / NT
+    int total_tiles;
+    int NT, stages, bkb;   // channels per tile, ring depth, bytes per K row of a stage (128 or 64)
+    int split_acc;         // 1: plane0 x plane0 products and correction products in separate accumulators
+    int Pout;              // planes written
+    int slab;              // channels per epilogue slab (32 or 16): one TMA store box = 128 pixels x slab channels
+    int nmask;             // mask staging buffers per warpgroup (2 with a mask, else 0)
     const float* bias;
     const float* posT;
     const float* pos_s;
@@ -93,163 +106,313 @@ struct ConvTcArgs {
     Planes out;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTcArgs a) {
+// P (planes read), KSTEPS (= bkb / 32) and SPLIT (separate correction accumulator) are compile-time: the MMA-issue
+// sequence of a k-slice unrolls to one descriptor add + one UTCHMMA per product.  (With run-time loop bounds the
+// dependent uniform-datapath address arithmetic cost ~350 cycles per MMA -- three times the MMA itself.)
+template <int P, int KSTEPS, int SPLIT>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmM, const ConvTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;
-    const int P = a.P;
-    const uint32_t a_bytes = 128u * a.bkb, b_bytes = (uint32_t)a.NT * a.bkb;
+    constexpr uint32_t kBkb = 32u * KSTEPS;
+    constexpr uint32_t a_bytes = 128u * kBkb;
+    const uint32_t b_bytes = (uint32_t)a.NT * kBkb;
     const uint32_t stage_bytes = P * (a_bytes + b_bytes);
     const uint32_t bars = sbase + a.stages * stage_bytes;
     auto full = [&](int s) { return bars + 8u * s; };
     auto empty = [&](int s) { return bars + 8u * (a.stages + s); };
-    const uint32_t tfull = bars + 16u * a.stages, tptr = tfull + 8u;
+    const uint32_t tfull0 = bars + 16u * a.stages;   // tfull[2], tempty[2]
+    auto tfull = [&](int b) { return tfull0 + 8u * b; };
+    auto tempty = [&](int b) { return tfull0 + 16u + 8u * b; };
+    auto mfull = [&](int wg, int b) { return tfull0 + 32u + 16u * wg + 8u * b; };   // mask slab landed (per warpgroup)
+    const uint32_t tptr = tfull0 + 64u;
+    float* bias_s = reinterpret_cast<float*>(smem_raw + (tptr + 16u - raw));   // [2][NT]
+    // epilogue staging, per warpgroup: 2 mask slabs + Pout output slabs of 128 rows x slab channels (1024-aligned)
+    const uint32_t slab_bytes = 128u * a.slab * 2u;
+    const uint32_t epi_wg_bytes = (uint32_t)(a.nmask + a.Pout) * slab_bytes;
+    const uint32_t epi_base = (tptr + 16u + 2u * 4u * a.NT + 1023u) & ~1023u;
 
-    int t = blockIdx.x;
-    const int tx = t % a.tiles_x;
-    t /= a.tiles_x;
-    const int ty = t % a.tiles_y;
-    const int tn = t / a.tiles_y;
-    const int x0 = tx << a.lw, y0 = ty << a.lh, n0 = tn * a.TN;
-    const int co0 = blockIdx.y * a.NT;
-    const int kelems = a.bkb >> 1;
+    constexpr int kelems = kBkb >> 1;
     const int kchunks = a.Cin / kelems;
     const int nk = a.KS * a.KS * kchunks;
     const int pad = a.KS >> 1;
+    const int acc_cols = SPLIT ? 2 * a.NT : a.NT;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.stages; ++s) {
             mbar_init(full(s), 1);
             mbar_init(empty(s), 1);
         }
-        mbar_init(tfull, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull(b), 1);
+            mbar_init(tempty(b), kEpiWarps);
+            mbar_init(mfull(0, b), 1);
+            mbar_init(mfull(1, b), 1);
+        }
         fence_barrier_init();
     }
-    if (warp == 4 && lane == 0) {
+    if (warp == 8 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmO);
+        tma_prefetch_desc(&tmM);
     }
-    // With P > 1 the plane-0 x plane-0 products go to one accumulator and all correction products (2^-8 and smaller)
-    // to a second one, added in the epilogue: the tensor core truncates the accumulator on every add, so keeping
-    // the adds into the large accumulator to K/16 (instead of 3x / 6x that) is what holds fp32-level accuracy.
-    const unsigned ncols = tmem_cols(P > 1 ? 2 * a.NT : a.NT);
-    if (warp == 5) tmem_alloc(tptr, ncols);
+    const unsigned ncols = tmem_cols(2 * acc_cols);
+    if (warp == 9) tmem_alloc(tptr, ncols);
     fence_before();
     __syncthreads();
     fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tptr - raw));
 
-    if (warp == 4) {
-        if (lane == 0) {
-            for (int kc = 0; kc < nk; ++kc) {
-                const int s = kc % a.stages;
-                mbar_wait(empty(s), ((kc / a.stages) & 1) ^ 1);
-                mbar_expect_tx(full(s), stage_bytes);
-                const int tap = kc / kchunks, cc = kc - tap * kchunks;
-                const int ky = tap / a.KS, kx = tap - ky * a.KS;
-                const uint32_t dst = sbase + s * stage_bytes;
-                for (int p = 0; p < P; ++p)
-                    tma_load_5d(dst + p * a_bytes, &tmA, full(s), cc * kelems, x0 + kx - pad, y0 + ky - pad, n0, p);
-                for (int p = 0; p < P; ++p)
-                    tma_load_3d(dst + P * a_bytes + p * b_bytes, &tmB, full(s), kc * kelems, co0, p);
+    auto tile_coords = [&](int t, int& x0, int& y0, int& n0, int& co0) {
+        const int nt = t % a.ntiles_n;
+        int pt = t / a.ntiles_n;
+        const int tx = pt % a.tiles_x;
+        pt /= a.tiles_x;
+        const int ty = pt % a.tiles_y;
+        const int tn = pt / a.tiles_y;
+        x0 = tx << a.lw, y0 = ty << a.lh, n0 = tn * a.TN, co0 = nt * a.NT;
+    };
+
+    // The producer and the MMA issuer are single threads: their loops carry only counters (no divisions, no
+    // descriptor rebuilds) -- a dependent-instruction chain of a few hundred cycles per k-slice would otherwise
+    // bound the whole kernel.
+    if (warp == 8) {
+        int s = 0;
+        uint32_t ph = 1;   // parity to wait for on the empty barrier of stage s (first pass: passes immediately)
+        constexpr uint32_t a_all = P * a_bytes;
+        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+            int x0, y0, n0, co0;
+            tile_coords(t, x0, y0, n0, co0);
+            int kcol = 0;   // K coordinate of the weight slice
+            for (int ky = 0; ky < a.KS; ++ky) {
+                for (int kx = 0; kx < a.KS; ++kx) {
+                    const int xs = x0 + kx - pad, ys = y0 + ky - pad;
+                    for (int c = 0; c < a.Cin; c += kelems, kcol += kelems) {
+                        mbar_wait_spin(empty(s), ph);
+                        const uint32_t fb = full(s);
+                        const uint32_t dst = sbase + s * stage_bytes;
+                        if (elect_one()) {
+                            mbar_expect_tx(fb, stage_bytes);
+#pragma unroll
+                            for (int p = 0; p < P; ++p) tma_load_5d(dst + p * a_bytes, &tmA, fb, c, xs, ys, n0, p);
+#pragma unroll
+                            for (int p = 0; p < P; ++p) tma_load_3d(dst + a_all + p * b_bytes, &tmB, fb, kcol, co0, p);
+                        }
+                        __syncwarp();
+                        if (++s == a.stages) s = 0, ph ^= 1;
+                    }
+                }
             }
         }
-    } else if (warp == 5) {
-        if (lane == 0) {
-            const uint32_t idesc = idesc_bf16(a.NT, 0, 0);
-            const uint32_t layout = a.bkb == 128 ? 2u : 4u;
-            const uint32_t sbo = 8u * a.bkb;
-            const int ksteps = a.bkb / 32;
-            uint32_t acc = 0, acc_corr = 0;
+    } else if (warp == 9) {
+        const uint32_t idesc = idesc_bf16(a.NT, 0, 0);
+        // descriptor = constant high part | (address >> 4) in the low 14 bits: per MMA only an add
+        const uint64_t dbase = smem_desc(0, 16, 8u * kBkb, KSTEPS == 4 ? 2u : 4u);
+        constexpr uint32_t a16 = a_bytes >> 4;
+        const uint32_t b16 = b_bytes >> 4;
+        int s = 0, ti = 0;
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++ti) {
+            const int b = ti & 1;
+            mbar_wait_spin(tempty(b), ((ti >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator buffer
+            fence_after();
+            const uint32_t d_main = tmem + b * acc_cols, d_corr = d_main + a.NT;
             for (int kc = 0; kc < nk; ++kc) {
-                const int s = kc % a.stages;
-                mbar_wait(full(s), (kc / a.stages) & 1);
+                mbar_wait_spin(full(s), ph);
                 fence_after();
-                const uint32_t abase = sbase + s * stage_bytes, bbase = abase + P * a_bytes;
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    for (int i = 0; i < P; ++i) {
-                        const uint64_t ad = smem_desc(abase + i * a_bytes + ks * 32, 16, sbo, layout);
-                        for (int j = 0; i + j < P; ++j) {
-                            const uint64_t bd = smem_desc(bbase + j * b_bytes + ks * 32, 16, sbo, layout);
-                            if (i + j == 0) {
-                                mma_bf16(tmem, ad, bd, idesc, acc);
-                                acc = 1;
-                            } else {
-                                mma_bf16(tmem + a.NT, ad, bd, idesc, acc_corr);
-                                acc_corr = 1;
+                const uint32_t abase = (sbase + s * stage_bytes) >> 4;
+                const uint64_t ad0 = dbase | abase, bd0 = dbase | (abase + P * a16);
+                if (elect_one()) {
+                    const uint32_t later = kc > 0 ? 1u : 0u;   // 0 only for the first products of a tile
+#pragma unroll
+                    for (int ks = 0; ks < KSTEPS; ++ks) {
+#pragma unroll
+                        for (int i = 0; i < P; ++i) {
+#pragma unroll
+                            for (int j = 0; j < P - i; ++j) {
+                                const uint64_t ad = ad0 + (uint32_t)(i * a16 + ks * 2);
+                                const uint64_t bd = bd0 + (uint32_t)(j * b16 + ks * 2);
+                                if (i + j == 0 || !SPLIT) {
+                                    mma_bf16(d_main, ad, bd, idesc, (ks == 0 && i + j == 0) ? later : 1u);
+                                } else {
+                                    mma_bf16(d_corr, ad, bd, idesc, (ks == 0 && i == 0 && j == 1) ? later : 1u);
+                                }
                             }
                         }
                     }
+                    mma_commit(empty(s));
                 }
-                mma_commit(empty(s));
+                __syncwarp();
+                if (++s == a.stages) s = 0, ph ^= 1;
             }
-            mma_commit(tfull);
+            if (elect_one()) mma_commit(tfull(b));
+            __syncwarp();
         }
-        __syncwarp();
     } else {
-        // ---- epilogue: one accumulator row (= one pixel) per thread
-        mbar_wait(tfull, 0);
-        fence_after();
-        const int r = warp * 32 + lane;
+        // ---- epilogue: one accumulator row (= one pixel) per thread; warpgroup wg = warp / 4 owns half of the tile's
+        // channels and walks them in slabs: TMEM -> registers -> (bias, stddev channel, LeakyReLU, mask, scale,
+        // plane split) -> swizzled shared memory -> one TMA tensor store per plane.  Masks arrive the same way (TMA
+        // load of plane 0, whose sign is the value's sign), double buffered one slab ahead.
+        const int q = warp & 3, wg = warp >> 2;
+        const int wcols = a.NT >= 32 ? a.NT / 2 : a.NT;
+        const bool active = wg == 0 || a.NT >= 32;
+        const int nslabs = wcols / a.slab;
+        const int r = q * 32 + lane;
         const int px = r & ((1 << a.lw) - 1);
         const int py = (r >> a.lw) & ((1 << a.lh) - 1);
-        const int n = n0 + (r >> (a.lw + a.lh));
-        const int x = x0 + px, y = y0 + py;
-        const bool valid = n < a.N;
-        const long long pix = ((long long)n * a.H + y) * a.W + x;
-        const float ps = (a.posT && valid) ? __ldg(a.pos_s + n) : 0.f;
-        const float* posrow = a.posT ? a.posT + (long long)(y * a.W + x) * a.Cout : nullptr;
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-        for (int c = 0; c < a.NT; c += 16) {
-            float v[16];
-            tmem_ld16(trow + c, v);
-            if (P > 1) {
-                float w[16];
-                tmem_ld16(trow + a.NT + c, w);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += w[j];
+        const int pn = r >> (a.lw + a.lh);
+        const bool lead_warp = (warp & 3) == 0;   // warp-uniform: its elected lane issues the warpgroup's TMA traffic
+        const uint32_t row_bytes = a.slab * 2u;
+        const uint32_t swz = a.slab == 32 ? 3u : 1u;
+        const uint32_t wg_base = epi_base + wg * epi_wg_bytes;
+        auto sm_mask = [&](int b) { return wg_base + b * slab_bytes; };
+        auto sm_out = [&](int p) { return wg_base + (a.nmask + p) * slab_bytes; };
+        auto chunk_addr = [&](uint32_t buf, int j) {   // 16-byte chunk j of this thread's row, TMA swizzle applied
+            const uint32_t off = r * row_bytes + j * 16u;
+            return buf + (off ^ (((off >> 7) & swz) << 4));
+        };
+        const int barid = 2 + wg;
+        int sc = 0;   // slabs processed by this warpgroup (mask buffer / phase bookkeeping)
+        if (active && a.has_mask && lead_warp && blockIdx.x < a.total_tiles) {
+            int x0, y0, n0, co0;
+            tile_coords(blockIdx.x, x0, y0, n0, co0);
+            if (elect_one()) {
+                mbar_expect_tx(mfull(wg, 0), slab_bytes);
+                tma_load_5d(sm_mask(0), &tmM, mfull(wg, 0), co0 + wg * wcols, x0, y0, n0, 0);
             }
-            if (!valid) continue;
-            const int co = co0 + c;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float* f = v + 8 * h;
-                const int cc = co + 8 * h;
-                if (a.bias) {
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + cc));
-                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + cc + 4));
-                    f[0] += b0.x, f[1] += b0.y, f[2] += b0.z, f[3] += b0.w;
-                    f[4] += b1.x, f[5] += b1.y, f[6] += b1.z, f[7] += b1.w;
-                }
-                if (posrow) {
-                    const float4 p0 = __ldg(reinterpret_cast<const float4*>(posrow + cc));
-                    const float4 p1 = __ldg(reinterpret_cast<const float4*>(posrow + cc + 4));
-                    f[0] = fmaf(ps, p0.x, f[0]), f[1] = fmaf(ps, p0.y, f[1]), f[2] = fmaf(ps, p0.z, f[2]);
-                    f[3] = fmaf(ps, p0.w, f[3]), f[4] = fmaf(ps, p1.x, f[4]), f[5] = fmaf(ps, p1.y, f[5]);
-                    f[6] = fmaf(ps, p1.z, f[6]), f[7] = fmaf(ps, p1.w, f[7]);
-                }
-                if (a.act) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) f[j] = lrelu(f[j]);
-                }
-                const long long o = pix * a.Cout + cc;
-                if (a.has_mask) {
-                    float m[8];
-                    ld8(a.mask, o, m);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) f[j] *= lrelu_grad(m[j]);
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] *= a.out_scale;
-                split_store8(a.out, o, f);
+            __syncwarp();
+        }
+        int ti = 0;
+        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++ti) {
+            const int b = ti & 1;
+            int x0, y0, n0, co0;
+            tile_coords(t, x0, y0, n0, co0);
+            // stage this tile's bias slice while the main loop runs (buffer b: the other one may still be in use)
+            float* bs = bias_s + b * a.NT;
+            if (a.bias) {
+                for (int i = threadIdx.x; i < a.NT; i += kEpiWarps * 32) bs[i] = __ldg(a.bias + co0 + i);
             }
+            named_bar_sync(1, kEpiWarps * 32);
+            const int n = n0 + pn, x = x0 + px, y = y0 + py;
+            const bool valid = n < a.N;
+            const float ps = (a.posT && valid) ? __ldg(a.pos_s + n) : 0.f;
+            const float* posrow = a.posT ? a.posT + (long long)(y * a.W + x) * a.Cout : nullptr;
+            mbar_wait(tfull(b), (ti >> 1) & 1);
+            fence_after();
+            const uint32_t trow = tmem + b * acc_cols + ((uint32_t)(q * 32) << 16);
+            if (active) {
+                for (int sl = 0; sl < nslabs; ++sl, ++sc) {
+                    const int c0 = wg * wcols + sl * a.slab;   // first channel of the slab within the tile
+                    if (a.has_mask) {
+                        if (lead_warp) {   // prefetch the next slab's mask (next tile's first slab at the end of a tile)
+                            int nx0 = x0, ny0 = y0, nn0 = n0, nco0 = co0, nsl = sl + 1;
+                            bool more = true;
+                            if (nsl == nslabs) {
+                                nsl = 0;
+                                more = t + (int)gridDim.x < a.total_tiles;
+                                if (more) tile_coords(t + gridDim.x, nx0, ny0, nn0, nco0);
+                            }
+                            if (more && elect_one()) {
+                                const int nb = (sc + 1) & 1;
+                                mbar_expect_tx(mfull(wg, nb), slab_bytes);
+                                tma_load_5d(sm_mask(nb), &tmM, mfull(wg, nb), nco0 + wg * wcols + nsl * a.slab, nx0, ny0,
+                                            nn0, 0);
+                            }
+                            __syncwarp();
+                        }
+                        mbar_wait(mfull(wg, sc & 1), (sc >> 1) & 1);
+                    }
+                    // the previous slab's stores no longer read the staging tiles (bulk groups belong to the issuing
+                    // thread: elect.sync picks the same lane every time)
+                    if (lead_warp) {
+                        if (elect_one()) tma_store_wait_read();
+                        __syncwarp();
+                    }
+                    named_bar_sync(barid, 128);
+                    for (int cc = 0; cc < a.slab; cc += 16) {
+                        float v[16];
+                        tmem_ld16(trow + c0 + cc, v);
+                        if (SPLIT) {
+                            float w[16];
+                            tmem_ld16(trow + a.NT + c0 + cc, w);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] += w[j];
+                        }
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            float* f = v + 8 * h;
+                            const int cl = c0 + cc + 8 * h;          // channel within the tile
+                            const int jc = (cc >> 3) + h;             // 16-byte chunk within the slab row
+                            if (a.bias) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) f[j] += bs[cl + j];
+                            }
+                            if (posrow) {
+                                const float4 p0 = __ldg(reinterpret_cast<const float4*>(posrow + co0 + cl));
+                                const float4 p1 = __ldg(reinterpret_cast<const float4*>(posrow + co0 + cl + 4));
+                                f[0] = fmaf(ps, p0.x, f[0]), f[1] = fmaf(ps, p0.y, f[1]), f[2] = fmaf(ps, p0.z, f[2]);
+                                f[3] = fmaf(ps, p0.w, f[3]), f[4] = fmaf(ps, p1.x, f[4]), f[5] = fmaf(ps, p1.y, f[5]);
+                                f[6] = fmaf(ps, p1.z, f[6]), f[7] = fmaf(ps, p1.w, f[7]);
+                            }
+                            if (a.act) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) f[j] = lrelu(f[j]);
+                            }
+                            if (a.has_mask) {
+                                float m[8];
+                                unpack8(ld_shared_v4(chunk_addr(sm_mask(sc & 1), jc)), m);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) f[j] *= lrelu_grad(m[j]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] *= a.out_scale;
+                            for (int p = 0; p < a.Pout; ++p) {
+                                uint4 qv;
+                                qv.x = pack2(f[0], f[1]), qv.y = pack2(f[2], f[3]);
+                                qv.z = pack2(f[4], f[5]), qv.w = pack2(f[6], f[7]);
+                                st_shared_v4(chunk_addr(sm_out(p), jc), qv);
+                                if (p + 1 < a.Pout) {
+                                    float hv[8];
+                                    unpack8(qv, hv);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) f[j] -= hv[j];
+                                }
+                            }
+                        }
+                    }
+                    if (sl == nslabs - 1) {   // all TMEM reads of this buffer are complete: hand it back to the MMA warp
+                        fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty(b));
+                    }
+                    fence_proxy_async();
+                    named_bar_sync(barid, 128);
+                    if (lead_warp) {
+                        if (elect_one()) {
+                            for (int p = 0; p < a.Pout; ++p) tma_store_5d(&tmO, sm_out(p), co0 + c0, x0, y0, n0, p);
+                            tma_store_commit();
+                        }
+                        __syncwarp();
+                    }
+                }
+            } else {
+                fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty(b));
+            }
+        }
+        if (lead_warp) {
+            if (elect_one()) tma_store_wait_all();
+            __syncwarp();
         }
     }
     fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem, ncols);
+    if (warp == 9) tmem_dealloc(tmem, ncols);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -267,14 +430,15 @@ struct WgradTcArgs {
     float* dwp;
 };
 
+template <int P>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
                 const WgradTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;
-    const int P = a.P, S = a.S;
+    const int S = a.S;
     const uint32_t box_bytes = (uint32_t)a.PXS * 128u;
     const int gboxes = a.NT / 64;
     const uint32_t plane_bytes = (2 * S + gboxes) * box_bytes;   // [2S boxes of X | NT/64 boxes of G]
@@ -313,67 +477,92 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tptr - raw));
 
     if (warp == 4) {
-        if (lane == 0) {
+        {
+            // warp-uniform loop with counters only (see conv_tc_kernel); per-box tap offsets are computed once
+            int bc[16], bdx[16], bdy[16];
+            for (int b = 0; b < 2 * S; ++b) {
+                int rg = slab0 * 2 + b;
+                if (rg >= a.RG) rg = a.RG - 1;   // padding rows of the last slab: loaded, never stored
+                const int tap = rg / cchunks, cc = rg - tap * cchunks;
+                const int ky = tap / a.KS, kx = tap - ky * a.KS;
+                bc[b] = cc * 64, bdx[b] = kx - pad, bdy[b] = ky - pad;
+            }
+            // position of the first pixel block of this CTA
+            int grp = (int)(t_begin / a.tiles_per_group);
+            int u = (int)(t_begin - grp * a.tiles_per_group);
+            int smp, v = 0;
+            if (a.tiles_per_sample > 0) {
+                smp = u / a.tiles_per_sample;
+                v = u - smp * a.tiles_per_sample;
+            } else {
+                smp = u * a.TN;
+            }
+            int vy = v / a.tiles_x, vx = v - vy * a.tiles_x;
+            int s = 0;
+            uint32_t ph = 1;
             for (int it = 0; it < ntiles; ++it) {
-                const int s = it % a.stages;
-                mbar_wait(empty(s), ((it / a.stages) & 1) ^ 1);
-                mbar_expect_tx(full(s), stage_bytes);
-                const long long t = t_begin + it;
-                const int grp = (int)(t / a.tiles_per_group);
-                const int u = (int)(t - grp * a.tiles_per_group);
-                int smp, y0 = 0, x0 = 0;
-                if (a.tiles_per_sample > 0) {
-                    smp = u / a.tiles_per_sample;
-                    const int v = u - smp * a.tiles_per_sample;
-                    y0 = (v / a.tiles_x) << a.lh;
-                    x0 = (v % a.tiles_x) << a.lw;
-                } else {
-                    smp = u * a.TN;
-                }
+                mbar_wait_spin(empty(s), ph);
+                const uint32_t fb = full(s);
+                const int y0 = vy << a.lh, x0 = vx << a.lw;
                 const int xn = a.xoff[grp] + smp, gn = a.goff[grp] + smp;
                 const uint32_t dst = sbase + s * stage_bytes;
-                for (int p = 0; p < P; ++p) {
-                    const uint32_t pd = dst + p * plane_bytes;
-                    for (int b = 0; b < 2 * S; ++b) {
-                        int rg = slab0 * 2 + b;
-                        if (rg >= a.RG) rg = a.RG - 1;   // padding rows of the last slab: loaded, never stored
-                        const int tap = rg / cchunks, cc = rg - tap * cchunks;
-                        const int ky = tap / a.KS, kx = tap - ky * a.KS;
-                        tma_load_5d(pd + b * box_bytes, &tmX, full(s), cc * 64, x0 + kx - pad, y0 + ky - pad, xn, p);
+                if (elect_one()) {
+                    mbar_expect_tx(fb, stage_bytes);
+                    for (int p = 0; p < P; ++p) {
+                        const uint32_t pd = dst + p * plane_bytes;
+                        for (int b = 0; b < 2 * S; ++b)
+                            tma_load_5d(pd + b * box_bytes, &tmX, fb, bc[b], x0 + bdx[b], y0 + bdy[b], xn, p);
+                        for (int b = 0; b < gboxes; ++b)
+                            tma_load_5d(pd + (2 * S + b) * box_bytes, &tmG, fb, co0 + b * 64, x0, y0, gn, p);
                     }
-                    for (int b = 0; b < gboxes; ++b)
-                        tma_load_5d(pd + (2 * S + b) * box_bytes, &tmG, full(s), co0 + b * 64, x0, y0, gn, p);
                 }
+                __syncwarp();
+                if (++s == a.stages) s = 0, ph ^= 1;
+                // next pixel block
+                if (a.tiles_per_sample > 0) {
+                    if (++vx == a.tiles_x) {
+                        vx = 0;
+                        if (++vy == a.tiles_per_sample / a.tiles_x) vy = 0, ++smp;
+                    }
+                } else {
+                    smp += a.TN;
+                }
+                if (smp >= a.group_n) smp = 0, ++grp;
             }
         }
     } else if (warp == 5) {
-        if (lane == 0) {
-            const uint32_t idesc = idesc_bf16(a.NT, 1, 1);
-            const int ksteps = a.PXS / 16;
-            for (int it = 0; it < ntiles; ++it) {
-                const int s = it % a.stages;
-                mbar_wait(full(s), (it / a.stages) & 1);
-                fence_after();
-                const uint32_t st = sbase + s * stage_bytes;
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    for (int sl = 0; sl < S; ++sl) {
-                        uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+        const uint32_t idesc = idesc_bf16(a.NT, 1, 1);
+        const uint64_t dbase = smem_desc(0, box_bytes, 1024, 2);
+        const uint32_t pl16 = plane_bytes >> 4, bx16 = box_bytes >> 4;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < ntiles; ++it) {
+            mbar_wait_spin(full(s), ph);
+            fence_after();
+            const uint32_t st = (sbase + s * stage_bytes) >> 4;
+            const uint64_t bd0 = dbase | (st + 2 * S * bx16);
+            if (elect_one()) {
+                const uint32_t later = it > 0 ? 1u : 0u;
+                uint64_t ad_sl = dbase | st;
+                uint32_t d = tmem;
+                for (int sl = 0; sl < S; ++sl, ad_sl += 2 * bx16, d += a.NT) {
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {   // PXS = 32 pixels = two K = 16 steps
+#pragma unroll
                         for (int i = 0; i < P; ++i) {
-                            const uint64_t ad =
-                                smem_desc(st + i * plane_bytes + (2 * sl) * box_bytes + ks * 2048, box_bytes, 1024, 2);
-                            for (int j = 0; i + j < P; ++j) {
-                                const uint64_t bd = smem_desc(st + j * plane_bytes + (2 * S) * box_bytes + ks * 2048,
-                                                              box_bytes, 1024, 2);
-                                mma_bf16(tmem + sl * a.NT, ad, bd, idesc, acc);
-                                acc = 1;
-                            }
+#pragma unroll
+                            for (int j = 0; j < P - i; ++j)
+                                mma_bf16(d, ad_sl + (uint32_t)(i * pl16 + ks * 128), bd0 + (uint32_t)(j * pl16 + ks * 128),
+                                         idesc, (ks == 0 && i + j == 0) ? later : 1u);
                         }
                     }
                 }
                 mma_commit(empty(s));
             }
-            mma_commit(tfull);
+            __syncwarp();
+            if (++s == a.stages) s = 0, ph ^= 1;
         }
+        if (elect_one()) mma_commit(tfull);
         __syncwarp();
     } else {
         mbar_wait(tfull, 0);
@@ -413,7 +602,6 @@ __global__ void pack_operand_kernel(const float* __restrict__ w, int K, int Nn, 
     }
 }
 
-bool g_attr_conv = false, g_attr_wgrad = false;
 
 }  // namespace
 
@@ -441,19 +629,32 @@ extern "C" int pgk_conv_tc(const void* x, int P, int Pr, long long x_ps, int N, 
     a.lw = ilog2(TW), a.lh = ilog2(TH);
     a.tiles_x = W / TW, a.tiles_y = H / TH;
     const int tiles_n = (N + a.TN - 1) / a.TN;
-    a.NT = Cout < 256 ? Cout : 256;
+    // Full-precision passes (all planes read) keep the plane0 x plane0 products in their own accumulator; with two
+    // accumulator buffers in the 512 TMEM columns that allows 128 channels per tile, otherwise 256.
+    a.split_acc = (Pr > 1 && Pr == P) ? 1 : 0;
+    int nt_max = a.split_acc ? 128 : 256;
+    if (const char* e = getenv("PGK_CONV_NT")) nt_max = atoi(e) < nt_max ? atoi(e) : nt_max;   // tuning knob
+    a.NT = Cout < nt_max ? Cout : nt_max;
+    a.ntiles_n = Cout / a.NT;
+    a.total_tiles = a.tiles_x * a.tiles_y * tiles_n * a.ntiles_n;
+    a.Pout = P;
+    a.nmask = mask_ref ? 2 : 0;
+    const int wcols = a.NT >= 32 ? a.NT / 2 : a.NT;
+    a.slab = (wcols >= 32 && !(P == 3 && mask_ref)) ? 32 : 16;
+    const int epi_bytes = 2 * (a.nmask + a.Pout) * 128 * a.slab * 2 + 1024;
+    const int fixed = 1024 + 512 + 2 * 4 * a.NT + epi_bytes;
+    const int budget = kSmemLimit - fixed;
     a.bkb = 128;
     int stage_bytes = Pr * (128 * a.bkb + a.NT * a.bkb);
-    if (2 * stage_bytes + 2048 > kSmemLimit && Cin % 32 == 0) {   // three planes of a 256-wide tile: halve the K slice
+    if (budget / stage_bytes < 3 && Cin % 32 == 0) {   // keep the ring at least three deep: halve the K slice
         a.bkb = 64;
         stage_bytes = Pr * (128 * a.bkb + a.NT * a.bkb);
     }
-    // several CTAs per SM (bounded by TMEM columns and by >= 3 smem stages each): one tile's prologue / epilogue
-    // overlaps another tile's main loop
-    int ctas = 512 / (int)tmem_cols(Pr > 1 ? 2 * a.NT : a.NT);
-    if (ctas > 4) ctas = 4;
-    while (ctas > 1 && (kSmemLimit / ctas - 2048) / stage_bytes < 3) --ctas;
-    a.stages = (kSmemLimit / ctas - 2048) / stage_bytes;
+    if (const char* e = getenv("PGK_CONV_BKB")) {   // tuning knob
+        a.bkb = atoi(e);
+        stage_bytes = Pr * (128 * a.bkb + a.NT * a.bkb);
+    }
+    a.stages = budget / stage_bytes;
     if (a.stages > 8) a.stages = 8;
     PGK_REQUIRE(a.stages >= 1, "pgk_conv_tc: tile does not fit in shared memory");
     a.bias = bias, a.posT = posT, a.pos_s = pos_s, a.act = act;
@@ -474,23 +675,51 @@ extern "C" int pgk_conv_tc(const void* x, int P, int Pr, long long x_ps, int N, 
     }
     {
         const unsigned long long K = (unsigned long long)KS * KS * Cin;
-        unsigned long long dims[3] = {K, (unsigned long long)Cout, (unsigned long long)P};
-        unsigned long long str[2] = {2ull * K, P > 1 ? 2ull * wt_ps : 2ull * K * Cout};
+        unsigned long long dims[3] = {K, (unsigned long long)Cout, 3ull};
+        unsigned long long str[2] = {2ull * K, 2ull * wt_ps};
         unsigned box[3] = {(unsigned)(a.bkb / 2), (unsigned)a.NT, 1u};
         int rc = pgk_make_tmap(&tmB, wt, 3, dims, str, box, a.bkb, "pgk_conv_tc(w)");
         if (rc) return rc;
     }
-    const int smem = a.stages * stage_bytes + 1024 + 256;
-    if (!g_attr_conv) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    CUtensorMap tmO, tmM;
+    {
+        unsigned long long dims[5] = {(unsigned long long)Cout, (unsigned long long)W, (unsigned long long)H,
+                                      (unsigned long long)N, (unsigned long long)P};
+        unsigned long long str[4] = {2ull * Cout, 2ull * Cout * W, 2ull * Cout * W * H,
+                                     P > 1 ? 2ull * out_ps : 2ull * Cout * W * H * N};
+        unsigned box[5] = {(unsigned)a.slab, (unsigned)TW, (unsigned)TH, (unsigned)a.TN, 1u};
+        int rc = pgk_make_tmap(&tmO, out, 5, dims, str, box, a.slab * 2, "pgk_conv_tc(out)");
+        if (rc) return rc;
+        tmM = tmO;
+        if (mask_ref) {
+            str[3] = P > 1 ? 2ull * mask_ps : 2ull * Cout * W * H * N;
+            rc = pgk_make_tmap(&tmM, mask_ref, 5, dims, str, box, a.slab * 2, "pgk_conv_tc(mask)");
+            if (rc) return rc;
+        }
+    }
+    const int smem = a.stages * stage_bytes + fixed;
+    int grid = pgk_num_sms();
+    if (grid > a.total_tiles) grid = a.total_tiles;
+    typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvTcArgs);
+    kern_t kern = nullptr;
+    const int ks = a.bkb / 32;
+#define PGK_CONV_CASE(P_, K_, S_) \
+    if (Pr == P_ && ks == K_ && a.split_acc == S_) kern = conv_tc_kernel<P_, K_, S_>;
+    PGK_CONV_CASE(1, 4, 0) PGK_CONV_CASE(1, 2, 0)
+    PGK_CONV_CASE(2, 4, 0) PGK_CONV_CASE(2, 2, 0) PGK_CONV_CASE(2, 4, 1) PGK_CONV_CASE(2, 2, 1)
+    PGK_CONV_CASE(3, 4, 1) PGK_CONV_CASE(3, 2, 1)
+#undef PGK_CONV_CASE
+    PGK_REQUIRE(kern != nullptr, "pgk_conv_tc: no kernel instance for Pr %d ksteps %d split %d", Pr, ks, a.split_acc);
+    static bool attr_done[3][2][2] = {};
+    if (!attr_done[Pr - 1][ks == 4][a.split_acc]) {
+        cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e != cudaSuccess) {
             pgk_set_error("pgk_conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return PGK_ERR_CUDA;
         }
-        g_attr_conv = true;
+        attr_done[Pr - 1][ks == 4][a.split_acc] = true;
     }
-    dim3 grid((unsigned)(a.tiles_x * a.tiles_y * tiles_n), (unsigned)(Cout / a.NT));
-    conv_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, a);
+    kern<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, tmO, tmM, a);
     PGK_LAUNCH_CHECK("pgk_conv(tcgen05)");
     return PGK_OK;
 }
@@ -585,16 +814,19 @@ extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long l
         if (rc) return rc;
     }
     const int smem = a.stages * stage_bytes + 1024 + 256;
-    if (!g_attr_wgrad) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const WgradTcArgs);
+    kern_t kern = Pr == 1 ? wgrad_tc_kernel<1> : Pr == 2 ? wgrad_tc_kernel<2> : wgrad_tc_kernel<3>;
+    static bool attr_done[3] = {};
+    if (!attr_done[Pr - 1]) {
+        cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e != cudaSuccess) {
             pgk_set_error("pgk_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return PGK_ERR_CUDA;
         }
-        g_attr_wgrad = true;
+        attr_done[Pr - 1] = true;
     }
     dim3 grid((unsigned)sgroups, (unsigned)(Cout / a.NT), (unsigned)split);
-    wgrad_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmX, tmG, a);
+    kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmX, tmG, a);
     PGK_LAUNCH_CHECK("pgk_wgrad(tcgen05)");
     return PGK_OK;
 }
