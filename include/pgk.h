@@ -57,6 +57,7 @@ void pgk_reset_launch_count(void);
 #define PGK_PROF_WGRAD 1      /* weight gradient on tcgen05 (pgk_wgrad)              */
 #define PGK_PROF_CONV_SIMT 2  /* pgk_conv launches served by the CUDA-core kernel    */
 #define PGK_PROF_WGRAD_SIMT 3 /* pgk_wgrad launches served by the CUDA-core kernel   */
+#define PGK_PROF_CONV_THIN 4  /* pgk_conv launches served by the thin-layer tcgen05 kernel (Cin 8/16/32) */
 void pgk_prof_enable(int on);
 int pgk_prof_read(int family, double* flops, double* ms, long long* launches);
 void pgk_prof_reset(void);
@@ -73,6 +74,11 @@ int pgk_prep_weight(const float* w, float c, int kind, int cin, int cin_stride, 
 /* tensor-core operand: out[p][n][k] = bf16 plane p of w[k][n]  (w = wf or wb above, fp32 [K][Nn]; out: P planes,
  * out_ps elements apart, each [Nn][K] K-major -- what the TMA descriptors of pgk_conv read). */
 int pgk_pack_operand(const float* w, int K, int Nn, void* out, long long out_ps, int P, pgk_stream_t stream);
+/* the same for the thin-layer kernel (KS = 3, Cin in {8,16,32}, Cout in {8,16,32,64}): out = P planes of
+ * pgk_pack_thin_plane_elems(Cin, Cout) bf16 each, in the K = 16 step order of csrc/pgk_conv_thin.cu.  For such channel
+ * counts pgk_conv's `wt` must point to THIS packing (wt_ps = the plane size). */
+long long pgk_pack_thin_plane_elems(int Cin, int Cout);
+int pgk_pack_thin(const float* w, int Cin, int Cout, void* out, long long out_ps, int P, pgk_stream_t stream);
 /* inverse map for weight gradients: dw (PyTorch layout) (+)= c * dwp (wf layout). */
 int pgk_unprep_grad(const float* dwp, float c, int kind, int cin, int cin_stride, int cout, int ks,
                     float* dw, int accumulate, pgk_stream_t stream);
@@ -87,8 +93,9 @@ int pgk_unprep_grad(const float* dwp, float c, int kind, int cin, int cin_stride
  * The same entry point computes data gradients (x = output gradient, wf = wb of the layer,
  * mask_ref = the stored input activation of the layer) and the gradient-penalty's second chain.
  * wt / wt_ps: the same operand packed by pgk_pack_operand (3 planes).  Shapes with Cin % 64 == 0, Cout % 16 == 0,
- * power-of-two H, W and ups == 0 run on the TMA + tcgen05 kernel and read wt; all others run on the CUDA-core
- * implicit GEMM and read wf.  Either pointer may be NULL if the shape never takes that path.
+ * power-of-two H, W and ups == 0 run on the TMA + tcgen05 kernel and read wt; KS = 3 layers with Cin in {8,16,32},
+ * Cout in {8,16,32,64}, W % 128 == 0 run on the row-streaming thin-layer tcgen05 kernel and read wt in
+ * pgk_pack_thin's layout; all others run on the CUDA-core implicit GEMM and read wf.  Either pointer may be NULL if the shape never takes that path.
  * Pr (1 <= Pr <= P): how many planes of x and wt the tensor-core kernel READS (products of planes i + j < Pr).
  * Forward passes, whose values decide the LeakyReLU masks, use Pr = P; the gradient chains use Pr = min(P, 2)
  * (16 mantissa bits, three products instead of six) -- gradients are continuous in these operands. */

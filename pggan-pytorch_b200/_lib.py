@@ -20,6 +20,7 @@ SIGNATURES = {
     'pgk_prep_weight': [P, F, I, I, I, I, I, P, P],
     'pgk_unprep_grad': [P, F, I, I, I, I, I, P, I],
     'pgk_pack_operand': [P, I, I, P, L, I],
+    'pgk_pack_thin': [P, I, I, P, L, I],
     'pgk_conv': [P, I, I, L, I, I, I, I, I, I, I, P, P, L, P, P, P, I, P, L, F, P, L],
     'pgk_wgrad': [P, L, P, L, I, I, I, I, I, I, I, I, I, I, P, P, P],
     'pgk_bias_grad': [P, L, I, I, I, I, I, P, F, P, I],
@@ -81,6 +82,8 @@ def load():
                                   ctypes.POINTER(c_longlong)]
     lib.pgk_prof_read.restype = c_int
     lib.pgk_prof_reset.restype = None
+    lib.pgk_pack_thin_plane_elems.argtypes = [c_int, c_int]
+    lib.pgk_pack_thin_plane_elems.restype = c_longlong
     lib.pgk_set_tc.argtypes = [c_int]
     lib.pgk_set_tc.restype = None
     for name, args in SIGNATURES.items():
@@ -93,7 +96,7 @@ def load():
 
 def exported_symbols():
     return ['pgk_version', 'pgk_last_error', 'pgk_arch_check', 'pgk_launch_count', 'pgk_reset_launch_count',
-            'pgk_prof_enable', 'pgk_prof_read', 'pgk_prof_reset', 'pgk_set_tc'] + list(SIGNATURES)
+            'pgk_prof_enable', 'pgk_prof_read', 'pgk_prof_reset', 'pgk_set_tc', 'pgk_pack_thin_plane_elems'] + list(SIGNATURES)
 
 
 _checked_devices = set()

@@ -26,6 +26,11 @@ extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long l
                             int Cin, int Cout, int KS, int ngroups, int group_n, const int* xoff, const int* goff,
                             float* dwp, pgk_stream_t stream);
 
+extern "C" int pgk_conv_thin_supported(int N, int H, int W, int Cin, int Cout, int KS, int ups);
+extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N, int H, int W, int Cin, int Cout,
+                             const void* wpack, long long wpack_ps, const float* bias, int act, const void* mask_ref,
+                             long long mask_ps, float out_scale, void* out, long long out_ps, pgk_stream_t stream);
+
 // PGK_TC=0 in the environment (or pgk_set_tc(0)) routes every shape to the CUDA-core kernels (A/B comparisons)
 static int g_tc = -1;
 static bool tc_enabled() {
@@ -103,6 +108,11 @@ extern "C" int pgk_conv(const void* x, int P, int Pr, long long x_ps, int N, int
                         long long out_ps, pgk_stream_t stream) {
     PGK_REQUIRE(Pr >= 1 && Pr <= P, "pgk_conv: need 1 <= Pr <= P");
     const double flops = 2.0 * N * H * W * (double)Cout * KS * KS * Cin;
+    if (wt && !posT && tc_enabled() && pgk_conv_thin_supported(N, H, W, Cin, Cout, KS, ups)) {
+        ProfScope prof(PGK_PROF_CONV_THIN, flops, stream);
+        return pgk_conv_thin(x, P, Pr, x_ps, N, H, W, Cin, Cout, wt, wt_ps, bias, act, mask_ref, mask_ps, out_scale, out,
+                             out_ps, stream);
+    }
     if (wt && tc_enabled() && pgk_conv_tc_supported(N, H, W, Cin, Cout, KS, ups)) {
         ProfScope prof(PGK_PROF_CONV, flops, stream);
         return pgk_conv_tc(x, P, Pr, x_ps, N, H, W, Cin, Cout, KS, wt, wt_ps, bias, posT, pos_s, act, mask_ref, mask_ps,

@@ -1,0 +1,379 @@
+// pgk_conv_thin.cu -- 3x3 convolution (forward and data gradient) for the thin, high-resolution layers:
+// Cin in {8, 16, 32}, Cout in {8, 16, 32, 64}, W a multiple of 128 (the 256^2 ... 1024^2 levels, network.py:94-95 with
+// fmap_base 4096).  These layers are HBM-bound (9*Cin*Cout/(Cin+Cout) = 36 ... 190 flop per byte), so the kernel is
+// organised around touching every activation byte once:
+//
+//   * persistent CTAs stream image rows: a work unit is (sample, 128-pixel column strip, RC consecutive rows); the
+//     three input rows of an output row live in a shared-memory ring, and moving down one row loads ONE new row
+//     (TMA; out-of-range rows and the +-1 pixel halo are zero filled by the hardware = the conv's padding);
+//   * a row buffer is stored channel-group planar, [Cin/8][130 + pad pixels][8 channels]: one pixel of one channel
+//     group is 16 bytes, so 8 consecutive pixels are exactly one un-swizzled K-major UMMA core matrix, and the 9 taps
+//     are nothing but 9 start addresses ((dy row buffer) + (1 + dx) * 16 bytes) into the same bytes -- no im2col,
+//     no per-tap reload;  K = 16 per MMA is two channel groups (LBO = plane stride) or, for Cin = 8, two
+//     neighbouring taps (LBO = 16 bytes);
+//   * the whole weight tensor (<= 9*32*64 bf16 per plane) is staged once per CTA in UMMA layout;
+//   * accumulator 128 pixels x Npad channels in TMEM, double buffered; 4 epilogue warps apply bias / LeakyReLU /
+//     backward mask / scale, split into planes and store straight to global memory (a thread's pixel row is
+//     contiguous with its neighbours': fully coalesced without staging).
+#include <stdlib.h>
+
+#include "pgk_tc.cuh"
+
+using namespace tc;
+
+namespace {
+
+constexpr int kThinThreads = 192;   // warps 0-3 epilogue, 4 producer, 5 MMA issue
+constexpr int kMaxRing = 8;         // row buffers: 8, or 4 when the planes make a row large (power of two)
+constexpr int kRowPix = 136;        // 130 loaded pixels, padded so that every channel-group plane is 128-byte aligned
+constexpr int kCgBytes = kRowPix * 16;
+constexpr int kSmemLimit = 227 * 1024;
+
+struct ThinArgs {
+    int N, H, W, Cout, Npad;
+    int RC, chunks_y, strips;   // rows per unit, units per column strip, W / 128
+    int ring, ring_log2;
+    int total_units;
+    int Pout, split_acc;
+    const bf16* wpack;          // [P][STEPS][2][Npad][8]
+    const float* bias;
+    int act, has_mask;
+    Planes mask;
+    float out_scale;
+    Planes out;
+};
+
+template <int CIN>
+struct Steps {
+    static constexpr int CG = CIN / 8;
+    static constexpr int N = CIN == 8 ? 6 : 9 * (CIN / 16);
+};
+
+template <int CIN, int P, int SPLIT>
+__global__ void __launch_bounds__(kThinThreads, 1) conv_thin_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                    const ThinArgs a) {
+    constexpr int CG = Steps<CIN>::CG, STEPS = Steps<CIN>::N;
+    constexpr uint32_t plane_bytes = CG * kCgBytes;
+    constexpr uint32_t row_bytes = P * plane_bytes;
+    constexpr uint32_t tx_bytes = P * CG * 130 * 16;
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t sbase = (raw + 127u) & ~127u;
+    const int kRing = a.ring, kRingLog = a.ring_log2;
+    const uint32_t rows0 = sbase;                                 // kRing row buffers
+    const uint32_t w0 = rows0 + kRing * row_bytes;                // weights [P][STEPS][2][Npad][8]
+    const uint32_t wstep = (uint32_t)a.Npad * 32u, wplane = STEPS * wstep;
+    const uint32_t bars = (w0 + P * wplane + 15u) & ~15u;
+    auto rfull = [&](int s) { return bars + 8u * s; };
+    auto rempty = [&](int s) { return bars + 8u * (kMaxRing + s); };
+    auto afull = [&](int b) { return bars + 16u * kMaxRing + 8u * b; };
+    auto aempty = [&](int b) { return bars + 16u * kMaxRing + 16u + 8u * b; };
+    const uint32_t tptr = bars + 16u * kMaxRing + 32u;
+    float* bias_s = reinterpret_cast<float*>(smem_raw + (tptr + 16u - raw));
+
+    // ---- one-time setup: zero the row ring (padding pixels must be finite), stage weights and bias
+    for (uint32_t o = threadIdx.x * 16u; o < kRing * row_bytes; o += kThinThreads * 16u)
+        st_shared_v4(rows0 + o, make_uint4(0, 0, 0, 0));
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(a.wpack);
+        const uint32_t n16 = P * wplane / 16u;
+        for (uint32_t i = threadIdx.x; i < n16; i += kThinThreads) st_shared_v4(w0 + i * 16u, __ldg(src + i));
+    }
+    for (int i = threadIdx.x; i < a.Npad; i += kThinThreads) bias_s[i] = (a.bias && i < a.Cout) ? __ldg(a.bias + i) : 0.f;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kRing; ++s) {
+            mbar_init(rfull(s), 1);
+            mbar_init(rempty(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(afull(b), 1);
+            mbar_init(aempty(b), 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 4 && lane == 0) tma_prefetch_desc(&tmA);
+    const int acc_cols = SPLIT ? 2 * a.Npad : a.Npad;
+    const unsigned ncols = 2 * acc_cols <= 32 ? 32u : 2 * acc_cols <= 64 ? 64u : 2 * acc_cols <= 128 ? 128u : 256u;
+    if (warp == 5) tmem_alloc(tptr, ncols);
+    fence_proxy_async();   // generic-proxy writes (weights, zeroed ring) -> visible to the tensor core / TMA
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tptr - raw));
+
+    auto unit_coords = [&](int u, int& n, int& x0, int& ya) {
+        const int cy = u % a.chunks_y;
+        int r = u / a.chunks_y;
+        const int st = r % a.strips;
+        n = r / a.strips;
+        x0 = st * 128;
+        ya = cy * a.RC;
+    };
+
+    if (warp == 4) {
+        // ---- producer: one input row per step of the ring
+        uint32_t g = 0;
+        for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
+            int n, x0, ya;
+            unit_coords(u, n, x0, ya);
+            for (int j = 0; j < a.RC + 2; ++j, ++g) {
+                const int s = g & (kRing - 1);
+                mbar_wait_spin(rempty(s), ((g >> kRingLog) & 1) ^ 1);
+                if (elect_one()) {
+                    const uint32_t fb = rfull(s);
+                    mbar_expect_tx(fb, tx_bytes);
+                    const uint32_t dst = rows0 + s * row_bytes;
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+#pragma unroll
+                        for (int cg = 0; cg < CG; ++cg)
+                            tma_load_5d(dst + p * plane_bytes + cg * kCgBytes, &tmA, fb, cg * 8, x0 - 1, ya - 1 + j, n, p);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 5) {
+        // ---- MMA issue: per output row, STEPS x (products of planes) MMAs of 128 pixels x Npad x 16
+        const uint32_t idesc = idesc_bf16(a.Npad, 0, 0);
+        // A: 8 pixels x 16 B core matrices, SBO = 128 B to the next 8 pixels; LBO = distance between the two K halves
+        const uint64_t adesc_hi = smem_desc(0, CIN == 8 ? 16u : (uint32_t)kCgBytes, 128, 0);
+        const uint64_t bdesc0 = smem_desc(w0, (uint32_t)a.Npad * 16u, 128, 0);
+        const uint32_t wstep16 = wstep >> 4, wplane16 = wplane >> 4;
+        uint32_t g = 0, ti = 0;
+        for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
+            mbar_wait_spin(rfull(g & (kRing - 1)), (g >> kRingLog) & 1);
+            mbar_wait_spin(rfull((g + 1) & (kRing - 1)), ((g + 1) >> kRingLog) & 1);
+            for (int i = 0; i < a.RC; ++i, ++g, ++ti) {
+                mbar_wait_spin(rfull((g + 2) & (kRing - 1)), ((g + 2) >> kRingLog) & 1);
+                const int b = ti & 1;
+                mbar_wait_spin(aempty(b), ((ti >> 1) & 1) ^ 1);
+                fence_after();
+                const uint32_t d_main = tmem + b * acc_cols, d_corr = d_main + a.Npad;
+                uint32_t rb[3];
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) rb[dy] = (rows0 + ((g + dy) & (kRing - 1)) * row_bytes) >> 4;
+                if (elect_one()) {
+#pragma unroll
+                    for (int st = 0; st < STEPS; ++st) {
+                        // tap / channel-group pair of this K = 16 step
+                        int dy, xoff, cgp;
+                        if (CIN == 8) {
+                            dy = st >> 1, xoff = (st & 1) * 2, cgp = 0;      // (dx -1, dx 0) | (dx +1, zero weights)
+                        } else {
+                            const int tap = st / (CIN / 16);
+                            cgp = st % (CIN / 16);
+                            dy = tap / 3, xoff = tap % 3;
+                        }
+#pragma unroll
+                        for (int pi = 0; pi < P; ++pi) {
+#pragma unroll
+                            for (int pj = 0; pj < P - pi; ++pj) {
+                                const uint64_t ad =
+                                    adesc_hi | (uint64_t)(rb[dy] + (pi * plane_bytes + 2 * cgp * kCgBytes + xoff * 16) / 16);
+                                const uint64_t bd = bdesc0 + (uint32_t)(pj * wplane16 + st * wstep16);
+                                if (pi + pj == 0 || !SPLIT)
+                                    mma_bf16(d_main, ad, bd, idesc, (st == 0 && pi + pj == 0) ? 0u : 1u);
+                                else
+                                    mma_bf16(d_corr, ad, bd, idesc, (st == 0 && pi == 0 && pj == 1) ? 0u : 1u);
+                            }
+                        }
+                    }
+                    mma_commit(afull(b));
+                    mma_commit(rempty(g & (kRing - 1)));   // the top row of this window is done
+                    if (i == a.RC - 1) {
+                        mma_commit(rempty((g + 1) & (kRing - 1)));
+                        mma_commit(rempty((g + 2) & (kRing - 1)));
+                    }
+                }
+                __syncwarp();
+            }
+            g += 2;
+        }
+    } else {
+        // ---- epilogue: thread = pixel
+        const int r = warp * 32 + lane;
+        const uint32_t trow_off = (uint32_t)(warp * 32) << 16;
+        uint32_t ti = 0;
+        for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
+            int n, x0, ya;
+            unit_coords(u, n, x0, ya);
+            for (int i = 0; i < a.RC; ++i, ++ti) {
+                const int b = ti & 1;
+                const long long pix = ((long long)n * a.H + (ya + i)) * a.W + x0 + r;
+                mbar_wait(afull(b), (ti >> 1) & 1);
+                fence_after();
+                const uint32_t trow = tmem + b * acc_cols + trow_off;
+                for (int c = 0; c < a.Npad; c += 16) {
+                    float v[16], m[16];
+                    const long long o = pix * a.Cout + c;
+                    if (a.has_mask) {   // sign of plane 0 = sign of the value
+                        Planes m0 = a.mask;
+                        m0.P = 1;
+                        ld8(m0, o, m);
+                        if (c + 8 < a.Cout) ld8(m0, o + 8, m + 8);
+                    }
+                    tmem_ld16(trow + c, v);
+                    if (SPLIT) {
+                        float w[16];
+                        tmem_ld16(trow + a.Npad + c, w);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += w[j];
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (c + 8 * h >= a.Cout) break;
+                        float* f = v + 8 * h;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] += bias_s[c + 8 * h + j];
+                        if (a.act) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] = lrelu(f[j]);
+                        }
+                        if (a.has_mask) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] *= lrelu_grad(m[8 * h + j]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] *= a.out_scale;
+                        split_store8(a.out, o + 8 * h, f);
+                    }
+                }
+                fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(aempty(b));
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem, ncols);
+}
+
+// out[p][step][khalf][n][e] for the K = 16 steps of conv_thin_kernel; w = fp32 [9*Cin][Cout] (pgk_prep_weight's wf / wb)
+__global__ void pack_thin_kernel(const float* __restrict__ w, int Cin, int Cout, int Npad, int steps, Planes out) {
+    const int total = steps * 2 * Npad * 8;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int e = i & 7;
+        int r = i >> 3;
+        const int n = r % Npad;
+        r /= Npad;
+        const int h = r & 1, st = r >> 1;
+        int k = -1;
+        if (Cin == 8) {
+            const int dy = st >> 1, q = st & 1;
+            const int dx = q * 2 + h;
+            if (dx < 3) k = (dy * 3 + dx) * 8 + e;
+        } else {
+            const int per_tap = Cin / 16;
+            const int tap = st / per_tap, cgp = st % per_tap;
+            k = tap * Cin + cgp * 16 + h * 8 + e;
+        }
+        const float v = (k >= 0 && n < Cout) ? w[(long long)k * Cout + n] : 0.f;
+        st1(out, i, v);
+    }
+}
+
+}  // namespace
+
+extern "C" int pgk_conv_thin_supported(int N, int H, int W, int Cin, int Cout, int KS, int ups) {
+    if (ups || KS != 3) return 0;
+    if (Cin != 8 && Cin != 16 && Cin != 32) return 0;
+    if (Cout != 8 && Cout != 16 && Cout != 32 && Cout != 64) return 0;
+    if (W % 128 || H < 8 || H % 8) return 0;
+    return N > 0;
+}
+
+// number of bf16 elements of one plane of the packed operand
+extern "C" long long pgk_pack_thin_plane_elems(int Cin, int Cout) {
+    const int npad = Cout < 16 ? 16 : Cout;
+    const int steps = Cin == 8 ? 6 : 9 * (Cin / 16);
+    return (long long)steps * 2 * npad * 8;
+}
+
+extern "C" int pgk_pack_thin(const float* w, int Cin, int Cout, void* out, long long out_ps, int P,
+                             pgk_stream_t stream) {
+    PGK_REQUIRE((Cin == 8 || Cin == 16 || Cin == 32) && Cout % 8 == 0 && Cout >= 8 && Cout <= 64 && P >= 1 && P <= 3,
+                "pgk_pack_thin: unsupported shape (Cin %d Cout %d)", Cin, Cout);
+    const int npad = Cout < 16 ? 16 : Cout;
+    const int steps = Cin == 8 ? 6 : 9 * (Cin / 16);
+    const int total = steps * 2 * npad * 8;
+    pack_thin_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, Cin, Cout, npad, steps,
+                                                                           make_planes(out, out_ps, P));
+    PGK_LAUNCH_CHECK("pgk_pack_thin");
+    return PGK_OK;
+}
+
+template <int CIN, int P, int SPLIT>
+static int launch_thin(const CUtensorMap& tmA, const ThinArgs& a, int smem, cudaStream_t stream) {
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(conv_thin_kernel<CIN, P, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kSmemLimit);
+        if (e != cudaSuccess) {
+            pgk_set_error("pgk_conv_thin: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return PGK_ERR_CUDA;
+        }
+        attr = true;
+    }
+    int grid = pgk_num_sms();
+    if (grid > a.total_units) grid = a.total_units;
+    conv_thin_kernel<CIN, P, SPLIT><<<grid, kThinThreads, smem, stream>>>(tmA, a);
+    return PGK_OK;
+}
+
+// wpack: pgk_pack_thin output with 3 planes, wpack_ps elements apart
+extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N, int H, int W, int Cin, int Cout,
+                             const void* wpack, long long wpack_ps, const float* bias, int act, const void* mask_ref,
+                             long long mask_ps, float out_scale, void* out, long long out_ps, pgk_stream_t stream) {
+    PGK_REQUIRE(pgk_conv_thin_supported(N, H, W, Cin, Cout, 3, 0), "pgk_conv_thin: unsupported shape");
+    PGK_REQUIRE(P >= 1 && P <= 3 && Pr >= 1 && Pr <= P, "pgk_conv_thin: need 1 <= Pr <= P <= 3");
+    ThinArgs a;
+    a.N = N, a.H = H, a.W = W, a.Cout = Cout;
+    a.Npad = Cout < 16 ? 16 : Cout;
+    a.RC = H >= 32 ? 32 : H;
+    a.chunks_y = H / a.RC;
+    a.strips = W / 128;
+    a.total_units = N * a.strips * a.chunks_y;
+    a.Pout = P;
+    a.split_acc = (Pr > 1 && Pr == P) ? 1 : 0;
+    PGK_REQUIRE(wpack_ps == pgk_pack_thin_plane_elems(Cin, Cout), "pgk_conv_thin: wpack plane stride mismatch");
+    a.wpack = (const bf16*)wpack;
+    a.bias = bias, a.act = act;
+    a.has_mask = mask_ref != nullptr;
+    a.mask = make_planes(mask_ref, mask_ps, P);
+    a.out_scale = out_scale;
+    a.out = make_planes(out, out_ps, P);
+    const int steps = Cin == 8 ? 6 : 9 * (Cin / 16);
+    const int fixed = 128 + Pr * steps * a.Npad * 32 + 16 + 16 * kMaxRing + 64 + 4 * a.Npad + 64;
+    a.ring = 8, a.ring_log2 = 3;
+    if (fixed + a.ring * Pr * (Cin / 8) * kCgBytes > kSmemLimit) a.ring = 4, a.ring_log2 = 2;
+    const int smem = fixed + a.ring * Pr * (Cin / 8) * kCgBytes;
+    PGK_REQUIRE(smem <= kSmemLimit, "pgk_conv_thin: %d bytes of shared memory needed", smem);
+    CUtensorMap tmA;
+    {
+        unsigned long long dims[5] = {(unsigned long long)Cin, (unsigned long long)W, (unsigned long long)H,
+                                      (unsigned long long)N, (unsigned long long)P};
+        unsigned long long str[4] = {2ull * Cin, 2ull * Cin * W, 2ull * Cin * W * H,
+                                     P > 1 ? 2ull * x_ps : 2ull * Cin * W * H * N};
+        unsigned box[5] = {8u, 130u, 1u, 1u, 1u};
+        int rc = pgk_make_tmap(&tmA, x, 5, dims, str, box, 0, "pgk_conv_thin(x)");
+        if (rc) return rc;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = PGK_ERR_ARG;
+#define PGK_THIN_CASE(C_, P_, S_) \
+    if (Cin == C_ && Pr == P_ && a.split_acc == S_) rc = launch_thin<C_, P_, S_>(tmA, a, smem, st);
+    PGK_THIN_CASE(8, 1, 0) PGK_THIN_CASE(16, 1, 0) PGK_THIN_CASE(32, 1, 0)
+    PGK_THIN_CASE(8, 2, 0) PGK_THIN_CASE(16, 2, 0) PGK_THIN_CASE(32, 2, 0)
+    PGK_THIN_CASE(8, 2, 1) PGK_THIN_CASE(16, 2, 1) PGK_THIN_CASE(32, 2, 1)
+    PGK_THIN_CASE(8, 3, 1) PGK_THIN_CASE(16, 3, 1) PGK_THIN_CASE(32, 3, 1)
+#undef PGK_THIN_CASE
+    if (rc) {
+        if (rc == PGK_ERR_ARG) pgk_set_error("pgk_conv_thin: no kernel instance for Cin %d Pr %d", Cin, Pr);
+        return rc;
+    }
+    PGK_LAUNCH_CHECK("pgk_conv(thin tcgen05)");
+    return PGK_OK;
+}

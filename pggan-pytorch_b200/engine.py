@@ -193,12 +193,25 @@ class ConvW(object):
             kf, nf_, kb, nb = self.cin, 16 * self.cout, 16 * self.cout, self.cin
         else:
             kf, nf_, kb, nb = 16 * self.cin, self.cout, self.cout, 16 * self.cin
+        # thin layers (csrc/pgk_conv_thin.cu) take their own packing; the data-gradient operand swaps the roles
+        thin = lambda ci, co: self.kind == W_CONV and self.ks == 3 and ci in (8, 16, 32) and co in (8, 16, 32, 64)
+        thin_f, thin_b = thin(self.cin, self.cout), thin(self.cout, self.cin)
         if self.F is None or self.F[1].device != dev:
-            self.F = (self.wf, torch.empty((3, nf_, kf), dtype=BF16, device=dev))
-            self.B = (self.wb, torch.empty((3, nb, kb), dtype=BF16, device=dev)) if self.need_wb else None
-        call('pgk_pack_operand', self.wf.data_ptr(), kf, nf_, self.F[1].data_ptr(), self.F[1].stride(0), 3)
+            lib = _lib.load()
+            shp_f = (3, lib.pgk_pack_thin_plane_elems(self.cin, self.cout)) if thin_f else (3, nf_, kf)
+            shp_b = (3, lib.pgk_pack_thin_plane_elems(self.cout, self.cin)) if thin_b else (3, nb, kb)
+            self.F = (self.wf, torch.empty(shp_f, dtype=BF16, device=dev))
+            self.B = (self.wb, torch.empty(shp_b, dtype=BF16, device=dev)) if self.need_wb else None
+        if thin_f:
+            call('pgk_pack_thin', self.wf.data_ptr(), self.cin, self.cout, self.F[1].data_ptr(), self.F[1].stride(0), 3)
+        else:
+            call('pgk_pack_operand', self.wf.data_ptr(), kf, nf_, self.F[1].data_ptr(), self.F[1].stride(0), 3)
         if self.need_wb:
-            call('pgk_pack_operand', self.wb.data_ptr(), kb, nb, self.B[1].data_ptr(), self.B[1].stride(0), 3)
+            if thin_b:
+                call('pgk_pack_thin', self.wb.data_ptr(), self.cout, self.cin, self.B[1].data_ptr(),
+                     self.B[1].stride(0), 3)
+            else:
+                call('pgk_pack_operand', self.wb.data_ptr(), kb, nb, self.B[1].data_ptr(), self.B[1].stride(0), 3)
         if self.pos_hw is not None:
             call('pgk_prep_posbias', w.data_ptr(), self.mod.cf, self.cin_stride, self.cin, self.cout, self.pos_hw[0],
                  self.pos_hw[1], self.posT.data_ptr())

@@ -29,8 +29,12 @@ def conv_case(N, H, W, Cin, Cout, KS, P, act=1, mask=False, bias=True, scale=1.0
     x = torch.randn(N, Cin, H, W, device='cuda', generator=g)
     K = KS * KS * Cin
     wf = (torch.randn(K, Cout, device='cuda', generator=g) / K ** 0.5).contiguous()
-    wt = torch.empty(3, Cout, K, dtype=BF16, device='cuda')
-    call('pgk_pack_operand', wf.data_ptr(), K, Cout, wt.data_ptr(), wt.stride(0), 3)
+    if KS == 3 and Cin in (8, 16, 32) and Cout in (8, 16, 32, 64):
+        wt = torch.empty(3, lib.pgk_pack_thin_plane_elems(Cin, Cout), dtype=BF16, device='cuda')
+        call('pgk_pack_thin', wf.data_ptr(), Cin, Cout, wt.data_ptr(), wt.stride(0), 3)
+    else:
+        wt = torch.empty(3, Cout, K, dtype=BF16, device='cuda')
+        call('pgk_pack_operand', wf.data_ptr(), K, Cout, wt.data_ptr(), wt.stride(0), 3)
     b = torch.randn(Cout, device='cuda', generator=g) if bias else None
     xp = E.PT.from_float(x, P)
     m = E.PT.from_float(torch.randn(N, Cout, H, W, device='cuda', generator=g), P) if mask else None
@@ -114,6 +118,15 @@ def main():
         ok &= conv_case(40, 16, 16, 512, 512, 3, 3)
         ok &= conv_case(40, 16, 16, 512, 512, 3, 1)
         ok &= conv_case(300, 4, 4, 64, 64, 3, 1)
+    if what in ('thin', 'all'):
+        ok &= conv_case(1, 128, 128, 16, 16, 3, 1)
+        ok &= conv_case(2, 256, 256, 16, 16, 3, 3)
+        ok &= conv_case(1, 256, 256, 8, 8, 3, 1)
+        ok &= conv_case(1, 256, 256, 8, 16, 3, 3, mask=True, act=0, bias=False, scale=0.25, fwd=False)
+        ok &= conv_case(2, 128, 256, 32, 32, 3, 1, mask=True)
+        ok &= conv_case(1, 256, 256, 32, 64, 3, 3)
+        ok &= conv_case(1, 512, 512, 16, 8, 3, 1, mask=True, act=0, fwd=False)
+        ok &= conv_case(3, 128, 128, 32, 16, 3, 2)
     if what in ('wgrad', 'all'):
         ok &= wgrad_case(4, 16, 16, 64, 64, 3, 1)
         ok &= wgrad_case(4, 16, 16, 64, 64, 3, 3)
