@@ -58,6 +58,7 @@ void pgk_reset_launch_count(void);
 #define PGK_PROF_CONV_SIMT 2  /* pgk_conv launches served by the CUDA-core kernel    */
 #define PGK_PROF_WGRAD_SIMT 3 /* pgk_wgrad launches served by the CUDA-core kernel   */
 #define PGK_PROF_CONV_THIN 4  /* pgk_conv launches served by the thin-layer tcgen05 kernel (Cin 8/16/32) */
+#define PGK_PROF_WGRAD_THIN 5 /* pgk_wgrad launches served by the thin-layer tcgen05 kernel              */
 void pgk_prof_enable(int on);
 int pgk_prof_read(int family, double* flops, double* ms, long long* launches);
 void pgk_prof_reset(void);

@@ -31,6 +31,12 @@ extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N
                              const void* wpack, long long wpack_ps, const float* bias, int act, const void* mask_ref,
                              long long mask_ps, float out_scale, void* out, long long out_ps, pgk_stream_t stream);
 
+extern "C" int pgk_wgrad_thin_supported(int H, int W, int Cin, int Cout, int KS, int ups, int ngroups, int group_n,
+                                        int Pr);
+extern "C" int pgk_wgrad_thin(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W,
+                              int Cin, int Cout, int ngroups, int group_n, const int* xoff, const int* goff, float* dwp,
+                              pgk_stream_t stream);
+
 // PGK_TC=0 in the environment (or pgk_set_tc(0)) routes every shape to the CUDA-core kernels (A/B comparisons)
 static int g_tc = -1;
 static bool tc_enabled() {
@@ -128,6 +134,10 @@ extern "C" int pgk_wgrad(const void* x, long long x_ps, const void* g, long long
                          int Cin, int Cout, int KS, int ups, int ngroups, int group_n, const int* xoff, const int* goff,
                          float* dwp, pgk_stream_t stream) {
     const double flops = 2.0 * ngroups * group_n * H * W * (double)Cout * KS * KS * Cin;
+    if (tc_enabled() && pgk_wgrad_thin_supported(H, W, Cin, Cout, KS, ups, ngroups, group_n, Pr)) {
+        ProfScope prof(PGK_PROF_WGRAD_THIN, flops, stream);
+        return pgk_wgrad_thin(x, x_ps, g, g_ps, P, Pr, H, W, Cin, Cout, ngroups, group_n, xoff, goff, dwp, stream);
+    }
     if (tc_enabled() && pgk_wgrad_tc_supported(H, W, Cin, Cout, KS, ups, ngroups, group_n)) {
         ProfScope prof(PGK_PROF_WGRAD, flops, stream);
         return pgk_wgrad_tc(x, x_ps, g, g_ps, P, Pr, H, W, Cin, Cout, KS, ngroups, group_n, xoff, goff, dwp, stream);

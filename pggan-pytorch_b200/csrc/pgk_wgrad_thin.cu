@@ -1,0 +1,371 @@
+// pgk_wgrad_thin.cu -- weight gradient of the thin, high-resolution 3x3 layers (Cin in {8,16,32}, Cout in {8..64},
+// W a multiple of 128) on the tensor cores.
+//
+//   dW[ky][kx][ci][co] = sum over samples, y, x of  X[y+ky-1][x+kx-1][ci] * G[y][x][co]
+//
+// The reduction runs over pixels, so both operands must be K-major along x -- the transpose of how activations are
+// stored (channels innermost).  Per CTA (persistent, streaming rows like pgk_conv_thin.cu):
+//   warp 4      TMA: halo rows of X ([Cin/8][130+ px][8 ch], zero filled outside the image) and rows of G into raw rings;
+//   warps 0-3   transpose in shared memory with ldmatrix.trans + stmatrix (8x8 bf16 blocks): every X row once into
+//               XT3 = three copies shifted by kx, stacked along M (row m = kx*Cin + ci), every G row once into GT;
+//   warp 5      per output row y: D[ky] (3*Cin x Cout, fp32 in TMEM) += XT3[row y+ky-1] * GT[row y]^T, K = 128 pixels
+//               (8 MMAs of K = 16 per ky); the accumulators persist over ALL rows this CTA processes;
+//   warps 0-3   at the very end: TMEM -> fp32 atomics into dW[(ky*3+kx)*Cin + ci][co] (one flush per CTA).
+// Every activation byte is read from HBM once; the tensor-core work is tiny, the kernel is bound by HBM / the
+// shared-memory transposes.
+#include <stdlib.h>
+
+#include "pgk_tc.cuh"
+
+using namespace tc;
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kRowPix = 136;
+constexpr int kCgBytes = kRowPix * 16;   // one channel group of a raw X row
+constexpr int kGrp = 2048;               // one transposed 8-channel group: 16 pixel chunks x (8 ch x 8 px)
+constexpr int kSmemLimit = 227 * 1024;
+
+struct WThinArgs {
+    int H, W, Cout, Npad, CGO;
+    int RC, chunks_y, strips;
+    int ngroups, group_n;
+    int xoff[4], goff[4];
+    int total_units;
+    uint32_t off_gt, off_rawx, off_rawg, off_bars;   // byte offsets from the 1024-aligned base
+    float* dwp;
+};
+
+template <int CIN, int P>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WThinArgs a) {
+    constexpr int CG = CIN / 8, XG = 3 * CG;
+    constexpr uint32_t xt_plane = XG * kGrp, xt_buf = P * xt_plane;
+    constexpr uint32_t rawx_plane = CG * kCgBytes, rawx_slot = P * rawx_plane;
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t sbase = (raw + 1023u) & ~1023u;
+    const uint32_t gt_plane = (uint32_t)a.CGO * kGrp, gt_slot = P * gt_plane;
+    const uint32_t rawg_plane = gt_plane, rawg_slot = gt_slot;
+    const uint32_t xt0 = sbase, gt0 = sbase + a.off_gt, rawx0 = sbase + a.off_rawx, rawg0 = sbase + a.off_rawg;
+    const uint32_t bars = sbase + a.off_bars;
+    auto xfull = [&](int s) { return bars + 8u * s; };          // [2]
+    auto xempty = [&](int s) { return bars + 16u + 8u * s; };   // [2]
+    auto gfull = [&](int s) { return bars + 32u + 8u * s; };    // [2]
+    auto gempty = [&](int s) { return bars + 48u + 8u * s; };   // [2]
+    auto xtfull = [&](int s) { return bars + 64u + 8u * s; };   // [4]
+    auto xtempty = [&](int s) { return bars + 96u + 8u * s; };  // [4]
+    auto gtfull = [&](int s) { return bars + 128u + 8u * s; };  // [2]
+    auto gtempty = [&](int s) { return bars + 144u + 8u * s; }; // [2]
+    const uint32_t done = bars + 160u, tptr = bars + 168u;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(xfull(s), 1), mbar_init(xempty(s), 4);
+            mbar_init(gfull(s), 1), mbar_init(gempty(s), 4);
+            mbar_init(gtfull(s), 4), mbar_init(gtempty(s), 1);
+        }
+        for (int s = 0; s < 4; ++s) mbar_init(xtfull(s), 4), mbar_init(xtempty(s), 1);
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmG);
+    }
+    const unsigned ncols = 3 * a.Npad <= 64 ? 64u : 3 * a.Npad <= 128 ? 128u : 256u;
+    if (warp == 5) tmem_alloc(tptr, ncols);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tptr - raw));
+
+    auto unit_coords = [&](int u, int& xn, int& gn, int& x0, int& ya) {
+        const int cy = u % a.chunks_y;
+        int r = u / a.chunks_y;
+        const int st = r % a.strips;
+        r /= a.strips;
+        const int smp = r % a.group_n, grp = r / a.group_n;
+        xn = a.xoff[grp] + smp, gn = a.goff[grp] + smp;
+        x0 = st * 128, ya = cy * a.RC;
+    };
+
+    if (warp == 4) {
+        // ---- TMA producer: X row j of the unit, then (from j = 2) G row j - 2
+        uint32_t gx = 0, gg = 0;
+        for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
+            int xn, gn, x0, ya;
+            unit_coords(u, xn, gn, x0, ya);
+            for (int j = 0; j < a.RC + 2; ++j) {
+                {
+                    const int s = gx & 1;
+                    mbar_wait_spin(xempty(s), ((gx >> 1) & 1) ^ 1);
+                    if (elect_one()) {
+                        const uint32_t fb = xfull(s);
+                        mbar_expect_tx(fb, P * CG * 130 * 16);
+                        const uint32_t dst = rawx0 + s * rawx_slot;
+#pragma unroll
+                        for (int p = 0; p < P; ++p) {
+#pragma unroll
+                            for (int cg = 0; cg < CG; ++cg)
+                                tma_load_5d(dst + p * rawx_plane + cg * kCgBytes, &tmX, fb, cg * 8, x0 - 1, ya - 1 + j, xn, p);
+                        }
+                    }
+                    __syncwarp();
+                    ++gx;
+                }
+                if (j >= 2) {
+                    const int s = gg & 1;
+                    mbar_wait_spin(gempty(s), ((gg >> 1) & 1) ^ 1);
+                    if (elect_one()) {
+                        const uint32_t fb = gfull(s);
+                        mbar_expect_tx(fb, P * a.CGO * 128 * 16);
+                        const uint32_t dst = rawg0 + s * rawg_slot;
+#pragma unroll
+                        for (int p = 0; p < P; ++p)
+                            for (int cg = 0; cg < a.CGO; ++cg)
+                                tma_load_5d(dst + p * rawg_plane + cg * kGrp, &tmG, fb, cg * 8, x0, ya + j - 2, gn, p);
+                    }
+                    __syncwarp();
+                    ++gg;
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ---- MMA issue
+        const uint32_t idesc = idesc_bf16(a.Npad, 0, 0);
+        const uint64_t dhi = smem_desc(0, 128, kGrp, 0);   // K-major, no swizzle: LBO = next 8 pixels, SBO = next 8 rows
+        const uint32_t gtp16 = gt_plane >> 4;
+        uint32_t gx = 0, gg = 0, rows_done = 0;
+        for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
+            mbar_wait_spin(xtfull(gx & 3), (gx >> 2) & 1);
+            mbar_wait_spin(xtfull((gx + 1) & 3), ((gx + 1) >> 2) & 1);
+            for (int i = 0; i < a.RC; ++i, ++gx, ++gg, ++rows_done) {
+                mbar_wait_spin(xtfull((gx + 2) & 3), ((gx + 2) >> 2) & 1);
+                mbar_wait_spin(gtfull(gg & 1), (gg >> 1) & 1);
+                fence_after();
+                const uint64_t bd0 = dhi | ((gt0 + (gg & 1) * gt_slot) >> 4);
+                uint32_t xb[3];
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) xb[ky] = (xt0 + ((gx + ky) & 3) * xt_buf) >> 4;
+                if (elect_one()) {
+                    const uint32_t later = rows_done > 0 ? 1u : 0u;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const uint32_t d = tmem + ky * a.Npad;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+                            for (int pi = 0; pi < P; ++pi) {
+#pragma unroll
+                                for (int pj = 0; pj < P - pi; ++pj)
+                                    mma_bf16(d, dhi | (uint64_t)(xb[ky] + (pi * xt_plane + ks * 256) / 16),
+                                             bd0 + (uint32_t)(pj * gtp16 + ks * 16), idesc,
+                                             (ks == 0 && pi + pj == 0) ? later : 1u);
+                            }
+                        }
+                    }
+                    mma_commit(gtempty(gg & 1));
+                    mma_commit(xtempty(gx & 3));
+                    if (i == a.RC - 1) {
+                        mma_commit(xtempty((gx + 1) & 3));
+                        mma_commit(xtempty((gx + 2) & 3));
+                    }
+                }
+                __syncwarp();
+            }
+            gx += 2;
+        }
+        if (elect_one()) mma_commit(done);
+        __syncwarp();
+    } else {
+        // ---- transposers (warps 0-3): lane l addresses row l & 7 of matrix l >> 3
+        const int li = lane & 7, lj = lane >> 3;
+        uint32_t gx = 0, gg = 0;
+        for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
+            for (int j = 0; j < a.RC + 2; ++j) {
+                {
+                    const int s = gx & 1, b = gx & 3;
+                    mbar_wait(xfull(s), (gx >> 1) & 1);
+                    mbar_wait(xtempty(b), ((gx >> 2) & 1) ^ 1);
+                    const uint32_t src0 = rawx0 + s * rawx_slot, dst0 = xt0 + b * xt_buf;
+                    // ops: (plane, kx, channel group, 32-pixel block)
+                    for (int o = warp; o < P * 3 * CG * 4; o += 4) {
+                        const int blk = o & 3;
+                        int r = o >> 2;
+                        const int cg = r % CG;
+                        r /= CG;
+                        const int kx = r % 3, p = r / 3;
+                        uint32_t v[4];
+                        ldmatrix_x4_trans(src0 + p * rawx_plane + cg * kCgBytes + (blk * 32 + lj * 8 + li + kx) * 16, v);
+                        stmatrix_x4(dst0 + p * xt_plane + (kx * CG + cg) * kGrp + (blk * 4 + lj) * 128 + li * 16, v);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(xempty(s));
+                        mbar_arrive(xtfull(b));
+                    }
+                    ++gx;
+                }
+                if (j >= 2) {
+                    const int s = gg & 1;
+                    mbar_wait(gfull(s), (gg >> 1) & 1);
+                    mbar_wait(gtempty(s), ((gg >> 1) & 1) ^ 1);
+                    const uint32_t src0 = rawg0 + s * rawg_slot, dst0 = gt0 + s * gt_slot;
+                    for (int o = warp; o < P * a.CGO * 4; o += 4) {
+                        const int blk = o & 3;
+                        const int r = o >> 2;
+                        const int cg = r % a.CGO, p = r / a.CGO;
+                        uint32_t v[4];
+                        ldmatrix_x4_trans(src0 + p * rawg_plane + cg * kGrp + (blk * 32 + lj * 8 + li) * 16, v);
+                        stmatrix_x4(dst0 + p * gt_plane + cg * kGrp + (blk * 4 + lj) * 128 + li * 16, v);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(gempty(s));
+                        mbar_arrive(gtfull(s));
+                    }
+                    ++gg;
+                }
+            }
+        }
+        // ---- flush: accumulator row m = kx*Cin + ci of D[ky] -> dW[(ky*3 + kx)*Cin + ci][:]
+        mbar_wait(done, 0);
+        fence_after();
+        const int m = warp * 32 + lane;
+        const bool valid = m < 3 * CIN;
+        const int kx = m / CIN, ci = m - kx * CIN;
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        for (int ky = 0; ky < 3; ++ky) {
+            float* drow = a.dwp + (long long)((ky * 3 + kx) * CIN + ci) * a.Cout;
+            for (int c = 0; c < a.Npad; c += 16) {
+                float v[16];
+                tmem_ld16(trow + ky * a.Npad + c, v);
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c + j < a.Cout) atomicAdd(drow + c + j, v[j]);
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem, ncols);
+}
+
+}  // namespace
+
+static size_t wthin_layout(int Cin, int Cout, int Pr, WThinArgs* a) {
+    const int CG = Cin / 8, CGO = Cout / 8, npad = Cout < 16 ? 16 : Cout;
+    const size_t xt_buf = (size_t)Pr * 3 * CG * kGrp, gt_slot = (size_t)Pr * CGO * kGrp;
+    const size_t rawx_slot = (size_t)Pr * CG * kCgBytes, rawg_slot = gt_slot;
+    size_t off = 4 * xt_buf;
+    const size_t off_gt = off;
+    off += 2 * gt_slot;
+    const size_t off_rawx = off;
+    off += 2 * rawx_slot;
+    off = (off + 127) & ~(size_t)127;
+    const size_t off_rawg = off;
+    off += 2 * rawg_slot;
+    // the MMAs read 16 row groups of A (3*Cin/8 are real) and Npad/8 of B: keep those reads inside the allocation
+    size_t need = 3 * xt_buf + (size_t)(Pr - 1) * 3 * CG * kGrp + 16 * kGrp;
+    const size_t need_b = off_gt + gt_slot + (size_t)(Pr - 1) * CGO * kGrp + (size_t)(npad / 8) * kGrp;
+    if (need_b > need) need = need_b;
+    if (off < need) off = need;
+    off = (off + 15) & ~(size_t)15;
+    if (a) {
+        a->off_gt = (uint32_t)off_gt, a->off_rawx = (uint32_t)off_rawx, a->off_rawg = (uint32_t)off_rawg;
+        a->off_bars = (uint32_t)off;
+    }
+    return off + 256 + 1024;
+}
+
+extern "C" int pgk_wgrad_thin_supported(int H, int W, int Cin, int Cout, int KS, int ups, int ngroups, int group_n,
+                                        int Pr) {
+    if (ups || KS != 3) return 0;
+    if (Cin != 8 && Cin != 16 && Cin != 32) return 0;
+    if (Cout != 8 && Cout != 16 && Cout != 32 && Cout != 64) return 0;
+    if (W % 128 || H < 8 || H % 8) return 0;
+    if (Pr < 1 || Pr > 3) return 0;
+    return wthin_layout(Cin, Cout, Pr, nullptr) <= (size_t)kSmemLimit;
+}
+
+template <int CIN, int P>
+static int launch_wthin(const CUtensorMap& tmX, const CUtensorMap& tmG, const WThinArgs& a, int smem,
+                        cudaStream_t stream) {
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e =
+            cudaFuncSetAttribute(wgrad_thin_kernel<CIN, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        if (e != cudaSuccess) {
+            pgk_set_error("pgk_wgrad_thin: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return PGK_ERR_CUDA;
+        }
+        attr = true;
+    }
+    int grid = pgk_num_sms();
+    if (grid > a.total_units) grid = a.total_units;
+    wgrad_thin_kernel<CIN, P><<<grid, kThreads, smem, stream>>>(tmX, tmG, a);
+    return PGK_OK;
+}
+
+extern "C" int pgk_wgrad_thin(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W,
+                              int Cin, int Cout, int ngroups, int group_n, const int* xoff, const int* goff, float* dwp,
+                              pgk_stream_t stream) {
+    PGK_REQUIRE(pgk_wgrad_thin_supported(H, W, Cin, Cout, 3, 0, ngroups, group_n, Pr), "pgk_wgrad_thin: unsupported shape");
+    PGK_REQUIRE(P >= Pr && P <= 3 && ngroups >= 1 && ngroups <= 4, "pgk_wgrad_thin: bad planes / groups");
+    WThinArgs a;
+    a.H = H, a.W = W, a.Cout = Cout, a.Npad = Cout < 16 ? 16 : Cout, a.CGO = Cout / 8;
+    a.RC = H >= 32 ? 32 : H;
+    a.chunks_y = H / a.RC;
+    a.strips = W / 128;
+    a.ngroups = ngroups, a.group_n = group_n;
+    int xmax = 0, gmax = 0;
+    for (int i = 0; i < 4; ++i) {
+        a.xoff[i] = i < ngroups ? xoff[i] : 0;
+        a.goff[i] = i < ngroups ? goff[i] : 0;
+        if (a.xoff[i] > xmax) xmax = a.xoff[i];
+        if (a.goff[i] > gmax) gmax = a.goff[i];
+    }
+    a.total_units = ngroups * group_n * a.strips * a.chunks_y;
+    a.dwp = dwp;
+    const int smem = (int)wthin_layout(Cin, Cout, Pr, &a);
+    CUtensorMap tmX, tmG;
+    {
+        unsigned long long dims[5] = {(unsigned long long)Cin, (unsigned long long)W, (unsigned long long)H,
+                                      (unsigned long long)(xmax + group_n), (unsigned long long)P};
+        unsigned long long str[4] = {2ull * Cin, 2ull * Cin * W, 2ull * Cin * W * H,
+                                     P > 1 ? 2ull * x_ps : 2ull * Cin * W * H * (xmax + group_n)};
+        unsigned box[5] = {8u, 130u, 1u, 1u, 1u};
+        int rc = pgk_make_tmap(&tmX, x, 5, dims, str, box, 0, "pgk_wgrad_thin(x)");
+        if (rc) return rc;
+    }
+    {
+        unsigned long long dims[5] = {(unsigned long long)Cout, (unsigned long long)W, (unsigned long long)H,
+                                      (unsigned long long)(gmax + group_n), (unsigned long long)P};
+        unsigned long long str[4] = {2ull * Cout, 2ull * Cout * W, 2ull * Cout * W * H,
+                                     P > 1 ? 2ull * g_ps : 2ull * Cout * W * H * (gmax + group_n)};
+        unsigned box[5] = {8u, 128u, 1u, 1u, 1u};
+        int rc = pgk_make_tmap(&tmG, g, 5, dims, str, box, 0, "pgk_wgrad_thin(g)");
+        if (rc) return rc;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = PGK_ERR_ARG;
+#define PGK_WTHIN_CASE(C_, P_) \
+    if (Cin == C_ && Pr == P_) rc = launch_wthin<C_, P_>(tmX, tmG, a, smem, st);
+    PGK_WTHIN_CASE(8, 1) PGK_WTHIN_CASE(16, 1) PGK_WTHIN_CASE(32, 1)
+    PGK_WTHIN_CASE(8, 2) PGK_WTHIN_CASE(16, 2) PGK_WTHIN_CASE(32, 2)
+    PGK_WTHIN_CASE(8, 3) PGK_WTHIN_CASE(16, 3) PGK_WTHIN_CASE(32, 3)
+#undef PGK_WTHIN_CASE
+    if (rc) {
+        if (rc == PGK_ERR_ARG) pgk_set_error("pgk_wgrad_thin: no kernel instance for Cin %d Pr %d", Cin, Pr);
+        return rc;
+    }
+    PGK_LAUNCH_CHECK("pgk_wgrad(thin tcgen05)");
+    return PGK_OK;
+}

@@ -67,6 +67,7 @@ def conv_case(N, H, W, Cin, Cout, KS, P, act=1, mask=False, bias=True, scale=1.0
 
 
 def wgrad_case(N, H, W, Cin, Cout, KS, P, ngroups=1):
+    # (the engine reads min(P, 2) planes for weight gradients)
     g = torch.Generator(device='cuda').manual_seed(N * 1000 + H + Cin + Cout)
     ntot = N * ngroups + 2
     x = torch.randn(ntot, Cin, H, W, device='cuda', generator=g)
@@ -93,7 +94,7 @@ def wgrad_case(N, H, W, Cin, Cout, KS, P, ngroups=1):
                 tap = ky * KS + kx
                 ref[tap * Cin:(tap + 1) * Cin] += torch.einsum('nchw,nohw->co', patch, gs)
     e_tc, e_simt = rel(outs[1], ref), rel(outs[0], ref)
-    tol = {1: 2e-2, 2: 1e-4, 3: 2e-5}[P]
+    tol = {1: 2e-2, 2: 1e-4, 3: 1e-4}[P]
     flag = 'ok ' if e_tc < tol else 'BAD'
     print('%s wgrad N%d x%d groups %dx%d %d->%d k%d P%d: tc %.2e simt %.2e' % (flag, N, ngroups, H, W, Cin, Cout, KS, P, e_tc, e_simt))
     return e_tc < tol
@@ -127,6 +128,14 @@ def main():
         ok &= conv_case(1, 256, 256, 32, 64, 3, 3)
         ok &= conv_case(1, 512, 512, 16, 8, 3, 1, mask=True, act=0, fwd=False)
         ok &= conv_case(3, 128, 128, 32, 16, 3, 2)
+    if what in ('wthin', 'all'):
+        ok &= wgrad_case(1, 128, 128, 16, 16, 3, 1)
+        ok &= wgrad_case(2, 256, 256, 16, 16, 3, 2, ngroups=2)
+        ok &= wgrad_case(1, 256, 256, 8, 8, 3, 1, ngroups=3)
+        ok &= wgrad_case(1, 128, 256, 8, 16, 3, 3)
+        ok &= wgrad_case(2, 128, 128, 32, 32, 3, 1, ngroups=4)
+        ok &= wgrad_case(1, 256, 256, 32, 64, 3, 1)
+        ok &= wgrad_case(1, 512, 512, 16, 8, 3, 1)
     if what in ('wgrad', 'all'):
         ok &= wgrad_case(4, 16, 16, 64, 64, 3, 1)
         ok &= wgrad_case(4, 16, 16, 64, 64, 3, 3)
