@@ -51,8 +51,9 @@ long long pgk_launch_count(void);
 void pgk_reset_launch_count(void);
 /* per-launch device timing of the GEMM-shaped kernels (bench.py's roofline): while enabled, pgk_conv / pgk_wgrad
  * bracket their launch with CUDA events on `stream`.  pgk_prof_read synchronises on the recorded events and returns
- * the summed algorithmic FLOPs (2*M*N*K of each launch), the summed device milliseconds and the launch count of one
- * kernel family; pgk_prof_reset drops the records. */
+ * the summed algorithmic FLOPs (2*M*N*K of each launch), the summed algorithmic HBM bytes (operand planes read +
+ * output planes written, each once), the summed device milliseconds and the launch count of one kernel family;
+ * pgk_prof_reset drops the records. */
 #define PGK_PROF_CONV 0       /* forward conv / data gradient on tcgen05 (pgk_conv)  */
 #define PGK_PROF_WGRAD 1      /* weight gradient on tcgen05 (pgk_wgrad)              */
 #define PGK_PROF_CONV_SIMT 2  /* pgk_conv launches served by the CUDA-core kernel    */
@@ -60,7 +61,7 @@ void pgk_reset_launch_count(void);
 #define PGK_PROF_CONV_THIN 4  /* pgk_conv launches served by the thin-layer tcgen05 kernel (Cin 8/16/32) */
 #define PGK_PROF_WGRAD_THIN 5 /* pgk_wgrad launches served by the thin-layer tcgen05 kernel              */
 void pgk_prof_enable(int on);
-int pgk_prof_read(int family, double* flops, double* ms, long long* launches);
+int pgk_prof_read(int family, double* flops, double* bytes, double* ms, long long* launches);
 void pgk_prof_reset(void);
 /* 0 routes every shape to the CUDA-core kernels (A/B comparisons; also PGK_TC=0 in the environment). */
 void pgk_set_tc(int on);

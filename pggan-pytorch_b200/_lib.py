@@ -79,7 +79,7 @@ def load():
     lib.pgk_prof_enable.argtypes = [c_int]
     lib.pgk_prof_enable.restype = None
     lib.pgk_prof_read.argtypes = [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
-                                  ctypes.POINTER(c_longlong)]
+                                  ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_longlong)]
     lib.pgk_prof_read.restype = c_int
     lib.pgk_prof_reset.restype = None
     lib.pgk_pack_thin_plane_elems.argtypes = [c_int, c_int]
@@ -141,13 +141,13 @@ def prof_enable(on):
 
 
 def prof_read(family):
-    """(algorithmic FLOPs, device ms, launches) of one kernel family since the last prof_reset()."""
+    """(algorithmic FLOPs, algorithmic bytes, device ms, launches) of one kernel family since the last prof_reset()."""
     lib = load()
-    f, t, n = ctypes.c_double(), ctypes.c_double(), c_longlong()
-    rc = lib.pgk_prof_read(family, ctypes.byref(f), ctypes.byref(t), ctypes.byref(n))
+    f, b, t, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), c_longlong()
+    rc = lib.pgk_prof_read(family, ctypes.byref(f), ctypes.byref(b), ctypes.byref(t), ctypes.byref(n))
     if rc != 0:
         raise PgkError('pgk_prof_read failed: %s' % lib.pgk_last_error().decode())
-    return f.value, t.value, n.value
+    return f.value, b.value, t.value, n.value
 
 
 def prof_reset():

@@ -52,7 +52,7 @@ extern "C" void pgk_set_tc(int on) { g_tc = on ? 1 : 0; }
 namespace {
 struct ProfRec {
     cudaEvent_t e0, e1;
-    double flops;
+    double flops, bytes;
     int family;
 };
 bool g_prof = false;
@@ -62,9 +62,9 @@ struct ProfScope {
     bool on;
     cudaStream_t s;
     ProfRec r;
-    ProfScope(int family, double flops, pgk_stream_t stream) : on(g_prof), s((cudaStream_t)stream) {
+    ProfScope(int family, double flops, double bytes, pgk_stream_t stream) : on(g_prof), s((cudaStream_t)stream) {
         if (!on) return;
-        r.family = family, r.flops = flops;
+        r.family = family, r.flops = flops, r.bytes = bytes;
         cudaEventCreate(&r.e0);
         cudaEventCreate(&r.e1);
         cudaEventRecord(r.e0, s);
@@ -79,8 +79,8 @@ struct ProfScope {
 
 extern "C" void pgk_prof_enable(int on) { g_prof = on != 0; }
 
-extern "C" int pgk_prof_read(int family, double* flops, double* ms, long long* launches) {
-    double f = 0.0, t = 0.0;
+extern "C" int pgk_prof_read(int family, double* flops, double* bytes, double* ms, long long* launches) {
+    double f = 0.0, t = 0.0, b = 0.0;
     long long n = 0;
     for (auto& r : g_recs) {
         if (r.family != family) continue;
@@ -91,8 +91,9 @@ extern "C" int pgk_prof_read(int family, double* flops, double* ms, long long* l
             pgk_set_error("pgk_prof_read: %s", cudaGetErrorString(e));
             return PGK_ERR_CUDA;
         }
-        f += r.flops, t += dt, ++n;
+        f += r.flops, b += r.bytes, t += dt, ++n;
     }
+    if (bytes) *bytes = b;
     if (flops) *flops = f;
     if (ms) *ms = t;
     if (launches) *launches = n;
@@ -114,18 +115,20 @@ extern "C" int pgk_conv(const void* x, int P, int Pr, long long x_ps, int N, int
                         long long out_ps, pgk_stream_t stream) {
     PGK_REQUIRE(Pr >= 1 && Pr <= P, "pgk_conv: need 1 <= Pr <= P");
     const double flops = 2.0 * N * H * W * (double)Cout * KS * KS * Cin;
+    // algorithmic HBM bytes: read the planes of x that are used, write all planes of out, read one mask plane
+    const double bytes = 2.0 * N * H * W * ((double)Cin * Pr / (ups ? 4 : 1) + (double)Cout * P + (mask_ref ? Cout : 0));
     if (wt && !posT && tc_enabled() && pgk_conv_thin_supported(N, H, W, Cin, Cout, KS, ups)) {
-        ProfScope prof(PGK_PROF_CONV_THIN, flops, stream);
+        ProfScope prof(PGK_PROF_CONV_THIN, flops, bytes, stream);
         return pgk_conv_thin(x, P, Pr, x_ps, N, H, W, Cin, Cout, wt, wt_ps, bias, act, mask_ref, mask_ps, out_scale, out,
                              out_ps, stream);
     }
     if (wt && tc_enabled() && pgk_conv_tc_supported(N, H, W, Cin, Cout, KS, ups)) {
-        ProfScope prof(PGK_PROF_CONV, flops, stream);
+        ProfScope prof(PGK_PROF_CONV, flops, bytes, stream);
         return pgk_conv_tc(x, P, Pr, x_ps, N, H, W, Cin, Cout, KS, wt, wt_ps, bias, posT, pos_s, act, mask_ref, mask_ps,
                            out_scale, out, out_ps, stream);
     }
     PGK_REQUIRE(wf != nullptr, "pgk_conv: this shape runs on the CUDA-core kernel, which needs the fp32 operand wf");
-    ProfScope prof(PGK_PROF_CONV_SIMT, flops, stream);
+    ProfScope prof(PGK_PROF_CONV_SIMT, flops, bytes, stream);
     return pgk_conv_simt(x, P, x_ps, N, H, W, Cin, Cout, KS, ups, wf, bias, posT, pos_s, act, mask_ref, mask_ps,
                          out_scale, out, out_ps, stream);
 }
@@ -134,14 +137,15 @@ extern "C" int pgk_wgrad(const void* x, long long x_ps, const void* g, long long
                          int Cin, int Cout, int KS, int ups, int ngroups, int group_n, const int* xoff, const int* goff,
                          float* dwp, pgk_stream_t stream) {
     const double flops = 2.0 * ngroups * group_n * H * W * (double)Cout * KS * KS * Cin;
+    const double bytes = 2.0 * ngroups * group_n * H * W * ((double)Cin / (ups ? 4 : 1) + Cout) * Pr;
     if (tc_enabled() && pgk_wgrad_thin_supported(H, W, Cin, Cout, KS, ups, ngroups, group_n, Pr)) {
-        ProfScope prof(PGK_PROF_WGRAD_THIN, flops, stream);
+        ProfScope prof(PGK_PROF_WGRAD_THIN, flops, bytes, stream);
         return pgk_wgrad_thin(x, x_ps, g, g_ps, P, Pr, H, W, Cin, Cout, ngroups, group_n, xoff, goff, dwp, stream);
     }
     if (tc_enabled() && pgk_wgrad_tc_supported(H, W, Cin, Cout, KS, ups, ngroups, group_n)) {
-        ProfScope prof(PGK_PROF_WGRAD, flops, stream);
+        ProfScope prof(PGK_PROF_WGRAD, flops, bytes, stream);
         return pgk_wgrad_tc(x, x_ps, g, g_ps, P, Pr, H, W, Cin, Cout, KS, ngroups, group_n, xoff, goff, dwp, stream);
     }
-    ProfScope prof(PGK_PROF_WGRAD_SIMT, flops, stream);
+    ProfScope prof(PGK_PROF_WGRAD_SIMT, flops, bytes, stream);
     return pgk_wgrad_simt(x, x_ps, g, g_ps, P, H, W, Cin, Cout, KS, ups, ngroups, group_n, xoff, goff, dwp, stream);
 }

@@ -146,7 +146,9 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
         long long o = (long long)m * a.Cout + co;
         if (a.has_mask) {
             float r4[4];
-            ld4(a.mask, o, r4);
+            Planes m0 = a.mask;   // the sign of plane 0 is the sign of the value
+            m0.P = 1;
+            ld4(m0, o, r4);
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] *= lrelu_grad(r4[j]);
         }
@@ -420,7 +422,7 @@ extern "C" int pgk_bias_grad(const void* g, long long g_ps, int P, int HW, int C
         }
     }
     BiasArgs a;
-    a.g = make_planes(g, g_ps, P);
+    a.g = make_planes(g, g_ps, P > 2 ? 2 : P);   // gradients: 16 mantissa bits suffice (see pgk_conv: Pr)
     a.HW = HW, a.Cout = Cout, a.ngroups = ngroups, a.group_n = group_n;
     for (int i = 0; i < 4; ++i) a.goff[i] = i < ngroups ? goff[i] : 0;
     a.scale = scale;

@@ -205,7 +205,9 @@ __global__ void __launch_bounds__(256) rgb_expand_kernel(ExpandArgs a) {
         long long o = pix * a.K + chunk * 8;
         if (a.has_mask) {
             float m[8];
-            ld8(a.mask, o, m);
+            Planes m0 = a.mask;   // the sign of plane 0 is the sign of the value
+            m0.P = 1;
+            ld8(m0, o, m);
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] *= lrelu_grad(m[j]);
         }
@@ -444,7 +446,9 @@ __global__ void mask_mul_kernel(Planes src, int N, int H, int W, int C, int ups,
         long long o = pix * C + chunk * 8;
         if (has_ref) {
             float m[8];
-            ld8(ref, o, m);
+            Planes r0 = ref;   // the sign of plane 0 is the sign of the value
+            r0.P = 1;
+            ld8(r0, o, m);
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] *= scale * lrelu_grad(m[j]);
         } else {

@@ -150,6 +150,59 @@ def test_step_vs_oracle_fresh_inputs(gpu, depth, alpha, n, ch):
         assert rel_err(grads[k], v) < TOL, k
 
 
+@pytest.mark.parametrize('depth,alpha,n,precision', [(6, 0.5, 2, 'fp32'), (5, 1.0, 2, 'fp32'), (6, 1.0, 2, 'bf16')])
+def test_step_vs_oracle_high_resolution_thin_layers(gpu, depth, alpha, n, precision):
+    """128^2 / 256^2 levels with 16..64 feature maps: the layers served by the row-streaming thin-layer tensor-core
+    kernels (csrc/pgk_conv_thin.cu, pgk_wgrad_thin.cu) inside the full D step + G step, against the oracle."""
+    O, pg = gpu['O'], gpu['pg']
+    res, ch, fb, fm, lat = 256, 3, 2048, 64, 64
+    pgp = O.make_generator_params(res, ch, fmap_base=fb, fmap_max=fm, latent_size=lat, seed=5)
+    pdp = O.make_discriminator_params(res, ch, fmap_base=fb, fmap_max=fm, seed=6)
+    g = dict(resolution=res, channels=ch, fmap_base=fb, fmap_max=fm, latent=lat, pg=pgp, pd=pdp, depth=depth,
+             alpha=alpha)
+    G, D = gpu['build_pair'](g, precision=precision)
+    r = 4 * 2 ** depth
+    nb = O.n_blocks_for(res)
+    # Fixed inputs.  With millions of LeakyReLU units some pre-activation always lies within float noise of zero, and
+    # a unit that takes the other slope (here or in the reference on another BLAS) moves gradients by ~1e-3; the
+    # seeds below were picked (scanning on the CPU, see tests/_gpu_util.relu_margin) so that the smallest layers,
+    # where one flipped unit matters most, have margins clear of that noise.
+    seed = {6: 61, 5: 99}[depth]
+    gen = torch.Generator().manual_seed(seed)
+    z1, z2 = torch.randn(n, lat, generator=gen), torch.randn(n, lat, generator=gen)
+    real = torch.randn(n, ch, r, r, generator=gen)
+    mix = torch.rand(n, 1, generator=gen)
+    res_o = {'d': O.d_step_grads(pdp, pgp, real, z1, mix, depth, alpha, nb),
+             'g': O.g_step_grads(pgp, pdp, z2, depth, alpha, nb)}
+    cost_o, rl_o, fl_o, gd_o = res_o['d']
+    gcost_o, gg_o = res_o['g']
+    tol_v, tol_g = (TOL, TOL) if precision == 'fp32' else (5e-2, 2.5e-1)
+    pg._lib.prof_reset()
+    pg._lib.prof_enable(True)
+    pg.wgan_gp_loss.mixing_factors_override = mix
+    try:
+        cost, rl, fl = pg.wgan_gp_D_loss(D, G, real.cuda(), z1.cuda())
+        cost.backward()
+        gcost = pg.wgan_gp_G_loss(G, D, z2.cuda())
+        gcost.backward()
+    finally:
+        pg.wgan_gp_loss.mixing_factors_override = None
+        pg._lib.prof_enable(False)
+    thin_conv, thin_wgrad = pg._lib.prof_read(4)[3], pg._lib.prof_read(5)[3]
+    pg._lib.prof_reset()
+    assert thin_conv > 0 and thin_wgrad > 0, 'the thin-layer tensor-core kernels were not exercised'
+    assert rel_err(cost, cost_o) < tol_v and rel_err(rl, rl_o) < tol_v and rel_err(fl, fl_o) < tol_v
+    assert rel_err(gcost, gcost_o) < tol_v
+    gd, gg = gpu['named_grads'](D), gpu['named_grads'](G)
+    assert set(gd) == set(gd_o) and set(gg) == set(gg_o)
+    for k, v in gd_o.items():
+        if k == 'linear.bias' and precision == 'bf16':
+            continue   # a sum of +-1/N seeds: cancels to ~0, meaningless in relative terms at 8 mantissa bits
+        assert rel_err(gd[k], v) < tol_g, k
+    for k, v in gg_o.items():
+        assert rel_err(gg[k], v) < tol_g, k
+
+
 def test_bf16_mode_close_to_oracle(gpu):
     """bf16 mode (one plane): activations and gradients are rounded to 8 mantissa bits at every layer boundary, so
     the tolerance against the fp32 oracle is 5e-2 on losses / outputs and 1e-1 on gradients."""
