@@ -109,10 +109,13 @@ int pgk_conv(const void* x, int P, int Pr, long long x_ps, int N, int H, int W, 
 /* ---- weight gradient (cuDNN convolution_backward, weight part) --------------------------
  * dwp[tap*Cin+ci][co] += sum over the listed sample groups of X[..., ci] (shifted by tap) * g[..., co].
  * Groups: ngroups (<= 4) groups of group_n samples; group i reads x samples starting at xoff[i] and g samples
- * starting at goff[i].  dwp must be zeroed by the caller (fp32, wf layout). */
+ * starting at goff[i].  dwp must be zeroed by the caller (fp32, wf layout).
+ * db (optional): the layer's bias gradient db[co] += sum over the pixels of the groups whose bit is set in
+ * bias_groups of g[..., co] (also accumulated: the caller zeroes it).  The thin-layer kernel produces it as one more
+ * accumulator row of the same launch; the other kernels are followed by pgk_bias_grad. */
 int pgk_wgrad(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W, int Cin,
               int Cout, int KS, int ups, int ngroups, int group_n, const int* xoff, const int* goff, float* dwp,
-              pgk_stream_t stream);
+              float* db, unsigned bias_groups, pgk_stream_t stream);
 /* db[co] (+)= scale * sum over pixels of the listed sample groups of g[..., co]. */
 int pgk_bias_grad(const void* g, long long g_ps, int P, int HW, int Cout, int ngroups, int group_n, const int* goff,
                   float scale, float* db, int accumulate, pgk_stream_t stream);

@@ -34,8 +34,8 @@ extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N
 extern "C" int pgk_wgrad_thin_supported(int H, int W, int Cin, int Cout, int KS, int ups, int ngroups, int group_n,
                                         int Pr);
 extern "C" int pgk_wgrad_thin(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W,
-                              int Cin, int Cout, int ngroups, int group_n, const int* xoff, const int* goff, float* dwp,
-                              pgk_stream_t stream);
+                              int Cin, int cin_total, int c0, int Cout, int ngroups, int group_n, const int* xoff,
+                              const int* goff, float* dwp, float* db, unsigned bias_mask, pgk_stream_t stream);
 
 // PGK_TC=0 in the environment (or pgk_set_tc(0)) routes every shape to the CUDA-core kernels (A/B comparisons)
 static int g_tc = -1;
@@ -135,17 +135,34 @@ extern "C" int pgk_conv(const void* x, int P, int Pr, long long x_ps, int N, int
 
 extern "C" int pgk_wgrad(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W,
                          int Cin, int Cout, int KS, int ups, int ngroups, int group_n, const int* xoff, const int* goff,
-                         float* dwp, pgk_stream_t stream) {
+                         float* dwp, float* db, unsigned bias_groups, pgk_stream_t stream) {
+    PGK_REQUIRE(ngroups >= 1 && ngroups <= 4, "pgk_wgrad: 1..4 groups");
     const double flops = 2.0 * ngroups * group_n * H * W * (double)Cout * KS * KS * Cin;
     const double bytes = 2.0 * ngroups * group_n * H * W * ((double)Cin / (ups ? 4 : 1) + Cout) * Pr;
-    if (tc_enabled() && pgk_wgrad_thin_supported(H, W, Cin, Cout, KS, ups, ngroups, group_n, Pr)) {
+    // thin layers: the bias gradient rides along as one more accumulator row (a 64-channel input = two launches)
+    const int thin_cin = Cin == 64 ? 32 : Cin;
+    if (tc_enabled() && (Cin != 64 || Cout < 64) &&
+        pgk_wgrad_thin_supported(H, W, thin_cin, Cout, KS, ups, ngroups, group_n, Pr)) {
         ProfScope prof(PGK_PROF_WGRAD_THIN, flops, bytes, stream);
-        return pgk_wgrad_thin(x, x_ps, g, g_ps, P, Pr, H, W, Cin, Cout, ngroups, group_n, xoff, goff, dwp, stream);
+        for (int c0 = 0; c0 < Cin; c0 += thin_cin) {
+            int rc = pgk_wgrad_thin(x, x_ps, g, g_ps, P, Pr, H, W, thin_cin, Cin, c0, Cout, ngroups, group_n, xoff, goff,
+                                    dwp, c0 == 0 ? db : nullptr, bias_groups, stream);
+            if (rc) return rc;
+        }
+        return PGK_OK;
     }
+    int rc;
     if (tc_enabled() && pgk_wgrad_tc_supported(H, W, Cin, Cout, KS, ups, ngroups, group_n)) {
         ProfScope prof(PGK_PROF_WGRAD, flops, bytes, stream);
-        return pgk_wgrad_tc(x, x_ps, g, g_ps, P, Pr, H, W, Cin, Cout, KS, ngroups, group_n, xoff, goff, dwp, stream);
+        rc = pgk_wgrad_tc(x, x_ps, g, g_ps, P, Pr, H, W, Cin, Cout, KS, ngroups, group_n, xoff, goff, dwp, stream);
+    } else {
+        ProfScope prof(PGK_PROF_WGRAD_SIMT, flops, bytes, stream);
+        rc = pgk_wgrad_simt(x, x_ps, g, g_ps, P, H, W, Cin, Cout, KS, ups, ngroups, group_n, xoff, goff, dwp, stream);
     }
-    ProfScope prof(PGK_PROF_WGRAD_SIMT, flops, bytes, stream);
-    return pgk_wgrad_simt(x, x_ps, g, g_ps, P, H, W, Cin, Cout, KS, ups, ngroups, group_n, xoff, goff, dwp, stream);
+    if (rc || !db) return rc;
+    int boff[4], nb = 0;
+    for (int i = 0; i < ngroups; ++i)
+        if ((bias_groups >> i) & 1) boff[nb++] = goff[i];
+    if (nb == 0) return PGK_OK;
+    return pgk_bias_grad(g, g_ps, P, H * W, Cout, nb, group_n, boff, 1.0f, db, 1, stream);
 }

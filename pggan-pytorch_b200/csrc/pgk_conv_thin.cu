@@ -23,7 +23,8 @@ using namespace tc;
 
 namespace {
 
-constexpr int kThinThreads = 192;   // warps 0-3 epilogue, 4 producer, 5 MMA issue
+constexpr int kThinThreads = 320;   // warps 0-3 / 4-7: two epilogue warpgroups (even / odd tiles), 8 producer, 9 MMA issue
+constexpr int kAcc = 4;             // TMEM accumulator buffers: hides the MMA -> epilogue -> MMA round trip
 constexpr int kMaxRing = 8;         // row buffers: 8, or 4 when the planes make a row large (power of two)
 constexpr int kRowPix = 136;        // 130 loaded pixels, padded so that every channel-group plane is 128-byte aligned
 constexpr int kCgBytes = kRowPix * 16;
@@ -68,8 +69,8 @@ __global__ void __launch_bounds__(kThinThreads, 1) conv_thin_kernel(const __grid
     auto rfull = [&](int s) { return bars + 8u * s; };
     auto rempty = [&](int s) { return bars + 8u * (kMaxRing + s); };
     auto afull = [&](int b) { return bars + 16u * kMaxRing + 8u * b; };
-    auto aempty = [&](int b) { return bars + 16u * kMaxRing + 16u + 8u * b; };
-    const uint32_t tptr = bars + 16u * kMaxRing + 32u;
+    auto aempty = [&](int b) { return bars + 16u * kMaxRing + 8u * kAcc + 8u * b; };
+    const uint32_t tptr = bars + 16u * kMaxRing + 16u * kAcc;
     float* bias_s = reinterpret_cast<float*>(smem_raw + (tptr + 16u - raw));
 
     // ---- one-time setup: zero the row ring (padding pixels must be finite), stage weights and bias
@@ -86,16 +87,16 @@ __global__ void __launch_bounds__(kThinThreads, 1) conv_thin_kernel(const __grid
             mbar_init(rfull(s), 1);
             mbar_init(rempty(s), 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < kAcc; ++b) {
             mbar_init(afull(b), 1);
             mbar_init(aempty(b), 4);
         }
         fence_barrier_init();
     }
-    if (warp == 4 && lane == 0) tma_prefetch_desc(&tmA);
+    if (warp == 8 && lane == 0) tma_prefetch_desc(&tmA);
     const int acc_cols = SPLIT ? 2 * a.Npad : a.Npad;
-    const unsigned ncols = 2 * acc_cols <= 32 ? 32u : 2 * acc_cols <= 64 ? 64u : 2 * acc_cols <= 128 ? 128u : 256u;
-    if (warp == 5) tmem_alloc(tptr, ncols);
+    const unsigned ncols = kAcc * acc_cols <= 64 ? 64u : kAcc * acc_cols <= 128 ? 128u : kAcc * acc_cols <= 256 ? 256u : 512u;
+    if (warp == 9) tmem_alloc(tptr, ncols);
     fence_proxy_async();   // generic-proxy writes (weights, zeroed ring) -> visible to the tensor core / TMA
     fence_before();
     __syncthreads();
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(kThinThreads, 1) conv_thin_kernel(const __grid
         ya = cy * a.RC;
     };
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ---- producer: one input row per step of the ring
         uint32_t g = 0;
         for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(kThinThreads, 1) conv_thin_kernel(const __grid
                 __syncwarp();
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ---- MMA issue: per output row, STEPS x (products of planes) MMAs of 128 pixels x Npad x 16
         const uint32_t idesc = idesc_bf16(a.Npad, 0, 0);
         // A: 8 pixels x 16 B core matrices, SBO = 128 B to the next 8 pixels; LBO = distance between the two K halves
@@ -147,8 +148,8 @@ __global__ void __launch_bounds__(kThinThreads, 1) conv_thin_kernel(const __grid
             mbar_wait_spin(rfull((g + 1) & (kRing - 1)), ((g + 1) >> kRingLog) & 1);
             for (int i = 0; i < a.RC; ++i, ++g, ++ti) {
                 mbar_wait_spin(rfull((g + 2) & (kRing - 1)), ((g + 2) >> kRingLog) & 1);
-                const int b = ti & 1;
-                mbar_wait_spin(aempty(b), ((ti >> 1) & 1) ^ 1);
+                const int b = ti & (kAcc - 1);
+                mbar_wait_spin(aempty(b), ((ti / kAcc) & 1) ^ 1);
                 fence_after();
                 const uint32_t d_main = tmem + b * acc_cols, d_corr = d_main + a.Npad;
                 uint32_t rb[3];
@@ -192,17 +193,19 @@ __global__ void __launch_bounds__(kThinThreads, 1) conv_thin_kernel(const __grid
             g += 2;
         }
     } else {
-        // ---- epilogue: thread = pixel
-        const int r = warp * 32 + lane;
-        const uint32_t trow_off = (uint32_t)(warp * 32) << 16;
+        // ---- epilogue: thread = pixel; warpgroup wg takes the tiles with (tile index & 1) == wg
+        const int wg = warp >> 2, q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t trow_off = (uint32_t)(q * 32) << 16;
         uint32_t ti = 0;
         for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
             int n, x0, ya;
             unit_coords(u, n, x0, ya);
             for (int i = 0; i < a.RC; ++i, ++ti) {
-                const int b = ti & 1;
+                if ((int)(ti & 1) != wg) continue;
+                const int b = ti & (kAcc - 1);
                 const long long pix = ((long long)n * a.H + (ya + i)) * a.W + x0 + r;
-                mbar_wait(afull(b), (ti >> 1) & 1);
+                mbar_wait(afull(b), (ti / kAcc) & 1);
                 fence_after();
                 const uint32_t trow = tmem + b * acc_cols + trow_off;
                 for (int c = 0; c < a.Npad; c += 16) {
@@ -225,8 +228,12 @@ __global__ void __launch_bounds__(kThinThreads, 1) conv_thin_kernel(const __grid
                     for (int h = 0; h < 2; ++h) {
                         if (c + 8 * h >= a.Cout) break;
                         float* f = v + 8 * h;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) f[j] += bias_s[c + 8 * h + j];
+                        {
+                            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c + 8 * h);
+                            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c + 8 * h + 4);
+                            f[0] += b0.x, f[1] += b0.y, f[2] += b0.z, f[3] += b0.w;
+                            f[4] += b1.x, f[5] += b1.y, f[6] += b1.z, f[7] += b1.w;
+                        }
                         if (a.act) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) f[j] = lrelu(f[j]);
@@ -248,7 +255,7 @@ __global__ void __launch_bounds__(kThinThreads, 1) conv_thin_kernel(const __grid
     }
     fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem, ncols);
+    if (warp == 9) tmem_dealloc(tmem, ncols);
 }
 
 // out[p][step][khalf][n][e] for the K = 16 steps of conv_thin_kernel; w = fp32 [9*Cin][Cout] (pgk_prep_weight's wf / wb)
@@ -346,7 +353,7 @@ extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N
     a.out_scale = out_scale;
     a.out = make_planes(out, out_ps, P);
     const int steps = Cin == 8 ? 6 : 9 * (Cin / 16);
-    const int fixed = 128 + Pr * steps * a.Npad * 32 + 16 + 16 * kMaxRing + 64 + 4 * a.Npad + 64;
+    const int fixed = 128 + Pr * steps * a.Npad * 32 + 16 + 16 * kMaxRing + 16 * kAcc + 32 + 4 * a.Npad + 64;
     a.ring = 8, a.ring_log2 = 3;
     if (fixed + a.ring * Pr * (Cin / 8) * kCgBytes > kSmemLimit) a.ring = 4, a.ring_log2 = 2;
     const int smem = fixed + a.ring * Pr * (Cin / 8) * kCgBytes;

@@ -34,14 +34,18 @@ struct WThinArgs {
     int xoff[4], goff[4];
     int total_units;
     uint32_t off_gt, off_rawx, off_rawg, off_bars;   // byte offsets from the 1024-aligned base
+    int cin_total, c0;        // this launch handles input channels [c0, c0 + CIN) of cin_total
     float* dwp;
+    float* db;                // optional fused bias gradient: db[co] += sum over pixels of G (groups in bias_mask)
+    unsigned bias_mask;
 };
 
 template <int CIN, int P>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WThinArgs a) {
+    // row groups of XT3: 3 * CG shifted copies + one group whose first row is all ones (the bias-gradient row)
     constexpr int CG = CIN / 8, XG = 3 * CG;
-    constexpr uint32_t xt_plane = XG * kGrp, xt_buf = P * xt_plane;
+    constexpr uint32_t xt_plane = (XG + 1) * kGrp, xt_buf = P * xt_plane;
     constexpr uint32_t rawx_plane = CG * kCgBytes, rawx_slot = P * rawx_plane;
     extern __shared__ uint8_t smem_raw[];
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
@@ -75,6 +79,13 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmG);
     }
+    // the group holding the ones row: everything but row 0 of plane 0 stays zero for the whole kernel
+    for (uint32_t o = threadIdx.x * 16u; o < 4u * P * kGrp; o += kThreads * 16u) {
+        const uint32_t buf = o / (P * kGrp), rem = o - buf * (P * kGrp);
+        const uint32_t p = rem / kGrp, w = rem - p * kGrp;
+        st_shared_v4(xt0 + buf * xt_buf + p * xt_plane + XG * kGrp + w, make_uint4(0, 0, 0, 0));
+    }
+    fence_proxy_async();
     const unsigned ncols = 3 * a.Npad <= 64 ? 64u : 3 * a.Npad <= 128 ? 128u : 256u;
     if (warp == 5) tmem_alloc(tptr, ncols);
     fence_before();
@@ -90,6 +101,7 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int smp = r % a.group_n, grp = r / a.group_n;
         xn = a.xoff[grp] + smp, gn = a.goff[grp] + smp;
         x0 = st * 128, ya = cy * a.RC;
+        return grp;
     };
 
     if (warp == 4) {
@@ -110,7 +122,7 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                         for (int p = 0; p < P; ++p) {
 #pragma unroll
                             for (int cg = 0; cg < CG; ++cg)
-                                tma_load_5d(dst + p * rawx_plane + cg * kCgBytes, &tmX, fb, cg * 8, x0 - 1, ya - 1 + j, xn, p);
+                                tma_load_5d(dst + p * rawx_plane + cg * kCgBytes, &tmX, fb, a.c0 + cg * 8, x0 - 1, ya - 1 + j, xn, p);
                         }
                     }
                     __syncwarp();
@@ -185,6 +197,9 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int li = lane & 7, lj = lane >> 3;
         uint32_t gx = 0, gg = 0;
         for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
+            int xn_, gn_, x0_, ya_;
+            const int grp = unit_coords(u, xn_, gn_, x0_, ya_);
+            const uint32_t one16 = (a.db && ((a.bias_mask >> grp) & 1)) ? 0x3F803F80u : 0u;   // bf16 1.0 pairs
             for (int j = 0; j < a.RC + 2; ++j) {
                 {
                     const int s = gx & 1, b = gx & 3;
@@ -202,6 +217,8 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                         ldmatrix_x4_trans(src0 + p * rawx_plane + cg * kCgBytes + (blk * 32 + lj * 8 + li + kx) * 16, v);
                         stmatrix_x4(dst0 + p * xt_plane + (kx * CG + cg) * kGrp + (blk * 4 + lj) * 128 + li * 16, v);
                     }
+                    if (warp == 0 && lane < 16)   // the ones row (plane 0, row 0 of group XG), 16 pixel chunks
+                        st_shared_v4(dst0 + XG * kGrp + lane * 128, make_uint4(one16, one16, one16, one16));
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
@@ -241,7 +258,8 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int kx = m / CIN, ci = m - kx * CIN;
         const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
         for (int ky = 0; ky < 3; ++ky) {
-            float* drow = a.dwp + (long long)((ky * 3 + kx) * CIN + ci) * a.Cout;
+            float* drow = a.dwp + (long long)((ky * 3 + kx) * a.cin_total + a.c0 + ci) * a.Cout;
+            const bool bias_row = a.db && ky == 1 && m == 3 * CIN;   // the ones row against G of the same row
             for (int c = 0; c < a.Npad; c += 16) {
                 float v[16];
                 tmem_ld16(trow + ky * a.Npad + c, v);
@@ -249,6 +267,10 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
                         if (c + j < a.Cout) atomicAdd(drow + c + j, v[j]);
+                } else if (bias_row) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c + j < a.Cout) atomicAdd(a.db + c + j, v[j]);
                 }
             }
         }
@@ -262,7 +284,7 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
 static size_t wthin_layout(int Cin, int Cout, int Pr, WThinArgs* a) {
     const int CG = Cin / 8, CGO = Cout / 8, npad = Cout < 16 ? 16 : Cout;
-    const size_t xt_buf = (size_t)Pr * 3 * CG * kGrp, gt_slot = (size_t)Pr * CGO * kGrp;
+    const size_t xt_buf = (size_t)Pr * (3 * CG + 1) * kGrp, gt_slot = (size_t)Pr * CGO * kGrp;
     const size_t rawx_slot = (size_t)Pr * CG * kCgBytes, rawg_slot = gt_slot;
     size_t off = 4 * xt_buf;
     const size_t off_gt = off;
@@ -273,7 +295,7 @@ static size_t wthin_layout(int Cin, int Cout, int Pr, WThinArgs* a) {
     const size_t off_rawg = off;
     off += 2 * rawg_slot;
     // the MMAs read 16 row groups of A (3*Cin/8 are real) and Npad/8 of B: keep those reads inside the allocation
-    size_t need = 3 * xt_buf + (size_t)(Pr - 1) * 3 * CG * kGrp + 16 * kGrp;
+    size_t need = 3 * xt_buf + (size_t)(Pr - 1) * (3 * CG + 1) * kGrp + 16 * kGrp;
     const size_t need_b = off_gt + gt_slot + (size_t)(Pr - 1) * CGO * kGrp + (size_t)(npad / 8) * kGrp;
     if (need_b > need) need = need_b;
     if (off < need) off = need;
@@ -314,10 +336,14 @@ static int launch_wthin(const CUtensorMap& tmX, const CUtensorMap& tmG, const WT
     return PGK_OK;
 }
 
+// Cin: channels handled by this launch (8, 16 or 32), starting at channel c0 of an x tensor with cin_total channels
+// (a 64-channel input is two launches).  db (optional): fused bias gradient over the groups in bias_mask; db and dwp
+// are accumulated into (the caller zeroes them).
 extern "C" int pgk_wgrad_thin(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W,
-                              int Cin, int Cout, int ngroups, int group_n, const int* xoff, const int* goff, float* dwp,
-                              pgk_stream_t stream) {
+                              int Cin, int cin_total, int c0, int Cout, int ngroups, int group_n, const int* xoff,
+                              const int* goff, float* dwp, float* db, unsigned bias_mask, pgk_stream_t stream) {
     PGK_REQUIRE(pgk_wgrad_thin_supported(H, W, Cin, Cout, 3, 0, ngroups, group_n, Pr), "pgk_wgrad_thin: unsupported shape");
+    PGK_REQUIRE(c0 >= 0 && c0 % 8 == 0 && c0 + Cin <= cin_total, "pgk_wgrad_thin: bad channel window");
     PGK_REQUIRE(P >= Pr && P <= 3 && ngroups >= 1 && ngroups <= 4, "pgk_wgrad_thin: bad planes / groups");
     WThinArgs a;
     a.H = H, a.W = W, a.Cout = Cout, a.Npad = Cout < 16 ? 16 : Cout, a.CGO = Cout / 8;
@@ -333,14 +359,16 @@ extern "C" int pgk_wgrad_thin(const void* x, long long x_ps, const void* g, long
         if (a.goff[i] > gmax) gmax = a.goff[i];
     }
     a.total_units = ngroups * group_n * a.strips * a.chunks_y;
-    a.dwp = dwp;
+    a.dwp = dwp, a.db = db, a.bias_mask = bias_mask;
+    a.cin_total = cin_total, a.c0 = c0;
     const int smem = (int)wthin_layout(Cin, Cout, Pr, &a);
     CUtensorMap tmX, tmG;
     {
-        unsigned long long dims[5] = {(unsigned long long)Cin, (unsigned long long)W, (unsigned long long)H,
+        const unsigned long long Ct = (unsigned long long)cin_total;
+        unsigned long long dims[5] = {Ct, (unsigned long long)W, (unsigned long long)H,
                                       (unsigned long long)(xmax + group_n), (unsigned long long)P};
-        unsigned long long str[4] = {2ull * Cin, 2ull * Cin * W, 2ull * Cin * W * H,
-                                     P > 1 ? 2ull * x_ps : 2ull * Cin * W * H * (xmax + group_n)};
+        unsigned long long str[4] = {2ull * Ct, 2ull * Ct * W, 2ull * Ct * W * H,
+                                     P > 1 ? 2ull * x_ps : 2ull * Ct * W * H * (xmax + group_n)};
         unsigned box[5] = {8u, 130u, 1u, 1u, 1u};
         int rc = pgk_make_tmap(&tmX, x, 5, dims, str, box, 0, "pgk_wgrad_thin(x)");
         if (rc) return rc;

@@ -99,10 +99,13 @@ def conv(x, w, cout, ks, out, ups=0, bias=None, posT=None, pos_s=None, act=0, ma
     return out
 
 
-def wgrad(x, g, H, W, cin, cout, ks, ups, groups, group_n, dwp):
+def wgrad(x, g, H, W, cin, cout, ks, ups, groups, group_n, dwp, db=None, bias_goffs=()):
+    """dwp += sum over the (x offset, g offset) sample groups; db (optional, zeroed by the caller) += the bias gradient
+    over the groups whose g offset is listed in bias_goffs (fused into the same launch on the thin-layer path)."""
     xoff, goff = _ints([a for a, _ in groups]), _ints([b for _, b in groups])
-    call('pgk_wgrad', x.ptr, x.ps, g.ptr, g.ps, x.P, min(x.P, GRAD_PLANES), H, W, cin, cout, ks, ups, len(groups), group_n, xoff, goff,
-         dwp.data_ptr())
+    mask = sum(1 << i for i, (_, go) in enumerate(groups) if go in bias_goffs)
+    call('pgk_wgrad', x.ptr, x.ps, g.ptr, g.ps, x.P, min(x.P, GRAD_PLANES), H, W, cin, cout, ks, ups, len(groups),
+         group_n, xoff, goff, dwp.data_ptr(), None if db is None else db.data_ptr(), mask)
 
 
 def bias_grad(g, hw, cout, goffs, group_n, db, scale=1.0, accumulate=0):
@@ -225,12 +228,12 @@ class ConvW(object):
             self.dwp = torch.empty_like(self.wf)
         return self.dwp
 
-    def wgrad_into(self, grad, x, g, H, W, ups, groups, group_n):
-        """grad (PyTorch layout, fp32) <- c * sum_groups x (*) g."""
+    def wgrad_into(self, grad, x, g, H, W, ups, groups, group_n, db=None, bias_goffs=()):
+        """grad (PyTorch layout, fp32) <- c * sum_groups x (*) g;  db (zero-initialised) += bias gradient."""
         dwp = self.scratch()
         dwp.zero_()
         if self.kind == W_CONV:
-            wgrad(x, g, H, W, self.cin, self.cout, self.ks, ups, groups, group_n, dwp)
+            wgrad(x, g, H, W, self.cin, self.cout, self.ks, ups, groups, group_n, dwp, db, bias_goffs)
         elif self.kind == W_GFIRST:   # x: (n,1,1,cin), g: (n,1,1,16*cout)
             wgrad(x, g, 1, 1, self.cin, 16 * self.cout, 1, 0, groups, group_n, dwp)
         else:                          # x: (n,1,1,16*cin), g: (n,1,1,cout)
@@ -500,8 +503,8 @@ class DEngine(object):
 
         def conv_layer(mod, x, ua, res):
             w = self.cw(mod)
-            w.wgrad_into(gs[mod.conv.weight], x, ua, res, res, 0, groups, n)
-            bias_grad(ua, res * res, w.cout, bias_goffs, n, gs[mod.conv.bias])
+            w.wgrad_into(gs[mod.conv.weight], x, ua, res, res, 0, groups, n, db=gs[mod.conv.bias],
+                         bias_goffs=bias_goffs)
 
         if depth > 0:
             conv_layer(top.c1, T.t0, T.ua_t1, r)
@@ -652,8 +655,7 @@ class GEngine(object):
             hprev, hup, u1, u2 = T.acts[i]
             w2 = self.cw(b.c2)
             da2 = self._act_bwd(d, u2, T, 'b%dc2' % i)
-            w2.wgrad_into(gs[b.c2.conv.weight], u1, da2, res, res, 0, groups, n)
-            bias_grad(da2, res * res, w2.cout, [0], n, gs[b.c2.conv.bias])
+            w2.wgrad_into(gs[b.c2.conv.weight], u1, da2, res, res, 0, groups, n, db=gs[b.c2.conv.bias], bias_goffs=[0])
             d1 = conv(da2, w2.B, w2.cin, 3, PT.empty(n, res, res, w2.cin, P, dev))
             da1 = self._act_bwd(d1, u1, T, 'b%dc1' % i)
             if i == 0:
@@ -662,8 +664,7 @@ class GEngine(object):
                 bias_grad(da1, 16, w1.cout, [0], n, gs[b.c1.conv.bias])
                 break
             w1 = self.cw(b.c1)
-            w1.wgrad_into(gs[b.c1.conv.weight], hup, da1, res, res, 0, groups, n)
-            bias_grad(da1, res * res, w1.cout, [0], n, gs[b.c1.conv.bias])
+            w1.wgrad_into(gs[b.c1.conv.weight], hup, da1, res, res, 0, groups, n, db=gs[b.c1.conv.bias], bias_goffs=[0])
             d_up = conv(da1, w1.B, w1.cin, 3, PT.empty(n, res, res, w1.cin, P, dev))
             res //= 2
             d = PT.empty(n, res, res, w1.cin, P, dev)

@@ -26,9 +26,10 @@ def oracle_case(spec):
     depth, alpha, n, ch = int(v[0]), float(v[1]), int(v[2]), int(v[3])
     res, fb, fm, lat = (int(x) for x in (v[4:8] if len(v) >= 8 else (32, 512, 64, 64)))
     dt = torch.float64 if len(v) > 8 and v[8] == '64' else torch.float32
-    pgp = O.make_generator_params(res, ch, fmap_base=fb, fmap_max=fm, latent_size=lat, seed=3)
-    pdp = O.make_discriminator_params(res, ch, fmap_base=fb, fmap_max=fm, seed=4)
-    gen = torch.Generator().manual_seed(99)
+    sg, sd, sx = (int(x) for x in v[9:12]) if len(v) >= 12 else (3, 4, 99)
+    pgp = O.make_generator_params(res, ch, fmap_base=fb, fmap_max=fm, latent_size=lat, seed=sg)
+    pdp = O.make_discriminator_params(res, ch, fmap_base=fb, fmap_max=fm, seed=sd)
+    gen = torch.Generator().manual_seed(sx)
     r = 4 * 2 ** depth
     z1, z2 = torch.randn(n, lat, generator=gen), torch.randn(n, lat, generator=gen)
     real = torch.randn(n, ch, r, r, generator=gen)

@@ -79,9 +79,10 @@ def wgrad_case(N, H, W, Cin, Cout, KS, P, ngroups=1):
     for tcon in (0, 1):
         lib.pgk_set_tc(tcon)
         dwp = torch.zeros(K, Cout, device='cuda')
-        E.wgrad(xp, gp, H, W, Cin, Cout, KS, 0, groups, N, dwp)
+        db = torch.zeros(Cout, device='cuda')
+        E.wgrad(xp, gp, H, W, Cin, Cout, KS, 0, groups, N, dwp, db, [go for _, go in groups[:max(1, ngroups - 1)]])
         torch.cuda.synchronize()
-        outs.append(dwp)
+        outs.append(torch.cat([dwp.flatten(), db]))
     lib.pgk_set_tc(1)
     xd, gd = xp.float().to(REF), gp.float().to(REF)
     ref = torch.zeros(K, Cout, dtype=REF, device='cuda')
@@ -93,6 +94,8 @@ def wgrad_case(N, H, W, Cin, Cout, KS, P, ngroups=1):
                 patch = xs[:, :, ky:ky + H, kx:kx + W]
                 tap = ky * KS + kx
                 ref[tap * Cin:(tap + 1) * Cin] += torch.einsum('nchw,nohw->co', patch, gs)
+    dbref = sum(gd[go:go + N].sum(dim=(0, 2, 3)) for _, go in groups[:max(1, ngroups - 1)])
+    ref = torch.cat([ref.flatten(), dbref])
     e_tc, e_simt = rel(outs[1], ref), rel(outs[0], ref)
     tol = {1: 2e-2, 2: 1e-4, 3: 1e-4}[P]
     flag = 'ok ' if e_tc < tol else 'BAD'
@@ -136,6 +139,8 @@ def main():
         ok &= wgrad_case(2, 128, 128, 32, 32, 3, 1, ngroups=4)
         ok &= wgrad_case(1, 256, 256, 32, 64, 3, 1)
         ok &= wgrad_case(1, 512, 512, 16, 8, 3, 1)
+        ok &= wgrad_case(2, 256, 256, 64, 32, 3, 1, ngroups=2)
+        ok &= wgrad_case(1, 128, 128, 64, 16, 3, 2)
     if what in ('wgrad', 'all'):
         ok &= wgrad_case(4, 16, 16, 64, 64, 3, 1)
         ok &= wgrad_case(4, 16, 16, 64, 64, 3, 3)
