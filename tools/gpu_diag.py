@@ -98,6 +98,6 @@ def run_case(case, precision):
 if __name__ == '__main__':
     cases = sys.argv[1:] or STEP_CASES
     print(torch.cuda.get_device_name(0), torch.__version__)
-    for prec in ('fp32',):
+    for prec in (os.environ.get('PGK_DIAG_PRECISION', 'fp32'),):
         for c in cases:
             run_case(c, prec)
