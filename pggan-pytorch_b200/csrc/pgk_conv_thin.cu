@@ -344,7 +344,7 @@ extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N
     a.strips = W / 128;
     a.total_units = N * a.strips * a.chunks_y;
     a.Pout = P;
-    a.split_acc = (Pr > 1 && Pr == P) ? 1 : 0;
+    a.split_acc = Pr == 3 ? 1 : 0;
     PGK_REQUIRE(wpack_ps == pgk_pack_thin_plane_elems(Cin, Cout), "pgk_conv_thin: wpack plane stride mismatch");
     a.wpack = (const bf16*)wpack;
     a.bias = bias, a.act = act;
@@ -374,7 +374,6 @@ extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N
     if (Cin == C_ && Pr == P_ && a.split_acc == S_) rc = launch_thin<C_, P_, S_>(tmA, a, smem, st);
     PGK_THIN_CASE(8, 1, 0) PGK_THIN_CASE(16, 1, 0) PGK_THIN_CASE(32, 1, 0)
     PGK_THIN_CASE(8, 2, 0) PGK_THIN_CASE(16, 2, 0) PGK_THIN_CASE(32, 2, 0)
-    PGK_THIN_CASE(8, 2, 1) PGK_THIN_CASE(16, 2, 1) PGK_THIN_CASE(32, 2, 1)
     PGK_THIN_CASE(8, 3, 1) PGK_THIN_CASE(16, 3, 1) PGK_THIN_CASE(32, 3, 1)
 #undef PGK_THIN_CASE
     if (rc) {

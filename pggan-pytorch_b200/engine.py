@@ -22,6 +22,7 @@ from . import _lib
 
 call = _lib.call
 BF16 = torch.bfloat16
+GRAD_PLANES = 2   # planes carried by gradient tensors / read by the gradient chains (include/pgk.h, pgk_conv: Pr)
 W_CONV, W_GFIRST, W_DLAST = 0, 1, 2
 
 
@@ -61,6 +62,10 @@ class PT(object):
         assert H * W * C == self.per
         return PT(self.t, self.N, H, W, C, self.P, self.off, self.ntot)
 
+    def g(self):
+        """The same storage seen through the planes the gradient chains use (GRAD_PLANES: 16 mantissa bits)."""
+        return PT(self.t, self.N, self.H, self.W, self.C, min(self.P, GRAD_PLANES), self.off, self.ntot)
+
     def float(self):
         """fp32 N,C,H,W copy (tests / debugging only)."""
         v = self.t.view(self.P, self.ntot, self.H, self.W, self.C)[:, self.off:self.off + self.N].float().sum(0)
@@ -85,7 +90,6 @@ def _mask(m):
 # ---------------------------------------------------------------------------------------------
 # thin op wrappers (argument marshalling only)
 # ---------------------------------------------------------------------------------------------
-GRAD_PLANES = 2   # planes read by the gradient chains (see include/pgk.h, pgk_conv: Pr)
 
 
 def conv(x, w, cout, ks, out, ups=0, bias=None, posT=None, pos_s=None, act=0, mask=None, scale=1.0, fwd=False):
@@ -104,7 +108,8 @@ def wgrad(x, g, H, W, cin, cout, ks, ups, groups, group_n, dwp, db=None, bias_go
     over the groups whose g offset is listed in bias_goffs (fused into the same launch on the thin-layer path)."""
     xoff, goff = _ints([a for a, _ in groups]), _ints([b for _, b in groups])
     mask = sum(1 << i for i, (_, go) in enumerate(groups) if go in bias_goffs)
-    call('pgk_wgrad', x.ptr, x.ps, g.ptr, g.ps, x.P, min(x.P, GRAD_PLANES), H, W, cin, cout, ks, ups, len(groups),
+    pg_ = min(x.P, g.P, GRAD_PLANES)
+    call('pgk_wgrad', x.ptr, x.ps, g.ptr, g.ps, pg_, pg_, H, W, cin, cout, ks, ups, len(groups),
          group_n, xoff, goff, dwp.data_ptr(), None if db is None else db.data_ptr(), mask)
 
 
@@ -373,7 +378,7 @@ class DEngine(object):
     def backward_head(self, T, seed, wseed, gs):
         """Fills T.ua_l2, T.ua_l1, T.q and T.d_hin (gradient w.r.t. the last block's input, stddev term included)
         for all B samples.  gs: GradSet receiving linear.weight/bias grads (None = no parameter grads)."""
-        D, B, P = self.D, T.B, T.P
+        D, B, P = self.D, T.B, min(T.P, GRAD_PLANES)   # gradient tensors carry GRAD_PLANES planes
         dev = T.scores.device
         last = self.blk(1)
         wl1, wl2 = self.cw(last.c1), self.cw(last.c2, W_DLAST)
@@ -398,7 +403,7 @@ class DEngine(object):
     def backward_body(self, T, d_hin, n0, n1, g0):
         """d_hin: gradient at the last block's input for tape samples [n0, n1).  Writes the pre-activation gradients
         into the `ua` tensors of the tape at sample offset g0 (allocating them with Bt slots on first use)."""
-        P, dev, n = T.P, d_hin.t.device, n1 - n0
+        P, dev, n = min(T.P, GRAD_PLANES), d_hin.t.device, n1 - n0
         depth, alpha, fade = T.depth, T.alpha, T.fade
         top = self.blk(depth + 1)
 
@@ -438,12 +443,12 @@ class DEngine(object):
         """D's forward applied to v0 (fp32 n,C,r,r) with biases dropped and LeakyReLU replaced by the masks of the
         tape samples [m0, m0+n) (the mixed samples).  The v tensors are written into slot `vs` of the tape's
         activation buffers.  Returns the extra-channel value ev and w_h (the w-chain seed)."""
-        P, dev = T.P, v0.device
+        P, dev = min(T.P, GRAD_PLANES), v0.device
         n = v0.shape[0]
         depth, alpha, fade = T.depth, T.alpha, T.fade
         top = self.blk(depth + 1)
         m = lambda t: t.sl(m0, m0 + n)
-        v = lambda t: t.sl(vs, vs + n)
+        v = lambda t: t.sl(vs, vs + n).g()     # the v tensors live in the spare sample slots, GRAD_PLANES planes
         from_rgb(v0, top.fromRGB, v(T.t0), act=0, bias=False, mask=m(T.t0))
         if depth == 0:
             vh = v(T.t0)
@@ -485,7 +490,7 @@ class DEngine(object):
         """groups: (x sample offset, ua sample offset) pairs of group_n samples each for the layers below the last
         block; head_groups: the same for the last block's c1 / c2.  img_pairs: (image tensor, img_n0, ua offset)
         triples for fromRGB.  ev_pair = (coef vector (n), ua offset) adds the v-chain's extra-channel term."""
-        n, P = T.group_n, T.P
+        n, P = T.group_n, min(T.P, GRAD_PLANES)
         depth, alpha, fade = T.depth, T.alpha, T.fade
         top = self.blk(depth + 1)
         C = T.ximg.shape[1]
@@ -628,7 +633,7 @@ class GEngine(object):
     def backward(self, T, dimg, gs):
         """dimg: fp32 gradient w.r.t. the generated image; fills gs with every active parameter's gradient."""
         G = self.G
-        depth, alpha, fade, n, P = T.depth, T.alpha, T.fade, T.n, T.P
+        depth, alpha, fade, n, P = T.depth, T.alpha, T.fade, T.n, min(T.P, GRAD_PLANES)
         dev = dimg.device
         C = dimg.shape[1]
         res = dimg.shape[-1]
@@ -676,10 +681,10 @@ class GEngine(object):
 
     def _act_bwd(self, d, y, T, name):
         """gradient w.r.t. the conv output given the gradient w.r.t. the (lrelu -> pixelnorm) output y."""
-        out = PT.empty(y.N, y.H, y.W, y.C, y.P, y.t.device)
+        out = PT.empty(y.N, y.H, y.W, y.C, d.P, y.t.device)
         if self.G.pixelnorm:
             r = getattr(T, 'r_' + name)
-            call('pgk_pixelnorm_bwd', d.ptr, d.ps, y.ptr, y.ps, r.data_ptr(), y.P, y.N * y.H * y.W, y.C, out.ptr,
+            call('pgk_pixelnorm_bwd', d.ptr, d.ps, y.ptr, y.ps, r.data_ptr(), d.P, y.N * y.H * y.W, y.C, out.ptr,
                  out.ps)
         else:
             mask_mul(d, out, ref=y)

@@ -85,8 +85,8 @@ def wgan_gp_D_loss(D, G, real_images_in, fake_latents_in, iwass_lambda=10.0, iwa
          d_fake_loss.data_ptr(), norms.data_ptr(), gp.data_ptr(), v0.data_ptr(), cost.data_ptr())
     # second order: v-chain (adjoint of the u-chain) and the w-chain entering through MinibatchStddev
     ed.v_chain(T, v0, 2 * n, 3 * n)
-    v_l2 = T.l2.sl(3 * n, 4 * n)
-    call('pgk_colsum', v_l2.ptr, v_l2.ps, P, n, v_l2.C, 1.0, gs[D.linear.weight].data_ptr())
+    v_l2 = T.l2.sl(3 * n, 4 * n).g()
+    call('pgk_colsum', v_l2.ptr, v_l2.ps, v_l2.P, n, v_l2.C, 1.0, gs[D.linear.weight].data_ptr())
     ed.backward_body(T, T.w_h, 2 * n, 3 * n, 3 * n)
     top_pairs = [(ximg, 0, 0, True), (ximg, n, n, True), (ximg, 2 * n, 3 * n, True), (v0, 0, 2 * n, False)]
     low_pairs = None
