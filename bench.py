@@ -190,8 +190,8 @@ def main():
     G.precision = D.precision = cfg['precision']
     G.depth = D.depth = depth
     G.alpha = D.alpha = alpha
-    opt_g = torch.optim.Adam(G.parameters(), 1e-3, betas=(0.0, 0.99))
-    opt_d = torch.optim.Adam(D.parameters(), 1e-3, betas=(0.0, 0.99))
+    opt_g = pg.FusedAdam(G.parameters(), 1e-3, betas=(0.0, 0.99))      # train.py:148-149,195
+    opt_d = pg.FusedAdam(D.parameters(), 1e-3, betas=(0.0, 0.99))
     gen = torch.Generator(device=dev).manual_seed(1337 + rank)
     nbuf = 4
     reals = [torch.randn(n, ch, r, r, device=dev, generator=gen) for _ in range(nbuf)]

@@ -227,6 +227,19 @@ int pgk_pool_img(const float* img, int N, int C, int H, int W, int avg, float sc
 int pgk_unpool_img_add(const float* src, int N, int C, int H, int W, float scale, int accumulate, float* dst,
                        pgk_stream_t stream);
 
+/* ---- real-image preparation (the step just before the path) -----------------------------------
+ * dataset.py:60-67: alpha_fade (dataset.py:109-113: 2x2 box mean -> nearest upsample -> lerp by 1 - alpha, applied iff
+ * alpha < 1) followed by utils.adjust_dynamic_range (utils.py:24-30).  src: N,C,H,W uint8 (src_is_u8) or fp32. */
+int pgk_real_prep(const void* src, int src_is_u8, int N, int C, int H, int W, double alpha, double min_in,
+                  double max_in, double min_out, double max_out, float* out, pgk_stream_t stream);
+
+/* ---- optimizer (the step just after the path) ----------------------------------------------------
+ * torch.optim.Adam as wired by train.py:148-149,195 for every parameter with a gradient, in ONE launch.
+ * table (device): ntensors rows of 8 x 64-bit words {param ptr, grad ptr, exp_avg ptr, exp_avg_sq ptr, numel,
+ * float bits of lr / (1 - beta1^t), float bits of 1 / sqrt(1 - beta2^t), 0}; all tensors fp32 contiguous. */
+int pgk_adam_multi(const void* table, int ntensors, long long max_numel, float beta1, float beta2, float eps,
+                   pgk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -301,3 +301,31 @@ def adam_step(params, grads, state, lr, beta1=0.0, beta2=0.99, eps=1e-8):
         denom = st['v'].sqrt() / math.sqrt(bc2) + eps
         params[k] = params[k] - (lr / bc1) * st['m'] / denom
     return params
+
+
+# --------------------------------------------------------------------------
+# real-image preparation (the step just before the path)
+# --------------------------------------------------------------------------
+def alpha_fade(datapoint, alpha):
+    """DepthDataset.alpha_fade (dataset.py:109-113, 238-242), numpy: 2x2 box mean, nearest upsample, lerp by 1-alpha."""
+    import numpy as np
+    c, h, w = datapoint.shape
+    t = datapoint.reshape(c, h // 2, 2, w // 2, 2).mean((2, 4)).repeat(2, 1).repeat(2, 2)
+    return datapoint + (t - datapoint) * (1 - alpha)
+
+
+def adjust_dynamic_range(data, range_in, range_out):
+    """utils.adjust_dynamic_range (utils.py:24-30)."""
+    if range_in != range_out:
+        (min_in, max_in) = range_in
+        (min_out, max_out) = range_out
+        scale_factor = (max_out - min_out) / (max_in - min_in)
+        data = (data - min_in) * scale_factor + min_out
+    return data
+
+
+def prepare_real(datapoint, alpha, range_in, range_out):
+    """DepthDataset.__getitem__ after the pyramid lookup (dataset.py:60-67): fade iff alpha < 1, range, float32."""
+    if alpha < 1.0:
+        datapoint = alpha_fade(datapoint, alpha)
+    return adjust_dynamic_range(datapoint, range_in, range_out).astype('float32')

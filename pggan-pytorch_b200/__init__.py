@@ -3,7 +3,9 @@
 
     from pggan_b200 import Generator, Discriminator, wgan_gp_D_loss, wgan_gp_G_loss, Trainer, DepthManager
 """
+from .dataset import prepare_reals                                 # noqa: F401
 from .network import Discriminator, Generator, PGConv2d            # noqa: F401
+from .optim import FusedAdam                                       # noqa: F401
 from .plugins import DepthManager, LRScheduler, Plugin, lr_rampup, schedule  # noqa: F401
 from .trainer import Trainer                                       # noqa: F401
 from .utils import random_latents                                  # noqa: F401

@@ -51,6 +51,9 @@ SIGNATURES = {
     'pgk_fill': [P, L, F],
     'pgk_pool_img': [P, I, I, I, I, I, F, P],
     'pgk_unpool_img_add': [P, I, I, I, I, F, I, P],
+    'pgk_real_prep': [P, I, I, I, I, I, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                      ctypes.c_double, P],
+    'pgk_adam_multi': [P, I, L, F, F, F],
 }
 
 _lib = None

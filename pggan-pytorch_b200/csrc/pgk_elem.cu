@@ -1210,6 +1210,90 @@ extern "C" int pgk_pool_img(const float* img, int N, int C, int H, int W, int av
     return PGK_OK;
 }
 
+// real-image preparation on the device (reference dataset.py:60-67 with alpha_fade :109-113 and
+// utils.adjust_dynamic_range utils.py:24-30): t = nearest-upsample(2x2 box mean(d)); d' = d + (t - d)*(1 - alpha);
+// out = (d' - min_in) * (max_out - min_out)/(max_in - min_in) + min_out.
+// The arithmetic type follows the reference's numpy code: uint8 data is promoted to float64 there (mean() of an
+// integer array), float32 data stays float32 (python scalars do not promote it); every operation is rounded
+// separately as numpy does (no FMA contraction), so the float32 results agree to the last bit almost always.
+__device__ __forceinline__ double rmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double radd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float rmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float radd(float a, float b) { return __fadd_rn(a, b); }
+
+template <typename T, typename A>
+__global__ void real_prep_kernel(const T* __restrict__ src, long long planes, int H, int W, double one_minus_alpha_d,
+                                 int fade, double min_in_d, double scale_d, double min_out_d, int rescale, float* out) {
+    const long long total = planes * H * W;
+    const A oma = (A)one_minus_alpha_d, min_in = (A)min_in_d, scale = (A)scale_d, min_out = (A)min_out_d;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int x = (int)(i % W);
+        long long r = i / W;
+        int y = (int)(r % H);
+        long long pl = r / H;
+        A d = (A)src[i];
+        if (fade) {
+            const T* q = src + (pl * H + (y & ~1)) * W + (x & ~1);
+            A t = rmul(radd(radd((A)q[0], (A)q[1]), radd((A)q[W], (A)q[W + 1])), (A)0.25);
+            d = radd(d, rmul(radd(t, -d), oma));
+        }
+        if (rescale) d = radd(rmul(radd(d, -min_in), scale), min_out);
+        out[i] = (float)d;
+    }
+}
+
+extern "C" int pgk_real_prep(const void* src, int src_is_u8, int N, int C, int H, int W, double alpha, double min_in,
+                             double max_in, double min_out, double max_out, float* out, pgk_stream_t stream) {
+    PGK_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, "pgk_real_prep: empty tensor");
+    const int fade = alpha < 1.0;
+    PGK_REQUIRE(!fade || (H % 2 == 0 && W % 2 == 0), "pgk_real_prep: the fade needs even H, W");
+    PGK_REQUIRE(max_in != min_in, "pgk_real_prep: empty input range");
+    const int rescale = !(min_in == min_out && max_in == max_out);
+    const double scale = (max_out - min_out) / (max_in - min_in);
+    long long total = (long long)N * C * H * W;
+    unsigned grid = grid_cap((total + 255) / 256);
+    if (src_is_u8)
+        real_prep_kernel<unsigned char, double><<<grid, 256, 0, ST>>>((const unsigned char*)src, (long long)N * C, H, W,
+                                                              1.0 - alpha, fade, min_in, scale, min_out, rescale, out);
+    else
+        real_prep_kernel<float, float><<<grid, 256, 0, ST>>>((const float*)src, (long long)N * C, H, W, 1.0 - alpha, fade, min_in,
+                                                      scale, min_out, rescale, out);
+    PGK_LAUNCH_CHECK("pgk_real_prep");
+    return PGK_OK;
+}
+
+// multi-tensor Adam (torch.optim.Adam as wired by train.py:148-149,195: betas (0, 0.99), eps 1e-8, no weight decay).
+// One launch for every parameter that has a gradient.  table: n rows of 8 x 64-bit words
+//   {param ptr, grad ptr, exp_avg ptr, exp_avg_sq ptr, numel, step_size = lr/bc1 (float bits), 1/sqrt(bc2) (float bits), 0}
+__global__ void adam_multi_kernel(const unsigned long long* __restrict__ table, float beta1, float beta2, float eps) {
+    const unsigned long long* e = table + 8ull * blockIdx.y;
+    float* p = reinterpret_cast<float*>(e[0]);
+    const float* g = reinterpret_cast<const float*>(e[1]);
+    float* m = reinterpret_cast<float*>(e[2]);
+    float* v = reinterpret_cast<float*>(e[3]);
+    const long long n = (long long)e[4];
+    const float step_size = __uint_as_float((unsigned)e[5]), inv_sqrt_bc2 = __uint_as_float((unsigned)e[6]);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gi = g[i];
+        const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+        const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+        m[i] = mi, v[i] = vi;
+        p[i] -= step_size * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
+    }
+}
+
+extern "C" int pgk_adam_multi(const void* table, int ntensors, long long max_numel, float beta1, float beta2, float eps,
+                              pgk_stream_t stream) {
+    PGK_REQUIRE(ntensors > 0 && ntensors <= 65535 && max_numel > 0, "pgk_adam_multi: bad table size");
+    long long bx = (max_numel + 1023) / 1024;   // 4 elements per thread at the largest tensor, grid-stride beyond
+    if (bx > 2048) bx = 2048;
+    dim3 grid((unsigned)bx, (unsigned)ntensors);
+    adam_multi_kernel<<<grid, 256, 0, ST>>>((const unsigned long long*)table, beta1, beta2, eps);
+    PGK_LAUNCH_CHECK("pgk_adam_multi");
+    return PGK_OK;
+}
+
 extern "C" int pgk_unpool_img_add(const float* src, int N, int C, int H, int W, float scale, int accumulate, float* dst,
                                   pgk_stream_t stream) {
     long long total = (long long)N * C * H * W;

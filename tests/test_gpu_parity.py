@@ -238,3 +238,50 @@ def test_no_cpu_path(gpu):
     G, D = gpu['build_pair'](g)
     with pytest.raises(RuntimeError):
         G.cpu()(g['z1'])
+
+
+def test_real_preparation_golden(gpu):
+    """pgk_real_prep (on-device alpha_fade + adjust_dynamic_range) against the vectors produced by the
+    reference's own code.  uint8 data (float64 arithmetic in numpy, exact box sums): bit exact; float32 data (float32
+    arithmetic in numpy, whose 4-term summation order is an implementation detail): <= 1 float32 ulp."""
+    import os
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'fade.npz'))
+    pg = gpu['pg']
+    for i, (alpha, a0, a1, b0, b1) in enumerate(z['cases']):
+        x = torch.from_numpy(z['in%d' % i])
+        ref = torch.from_numpy(z['out%d' % i])
+        got = pg.prepare_reals(x.pin_memory(), alpha=float(alpha), range_in=(a0, a1), range_out=(b0, b1)).cpu()
+        assert got.dtype == torch.float32 and got.shape == ref.shape
+        if x.dtype == torch.uint8:
+            assert torch.equal(got, ref), i
+        else:
+            assert float((got - ref).abs().max()) <= 1.2e-7 * max(1.0, float(ref.abs().max())), i
+
+
+def test_fused_adam_matches_torch_adam(gpu):
+    """pgk_adam_multi vs torch.optim.Adam(betas=(0, .99)) over 5 steps, parameters without a
+    gradient skipped, LambdaLR driving the learning rate (train.py:148-158): <= 1e-6 relative on every parameter."""
+    pg = gpu['pg']
+    torch.manual_seed(0)
+    shapes = [(64, 33, 3, 3), (64,), (3, 64, 1, 1), (1, 512), (1,)]
+    pa = [torch.nn.Parameter(torch.randn(s, device='cuda')) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa = torch.optim.Adam(pa, 1e-3, betas=(0.0, 0.99))
+    ob = pg.FusedAdam(pb, 1e-3, betas=(0.0, 0.99))
+    sa = torch.optim.lr_scheduler.LambdaLR(oa, pg.lr_rampup)
+    sb = torch.optim.lr_scheduler.LambdaLR(ob, pg.lr_rampup)
+    for it in range(5):
+        for i, (a, b) in enumerate(zip(pa, pb)):
+            if i == 2 and it % 2 == 1:           # an inactive block: no gradient this step
+                a.grad = b.grad = None
+                continue
+            g = torch.randn_like(a) * (10.0 ** (it - 2))
+            a.grad, b.grad = g.clone(), g.clone()
+        oa.step()
+        ob.step()
+        sa.step(it * 8000)
+        sb.step(it * 8000)
+    for a, b in zip(pa, pb):
+        assert rel_err(b, a) < 1e-6
+    assert ob.state[pb[2]]['step'] == oa.state[pa[2]]['step'] == 3

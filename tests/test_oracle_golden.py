@@ -94,3 +94,16 @@ def test_lr_rampup_values():
     assert abs(1e-3 * O.lr_rampup(0) - 6.7379e-6) < 1e-9
     assert abs(1e-3 * O.lr_rampup(20000) - 2.8650e-4) < 1e-8
     assert O.lr_rampup(40000) == 1.0
+
+
+def test_real_preparation_matches_reference():
+    """oracle alpha_fade / adjust_dynamic_range vs vectors produced by the reference's own function bodies
+    (tests/golden/make_golden_fade.py): bit exact, same numpy arithmetic."""
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'fade.npz'))
+    for i, (alpha, a0, a1, b0, b1) in enumerate(z['cases']):
+        rin = (int(a0), int(a1)) if float(a0).is_integer() else (a0, a1)
+        rout = (int(b0), int(b1))
+        for d, ref in zip(z['in%d' % i], z['out%d' % i]):
+            got = O.prepare_real(d, float(alpha), rin, rout)
+            assert got.dtype == np.float32 and np.array_equal(got, ref), i
