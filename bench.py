@@ -145,6 +145,7 @@ def main():
     ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--graphs', action='store_true', help='replay the losses as CUDA graphs (wgan_gp_loss.cuda_graphs)')
     ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch of the config')
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
@@ -188,6 +189,7 @@ def main():
     shape = (1000, ch, cfg['res'], cfg['res'])
     G, D = pg.Generator(shape).to(dev), pg.Discriminator(shape).to(dev)
     G.precision = D.precision = cfg['precision']
+    pg.wgan_gp_loss.cuda_graphs = args.graphs     # measured: no gain -- the step is GPU-bound at every config
     G.depth = D.depth = depth
     G.alpha = D.alpha = alpha
     opt_g = pg.FusedAdam(G.parameters(), 1e-3, betas=(0.0, 0.99))      # train.py:148-149,195

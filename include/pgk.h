@@ -49,6 +49,8 @@ int pgk_arch_check(int device);
 /* number of kernels launched by this library since load / since the last reset (bench's gpu_launches). */
 long long pgk_launch_count(void);
 void pgk_reset_launch_count(void);
+/* add n to the counter: kernels replayed from a captured CUDA graph do not pass through the entry points */
+void pgk_count_launch(int n);
 /* per-launch device timing of the GEMM-shaped kernels (bench.py's roofline): while enabled, pgk_conv / pgk_wgrad
  * bracket their launch with CUDA events on `stream`.  pgk_prof_read synchronises on the recorded events and returns
  * the summed algorithmic FLOPs (2*M*N*K of each launch), the summed algorithmic HBM bytes (operand planes read +

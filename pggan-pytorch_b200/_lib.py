@@ -79,6 +79,8 @@ def load():
     lib.pgk_arch_check.restype = c_int
     lib.pgk_launch_count.restype = c_longlong
     lib.pgk_reset_launch_count.restype = None
+    lib.pgk_count_launch.argtypes = [c_int]
+    lib.pgk_count_launch.restype = None
     lib.pgk_prof_enable.argtypes = [c_int]
     lib.pgk_prof_enable.restype = None
     lib.pgk_prof_read.argtypes = [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
@@ -99,6 +101,7 @@ def load():
 
 def exported_symbols():
     return ['pgk_version', 'pgk_last_error', 'pgk_arch_check', 'pgk_launch_count', 'pgk_reset_launch_count',
+            'pgk_count_launch',
             'pgk_prof_enable', 'pgk_prof_read', 'pgk_prof_reset', 'pgk_set_tc', 'pgk_pack_thin_plane_elems'] + list(SIGNATURES)
 
 
@@ -133,6 +136,11 @@ def call(name, *args):
 
 def launch_count():
     return int(load().pgk_launch_count())
+
+
+def add_launches(n):
+    """Account for kernels launched by a replayed CUDA graph (they do not pass through the C entry points)."""
+    load().pgk_count_launch(int(n))
 
 
 def reset_launch_count():

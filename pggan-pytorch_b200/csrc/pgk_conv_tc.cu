@@ -635,6 +635,12 @@ extern "C" int pgk_conv_tc(const void* x, int P, int Pr, long long x_ps, int N, 
     int nt_max = a.split_acc ? 128 : 256;
     if (const char* e = getenv("PGK_CONV_NT")) nt_max = atoi(e) < nt_max ? atoi(e) : nt_max;   // tuning knob
     a.NT = Cout < nt_max ? Cout : nt_max;
+    // few pixel blocks (the 4x4 ... 16x16 levels at small batch): the launch is bound by streaming the weights, so
+    // spread them over more CTAs with narrower channel slices
+    {
+        const int pixel_tiles = a.tiles_x * a.tiles_y * tiles_n, sms = pgk_num_sms();
+        while (a.NT > 32 && pixel_tiles * (Cout / a.NT) < sms) a.NT >>= 1;
+    }
     a.ntiles_n = Cout / a.NT;
     a.total_tiles = a.tiles_x * a.tiles_y * tiles_n * a.ntiles_n;
     a.Pout = P;

@@ -22,6 +22,7 @@ from . import _lib
 
 call = _lib.call
 BF16 = torch.bfloat16
+CAPTURE_EPOCH = 0    # > 0 while a CUDA graph is being captured: every weight re-layout must be recorded once
 GRAD_PLANES = 2   # planes carried by gradient tensors / read by the gradient chains (include/pgk.h, pgk_conv: Pr)
 W_CONV, W_GFIRST, W_DLAST = 0, 1, 2
 
@@ -170,6 +171,7 @@ class ConvW(object):
         self.wf = self.wb = self.posT = self.bias16 = self.dwp = None
         self.F = self.B = None   # (fp32 [K][N], bf16 planes [3][N][K]) operand pairs: forward / data gradient
         self.version = None
+        self.cap_epoch = 0
 
     @property
     def weight(self):
@@ -182,7 +184,7 @@ class ConvW(object):
     def ensure(self):
         w = self.weight
         ver = (w._version, w.data_ptr(), self.bias._version, self.mod.cf)
-        if ver == self.version:
+        if ver == self.version and (CAPTURE_EPOCH == 0 or self.cap_epoch == CAPTURE_EPOCH):
             return self
         dev = w.device
         n = self.cout * self.cin * self.ks * self.ks
@@ -226,6 +228,7 @@ class ConvW(object):
         if self.kind == W_GFIRST:
             self.bias16 = self.bias.detach().repeat(16)
         self.version = ver
+        self.cap_epoch = CAPTURE_EPOCH
         return self
 
     def scratch(self):

@@ -285,3 +285,45 @@ def test_fused_adam_matches_torch_adam(gpu):
     for a, b in zip(pa, pb):
         assert rel_err(b, a) < 1e-6
     assert ob.state[pb[2]]['step'] == oa.state[pa[2]]['step'] == 3
+
+
+def test_cuda_graph_replay_equals_eager(gpu):
+    """wgan_gp_loss.cuda_graphs: the captured + replayed kernel sequence gives the eager results, including after the
+    optimizer changed the weights (the weight re-layout kernels are part of the graph)."""
+    pg = gpu['pg']
+    g = load_step('tiny3_d2_a03')
+
+    def run(graphs):
+        G, D = gpu['build_pair'](g)
+        od = torch.optim.SGD(D.parameters(), 1e-2)
+        og = torch.optim.SGD(G.parameters(), 1e-2)
+        pg.wgan_gp_loss.cuda_graphs = graphs
+        pg.wgan_gp_loss._graphs.clear()
+        out = []
+        try:
+            for it in range(5):
+                gen = torch.Generator().manual_seed(100 + it)
+                real = torch.randn(g['n'], g['channels'], g['real'].shape[-1], g['real'].shape[-1], generator=gen).cuda()
+                z1 = torch.randn(g['n'], g['latent'], generator=gen).cuda()
+                z2 = torch.randn(g['n'], g['latent'], generator=gen).cuda()
+                pg.wgan_gp_loss.mixing_factors_override = torch.rand(g['n'], 1, generator=gen)
+                cost, rl, fl = pg.wgan_gp_D_loss(D, G, real, z1)
+                cost.backward()
+                od.step()
+                gcost = pg.wgan_gp_G_loss(G, D, z2)
+                gcost.backward()
+                og.step()
+                out.append((float(cost), float(gcost), rl.clone(), fl.clone()))
+        finally:
+            pg.wgan_gp_loss.cuda_graphs = False
+            pg.wgan_gp_loss.mixing_factors_override = None
+            pg.wgan_gp_loss._graphs.clear()
+        return out, [p.detach().clone() for p in list(D.parameters()) + list(G.parameters())]
+
+    eager, pe = run(False)
+    graph, pgr = run(True)
+    for (c0, g0, r0, f0), (c1, g1, r1, f1) in zip(eager, graph):
+        assert abs(c0 - c1) <= 1e-5 * max(1.0, abs(c0)) and abs(g0 - g1) <= 1e-5 * max(1.0, abs(g0))
+        assert rel_err(r1, r0) < 1e-5 and rel_err(f1, f0) < 1e-5
+    for a, b in zip(pe, pgr):
+        assert rel_err(b, a) < 1e-5      # atomics make the last bits of the weight gradients order dependent
