@@ -317,23 +317,43 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(BiasArgs a) {
     const int lanes = 256 / nch;  // pixel lanes
     const int ch = t % nch, pl = t / nch;
     float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const long long per_group = (long long)a.group_n * a.HW;
-    long long r_begin = (long long)blockIdx.x * a.r_per_cta, r_end = r_begin + a.r_per_cta;
-    if (r_end > a.R) r_end = a.R;
+    // R < 2^31 (checked by the launcher): 32-bit index arithmetic keeps the division out of the load loop's way
+    const unsigned per_group = (unsigned)a.group_n * (unsigned)a.HW;
+    unsigned r_begin = (unsigned)((long long)blockIdx.x * a.r_per_cta);
+    unsigned r_end = (unsigned)(((long long)blockIdx.x + 1) * a.r_per_cta < a.R ? ((long long)blockIdx.x + 1) * a.r_per_cta : a.R);
     if (pl < lanes) {
-        for (long long r = r_begin + pl; r < r_end; r += lanes) {
-            int grp = (int)(r / per_group);
-            long long w = r - grp * per_group;
+#pragma unroll 4
+        for (unsigned r = r_begin + pl; r < r_end; r += lanes) {
+            const unsigned grp = r / per_group;
+            const unsigned w = r - grp * per_group;
             float f[8];
             ld8(a.g, ((long long)a.goff[grp] * a.HW + w) * a.Cout + ch * 8, f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) s[j] += f[j];
         }
     }
+    // nch a power of two <= 32: lanes l, l + nch, ... of a warp share a channel chunk -> xor shuffles, then the 8 warp
+    // partials through shared memory; other widths: one thread per chunk walks its lanes
+    const bool fast = nch <= 32 && (nch & (nch - 1)) == 0;
+    const int lane = t & 31;
+    if (fast) {
+        for (int o = nch; o < 32; o <<= 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+        }
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) red[t][j] = s[j];
     __syncthreads();
-    if (t < nch) {
+    if (fast) {
+        if (t < nch * 8) {
+            const int chn = t >> 3, j = t & 7;
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) tot += red[w * 32 + chn][j];
+            atomicAdd(a.db + chn * 8 + j, a.scale * tot);
+        }
+    } else if (t < nch) {
         float tot[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int l = 0; l < lanes; ++l)
 #pragma unroll
@@ -428,8 +448,9 @@ extern "C" int pgk_bias_grad(const void* g, long long g_ps, int P, int HW, int C
     a.scale = scale;
     a.db = db;
     a.R = (long long)ngroups * group_n * HW;
+    PGK_REQUIRE(a.R < (1ll << 31), "pgk_bias_grad: more than 2^31 pixels");
     long long ctas = (a.R + 511) / 512;
-    long long cap = 2ll * pgk_num_sms();
+    long long cap = 4ll * pgk_num_sms();
     if (ctas > cap) ctas = cap;
     if (ctas < 1) ctas = 1;
     a.r_per_cta = (a.R + ctas - 1) / ctas;

@@ -50,8 +50,15 @@ struct Steps {
     static constexpr int N = CIN == 8 ? 6 : 9 * (CIN / 16);
 };
 
-template <int CIN, int P, int SPLIT>
-__global__ void __launch_bounds__(kThinThreads, 1) conv_thin_kernel(const __grid_constant__ CUtensorMap tmA,
+// 16-byte read-only load that stays where it is written (volatile asm is not moved across the mbarrier waits)
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+template <int CIN, int P, int SPLIT, int NPAD>
+__global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const ThinArgs a) {
     constexpr int CG = Steps<CIN>::CG, STEPS = Steps<CIN>::N;
     constexpr uint32_t plane_bytes = CG * kCgBytes;
@@ -64,7 +71,7 @@ __global__ void __launch_bounds__(kThinThreads, 1) conv_thin_kernel(const __grid
     const int kRing = a.ring, kRingLog = a.ring_log2;
     const uint32_t rows0 = sbase;                                 // kRing row buffers
     const uint32_t w0 = rows0 + kRing * row_bytes;                // weights [P][STEPS][2][Npad][8]
-    const uint32_t wstep = (uint32_t)a.Npad * 32u, wplane = STEPS * wstep;
+    constexpr uint32_t wstep = (uint32_t)NPAD * 32u, wplane = STEPS * wstep;
     const uint32_t bars = (w0 + P * wplane + 15u) & ~15u;
     auto rfull = [&](int s) { return bars + 8u * s; };
     auto rempty = [&](int s) { return bars + 8u * (kMaxRing + s); };
@@ -81,7 +88,7 @@ __global__ void __launch_bounds__(kThinThreads, 1) conv_thin_kernel(const __grid
         const uint32_t n16 = P * wplane / 16u;
         for (uint32_t i = threadIdx.x; i < n16; i += kThinThreads) st_shared_v4(w0 + i * 16u, __ldg(src + i));
     }
-    for (int i = threadIdx.x; i < a.Npad; i += kThinThreads) bias_s[i] = (a.bias && i < a.Cout) ? __ldg(a.bias + i) : 0.f;
+    for (int i = threadIdx.x; i < NPAD; i += kThinThreads) bias_s[i] = (a.bias && i < a.Cout) ? __ldg(a.bias + i) : 0.f;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kRing; ++s) {
             mbar_init(rfull(s), 1);
@@ -94,8 +101,8 @@ __global__ void __launch_bounds__(kThinThreads, 1) conv_thin_kernel(const __grid
         fence_barrier_init();
     }
     if (warp == 8 && lane == 0) tma_prefetch_desc(&tmA);
-    const int acc_cols = SPLIT ? 2 * a.Npad : a.Npad;
-    const unsigned ncols = kAcc * acc_cols <= 64 ? 64u : kAcc * acc_cols <= 128 ? 128u : kAcc * acc_cols <= 256 ? 256u : 512u;
+    constexpr int acc_cols = SPLIT ? 2 * NPAD : NPAD;
+    constexpr unsigned ncols = kAcc * acc_cols <= 64 ? 64u : kAcc * acc_cols <= 128 ? 128u : kAcc * acc_cols <= 256 ? 256u : 512u;
     if (warp == 9) tmem_alloc(tptr, ncols);
     fence_proxy_async();   // generic-proxy writes (weights, zeroed ring) -> visible to the tensor core / TMA
     fence_before();
@@ -137,11 +144,11 @@ __global__ void __launch_bounds__(kThinThreads, 1) conv_thin_kernel(const __grid
         }
     } else if (warp == 9) {
         // ---- MMA issue: per output row, STEPS x (products of planes) MMAs of 128 pixels x Npad x 16
-        const uint32_t idesc = idesc_bf16(a.Npad, 0, 0);
+        const uint32_t idesc = idesc_bf16(NPAD, 0, 0);
         // A: 8 pixels x 16 B core matrices, SBO = 128 B to the next 8 pixels; LBO = distance between the two K halves
         const uint64_t adesc_hi = smem_desc(0, CIN == 8 ? 16u : (uint32_t)kCgBytes, 128, 0);
-        const uint64_t bdesc0 = smem_desc(w0, (uint32_t)a.Npad * 16u, 128, 0);
-        const uint32_t wstep16 = wstep >> 4, wplane16 = wplane >> 4;
+        const uint64_t bdesc0 = smem_desc(w0, (uint32_t)NPAD * 16u, 128, 0);
+        constexpr uint32_t wstep16 = wstep >> 4, wplane16 = wplane >> 4;
         uint32_t g = 0, ti = 0;
         for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
             mbar_wait_spin(rfull(g & (kRing - 1)), (g >> kRingLog) & 1);
@@ -151,7 +158,7 @@ __global__ void __launch_bounds__(kThinThreads, 1) conv_thin_kernel(const __grid
                 const int b = ti & (kAcc - 1);
                 mbar_wait_spin(aempty(b), ((ti / kAcc) & 1) ^ 1);
                 fence_after();
-                const uint32_t d_main = tmem + b * acc_cols, d_corr = d_main + a.Npad;
+                const uint32_t d_main = tmem + b * acc_cols, d_corr = d_main + NPAD;
                 uint32_t rb[3];
 #pragma unroll
                 for (int dy = 0; dy < 3; ++dy) rb[dy] = (rows0 + ((g + dy) & (kRing - 1)) * row_bytes) >> 4;
@@ -193,40 +200,63 @@ __global__ void __launch_bounds__(kThinThreads, 1) conv_thin_kernel(const __grid
             g += 2;
         }
     } else {
-        // ---- epilogue: thread = pixel; warpgroup wg takes the tiles with (tile index & 1) == wg
+        // ---- epilogue: thread = pixel; warpgroup wg takes the tiles with (tile index & 1) == wg.  Tiles are numbered
+        // over the whole life of the CTA (tile = unit index * RC + row), exactly as the MMA warp counts them.  The
+        // backward-mask vectors of a thread's NEXT tile are requested before it waits for the current accumulator, so
+        // their HBM latency is hidden behind a whole tile of work.
+        constexpr int NV = NPAD / 8;
         const int wg = warp >> 2, q = warp & 3;
         const int r = q * 32 + lane;
         const uint32_t trow_off = (uint32_t)(q * 32) << 16;
-        uint32_t ti = 0;
-        for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
+        const int my_units = (int)blockIdx.x < a.total_units ? (a.total_units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        const uint32_t ntiles = (uint32_t)my_units * (uint32_t)a.RC;
+        auto tile_pix = [&](uint32_t t) {
+            const uint32_t k = t / (uint32_t)a.RC, i = t - k * (uint32_t)a.RC;
             int n, x0, ya;
-            unit_coords(u, n, x0, ya);
-            for (int i = 0; i < a.RC; ++i, ++ti) {
-                if ((int)(ti & 1) != wg) continue;
-                const int b = ti & (kAcc - 1);
-                const long long pix = ((long long)n * a.H + (ya + i)) * a.W + x0 + r;
-                mbar_wait(afull(b), (ti / kAcc) & 1);
-                fence_after();
-                const uint32_t trow = tmem + b * acc_cols + trow_off;
-                for (int c = 0; c < a.Npad; c += 16) {
-                    float v[16], m[16];
-                    const long long o = pix * a.Cout + c;
-                    if (a.has_mask) {   // sign of plane 0 = sign of the value
-                        Planes m0 = a.mask;
-                        m0.P = 1;
-                        ld8(m0, o, m);
-                        if (c + 8 < a.Cout) ld8(m0, o + 8, m + 8);
-                    }
-                    tmem_ld16(trow + c, v);
-                    if (SPLIT) {
-                        float w[16];
-                        tmem_ld16(trow + a.Npad + c, w);
+            unit_coords((int)(blockIdx.x + k * gridDim.x), n, x0, ya);
+            return ((long long)n * a.H + (ya + (int)i)) * a.W + x0 + r;
+        };
+        uint4 mk[NV];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] += w[j];
-                    }
+        for (int k = 0; k < NV; ++k) mk[k] = make_uint4(0, 0, 0, 0);
+        auto load_mask = [&](long long pix) {   // plane 0 only: its sign is the sign of the value
+            const uint4* mp = reinterpret_cast<const uint4*>(a.mask.p + pix * a.Cout);
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (c + 8 * h >= a.Cout) break;
+            for (int k = 0; k < NV; ++k)
+                if (k * 8 < a.Cout) mk[k] = ldg_nc_v4(mp + k);
+        };
+        uint32_t ti = (uint32_t)wg;
+        long long pix = 0;
+        if (ti < ntiles) {
+            pix = tile_pix(ti);
+            if (a.has_mask) load_mask(pix);
+        }
+        for (; ti < ntiles; ti += 2) {
+            uint4 mc[NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) mc[k] = mk[k];
+            const long long o = pix * a.Cout;
+            if (ti + 2 < ntiles) {
+                pix = tile_pix(ti + 2);
+                if (a.has_mask) load_mask(pix);
+            }
+            const int b = ti & (kAcc - 1);
+            mbar_wait(afull(b), (ti / kAcc) & 1);
+            fence_after();
+            const uint32_t trow = tmem + b * acc_cols + trow_off;
+#pragma unroll
+            for (int c = 0; c < NPAD; c += 16) {
+                float v[16];
+                tmem_ld16(trow + c, v);
+                if (SPLIT) {
+                    float w[16];
+                    tmem_ld16(trow + NPAD + c, w);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += w[j];
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (c + 8 * h < a.Cout) {
                         float* f = v + 8 * h;
                         {
                             const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c + 8 * h);
@@ -239,18 +269,20 @@ __global__ void __launch_bounds__(kThinThreads, 1) conv_thin_kernel(const __grid
                             for (int j = 0; j < 8; ++j) f[j] = lrelu(f[j]);
                         }
                         if (a.has_mask) {
+                            float m[8];
+                            unpack8(mc[c / 8 + h], m);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) f[j] *= lrelu_grad(m[8 * h + j]);
+                            for (int j = 0; j < 8; ++j) f[j] *= lrelu_grad(m[j]);
                         }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) f[j] *= a.out_scale;
-                        split_store8(a.out, o + 8 * h, f);
+                        split_store8(a.out, o + c + 8 * h, f);
                     }
                 }
-                fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(aempty(b));
             }
+            fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(aempty(b));
         }
     }
     fence_before();
@@ -312,21 +344,82 @@ extern "C" int pgk_pack_thin(const float* w, int Cin, int Cout, void* out, long 
     return PGK_OK;
 }
 
-template <int CIN, int P, int SPLIT>
-static int launch_thin(const CUtensorMap& tmA, const ThinArgs& a, int smem, cudaStream_t stream) {
+// CTAs per SM: the kernel is bound by memory latency (one row of 128 pixels per pipeline step), so co-resident CTAs
+// are what fills the HBM pipe.  Limits: shared memory + registers (asked of the runtime), 512 TMEM columns per SM,
+// and the PGK_THIN_OCC knob (default 2).
+static int thin_occ_cap() {
+    static int cap = 0;
+    if (cap == 0) {
+        const char* e = getenv("PGK_THIN_OCC");
+        cap = e ? atoi(e) : 2;
+        if (cap < 1) cap = 1;
+        if (cap > 4) cap = 4;
+    }
+    return cap;
+}
+
+struct ThinPlan {
+    int occ, ring, smem;
+};
+
+template <int CIN, int P, int SPLIT, int NPAD>
+static int launch_thin(const CUtensorMap& tmA, ThinArgs& a, cudaStream_t stream) {
     static bool attr = false;
+    static ThinPlan plan;   // CTAs per SM, ring depth and shared memory of this instance
+    auto kern = conv_thin_kernel<CIN, P, SPLIT, NPAD>;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(conv_thin_kernel<CIN, P, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kSmemLimit);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e != cudaSuccess) {
             pgk_set_error("pgk_conv_thin: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return PGK_ERR_CUDA;
         }
+        constexpr int steps = Steps<CIN>::N;
+        constexpr int acc_cols = SPLIT ? 2 * NPAD : NPAD;
+        constexpr int ncols = kAcc * acc_cols <= 64 ? 64 : kAcc * acc_cols <= 128 ? 128 : kAcc * acc_cols <= 256 ? 256 : 512;
+        const int fixed = 128 + P * steps * NPAD * 32 + 16 + 16 * kMaxRing + 16 * kAcc + 32 + 4 * NPAD + 64;
+        const int row = P * (CIN / 8) * kCgBytes;
+        ThinPlan pl = {0, 0, 0};
+        const int cap = thin_occ_cap();
+        for (int occ = cap < 512 / ncols ? cap : 512 / ncols; occ >= 1 && pl.occ == 0; --occ) {
+            for (int ring = 8; ring >= 4 && pl.occ == 0; ring >>= 1) {
+                const int smem = fixed + ring * row;
+                if (smem > kSmemLimit) continue;
+                int got = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, kern, kThinThreads, smem) != cudaSuccess) got = 0;
+                if (got >= occ) pl.occ = occ, pl.ring = ring, pl.smem = smem;
+            }
+        }
+        if (pl.occ == 0) {
+            cudaGetLastError();
+            pgk_set_error("pgk_conv_thin: no shared-memory plan for Cin %d Npad %d P %d", CIN, NPAD, P);
+            return PGK_ERR_ARG;
+        }
+        plan = pl;
         attr = true;
     }
-    int grid = pgk_num_sms();
-    if (grid > a.total_units) grid = a.total_units;
-    conv_thin_kernel<CIN, P, SPLIT><<<grid, kThinThreads, smem, stream>>>(tmA, a);
+    // rows per unit: minimise the rows of the busiest CTA, ceil(units / grid) * (RC + 2 halo rows), over the chunk
+    // sizes that divide H
+    const ThinPlan best_pl = plan;
+    int best_rc = 0, best_grid = 0;
+    long long best_cost = -1;
+    for (int rc = 64; rc >= 8; rc >>= 1) {
+        if (a.H % rc) continue;
+        const long long units = (long long)a.N * a.strips * (a.H / rc);
+        long long grid = (long long)best_pl.occ * pgk_num_sms();
+        if (grid > units) grid = units;
+        const long long cost = (units + grid - 1) / grid * (rc + 2);
+        if (best_cost < 0 || cost < best_cost) best_cost = cost, best_rc = rc, best_grid = (int)grid;
+    }
+    if (best_rc == 0) {
+        pgk_set_error("pgk_conv_thin: no row chunk divides H = %d", a.H);
+        return PGK_ERR_ARG;
+    }
+    a.RC = best_rc;
+    a.chunks_y = a.H / a.RC;
+    a.total_units = a.N * a.strips * a.chunks_y;
+    a.ring = best_pl.ring;
+    a.ring_log2 = best_pl.ring == 8 ? 3 : 2;
+    kern<<<best_grid, kThinThreads, best_pl.smem, stream>>>(tmA, a);
     return PGK_OK;
 }
 
@@ -339,10 +432,8 @@ extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N
     ThinArgs a;
     a.N = N, a.H = H, a.W = W, a.Cout = Cout;
     a.Npad = Cout < 16 ? 16 : Cout;
-    a.RC = H >= 32 ? 32 : H;
-    a.chunks_y = H / a.RC;
     a.strips = W / 128;
-    a.total_units = N * a.strips * a.chunks_y;
+    a.RC = a.chunks_y = a.total_units = a.ring = a.ring_log2 = 0;   // chosen by launch_thin
     a.Pout = P;
     a.split_acc = Pr == 3 ? 1 : 0;
     PGK_REQUIRE(wpack_ps == pgk_pack_thin_plane_elems(Cin, Cout), "pgk_conv_thin: wpack plane stride mismatch");
@@ -352,12 +443,6 @@ extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N
     a.mask = make_planes(mask_ref, mask_ps, P);
     a.out_scale = out_scale;
     a.out = make_planes(out, out_ps, P);
-    const int steps = Cin == 8 ? 6 : 9 * (Cin / 16);
-    const int fixed = 128 + Pr * steps * a.Npad * 32 + 16 + 16 * kMaxRing + 16 * kAcc + 32 + 4 * a.Npad + 64;
-    a.ring = 8, a.ring_log2 = 3;
-    if (fixed + a.ring * Pr * (Cin / 8) * kCgBytes > kSmemLimit) a.ring = 4, a.ring_log2 = 2;
-    const int smem = fixed + a.ring * Pr * (Cin / 8) * kCgBytes;
-    PGK_REQUIRE(smem <= kSmemLimit, "pgk_conv_thin: %d bytes of shared memory needed", smem);
     CUtensorMap tmA;
     {
         unsigned long long dims[5] = {(unsigned long long)Cin, (unsigned long long)W, (unsigned long long)H,
@@ -370,14 +455,16 @@ extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N
     }
     cudaStream_t st = (cudaStream_t)stream;
     int rc = PGK_ERR_ARG;
-#define PGK_THIN_CASE(C_, P_, S_) \
-    if (Cin == C_ && Pr == P_ && a.split_acc == S_) rc = launch_thin<C_, P_, S_>(tmA, a, smem, st);
+#define PGK_THIN_CASE_N(C_, P_, S_, N_) \
+    if (Cin == C_ && Pr == P_ && a.split_acc == S_ && a.Npad == N_) rc = launch_thin<C_, P_, S_, N_>(tmA, a, st);
+#define PGK_THIN_CASE(C_, P_, S_) PGK_THIN_CASE_N(C_, P_, S_, 16) PGK_THIN_CASE_N(C_, P_, S_, 32) PGK_THIN_CASE_N(C_, P_, S_, 64)
     PGK_THIN_CASE(8, 1, 0) PGK_THIN_CASE(16, 1, 0) PGK_THIN_CASE(32, 1, 0)
     PGK_THIN_CASE(8, 2, 0) PGK_THIN_CASE(16, 2, 0) PGK_THIN_CASE(32, 2, 0)
     PGK_THIN_CASE(8, 3, 1) PGK_THIN_CASE(16, 3, 1) PGK_THIN_CASE(32, 3, 1)
 #undef PGK_THIN_CASE
+#undef PGK_THIN_CASE_N
     if (rc) {
-        if (rc == PGK_ERR_ARG) pgk_set_error("pgk_conv_thin: no kernel instance for Cin %d Pr %d", Cin, Pr);
+        if (rc == PGK_ERR_ARG) pgk_set_error("pgk_conv_thin: no kernel instance for Cin %d Pr %d Npad %d", Cin, Pr, a.Npad);
         return rc;
     }
     PGK_LAUNCH_CHECK("pgk_conv(thin tcgen05)");

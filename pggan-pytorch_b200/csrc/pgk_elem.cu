@@ -367,25 +367,62 @@ __global__ void __launch_bounds__(256) rgb_wgrad_kernel(RgbWgradArgs a) {
             }
         }
     }
+    // reduce over the pixel lanes that share a channel chunk.  nch a power of two <= 32 (every real layer): lanes
+    // l, l + nch, ... of a warp share a chunk -> xor shuffles, then 8 warp partials per value through shared memory,
+    // summed by nch * 40 threads in parallel.  Other widths: one thread per chunk walks its lanes.
+    const bool fast = nch <= 32 && (nch & (nch - 1)) == 0;
+    const int lane = t & 31;
+    if (fast) {
+        for (int o = nch; o < 32; o <<= 1) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        red[t][MAXC * 8 + j] = cs[j];
+            for (int j = 0; j < 8; ++j) {
+                cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], o);
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) red[t][c * 8 + j] = acc[c][j];
+                for (int c = 0; c < MAXC; ++c) acc[c][j] += __shfl_xor_sync(0xffffffffu, acc[c][j], o);
+            }
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) is[c] += __shfl_xor_sync(0xffffffffu, is[c], o);
+        }
+    }
+    if (!fast || lane < nch) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            red[t][MAXC * 8 + j] = cs[j];
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) red[t][c * 8 + j] = acc[c][j];
+        }
     }
     __syncthreads();
-    if (ch == 0 && pl < lanes && a.imgsum) {
-        for (int c = 0; c < a.C; ++c) atomicAdd(&isum[c], is[c]);
-    }
-    if (t < nch) {
-        for (int q = 0; q < MAXC * 8 + 8; ++q) {
+    if (fast) {
+        if (lane == 0 && a.imgsum) {
+            for (int c = 0; c < a.C; ++c) atomicAdd(&isum[c], is[c]);
+        }
+        for (int o = t; o < nch * (MAXC * 8 + 8); o += 256) {
+            const int chn = o / (MAXC * 8 + 8), q = o - chn * (MAXC * 8 + 8);
             float tot = 0.f;
-            for (int l = 0; l < lanes; ++l) tot += red[l * nch + t][q];
-            int j = q & 7, c = q >> 3;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) tot += red[w * 32 + chn][q];
+            const int j = q & 7, c = q >> 3;
             if (c < MAXC) {
-                if (c < a.C && a.dw) atomicAdd(a.dw + (long long)c * a.sa + (long long)(t * 8 + j) * a.sk, a.scale * tot);
+                if (c < a.C && a.dw) atomicAdd(a.dw + (long long)c * a.sa + (long long)(chn * 8 + j) * a.sk, a.scale * tot);
             } else if (a.colsum) {
-                atomicAdd(a.colsum + t * 8 + j, a.scale_b * tot);
+                atomicAdd(a.colsum + chn * 8 + j, a.scale_b * tot);
+            }
+        }
+    } else {
+        if (ch == 0 && pl < lanes && a.imgsum) {
+            for (int c = 0; c < a.C; ++c) atomicAdd(&isum[c], is[c]);
+        }
+        if (t < nch) {
+            for (int q = 0; q < MAXC * 8 + 8; ++q) {
+                float tot = 0.f;
+                for (int l = 0; l < lanes; ++l) tot += red[l * nch + t][q];
+                int j = q & 7, c = q >> 3;
+                if (c < MAXC) {
+                    if (c < a.C && a.dw) atomicAdd(a.dw + (long long)c * a.sa + (long long)(t * 8 + j) * a.sk, a.scale * tot);
+                } else if (a.colsum) {
+                    atomicAdd(a.colsum + t * 8 + j, a.scale_b * tot);
+                }
             }
         }
     }

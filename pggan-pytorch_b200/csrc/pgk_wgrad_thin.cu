@@ -41,7 +41,7 @@ struct WThinArgs {
 };
 
 template <int CIN, int P>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WThinArgs a) {
     // row groups of XT3: 3 * CG shifted copies + one group whose first row is all ones (the bias-gradient row)
     constexpr int CG = CIN / 8, XG = 3 * CG;
@@ -330,7 +330,24 @@ static int launch_wthin(const CUtensorMap& tmX, const CUtensorMap& tmG, const WT
         }
         attr = true;
     }
-    int grid = pgk_num_sms();
+    // co-resident CTAs hide the latency of the two-deep raw rings (same reasoning and knob as pgk_conv_thin.cu);
+    // limits: shared memory (asked of the runtime) and 512 TMEM columns per SM
+    int occ = 1;
+    {
+        const char* e = getenv("PGK_THIN_OCC");
+        int cap = e ? atoi(e) : 2;
+        cap = cap < 1 ? 1 : cap > 4 ? 4 : cap;
+        const int ncols = 3 * a.Npad <= 64 ? 64 : 3 * a.Npad <= 128 ? 128 : 256;
+        if (cap > 512 / ncols) cap = 512 / ncols;
+        int got = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, wgrad_thin_kernel<CIN, P>, kThreads, smem) != cudaSuccess) {
+            cudaGetLastError();
+            got = 1;
+        }
+        occ = got < cap ? got : cap;
+        if (occ < 1) occ = 1;
+    }
+    int grid = occ * pgk_num_sms();
     if (grid > a.total_units) grid = a.total_units;
     wgrad_thin_kernel<CIN, P><<<grid, kThreads, smem, stream>>>(tmX, tmG, a);
     return PGK_OK;
