@@ -3,6 +3,7 @@
 
     from pggan_b200 import Generator, Discriminator, wgan_gp_D_loss, wgan_gp_G_loss, Trainer, DepthManager
 """
+from .checkpoint import from_reference, load_snapshot, resume      # noqa: F401
 from .dataset import prepare_reals                                 # noqa: F401
 from .network import Discriminator, Generator, PGConv2d            # noqa: F401
 from .optim import FusedAdam                                       # noqa: F401

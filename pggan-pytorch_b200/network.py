@@ -145,12 +145,20 @@ class Generator(_EngineOwner):
         nf = nf_fn(fmap_base, fmap_decay, fmap_max)
         if latent_size is None:
             latent_size = nf(0)
-        _check_channels([latent_size] + [nf(i) for i in range(1, R)], 'Generator')
+        self._construct([nf(i) for i in range(1, R)], num_channels, latent_size, normalize_latents, wscale, pixelnorm,
+                        leakyrelu)
+
+    def _construct(self, widths, num_channels, latent_size, normalize_latents=True, wscale=True, pixelnorm=True,
+                   leakyrelu=True):
+        """widths[i-1] = feature maps of stage i (nf(i), i = 1..R-1).  Shared by __init__ and checkpoint.from_reference
+        (a snapshot carries its widths, not the fmap_* arguments that produced them)."""
+        _check_channels([latent_size] + list(widths), 'Generator')
         self.normalize_latents = normalize_latents
         self.pixelnorm = pixelnorm
         settings = dict(wscale=wscale, pixelnorm=pixelnorm, act='lrelu' if leakyrelu else 'relu')
-        self.block0 = GFirstBlock(latent_size, nf(1), num_channels, **settings)
-        self.blocks = nn.ModuleList([GBlock(nf(i - 1), nf(i), num_channels, **settings) for i in range(2, R)])
+        self.block0 = GFirstBlock(latent_size, widths[0], num_channels, **settings)
+        self.blocks = nn.ModuleList([GBlock(widths[i - 1], widths[i], num_channels, **settings)
+                                     for i in range(1, len(widths))])
         self.depth = 0
         self.alpha = 1.0
         self.eps = 1e-8
@@ -180,13 +188,21 @@ class Discriminator(_EngineOwner):
         resolution, num_channels = dataset_shape[-1], dataset_shape[1]
         R = int(math.log2(resolution))
         assert resolution == 2 ** R and resolution >= 4
-        self.R = R
         nf = nf_fn(fmap_base, fmap_decay, fmap_max)
-        _check_channels([nf(i) for i in range(0, R)], 'Discriminator')
+        self._construct([nf(i) for i in range(0, R)], num_channels, wscale, pixelnorm, leakyrelu)
+
+    def _construct(self, widths, num_channels, wscale=True, pixelnorm=False, leakyrelu=True):
+        """widths[i] = feature maps of stage i (nf(i), i = 0..R-1); see Generator._construct."""
+        if pixelnorm:
+            raise NotImplementedError('the discriminator kernels implement pixelnorm=False (the reference default)')
+        R = len(widths)
+        self.R = R
+        _check_channels(list(widths), 'Discriminator')
         settings = dict(wscale=wscale, pixelnorm=pixelnorm, act='lrelu' if leakyrelu else 'relu')
-        self.blocks = nn.ModuleList([DBlock(nf(i), nf(i - 1), num_channels, **settings) for i in range(R - 1, 1, -1)]
-                                    + [DLastBlock(nf(1), nf(0), num_channels, **settings)])
-        self.linear = nn.Linear(nf(0), 1)
+        self.blocks = nn.ModuleList([DBlock(widths[i], widths[i - 1], num_channels, **settings)
+                                     for i in range(R - 1, 1, -1)]
+                                    + [DLastBlock(widths[1], widths[0], num_channels, **settings)])
+        self.linear = nn.Linear(widths[0], 1)
         self.depth = 0
         self.alpha = 1.0
         self.eps = 1e-8
