@@ -5,7 +5,10 @@
 //
 //   * persistent CTAs stream image rows: a work unit is (sample, 128-pixel column strip, RC consecutive rows); the
 //     three input rows of an output row live in a shared-memory ring, and moving down one row loads ONE new row
-//     (TMA; out-of-range rows and the +-1 pixel halo are zero filled by the hardware = the conv's padding);
+//     (a producer warp of 16-byte cp.async with zero fill for out-of-range rows and the +-1 pixel halo = the conv's
+//     padding; each warp instruction reads 512 contiguous bytes.  A TMA box with the 16-byte inner extent this
+//     layout needs delivers one 16-byte row per ~5 cycles -- measured, it bounded the first version of this kernel
+//     at 1.7-2.5 TB/s whatever the number of CTAs per SM);
 //   * a row buffer is stored channel-group planar, [Cin/8][130 + pad pixels][8 channels]: one pixel of one channel
 //     group is 16 bytes, so 8 consecutive pixels are exactly one un-swizzled K-major UMMA core matrix, and the 9 taps
 //     are nothing but 9 start addresses ((dy row buffer) + (1 + dx) * 16 bytes) into the same bytes -- no im2col,
@@ -25,15 +28,17 @@ namespace {
 
 constexpr int kThinThreads = 320;   // warps 0-3 / 4-7: two epilogue warpgroups (even / odd tiles), 8 producer, 9 MMA issue
 constexpr int kAcc = 4;             // TMEM accumulator buffers: hides the MMA -> epilogue -> MMA round trip
-constexpr int kMaxRing = 8;         // row buffers: 8, or 4 when the planes make a row large (power of two)
+constexpr int kMaxRing = 16;        // row buffers: 16, 8 or 4 (power of two), as many as fit
 constexpr int kRowPix = 136;        // 130 loaded pixels, padded so that every channel-group plane is 128-byte aligned
 constexpr int kCgBytes = kRowPix * 16;
 constexpr int kSmemLimit = 227 * 1024;
 
 struct ThinArgs {
+    const bf16* x;              // input planes, N,H,W,Cin each, x_ps elements apart
+    long long x_ps;
     int N, H, W, Cout, Npad;
     int RC, chunks_y, strips;   // rows per unit, units per column strip, W / 128
-    int ring, ring_log2;
+    int ring, ring_log2, look;  // row buffers; rows the producer keeps in flight before it hands the oldest over
     int total_units;
     int Pout, split_acc;
     const bf16* wpack;          // [P][STEPS][2][Npad][8]
@@ -58,12 +63,10 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
 }
 
 template <int CIN, int P, int SPLIT, int NPAD>
-__global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                    const ThinArgs a) {
+__global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const ThinArgs a) {
     constexpr int CG = Steps<CIN>::CG, STEPS = Steps<CIN>::N;
     constexpr uint32_t plane_bytes = CG * kCgBytes;
     constexpr uint32_t row_bytes = P * plane_bytes;
-    constexpr uint32_t tx_bytes = P * CG * 130 * 16;
     extern __shared__ uint8_t smem_raw[];
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const uint32_t raw = smem_u32(smem_raw);
@@ -100,7 +103,6 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
         }
         fence_barrier_init();
     }
-    if (warp == 8 && lane == 0) tma_prefetch_desc(&tmA);
     constexpr int acc_cols = SPLIT ? 2 * NPAD : NPAD;
     constexpr unsigned ncols = kAcc * acc_cols <= 64 ? 64u : kAcc * acc_cols <= 128 ? 128u : kAcc * acc_cols <= 256 ? 256u : 512u;
     if (warp == 9) tmem_alloc(tptr, ncols);
@@ -120,28 +122,64 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
     };
 
     if (warp == 8) {
-        // ---- producer: one input row per step of the ring
-        uint32_t g = 0;
+        // ---- producer: one input row per step of the ring, as 130 * CG 16-byte chunks (pixel, channel group) per
+        // plane.  Chunk q of a row sits at byte 16 * q of the global row segment, so a warp instruction reads 512
+        // contiguous bytes; its shared-memory home is [channel group][pixel].  Up to `look` rows stay in flight
+        // (one cp.async group per row); a row is handed to the MMA warp once every lane's copies of it have landed
+        // and been fenced towards the async proxy.
+        uint32_t g = 0, signalled = 0;   // rows requested / rows handed over (warp-uniform)
+        auto hand_over = [&](uint32_t upto) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0)
+                for (uint32_t r = signalled; r < upto; ++r) mbar_arrive(rfull(r & (kRing - 1)));
+            signalled = upto;
+        };
+        const int look = a.look;
         for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
             int n, x0, ya;
             unit_coords(u, n, x0, ya);
             for (int j = 0; j < a.RC + 2; ++j, ++g) {
                 const int s = g & (kRing - 1);
-                mbar_wait_spin(rempty(s), ((g >> kRingLog) & 1) ^ 1);
-                if (elect_one()) {
-                    const uint32_t fb = rfull(s);
-                    mbar_expect_tx(fb, tx_bytes);
-                    const uint32_t dst = rows0 + s * row_bytes;
+                const uint32_t par = ((g >> kRingLog) & 1) ^ 1;
+                if (!__all_sync(0xffffffffu, mbar_test(rempty(s), par))) {
+                    // about to sleep on a busy slot: hand over everything requested so far first -- the MMA warp may
+                    // need exactly those rows to finish the tile that frees this slot
+                    cp_async_wait<0>();
+                    hand_over(g);
+                    mbar_wait_spin(rempty(s), par);
+                }
+                const int y = ya - 1 + j;
+                const bool row_ok = y >= 0 && y < a.H;
+                const bf16* rowp = a.x + ((long long)n * a.H + (row_ok ? y : 0)) * a.W * CIN;
+                const uint32_t dst = rows0 + s * row_bytes;
 #pragma unroll
-                    for (int p = 0; p < P; ++p) {
+                for (int p = 0; p < P; ++p) {
 #pragma unroll
-                        for (int cg = 0; cg < CG; ++cg)
-                            tma_load_5d(dst + p * plane_bytes + cg * kCgBytes, &tmA, fb, cg * 8, x0 - 1, ya - 1 + j, n, p);
+                    for (int it = 0; it < (130 * CG + 31) / 32; ++it) {
+                        const int q = it * 32 + lane;
+                        if (q < 130 * CG) {
+                            const int px = q / CG, cg = q % CG;
+                            const int xx = x0 - 1 + px;
+                            const bool ok = row_ok && xx >= 0 && xx < a.W;
+                            const bf16* src = rowp + (long long)p * a.x_ps + (long long)(ok ? xx : 0) * CIN + cg * 8;
+                            cp_async16(dst + p * plane_bytes + cg * kCgBytes + px * 16, src, ok ? 16u : 0u);
+                        }
                     }
                 }
-                __syncwarp();
+                cp_async_commit();
+                if ((int)(g + 1 - signalled) > look) {   // rows <= g - look have landed for this lane
+                    if (look >= 12) cp_async_wait<12>();
+                    else if (look >= 4) cp_async_wait<4>();
+                    else if (look >= 1) cp_async_wait<1>();
+                    else cp_async_wait<0>();
+                    const int lk = look >= 12 ? 12 : look >= 4 ? 4 : look >= 1 ? 1 : 0;
+                    hand_over(g + 1 - lk);
+                }
             }
         }
+        cp_async_wait<0>();
+        hand_over(g);
     } else if (warp == 9) {
         // ---- MMA issue: per output row, STEPS x (products of planes) MMAs of 128 pixels x Npad x 16
         const uint32_t idesc = idesc_bf16(NPAD, 0, 0);
@@ -363,7 +401,7 @@ struct ThinPlan {
 };
 
 template <int CIN, int P, int SPLIT, int NPAD>
-static int launch_thin(const CUtensorMap& tmA, ThinArgs& a, cudaStream_t stream) {
+static int launch_thin(ThinArgs& a, cudaStream_t stream) {
     static bool attr = false;
     static ThinPlan plan;   // CTAs per SM, ring depth and shared memory of this instance
     auto kern = conv_thin_kernel<CIN, P, SPLIT, NPAD>;
@@ -380,13 +418,17 @@ static int launch_thin(const CUtensorMap& tmA, ThinArgs& a, cudaStream_t stream)
         const int row = P * (CIN / 8) * kCgBytes;
         ThinPlan pl = {0, 0, 0};
         const int cap = thin_occ_cap();
-        for (int occ = cap < 512 / ncols ? cap : 512 / ncols; occ >= 1 && pl.occ == 0; --occ) {
-            for (int ring = 8; ring >= 4 && pl.occ == 0; ring >>= 1) {
-                const int smem = fixed + ring * row;
-                if (smem > kSmemLimit) continue;
-                int got = 0;
-                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, kern, kThinThreads, smem) != cudaSuccess) got = 0;
-                if (got >= occ) pl.occ = occ, pl.ring = ring, pl.smem = smem;
+        // preference: CTAs per SM first (two tiles in the epilogue / MMA pipe per SM), then ring depth (rows in flight)
+        const int occ_max = cap < 512 / ncols ? cap : 512 / ncols;
+        for (int pass = 0; pass < 2 && pl.occ == 0; ++pass) {
+            for (int occ = occ_max; occ >= 1 && pl.occ == 0; --occ) {
+                for (int ring = pass == 0 ? 16 : 4; ring >= (pass == 0 ? 8 : 4) && pl.occ == 0; ring >>= 1) {
+                    const int smem = fixed + ring * row;
+                    if (smem > kSmemLimit) continue;
+                    int got = 0;
+                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, kern, kThinThreads, smem) != cudaSuccess) got = 0;
+                    if (got >= occ) pl.occ = occ, pl.ring = ring, pl.smem = smem;
+                }
             }
         }
         if (pl.occ == 0) {
@@ -418,8 +460,9 @@ static int launch_thin(const CUtensorMap& tmA, ThinArgs& a, cudaStream_t stream)
     a.chunks_y = a.H / a.RC;
     a.total_units = a.N * a.strips * a.chunks_y;
     a.ring = best_pl.ring;
-    a.ring_log2 = best_pl.ring == 8 ? 3 : 2;
-    kern<<<best_grid, kThinThreads, best_pl.smem, stream>>>(tmA, a);
+    a.ring_log2 = best_pl.ring == 16 ? 4 : best_pl.ring == 8 ? 3 : 2;
+    a.look = best_pl.ring == 16 ? 12 : best_pl.ring == 8 ? 4 : 1;   // <= ring - 3: the MMA window holds three rows
+    kern<<<best_grid, kThinThreads, best_pl.smem, stream>>>(a);
     return PGK_OK;
 }
 
@@ -433,7 +476,7 @@ extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N
     a.N = N, a.H = H, a.W = W, a.Cout = Cout;
     a.Npad = Cout < 16 ? 16 : Cout;
     a.strips = W / 128;
-    a.RC = a.chunks_y = a.total_units = a.ring = a.ring_log2 = 0;   // chosen by launch_thin
+    a.RC = a.chunks_y = a.total_units = a.ring = a.ring_log2 = a.look = 0;   // chosen by launch_thin
     a.Pout = P;
     a.split_acc = Pr == 3 ? 1 : 0;
     PGK_REQUIRE(wpack_ps == pgk_pack_thin_plane_elems(Cin, Cout), "pgk_conv_thin: wpack plane stride mismatch");
@@ -443,20 +486,13 @@ extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N
     a.mask = make_planes(mask_ref, mask_ps, P);
     a.out_scale = out_scale;
     a.out = make_planes(out, out_ps, P);
-    CUtensorMap tmA;
-    {
-        unsigned long long dims[5] = {(unsigned long long)Cin, (unsigned long long)W, (unsigned long long)H,
-                                      (unsigned long long)N, (unsigned long long)P};
-        unsigned long long str[4] = {2ull * Cin, 2ull * Cin * W, 2ull * Cin * W * H,
-                                     P > 1 ? 2ull * x_ps : 2ull * Cin * W * H * N};
-        unsigned box[5] = {8u, 130u, 1u, 1u, 1u};
-        int rc = pgk_make_tmap(&tmA, x, 5, dims, str, box, 0, "pgk_conv_thin(x)");
-        if (rc) return rc;
-    }
+    a.x = (const bf16*)x;
+    a.x_ps = x_ps;
+    PGK_REQUIRE((((uintptr_t)x) & 15) == 0 && (P == 1 || (x_ps * 2) % 16 == 0), "pgk_conv_thin: x must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = PGK_ERR_ARG;
 #define PGK_THIN_CASE_N(C_, P_, S_, N_) \
-    if (Cin == C_ && Pr == P_ && a.split_acc == S_ && a.Npad == N_) rc = launch_thin<C_, P_, S_, N_>(tmA, a, st);
+    if (Cin == C_ && Pr == P_ && a.split_acc == S_ && a.Npad == N_) rc = launch_thin<C_, P_, S_, N_>(a, st);
 #define PGK_THIN_CASE(C_, P_, S_) PGK_THIN_CASE_N(C_, P_, S_, 16) PGK_THIN_CASE_N(C_, P_, S_, 32) PGK_THIN_CASE_N(C_, P_, S_, 64)
     PGK_THIN_CASE(8, 1, 0) PGK_THIN_CASE(16, 1, 0) PGK_THIN_CASE(32, 1, 0)
     PGK_THIN_CASE(8, 2, 0) PGK_THIN_CASE(16, 2, 0) PGK_THIN_CASE(32, 2, 0)

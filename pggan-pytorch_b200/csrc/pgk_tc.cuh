@@ -64,6 +64,33 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
     } while (!done);
 }
 
+// one non-blocking test of a phase
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+
+// ---- cp.async (LDGSTS): 16 bytes per thread, global -> shared, zero fill when src_bytes == 0 ----------------
+// Used where the shared-memory layout wanted by the tensor core is a permutation of the global one at 16-byte
+// granularity: a TMA box with a 16-byte inner extent moves one such row per few cycles (measured: the thin conv was
+// bound by exactly that, ~5 cycles per 16-byte box row, independent of CTAs per SM), while a warp of cp.async moves
+// 512 contiguous bytes per instruction.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---- TMA ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");

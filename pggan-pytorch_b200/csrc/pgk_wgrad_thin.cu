@@ -5,7 +5,9 @@
 //
 // The reduction runs over pixels, so both operands must be K-major along x -- the transpose of how activations are
 // stored (channels innermost).  Per CTA (persistent, streaming rows like pgk_conv_thin.cu):
-//   warp 4      TMA: halo rows of X ([Cin/8][130+ px][8 ch], zero filled outside the image) and rows of G into raw rings;
+//   warp 4      producer: halo rows of X ([Cin/8][130+ px][8 ch], zero filled outside the image) and rows of G into raw
+//               rings, as 16-byte cp.async chunks (a warp instruction reads 512 contiguous bytes; a TMA box with a
+//               16-byte inner extent moves ~one such row per 5 cycles, which is what bounded the first version);
 //   warps 0-3   transpose in shared memory with ldmatrix.trans + stmatrix (8x8 bf16 blocks): every X row once into
 //               XT3 = three copies shifted by kx, stacked along M (row m = kx*Cin + ci), every G row once into GT;
 //   warp 5      per output row y: D[ky] (3*Cin x Cout, fp32 in TMEM) += XT3[row y+ky-1] * GT[row y]^T, K = 128 pixels
@@ -27,7 +29,13 @@ constexpr int kCgBytes = kRowPix * 16;   // one channel group of a raw X row
 constexpr int kGrp = 2048;               // one transposed 8-channel group: 16 pixel chunks x (8 ch x 8 px)
 constexpr int kSmemLimit = 227 * 1024;
 
+constexpr int kMaxRaw = 8;               // raw ring depth: 8, 4 or 2 rows of X and of G
+
 struct WThinArgs {
+    const bf16* x;            // X planes (N,H,W,cin_total), x_ps elements apart
+    const bf16* g;            // G planes (N,H,W,Cout), g_ps elements apart
+    long long x_ps, g_ps;
+    int raw, raw_log2, look;  // raw ring depth and the rows (X or G) the producer keeps in flight
     int H, W, Cout, Npad, CGO;
     int RC, chunks_y, strips;
     int ngroups, group_n;
@@ -42,7 +50,7 @@ struct WThinArgs {
 
 template <int CIN, int P>
 __global__ void __launch_bounds__(kThreads, 2)
-wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WThinArgs a) {
+wgrad_thin_kernel(const WThinArgs a) {
     // row groups of XT3: 3 * CG shifted copies + one group whose first row is all ones (the bias-gradient row)
     constexpr int CG = CIN / 8, XG = 3 * CG;
     constexpr uint32_t xt_plane = (XG + 1) * kGrp, xt_buf = P * xt_plane;
@@ -55,29 +63,27 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const uint32_t rawg_plane = gt_plane, rawg_slot = gt_slot;
     const uint32_t xt0 = sbase, gt0 = sbase + a.off_gt, rawx0 = sbase + a.off_rawx, rawg0 = sbase + a.off_rawg;
     const uint32_t bars = sbase + a.off_bars;
-    auto xfull = [&](int s) { return bars + 8u * s; };          // [2]
-    auto xempty = [&](int s) { return bars + 16u + 8u * s; };   // [2]
-    auto gfull = [&](int s) { return bars + 32u + 8u * s; };    // [2]
-    auto gempty = [&](int s) { return bars + 48u + 8u * s; };   // [2]
-    auto xtfull = [&](int s) { return bars + 64u + 8u * s; };   // [4]
-    auto xtempty = [&](int s) { return bars + 96u + 8u * s; };  // [4]
-    auto gtfull = [&](int s) { return bars + 128u + 8u * s; };  // [2]
-    auto gtempty = [&](int s) { return bars + 144u + 8u * s; }; // [2]
-    const uint32_t done = bars + 160u, tptr = bars + 168u;
+    const int kRaw = a.raw, kRawLog = a.raw_log2;
+    auto xfull = [&](int s) { return bars + 8u * s; };                       // [kMaxRaw]
+    auto xempty = [&](int s) { return bars + 8u * (kMaxRaw + s); };          // [kMaxRaw]
+    auto gfull = [&](int s) { return bars + 8u * (2 * kMaxRaw + s); };       // [kMaxRaw]
+    auto gempty = [&](int s) { return bars + 8u * (3 * kMaxRaw + s); };      // [kMaxRaw]
+    const uint32_t bars2 = bars + 32u * kMaxRaw;
+    auto xtfull = [&](int s) { return bars2 + 8u * s; };           // [4]
+    auto xtempty = [&](int s) { return bars2 + 32u + 8u * s; };    // [4]
+    auto gtfull = [&](int s) { return bars2 + 64u + 8u * s; };     // [2]
+    auto gtempty = [&](int s) { return bars2 + 80u + 8u * s; };    // [2]
+    const uint32_t done = bars2 + 96u, tptr = bars2 + 104u;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < kRaw; ++s) {
             mbar_init(xfull(s), 1), mbar_init(xempty(s), 4);
             mbar_init(gfull(s), 1), mbar_init(gempty(s), 4);
-            mbar_init(gtfull(s), 4), mbar_init(gtempty(s), 1);
         }
+        for (int s = 0; s < 2; ++s) mbar_init(gtfull(s), 4), mbar_init(gtempty(s), 1);
         for (int s = 0; s < 4; ++s) mbar_init(xtfull(s), 4), mbar_init(xtempty(s), 1);
         mbar_init(done, 1);
         fence_barrier_init();
-    }
-    if (warp == 4 && lane == 0) {
-        tma_prefetch_desc(&tmX);
-        tma_prefetch_desc(&tmG);
     }
     // the group holding the ones row: everything but row 0 of plane 0 stays zero for the whole kernel
     for (uint32_t o = threadIdx.x * 16u; o < 4u * P * kGrp; o += kThreads * 16u) {
@@ -105,46 +111,94 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     };
 
     if (warp == 4) {
-        // ---- TMA producer: X row j of the unit, then (from j = 2) G row j - 2
-        uint32_t gx = 0, gg = 0;
+        // ---- producer: X row j of the unit, then (from j = 2) G row j - 2, each one cp.async group of 16-byte chunks
+        // (chunk q of a row = byte 16 * q of the global row segment; home [channel group][pixel]).  `look` rows stay
+        // in flight; bit (k & 31) of `kinds` remembers whether the k-th requested row was a G row, so that rows are
+        // handed to the transposers in request order on the right barrier.
+        uint32_t req = 0, signalled = 0, kinds = 0, gx = 0, gg = 0, sx = 0, sg = 0;
+        auto hand_over = [&](uint32_t upto) {
+            fence_proxy_async();
+            __syncwarp();
+            for (uint32_t r = signalled; r < upto; ++r) {
+                if ((kinds >> (r & 31)) & 1) {
+                    if (lane == 0) mbar_arrive(gfull(sg & (kRaw - 1)));
+                    ++sg;
+                } else {
+                    if (lane == 0) mbar_arrive(xfull(sx & (kRaw - 1)));
+                    ++sx;
+                }
+            }
+            signalled = upto;
+        };
+        const int look = a.look;
+        auto acquire = [&](uint32_t bar, uint32_t par) {
+            if (!__all_sync(0xffffffffu, mbar_test(bar, par))) {
+                cp_async_wait<0>();   // never sleep on a busy slot while holding rows back (the consumers may need them)
+                hand_over(req);
+                mbar_wait_spin(bar, par);
+            }
+        };
+        auto after_request = [&](bool is_g) {
+            cp_async_commit();
+            kinds = (kinds & ~(1u << (req & 31))) | ((is_g ? 1u : 0u) << (req & 31));
+            ++req;
+            if ((int)(req - signalled) > look) {
+                if (look >= 8) cp_async_wait<8>();
+                else if (look >= 4) cp_async_wait<4>();
+                else if (look >= 1) cp_async_wait<1>();
+                else cp_async_wait<0>();
+                const int lk = look >= 8 ? 8 : look >= 4 ? 4 : look >= 1 ? 1 : 0;
+                hand_over(req - lk);
+            }
+        };
         for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
             int xn, gn, x0, ya;
             unit_coords(u, xn, gn, x0, ya);
             for (int j = 0; j < a.RC + 2; ++j) {
                 {
-                    const int s = gx & 1;
-                    mbar_wait_spin(xempty(s), ((gx >> 1) & 1) ^ 1);
-                    if (elect_one()) {
-                        const uint32_t fb = xfull(s);
-                        mbar_expect_tx(fb, P * CG * 130 * 16);
-                        const uint32_t dst = rawx0 + s * rawx_slot;
+                    const int s = gx & (kRaw - 1);
+                    acquire(xempty(s), ((gx >> kRawLog) & 1) ^ 1);
+                    const int y = ya - 1 + j;
+                    const bool row_ok = y >= 0 && y < a.H;
+                    const bf16* rowp = a.x + (((long long)xn * a.H + (row_ok ? y : 0)) * a.W) * a.cin_total + a.c0;
+                    const uint32_t dst = rawx0 + s * rawx_slot;
 #pragma unroll
-                        for (int p = 0; p < P; ++p) {
+                    for (int p = 0; p < P; ++p) {
 #pragma unroll
-                            for (int cg = 0; cg < CG; ++cg)
-                                tma_load_5d(dst + p * rawx_plane + cg * kCgBytes, &tmX, fb, a.c0 + cg * 8, x0 - 1, ya - 1 + j, xn, p);
+                        for (int it = 0; it < (130 * CG + 31) / 32; ++it) {
+                            const int q = it * 32 + lane;
+                            if (q < 130 * CG) {
+                                const int px = q / CG, cg = q % CG;
+                                const int xx = x0 - 1 + px;
+                                const bool ok = row_ok && xx >= 0 && xx < a.W;
+                                const bf16* src = rowp + (long long)p * a.x_ps + (long long)(ok ? xx : 0) * a.cin_total + cg * 8;
+                                cp_async16(dst + p * rawx_plane + cg * kCgBytes + px * 16, src, ok ? 16u : 0u);
+                            }
                         }
                     }
-                    __syncwarp();
                     ++gx;
+                    after_request(false);
                 }
                 if (j >= 2) {
-                    const int s = gg & 1;
-                    mbar_wait_spin(gempty(s), ((gg >> 1) & 1) ^ 1);
-                    if (elect_one()) {
-                        const uint32_t fb = gfull(s);
-                        mbar_expect_tx(fb, P * a.CGO * 128 * 16);
-                        const uint32_t dst = rawg0 + s * rawg_slot;
+                    const int s = gg & (kRaw - 1);
+                    acquire(gempty(s), ((gg >> kRawLog) & 1) ^ 1);
+                    const bf16* rowp = a.g + (((long long)gn * a.H + (ya + j - 2)) * a.W + x0) * a.Cout;
+                    const uint32_t dst = rawg0 + s * rawg_slot;
+                    const int nchunk = 128 * a.CGO;
 #pragma unroll
-                        for (int p = 0; p < P; ++p)
-                            for (int cg = 0; cg < a.CGO; ++cg)
-                                tma_load_5d(dst + p * rawg_plane + cg * kGrp, &tmG, fb, cg * 8, x0, ya + j - 2, gn, p);
+                    for (int p = 0; p < P; ++p) {
+                        for (int q = lane; q < nchunk; q += 32) {
+                            const int px = q / a.CGO, cg = q - px * a.CGO;
+                            cp_async16(dst + p * rawg_plane + cg * kGrp + px * 16, rowp + (long long)p * a.g_ps + (long long)q * 8, 16u);
+                        }
                     }
-                    __syncwarp();
                     ++gg;
+                    after_request(true);
                 }
             }
         }
+        cp_async_wait<0>();
+        hand_over(req);
     } else if (warp == 5) {
         // ---- MMA issue
         const uint32_t idesc = idesc_bf16(a.Npad, 0, 0);
@@ -202,8 +256,8 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const uint32_t one16 = (a.db && ((a.bias_mask >> grp) & 1)) ? 0x3F803F80u : 0u;   // bf16 1.0 pairs
             for (int j = 0; j < a.RC + 2; ++j) {
                 {
-                    const int s = gx & 1, b = gx & 3;
-                    mbar_wait(xfull(s), (gx >> 1) & 1);
+                    const int s = gx & (kRaw - 1), b = gx & 3;
+                    mbar_wait(xfull(s), (gx >> kRawLog) & 1);
                     mbar_wait(xtempty(b), ((gx >> 2) & 1) ^ 1);
                     const uint32_t src0 = rawx0 + s * rawx_slot, dst0 = xt0 + b * xt_buf;
                     // ops: (plane, kx, channel group, 32-pixel block)
@@ -228,10 +282,10 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     ++gx;
                 }
                 if (j >= 2) {
-                    const int s = gg & 1;
-                    mbar_wait(gfull(s), (gg >> 1) & 1);
-                    mbar_wait(gtempty(s), ((gg >> 1) & 1) ^ 1);
-                    const uint32_t src0 = rawg0 + s * rawg_slot, dst0 = gt0 + s * gt_slot;
+                    const int s = gg & (kRaw - 1), t = gg & 1;
+                    mbar_wait(gfull(s), (gg >> kRawLog) & 1);
+                    mbar_wait(gtempty(t), ((gg >> 1) & 1) ^ 1);
+                    const uint32_t src0 = rawg0 + s * rawg_slot, dst0 = gt0 + t * gt_slot;
                     for (int o = warp; o < P * a.CGO * 4; o += 4) {
                         const int blk = o & 3;
                         const int r = o >> 2;
@@ -244,7 +298,7 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     __syncwarp();
                     if (lane == 0) {
                         mbar_arrive(gempty(s));
-                        mbar_arrive(gtfull(s));
+                        mbar_arrive(gtfull(t));
                     }
                     ++gg;
                 }
@@ -282,7 +336,7 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
 }  // namespace
 
-static size_t wthin_layout(int Cin, int Cout, int Pr, WThinArgs* a) {
+static size_t wthin_layout(int Cin, int Cout, int Pr, int R, WThinArgs* a) {
     const int CG = Cin / 8, CGO = Cout / 8, npad = Cout < 16 ? 16 : Cout;
     const size_t xt_buf = (size_t)Pr * (3 * CG + 1) * kGrp, gt_slot = (size_t)Pr * CGO * kGrp;
     const size_t rawx_slot = (size_t)Pr * CG * kCgBytes, rawg_slot = gt_slot;
@@ -290,10 +344,10 @@ static size_t wthin_layout(int Cin, int Cout, int Pr, WThinArgs* a) {
     const size_t off_gt = off;
     off += 2 * gt_slot;
     const size_t off_rawx = off;
-    off += 2 * rawx_slot;
+    off += (size_t)R * rawx_slot;
     off = (off + 127) & ~(size_t)127;
     const size_t off_rawg = off;
-    off += 2 * rawg_slot;
+    off += (size_t)R * rawg_slot;
     // the MMAs read 16 row groups of A (3*Cin/8 are real) and Npad/8 of B: keep those reads inside the allocation
     size_t need = 3 * xt_buf + (size_t)(Pr - 1) * (3 * CG + 1) * kGrp + 16 * kGrp;
     const size_t need_b = off_gt + gt_slot + (size_t)(Pr - 1) * CGO * kGrp + (size_t)(npad / 8) * kGrp;
@@ -304,7 +358,7 @@ static size_t wthin_layout(int Cin, int Cout, int Pr, WThinArgs* a) {
         a->off_gt = (uint32_t)off_gt, a->off_rawx = (uint32_t)off_rawx, a->off_rawg = (uint32_t)off_rawg;
         a->off_bars = (uint32_t)off;
     }
-    return off + 256 + 1024;
+    return off + 512 + 1024;
 }
 
 extern "C" int pgk_wgrad_thin_supported(int H, int W, int Cin, int Cout, int KS, int ups, int ngroups, int group_n,
@@ -314,42 +368,65 @@ extern "C" int pgk_wgrad_thin_supported(int H, int W, int Cin, int Cout, int KS,
     if (Cout != 8 && Cout != 16 && Cout != 32 && Cout != 64) return 0;
     if (W % 128 || H < 8 || H % 8) return 0;
     if (Pr < 1 || Pr > 3) return 0;
-    return wthin_layout(Cin, Cout, Pr, nullptr) <= (size_t)kSmemLimit;
+    return wthin_layout(Cin, Cout, Pr, 2, nullptr) <= (size_t)kSmemLimit;
 }
 
+struct WThinPlan {
+    int occ, raw, smem;
+};
+
 template <int CIN, int P>
-static int launch_wthin(const CUtensorMap& tmX, const CUtensorMap& tmG, const WThinArgs& a, int smem,
-                        cudaStream_t stream) {
+static int launch_wthin(WThinArgs& a, cudaStream_t stream) {
+    auto kern = wgrad_thin_kernel<CIN, P>;
     static bool attr = false;
+    static WThinPlan plans[4];   // by Cout / 8 -> index 0..3 (8, 16, 32, 64)
+    static bool have[4] = {};
     if (!attr) {
-        cudaError_t e =
-            cudaFuncSetAttribute(wgrad_thin_kernel<CIN, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e != cudaSuccess) {
             pgk_set_error("pgk_wgrad_thin: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return PGK_ERR_CUDA;
         }
         attr = true;
     }
-    // co-resident CTAs hide the latency of the two-deep raw rings (same reasoning and knob as pgk_conv_thin.cu);
-    // limits: shared memory (asked of the runtime) and 512 TMEM columns per SM
-    int occ = 1;
-    {
+    const int pi = a.Cout == 8 ? 0 : a.Cout == 16 ? 1 : a.Cout == 32 ? 2 : 3;
+    if (!have[pi]) {
+        // CTAs per SM first (co-resident CTAs overlap one CTA's transposes with the other's loads; PGK_THIN_OCC caps
+        // it, default 2), then raw ring depth.  Limits: shared memory (asked of the runtime), 512 TMEM columns per SM.
         const char* e = getenv("PGK_THIN_OCC");
         int cap = e ? atoi(e) : 2;
         cap = cap < 1 ? 1 : cap > 4 ? 4 : cap;
         const int ncols = 3 * a.Npad <= 64 ? 64 : 3 * a.Npad <= 128 ? 128 : 256;
         if (cap > 512 / ncols) cap = 512 / ncols;
-        int got = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, wgrad_thin_kernel<CIN, P>, kThreads, smem) != cudaSuccess) {
-            cudaGetLastError();
-            got = 1;
+        WThinPlan pl = {0, 0, 0};
+        for (int pass = 0; pass < 2 && pl.occ == 0; ++pass) {
+            for (int occ = cap; occ >= 1 && pl.occ == 0; --occ) {
+                for (int R = pass == 0 ? 8 : 2; R >= (pass == 0 ? 4 : 2) && pl.occ == 0; R >>= 1) {
+                    const size_t smem = wthin_layout(CIN, a.Cout, P, R, nullptr);
+                    if (smem > (size_t)kSmemLimit) continue;
+                    int got = 0;
+                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, kern, kThreads, smem) != cudaSuccess) {
+                        cudaGetLastError();
+                        got = 0;
+                    }
+                    if (got >= occ) pl.occ = occ, pl.raw = R, pl.smem = (int)smem;
+                }
+            }
         }
-        occ = got < cap ? got : cap;
-        if (occ < 1) occ = 1;
+        if (pl.occ == 0) {
+            pgk_set_error("pgk_wgrad_thin: no shared-memory plan for Cin %d Cout %d P %d", CIN, a.Cout, P);
+            return PGK_ERR_ARG;
+        }
+        plans[pi] = pl, have[pi] = true;
     }
-    int grid = occ * pgk_num_sms();
+    const WThinPlan pl = plans[pi];
+    wthin_layout(CIN, a.Cout, P, pl.raw, &a);
+    a.raw = pl.raw;
+    a.raw_log2 = pl.raw == 8 ? 3 : pl.raw == 4 ? 2 : 1;
+    a.look = pl.raw == 8 ? 8 : pl.raw == 4 ? 4 : 1;
+    int grid = pl.occ * pgk_num_sms();
     if (grid > a.total_units) grid = a.total_units;
-    wgrad_thin_kernel<CIN, P><<<grid, kThreads, smem, stream>>>(tmX, tmG, a);
+    kern<<<grid, kThreads, pl.smem, stream>>>(a);
     return PGK_OK;
 }
 
@@ -368,41 +445,21 @@ extern "C" int pgk_wgrad_thin(const void* x, long long x_ps, const void* g, long
     a.chunks_y = H / a.RC;
     a.strips = W / 128;
     a.ngroups = ngroups, a.group_n = group_n;
-    int xmax = 0, gmax = 0;
     for (int i = 0; i < 4; ++i) {
         a.xoff[i] = i < ngroups ? xoff[i] : 0;
         a.goff[i] = i < ngroups ? goff[i] : 0;
-        if (a.xoff[i] > xmax) xmax = a.xoff[i];
-        if (a.goff[i] > gmax) gmax = a.goff[i];
     }
     a.total_units = ngroups * group_n * a.strips * a.chunks_y;
     a.dwp = dwp, a.db = db, a.bias_mask = bias_mask;
     a.cin_total = cin_total, a.c0 = c0;
-    const int smem = (int)wthin_layout(Cin, Cout, Pr, &a);
-    CUtensorMap tmX, tmG;
-    {
-        const unsigned long long Ct = (unsigned long long)cin_total;
-        unsigned long long dims[5] = {Ct, (unsigned long long)W, (unsigned long long)H,
-                                      (unsigned long long)(xmax + group_n), (unsigned long long)P};
-        unsigned long long str[4] = {2ull * Ct, 2ull * Ct * W, 2ull * Ct * W * H,
-                                     P > 1 ? 2ull * x_ps : 2ull * Ct * W * H * (xmax + group_n)};
-        unsigned box[5] = {8u, 130u, 1u, 1u, 1u};
-        int rc = pgk_make_tmap(&tmX, x, 5, dims, str, box, 0, "pgk_wgrad_thin(x)");
-        if (rc) return rc;
-    }
-    {
-        unsigned long long dims[5] = {(unsigned long long)Cout, (unsigned long long)W, (unsigned long long)H,
-                                      (unsigned long long)(gmax + group_n), (unsigned long long)P};
-        unsigned long long str[4] = {2ull * Cout, 2ull * Cout * W, 2ull * Cout * W * H,
-                                     P > 1 ? 2ull * g_ps : 2ull * Cout * W * H * (gmax + group_n)};
-        unsigned box[5] = {8u, 128u, 1u, 1u, 1u};
-        int rc = pgk_make_tmap(&tmG, g, 5, dims, str, box, 0, "pgk_wgrad_thin(g)");
-        if (rc) return rc;
-    }
+    a.x = (const bf16*)x, a.g = (const bf16*)g;
+    a.x_ps = x_ps, a.g_ps = g_ps;
+    PGK_REQUIRE((((uintptr_t)x | (uintptr_t)g) & 15) == 0 && (Pr == 1 || ((x_ps | g_ps) * 2) % 16 == 0),
+                "pgk_wgrad_thin: x and g must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = PGK_ERR_ARG;
 #define PGK_WTHIN_CASE(C_, P_) \
-    if (Cin == C_ && Pr == P_) rc = launch_wthin<C_, P_>(tmX, tmG, a, smem, st);
+    if (Cin == C_ && Pr == P_) rc = launch_wthin<C_, P_>(a, st);
     PGK_WTHIN_CASE(8, 1) PGK_WTHIN_CASE(16, 1) PGK_WTHIN_CASE(32, 1)
     PGK_WTHIN_CASE(8, 2) PGK_WTHIN_CASE(16, 2) PGK_WTHIN_CASE(32, 2)
     PGK_WTHIN_CASE(8, 3) PGK_WTHIN_CASE(16, 3) PGK_WTHIN_CASE(32, 3)
