@@ -19,6 +19,7 @@
 //     backward mask / scale, split into planes and store straight to global memory (a thread's pixel row is
 //     contiguous with its neighbours': fully coalesced without staging).
 #include <stdlib.h>
+#include <string.h>
 
 #include "pgk_tc.cuh"
 
@@ -39,6 +40,8 @@ struct ThinArgs {
     int N, H, W, Cout, Npad;
     int RC, chunks_y, strips;   // rows per unit, units per column strip, W / 128
     int ring, ring_log2, look;  // row buffers; rows the producer keeps in flight before it hands the oldest over
+    int pair;                   // MMA warp interleaves the K steps of two output rows (two accumulators)
+    int tma;                    // producer: 1 = TMA boxes (16-byte inner extent), 0 = cp.async chunks
     int total_units;
     int Pout, split_acc;
     const bf16* wpack;          // [P][STEPS][2][Npad][8]
@@ -63,7 +66,8 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
 }
 
 template <int CIN, int P, int SPLIT, int NPAD>
-__global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const ThinArgs a) {
+__global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                    const ThinArgs a) {
     constexpr int CG = Steps<CIN>::CG, STEPS = Steps<CIN>::N;
     constexpr uint32_t plane_bytes = CG * kCgBytes;
     constexpr uint32_t row_bytes = P * plane_bytes;
@@ -121,7 +125,33 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const ThinAr
         ya = cy * a.RC;
     };
 
-    if (warp == 8) {
+    if (warp == 8 && a.tma) {
+        // ---- producer, TMA flavour: per row and plane CG boxes of [130 pixels][8 channels]; halo and out-of-image
+        // rows are zero filled by the hardware
+        constexpr uint32_t tx_bytes = P * CG * 130 * 16;
+        if (lane == 0) tma_prefetch_desc(&tmA);
+        uint32_t g = 0;
+        for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
+            int n, x0, ya;
+            unit_coords(u, n, x0, ya);
+            for (int j = 0; j < a.RC + 2; ++j, ++g) {
+                const int s = g & (kRing - 1);
+                mbar_wait_spin(rempty(s), ((g >> kRingLog) & 1) ^ 1);
+                if (elect_one()) {
+                    const uint32_t fb = rfull(s);
+                    mbar_expect_tx(fb, tx_bytes);
+                    const uint32_t dst = rows0 + s * row_bytes;
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+#pragma unroll
+                        for (int cg = 0; cg < CG; ++cg)
+                            tma_load_5d(dst + p * plane_bytes + cg * kCgBytes, &tmA, fb, cg * 8, x0 - 1, ya - 1 + j, n, p);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 8) {
         // ---- producer: one input row per step of the ring, as 130 * CG 16-byte chunks (pixel, channel group) per
         // plane.  Chunk q of a row sits at byte 16 * q of the global row segment, so a warp instruction reads 512
         // contiguous bytes; its shared-memory home is [channel group][pixel].  Up to `look` rows stay in flight
@@ -188,52 +218,84 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const ThinAr
         const uint64_t bdesc0 = smem_desc(w0, (uint32_t)NPAD * 16u, 128, 0);
         constexpr uint32_t wstep16 = wstep >> 4, wplane16 = wplane >> 4;
         uint32_t g = 0, ti = 0;
+        // one K = 16 step of output row `row` (window rows rb[0..2]) into accumulator buffer b
+        auto issue_step = [&](int st, const uint32_t* rb, int b) {
+            const uint32_t d_main = tmem + b * acc_cols, d_corr = d_main + NPAD;
+            int dy, xoff, cgp;
+            if (CIN == 8) {
+                dy = st >> 1, xoff = (st & 1) * 2, cgp = 0;      // (dx -1, dx 0) | (dx +1, zero weights)
+            } else {
+                const int tap = st / (CIN / 16);
+                cgp = st % (CIN / 16);
+                dy = tap / 3, xoff = tap % 3;
+            }
+#pragma unroll
+            for (int pi = 0; pi < P; ++pi) {
+#pragma unroll
+                for (int pj = 0; pj < P - pi; ++pj) {
+                    const uint64_t ad = adesc_hi | (uint64_t)(rb[dy] + (pi * plane_bytes + 2 * cgp * kCgBytes + xoff * 16) / 16);
+                    const uint64_t bd = bdesc0 + (uint32_t)(pj * wplane16 + st * wstep16);
+                    if (pi + pj == 0 || !SPLIT)
+                        mma_bf16(d_main, ad, bd, idesc, (st == 0 && pi + pj == 0) ? 0u : 1u);
+                    else
+                        mma_bf16(d_corr, ad, bd, idesc, (st == 0 && pi == 0 && pj == 1) ? 0u : 1u);
+                }
+            }
+        };
         for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
             mbar_wait_spin(rfull(g & (kRing - 1)), (g >> kRingLog) & 1);
             mbar_wait_spin(rfull((g + 1) & (kRing - 1)), ((g + 1) >> kRingLog) & 1);
-            for (int i = 0; i < a.RC; ++i, ++g, ++ti) {
-                mbar_wait_spin(rfull((g + 2) & (kRing - 1)), ((g + 2) >> kRingLog) & 1);
-                const int b = ti & (kAcc - 1);
-                mbar_wait_spin(aempty(b), ((ti / kAcc) & 1) ^ 1);
-                fence_after();
-                const uint32_t d_main = tmem + b * acc_cols, d_corr = d_main + NPAD;
-                uint32_t rb[3];
+            if (a.pair) {
+                // two output rows at a time: their MMA chains accumulate into different TMEM buffers, so the tensor
+                // core can overlap the (latency-bound, N <= 64) steps of one row with those of the other
+                for (int i = 0; i < a.RC; i += 2, g += 2, ti += 2) {
+                    mbar_wait_spin(rfull((g + 2) & (kRing - 1)), ((g + 2) >> kRingLog) & 1);
+                    mbar_wait_spin(rfull((g + 3) & (kRing - 1)), ((g + 3) >> kRingLog) & 1);
+                    const int b0 = ti & (kAcc - 1), b1 = (ti + 1) & (kAcc - 1);
+                    mbar_wait_spin(aempty(b0), ((ti / kAcc) & 1) ^ 1);
+                    mbar_wait_spin(aempty(b1), (((ti + 1) / kAcc) & 1) ^ 1);
+                    fence_after();
+                    uint32_t rb[4];
 #pragma unroll
-                for (int dy = 0; dy < 3; ++dy) rb[dy] = (rows0 + ((g + dy) & (kRing - 1)) * row_bytes) >> 4;
-                if (elect_one()) {
+                    for (int dy = 0; dy < 4; ++dy) rb[dy] = (rows0 + ((g + dy) & (kRing - 1)) * row_bytes) >> 4;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int st = 0; st < STEPS; ++st) {
-                        // tap / channel-group pair of this K = 16 step
-                        int dy, xoff, cgp;
-                        if (CIN == 8) {
-                            dy = st >> 1, xoff = (st & 1) * 2, cgp = 0;      // (dx -1, dx 0) | (dx +1, zero weights)
-                        } else {
-                            const int tap = st / (CIN / 16);
-                            cgp = st % (CIN / 16);
-                            dy = tap / 3, xoff = tap % 3;
+                        for (int st = 0; st < STEPS; ++st) {
+                            issue_step(st, rb, b0);
+                            issue_step(st, rb + 1, b1);
                         }
-#pragma unroll
-                        for (int pi = 0; pi < P; ++pi) {
-#pragma unroll
-                            for (int pj = 0; pj < P - pi; ++pj) {
-                                const uint64_t ad =
-                                    adesc_hi | (uint64_t)(rb[dy] + (pi * plane_bytes + 2 * cgp * kCgBytes + xoff * 16) / 16);
-                                const uint64_t bd = bdesc0 + (uint32_t)(pj * wplane16 + st * wstep16);
-                                if (pi + pj == 0 || !SPLIT)
-                                    mma_bf16(d_main, ad, bd, idesc, (st == 0 && pi + pj == 0) ? 0u : 1u);
-                                else
-                                    mma_bf16(d_corr, ad, bd, idesc, (st == 0 && pi == 0 && pj == 1) ? 0u : 1u);
-                            }
-                        }
-                    }
-                    mma_commit(afull(b));
-                    mma_commit(rempty(g & (kRing - 1)));   // the top row of this window is done
-                    if (i == a.RC - 1) {
+                        mma_commit(afull(b0));
+                        mma_commit(afull(b1));
+                        mma_commit(rempty(g & (kRing - 1)));
                         mma_commit(rempty((g + 1) & (kRing - 1)));
-                        mma_commit(rempty((g + 2) & (kRing - 1)));
+                        if (i == a.RC - 2) {
+                            mma_commit(rempty((g + 2) & (kRing - 1)));
+                            mma_commit(rempty((g + 3) & (kRing - 1)));
+                        }
                     }
+                    __syncwarp();
                 }
-                __syncwarp();
+            } else {
+                for (int i = 0; i < a.RC; ++i, ++g, ++ti) {
+                    mbar_wait_spin(rfull((g + 2) & (kRing - 1)), ((g + 2) >> kRingLog) & 1);
+                    const int b = ti & (kAcc - 1);
+                    mbar_wait_spin(aempty(b), ((ti / kAcc) & 1) ^ 1);
+                    fence_after();
+                    uint32_t rb[3];
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) rb[dy] = (rows0 + ((g + dy) & (kRing - 1)) * row_bytes) >> 4;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int st = 0; st < STEPS; ++st) issue_step(st, rb, b);
+                        mma_commit(afull(b));
+                        mma_commit(rempty(g & (kRing - 1)));   // the top row of this window is done
+                        if (i == a.RC - 1) {
+                            mma_commit(rempty((g + 1) & (kRing - 1)));
+                            mma_commit(rempty((g + 2) & (kRing - 1)));
+                        }
+                    }
+                    __syncwarp();
+                }
             }
             g += 2;
         }
@@ -401,7 +463,7 @@ struct ThinPlan {
 };
 
 template <int CIN, int P, int SPLIT, int NPAD>
-static int launch_thin(ThinArgs& a, cudaStream_t stream) {
+static int launch_thin(const CUtensorMap& tmA, ThinArgs& a, cudaStream_t stream) {
     static bool attr = false;
     static ThinPlan plan;   // CTAs per SM, ring depth and shared memory of this instance
     auto kern = conv_thin_kernel<CIN, P, SPLIT, NPAD>;
@@ -418,18 +480,28 @@ static int launch_thin(ThinArgs& a, cudaStream_t stream) {
         const int row = P * (CIN / 8) * kCgBytes;
         ThinPlan pl = {0, 0, 0};
         const int cap = thin_occ_cap();
-        // preference: CTAs per SM first (two tiles in the epilogue / MMA pipe per SM), then ring depth (rows in flight)
+        // preference: CTAs per SM first (two tiles in the epilogue / MMA pipe per SM), then ring depth (rows in flight).
+        // Residency is computed here -- shared memory (+1 KB reserved per CTA) against the 228 KB of an SM, 512 TMEM
+        // columns, and registers through __launch_bounds__(kThinThreads, 2).
         const int occ_max = cap < 512 / ncols ? cap : 512 / ncols;
         for (int pass = 0; pass < 2 && pl.occ == 0; ++pass) {
-            for (int occ = occ_max; occ >= 1 && pl.occ == 0; --occ) {
+            for (int occ = occ_max > 2 ? 2 : occ_max; occ >= 1 && pl.occ == 0; --occ) {
                 for (int ring = pass == 0 ? 16 : 4; ring >= (pass == 0 ? 8 : 4) && pl.occ == 0; ring >>= 1) {
                     const int smem = fixed + ring * row;
-                    if (smem > kSmemLimit) continue;
-                    int got = 0;
-                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, kern, kThinThreads, smem) != cudaSuccess) got = 0;
-                    if (got >= occ) pl.occ = occ, pl.ring = ring, pl.smem = smem;
+                    if (smem > kSmemLimit || occ * (smem + 1024) > 228 * 1024) continue;
+                    pl.occ = occ, pl.ring = ring, pl.smem = smem;
                 }
             }
+        }
+        if (getenv("PGK_THIN_DEBUG")) {
+            int got = -1;
+            cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, kern, kThinThreads, pl.smem);
+            cudaFuncAttributes fa;
+            cudaFuncGetAttributes(&fa, kern);
+            fprintf(stderr, "pgk_conv_thin<%d,%d,%d,%d>: plan occ %d ring %d smem %d | runtime says %d blocks/SM (%s), regs %d, "
+                            "static smem %zu, max dyn %d\n", CIN, P, SPLIT, NPAD, pl.occ, pl.ring, pl.smem, got,
+                    cudaGetErrorString(oe), fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes);
+            cudaGetLastError();
         }
         if (pl.occ == 0) {
             cudaGetLastError();
@@ -461,8 +533,16 @@ static int launch_thin(ThinArgs& a, cudaStream_t stream) {
     a.total_units = a.N * a.strips * a.chunks_y;
     a.ring = best_pl.ring;
     a.ring_log2 = best_pl.ring == 16 ? 4 : best_pl.ring == 8 ? 3 : 2;
-    a.look = best_pl.ring == 16 ? 12 : best_pl.ring == 8 ? 4 : 1;   // <= ring - 3: the MMA window holds three rows
-    kern<<<best_grid, kThinThreads, best_pl.smem, stream>>>(a);
+    a.look = best_pl.ring == 16 ? 12 : best_pl.ring == 8 ? 4 : 1;   // <= ring - 4: the MMA window holds up to four rows
+    {
+        static int pair = -1;
+        if (pair < 0) {
+            const char* e = getenv("PGK_THIN_PAIR");
+            pair = e ? atoi(e) != 0 : 1;
+        }
+        a.pair = pair && best_pl.ring >= 8 && best_rc % 2 == 0;
+    }
+    kern<<<best_grid, kThinThreads, best_pl.smem, stream>>>(tmA, a);
     return PGK_OK;
 }
 
@@ -489,10 +569,27 @@ extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N
     a.x = (const bf16*)x;
     a.x_ps = x_ps;
     PGK_REQUIRE((((uintptr_t)x) & 15) == 0 && (P == 1 || (x_ps * 2) % 16 == 0), "pgk_conv_thin: x must be 16-byte aligned");
+    static int use_tma = -1;
+    if (use_tma < 0) {
+        const char* e = getenv("PGK_THIN_TMA");
+        use_tma = e ? atoi(e) != 0 : 0;
+    }
+    a.tma = use_tma;
+    CUtensorMap tmA;
+    memset(&tmA, 0, sizeof(tmA));
+    if (a.tma) {
+        unsigned long long dims[5] = {(unsigned long long)Cin, (unsigned long long)W, (unsigned long long)H,
+                                      (unsigned long long)N, (unsigned long long)P};
+        unsigned long long str[4] = {2ull * Cin, 2ull * Cin * W, 2ull * Cin * W * H,
+                                     P > 1 ? 2ull * x_ps : 2ull * Cin * W * H * N};
+        unsigned box[5] = {8u, 130u, 1u, 1u, 1u};
+        int rc = pgk_make_tmap(&tmA, x, 5, dims, str, box, 0, "pgk_conv_thin(x)");
+        if (rc) return rc;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     int rc = PGK_ERR_ARG;
 #define PGK_THIN_CASE_N(C_, P_, S_, N_) \
-    if (Cin == C_ && Pr == P_ && a.split_acc == S_ && a.Npad == N_) rc = launch_thin<C_, P_, S_, N_>(a, st);
+    if (Cin == C_ && Pr == P_ && a.split_acc == S_ && a.Npad == N_) rc = launch_thin<C_, P_, S_, N_>(tmA, a, st);
 #define PGK_THIN_CASE(C_, P_, S_) PGK_THIN_CASE_N(C_, P_, S_, 16) PGK_THIN_CASE_N(C_, P_, S_, 32) PGK_THIN_CASE_N(C_, P_, S_, 64)
     PGK_THIN_CASE(8, 1, 0) PGK_THIN_CASE(16, 1, 0) PGK_THIN_CASE(32, 1, 0)
     PGK_THIN_CASE(8, 2, 0) PGK_THIN_CASE(16, 2, 0) PGK_THIN_CASE(32, 2, 0)

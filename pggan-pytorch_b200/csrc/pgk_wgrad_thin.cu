@@ -395,7 +395,7 @@ static int launch_wthin(WThinArgs& a, cudaStream_t stream) {
         // it, default 2), then raw ring depth.  Limits: shared memory (asked of the runtime), 512 TMEM columns per SM.
         const char* e = getenv("PGK_THIN_OCC");
         int cap = e ? atoi(e) : 2;
-        cap = cap < 1 ? 1 : cap > 4 ? 4 : cap;
+        cap = cap < 1 ? 1 : cap > 2 ? 2 : cap;
         const int ncols = 3 * a.Npad <= 64 ? 64 : 3 * a.Npad <= 128 ? 128 : 256;
         if (cap > 512 / ncols) cap = 512 / ncols;
         WThinPlan pl = {0, 0, 0};
@@ -403,15 +403,21 @@ static int launch_wthin(WThinArgs& a, cudaStream_t stream) {
             for (int occ = cap; occ >= 1 && pl.occ == 0; --occ) {
                 for (int R = pass == 0 ? 8 : 2; R >= (pass == 0 ? 4 : 2) && pl.occ == 0; R >>= 1) {
                     const size_t smem = wthin_layout(CIN, a.Cout, P, R, nullptr);
-                    if (smem > (size_t)kSmemLimit) continue;
-                    int got = 0;
-                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, kern, kThreads, smem) != cudaSuccess) {
-                        cudaGetLastError();
-                        got = 0;
-                    }
-                    if (got >= occ) pl.occ = occ, pl.raw = R, pl.smem = (int)smem;
+                    // residency computed here: shared memory (+1 KB reserved per CTA) against the 228 KB of an SM
+                    // (registers are bounded by __launch_bounds__(kThreads, 2), TMEM columns by `cap` above)
+                    if (smem > (size_t)kSmemLimit || (size_t)occ * (smem + 1024) > (size_t)228 * 1024) continue;
+                    pl.occ = occ, pl.raw = R, pl.smem = (int)smem;
                 }
             }
+        }
+        if (getenv("PGK_THIN_DEBUG")) {
+            int got = -1;
+            cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, kern, kThreads, pl.smem);
+            cudaFuncAttributes fa;
+            cudaFuncGetAttributes(&fa, kern);
+            fprintf(stderr, "pgk_wgrad_thin<%d,%d> Cout %d: plan occ %d raw %d smem %d | runtime says %d blocks/SM (%s), regs %d\n",
+                    CIN, P, a.Cout, pl.occ, pl.raw, pl.smem, got, cudaGetErrorString(oe), fa.numRegs);
+            cudaGetLastError();
         }
         if (pl.occ == 0) {
             pgk_set_error("pgk_wgrad_thin: no shared-memory plan for Cin %d Cout %d P %d", CIN, a.Cout, P);
