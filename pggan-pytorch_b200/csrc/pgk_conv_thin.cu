@@ -572,7 +572,7 @@ extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N
     static int use_tma = -1;
     if (use_tma < 0) {
         const char* e = getenv("PGK_THIN_TMA");
-        use_tma = e ? atoi(e) != 0 : 0;
+        use_tma = e ? atoi(e) != 0 : 1;
     }
     a.tma = use_tma;
     CUtensorMap tmA;

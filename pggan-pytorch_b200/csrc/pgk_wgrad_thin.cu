@@ -16,6 +16,7 @@
 // Every activation byte is read from HBM once; the tensor-core work is tiny, the kernel is bound by HBM / the
 // shared-memory transposes.
 #include <stdlib.h>
+#include <string.h>
 
 #include "pgk_tc.cuh"
 
@@ -36,6 +37,8 @@ struct WThinArgs {
     const bf16* g;            // G planes (N,H,W,Cout), g_ps elements apart
     long long x_ps, g_ps;
     int raw, raw_log2, look;  // raw ring depth and the rows (X or G) the producer keeps in flight
+    int tma;                  // producer: 1 = TMA boxes, 0 = cp.async chunks
+    int ks_major;             // MMA issue order: 1 = the three ky accumulators interleaved per K step
     int H, W, Cout, Npad, CGO;
     int RC, chunks_y, strips;
     int ngroups, group_n;
@@ -50,7 +53,7 @@ struct WThinArgs {
 
 template <int CIN, int P>
 __global__ void __launch_bounds__(kThreads, 2)
-wgrad_thin_kernel(const WThinArgs a) {
+wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WThinArgs a) {
     // row groups of XT3: 3 * CG shifted copies + one group whose first row is all ones (the bias-gradient row)
     constexpr int CG = CIN / 8, XG = 3 * CG;
     constexpr uint32_t xt_plane = (XG + 1) * kGrp, xt_buf = P * xt_plane;
@@ -110,7 +113,52 @@ wgrad_thin_kernel(const WThinArgs a) {
         return grp;
     };
 
-    if (warp == 4) {
+    if (warp == 4 && a.tma) {
+        // ---- producer, TMA flavour: X row j of the unit, then (from j = 2) G row j - 2
+        if (lane == 0) {
+            tma_prefetch_desc(&tmX);
+            tma_prefetch_desc(&tmG);
+        }
+        uint32_t gx = 0, gg = 0;
+        for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
+            int xn, gn, x0, ya;
+            unit_coords(u, xn, gn, x0, ya);
+            for (int j = 0; j < a.RC + 2; ++j) {
+                {
+                    const int s = gx & (kRaw - 1);
+                    mbar_wait_spin(xempty(s), ((gx >> kRawLog) & 1) ^ 1);
+                    if (elect_one()) {
+                        const uint32_t fb = xfull(s);
+                        mbar_expect_tx(fb, P * CG * 130 * 16);
+                        const uint32_t dst = rawx0 + s * rawx_slot;
+#pragma unroll
+                        for (int p = 0; p < P; ++p) {
+#pragma unroll
+                            for (int cg = 0; cg < CG; ++cg)
+                                tma_load_5d(dst + p * rawx_plane + cg * kCgBytes, &tmX, fb, a.c0 + cg * 8, x0 - 1, ya - 1 + j, xn, p);
+                        }
+                    }
+                    __syncwarp();
+                    ++gx;
+                }
+                if (j >= 2) {
+                    const int s = gg & (kRaw - 1);
+                    mbar_wait_spin(gempty(s), ((gg >> kRawLog) & 1) ^ 1);
+                    if (elect_one()) {
+                        const uint32_t fb = gfull(s);
+                        mbar_expect_tx(fb, P * a.CGO * 128 * 16);
+                        const uint32_t dst = rawg0 + s * rawg_slot;
+#pragma unroll
+                        for (int p = 0; p < P; ++p)
+                            for (int cg = 0; cg < a.CGO; ++cg)
+                                tma_load_5d(dst + p * rawg_plane + cg * kGrp, &tmG, fb, cg * 8, x0, ya + j - 2, gn, p);
+                    }
+                    __syncwarp();
+                    ++gg;
+                }
+            }
+        }
+    } else if (warp == 4) {
         // ---- producer: X row j of the unit, then (from j = 2) G row j - 2, each one cp.async group of 16-byte chunks
         // (chunk q of a row = byte 16 * q of the global row segment; home [channel group][pixel]).  `look` rows stay
         // in flight; bit (k & 31) of `kinds` remembers whether the k-th requested row was a G row, so that rows are
@@ -218,19 +266,28 @@ wgrad_thin_kernel(const WThinArgs a) {
                 for (int ky = 0; ky < 3; ++ky) xb[ky] = (xt0 + ((gx + ky) & 3) * xt_buf) >> 4;
                 if (elect_one()) {
                     const uint32_t later = rows_done > 0 ? 1u : 0u;
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
+                    auto issue = [&](int ky, int ks) {
                         const uint32_t d = tmem + ky * a.Npad;
+#pragma unroll
+                        for (int pi = 0; pi < P; ++pi) {
+#pragma unroll
+                            for (int pj = 0; pj < P - pi; ++pj)
+                                mma_bf16(d, dhi | (uint64_t)(xb[ky] + (pi * xt_plane + ks * 256) / 16),
+                                         bd0 + (uint32_t)(pj * gtp16 + ks * 16), idesc,
+                                         (ks == 0 && pi + pj == 0) ? later : 1u);
+                        }
+                    };
+                    if (a.ks_major) {
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks) {
 #pragma unroll
-                            for (int pi = 0; pi < P; ++pi) {
+                            for (int ky = 0; ky < 3; ++ky) issue(ky, ks);
+                        }
+                    } else {
 #pragma unroll
-                                for (int pj = 0; pj < P - pi; ++pj)
-                                    mma_bf16(d, dhi | (uint64_t)(xb[ky] + (pi * xt_plane + ks * 256) / 16),
-                                             bd0 + (uint32_t)(pj * gtp16 + ks * 16), idesc,
-                                             (ks == 0 && pi + pj == 0) ? later : 1u);
-                            }
+                        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                            for (int ks = 0; ks < 8; ++ks) issue(ky, ks);
                         }
                     }
                     mma_commit(gtempty(gg & 1));
@@ -376,7 +433,7 @@ struct WThinPlan {
 };
 
 template <int CIN, int P>
-static int launch_wthin(WThinArgs& a, cudaStream_t stream) {
+static int launch_wthin(const CUtensorMap& tmX, const CUtensorMap& tmG, WThinArgs& a, cudaStream_t stream) {
     auto kern = wgrad_thin_kernel<CIN, P>;
     static bool attr = false;
     static WThinPlan plans[4];   // by Cout / 8 -> index 0..3 (8, 16, 32, 64)
@@ -399,15 +456,13 @@ static int launch_wthin(WThinArgs& a, cudaStream_t stream) {
         const int ncols = 3 * a.Npad <= 64 ? 64 : 3 * a.Npad <= 128 ? 128 : 256;
         if (cap > 512 / ncols) cap = 512 / ncols;
         WThinPlan pl = {0, 0, 0};
-        for (int pass = 0; pass < 2 && pl.occ == 0; ++pass) {
-            for (int occ = cap; occ >= 1 && pl.occ == 0; --occ) {
-                for (int R = pass == 0 ? 8 : 2; R >= (pass == 0 ? 4 : 2) && pl.occ == 0; R >>= 1) {
-                    const size_t smem = wthin_layout(CIN, a.Cout, P, R, nullptr);
-                    // residency computed here: shared memory (+1 KB reserved per CTA) against the 228 KB of an SM
-                    // (registers are bounded by __launch_bounds__(kThreads, 2), TMEM columns by `cap` above)
-                    if (smem > (size_t)kSmemLimit || (size_t)occ * (smem + 1024) > (size_t)228 * 1024) continue;
-                    pl.occ = occ, pl.raw = R, pl.smem = (int)smem;
-                }
+        for (int occ = cap; occ >= 1 && pl.occ == 0; --occ) {
+            for (int R = 8; R >= 2 && pl.occ == 0; R >>= 1) {
+                const size_t smem = wthin_layout(CIN, a.Cout, P, R, nullptr);
+                // residency computed here: shared memory (+1 KB reserved per CTA) against the 228 KB of an SM
+                // (registers are bounded by __launch_bounds__(kThreads, 2), TMEM columns by `cap` above)
+                if (smem > (size_t)kSmemLimit || (size_t)occ * (smem + 1024) > (size_t)228 * 1024) continue;
+                pl.occ = occ, pl.raw = R, pl.smem = (int)smem;
             }
         }
         if (getenv("PGK_THIN_DEBUG")) {
@@ -432,7 +487,7 @@ static int launch_wthin(WThinArgs& a, cudaStream_t stream) {
     a.look = pl.raw == 8 ? 8 : pl.raw == 4 ? 4 : 1;
     int grid = pl.occ * pgk_num_sms();
     if (grid > a.total_units) grid = a.total_units;
-    kern<<<grid, kThreads, pl.smem, stream>>>(a);
+    kern<<<grid, kThreads, pl.smem, stream>>>(tmX, tmG, a);
     return PGK_OK;
 }
 
@@ -462,10 +517,47 @@ extern "C" int pgk_wgrad_thin(const void* x, long long x_ps, const void* g, long
     a.x_ps = x_ps, a.g_ps = g_ps;
     PGK_REQUIRE((((uintptr_t)x | (uintptr_t)g) & 15) == 0 && (Pr == 1 || ((x_ps | g_ps) * 2) % 16 == 0),
                 "pgk_wgrad_thin: x and g must be 16-byte aligned");
+    static int use_tma = -1, ks_major = -1;
+    if (use_tma < 0) {
+        const char* e = getenv("PGK_THIN_TMA");
+        use_tma = e ? atoi(e) != 0 : 1;
+        e = getenv("PGK_WTHIN_KS_MAJOR");
+        ks_major = e ? atoi(e) != 0 : 0;
+    }
+    a.tma = use_tma, a.ks_major = ks_major;
+    CUtensorMap tmX, tmG;
+    memset(&tmX, 0, sizeof(tmX));
+    memset(&tmG, 0, sizeof(tmG));
+    if (a.tma) {
+        int xmax = 0, gmax = 0;
+        for (int i = 0; i < ngroups; ++i) {
+            if (xoff[i] > xmax) xmax = xoff[i];
+            if (goff[i] > gmax) gmax = goff[i];
+        }
+        {
+            const unsigned long long Ct = (unsigned long long)cin_total;
+            unsigned long long dims[5] = {Ct, (unsigned long long)W, (unsigned long long)H,
+                                          (unsigned long long)(xmax + group_n), (unsigned long long)P};
+            unsigned long long str[4] = {2ull * Ct, 2ull * Ct * W, 2ull * Ct * W * H,
+                                         P > 1 ? 2ull * x_ps : 2ull * Ct * W * H * (xmax + group_n)};
+            unsigned box[5] = {8u, 130u, 1u, 1u, 1u};
+            int rc = pgk_make_tmap(&tmX, x, 5, dims, str, box, 0, "pgk_wgrad_thin(x)");
+            if (rc) return rc;
+        }
+        {
+            unsigned long long dims[5] = {(unsigned long long)Cout, (unsigned long long)W, (unsigned long long)H,
+                                          (unsigned long long)(gmax + group_n), (unsigned long long)P};
+            unsigned long long str[4] = {2ull * Cout, 2ull * Cout * W, 2ull * Cout * W * H,
+                                         P > 1 ? 2ull * g_ps : 2ull * Cout * W * H * (gmax + group_n)};
+            unsigned box[5] = {8u, 128u, 1u, 1u, 1u};
+            int rc = pgk_make_tmap(&tmG, g, 5, dims, str, box, 0, "pgk_wgrad_thin(g)");
+            if (rc) return rc;
+        }
+    }
     cudaStream_t st = (cudaStream_t)stream;
     int rc = PGK_ERR_ARG;
 #define PGK_WTHIN_CASE(C_, P_) \
-    if (Cin == C_ && Pr == P_) rc = launch_wthin<C_, P_>(a, st);
+    if (Cin == C_ && Pr == P_) rc = launch_wthin<C_, P_>(tmX, tmG, a, st);
     PGK_WTHIN_CASE(8, 1) PGK_WTHIN_CASE(16, 1) PGK_WTHIN_CASE(32, 1)
     PGK_WTHIN_CASE(8, 2) PGK_WTHIN_CASE(16, 2) PGK_WTHIN_CASE(32, 2)
     PGK_WTHIN_CASE(8, 3) PGK_WTHIN_CASE(16, 3) PGK_WTHIN_CASE(32, 3)
