@@ -449,7 +449,10 @@ extern "C" int pgk_bias_grad(const void* g, long long g_ps, int P, int HW, int C
     a.db = db;
     a.R = (long long)ngroups * group_n * HW;
     PGK_REQUIRE(a.R < (1ll << 31), "pgk_bias_grad: more than 2^31 pixels");
-    long long ctas = (a.R + 511) / 512;
+    // every thread walks r_per_cta / lanes pixels one dependent 16-byte load at a time, so small tensors need many
+    // short CTAs (a 512-channel 4x4 .. 16x16 level at batch 4 took 75 us on two CTAs): ~8 loads per thread
+    const int nch = Cout >> 3, lanes = 256 / nch > 0 ? 256 / nch : 1;
+    long long ctas = (a.R + 8ll * lanes - 1) / (8ll * lanes);
     long long cap = 4ll * pgk_num_sms();
     if (ctas > cap) ctas = cap;
     if (ctas < 1) ctas = 1;

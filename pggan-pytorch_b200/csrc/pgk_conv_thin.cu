@@ -42,6 +42,7 @@ struct ThinArgs {
     int ring, ring_log2, look;  // row buffers; rows the producer keeps in flight before it hands the oldest over
     int pair;                   // MMA warp interleaves the K steps of two output rows (two accumulators)
     int tma;                    // producer: 1 = TMA boxes (16-byte inner extent), 0 = cp.async chunks
+    int spin;                   // producer / MMA warps poll their barriers (1) or suspend in try_wait (0)
     int total_units;
     int Pout, split_acc;
     const bf16* wpack;          // [P][STEPS][2][Npad][8]
@@ -116,6 +117,12 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
     fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tptr - raw));
 
+    // The two single-warp roles share their SM sub-partitions with epilogue warps: busy polling (test_wait) costs
+    // those warps issue slots (12 % of all issued instructions in the ncu capture), try_wait suspends instead.
+    auto wait_bar = [&](uint32_t bar, uint32_t parity) {
+        if (a.spin) mbar_wait_spin(bar, parity);
+        else mbar_wait(bar, parity);
+    };
     auto unit_coords = [&](int u, int& n, int& x0, int& ya) {
         const int cy = u % a.chunks_y;
         int r = u / a.chunks_y;
@@ -136,7 +143,7 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
             unit_coords(u, n, x0, ya);
             for (int j = 0; j < a.RC + 2; ++j, ++g) {
                 const int s = g & (kRing - 1);
-                mbar_wait_spin(rempty(s), ((g >> kRingLog) & 1) ^ 1);
+                wait_bar(rempty(s), ((g >> kRingLog) & 1) ^ 1);
                 if (elect_one()) {
                     const uint32_t fb = rfull(s);
                     mbar_expect_tx(fb, tx_bytes);
@@ -177,7 +184,7 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
                     // need exactly those rows to finish the tile that frees this slot
                     cp_async_wait<0>();
                     hand_over(g);
-                    mbar_wait_spin(rempty(s), par);
+                    wait_bar(rempty(s), par);
                 }
                 const int y = ya - 1 + j;
                 const bool row_ok = y >= 0 && y < a.H;
@@ -243,17 +250,17 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
             }
         };
         for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
-            mbar_wait_spin(rfull(g & (kRing - 1)), (g >> kRingLog) & 1);
-            mbar_wait_spin(rfull((g + 1) & (kRing - 1)), ((g + 1) >> kRingLog) & 1);
+            wait_bar(rfull(g & (kRing - 1)), (g >> kRingLog) & 1);
+            wait_bar(rfull((g + 1) & (kRing - 1)), ((g + 1) >> kRingLog) & 1);
             if (a.pair) {
                 // two output rows at a time: their MMA chains accumulate into different TMEM buffers, so the tensor
                 // core can overlap the (latency-bound, N <= 64) steps of one row with those of the other
                 for (int i = 0; i < a.RC; i += 2, g += 2, ti += 2) {
-                    mbar_wait_spin(rfull((g + 2) & (kRing - 1)), ((g + 2) >> kRingLog) & 1);
-                    mbar_wait_spin(rfull((g + 3) & (kRing - 1)), ((g + 3) >> kRingLog) & 1);
+                    wait_bar(rfull((g + 2) & (kRing - 1)), ((g + 2) >> kRingLog) & 1);
+                    wait_bar(rfull((g + 3) & (kRing - 1)), ((g + 3) >> kRingLog) & 1);
                     const int b0 = ti & (kAcc - 1), b1 = (ti + 1) & (kAcc - 1);
-                    mbar_wait_spin(aempty(b0), ((ti / kAcc) & 1) ^ 1);
-                    mbar_wait_spin(aempty(b1), (((ti + 1) / kAcc) & 1) ^ 1);
+                    wait_bar(aempty(b0), ((ti / kAcc) & 1) ^ 1);
+                    wait_bar(aempty(b1), (((ti + 1) / kAcc) & 1) ^ 1);
                     fence_after();
                     uint32_t rb[4];
 #pragma unroll
@@ -277,9 +284,9 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
                 }
             } else {
                 for (int i = 0; i < a.RC; ++i, ++g, ++ti) {
-                    mbar_wait_spin(rfull((g + 2) & (kRing - 1)), ((g + 2) >> kRingLog) & 1);
+                    wait_bar(rfull((g + 2) & (kRing - 1)), ((g + 2) >> kRingLog) & 1);
                     const int b = ti & (kAcc - 1);
-                    mbar_wait_spin(aempty(b), ((ti / kAcc) & 1) ^ 1);
+                    wait_bar(aempty(b), ((ti / kAcc) & 1) ^ 1);
                     fence_after();
                     uint32_t rb[3];
 #pragma unroll
@@ -310,11 +317,12 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
         const uint32_t trow_off = (uint32_t)(q * 32) << 16;
         const int my_units = (int)blockIdx.x < a.total_units ? (a.total_units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
         const uint32_t ntiles = (uint32_t)my_units * (uint32_t)a.RC;
-        auto tile_pix = [&](uint32_t t) {
-            const uint32_t k = t / (uint32_t)a.RC, i = t - k * (uint32_t)a.RC;
+        // pixel index of this thread in tile (unit k of this CTA, row i); the walk below advances (k, i) two rows at
+        // a time (RC is even or the warpgroups alternate units), so the divisions happen once per unit, not per tile
+        auto unit_pix0 = [&](uint32_t k) {
             int n, x0, ya;
             unit_coords((int)(blockIdx.x + k * gridDim.x), n, x0, ya);
-            return ((long long)n * a.H + (ya + (int)i)) * a.W + x0 + r;
+            return ((long long)n * a.H + ya) * a.W + x0 + r;
         };
         uint4 mk[NV];
 #pragma unroll
@@ -325,19 +333,26 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
             for (int k = 0; k < NV; ++k)
                 if (k * 8 < a.Cout) mk[k] = ldg_nc_v4(mp + k);
         };
+        const float s_pos = a.out_scale, s_neg = a.act ? PGK_LRELU * a.out_scale : a.out_scale;
         uint32_t ti = (uint32_t)wg;
-        long long pix = 0;
-        if (ti < ntiles) {
-            pix = tile_pix(ti);
-            if (a.has_mask) load_mask(pix);
-        }
+        // (uk, ui): unit and row of the NEXT tile this warpgroup will prefetch for; base = pixel of row 0 of unit uk
+        uint32_t uk = ti / (uint32_t)a.RC, ui = ti - uk * (uint32_t)a.RC;
+        long long base = ti < ntiles ? unit_pix0(uk) : 0;
+        long long pix = base + (long long)ui * a.W;
+        if (ti < ntiles && a.has_mask) load_mask(pix);
         for (; ti < ntiles; ti += 2) {
             uint4 mc[NV];
 #pragma unroll
             for (int k = 0; k < NV; ++k) mc[k] = mk[k];
             const long long o = pix * a.Cout;
             if (ti + 2 < ntiles) {
-                pix = tile_pix(ti + 2);
+                ui += 2;
+                if (ui >= (uint32_t)a.RC) {
+                    ui -= (uint32_t)a.RC;
+                    ++uk;
+                    base = unit_pix0(uk);
+                }
+                pix = base + (long long)ui * a.W;
                 if (a.has_mask) load_mask(pix);
             }
             const int b = ti & (kAcc - 1);
@@ -364,18 +379,15 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
                             f[0] += b0.x, f[1] += b0.y, f[2] += b0.z, f[3] += b0.w;
                             f[4] += b1.x, f[5] += b1.y, f[6] += b1.z, f[7] += b1.w;
                         }
-                        if (a.act) {
+                        // LeakyReLU and the output scale as one select + multiply
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) f[j] = lrelu(f[j]);
-                        }
+                        for (int j = 0; j < 8; ++j) f[j] *= f[j] > 0.f ? s_pos : s_neg;
                         if (a.has_mask) {
                             float m[8];
                             unpack8(mc[c / 8 + h], m);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) f[j] *= lrelu_grad(m[j]);
                         }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) f[j] *= a.out_scale;
                         split_store8(a.out, o + c + 8 * h, f);
                     }
                 }
@@ -575,6 +587,12 @@ extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N
         use_tma = e ? atoi(e) != 0 : 1;
     }
     a.tma = use_tma;
+    static int spin = -1;
+    if (spin < 0) {
+        const char* e = getenv("PGK_THIN_SPIN");
+        spin = e ? atoi(e) != 0 : 0;
+    }
+    a.spin = spin;
     CUtensorMap tmA;
     memset(&tmA, 0, sizeof(tmA));
     if (a.tma) {

@@ -38,6 +38,7 @@ struct WThinArgs {
     long long x_ps, g_ps;
     int raw, raw_log2, look;  // raw ring depth and the rows (X or G) the producer keeps in flight
     int tma;                  // producer: 1 = TMA boxes, 0 = cp.async chunks
+    int spin;                 // producer / MMA warps poll their barriers (1) or suspend in try_wait (0)
     int ks_major;             // MMA issue order: 1 = the three ky accumulators interleaved per K step
     int H, W, Cout, Npad, CGO;
     int RC, chunks_y, strips;
@@ -102,6 +103,12 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tptr - raw));
 
+    // busy polling by the two single-warp roles takes issue slots from the transposer warps of the same SM
+    // sub-partitions; try_wait suspends instead
+    auto wait_bar = [&](uint32_t bar, uint32_t parity) {
+        if (a.spin) mbar_wait_spin(bar, parity);
+        else mbar_wait(bar, parity);
+    };
     auto unit_coords = [&](int u, int& xn, int& gn, int& x0, int& ya) {
         const int cy = u % a.chunks_y;
         int r = u / a.chunks_y;
@@ -126,7 +133,7 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             for (int j = 0; j < a.RC + 2; ++j) {
                 {
                     const int s = gx & (kRaw - 1);
-                    mbar_wait_spin(xempty(s), ((gx >> kRawLog) & 1) ^ 1);
+                    wait_bar(xempty(s), ((gx >> kRawLog) & 1) ^ 1);
                     if (elect_one()) {
                         const uint32_t fb = xfull(s);
                         mbar_expect_tx(fb, P * CG * 130 * 16);
@@ -143,7 +150,7 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 }
                 if (j >= 2) {
                     const int s = gg & (kRaw - 1);
-                    mbar_wait_spin(gempty(s), ((gg >> kRawLog) & 1) ^ 1);
+                    wait_bar(gempty(s), ((gg >> kRawLog) & 1) ^ 1);
                     if (elect_one()) {
                         const uint32_t fb = gfull(s);
                         mbar_expect_tx(fb, P * a.CGO * 128 * 16);
@@ -183,7 +190,7 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             if (!__all_sync(0xffffffffu, mbar_test(bar, par))) {
                 cp_async_wait<0>();   // never sleep on a busy slot while holding rows back (the consumers may need them)
                 hand_over(req);
-                mbar_wait_spin(bar, par);
+                wait_bar(bar, par);
             }
         };
         auto after_request = [&](bool is_g) {
@@ -254,11 +261,11 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const uint32_t gtp16 = gt_plane >> 4;
         uint32_t gx = 0, gg = 0, rows_done = 0;
         for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
-            mbar_wait_spin(xtfull(gx & 3), (gx >> 2) & 1);
-            mbar_wait_spin(xtfull((gx + 1) & 3), ((gx + 1) >> 2) & 1);
+            wait_bar(xtfull(gx & 3), (gx >> 2) & 1);
+            wait_bar(xtfull((gx + 1) & 3), ((gx + 1) >> 2) & 1);
             for (int i = 0; i < a.RC; ++i, ++gx, ++gg, ++rows_done) {
-                mbar_wait_spin(xtfull((gx + 2) & 3), ((gx + 2) >> 2) & 1);
-                mbar_wait_spin(gtfull(gg & 1), (gg >> 1) & 1);
+                wait_bar(xtfull((gx + 2) & 3), ((gx + 2) >> 2) & 1);
+                wait_bar(gtfull(gg & 1), (gg >> 1) & 1);
                 fence_after();
                 const uint64_t bd0 = dhi | ((gt0 + (gg & 1) * gt_slot) >> 4);
                 uint32_t xb[3];
@@ -525,6 +532,14 @@ extern "C" int pgk_wgrad_thin(const void* x, long long x_ps, const void* g, long
         ks_major = e ? atoi(e) != 0 : 0;
     }
     a.tma = use_tma, a.ks_major = ks_major;
+    {
+        static int spin = -1;
+        if (spin < 0) {
+            const char* e = getenv("PGK_THIN_SPIN");
+            spin = e ? atoi(e) != 0 : 0;
+        }
+        a.spin = spin;
+    }
     CUtensorMap tmX, tmG;
     memset(&tmX, 0, sizeof(tmX));
     memset(&tmG, 0, sizeof(tmG));
