@@ -325,7 +325,19 @@ def main():
     else:
         roof = {'bound': 'tensor', 'kernel': FAMILIES[dom], 'achieved': tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
                 'frac': tf / peak_tf, 'peak_source': peak_src}
-    roof.update(traffic=None, launches_timed=n_k, kernel_ms_per_step=ms_k / ksteps,
+    # DRAM bytes per launch of the dominant kernel from a committed ncu capture of this config (tools/ncu_traffic.py)
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            t = json.load(f).get(args.config, {}).get(FAMILIES[dom].split(' ')[0])
+        if t and not args.batch:
+            traffic, traffic_src = t['bytes_per_launch'], t['source']
+    except Exception:
+        pass
+    if traffic is not None:
+        roof['traffic_source'] = traffic_src
+        roof['algorithmic_bytes_per_launch'] = by / max(1, n_k)
+    roof.update(traffic=traffic, launches_timed=n_k, kernel_ms_per_step=ms_k / ksteps,
                 share_of_step=ms_k / ksteps / (step_s * 1e3),
                 families={FAMILIES[k].split(' ')[0]: {'ms_per_step': v[2] / ksteps, 'launches': v[3],
                                                        'tflops': v[0] / (v[2] * 1e-3) / 1e12 if v[2] > 0 else 0.0,

@@ -58,6 +58,13 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // row groups of XT3: 3 * CG shifted copies + one group whose first row is all ones (the bias-gradient row)
     constexpr int CG = CIN / 8, XG = 3 * CG;
     constexpr uint32_t xt_plane = (XG + 1) * kGrp, xt_buf = P * xt_plane;
+    // CIN == 8: one transposed row is 4 row groups (3 kx copies + the ones group) = 32 accumulator rows, so the FOUR
+    // ring slots of one plane, laid out back to back, are exactly the 16 row groups (M = 128) one tcgen05.mma reads:
+    // a single MMA chain per output row covers ky = 0, 1, 2 (plus one slot of don't-care rows) instead of three
+    // chains -- a third of the MMAs, and this kernel is bound by the MMA rate (every MMA streams its 128-row A tile
+    // from shared memory, whatever N is).  Slot j then holds ky = (j - row index) & 3, which changes from row to row,
+    // so there are four accumulators, selected by (row index & 3): inside accumulator c slot j is always ky = (j-c)&3.
+    constexpr bool STACK = CIN == 8;
     constexpr uint32_t rawx_plane = CG * kCgBytes, rawx_slot = P * rawx_plane;
     extern __shared__ uint8_t smem_raw[];
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
@@ -66,6 +73,10 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const uint32_t gt_plane = (uint32_t)a.CGO * kGrp, gt_slot = P * gt_plane;
     const uint32_t rawg_plane = gt_plane, rawg_slot = gt_slot;
     const uint32_t xt0 = sbase, gt0 = sbase + a.off_gt, rawx0 = sbase + a.off_rawx, rawg0 = sbase + a.off_rawg;
+    // transposed X row buffers: [slot][plane] (three chains) or [plane][slot] (stacked)
+    auto xt_at = [&](uint32_t buf, uint32_t p) {
+        return STACK ? xt0 + p * (4u * xt_plane) + buf * xt_plane : xt0 + buf * xt_buf + p * xt_plane;
+    };
     const uint32_t bars = sbase + a.off_bars;
     const int kRaw = a.raw, kRawLog = a.raw_log2;
     auto xfull = [&](int s) { return bars + 8u * s; };                       // [kMaxRaw]
@@ -93,10 +104,11 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     for (uint32_t o = threadIdx.x * 16u; o < 4u * P * kGrp; o += kThreads * 16u) {
         const uint32_t buf = o / (P * kGrp), rem = o - buf * (P * kGrp);
         const uint32_t p = rem / kGrp, w = rem - p * kGrp;
-        st_shared_v4(xt0 + buf * xt_buf + p * xt_plane + XG * kGrp + w, make_uint4(0, 0, 0, 0));
+        st_shared_v4(xt_at(buf, p) + XG * kGrp + w, make_uint4(0, 0, 0, 0));
     }
     fence_proxy_async();
-    const unsigned ncols = 3 * a.Npad <= 64 ? 64u : 3 * a.Npad <= 128 ? 128u : 256u;
+    const unsigned nacc = STACK ? 4u : 3u;
+    const unsigned ncols = nacc * a.Npad <= 64 ? 64u : nacc * a.Npad <= 128 ? 128u : 256u;
     if (warp == 5) tmem_alloc(tptr, ncols);
     fence_before();
     __syncthreads();
@@ -259,7 +271,7 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const uint32_t idesc = idesc_bf16(a.Npad, 0, 0);
         const uint64_t dhi = smem_desc(0, 128, kGrp, 0);   // K-major, no swizzle: LBO = next 8 pixels, SBO = next 8 rows
         const uint32_t gtp16 = gt_plane >> 4;
-        uint32_t gx = 0, gg = 0, rows_done = 0;
+        uint32_t gx = 0, gg = 0, rows_done = 0, used = 0;
         for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
             wait_bar(xtfull(gx & 3), (gx >> 2) & 1);
             wait_bar(xtfull((gx + 1) & 3), ((gx + 1) >> 2) & 1);
@@ -271,6 +283,9 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 uint32_t xb[3];
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky) xb[ky] = (xt0 + ((gx + ky) & 3) * xt_buf) >> 4;
+                const uint32_t c4 = gx & 3;
+                const uint32_t later4 = (used >> c4) & 1u;   // stacked flavour: has accumulator c4 been started?
+                used |= 1u << c4;
                 if (elect_one()) {
                     const uint32_t later = rows_done > 0 ? 1u : 0u;
                     auto issue = [&](int ky, int ks) {
@@ -284,7 +299,20 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                                          (ks == 0 && pi + pj == 0) ? later : 1u);
                         }
                     };
-                    if (a.ks_major) {
+                    if (STACK) {
+                        const uint32_t d = tmem + c4 * a.Npad;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+                            for (int pi = 0; pi < P; ++pi) {
+#pragma unroll
+                                for (int pj = 0; pj < P - pi; ++pj)
+                                    mma_bf16(d, dhi | (uint64_t)((xt0 + pi * (4u * xt_plane) + ks * 256) >> 4),
+                                             bd0 + (uint32_t)(pj * gtp16 + ks * 16), idesc,
+                                             (ks == 0 && pi + pj == 0) ? later4 : 1u);
+                            }
+                        }
+                    } else if (a.ks_major) {
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks) {
 #pragma unroll
@@ -323,7 +351,7 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     const int s = gx & (kRaw - 1), b = gx & 3;
                     mbar_wait(xfull(s), (gx >> kRawLog) & 1);
                     mbar_wait(xtempty(b), ((gx >> 2) & 1) ^ 1);
-                    const uint32_t src0 = rawx0 + s * rawx_slot, dst0 = xt0 + b * xt_buf;
+                    const uint32_t src0 = rawx0 + s * rawx_slot;
                     // ops: (plane, kx, channel group, 32-pixel block)
                     for (int o = warp; o < P * 3 * CG * 4; o += 4) {
                         const int blk = o & 3;
@@ -333,10 +361,10 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                         const int kx = r % 3, p = r / 3;
                         uint32_t v[4];
                         ldmatrix_x4_trans(src0 + p * rawx_plane + cg * kCgBytes + (blk * 32 + lj * 8 + li + kx) * 16, v);
-                        stmatrix_x4(dst0 + p * xt_plane + (kx * CG + cg) * kGrp + (blk * 4 + lj) * 128 + li * 16, v);
+                        stmatrix_x4(xt_at(b, p) + (kx * CG + cg) * kGrp + (blk * 4 + lj) * 128 + li * 16, v);
                     }
                     if (warp == 0 && lane < 16)   // the ones row (plane 0, row 0 of group XG), 16 pixel chunks
-                        st_shared_v4(dst0 + XG * kGrp + lane * 128, make_uint4(one16, one16, one16, one16));
+                        st_shared_v4(xt_at(b, 0) + XG * kGrp + lane * 128, make_uint4(one16, one16, one16, one16));
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
@@ -371,24 +399,48 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         // ---- flush: accumulator row m = kx*Cin + ci of D[ky] -> dW[(ky*3 + kx)*Cin + ci][:]
         mbar_wait(done, 0);
         fence_after();
-        const int m = warp * 32 + lane;
-        const bool valid = m < 3 * CIN;
-        const int kx = m / CIN, ci = m - kx * CIN;
         const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-        for (int ky = 0; ky < 3; ++ky) {
-            float* drow = a.dwp + (long long)((ky * 3 + kx) * a.cin_total + a.c0 + ci) * a.Cout;
-            const bool bias_row = a.db && ky == 1 && m == 3 * CIN;   // the ones row against G of the same row
-            for (int c = 0; c < a.Npad; c += 16) {
-                float v[16];
-                tmem_ld16(trow + ky * a.Npad + c, v);
-                if (valid) {
+        if (STACK) {
+            // accumulator c, rows 32*j .. 32*j+31 (this warp: j = warp) = slot j = ky (j - c) & 3; row kx*8 + ci of
+            // the block, row 24 = the ones row.  Every CTA processes at least one unit of >= 8 rows, so all four
+            // accumulators have been written.
+            const int kx = lane >> 3, ci = lane & 7;
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const int ky = (warp - c4) & 3;
+                float* drow = a.dwp + (long long)((ky * 3 + kx) * a.cin_total + a.c0 + ci) * a.Cout;
+                for (int c = 0; c < a.Npad; c += 16) {
+                    float v[16];
+                    tmem_ld16(trow + c4 * a.Npad + c, v);
+                    if (ky < 3 && lane < 24) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c + j < a.Cout) atomicAdd(drow + c + j, v[j]);
-                } else if (bias_row) {
+                        for (int j = 0; j < 16; ++j)
+                            if (c + j < a.Cout) atomicAdd(drow + c + j, v[j]);
+                    } else if (ky == 1 && lane == 24 && a.db) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c + j < a.Cout) atomicAdd(a.db + c + j, v[j]);
+                        for (int j = 0; j < 16; ++j)
+                            if (c + j < a.Cout) atomicAdd(a.db + c + j, v[j]);
+                    }
+                }
+            }
+        } else {
+            const int m = warp * 32 + lane;
+            const bool valid = m < 3 * CIN;
+            const int kx = m / CIN, ci = m - kx * CIN;
+            for (int ky = 0; ky < 3; ++ky) {
+                float* drow = a.dwp + (long long)((ky * 3 + kx) * a.cin_total + a.c0 + ci) * a.Cout;
+                const bool bias_row = a.db && ky == 1 && m == 3 * CIN;   // the ones row against G of the same row
+                for (int c = 0; c < a.Npad; c += 16) {
+                    float v[16];
+                    tmem_ld16(trow + ky * a.Npad + c, v);
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c + j < a.Cout) atomicAdd(drow + c + j, v[j]);
+                    } else if (bias_row) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c + j < a.Cout) atomicAdd(a.db + c + j, v[j]);
+                    }
                 }
             }
         }
@@ -460,7 +512,8 @@ static int launch_wthin(const CUtensorMap& tmX, const CUtensorMap& tmG, WThinArg
         const char* e = getenv("PGK_THIN_OCC");
         int cap = e ? atoi(e) : 2;
         cap = cap < 1 ? 1 : cap > 2 ? 2 : cap;
-        const int ncols = 3 * a.Npad <= 64 ? 64 : 3 * a.Npad <= 128 ? 128 : 256;
+        const int nacc = CIN == 8 ? 4 : 3;
+        const int ncols = nacc * a.Npad <= 64 ? 64 : nacc * a.Npad <= 128 ? 128 : 256;
         if (cap > 512 / ncols) cap = 512 / ncols;
         WThinPlan pl = {0, 0, 0};
         for (int occ = cap; occ >= 1 && pl.occ == 0; --occ) {
