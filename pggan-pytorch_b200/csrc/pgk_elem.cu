@@ -298,6 +298,65 @@ __global__ void __launch_bounds__(256) rgb_reduce_kernel(ReduceArgs a) {
     }
 }
 
+// The same reduction for thin feature maps (every source K <= 32: the 256^2 ... 1024^2 levels): one thread per output
+// pixel -- full-warp coalesced image stores, no idle lanes or shuffles, 32-bit index arithmetic, weights read from
+// shared memory as float4, the bias terms folded into one constant per image channel.
+__global__ void __launch_bounds__(256) rgb_reduce_px_kernel(ReduceArgs a) {
+    extern __shared__ __align__(16) float wsm[];  // source 0: [C][K0], source 1: [C][K1], then bsum[MAXC]
+    const int off1 = a.C * a.s[0].K;
+    const int offb = off1 + (a.nsrc > 1 ? a.C * a.s[1].K : 0);
+    for (int s = 0; s < a.nsrc; ++s) {
+        const int K = a.s[s].K;
+        float* dst = wsm + (s ? off1 : 0);
+        for (int i = threadIdx.x; i < a.C * K; i += blockDim.x) {
+            const int c = i / K, k = i - c * K;
+            dst[i] = a.s[s].a * a.s[s].wscale * a.s[s].w[(long long)c * a.s[s].sc + (long long)k * a.s[s].sk];
+        }
+    }
+    if (threadIdx.x < MAXC) {
+        float b = 0.f;
+        if ((int)threadIdx.x < a.C)
+            for (int s = 0; s < a.nsrc; ++s)
+                if (a.s[s].bias) b = fmaf(a.s[s].a, a.s[s].bias[threadIdx.x], b);
+        wsm[offb + threadIdx.x] = b;
+    }
+    __syncthreads();
+    const unsigned npix = (unsigned)a.N * a.H * a.W, HW = (unsigned)a.H * a.W, W = (unsigned)a.W;
+    for (unsigned pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
+        const unsigned n = pix / HW, r = pix - n * HW;
+        const unsigned y = r / W, x = r - y * W;
+        float acc[MAXC];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) acc[c] = wsm[offb + c];
+        for (int s = 0; s < a.nsrc; ++s) {
+            const ReduceSrc& S = a.s[s];
+            const float* wm = wsm + (s ? off1 : 0);
+            const unsigned Hs = a.H >> S.ups, Ws = a.W >> S.ups;
+            const long long base = ((long long)(n * Hs + (y >> S.ups)) * Ws + (x >> S.ups)) * S.K;
+            for (int ch = 0; ch < (S.K >> 3); ++ch) {
+                float f[8];
+                ld8(S.t, base + ch * 8, f);
+#pragma unroll
+                for (int c = 0; c < MAXC; ++c)
+                    if (c < a.C) {
+                        const float4 w0 = *reinterpret_cast<const float4*>(wm + c * S.K + ch * 8);
+                        const float4 w1 = *reinterpret_cast<const float4*>(wm + c * S.K + ch * 8 + 4);
+                        float t = acc[c];
+                        t = fmaf(f[0], w0.x, t), t = fmaf(f[1], w0.y, t), t = fmaf(f[2], w0.z, t), t = fmaf(f[3], w0.w, t);
+                        t = fmaf(f[4], w1.x, t), t = fmaf(f[5], w1.y, t), t = fmaf(f[6], w1.z, t), t = fmaf(f[7], w1.w, t);
+                        acc[c] = t;
+                    }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c)
+            if (c < a.C) {
+                const long long o = ((long long)n * a.C + c) * HW + r;
+                a.img[o] = a.accumulate ? a.img[o] + acc[c] : acc[c];
+            }
+    }
+}
+
 // weight / bias gradients of the 1x1 families:
 //   dw[a*sa + k*sk] += scale * sum IMG(n,a,pix) * t[n,pix,k]; colsum[k] += scale * sum t; imgsum[a] += scale * sum IMG
 struct RgbWgradArgs {
@@ -996,6 +1055,12 @@ static int launch_reduce(ReduceArgs& a, pgk_stream_t stream, const char* name) {
         if ((a.s[s].K >> 3) > maxch) maxch = a.s[s].K >> 3;
     }
     PGK_REQUIRE(smem <= 48 * 1024, "%s: weights do not fit shared memory", name);
+    if (maxch <= 4 && (long long)a.N * a.H * a.W < (1ll << 31)) {   // thin feature maps: one thread per pixel
+        const long long npix = (long long)a.N * a.H * a.W;
+        rgb_reduce_px_kernel<<<grid_cap((npix + 255) / 256), 256, smem + sizeof(float) * MAXC, ST>>>(a);
+        PGK_LAUNCH_CHECK(name);
+        return PGK_OK;
+    }
     a.L = lanes_for(maxch);
     long long threads = (long long)a.N * a.H * a.W * a.L;
     rgb_reduce_kernel<<<grid_cap((threads + 255) / 256), 256, smem, ST>>>(a);
