@@ -298,9 +298,10 @@ __global__ void __launch_bounds__(256) rgb_reduce_kernel(ReduceArgs a) {
     }
 }
 
-// The same reduction for thin feature maps (every source K <= 32: the 256^2 ... 1024^2 levels): one thread per output
-// pixel -- full-warp coalesced image stores, no idle lanes or shuffles, 32-bit index arithmetic, weights read from
-// shared memory as float4, the bias terms folded into one constant per image channel.
+// The same reduction with one thread per output pixel -- full-warp coalesced image stores, no idle lanes or shuffles,
+// 32-bit index arithmetic, weights read from shared memory as float4 broadcasts, the bias terms folded into one
+// constant per image channel.  (A lane reads its pixel's K channels 16 bytes at a time; the other half of every
+// sector it touches is the next chunk of the same pixel and comes from L1.)
 __global__ void __launch_bounds__(256) rgb_reduce_px_kernel(ReduceArgs a) {
     extern __shared__ __align__(16) float wsm[];  // source 0: [C][K0], source 1: [C][K1], then bsum[MAXC]
     const int off1 = a.C * a.s[0].K;
@@ -333,6 +334,7 @@ __global__ void __launch_bounds__(256) rgb_reduce_px_kernel(ReduceArgs a) {
             const float* wm = wsm + (s ? off1 : 0);
             const unsigned Hs = a.H >> S.ups, Ws = a.W >> S.ups;
             const long long base = ((long long)(n * Hs + (y >> S.ups)) * Ws + (x >> S.ups)) * S.K;
+#pragma unroll 4
             for (int ch = 0; ch < (S.K >> 3); ++ch) {
                 float f[8];
                 ld8(S.t, base + ch * 8, f);
@@ -1055,7 +1057,10 @@ static int launch_reduce(ReduceArgs& a, pgk_stream_t stream, const char* name) {
         if ((a.s[s].K >> 3) > maxch) maxch = a.s[s].K >> 3;
     }
     PGK_REQUIRE(smem <= 48 * 1024, "%s: weights do not fit shared memory", name);
-    if (maxch <= 4 && (long long)a.N * a.H * a.W < (1ll << 31)) {   // thin feature maps: one thread per pixel
+    // One thread per pixel for every width: the lanes-per-pixel kernel below spends its time in shuffles, conflicting
+    // shared-memory weight reads and 8-byte image stores (measured 527 us on the 128-channel 64^2 level at batch 128,
+    // 8x its HBM time); per-pixel threads read the weights as broadcasts and store full 128-byte lines.
+    if ((long long)a.N * a.H * a.W < (1ll << 31)) {
         const long long npix = (long long)a.N * a.H * a.W;
         rgb_reduce_px_kernel<<<grid_cap((npix + 255) / 256), 256, smem + sizeof(float) * MAXC, ST>>>(a);
         PGK_LAUNCH_CHECK(name);
