@@ -100,13 +100,17 @@ int pgk_unprep_grad(const float* dwp, float c, int kind, int cin, int cin_stride
  * power-of-two H, W and ups == 0 run on the TMA + tcgen05 kernel and read wt; KS = 3 layers with Cin in {8,16,32},
  * Cout in {8,16,32,64}, W % 128 == 0 run on the row-streaming thin-layer tcgen05 kernel and read wt in
  * pgk_pack_thin's layout; all others run on the CUDA-core implicit GEMM and read wf.  Either pointer may be NULL if the shape never takes that path.
+ * pn_r (optional, fp32 per output pixel): the generator's pixel norm after the activation (network.py:37-40):
+ *          out = E(v) * r, r = rsqrt(mean_co(E(v)^2) + 1e-8), r stored for the backward pass.  Requires
+ *          mask_ref == NULL and out_scale == 1.  On the thin-layer kernel (Cout <= 32) it is part of the epilogue;
+ *          on the other kernels pgk_conv runs pgk_pixelnorm in place right after the convolution.
  * Pr (1 <= Pr <= P): how many planes of x and wt the tensor-core kernel READS (products of planes i + j < Pr).
  * Forward passes, whose values decide the LeakyReLU masks, use Pr = P; the gradient chains use Pr = min(P, 2)
  * (16 mantissa bits, three products instead of six) -- gradients are continuous in these operands. */
 int pgk_conv(const void* x, int P, int Pr, long long x_ps, int N, int H, int W, int Cin, int Cout, int KS, int ups,
              const float* wf, const void* wt, long long wt_ps, const float* bias, const float* posT,
              const float* pos_s, int act, const void* mask_ref, long long mask_ps, float out_scale, void* out,
-             long long out_ps, pgk_stream_t stream);
+             long long out_ps, float* pn_r, pgk_stream_t stream);
 
 /* ---- weight gradient (cuDNN convolution_backward, weight part) --------------------------
  * dwp[tap*Cin+ci][co] += sum over the listed sample groups of X[..., ci] (shifted by tap) * g[..., co].

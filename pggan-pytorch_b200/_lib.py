@@ -21,7 +21,7 @@ SIGNATURES = {
     'pgk_unprep_grad': [P, F, I, I, I, I, I, P, I],
     'pgk_pack_operand': [P, I, I, P, L, I],
     'pgk_pack_thin': [P, I, I, P, L, I],
-    'pgk_conv': [P, I, I, L, I, I, I, I, I, I, I, P, P, L, P, P, P, I, P, L, F, P, L],
+    'pgk_conv': [P, I, I, L, I, I, I, I, I, I, I, P, P, L, P, P, P, I, P, L, F, P, L, P],
     'pgk_wgrad': [P, L, P, L, I, I, I, I, I, I, I, I, I, I, P, P, P, P, ctypes.c_uint],
     'pgk_bias_grad': [P, L, I, I, I, I, I, P, F, P, I],
     'pgk_from_rgb': [P, I, I, I, I, I, P, F, P, I, P, L, P, I, L],

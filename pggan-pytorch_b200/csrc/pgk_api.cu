@@ -29,7 +29,9 @@ extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long l
 extern "C" int pgk_conv_thin_supported(int N, int H, int W, int Cin, int Cout, int KS, int ups);
 extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N, int H, int W, int Cin, int Cout,
                              const void* wpack, long long wpack_ps, const float* bias, int act, const void* mask_ref,
-                             long long mask_ps, float out_scale, void* out, long long out_ps, pgk_stream_t stream);
+                             long long mask_ps, float out_scale, void* out, long long out_ps, float* pn_r,
+                             pgk_stream_t stream);
+extern "C" int pgk_conv_thin_fuses_pixelnorm(int Cout);
 
 extern "C" int pgk_wgrad_thin_supported(int H, int W, int Cin, int Cout, int KS, int ups, int ngroups, int group_n,
                                         int Pr);
@@ -112,25 +114,32 @@ extern "C" int pgk_conv(const void* x, int P, int Pr, long long x_ps, int N, int
                         int ups,
                         const float* wf, const void* wt, long long wt_ps, const float* bias, const float* posT,
                         const float* pos_s, int act, const void* mask_ref, long long mask_ps, float out_scale, void* out,
-                        long long out_ps, pgk_stream_t stream) {
+                        long long out_ps, float* pn_r, pgk_stream_t stream) {
     PGK_REQUIRE(Pr >= 1 && Pr <= P, "pgk_conv: need 1 <= Pr <= P");
+    PGK_REQUIRE(!pn_r || (!mask_ref && out_scale == 1.0f), "pgk_conv: the pixel norm needs mask_ref == NULL and out_scale == 1");
     const double flops = 2.0 * N * H * W * (double)Cout * KS * KS * Cin;
     // algorithmic HBM bytes: read the planes of x that are used, write all planes of out, read one mask plane
     const double bytes = 2.0 * N * H * W * ((double)Cin * Pr / (ups ? 4 : 1) + (double)Cout * P + (mask_ref ? Cout : 0));
+    int rc;
+    bool pn_done = false;
     if (wt && !posT && tc_enabled() && pgk_conv_thin_supported(N, H, W, Cin, Cout, KS, ups)) {
         ProfScope prof(PGK_PROF_CONV_THIN, flops, bytes, stream);
-        return pgk_conv_thin(x, P, Pr, x_ps, N, H, W, Cin, Cout, wt, wt_ps, bias, act, mask_ref, mask_ps, out_scale, out,
-                             out_ps, stream);
-    }
-    if (wt && tc_enabled() && pgk_conv_tc_supported(N, H, W, Cin, Cout, KS, ups)) {
+        pn_done = pn_r && pgk_conv_thin_fuses_pixelnorm(Cout);
+        rc = pgk_conv_thin(x, P, Pr, x_ps, N, H, W, Cin, Cout, wt, wt_ps, bias, act, mask_ref, mask_ps, out_scale, out,
+                           out_ps, pn_done ? pn_r : nullptr, stream);
+    } else if (wt && tc_enabled() && pgk_conv_tc_supported(N, H, W, Cin, Cout, KS, ups)) {
         ProfScope prof(PGK_PROF_CONV, flops, bytes, stream);
-        return pgk_conv_tc(x, P, Pr, x_ps, N, H, W, Cin, Cout, KS, wt, wt_ps, bias, posT, pos_s, act, mask_ref, mask_ps,
+        rc = pgk_conv_tc(x, P, Pr, x_ps, N, H, W, Cin, Cout, KS, wt, wt_ps, bias, posT, pos_s, act, mask_ref, mask_ps,
+                         out_scale, out, out_ps, stream);
+    } else {
+        PGK_REQUIRE(wf != nullptr, "pgk_conv: this shape runs on the CUDA-core kernel, which needs the fp32 operand wf");
+        ProfScope prof(PGK_PROF_CONV_SIMT, flops, bytes, stream);
+        rc = pgk_conv_simt(x, P, x_ps, N, H, W, Cin, Cout, KS, ups, wf, bias, posT, pos_s, act, mask_ref, mask_ps,
                            out_scale, out, out_ps, stream);
     }
-    PGK_REQUIRE(wf != nullptr, "pgk_conv: this shape runs on the CUDA-core kernel, which needs the fp32 operand wf");
-    ProfScope prof(PGK_PROF_CONV_SIMT, flops, bytes, stream);
-    return pgk_conv_simt(x, P, x_ps, N, H, W, Cin, Cout, KS, ups, wf, bias, posT, pos_s, act, mask_ref, mask_ps,
-                         out_scale, out, out_ps, stream);
+    if (rc || !pn_r || pn_done) return rc;
+    // kernels whose tile does not hold every channel of a pixel: the pixel norm as a second pass, in place
+    return pgk_pixelnorm(out, out_ps, P, (long long)N * H * W, Cout, out, out_ps, pn_r, stream);
 }
 
 extern "C" int pgk_wgrad(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W,

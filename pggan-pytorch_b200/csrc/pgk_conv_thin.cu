@@ -43,6 +43,7 @@ struct ThinArgs {
     int pair;                   // MMA warp interleaves the K steps of two output rows (two accumulators)
     int tma;                    // producer: 1 = TMA boxes (16-byte inner extent), 0 = cp.async chunks
     int spin;                   // producer / MMA warps poll their barriers (1) or suspend in try_wait (0)
+    float* pn_r;                // pixel norm after the activation (NPAD <= 32): per-pixel factor stored here, or NULL
     int total_units;
     int Pout, split_acc;
     const bf16* wpack;          // [P][STEPS][2][Npad][8]
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
             uint4 mc[NV];
 #pragma unroll
             for (int k = 0; k < NV; ++k) mc[k] = mk[k];
-            const long long o = pix * a.Cout;
+            const long long pcur = pix, o = pix * a.Cout;
             if (ti + 2 < ntiles) {
                 ui += 2;
                 if (ui >= (uint32_t)a.RC) {
@@ -359,6 +360,45 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
             mbar_wait(afull(b), (ti / kAcc) & 1);
             fence_after();
             const uint32_t trow = tmem + b * acc_cols + trow_off;
+            bool done_pn = false;
+            if constexpr (NPAD <= 32) {
+                if (a.pn_r) {
+                    // generator layers: bias, LeakyReLU, then the pixel norm over this pixel's Cout channels
+                    // (network.py:37-40) -- the thread holds all of them
+                    float v[NPAD];
+#pragma unroll
+                    for (int c = 0; c < NPAD; c += 16) {
+                        tmem_ld16(trow + c, v + c);
+                        if (SPLIT) {
+                            float w[16];
+                            tmem_ld16(trow + NPAD + c, w);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[c + j] += w[j];
+                        }
+                    }
+                    float ss = 0.f;
+#pragma unroll
+                    for (int j = 0; j < NPAD; ++j) {
+                        float f = v[j] + bias_s[j];
+                        f *= f > 0.f ? s_pos : s_neg;
+                        f = j < a.Cout ? f : 0.f;
+                        v[j] = f;
+                        ss = fmaf(f, f, ss);
+                    }
+                    const float rr = rsqrtf(ss / (float)a.Cout + 1e-8f);
+                    a.pn_r[pcur] = rr;
+#pragma unroll
+                    for (int h = 0; h < NPAD / 8; ++h) {
+                        if (8 * h < a.Cout) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[8 * h + j] *= rr;
+                            split_store8(a.out, o + 8 * h, v + 8 * h);
+                        }
+                    }
+                    done_pn = true;
+                }
+            }
+            if (!done_pn) {
 #pragma unroll
             for (int c = 0; c < NPAD; c += 16) {
                 float v[16];
@@ -391,6 +431,7 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
                         split_store8(a.out, o + c + 8 * h, f);
                     }
                 }
+            }
             }
             fence_before();
             __syncwarp();
@@ -559,9 +600,15 @@ static int launch_thin(const CUtensorMap& tmA, ThinArgs& a, cudaStream_t stream)
 }
 
 // wpack: pgk_pack_thin output with 3 planes, wpack_ps elements apart
+// the epilogue applies the pixel norm itself when one thread holds every channel of its pixel in registers
+extern "C" int pgk_conv_thin_fuses_pixelnorm(int Cout) { return Cout <= 32; }
+
 extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N, int H, int W, int Cin, int Cout,
                              const void* wpack, long long wpack_ps, const float* bias, int act, const void* mask_ref,
-                             long long mask_ps, float out_scale, void* out, long long out_ps, pgk_stream_t stream) {
+                             long long mask_ps, float out_scale, void* out, long long out_ps, float* pn_r,
+                             pgk_stream_t stream) {
+    PGK_REQUIRE(!pn_r || (pgk_conv_thin_fuses_pixelnorm(Cout) && !mask_ref && out_scale == 1.0f),
+                "pgk_conv_thin: the fused pixel norm needs Cout <= 32, no mask and out_scale 1");
     PGK_REQUIRE(pgk_conv_thin_supported(N, H, W, Cin, Cout, 3, 0), "pgk_conv_thin: unsupported shape");
     PGK_REQUIRE(P >= 1 && P <= 3 && Pr >= 1 && Pr <= P, "pgk_conv_thin: need 1 <= Pr <= P <= 3");
     ThinArgs a;
@@ -578,6 +625,7 @@ extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N
     a.mask = make_planes(mask_ref, mask_ps, P);
     a.out_scale = out_scale;
     a.out = make_planes(out, out_ps, P);
+    a.pn_r = pn_r;
     a.x = (const bf16*)x;
     a.x_ps = x_ps;
     PGK_REQUIRE((((uintptr_t)x) & 15) == 0 && (P == 1 || (x_ps * 2) % 16 == 0), "pgk_conv_thin: x must be 16-byte aligned");

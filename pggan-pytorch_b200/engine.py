@@ -93,14 +93,17 @@ def _mask(m):
 # ---------------------------------------------------------------------------------------------
 
 
-def conv(x, w, cout, ks, out, ups=0, bias=None, posT=None, pos_s=None, act=0, mask=None, scale=1.0, fwd=False):
+def conv(x, w, cout, ks, out, ups=0, bias=None, posT=None, pos_s=None, act=0, mask=None, scale=1.0, fwd=False,
+         pn_r=None):
     """out <- pgk_conv(x); H, W are taken from `out`.  w = (fp32 [K][Cout] operand, bf16 planes [3][Cout][K] operand).
-    fwd=True: a forward pass whose values decide LeakyReLU masks -- all planes are read."""
+    fwd=True: a forward pass whose values decide LeakyReLU masks -- all planes are read.
+    pn_r: fp32 (N*H*W) tensor -- apply the pixel norm after the activation and store its per-pixel factor there."""
     mp, mps = _mask(mask)
     wf, wt = w
     call('pgk_conv', x.ptr, x.P, x.P if fwd else min(x.P, GRAD_PLANES), x.ps, out.N, out.H, out.W, x.C, cout, ks, ups, wf.data_ptr(), wt.data_ptr(),
          wt.stride(0), None if bias is None else bias.data_ptr(), None if posT is None else posT.data_ptr(),
-         None if pos_s is None else pos_s.data_ptr(), act, mp, mps, scale, out.ptr, out.ps)
+         None if pos_s is None else pos_s.data_ptr(), act, mp, mps, scale, out.ptr, out.ps,
+         None if pn_r is None else pn_r.data_ptr())
     return out
 
 
@@ -571,13 +574,15 @@ class GEngine(object):
             ps += [self.block(depth - 1).toRGB.conv.weight, self.block(depth - 1).toRGB.conv.bias]
         return ps
 
-    def _post(self, h, T, name):
-        """LeakyReLU has been applied by the conv; apply the pixel norm in place (network.py:37-40)."""
-        if self.G.pixelnorm:
-            r = torch.empty(h.N * h.H * h.W, dtype=torch.float32, device=h.t.device)
-            call('pgk_pixelnorm', h.ptr, h.ps, h.P, h.N * h.H * h.W, h.C, h.ptr, h.ps, r.data_ptr())
-            if T is not None:
-                setattr(T, 'r_' + name, r)
+    def _pn(self, h, T, name):
+        """The per-pixel factor buffer of the pixel norm that pgk_conv applies after the activation
+        (network.py:37-40); kept on the tape for the backward pass.  None when the generator has no pixel norm."""
+        if not self.G.pixelnorm:
+            return None
+        r = torch.empty(h.N * h.H * h.W, dtype=torch.float32, device=h.t.device)
+        if T is not None:
+            setattr(T, 'r_' + name, r)
+        return r
 
     def forward(self, z, P, out=None, tape=False):
         """z: fp32 (N, latent).  Returns (image fp32 N,C,r,r, tape or None); `out` lets the caller place the image
@@ -593,10 +598,11 @@ class GEngine(object):
         w1, w2 = self.cw(b0.c1, W_GFIRST), self.cw(b0.c2)
         h1 = PT.empty(n, 4, 4, w1.cout, P, dev)
         conv(zn, w1.F, 16 * w1.cout, 1, h1.view(1, 1, 16 * w1.cout), bias=w1.bias16, act=1, fwd=True)
-        self._post(h1, T, 'b0c1')
+        r = self._pn(h1, T, 'b0c1')   # the dense first layer: its 16 output pixels sit side by side in one GEMM row
+        if r is not None:
+            call('pgk_pixelnorm', h1.ptr, h1.ps, h1.P, h1.N * h1.H * h1.W, h1.C, h1.ptr, h1.ps, r.data_ptr())
         h2 = PT.empty(n, 4, 4, w2.cout, P, dev)
-        conv(h1, w2.F, w2.cout, 3, h2, bias=w2.bias, act=1, fwd=True)
-        self._post(h2, T, 'b0c2')
+        conv(h1, w2.F, w2.cout, 3, h2, bias=w2.bias, act=1, fwd=True, pn_r=self._pn(h2, T, 'b0c2'))
         if tape:
             T.zn = zn
             T.acts.append((None, None, h1, h2))
@@ -610,11 +616,9 @@ class GEngine(object):
             # weight gradient both read it through plain TMA boxes
             hu = mask_mul(h, PT.empty(n, res, res, h.C, P, dev), ups=1)
             u1 = PT.empty(n, res, res, w1.cout, P, dev)
-            conv(hu, w1.F, w1.cout, 3, u1, bias=w1.bias, act=1, fwd=True)
-            self._post(u1, T, 'b%dc1' % i)
+            conv(hu, w1.F, w1.cout, 3, u1, bias=w1.bias, act=1, fwd=True, pn_r=self._pn(u1, T, 'b%dc1' % i))
             u2 = PT.empty(n, res, res, w2.cout, P, dev)
-            conv(u1, w2.F, w2.cout, 3, u2, bias=w2.bias, act=1, fwd=True)
-            self._post(u2, T, 'b%dc2' % i)
+            conv(u1, w2.F, w2.cout, 3, u2, bias=w2.bias, act=1, fwd=True, pn_r=self._pn(u2, T, 'b%dc2' % i))
             if tape:
                 T.acts.append((h, hu, u1, u2))
             hprev, h = h, u2

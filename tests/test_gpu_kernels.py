@@ -102,3 +102,14 @@ WGRAD = [
 def test_wgrad(T, case):
     n, h, w, ci, co, p, groups = case
     assert T.wgrad_case(n, h, w, ci, co, 3, p, ngroups=groups)
+
+
+# conv + bias + LeakyReLU + pixel norm in one call (the generator's PGConv2d.forward, network.py:32-40): fused into the
+# thin kernel's epilogue for Cout <= 32, a second in-place pass on the other kernels
+PIXELNORM = [(2, 128, 128, 16, 8, 1), (1, 256, 256, 8, 8, 3), (3, 128, 256, 32, 16, 2), (2, 256, 128, 32, 32, 1),
+             (1, 128, 128, 16, 64, 3), (2, 32, 32, 64, 32, 3), (3, 8, 8, 128, 128, 1)]
+
+
+@pytest.mark.parametrize('case', PIXELNORM, ids=lambda c: 'N%d_%dx%d_%d-%d_P%d' % c)
+def test_conv_pixelnorm(T, case):
+    assert T.pixelnorm_case(*case)

@@ -66,6 +66,36 @@ def conv_case(N, H, W, Cin, Cout, KS, P, act=1, mask=False, bias=True, scale=1.0
     return e_tc < tol
 
 
+def pixelnorm_case(N, H, W, Cin, Cout, P):
+    """pgk_conv with pn_r (bias + LeakyReLU + pixel norm, network.py:34-40) against conv2d -> leaky_relu -> pixel norm in
+    PyTorch fp32; also checks the stored per-pixel factor."""
+    g = torch.Generator(device='cuda').manual_seed(N * 77 + H + Cin + Cout)
+    x = torch.randn(N, Cin, H, W, device='cuda', generator=g)
+    K = 9 * Cin
+    wf = (torch.randn(K, Cout, device='cuda', generator=g) / K ** 0.5).contiguous()
+    if Cin in (8, 16, 32) and Cout in (8, 16, 32, 64):
+        wt = torch.empty(3, lib.pgk_pack_thin_plane_elems(Cin, Cout), dtype=BF16, device='cuda')
+        call('pgk_pack_thin', wf.data_ptr(), Cin, Cout, wt.data_ptr(), wt.stride(0), 3)
+    else:
+        wt = torch.empty(3, Cout, K, dtype=BF16, device='cuda')
+        call('pgk_pack_operand', wf.data_ptr(), K, Cout, wt.data_ptr(), wt.stride(0), 3)
+    b = torch.randn(Cout, device='cuda', generator=g)
+    xp = E.PT.from_float(x, P)
+    o = E.PT.empty(N, H, W, Cout, P, 'cuda')
+    o.t.fill_(float('nan'))
+    r = torch.full((N * H * W,), float('nan'), device='cuda')
+    E.conv(xp, (wf, wt), Cout, 3, o, bias=b, act=1, fwd=True, pn_r=r)
+    torch.cuda.synchronize()
+    w4 = wf.view(3, 3, Cin, Cout).permute(3, 2, 0, 1).to(REF)
+    h = torch.nn.functional.leaky_relu(torch.nn.functional.conv2d(xp.float().to(REF), w4, b.to(REF), padding=1), 0.2)
+    rr = torch.rsqrt(torch.mean(h * h, 1, keepdim=True) + 1e-8)
+    e_y, e_r = rel(o.float(), h * rr), rel(r.view(N, 1, H, W), rr)
+    tol = {1: 2e-2, 2: 1e-4, 3: 2e-5}[P]
+    flag = 'ok ' if e_y < tol and e_r < tol else 'BAD'
+    print('%s conv+pixelnorm N%d %dx%d %d->%d P%d: y %.2e r %.2e' % (flag, N, H, W, Cin, Cout, P, e_y, e_r))
+    return e_y < tol and e_r < tol
+
+
 def wgrad_case(N, H, W, Cin, Cout, KS, P, ngroups=1):
     # (the engine reads min(P, 2) planes for weight gradients)
     g = torch.Generator(device='cuda').manual_seed(N * 1000 + H + Cin + Cout)
