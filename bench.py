@@ -269,7 +269,7 @@ def main():
             pass
 
         def iteration(self, it, g_cost, d_cost, *rest):
-            got['v'] = (float(g_cost), float(d_cost))          # D2H read of both losses (2 x 4 bytes)
+            got['v'] = (float(g_cost.detach()), float(d_cost.detach()))   # D2H read of both losses (2 x 4 bytes)
 
     tr = pg.Trainer(D, G, pg.wgan_gp_D_loss, pg.wgan_gp_G_loss, opt_d, opt_g, None, next_real(), next_lat)
     tr.register_plugin(Grab())
