@@ -5,19 +5,21 @@
 //
 //   * persistent CTAs stream image rows: a work unit is (sample, 128-pixel column strip, RC consecutive rows); the
 //     three input rows of an output row live in a shared-memory ring, and moving down one row loads ONE new row
-//     (a producer warp of 16-byte cp.async with zero fill for out-of-range rows and the +-1 pixel halo = the conv's
-//     padding; each warp instruction reads 512 contiguous bytes.  A TMA box with the 16-byte inner extent this
-//     layout needs delivers one 16-byte row per ~5 cycles -- measured, it bounded the first version of this kernel
-//     at 1.7-2.5 TB/s whatever the number of CTAs per SM);
+//     (TMA boxes of [130 pixels][8 channels]: out-of-range rows and the +-1 pixel halo are zero filled by the
+//     hardware = the conv's padding.  A producer warp of 16-byte cp.async with the same shared-memory layout is kept
+//     as a switchable flavour, PGK_THIN_TMA=0: measured equal at one CTA per SM, 5-15 % slower at two);
+//   * two CTAs per SM: the tile chain load -> MMA -> commit -> epilogue is latency-bound, and every tcgen05.mma
+//     streams its 128-row A tile from shared memory whatever N is ("what bounds the thin kernels");
 //   * a row buffer is stored channel-group planar, [Cin/8][130 + pad pixels][8 channels]: one pixel of one channel
 //     group is 16 bytes, so 8 consecutive pixels are exactly one un-swizzled K-major UMMA core matrix, and the 9 taps
 //     are nothing but 9 start addresses ((dy row buffer) + (1 + dx) * 16 bytes) into the same bytes -- no im2col,
 //     no per-tap reload;  K = 16 per MMA is two channel groups (LBO = plane stride) or, for Cin = 8, two
 //     neighbouring taps (LBO = 16 bytes);
 //   * the whole weight tensor (<= 9*32*64 bf16 per plane) is staged once per CTA in UMMA layout;
-//   * accumulator 128 pixels x Npad channels in TMEM, double buffered; 4 epilogue warps apply bias / LeakyReLU /
-//     backward mask / scale, split into planes and store straight to global memory (a thread's pixel row is
-//     contiguous with its neighbours': fully coalesced without staging).
+//   * accumulator 128 pixels x Npad channels in TMEM, four buffers; two epilogue warpgroups (thread = pixel) apply
+//     bias / LeakyReLU / backward mask (prefetched one tile ahead) / scale or the generator's pixel norm, split into
+//     planes and store straight to global memory (a thread's pixel row is contiguous with its neighbours': fully
+//     coalesced without staging).
 #include <stdlib.h>
 #include <string.h>
 

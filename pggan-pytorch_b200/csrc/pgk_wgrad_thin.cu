@@ -6,15 +6,16 @@
 // The reduction runs over pixels, so both operands must be K-major along x -- the transpose of how activations are
 // stored (channels innermost).  Per CTA (persistent, streaming rows like pgk_conv_thin.cu):
 //   warp 4      producer: halo rows of X ([Cin/8][130+ px][8 ch], zero filled outside the image) and rows of G into raw
-//               rings, as 16-byte cp.async chunks (a warp instruction reads 512 contiguous bytes; a TMA box with a
-//               16-byte inner extent moves ~one such row per 5 cycles, which is what bounded the first version);
+//               rings of 2-8 rows (TMA boxes; a 16-byte cp.async producer is kept as the PGK_THIN_TMA=0 flavour);
 //   warps 0-3   transpose in shared memory with ldmatrix.trans + stmatrix (8x8 bf16 blocks): every X row once into
 //               XT3 = three copies shifted by kx, stacked along M (row m = kx*Cin + ci), every G row once into GT;
 //   warp 5      per output row y: D[ky] (3*Cin x Cout, fp32 in TMEM) += XT3[row y+ky-1] * GT[row y]^T, K = 128 pixels
 //               (8 MMAs of K = 16 per ky); the accumulators persist over ALL rows this CTA processes;
 //   warps 0-3   at the very end: TMEM -> fp32 atomics into dW[(ky*3+kx)*Cin + ci][co] (one flush per CTA).
-// Every activation byte is read from HBM once; the tensor-core work is tiny, the kernel is bound by HBM / the
-// shared-memory transposes.
+// Cin = 8: the four ring slots of transposed rows are exactly the 16 row groups one M = 128 MMA reads, so ONE chain
+// per output row covers ky = 0, 1, 2 (four rotating accumulators, see STACK below) -- a third of the MMAs.
+// Every activation byte is read from HBM once; two CTAs per SM where shared memory allows (Cin <= 16).  The kernel is
+// bound by the MMA rate (each MMA streams a 128-row A tile from shared memory) and the load -> transpose -> MMA chain.
 #include <stdlib.h>
 #include <string.h>
 
