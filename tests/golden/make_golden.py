@@ -93,7 +93,16 @@ def build(cfg):
     return G, D
 
 
-def make_step(name, cfg):
+# cases that pin the oracle only (CPU tests): file prefix 'ostep_', not picked up by the GPU parity tests
+ORACLE_ONLY = {
+    # name: (resolution, channels, fmap_base, fmap_max, latent, N, depth, alpha)
+    'd3_a0':      (32, 3, 256, 32, 32, 3, 3, 0.0),    # the first iteration of a new depth: alpha == 0.0 exactly
+    'd2_n1':      (16, 1, 128, 32, 16, 1, 2, 0.6),    # a batch of one (minibatch stddev over a single sample)
+    'd1_a1_wide': (8, 3, 256, 48, 40, 5, 1, 1.0),     # widths that are not powers of two
+}
+
+
+def make_step(name, cfg, prefix='step_'):
     import wgan_gp_loss
     res, ch, fb, fm, lat, n, depth, alpha = cfg
     G, D = build(cfg)
@@ -142,7 +151,7 @@ def make_step(name, cfg):
     for k, p_ in G.named_parameters():
         if p_.grad is not None:
             out['Ggrad.' + k] = p_.grad.detach().clone().numpy()
-    np.savez_compressed(os.path.join(HERE, 'step_%s.npz' % name), **out)
+    np.savez_compressed(os.path.join(HERE, '%s%s.npz' % (prefix, name)), **out)
     print(name, 'd_cost', float(d_cost), 'g_cost', float(g_cost), 'keys', len(out))
 
 
@@ -234,7 +243,13 @@ def make_schedule():
 
 if __name__ == '__main__':
     install_shims()
+    if len(sys.argv) > 1 and sys.argv[1] == 'oracle-only':     # adds the ostep_* files without touching the others
+        for name, cfg in ORACLE_ONLY.items():
+            make_step(name, cfg, prefix='ostep_')
+        sys.exit(0)
     for name, cfg in CONFIGS.items():
         make_step(name, cfg)
+    for name, cfg in ORACLE_ONLY.items():
+        make_step(name, cfg, prefix='ostep_')
     make_trainer()
     make_schedule()

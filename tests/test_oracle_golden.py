@@ -7,17 +7,19 @@ import sys
 import pytest
 import torch
 
-from _util import STEP_CASES, load_schedule, load_step, load_trainer, rel_err
+from _util import ORACLE_ONLY_CASES, STEP_CASES, load_schedule, load_step, load_trainer, rel_err
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle'))
 import pggan_oracle as O  # noqa: E402
 
 TOL = 2e-5  # same fp32 torch ops in a different association order
+CASES = [(c, 'step_') for c in STEP_CASES] + [(c, 'ostep_') for c in ORACLE_ONLY_CASES]
+IDS = [p + c for c, p in CASES]
 
 
-@pytest.mark.parametrize('case', STEP_CASES)
+@pytest.mark.parametrize('case', CASES, ids=IDS)
 def test_forward_matches_reference(case):
-    g = load_step(case)
+    g = load_step(case[0], prefix=case[1])
     nb = O.n_blocks_for(g['resolution'])
     fake = O.generator_forward(g['pg'], g['z1'], g['depth'], g['alpha'])
     assert fake.shape == g['fake'].shape
@@ -26,9 +28,9 @@ def test_forward_matches_reference(case):
     assert rel_err(O.discriminator_forward(g['pd'], g['fake'], g['depth'], g['alpha'], nb), g['d_fake_scores']) < TOL
 
 
-@pytest.mark.parametrize('case', STEP_CASES)
+@pytest.mark.parametrize('case', CASES, ids=IDS)
 def test_d_step_matches_reference(case):
-    g = load_step(case)
+    g = load_step(case[0], prefix=case[1])
     nb = O.n_blocks_for(g['resolution'])
     cost, rl, fl, grads = O.d_step_grads(g['pd'], g['pg'], g['real'], g['z1'], g['mixing'], g['depth'], g['alpha'], nb)
     assert rel_err(cost, g['d_cost']) < TOL
@@ -39,9 +41,9 @@ def test_d_step_matches_reference(case):
         assert rel_err(grads[k], g['dgrad'][k]) < 2e-4, k
 
 
-@pytest.mark.parametrize('case', STEP_CASES)
+@pytest.mark.parametrize('case', CASES, ids=IDS)
 def test_g_step_matches_reference(case):
-    g = load_step(case)
+    g = load_step(case[0], prefix=case[1])
     nb = O.n_blocks_for(g['resolution'])
     cost, grads = O.g_step_grads(g['pg'], g['pd'], g['z2'], g['depth'], g['alpha'], nb)
     assert rel_err(cost, g['g_cost']) < TOL
