@@ -360,7 +360,7 @@ def main():
         'clocks': clocks,
         'roofline': roof,
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # the CPU leg is reported at N = 1 only
         base, _, _, _ = cpu_reference_leg(cfg, 3, 1, budget_s=20.0)
         out['cpu_baseline'] = base
     print(json.dumps(out))
