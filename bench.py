@@ -137,6 +137,71 @@ def cpu_reference_leg(cfg, steps, warmup, budget_s=25.0):
                        % (k, n, depth, r, r, alpha, cores)), dt, k, w
 
 
+FAMILIES = {0: 'conv_tc_kernel (tcgen05 implicit-GEMM conv: forward + data gradient)',
+            1: 'wgrad_tc_kernel (tcgen05 weight gradient)', 2: 'conv_simt_kernel (CUDA-core conv)',
+            3: 'wgrad_simt_kernel (CUDA-core weight gradient)',
+            4: 'conv_thin_kernel (row-streaming tcgen05 conv, Cin 8/16/32)',
+            5: 'wgrad_thin_kernel (row-streaming tcgen05 weight gradient, Cin 8/16/32)'}
+
+
+def assemble_roofline(config, cfg, fam, prod, ksteps, step_s, batch_overridden=False):
+    """The `roofline` object of the JSON line from the per-family launch records (pure function; CPU-tested).
+    fam[k] = (algorithmic FLOPs, algorithmic bytes, device ms, launches) and prod[k] = bf16 tensor-core FLOPs issued,
+    summed over `ksteps` steps of `step_s` seconds each, for the kernel families of include/pgk.h (PGK_PROF_*)."""
+    depth, alpha, n, ch = cfg['depth'], cfg['alpha'], cfg['n'], cfg['ch']
+    fade = depth > 0 and alpha < 1.0
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_tf = float(peaks.get('bf16_tflops_sustained', 1400.0))
+    peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'
+    fimg = flops_per_image(depth, ch, fade)
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    dom = max(fam, key=lambda k: fam[k][2])           # the kernel family with the largest share of the step
+    fl, by, ms_k, n_k = fam[dom]
+    tf = fl / (ms_k * 1e-3) / 1e12 if ms_k > 0 else 0.0
+    gbs = by / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0
+    if dom in (4, 5):      # thin layers: 36..190 flop/byte, left of the ridge (209): HBM roofline
+        roof = {'bound': 'hbm', 'kernel': FAMILIES[dom], 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+                'frac': gbs / hbm_peak, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6.65 TB/s'}
+    else:
+        roof = {'bound': 'tensor', 'kernel': FAMILIES[dom], 'achieved': tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                'frac': tf / peak_tf, 'peak_source': peak_src}
+    # DRAM bytes per launch of the dominant kernel from a committed ncu capture of this config (tools/ncu_traffic.py)
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            t = json.load(f).get(config, {}).get(FAMILIES[dom].split(' ')[0])
+        if t and not batch_overridden:
+            traffic, traffic_src = t['bytes_per_launch'], t['source']
+    except Exception:
+        pass
+    if traffic is not None:
+        roof['traffic_source'] = traffic_src
+        roof['algorithmic_bytes_per_launch'] = by / max(1, n_k)
+    # what the tensor pipe itself executed for the dominant kernel: issued bf16 products per second against the same
+    # measured peak (in the bf16 mode this equals achieved / frac; in the fp32-faithful mode it is 3..6x higher)
+    ptf = prod[dom] / (ms_k * 1e-3) / 1e12 if ms_k > 0 else 0.0
+    roof['tensor_pipe'] = {'issued_tflops': ptf, 'frac_of_peak': ptf / peak_tf,
+                           'products_per_flop': prod[dom] / fl if fl > 0 else 0.0}
+    roof.update(traffic=traffic, launches_timed=n_k, kernel_ms_per_step=ms_k / ksteps,
+                share_of_step=ms_k / ksteps / (step_s * 1e3),
+                families={FAMILIES[k].split(' ')[0]: {'ms_per_step': v[2] / ksteps, 'launches': v[3],
+                                                       'tflops': v[0] / (v[2] * 1e-3) / 1e12 if v[2] > 0 else 0.0,
+                                                       'issued_tflops': prod[k] / (v[2] * 1e-3) / 1e12 if v[2] > 0 else 0.0,
+                                                       'gbs': v[1] / (v[2] * 1e-3) / 1e9 if v[2] > 0 else 0.0}
+                          for k, v in fam.items() if v[3]},
+                step_algorithmic={'gflop_per_image': fimg / 1e9, 'achieved': fimg * n / step_s / 1e12,
+                                  'frac': fimg * n / step_s / 1e12 / peak_tf})
+    if cfg['precision'] == 'fp32':
+        roof['note'] = ('fp32-faithful mode: every algorithmic FLOP costs 6 (forward) or 3 (gradient chains) bf16 '
+                        'tensor-core products, so frac <= 1/6 .. 1/3 by construction; tensor_pipe counts the products')
+    return roof
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -167,9 +232,10 @@ def main():
             return
         base, dt, k, w = cpu_reference_leg(cfg, args.steps, args.warmup, budget_s=60.0)
         print(json.dumps({'impl': 'reference', 'metric': 'images/sec (G+D+GP step)', 'value': base['value'],
-                          'unit': 'images/sec', 'n_gpus': 0, 'steps': k, 'warmup': w, 'ms_per_step': dt * 1e3,
+                          'unit': 'images/sec', 'n_gpus': args.gpus, 'steps': k, 'warmup': w, 'ms_per_step': dt * 1e3,
                           'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
                           'data': 'synthetic', 'config': workload, 'cpu_baseline': base,
+                          'note': 'host CPU only (rank 0); n_gpus names the launch this line pairs with',
                           'e2e': {'value': base['value'], 'unit': 'images/sec', 'h2d_bytes_per_step': 0,
                                   'd2h_bytes_per_step': 0}}))
         return
@@ -291,63 +357,17 @@ def main():
         step_device(i)
     torch.cuda.synchronize()
     pg._lib.prof_enable(False)
-    FAMILIES = {0: 'conv_tc_kernel (tcgen05 implicit-GEMM conv: forward + data gradient)',
-                1: 'wgrad_tc_kernel (tcgen05 weight gradient)', 2: 'conv_simt_kernel (CUDA-core conv)',
-                3: 'wgrad_simt_kernel (CUDA-core weight gradient)',
-                4: 'conv_thin_kernel (row-streaming tcgen05 conv, Cin 8/16/32)',
-                5: 'wgrad_thin_kernel (row-streaming tcgen05 weight gradient, Cin 8/16/32)'}
     fam = {k: pg._lib.prof_read(k) for k in FAMILIES}
+    prod = {k: pg._lib.prof_read_products(k) for k in FAMILIES}    # bf16 tensor-core FLOPs issued (1/3/6 per FLOP)
     pg._lib.prof_reset()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
-    peak_tf = float(peaks.get('bf16_tflops_sustained', 1400.0))
-    peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'
     step_s = ms / 1e3 / args.steps
     value = n * world / step_s
-    fimg = flops_per_image(depth, ch, fade)
-    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
-    dom = max(fam, key=lambda k: fam[k][2])           # the kernel family with the largest share of the step
-    fl, by, ms_k, n_k = fam[dom]
-    tf = fl / (ms_k * 1e-3) / 1e12 if ms_k > 0 else 0.0
-    gbs = by / (ms_k * 1e-3) / 1e9 if ms_k > 0 else 0.0
-    if dom in (4, 5):      # thin layers: 36..190 flop/byte, left of the ridge (209): HBM roofline
-        roof = {'bound': 'hbm', 'kernel': FAMILIES[dom], 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s',
-                'frac': gbs / hbm_peak, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6.65 TB/s'}
-    else:
-        roof = {'bound': 'tensor', 'kernel': FAMILIES[dom], 'achieved': tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                'frac': tf / peak_tf, 'peak_source': peak_src}
-    # DRAM bytes per launch of the dominant kernel from a committed ncu capture of this config (tools/ncu_traffic.py)
-    traffic, traffic_src = None, None
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
-            t = json.load(f).get(args.config, {}).get(FAMILIES[dom].split(' ')[0])
-        if t and not args.batch:
-            traffic, traffic_src = t['bytes_per_launch'], t['source']
-    except Exception:
-        pass
-    if traffic is not None:
-        roof['traffic_source'] = traffic_src
-        roof['algorithmic_bytes_per_launch'] = by / max(1, n_k)
-    roof.update(traffic=traffic, launches_timed=n_k, kernel_ms_per_step=ms_k / ksteps,
-                share_of_step=ms_k / ksteps / (step_s * 1e3),
-                families={FAMILIES[k].split(' ')[0]: {'ms_per_step': v[2] / ksteps, 'launches': v[3],
-                                                       'tflops': v[0] / (v[2] * 1e-3) / 1e12 if v[2] > 0 else 0.0,
-                                                       'gbs': v[1] / (v[2] * 1e-3) / 1e9 if v[2] > 0 else 0.0}
-                          for k, v in fam.items() if v[3]},
-                step_algorithmic={'gflop_per_image': fimg / 1e9, 'achieved': fimg * n / step_s / 1e12,
-                                  'frac': fimg * n / step_s / 1e12 / peak_tf})
-    if cfg['precision'] == 'fp32':
-        roof['note'] = ('fp32-faithful mode: every algorithmic FLOP costs 6 (forward) or 3 (gradient chains) bf16 '
-                        'tensor-core products, so frac <= 1/6 .. 1/3 by construction')
+    roof = assemble_roofline(args.config, cfg, fam, prod, ksteps, step_s, bool(args.batch))
     out = {
         'metric': 'images/sec (G+D+GP step)', 'value': value, 'unit': 'images/sec', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': step_s * 1e3, 'higher_is_better': True,

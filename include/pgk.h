@@ -64,6 +64,10 @@ void pgk_count_launch(int n);
 #define PGK_PROF_WGRAD_THIN 5 /* pgk_wgrad launches served by the thin-layer tcgen05 kernel              */
 void pgk_prof_enable(int on);
 int pgk_prof_read(int family, double* flops, double* bytes, double* ms, long long* launches);
+/* the bf16 tensor-core FLOPs the recorded launches of a family ISSUED: 2*M*N*K x the number of plane products
+ * (Pr = 1, 2, 3 planes read -> 1, 3, 6 products per algorithmic FLOP); 0 for the CUDA-core families.  This is what
+ * the tensor pipe's own peak bounds -- in the fp32-faithful mode it is 3..6x the algorithmic figure above. */
+int pgk_prof_read_products(int family, double* product_flops);
 void pgk_prof_reset(void);
 /* 0 routes every shape to the CUDA-core kernels (A/B comparisons; also PGK_TC=0 in the environment). */
 void pgk_set_tc(int on);

@@ -86,6 +86,8 @@ def load():
     lib.pgk_prof_read.argtypes = [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                   ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_longlong)]
     lib.pgk_prof_read.restype = c_int
+    lib.pgk_prof_read_products.argtypes = [c_int, ctypes.POINTER(ctypes.c_double)]
+    lib.pgk_prof_read_products.restype = c_int
     lib.pgk_prof_reset.restype = None
     lib.pgk_pack_thin_plane_elems.argtypes = [c_int, c_int]
     lib.pgk_pack_thin_plane_elems.restype = c_longlong
@@ -102,7 +104,7 @@ def load():
 def exported_symbols():
     return ['pgk_version', 'pgk_last_error', 'pgk_arch_check', 'pgk_launch_count', 'pgk_reset_launch_count',
             'pgk_count_launch',
-            'pgk_prof_enable', 'pgk_prof_read', 'pgk_prof_reset', 'pgk_set_tc', 'pgk_pack_thin_plane_elems'] + list(SIGNATURES)
+            'pgk_prof_enable', 'pgk_prof_read', 'pgk_prof_read_products', 'pgk_prof_reset', 'pgk_set_tc', 'pgk_pack_thin_plane_elems'] + list(SIGNATURES)
 
 
 _checked_devices = set()
@@ -159,6 +161,17 @@ def prof_read(family):
     if rc != 0:
         raise PgkError('pgk_prof_read failed: %s' % lib.pgk_last_error().decode())
     return f.value, b.value, t.value, n.value
+
+
+def prof_read_products(family):
+    """bf16 tensor-core FLOPs issued by one kernel family since the last prof_reset() (algorithmic FLOPs x the
+    1 / 3 / 6 plane products of each launch)."""
+    lib = load()
+    f = ctypes.c_double()
+    rc = lib.pgk_prof_read_products(family, ctypes.byref(f))
+    if rc != 0:
+        raise PgkError('pgk_prof_read_products failed: %s' % lib.pgk_last_error().decode())
+    return f.value
 
 
 def prof_reset():

@@ -55,6 +55,7 @@ namespace {
 struct ProfRec {
     cudaEvent_t e0, e1;
     double flops, bytes;
+    double products;   // bf16 tensor-core FLOPs actually issued: flops x (products of planes i + j < Pr); 0 on CUDA cores
     int family;
 };
 bool g_prof = false;
@@ -64,9 +65,11 @@ struct ProfScope {
     bool on;
     cudaStream_t s;
     ProfRec r;
-    ProfScope(int family, double flops, double bytes, pgk_stream_t stream) : on(g_prof), s((cudaStream_t)stream) {
+    ProfScope(int family, double flops, double bytes, pgk_stream_t stream, int Pr = 0)
+        : on(g_prof), s((cudaStream_t)stream) {
         if (!on) return;
         r.family = family, r.flops = flops, r.bytes = bytes;
+        r.products = flops * (Pr * (Pr + 1) / 2);
         cudaEventCreate(&r.e0);
         cudaEventCreate(&r.e1);
         cudaEventRecord(r.e0, s);
@@ -102,6 +105,14 @@ extern "C" int pgk_prof_read(int family, double* flops, double* bytes, double* m
     return PGK_OK;
 }
 
+extern "C" int pgk_prof_read_products(int family, double* product_flops) {
+    double f = 0.0;
+    for (auto& r : g_recs)
+        if (r.family == family) f += r.products;
+    if (product_flops) *product_flops = f;
+    return PGK_OK;
+}
+
 extern "C" void pgk_prof_reset(void) {
     for (auto& r : g_recs) {
         cudaEventDestroy(r.e0);
@@ -123,12 +134,12 @@ extern "C" int pgk_conv(const void* x, int P, int Pr, long long x_ps, int N, int
     int rc;
     bool pn_done = false;
     if (wt && !posT && tc_enabled() && pgk_conv_thin_supported(N, H, W, Cin, Cout, KS, ups)) {
-        ProfScope prof(PGK_PROF_CONV_THIN, flops, bytes, stream);
+        ProfScope prof(PGK_PROF_CONV_THIN, flops, bytes, stream, Pr);
         pn_done = pn_r && pgk_conv_thin_fuses_pixelnorm(Cout);
         rc = pgk_conv_thin(x, P, Pr, x_ps, N, H, W, Cin, Cout, wt, wt_ps, bias, act, mask_ref, mask_ps, out_scale, out,
                            out_ps, pn_done ? pn_r : nullptr, stream);
     } else if (wt && tc_enabled() && pgk_conv_tc_supported(N, H, W, Cin, Cout, KS, ups)) {
-        ProfScope prof(PGK_PROF_CONV, flops, bytes, stream);
+        ProfScope prof(PGK_PROF_CONV, flops, bytes, stream, Pr);
         rc = pgk_conv_tc(x, P, Pr, x_ps, N, H, W, Cin, Cout, KS, wt, wt_ps, bias, posT, pos_s, act, mask_ref, mask_ps,
                          out_scale, out, out_ps, stream);
     } else {
@@ -152,7 +163,7 @@ extern "C" int pgk_wgrad(const void* x, long long x_ps, const void* g, long long
     const int thin_cin = Cin == 64 ? 32 : Cin;
     if (tc_enabled() && (Cin != 64 || Cout < 64) &&
         pgk_wgrad_thin_supported(H, W, thin_cin, Cout, KS, ups, ngroups, group_n, Pr)) {
-        ProfScope prof(PGK_PROF_WGRAD_THIN, flops, bytes, stream);
+        ProfScope prof(PGK_PROF_WGRAD_THIN, flops, bytes, stream, Pr);
         for (int c0 = 0; c0 < Cin; c0 += thin_cin) {
             int rc = pgk_wgrad_thin(x, x_ps, g, g_ps, P, Pr, H, W, thin_cin, Cin, c0, Cout, ngroups, group_n, xoff, goff,
                                     dwp, c0 == 0 ? db : nullptr, bias_groups, stream);
@@ -162,7 +173,7 @@ extern "C" int pgk_wgrad(const void* x, long long x_ps, const void* g, long long
     }
     int rc;
     if (tc_enabled() && pgk_wgrad_tc_supported(H, W, Cin, Cout, KS, ups, ngroups, group_n)) {
-        ProfScope prof(PGK_PROF_WGRAD, flops, bytes, stream);
+        ProfScope prof(PGK_PROF_WGRAD, flops, bytes, stream, Pr);
         rc = pgk_wgrad_tc(x, x_ps, g, g_ps, P, Pr, H, W, Cin, Cout, KS, ngroups, group_n, xoff, goff, dwp, stream);
     } else {
         ProfScope prof(PGK_PROF_WGRAD_SIMT, flops, bytes, stream);

@@ -71,3 +71,37 @@ def test_committed_traffic_figure_is_what_the_committed_capture_says():
     ids = ids[len(ids) // 2:]
     assert len(ids) == entry['launches']
     assert sum(per[i] for i in ids) / len(ids) == pytest.approx(entry['bytes_per_launch'], rel=1e-9)
+
+
+def test_roofline_assembly_from_launch_records():
+    """bench.assemble_roofline is a pure function of the per-family launch records: feed it the figures of the
+    committed end-of-round c2 run (gpurun_out/call8) and check the JSON it builds, including the tensor-pipe view
+    (issued bf16 products: 6 per FLOP in forward passes, 3 in the gradient chains of the fp32-faithful mode)."""
+    cfg = bench.CONFIGS['c2']
+    ksteps, step_s = 3, 88.6e-3
+    conv_ms, wgrad_ms = 58.08 * ksteps, 16.34 * ksteps
+    conv_fl, wgrad_fl = 296.37e12 * conv_ms * 1e-3, 404.64e12 * wgrad_ms * 1e-3
+    fam = {0: (conv_fl, 694.8e9 * conv_ms * 1e-3, conv_ms, 261), 1: (wgrad_fl, 721.5e9 * wgrad_ms * 1e-3, wgrad_ms, 57),
+           2: (0.0, 0.0, 0.0, 0), 3: (1.0e9, 1.0e6, 0.2, 3), 4: (0.0, 0.0, 0.0, 0), 5: (0.0, 0.0, 0.0, 0)}
+    prod = {0: 4.7 * conv_fl, 1: 3.0 * wgrad_fl, 2: 0.0, 3: 0.0, 4: 0.0, 5: 0.0}
+    roof = bench.assemble_roofline('c2', cfg, fam, prod, ksteps, step_s)
+    with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+        peak = json.load(f)['bf16_tflops_sustained']
+    assert roof['bound'] == 'tensor' and roof['kernel'].startswith('conv_tc_kernel') and roof['unit'] == 'TFLOP/s'
+    assert roof['peak'] == peak and roof['achieved'] == pytest.approx(296.37, rel=1e-6)
+    assert roof['frac'] == pytest.approx(296.37 / peak, rel=1e-6)
+    assert roof['tensor_pipe']['products_per_flop'] == pytest.approx(4.7)
+    assert roof['tensor_pipe']['issued_tflops'] == pytest.approx(4.7 * 296.37, rel=1e-6)
+    assert roof['tensor_pipe']['frac_of_peak'] == pytest.approx(4.7 * 296.37 / peak, rel=1e-6)
+    assert roof['share_of_step'] == pytest.approx(58.08 / 88.6, rel=1e-6) and roof['launches_timed'] == 261
+    assert set(roof['families']) == {'conv_tc_kernel', 'wgrad_tc_kernel', 'wgrad_simt_kernel'}
+    assert roof['families']['wgrad_tc_kernel']['issued_tflops'] == pytest.approx(3 * 404.64, rel=1e-6)
+    assert roof['traffic'] is not None and roof['algorithmic_bytes_per_launch'] > 0     # profiles/traffic.json, c2
+    assert roof['step_algorithmic']['gflop_per_image'] == pytest.approx(186.41, rel=1e-3)
+    assert 'note' in roof
+    # a thin-layer family on top: the HBM roofline is reported, and a batch override drops the committed traffic figure
+    fam[4] = (1.0e12, 3.0e9 * 100.0, 100.0e3 * 1e-3 * 1000, 10)
+    prod[4] = 1.0e12
+    r2 = bench.assemble_roofline('c4', bench.CONFIGS['c4'], fam, prod, ksteps, step_s, batch_overridden=True)
+    assert r2['bound'] == 'hbm' and r2['unit'] == 'GB/s' and r2['traffic'] is None and 'note' not in r2
+    json.dumps(roof), json.dumps(r2)
