@@ -1,0 +1,43 @@
+#!/bin/bash
+# Round 2, first GPU call: re-validate the round-1 end state on a fresh box, then collect the two measurements the
+# round-1 sessions did not get to (no GPU minutes were left): the per-shape breakdown of every conv / weight-gradient
+# launch (tools/shape_profile.py) and the "GPU reference bar" of SURVEY.md 8(d) (the reference's arithmetic in PyTorch
+# eager on the GPU, tools/gpu_eager_bar.py).     gpurun --timeout 1500 -- 'bash tools/gpu_call_r2_first.sh'
+set -u
+OUT=gpurun_out/r2_first
+mkdir -p $OUT
+export PYTHONUNBUFFERED=1
+t0=$(date +%s)
+stamp() { echo "=== $1 (t+$(( $(date +%s) - t0 ))s)"; }
+stamp "full gpu test-suite"
+timeout 1200 python -m pytest tests -x -q -m gpu > $OUT/pytest_gpu.log 2>&1; echo "rc=$?" >> $OUT/pytest_gpu.log
+tail -3 $OUT/pytest_gpu.log
+stamp "smoke"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; tail -2 $OUT/smoke.log
+stamp "default bench line (c2) with the tensor-pipe view"
+timeout 600 python bench.py > $OUT/bench_c2.json 2> $OUT/bench_c2.err
+python - $OUT/bench_c2.json <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    r=d['roofline']
+    print(' ms/step %.2f  img/s %.1f  e2e %.1f  launches %d  clocks %s' % (d['ms_per_step'], d['value'], d['e2e']['value'], d['gpu_launches'], d['clocks']))
+    print('  dominant %s %s %.1f %s frac %.3f share %.2f tensor_pipe %s' % (r['kernel'].split(' ')[0], r['bound'], r['achieved'], r['unit'], r['frac'], r['share_of_step'], r['tensor_pipe']))
+except Exception as e: print(' failed', e)
+PY
+stamp "per-shape profiles c4 c3 c5 c2"
+for c in c4 c3 c5 c2; do
+  timeout 300 python tools/shape_profile.py --config $c --steps 3 --warmup 2 --json $OUT/shapes_$c.json > $OUT/shapes_$c.txt 2>&1
+  head -30 $OUT/shapes_$c.txt
+done
+stamp "wave-quantisation A/B of the wide conv's channel-tile cap (c4, c3)"
+for nt in 64 128; do
+  for c in c4 c3; do
+    PGK_CONV_NT=$nt timeout 300 python tools/shape_profile.py --config $c --steps 3 --warmup 2 --json $OUT/shapes_${c}_nt$nt.json > $OUT/shapes_${c}_nt$nt.txt 2>&1
+    head -1 $OUT/shapes_${c}_nt$nt.txt
+  done
+done
+stamp "GPU reference bar (PyTorch eager, fp32 and TF32)"
+timeout 900 python tools/gpu_eager_bar.py c2 c3 c4 c5 --steps 3 --warmup 2 > $OUT/eager_bar.jsonl 2> $OUT/eager_bar.err
+cat $OUT/eager_bar.jsonl
+stamp "done"
