@@ -6,7 +6,7 @@ import traceback
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 from _util import STEP_CASES, load_step, rel_err  # noqa: E402
 from _gpu_util import O, build_pair, named_grads, pg  # noqa: E402

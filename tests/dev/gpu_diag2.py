@@ -4,7 +4,7 @@ import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 from _util import rel_err  # noqa: E402
 from _gpu_util import O, build_pair, pg  # noqa: E402

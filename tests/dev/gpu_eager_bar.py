@@ -3,7 +3,7 @@ torch library ops, autograd double backward) run in PyTorch eager mode ON THE GP
 bench configs.  This is the number the hand-written kernels have to beat; it is NOT part of bench.py's contract (the
 reference arm there is the host-CPU path) and nothing in the product imports this file.
 
-    python tools/gpu_eager_bar.py [c1 c2 c3 c4 c5] [--steps 5] [--warmup 2] [--batch N]
+    python tests/dev/gpu_eager_bar.py [c1 c2 c3 c4 c5] [--steps 5] [--warmup 2] [--batch N]
 
 Prints one JSON line per (config, precision): images/sec of D step + Adam + G step + Adam with inputs resident in HBM.
 Batches that do not fit (cuDNN workspace at depth 8) are halved until they do and the batch used is reported.
@@ -15,7 +15,7 @@ import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 import bench  # noqa: E402

@@ -2,7 +2,7 @@
 # Round 2, first GPU call: re-validate the round-1 end state on a fresh box, then collect the two measurements the
 # round-1 sessions did not get to (no GPU minutes were left): the per-shape breakdown of every conv / weight-gradient
 # launch (tools/shape_profile.py) and the "GPU reference bar" of SURVEY.md 8(d) (the reference's arithmetic in PyTorch
-# eager on the GPU, tools/gpu_eager_bar.py).     gpurun --timeout 1500 -- 'bash tools/gpu_call_r2_first.sh'
+# eager on the GPU, tests/dev/gpu_eager_bar.py).     gpurun --timeout 1500 -- 'bash tools/gpu_call_r2_first.sh'
 set -u
 OUT=gpurun_out/r2_first
 mkdir -p $OUT
@@ -38,6 +38,6 @@ for nt in 64 128; do
   done
 done
 stamp "GPU reference bar (PyTorch eager, fp32 and TF32)"
-timeout 900 python tools/gpu_eager_bar.py c2 c3 c4 c5 --steps 3 --warmup 2 > $OUT/eager_bar.jsonl 2> $OUT/eager_bar.err
+timeout 900 python tests/dev/gpu_eager_bar.py c2 c3 c4 c5 --steps 3 --warmup 2 > $OUT/eager_bar.jsonl 2> $OUT/eager_bar.err
 cat $OUT/eager_bar.jsonl
 stamp "done"
