@@ -25,6 +25,9 @@ try:
     print('  dominant %s %s %.1f %s frac %.3f share %.2f tensor_pipe %s' % (r['kernel'].split(' ')[0], r['bound'], r['achieved'], r['unit'], r['frac'], r['share_of_step'], r['tensor_pipe']))
 except Exception as e: print(' failed', e)
 PY
+stamp "hardware probe: swizzled row-shifted starts, cycles per MMA by layout / N / A-in-TMEM"
+(nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o /tmp/umma_probe tools/probes/umma_probe.cu && timeout 120 /tmp/umma_probe) > $OUT/umma_probe.txt 2>&1
+cat $OUT/umma_probe.txt
 stamp "per-shape profiles c4 c3 c5 c2"
 for c in c4 c3 c5 c2; do
   timeout 300 python tools/shape_profile.py --config $c --steps 3 --warmup 2 --json $OUT/shapes_$c.json > $OUT/shapes_$c.txt 2>&1
