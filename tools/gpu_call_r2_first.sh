@@ -28,6 +28,11 @@ PY
 stamp "hardware probe: swizzled row-shifted starts, cycles per MMA by layout / N / A-in-TMEM"
 (nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o /tmp/umma_probe tools/probes/umma_probe.cu && timeout 120 /tmp/umma_probe) > $OUT/umma_probe.txt 2>&1
 cat $OUT/umma_probe.txt
+stamp "experimental: thin weight gradient with SWIZZLE_128B transposed tiles (PGK_WTHIN_SW128=1): numerics, then timing A/B"
+PGK_WTHIN_SW128=1 timeout 300 python tools/tc_test.py wthin > $OUT/wthin_sw128_numerics.txt 2>&1; tail -12 $OUT/wthin_sw128_numerics.txt
+for sw in 0 1; do
+  PGK_WTHIN_SW128=$sw timeout 300 python tools/thin_bench.py 1 4 > $OUT/thin_bench_sw$sw.txt 2>&1; echo "-- PGK_WTHIN_SW128=$sw"; cat $OUT/thin_bench_sw$sw.txt
+done
 stamp "per-shape profiles c4 c3 c5 c2"
 for c in c4 c3 c5 c2; do
   timeout 300 python tools/shape_profile.py --config $c --steps 3 --warmup 2 --json $OUT/shapes_$c.json > $OUT/shapes_$c.txt 2>&1

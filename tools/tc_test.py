@@ -180,6 +180,7 @@ def main():
         ok &= wgrad_case(2, 64, 64, 256, 512, 3, 1)
         ok &= wgrad_case(1, 128, 128, 64, 64, 3, 3, ngroups=2)
     print('ALL OK' if ok else 'FAILURES')
+    sys.exit(0 if ok else 1)
 
 
 if __name__ == '__main__':
