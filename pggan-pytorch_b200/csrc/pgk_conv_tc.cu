@@ -428,7 +428,13 @@ struct WgradTcArgs {
     int RG;               // 64-row groups in K = KS*KS*Cin / 64
     long long tiles_per_group, tiles_total, tiles_per_cta;
     float* dwp;
+    int red4;             // flush with 16-byte vector reductions (PGK_WGRAD_RED4=1, experimental) instead of scalar ones
 };
+
+// four consecutive floats added to global memory in one reduction (sm_90+; the address must be 16-byte aligned)
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 template <int P>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -576,8 +582,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 float v[16];
                 tmem_ld16(trow + sl * a.NT + c, v);
                 if (k < K) {
+                    if (a.red4) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) atomicAdd(drow + c + j, v[j]);
+                        for (int j = 0; j < 16; j += 4) red_add_v4(drow + c + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) atomicAdd(drow + c + j, v[j]);
+                    }
                 }
             }
         }
@@ -807,6 +818,14 @@ extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long l
     a.tiles_per_cta = (a.tiles_total + split - 1) / split;
     split = (a.tiles_total + a.tiles_per_cta - 1) / a.tiles_per_cta;
     a.dwp = dwp;
+    {
+        static int red4 = -1;
+        if (red4 < 0) {
+            const char* e = getenv("PGK_WGRAD_RED4");
+            red4 = e ? atoi(e) != 0 : 0;
+        }
+        a.red4 = red4 && (((uintptr_t)dwp) & 15) == 0;
+    }
 
     CUtensorMap tmX, tmG;
     {

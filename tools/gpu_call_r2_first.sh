@@ -33,6 +33,8 @@ PGK_WTHIN_SW128=1 timeout 300 python tools/tc_test.py wthin > $OUT/wthin_sw128_n
 for sw in 0 1; do
   PGK_WTHIN_SW128=$sw timeout 300 python tools/thin_bench.py 1 4 > $OUT/thin_bench_sw$sw.txt 2>&1; echo "-- PGK_WTHIN_SW128=$sw"; cat $OUT/thin_bench_sw$sw.txt
 done
+stamp "experimental: 16-byte vector reductions in the wide weight gradient's flush (PGK_WGRAD_RED4=1): numerics"
+PGK_WGRAD_RED4=1 timeout 300 python tools/tc_test.py wgrad > $OUT/wgrad_red4_numerics.txt 2>&1; tail -9 $OUT/wgrad_red4_numerics.txt
 stamp "per-shape profiles c4 c3 c5 c2"
 for c in c4 c3 c5 c2; do
   timeout 300 python tools/shape_profile.py --config $c --steps 3 --warmup 2 --json $OUT/shapes_$c.json > $OUT/shapes_$c.txt 2>&1
@@ -44,6 +46,11 @@ for nt in 64 128; do
     PGK_CONV_NT=$nt timeout 300 python tools/shape_profile.py --config $c --steps 3 --warmup 2 --json $OUT/shapes_${c}_nt$nt.json > $OUT/shapes_${c}_nt$nt.txt 2>&1
     head -1 $OUT/shapes_${c}_nt$nt.txt
   done
+done
+stamp "A/B of the two experimental switches on the step (c4, c3)"
+for c in c4 c3; do
+  PGK_WGRAD_RED4=1 timeout 300 python tools/shape_profile.py --config $c --steps 3 --warmup 2 --json $OUT/shapes_${c}_red4.json > $OUT/shapes_${c}_red4.txt 2>&1; head -1 $OUT/shapes_${c}_red4.txt
+  PGK_WTHIN_SW128=1 timeout 300 python tools/shape_profile.py --config $c --steps 3 --warmup 2 --json $OUT/shapes_${c}_sw128.json > $OUT/shapes_${c}_sw128.txt 2>&1; head -1 $OUT/shapes_${c}_sw128.txt
 done
 stamp "GPU reference bar (PyTorch eager, fp32 and TF32)"
 timeout 900 python tests/dev/gpu_eager_bar.py c2 c3 c4 c5 --steps 3 --warmup 2 > $OUT/eager_bar.jsonl 2> $OUT/eager_bar.err
