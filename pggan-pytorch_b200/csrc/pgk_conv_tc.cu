@@ -428,7 +428,8 @@ struct WgradTcArgs {
     int RG;               // 64-row groups in K = KS*KS*Cin / 64
     long long tiles_per_group, tiles_total, tiles_per_cta;
     float* dwp;
-    int red4;             // flush with 16-byte vector reductions (PGK_WGRAD_RED4=1, experimental) instead of scalar ones
+    int red4;             // PGK_WGRAD_RED4=1 (experimental): flush with 16-byte vector reductions, or plain
+                          // read-add-write when the pixel range is not split, instead of scalar atomics
 };
 
 // four consecutive floats added to global memory in one reduction (sm_90+; the address must be 16-byte aligned)
@@ -583,8 +584,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 tmem_ld16(trow + sl * a.NT + c, v);
                 if (k < K) {
                     if (a.red4) {
+                        if (gridDim.z == 1) {
+                            // the pixel range is not split: this thread is the only writer of its row slice, so the
+                            // accumulation into dwp needs no atomics at all
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) red_add_v4(drow + c + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            for (int j = 0; j < 16; j += 4) {
+                                float4* p4 = reinterpret_cast<float4*>(drow + c + j);
+                                float4 o = *p4;
+                                o.x += v[j], o.y += v[j + 1], o.z += v[j + 2], o.w += v[j + 3];
+                                *p4 = o;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) red_add_v4(drow + c + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) atomicAdd(drow + c + j, v[j]);
