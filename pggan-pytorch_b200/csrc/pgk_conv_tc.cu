@@ -663,7 +663,20 @@ extern "C" int pgk_conv_tc(const void* x, int P, int Pr, long long x_ps, int N, 
     // spread them over more CTAs with narrower channel slices
     {
         const int pixel_tiles = a.tiles_x * a.tiles_y * tiles_n, sms = pgk_num_sms();
-        while (a.NT > 32 && pixel_tiles * (Cout / a.NT) < sms) a.NT >>= 1;
+        // PGK_CONV_WAVE=1 (experimental): stop halving while the tiles still fit ONE wave.  The default rule halves
+        // until there are at least `sms` tiles, which lands between one and two waves (e.g. 24 pixel blocks x 512
+        // channels: 192 tiles of 64 channels = two rounds of the persistent loop, where 96 tiles of 128 channels
+        // are one round of tiles that cost well under twice as much).
+        static int wave = -1;
+        if (wave < 0) {
+            const char* e = getenv("PGK_CONV_WAVE");
+            wave = e ? atoi(e) != 0 : 0;
+        }
+        if (wave) {
+            while (a.NT > 32 && pixel_tiles * (Cout / (a.NT >> 1)) <= sms) a.NT >>= 1;
+        } else {
+            while (a.NT > 32 && pixel_tiles * (Cout / a.NT) < sms) a.NT >>= 1;
+        }
     }
     a.ntiles_n = Cout / a.NT;
     a.total_tiles = a.tiles_x * a.tiles_y * tiles_n * a.ntiles_n;

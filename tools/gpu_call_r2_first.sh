@@ -47,9 +47,10 @@ for nt in 64 128; do
     head -1 $OUT/shapes_${c}_nt$nt.txt
   done
 done
-stamp "A/B of the two experimental switches on the step (c4, c3)"
+stamp "A/B of the experimental switches on the step (c4, c3)"
 for c in c4 c3; do
   PGK_WGRAD_RED4=1 timeout 300 python tools/shape_profile.py --config $c --steps 3 --warmup 2 --json $OUT/shapes_${c}_red4.json > $OUT/shapes_${c}_red4.txt 2>&1; head -1 $OUT/shapes_${c}_red4.txt
+  PGK_CONV_WAVE=1 timeout 300 python tools/shape_profile.py --config $c --steps 3 --warmup 2 --json $OUT/shapes_${c}_wave.json > $OUT/shapes_${c}_wave.txt 2>&1; head -1 $OUT/shapes_${c}_wave.txt
   PGK_WTHIN_SW128=1 timeout 300 python tools/shape_profile.py --config $c --steps 3 --warmup 2 --json $OUT/shapes_${c}_sw128.json > $OUT/shapes_${c}_sw128.txt 2>&1; head -1 $OUT/shapes_${c}_sw128.txt
 done
 stamp "GPU reference bar (PyTorch eager, fp32 and TF32)"
