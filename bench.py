@@ -212,6 +212,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--graphs', action='store_true', help='replay the losses as CUDA graphs (wgan_gp_loss.cuda_graphs)')
     ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch of the config')
+    ap.add_argument('--prefetch', action='store_true',
+                    help='e2e leg: look-ahead H2D copy of the next real batch (trainer.prefetch_reals; not yet verified on a GPU)')
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.batch:
@@ -339,6 +341,7 @@ def main():
 
     tr = pg.Trainer(D, G, pg.wgan_gp_D_loss, pg.wgan_gp_G_loss, opt_d, opt_g, None, next_real(), next_lat)
     tr.register_plugin(Grab())
+    tr.prefetch_reals = args.prefetch
     import heapq
     for q in tr.plugin_queues.values():
         heapq.heapify(q)
@@ -375,7 +378,8 @@ def main():
         'config': dict(workload, l2='no flush needed: activations written per step (%.1f GB peak allocated) >> 126 MB L2'
                        % (peak_mem / 1e9)),
         'e2e': {'value': n * world / (ms_e2e / 1e3 / args.steps), 'unit': 'images/sec', 'h2d_bytes_per_step': h2d,
-                'd2h_bytes_per_step': d2h, 'api': 'Trainer.train() with pinned host reals/latents'},
+                'd2h_bytes_per_step': d2h,
+                'api': 'Trainer.train() with pinned host reals/latents' + (', real batches copied one step ahead' if args.prefetch else '')},
         'gpu_launches': launches,
         'clocks': clocks,
         'roofline': roof,

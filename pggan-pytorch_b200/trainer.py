@@ -28,6 +28,15 @@ class Trainer(object):
             'tick_stat': {'val': self.cur_tick, 'log_epoch_fields': ['{val:5}'], 'log_name': 'tick'},
         }
         self.plugin_queues = {'iteration': [], 'epoch': [], 's': [], 'end': []}
+        # Opt-in ("pinned async H2D"): fetch the NEXT real batch and start its host-to-device copy on a
+        # copy stream as soon as this iteration's kernels are enqueued, so that the copy runs under the iteration's GPU
+        # work instead of in front of the next one (at depth 8 the 50 MB batch is ~1 ms of a 14 ms iteration).  Only
+        # the real images are fetched ahead -- the latents stay where the reference draws them (the order of numpy
+        # RNG draws is observable) -- and a batch fetched from an iterator that a plugin has since replaced
+        # (DepthManager on a depth change, plugins.py:65-77) is dropped.
+        self.prefetch_reals = False
+        self._ahead = None          # (iterator it came from, device tensor, copy-done event or None)
+        self._copy_stream = None
 
     # -- plugin bus (reference trainer.py:47-69): a heap of (next trigger time, registration order, plugin) ------
     def register_plugin(self, plugin):
@@ -65,12 +74,52 @@ class Trainer(object):
     def _to_device(t):
         return t.cuda(non_blocking=True)
 
+    def _copy_ahead(self, host):
+        """Start the host-to-device copy of `host` on the copy stream; returns (device tensor, event)."""
+        import torch
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+        with torch.cuda.stream(self._copy_stream):
+            dev = host.cuda(non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._copy_stream)
+        return dev, done
+
+    def _claim(self, dev, done):
+        """Make a tensor copied on the copy stream usable on the current stream."""
+        if done is not None:
+            import torch
+            cur = torch.cuda.current_stream()
+            cur.wait_event(done)
+            dev.record_stream(cur)
+        return dev
+
+    def _next_real(self):
+        ahead, self._ahead = self._ahead, None
+        if ahead is not None and ahead[0] is self.dataiter:
+            return self._claim(ahead[1], ahead[2])
+        return self._to_device(next(self.dataiter))      # the reference's own path (trainer.py:92)
+
+    def _fetch_ahead(self):
+        if not self.prefetch_reals:
+            return
+        it = self.dataiter
+        try:
+            host = next(it)
+        except StopIteration:       # the next train() call raises it, exactly where the reference would
+            return
+        if getattr(host, 'is_pinned', lambda: False)():
+            dev, done = self._copy_ahead(host)
+        else:
+            dev, done = self._to_device(host), None
+        self._ahead = (it, dev, done)
+
     def train(self):
         """One iteration (reference trainer.py:85-115)."""
         latents = self._to_device(self.random_latents_generator())
         d_losses = (0, 0, 0)
         for _ in range(self.D_training_repeats):
-            real = self._to_device(next(self.dataiter))
+            real = self._next_real()
             self.cur_nimg += real.size(0)
             d_losses = tuple(self.D_loss(self.D, self.G, real, latents))
             d_losses[0].backward()
@@ -83,5 +132,6 @@ class Trainer(object):
             g_losses = (g_losses,)
         g_losses[0].backward()
         self.optimizer_g.step()
+        self._fetch_ahead()         # before the plugins: their loss reads synchronise with the device
         self.iterations += 1
         self.call_plugins('iteration', self.iterations, *(g_losses + d_losses))

@@ -1,6 +1,8 @@
 """-m gpu: the CUDA path (through the C ABI) against the golden vectors produced by the reference and against
 the oracle on fresh seeded inputs.  Tolerance (SURVEY.md 8c / BASELINE.json north_star): per-tensor
 ||a-b||_2 / ||b||_2 <= 1e-3 in the fp32-faithful mode; bf16 mode tolerances are stated per test."""
+import os
+
 import pytest
 import torch
 
@@ -101,6 +103,35 @@ def test_two_trainer_iterations_golden(gpu):
             assert rel_err(upd, upd_ref) < 5e-2, k
         else:
             assert float(upd.norm()) == 0, k
+
+
+@pytest.mark.skipif(os.environ.get('PGK_TEST_EXPERIMENTAL') != '1',
+                    reason='opt-in path not yet run on a GPU (PGK_TEST_EXPERIMENTAL=1 enables it)')
+def test_prefetched_reals_give_the_same_parameters(gpu):
+    """trainer.prefetch_reals = True (look-ahead H2D copy of pinned real batches on a copy stream) must not change a
+    single bit of what two Trainer.train() iterations do."""
+    g = load_trainer()
+    pg = gpu['pg']
+    out = []
+    for prefetch in (False, True):
+        g2 = dict(g, pg=g['G0'], pd=g['D0'])
+        G, D = gpu['build_pair'](g2)
+        G.depth = D.depth = g['depth']
+        G.alpha = D.alpha = g['alpha']
+        opt_g = torch.optim.Adam(G.parameters(), 1e-3, betas=(0.0, 0.99))
+        opt_d = torch.optim.Adam(D.parameters(), 1e-3, betas=(0.0, 0.99))
+        lats = iter(list(g['latents']))
+        reals = [r.clone().pin_memory() for r in g['reals']]
+        t = pg.Trainer(D, G, pg.wgan_gp_D_loss, pg.wgan_gp_G_loss, opt_d, opt_g, None, iter(reals), lambda: next(lats))
+        t.prefetch_reals = prefetch
+        for it in range(2):
+            pg.wgan_gp_loss.mixing_factors_override = g['mixing'][it]
+            t.train()
+        pg.wgan_gp_loss.mixing_factors_override = None
+        torch.cuda.synchronize()
+        out.append({k: v.detach().clone() for k, v in list(D.state_dict().items()) + list(G.state_dict().items())})
+    for k in out[0]:
+        assert rel_err(out[1][k], out[0][k]) < 1e-5, k     # weight-gradient atomics: last bits are order dependent
 
 
 @pytest.mark.parametrize('depth,alpha,n,ch', [(3, 0.5, 4, 3), (3, 1.0, 3, 3), (2, 0.0, 5, 1)])

@@ -136,3 +136,45 @@ def test_deposit_scales_with_upstream_gradient():
     gs[p].copy_(torch.tensor([1.0, 2.0, 3.0, 4.0]))
     (pg.wgan_gp_loss._deposit(torch.tensor(1.0), gs) * 0.5).backward()
     assert torch.equal(p.grad, torch.tensor([0.5, 1.0, 1.5, 2.0]))
+
+
+def _fake_trainer(batches, prefetch):
+    """A Trainer whose losses / optimizers are stubs and whose device transfer is the identity (host logic only)."""
+    seen = []
+
+    class Opt(object):
+        def step(self):
+            pass
+
+    def d_loss(D, G, real, lat):
+        seen.append(int(real[0]))
+        return (torch.zeros((), requires_grad=True) * 1.0, torch.zeros(1), torch.zeros(1))
+
+    def g_loss(G, D, lat):
+        return torch.zeros((), requires_grad=True) * 1.0
+
+    t = pg.Trainer(None, None, d_loss, g_loss, Opt(), Opt(), None, iter(batches), lambda: torch.zeros(2, 4))
+    t._to_device = lambda x: x
+    t.prefetch_reals = prefetch
+    return t, seen
+
+
+def test_real_batch_prefetch_keeps_the_reference_order_and_drops_stale_batches():
+    """Opt-in look-ahead of the real batch (trainer.prefetch_reals): same batches in the same order, a batch fetched
+    from an iterator that a plugin has replaced is dropped, StopIteration surfaces in the same train() call."""
+    mk = lambda lo, hi: [torch.full((3,), float(i)) for i in range(lo, hi)]
+    for prefetch in (False, True):
+        t, seen = _fake_trainer(mk(0, 4), prefetch)
+        t.train(), t.train()
+        assert seen == [0, 1] and t.cur_nimg == 6
+        # a plugin swaps the loader between iterations (DepthManager on a depth change, plugins.py:65-77)
+        t.dataiter = iter(mk(100, 102))
+        t.train(), t.train()
+        assert seen == [0, 1, 100, 101]
+        with pytest.raises(StopIteration):      # the new iterator is exhausted: raised by THIS call, as in the reference
+            t.train()
+        assert t.cur_nimg == 12 and t.iterations == 4
+    # the look-ahead batch really is fetched before the plugins run (its copy has to be in flight under the step)
+    t, seen = _fake_trainer(mk(0, 3), True)
+    t.train()
+    assert t._ahead is not None and int(t._ahead[1][0]) == 1

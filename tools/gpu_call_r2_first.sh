@@ -53,6 +53,20 @@ for c in c4 c3; do
   PGK_CONV_WAVE=1 timeout 300 python tools/shape_profile.py --config $c --steps 3 --warmup 2 --json $OUT/shapes_${c}_wave.json > $OUT/shapes_${c}_wave.txt 2>&1; head -1 $OUT/shapes_${c}_wave.txt
   PGK_WTHIN_SW128=1 timeout 300 python tools/shape_profile.py --config $c --steps 3 --warmup 2 --json $OUT/shapes_${c}_sw128.json > $OUT/shapes_${c}_sw128.txt 2>&1; head -1 $OUT/shapes_${c}_sw128.txt
 done
+stamp "experimental: look-ahead H2D of the real batch (trainer.prefetch_reals): test, then e2e A/B on c4 and c2"
+PGK_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -k prefetched > $OUT/prefetch_test.log 2>&1; tail -2 $OUT/prefetch_test.log
+for c in c4 c2; do
+  for f in "" "--prefetch"; do
+    timeout 300 python bench.py --config $c --steps 8 --warmup 3 --no-cpu-baseline $f > $OUT/bench_${c}_e2e$f.json 2> $OUT/bench_${c}_e2e$f.err
+    python - "$OUT/bench_${c}_e2e$f.json" "$c $f" <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(' %-14s value %.1f  e2e %.1f img/s' % (sys.argv[2], d['value'], d['e2e']['value']))
+except Exception as e: print(' failed', e)
+PY
+  done
+done
 stamp "GPU reference bar (PyTorch eager, fp32 and TF32)"
 timeout 900 python tests/dev/gpu_eager_bar.py c2 c3 c4 c5 --steps 3 --warmup 2 > $OUT/eager_bar.jsonl 2> $OUT/eager_bar.err
 cat $OUT/eager_bar.jsonl
