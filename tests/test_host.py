@@ -178,3 +178,12 @@ def test_real_batch_prefetch_keeps_the_reference_order_and_drops_stale_batches()
     t, seen = _fake_trainer(mk(0, 3), True)
     t.train()
     assert t._ahead is not None and int(t._ahead[1][0]) == 1
+
+
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md's table maps every function of include/pgk.h to the reference lines it replaces."""
+    hdr = re.sub(r'/\*.*?\*/', '', open(os.path.join(ROOT, 'include', 'pgk.h')).read(), flags=re.S)
+    declared = set(re.findall(r'\b(pgk_[a-z0-9_]+)\s*\(', hdr))
+    doc = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    missing = sorted(d for d in declared if d not in doc and not d.startswith('pgk_prof_'))
+    assert not missing, missing
