@@ -116,6 +116,28 @@ int pgk_conv(const void* x, int P, int Pr, long long x_ps, int N, int H, int W, 
              const float* pos_s, int act, const void* mask_ref, long long mask_ps, float out_scale, void* out,
              long long out_ps, float* pn_r, pgk_stream_t stream);
 
+/* ---- forward convolution on IEEE-half operand planes (experimental; fp32-faithful modes only) ----------------------
+ * The fp32-faithful mode pays six bf16 products per forward FLOP (three planes, i + j <= 2) because two bf16 planes
+ * (16 bits) flip too many LeakyReLU units.  Two fp16 planes carry 22 bits, so the three products hi*hi, hi*lo, lo*hi
+ * do the same job at half the tensor work (tests/dev/precision_model.py: gradient error 5e-7 against 4e-3 for two
+ * bf16 planes, on the same three products).  Only the OPERANDS of forward convolutions change format; everything
+ * stored stays bf16 planes:
+ *   pgk_cvt_fp16x2      dst = {half(v), half(v - hi)} of v = sum of the P bf16 planes of src (count elements per plane)
+ *   pgk_pack_operand_fp16  like pgk_pack_operand, P <= 2 half planes of w * 2^PGK_FP16_WSHIFT (the low plane of the
+ *                       small equalised-LR weights would otherwise fall into the fp16 subnormals)
+ *   pgk_conv_fp16       pgk_conv for a forward pass (no mask, out_scale 1, no upsample) reading xh / wth as produced by
+ *                       the two calls above and writing P (2 or 3) bf16 planes; shapes of the wide tensor-core kernel
+ *                       only (error otherwise -- the caller keeps pgk_conv for the rest).  E(v) as in pgk_conv. */
+#define PGK_FP16_WSHIFT 6
+int pgk_cvt_fp16x2(const void* src, long long src_ps, int P, long long count, void* dst, long long dst_ps,
+                   pgk_stream_t stream);
+int pgk_pack_operand_fp16(const float* w, int K, int Nn, void* out, long long out_ps, int P, pgk_stream_t stream);
+int pgk_conv_fp16(const void* xh, long long xh_ps, int N, int H, int W, int Cin, int Cout, int KS, const void* wth,
+                  long long wth_ps, const float* bias, const float* posT, const float* pos_s, int act, void* out, int P,
+                  long long out_ps, pgk_stream_t stream);
+/* 1 iff pgk_conv would run this shape on the wide tensor-core kernel (what pgk_conv_fp16 accepts) */
+int pgk_conv_tc_supported(int N, int H, int W, int Cin, int Cout, int KS, int ups);
+
 /* ---- weight gradient (cuDNN convolution_backward, weight part) --------------------------
  * dwp[tap*Cin+ci][co] += sum over the listed sample groups of X[..., ci] (shifted by tap) * g[..., co].
  * Groups: ngroups (<= 4) groups of group_n samples; group i reads x samples starting at xoff[i] and g samples

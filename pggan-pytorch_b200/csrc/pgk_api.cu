@@ -20,7 +20,7 @@ extern "C" int pgk_conv_tc_supported(int N, int H, int W, int Cin, int Cout, int
 extern "C" int pgk_conv_tc(const void* x, int P, int Pr, long long x_ps, int N, int H, int W, int Cin, int Cout, int KS,
                            const void* wt, long long wt_ps, const float* bias, const float* posT, const float* pos_s,
                            int act, const void* mask_ref, long long mask_ps, float out_scale, void* out,
-                           long long out_ps, pgk_stream_t stream);
+                           long long out_ps, pgk_stream_t stream, int fp16_x, int fp16_w, float acc_scale);
 extern "C" int pgk_wgrad_tc_supported(int H, int W, int Cin, int Cout, int KS, int ups, int ngroups, int group_n);
 extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W,
                             int Cin, int Cout, int KS, int ngroups, int group_n, const int* xoff, const int* goff,
@@ -141,7 +141,7 @@ extern "C" int pgk_conv(const void* x, int P, int Pr, long long x_ps, int N, int
     } else if (wt && tc_enabled() && pgk_conv_tc_supported(N, H, W, Cin, Cout, KS, ups)) {
         ProfScope prof(PGK_PROF_CONV, flops, bytes, stream, Pr);
         rc = pgk_conv_tc(x, P, Pr, x_ps, N, H, W, Cin, Cout, KS, wt, wt_ps, bias, posT, pos_s, act, mask_ref, mask_ps,
-                         out_scale, out, out_ps, stream);
+                         out_scale, out, out_ps, stream, 0, 0, 1.0f);
     } else {
         PGK_REQUIRE(wf != nullptr, "pgk_conv: this shape runs on the CUDA-core kernel, which needs the fp32 operand wf");
         ProfScope prof(PGK_PROF_CONV_SIMT, flops, bytes, stream);
@@ -151,6 +151,23 @@ extern "C" int pgk_conv(const void* x, int P, int Pr, long long x_ps, int N, int
     if (rc || !pn_r || pn_done) return rc;
     // kernels whose tile does not hold every channel of a pixel: the pixel norm as a second pass, in place
     return pgk_pixelnorm(out, out_ps, P, (long long)N * H * W, Cout, out, out_ps, pn_r, stream);
+}
+
+// forward convolution on IEEE-half operand planes (see include/pgk.h): the wide tensor-core kernel with fp16 A and B
+// formats, three products (hi*hi, hi*lo, lo*hi) into one accumulator, scaled back by 2^-PGK_FP16_WSHIFT
+extern "C" int pgk_conv_fp16(const void* xh, long long xh_ps, int N, int H, int W, int Cin, int Cout, int KS,
+                             const void* wth, long long wth_ps, const float* bias, const float* posT,
+                             const float* pos_s, int act, void* out, int P, long long out_ps, pgk_stream_t stream) {
+    PGK_REQUIRE(P >= 2 && P <= 3, "pgk_conv_fp16: out has 2 or 3 bf16 planes (the fp32-faithful modes)");
+    PGK_REQUIRE(xh && wth && out, "pgk_conv_fp16: null operand");
+    PGK_REQUIRE(tc_enabled() && pgk_conv_tc_supported(N, H, W, Cin, Cout, KS, 0),
+                "pgk_conv_fp16: only shapes of the wide tensor-core kernel (Cin %% 64 == 0, Cout %% 16 == 0, power-of-two H, W)");
+    const double flops = 2.0 * N * H * W * (double)Cout * KS * KS * Cin;
+    const double bytes = 2.0 * N * H * W * ((double)Cin * 2 + (double)Cout * P);
+    ProfScope prof(PGK_PROF_CONV, flops, bytes, stream, 2);
+    // the kernel reads Pr = 2 planes of x and wt (its tensor maps are declared P >= 2 planes deep) and writes P planes
+    return pgk_conv_tc(xh, P, 2, xh_ps, N, H, W, Cin, Cout, KS, wth, wth_ps, bias, posT, pos_s, act, nullptr, 0, 1.0f,
+                       out, out_ps, stream, 1, 1, 1.0f / (float)(1 << PGK_FP16_WSHIFT));
 }
 
 extern "C" int pgk_wgrad(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W,

@@ -17,6 +17,8 @@
 // a stage back to the producer and, after the last k-step, hands the accumulator to the epilogue.
 #include <stdlib.h>
 
+#include <cuda_fp16.h>
+
 #include "pgk_tc.cuh"
 
 using namespace tc;
@@ -104,6 +106,8 @@ struct ConvTcArgs {
     Planes mask;
     float out_scale;
     Planes out;
+    int fp16_a, fp16_b;    // operand formats of this launch: 1 = IEEE half planes (pgk_conv_fp16), 0 = bf16 planes
+    float acc_scale;       // applied to the accumulator before the bias: 2^-PGK_FP16_WSHIFT with fp16 weights, else 1
 };
 
 // P (planes read), KSTEPS (= bkb / 32) and SPLIT (separate correction accumulator) are compile-time: the MMA-issue
@@ -209,7 +213,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp == 9) {
-        const uint32_t idesc = idesc_bf16(a.NT, 0, 0);
+        const uint32_t idesc = idesc_f16(a.NT, 0, 0, a.fp16_a, a.fp16_b);   // == idesc_bf16(NT, 0, 0) for bf16 planes
         // descriptor = constant high part | (address >> 4) in the low 14 bits: per MMA only an add
         const uint64_t dbase = smem_desc(0, 16, 8u * kBkb, KSTEPS == 4 ? 2u : 4u);
         constexpr uint32_t a16 = a_bytes >> 4;
@@ -341,6 +345,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             tmem_ld16(trow + a.NT + c0 + cc, w);
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] += w[j];
+                        }
+                        if (a.acc_scale != 1.f) {   // fp16 weight operands are packed times a power of two
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] *= a.acc_scale;
                         }
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
@@ -626,6 +634,29 @@ __global__ void pack_operand_kernel(const float* __restrict__ w, int K, int Nn, 
     }
 }
 
+// out[p][n][k] = IEEE-half plane p of w[k][n] * scale (scale = 2^PGK_FP16_WSHIFT keeps the low plane of the small
+// equalised-LR weights out of the fp16 subnormals; the conv scales its accumulator back)
+__global__ void pack_operand_h_kernel(const float* __restrict__ w, int K, int Nn, float scale, __half* out,
+                                      long long out_ps, int P) {
+    __shared__ float tile[32][33];
+    const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int k = k0 + i, n = n0 + threadIdx.x;
+        tile[i][threadIdx.x] = (k < K && n < Nn) ? w[(long long)k * Nn + n] * scale : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int n = n0 + i, k = k0 + threadIdx.x;
+        if (n < Nn && k < K) {
+            float v = tile[threadIdx.x][i];
+            for (int pl = 0; pl < P; ++pl) {
+                const __half h = __float2half_rn(v);
+                out[pl * out_ps + (long long)n * K + k] = h;
+                v -= __half2float(h);
+            }
+        }
+    }
+}
 
 }  // namespace
 
@@ -642,7 +673,7 @@ extern "C" int pgk_conv_tc_supported(int N, int H, int W, int Cin, int Cout, int
 extern "C" int pgk_conv_tc(const void* x, int P, int Pr, long long x_ps, int N, int H, int W, int Cin, int Cout, int KS,
                            const void* wt, long long wt_ps, const float* bias, const float* posT, const float* pos_s,
                            int act, const void* mask_ref, long long mask_ps, float out_scale, void* out,
-                           long long out_ps, pgk_stream_t stream) {
+                           long long out_ps, pgk_stream_t stream, int fp16_x, int fp16_w, float acc_scale) {
     PGK_REQUIRE(pgk_conv_tc_supported(N, H, W, Cin, Cout, KS, 0), "pgk_conv_tc: unsupported shape");
     PGK_REQUIRE(P >= 1 && P <= 3 && Pr >= 1 && Pr <= P, "pgk_conv_tc: need 1 <= Pr <= P <= 3");
     ConvTcArgs a;
@@ -705,6 +736,8 @@ extern "C" int pgk_conv_tc(const void* x, int P, int Pr, long long x_ps, int N, 
     a.mask = make_planes(mask_ref, mask_ps, P);
     a.out_scale = out_scale;
     a.out = make_planes(out, out_ps, P);
+    a.fp16_a = fp16_x ? 1 : 0, a.fp16_b = fp16_w ? 1 : 0;
+    a.acc_scale = acc_scale;
 
     CUtensorMap tmA, tmB;
     {
@@ -887,6 +920,16 @@ extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long l
     dim3 grid((unsigned)sgroups, (unsigned)(Cout / a.NT), (unsigned)split);
     kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmX, tmG, a);
     PGK_LAUNCH_CHECK("pgk_wgrad(tcgen05)");
+    return PGK_OK;
+}
+
+extern "C" int pgk_pack_operand_fp16(const float* w, int K, int Nn, void* out, long long out_ps, int P,
+                                     pgk_stream_t stream) {
+    PGK_REQUIRE(P >= 1 && P <= 2 && K > 0 && Nn > 0, "pgk_pack_operand_fp16: bad arguments");
+    dim3 grid((unsigned)((K + 31) / 32), (unsigned)((Nn + 31) / 32));
+    pack_operand_h_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(w, K, Nn, (float)(1 << PGK_FP16_WSHIFT),
+                                                                          (__half*)out, out_ps, P);
+    PGK_LAUNCH_CHECK("pgk_pack_operand_fp16");
     return PGK_OK;
 }
 

@@ -3,6 +3,8 @@
 // algebra.  All HBM-bound: 16-byte vector access on the channel-innermost planes, warp-shuffle reductions.
 #include <stdarg.h>
 
+#include <cuda_fp16.h>
+
 #include "pgk_common.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -1407,5 +1409,37 @@ extern "C" int pgk_unpool_img_add(const float* src, int N, int C, int H, int W, 
     unpool_img_add_kernel<<<grid_cap((total + 255) / 256), 256, 0, ST>>>(src, (long long)N * C, H, W, scale, accumulate,
                                                                          dst);
     PGK_LAUNCH_CHECK("pgk_unpool_img_add");
+    return PGK_OK;
+}
+
+// ---- fp16 two-plane copy of an activation (the forward operand of pgk_conv_fp16) ----------------------------------
+// dst planes {hi, lo} = {half(v), half(v - hi)} of v = the sum of the source's bf16 planes: 22 significand bits
+static __global__ void __launch_bounds__(256) cvt_fp16x2_kernel(Planes src, long long count8, __half* dst, long long dst_ps) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count8;
+         i += (long long)gridDim.x * blockDim.x) {
+        float v[8];
+        ld8(src, i * 8, v);
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);     // .x = low 16 bits = element 2j
+            const float2 b = __half22float2(h);
+            const __half2 l = __floats2half2_rn(v[2 * j] - b.x, v[2 * j + 1] - b.y);
+            hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+            lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        *reinterpret_cast<uint4*>(dst + i * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(dst + dst_ps + i * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+extern "C" int pgk_cvt_fp16x2(const void* src, long long src_ps, int P, long long count, void* dst, long long dst_ps,
+                              pgk_stream_t stream) {
+    PGK_REQUIRE(P >= 1 && P <= 3 && count > 0 && count % 8 == 0, "pgk_cvt_fp16x2: count must be a positive multiple of 8");
+    PGK_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0 && (dst_ps * 2) % 16 == 0 && (P == 1 || (src_ps * 2) % 16 == 0),
+                "pgk_cvt_fp16x2: 16-byte alignment");
+    cvt_fp16x2_kernel<<<grid_cap((count / 8 + 255) / 256), 256, 0, ST>>>(make_planes(src, src_ps, P), count / 8,
+                                                                         (__half*)dst, dst_ps);
+    PGK_LAUNCH_CHECK("pgk_cvt_fp16x2");
     return PGK_OK;
 }

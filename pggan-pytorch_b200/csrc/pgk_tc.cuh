@@ -200,6 +200,13 @@ __host__ __device__ inline uint32_t idesc_bf16(int n, int a_mn_major, int b_mn_m
            ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) |
            ((uint32_t)(128 >> 4) << 24);
 }
+// the same with the operand formats chosen per operand (kind::f16 takes fp16 and bf16 independently for A and B):
+// a_fp16 / b_fp16 = 1 -> that operand is IEEE half (format code 0) instead of bf16 (format code 1)
+__host__ __device__ inline uint32_t idesc_f16(int n, int a_mn_major, int b_mn_major, int a_fp16, int b_fp16) {
+    return (1u << 4) /* D = f32 */ | ((a_fp16 ? 0u : 1u) << 7) | ((b_fp16 ? 0u : 1u) << 10) |
+           ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(128 >> 4) << 24);
+}
 // shared-memory matrix descriptor; all byte quantities are encoded >> 4
 // layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B, 0 = none
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {

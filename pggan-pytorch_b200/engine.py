@@ -14,6 +14,7 @@ Notation used below (see DESIGN.md "the gradient-penalty double backward"):
   w-chain  the second-order term that enters the forward graph through MinibatchStddev (network.py:174-187).
 """
 import ctypes
+import os
 from types import SimpleNamespace
 
 import torch
@@ -25,6 +26,10 @@ BF16 = torch.bfloat16
 CAPTURE_EPOCH = 0    # > 0 while a CUDA graph is being captured: every weight re-layout must be recorded once
 GRAD_PLANES = 2   # planes carried by gradient tensors / read by the gradient chains (include/pgk.h, pgk_conv: Pr)
 W_CONV, W_GFIRST, W_DLAST = 0, 1, 2
+# Experimental (PGK_FWD_FP16=1, fp32-faithful mode only; include/pgk.h "forward convolution on IEEE-half operand
+# planes"): forward convolutions that run on the wide tensor-core kernel read a two-plane fp16 copy of their input and
+# an fp16 packing of their weights -- three products per FLOP instead of six.  Not yet run on a GPU: default off.
+FWD_FP16 = os.environ.get('PGK_FWD_FP16', '0') == '1'
 
 
 def _ints(vals):
@@ -99,7 +104,19 @@ def conv(x, w, cout, ks, out, ups=0, bias=None, posT=None, pos_s=None, act=0, ma
     fwd=True: a forward pass whose values decide LeakyReLU masks -- all planes are read.
     pn_r: fp32 (N*H*W) tensor -- apply the pixel norm after the activation and store its per-pixel factor there."""
     mp, mps = _mask(mask)
-    wf, wt = w
+    wf, wt = w[0], w[1]
+    if (FWD_FP16 and fwd and len(w) > 2 and w[2] is not None and x.P >= 2 and mask is None and not ups and scale == 1.0
+            and _lib.load().pgk_conv_tc_supported(out.N, out.H, out.W, x.C, cout, ks, 0)):
+        # fp16 two-plane copy of the input (one extra pass), then the conv on half operands
+        xh = torch.empty((2, x.N * x.per), dtype=torch.float16, device=x.t.device)
+        call('pgk_cvt_fp16x2', x.ptr, x.ps, x.P, x.N * x.per, xh.data_ptr(), xh.stride(0))
+        call('pgk_conv_fp16', xh.data_ptr(), xh.stride(0), out.N, out.H, out.W, x.C, cout, ks, w[2].data_ptr(),
+             w[2].stride(0), None if bias is None else bias.data_ptr(), None if posT is None else posT.data_ptr(),
+             None if pos_s is None else pos_s.data_ptr(), act, out.ptr, out.P, out.ps)
+        if pn_r is not None:
+            call('pgk_pixelnorm', out.ptr, out.ps, out.P, out.N * out.H * out.W, out.C, out.ptr, out.ps,
+                 pn_r.data_ptr())
+        return out
     call('pgk_conv', x.ptr, x.P, x.P if fwd else min(x.P, GRAD_PLANES), x.ps, out.N, out.H, out.W, x.C, cout, ks, ups, wf.data_ptr(), wt.data_ptr(),
          wt.stride(0), None if bias is None else bias.data_ptr(), None if posT is None else posT.data_ptr(),
          None if pos_s is None else pos_s.data_ptr(), act, mp, mps, scale, out.ptr, out.ps,
@@ -219,6 +236,11 @@ class ConvW(object):
             call('pgk_pack_thin', self.wf.data_ptr(), self.cin, self.cout, self.F[1].data_ptr(), self.F[1].stride(0), 3)
         else:
             call('pgk_pack_operand', self.wf.data_ptr(), kf, nf_, self.F[1].data_ptr(), self.F[1].stride(0), 3)
+        if FWD_FP16 and not thin_f:
+            # third element of the forward operand tuple: [2 planes][output channel][K] IEEE half, times 2^PGK_FP16_WSHIFT
+            if len(self.F) < 3 or self.F[2].device != dev:
+                self.F = (self.F[0], self.F[1], torch.empty((2, nf_, kf), dtype=torch.float16, device=dev))
+            call('pgk_pack_operand_fp16', self.wf.data_ptr(), kf, nf_, self.F[2].data_ptr(), self.F[2].stride(0), 2)
         if self.need_wb:
             if thin_b:
                 call('pgk_pack_thin', self.wb.data_ptr(), self.cout, self.cin, self.B[1].data_ptr(),

@@ -67,6 +67,19 @@ except Exception as e: print(' failed', e)
 PY
   done
 done
+stamp "experimental: fp16 two-plane forward operands (PGK_FWD_FP16=1): kernel numerics, the whole parity suite, bench c2 A/B"
+PGK_FWD_FP16=1 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_full_size.py -q -m gpu > $OUT/fwd_fp16_parity.log 2>&1; tail -5 $OUT/fwd_fp16_parity.log
+PGK_FWD_FP16=1 timeout 600 python bench.py --config c2 --steps 8 --warmup 3 --no-cpu-baseline > $OUT/bench_c2_fwd_fp16.json 2> $OUT/bench_c2_fwd_fp16.err
+python - $OUT/bench_c2_fwd_fp16.json <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    r=d['roofline']
+    print(' PGK_FWD_FP16=1: ms/step %.2f  img/s %.1f  e2e %.1f  clocks %s' % (d['ms_per_step'], d['value'], d['e2e']['value'], d['clocks']))
+    print('  tensor_pipe %s' % r['tensor_pipe'])
+    for k,v in r['families'].items(): print('   ',k,{a:round(b,3) for a,b in v.items()})
+except Exception as e: print(' failed', e)
+PY
 stamp "GPU reference bar (PyTorch eager, fp32 and TF32)"
 timeout 900 python tests/dev/gpu_eager_bar.py c2 c3 c4 c5 --steps 3 --warmup 2 > $OUT/eager_bar.jsonl 2> $OUT/eager_bar.err
 cat $OUT/eager_bar.jsonl
