@@ -37,6 +37,11 @@ def signature(name, a):
         by = 2.0 * N * H * W * (Cin * Pr / (4 if ups else 1) + Cout * P + (Cout if mask else 0))
         return ('conv', N, H, W, Cin, Cout, KS, Pr, 'mask' if mask else ('pn' if pn_r else ('act' if act else '-')),
                 'ups' if ups else ''), fl, by
+    if name == 'pgk_conv_fp16':
+        (xh, xh_ps, N, H, W, Cin, Cout, KS, wth, wth_ps, bias, posT, pos_s, act, out, P, out_ps) = a
+        fl = 2.0 * N * H * W * Cout * KS * KS * Cin
+        by = 2.0 * N * H * W * (Cin * 2 + Cout * P)
+        return ('conv', N, H, W, Cin, Cout, KS, 2, 'act' if act else '-', 'fp16'), fl, by
     (x, x_ps, g, g_ps, P, Pr, H, W, Cin, Cout, KS, ups, ngroups, group_n, xoff, goff, dwp, db, bmask) = a
     n = ngroups * group_n
     fl = 2.0 * n * H * W * Cout * KS * KS * Cin
@@ -96,7 +101,7 @@ def main():
     real_call = pg._lib.call
 
     def timed_call(name, *a):
-        if name not in ('pgk_conv', 'pgk_wgrad'):
+        if name not in ('pgk_conv', 'pgk_wgrad', 'pgk_conv_fp16'):
             return real_call(name, *a)
         sig, fl, by = signature(name, a)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
