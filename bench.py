@@ -134,7 +134,7 @@ def cpu_reference_leg(cfg, steps, warmup, budget_s=25.0):
     dt = (time.perf_counter() - t0) / k
     return dict(value=n / dt, unit='images/sec', cores=cores, kind='port',
                 sample='%d timed iteration(s) of batch %d at depth %d (%dx%d), alpha %g, fp32, torch CPU ops on %d threads'
-                       % (k, n, depth, r, r, alpha, cores)), dt, k, w
+                       % (k, n, depth, r, r, alpha, cores)), dt, k, w + 1     # the probe step is an untimed warm-up too
 
 
 FAMILIES = {0: 'conv_tc_kernel (tcgen05 implicit-GEMM conv: forward + data gradient)',

@@ -685,8 +685,10 @@ extern "C" int pgk_conv_tc(const void* x, int P, int Pr, long long x_ps, int N, 
     a.tiles_x = W / TW, a.tiles_y = H / TH;
     const int tiles_n = (N + a.TN - 1) / a.TN;
     // Full-precision passes (three planes read) keep the plane0 x plane0 products in their own accumulator; with two
-    // accumulator buffers in the 512 TMEM columns that allows 128 channels per tile, otherwise 256.
-    a.split_acc = Pr == 3 ? 1 : 0;
+    // accumulator buffers in the 512 TMEM columns that allows 128 channels per tile, otherwise 256.  The fp16 forward
+    // pass (pgk_conv_fp16: two half planes, 22 bits) is a full-precision pass too: its hi x hi products get the same
+    // treatment, or three times as many truncating accumulator adds would land on the main sum.
+    a.split_acc = (Pr == 3 || (Pr == 2 && fp16_x && fp16_w)) ? 1 : 0;
     int nt_max = a.split_acc ? 128 : 256;
     if (const char* e = getenv("PGK_CONV_NT")) nt_max = atoi(e) < nt_max ? atoi(e) : nt_max;   // tuning knob
     a.NT = Cout < nt_max ? Cout : nt_max;
@@ -783,6 +785,7 @@ extern "C" int pgk_conv_tc(const void* x, int P, int Pr, long long x_ps, int N, 
     if (Pr == P_ && ks == K_ && a.split_acc == S_) kern = conv_tc_kernel<P_, K_, S_>;
     PGK_CONV_CASE(1, 4, 0) PGK_CONV_CASE(1, 2, 0)
     PGK_CONV_CASE(2, 4, 0) PGK_CONV_CASE(2, 2, 0)
+    PGK_CONV_CASE(2, 4, 1) PGK_CONV_CASE(2, 2, 1)
     PGK_CONV_CASE(3, 4, 1) PGK_CONV_CASE(3, 2, 1)
 #undef PGK_CONV_CASE
     PGK_REQUIRE(kern != nullptr, "pgk_conv_tc: no kernel instance for Pr %d ksteps %d split %d", Pr, ks, a.split_acc);

@@ -68,6 +68,7 @@ PY
   done
 done
 stamp "experimental: fp16 two-plane forward operands (PGK_FWD_FP16=1): kernel numerics, the whole parity suite, bench c2 A/B"
+timeout 300 python tools/tc_test.py fp16 > $OUT/fwd_fp16_kernel.txt 2>&1; tail -10 $OUT/fwd_fp16_kernel.txt
 PGK_FWD_FP16=1 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_full_size.py -q -m gpu > $OUT/fwd_fp16_parity.log 2>&1; tail -5 $OUT/fwd_fp16_parity.log
 PGK_FWD_FP16=1 timeout 600 python bench.py --config c2 --steps 8 --warmup 3 --no-cpu-baseline > $OUT/bench_c2_fwd_fp16.json 2> $OUT/bench_c2_fwd_fp16.err
 python - $OUT/bench_c2_fwd_fp16.json <<'PY'

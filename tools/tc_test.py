@@ -1,5 +1,5 @@
 """Development aid (GPU box): tensor-core kernels vs the CUDA-core kernels of the same library on random operands.
-   python tools/tc_test.py [conv|wgrad|all]"""
+   python tools/tc_test.py [conv|fp16|thin|wthin|wgrad|all]"""
 import os
 import sys
 import time
@@ -64,6 +64,52 @@ def conv_case(N, H, W, Cin, Cout, KS, P, act=1, mask=False, bias=True, scale=1.0
     flag = 'ok ' if e_tc < tol else 'BAD'
     print('%s conv N%d %dx%d %d->%d k%d P%d act%d mask%d pos%d: tc %.2e simt %.2e' % (flag, N, H, W, Cin, Cout, KS, P, act, mask, pos, e_tc, e_simt))
     return e_tc < tol
+
+
+def conv_fp16_case(N, H, W, Cin, Cout, KS, P=3, pos=False):
+    """pgk_cvt_fp16x2 + pgk_pack_operand_fp16 + pgk_conv_fp16 (forward conv on two IEEE-half operand planes, three
+    products) against an fp64 reference, next to the six-product bf16 path on the same operands: the pre-activation
+    error decides LeakyReLU masks, so it is printed before the activation (act=0) as max |err| / rms(ref) too."""
+    g = torch.Generator(device='cuda').manual_seed(N * 999 + H + Cin + Cout)
+    x = torch.randn(N, Cin, H, W, device='cuda', generator=g)
+    K = KS * KS * Cin
+    wf = (torch.randn(K, Cout, device='cuda', generator=g) * (2.0 / K) ** 0.5).contiguous()   # equalised-LR scale
+    wt = torch.empty(3, Cout, K, dtype=BF16, device='cuda')
+    call('pgk_pack_operand', wf.data_ptr(), K, Cout, wt.data_ptr(), wt.stride(0), 3)
+    wh = torch.empty(2, Cout, K, dtype=torch.float16, device='cuda')
+    call('pgk_pack_operand_fp16', wf.data_ptr(), K, Cout, wh.data_ptr(), wh.stride(0), 2)
+    b = torch.randn(Cout, device='cuda', generator=g)
+    posT = torch.randn(H * W * Cout, device='cuda', generator=g) if pos else None
+    pos_s = torch.randn(N, device='cuda', generator=g) if pos else None
+    xp = E.PT.from_float(x, P)
+    xh = torch.empty((2, xp.N * xp.per), dtype=torch.float16, device='cuda')
+    call('pgk_cvt_fp16x2', xp.ptr, xp.ps, xp.P, xp.N * xp.per, xh.data_ptr(), xh.stride(0))
+    torch.cuda.synchronize()
+    # the two half planes must reproduce the bf16 planes' value to 2^-22
+    xv = xp.float().permute(0, 2, 3, 1).reshape(-1).double()
+    e_cvt = float(((xh[0].double() + xh[1].double()) - xv).abs().max() / xv.abs().max())
+    w_back = (wh[0].double() + wh[1].double()) / float(1 << 6)
+    e_pack = float((w_back - wf.t().double()).abs().max() / wf.abs().max())
+    o16 = E.PT.empty(N, H, W, Cout, P, 'cuda')
+    o16.t.fill_(float('nan'))
+    call('pgk_conv_fp16', xh.data_ptr(), xh.stride(0), N, H, W, Cin, Cout, KS, wh.data_ptr(), wh.stride(0), b.data_ptr(),
+         None if posT is None else posT.data_ptr(), None if pos_s is None else pos_s.data_ptr(), 0, o16.ptr, P, o16.ps)
+    o6 = E.PT.empty(N, H, W, Cout, P, 'cuda')
+    o6.t.fill_(float('nan'))
+    E.conv(xp, (wf, wt), Cout, KS, o6, bias=b, posT=posT, pos_s=pos_s, act=0, fwd=True)
+    torch.cuda.synchronize()
+    w4 = wf.view(KS, KS, Cin, Cout).permute(3, 2, 0, 1).double()
+    ref = torch.nn.functional.conv2d(xp.float().double(), w4, b.double(), padding=KS // 2)
+    if pos:
+        ref = ref + pos_s.double().view(N, 1, 1, 1) * posT.double().view(H, W, Cout).permute(2, 0, 1)
+    rms = float(ref.pow(2).mean().sqrt())
+    e16, e6 = rel(o16.float(), ref), rel(o6.float(), ref)
+    m16 = float((o16.float().double() - ref).abs().max()) / rms
+    m6 = float((o6.float().double() - ref).abs().max()) / rms
+    ok = e16 < 2e-5 and e_cvt < 2.0 ** -21 and e_pack < 2.0 ** -21
+    print('%s conv_fp16 N%d %dx%d %d->%d k%d P%d pos%d: fp16x2 rel %.2e max/rms %.2e | bf16x3 rel %.2e max/rms %.2e | cvt %.1e pack %.1e'
+          % ('ok ' if ok else 'BAD', N, H, W, Cin, Cout, KS, P, pos, e16, m16, e6, m6, e_cvt, e_pack))
+    return ok
 
 
 def pixelnorm_case(N, H, W, Cin, Cout, P):
@@ -152,6 +198,15 @@ def main():
         ok &= conv_case(40, 16, 16, 512, 512, 3, 3)
         ok &= conv_case(40, 16, 16, 512, 512, 3, 1)
         ok &= conv_case(300, 4, 4, 64, 64, 3, 1)
+    if what in ('fp16', 'all'):
+        ok &= conv_fp16_case(2, 16, 16, 64, 64, 3)
+        ok &= conv_fp16_case(3, 4, 4, 512, 512, 3, pos=True)
+        ok &= conv_fp16_case(2, 32, 32, 256, 256, 3)
+        ok &= conv_fp16_case(2, 64, 64, 128, 256, 3)
+        ok &= conv_fp16_case(1, 128, 128, 64, 128, 3, P=2)
+        ok &= conv_fp16_case(9, 1, 1, 512, 8192, 1)
+        ok &= conv_fp16_case(5, 1, 1, 8192, 512, 1)
+        ok &= conv_fp16_case(40, 16, 16, 512, 512, 3)
     if what in ('thin', 'all'):
         ok &= conv_case(1, 128, 128, 16, 16, 3, 1)
         ok &= conv_case(2, 256, 256, 16, 16, 3, 3)
