@@ -29,6 +29,7 @@ struct ConvArgs {
 };
 
 __global__ void __launch_bounds__(256) conv_simt_kernel(ConvArgs a) {
+    pgk_pdl_enter();
     __shared__ __align__(16) float As[2][BK][BM + 4];
     __shared__ __align__(16) float Bs[2][BK][BN];
     const int t = threadIdx.x;
@@ -177,6 +178,7 @@ struct WgradArgs {
 };
 
 __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradArgs a) {
+    pgk_pdl_enter();
     __shared__ __align__(16) float As[2][WR][WK];
     __shared__ __align__(16) float Gs[2][WR][WN];
     const int t = threadIdx.x;
@@ -311,6 +313,7 @@ struct BiasArgs {
 };
 
 __global__ void __launch_bounds__(256) bias_grad_kernel(BiasArgs a) {
+    pgk_pdl_enter();
     __shared__ float red[256][9];
     const int nch = a.Cout >> 3;  // <= 256
     const int t = threadIdx.x;
@@ -388,7 +391,7 @@ extern "C" int pgk_conv_simt(const void* x, int P, long long x_ps, int N, int H,
     a.M = (int)M;
     a.K = KS * KS * Cin;
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((Cout + BN - 1) / BN));
-    conv_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    pgk_launch(conv_simt_kernel, grid, 256, 0, (cudaStream_t)stream, a);
     PGK_LAUNCH_CHECK("pgk_conv(simt)");
     return PGK_OK;
 }
@@ -424,7 +427,7 @@ extern "C" int pgk_wgrad_simt(const void* x, long long x_ps, const void* g, long
     int gz = (int)((a.R + per - 1) / per);
     a.r_per_cta = per;
     dim3 grid(gx, gy, gz);
-    wgrad_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    pgk_launch(wgrad_simt_kernel, grid, 256, 0, (cudaStream_t)stream, a);
     PGK_LAUNCH_CHECK("pgk_wgrad(simt)");
     return PGK_OK;
 }
@@ -457,7 +460,7 @@ extern "C" int pgk_bias_grad(const void* g, long long g_ps, int P, int HW, int C
     if (ctas > cap) ctas = cap;
     if (ctas < 1) ctas = 1;
     a.r_per_cta = (a.R + ctas - 1) / ctas;
-    bias_grad_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(a);
+    pgk_launch(bias_grad_kernel, dim3((unsigned)ctas), 256, 0, (cudaStream_t)stream, a);
     PGK_LAUNCH_CHECK("pgk_bias_grad");
     return PGK_OK;
 }

@@ -170,6 +170,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tptr - raw));
+    pgk_pdl_enter();   // everything above touched shared / tensor memory and the kernel parameters only
 
     auto tile_coords = [&](int t, int& x0, int& y0, int& n0, int& co0) {
         const int nt = t % a.ntiles_n;
@@ -490,6 +491,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     __syncthreads();
     fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tptr - raw));
+    pgk_pdl_enter();   // everything above touched shared / tensor memory and the kernel parameters only
 
     if (warp == 4) {
         {
@@ -621,6 +623,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
 // out[p][n][k] = plane p of w[k][n]
 __global__ void pack_operand_kernel(const float* __restrict__ w, int K, int Nn, Planes out) {
+    pgk_pdl_enter();
     __shared__ float tile[32][33];
     const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -638,6 +641,7 @@ __global__ void pack_operand_kernel(const float* __restrict__ w, int K, int Nn, 
 // equalised-LR weights out of the fp16 subnormals; the conv scales its accumulator back)
 __global__ void pack_operand_h_kernel(const float* __restrict__ w, int K, int Nn, float scale, __half* out,
                                       long long out_ps, int P) {
+    pgk_pdl_enter();
     __shared__ float tile[32][33];
     const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -798,7 +802,7 @@ extern "C" int pgk_conv_tc(const void* x, int P, int Pr, long long x_ps, int N, 
         }
         attr_done[Pr - 1][ks == 4][a.split_acc] = true;
     }
-    kern<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, tmO, tmM, a);
+    pgk_launch(kern, grid, kConvThreads, smem, (cudaStream_t)stream, tmA, tmB, tmO, tmM, a);
     PGK_LAUNCH_CHECK("pgk_conv(tcgen05)");
     return PGK_OK;
 }
@@ -921,7 +925,7 @@ extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long l
         attr_done[Pr - 1] = true;
     }
     dim3 grid((unsigned)sgroups, (unsigned)(Cout / a.NT), (unsigned)split);
-    kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmX, tmG, a);
+    pgk_launch(kern, grid, kThreads, smem, (cudaStream_t)stream, tmX, tmG, a);
     PGK_LAUNCH_CHECK("pgk_wgrad(tcgen05)");
     return PGK_OK;
 }
@@ -930,7 +934,7 @@ extern "C" int pgk_pack_operand_fp16(const float* w, int K, int Nn, void* out, l
                                      pgk_stream_t stream) {
     PGK_REQUIRE(P >= 1 && P <= 2 && K > 0 && Nn > 0, "pgk_pack_operand_fp16: bad arguments");
     dim3 grid((unsigned)((K + 31) / 32), (unsigned)((Nn + 31) / 32));
-    pack_operand_h_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(w, K, Nn, (float)(1 << PGK_FP16_WSHIFT),
+    pgk_launch(pack_operand_h_kernel, grid, dim3(32, 8), 0, (cudaStream_t)stream, w, K, Nn, (float)(1 << PGK_FP16_WSHIFT),
                                                                           (__half*)out, out_ps, P);
     PGK_LAUNCH_CHECK("pgk_pack_operand_fp16");
     return PGK_OK;
@@ -940,7 +944,7 @@ extern "C" int pgk_pack_operand(const float* w, int K, int Nn, void* out, long l
                                 pgk_stream_t stream) {
     PGK_REQUIRE(P >= 1 && P <= 3 && K > 0 && Nn > 0, "pgk_pack_operand: bad arguments");
     dim3 grid((unsigned)((K + 31) / 32), (unsigned)((Nn + 31) / 32));
-    pack_operand_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(w, K, Nn, make_planes(out, out_ps, P));
+    pgk_launch(pack_operand_kernel, grid, dim3(32, 8), 0, (cudaStream_t)stream, w, K, Nn, make_planes(out, out_ps, P));
     PGK_LAUNCH_CHECK("pgk_pack_operand");
     return PGK_OK;
 }

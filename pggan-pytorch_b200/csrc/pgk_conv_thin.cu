@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
     // ---- one-time setup: zero the row ring (padding pixels must be finite), stage weights and bias
     for (uint32_t o = threadIdx.x * 16u; o < kRing * row_bytes; o += kThinThreads * 16u)
         st_shared_v4(rows0 + o, make_uint4(0, 0, 0, 0));
+    pgk_pdl_enter();   // the weight operand and the bias are written by earlier launches of the stream
     {
         const uint4* src = reinterpret_cast<const uint4*>(a.wpack);
         const uint32_t n16 = P * wplane / 16u;
@@ -447,6 +448,7 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
 
 // out[p][step][khalf][n][e] for the K = 16 steps of conv_thin_kernel; w = fp32 [9*Cin][Cout] (pgk_prep_weight's wf / wb)
 __global__ void pack_thin_kernel(const float* __restrict__ w, int Cin, int Cout, int Npad, int steps, Planes out) {
+    pgk_pdl_enter();
     const int total = steps * 2 * Npad * 8;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int e = i & 7;
@@ -493,7 +495,7 @@ extern "C" int pgk_pack_thin(const float* w, int Cin, int Cout, void* out, long 
     const int npad = Cout < 16 ? 16 : Cout;
     const int steps = Cin == 8 ? 6 : 9 * (Cin / 16);
     const int total = steps * 2 * npad * 8;
-    pack_thin_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, Cin, Cout, npad, steps,
+    pgk_launch(pack_thin_kernel, dim3((total + 255) / 256), 256, 0, (cudaStream_t)stream, w, Cin, Cout, npad, steps,
                                                                            make_planes(out, out_ps, P));
     PGK_LAUNCH_CHECK("pgk_pack_thin");
     return PGK_OK;
@@ -597,7 +599,7 @@ static int launch_thin(const CUtensorMap& tmA, ThinArgs& a, cudaStream_t stream)
         }
         a.pair = pair && best_pl.ring >= 8 && best_rc % 2 == 0;
     }
-    kern<<<best_grid, kThinThreads, best_pl.smem, stream>>>(tmA, a);
+    pgk_launch(kern, best_grid, kThinThreads, best_pl.smem, stream, tmA, a);
     return PGK_OK;
 }
 

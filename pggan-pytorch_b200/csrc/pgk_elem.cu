@@ -67,6 +67,7 @@ __device__ __forceinline__ void weight_index(int kind, int cin, int cout, int ks
 
 __global__ void prep_weight_kernel(const float* __restrict__ w, float c, int kind, int cin, int cin_stride, int cout,
                                    int ks, float* __restrict__ wf, float* __restrict__ wb) {
+    pgk_pdl_enter();
     long long total = (long long)cout * cin * ks * ks;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
@@ -86,6 +87,7 @@ __global__ void prep_weight_kernel(const float* __restrict__ w, float c, int kin
 
 __global__ void unprep_grad_kernel(const float* __restrict__ dwp, float c, int kind, int cin, int cin_stride, int cout,
                                    int ks, float* __restrict__ dw, int accumulate) {
+    pgk_pdl_enter();
     long long total = (long long)cout * cin * ks * ks;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
@@ -105,6 +107,7 @@ __global__ void unprep_grad_kernel(const float* __restrict__ dwp, float c, int k
 
 __global__ void prep_posbias_kernel(const float* __restrict__ w, float c, int cin_stride, int ch, int Cout, int H,
                                     int W, float* __restrict__ posT) {
+    pgk_pdl_enter();
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= H * W * Cout) return;
     int co = idx % Cout, p = idx / Cout;
@@ -121,6 +124,7 @@ __global__ void prep_posbias_kernel(const float* __restrict__ w, float c, int ci
 // dw[co][ch][ky][kx] += c * sum_{n, (y,x) with (y+ky-1, x+kx-1) inside} coef[n] * ua[n,y,x,co]
 __global__ void posbias_wgrad_kernel(Planes ua, int N, int H, int W, int Cout, const float* __restrict__ coef, float c,
                                      int cin_stride, int ch, float* __restrict__ dw, int n_per_cta) {
+    pgk_pdl_enter();
     int co = blockIdx.x * blockDim.x + threadIdx.x;
     int tap = blockIdx.y;
     int ky = tap / 3, kx = tap % 3;
@@ -163,6 +167,7 @@ struct ExpandArgs {
 };
 
 __global__ void __launch_bounds__(256) rgb_expand_kernel(ExpandArgs a) {
+    pgk_pdl_enter();
     extern __shared__ float wsm[];  // [C][K]
     for (int i = threadIdx.x; i < a.C * a.K; i += blockDim.x) {
         int c = i / a.K, k = i - c * a.K;
@@ -238,6 +243,7 @@ struct ReduceArgs {
 };
 
 __global__ void __launch_bounds__(256) rgb_reduce_kernel(ReduceArgs a) {
+    pgk_pdl_enter();
     extern __shared__ float wsm[];  // source 0: [C][K0], then source 1: [C][K1]
     int off1 = a.C * a.s[0].K;
     for (int s = 0; s < a.nsrc; ++s) {
@@ -305,6 +311,7 @@ __global__ void __launch_bounds__(256) rgb_reduce_kernel(ReduceArgs a) {
 // constant per image channel.  (A lane reads its pixel's K channels 16 bytes at a time; the other half of every
 // sector it touches is the next chunk of the same pixel and comes from L1.)
 __global__ void __launch_bounds__(256) rgb_reduce_px_kernel(ReduceArgs a) {
+    pgk_pdl_enter();
     extern __shared__ __align__(16) float wsm[];  // source 0: [C][K0], source 1: [C][K1], then bsum[MAXC]
     const int off1 = a.C * a.s[0].K;
     const int offb = off1 + (a.nsrc > 1 ? a.C * a.s[1].K : 0);
@@ -378,6 +385,7 @@ struct RgbWgradArgs {
 };
 
 __global__ void __launch_bounds__(256) rgb_wgrad_kernel(RgbWgradArgs a) {
+    pgk_pdl_enter();
     __shared__ float red[256][MAXC * 8 + 8 + 1];
     __shared__ float isum[MAXC];
     const int nch = a.K >> 3;
@@ -498,6 +506,7 @@ __global__ void __launch_bounds__(256) rgb_wgrad_kernel(RgbWgradArgs a) {
 // ------------------------------------------------------------------------------------------
 __global__ void pool2_kernel(Planes src, int N, int H, int W, int C, float a, Planes other, int has_other, float b,
                              Planes out) {
+    pgk_pdl_enter();
     const int nch = C >> 3;
     const long long total = (long long)N * H * W * nch;
     const float sa = a;
@@ -530,6 +539,7 @@ __global__ void pool2_kernel(Planes src, int N, int H, int W, int C, float a, Pl
 
 __global__ void mask_mul_kernel(Planes src, int N, int H, int W, int C, int ups, float scale, Planes ref, int has_ref,
                                 Planes out) {
+    pgk_pdl_enter();
     const int nch = C >> 3;
     const long long total = (long long)N * H * W * nch;
     const int Hs = H >> ups, Ws = W >> ups;
@@ -560,6 +570,7 @@ __global__ void mask_mul_kernel(Planes src, int N, int H, int W, int C, int ups,
 }
 
 __global__ void axpby_kernel(Planes x, float a, Planes y, int has_y, float b, long long count, Planes out) {
+    pgk_pdl_enter();
     const long long total = count >> 3;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -580,6 +591,7 @@ __global__ void axpby_kernel(Planes x, float a, Planes y, int has_y, float b, lo
 
 // pixel norm: L lanes per pixel, each lane owns up to 4 chunks of 8 channels
 __global__ void __launch_bounds__(256) pixelnorm_kernel(Planes h, long long npix, int C, int L, Planes y, float* r) {
+    pgk_pdl_enter();
     const int nch = C >> 3;
     const int sub = threadIdx.x & (L - 1);
     const long long gstride = ((long long)gridDim.x * blockDim.x) / L;
@@ -615,6 +627,7 @@ __global__ void __launch_bounds__(256) pixelnorm_kernel(Planes h, long long npix
 
 __global__ void __launch_bounds__(256) pixelnorm_bwd_kernel(Planes dy, Planes y, const float* __restrict__ r,
                                                             long long npix, int C, int L, Planes da) {
+    pgk_pdl_enter();
     const int nch = C >> 3;
     const int sub = threadIdx.x & (L - 1);
     const long long gstride = ((long long)gridDim.x * blockDim.x) / L;
@@ -651,6 +664,7 @@ __global__ void __launch_bounds__(256) pixelnorm_bwd_kernel(Planes dy, Planes y,
 }
 
 __global__ void latent_norm_kernel(const float* __restrict__ z, int L, int normalize, Planes out) {
+    pgk_pdl_enter();
     __shared__ float sh[33];
     int n = blockIdx.x;
     float ss = 0.f;
@@ -668,6 +682,7 @@ __global__ void latent_norm_kernel(const float* __restrict__ z, int L, int norma
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) stddev_stats_kernel(Planes h, long long count, float* stats, float* svec,
                                                             int group_n) {
+    pgk_pdl_enter();
     __shared__ float sh[33];
     int g = blockIdx.x;
     long long base = (long long)g * count;
@@ -706,6 +721,7 @@ __global__ void __launch_bounds__(1024) stddev_stats_kernel(Planes h, long long 
 __global__ void __launch_bounds__(256) group_dot_pos_kernel(Planes ua, long long group_count, int HWC,
                                                             const float* __restrict__ posT, float* q,
                                                             int ctas_per_group) {
+    pgk_pdl_enter();
     __shared__ float sh[33];
     int g = blockIdx.x / ctas_per_group, part = blockIdx.x % ctas_per_group;
     long long base = (long long)g * group_count;
@@ -723,6 +739,7 @@ __global__ void __launch_bounds__(256) group_dot_pos_kernel(Planes ua, long long
 
 __global__ void stddev_bwd_kernel(Planes h, const float* __restrict__ stats, const float* __restrict__ q,
                                   long long group_count, int ngroups, Planes dh) {
+    pgk_pdl_enter();
     const long long total = (group_count * ngroups) >> 3;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -741,6 +758,7 @@ __global__ void stddev_bwd_kernel(Planes h, const float* __restrict__ stats, con
 // scratch[0] = sum v*(h-mean), scratch[1] = sum v   (scratch zeroed by the caller wrapper)
 __global__ void __launch_bounds__(256) stddev_bwd2_reduce_kernel(Planes h, Planes v, const float* __restrict__ stats,
                                                                  long long count, float* scratch) {
+    pgk_pdl_enter();
     __shared__ float sh[33];
     float mean = stats[0];
     float s0 = 0.f, s1 = 0.f;
@@ -765,6 +783,7 @@ __global__ void __launch_bounds__(256) stddev_bwd2_reduce_kernel(Planes h, Plane
 __global__ void stddev_bwd2_apply_kernel(Planes h, Planes v, const float* __restrict__ stats,
                                          const float* __restrict__ q, const float* __restrict__ scratch,
                                          long long count, float* ev, int ev_n, Planes wh) {
+    pgk_pdl_enter();
     const float mean = stats[0], sd = stats[1], inv_ns = stats[2];
     const float e = scratch[0] * inv_ns;
     const float vmean = scratch[1] / (float)count;
@@ -790,6 +809,7 @@ __global__ void stddev_bwd2_apply_kernel(Planes h, Planes v, const float* __rest
 // ------------------------------------------------------------------------------------------
 __global__ void linear_fwd_kernel(Planes h, int N, int K, const float* __restrict__ w, const float* __restrict__ b,
                                   float* scores) {
+    pgk_pdl_enter();
     int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (n >= N) return;
@@ -806,6 +826,7 @@ __global__ void linear_fwd_kernel(Planes h, int N, int K, const float* __restric
 
 __global__ void linear_bwd_kernel(Planes h, int N, int K, const float* __restrict__ w, const float* __restrict__ seed,
                                   const float* __restrict__ wseed, Planes ua, float* dw, float* db) {
+    pgk_pdl_enter();
     int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch < (K >> 3)) {
         float wv[8], acc[8];
@@ -839,6 +860,7 @@ __global__ void linear_bwd_kernel(Planes h, int N, int K, const float* __restric
 }
 
 __global__ void colsum_kernel(Planes v, int N, int K, float scale, float* dw) {
+    pgk_pdl_enter();
     int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= (K >> 3)) return;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -857,6 +879,7 @@ __global__ void colsum_kernel(Planes v, int N, int K, float scale, float* dw) {
 // ------------------------------------------------------------------------------------------
 __global__ void interpolate_kernel(const float* __restrict__ real, const float* __restrict__ fake,
                                    const float* __restrict__ eps, long long per, long long total, float* mixed) {
+    pgk_pdl_enter();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         float e = eps[i / per];
@@ -866,6 +889,7 @@ __global__ void interpolate_kernel(const float* __restrict__ real, const float* 
 
 __global__ void d_loss_seed_kernel(const float* __restrict__ scores, int N, float eps_drift, float* d_real_loss,
                                    float* d_fake_loss, float* seed, float* wseed) {
+    pgk_pdl_enter();
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     float dr = scores[n], df = scores[N + n];
@@ -881,6 +905,7 @@ __global__ void d_loss_seed_kernel(const float* __restrict__ scores, int N, floa
 }
 
 __global__ void mean_scale_kernel(const float* __restrict__ x, int n, float scale, float* out) {
+    pgk_pdl_enter();
     __shared__ float sh[33];
     float s = 0.f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
@@ -890,6 +915,7 @@ __global__ void mean_scale_kernel(const float* __restrict__ x, int n, float scal
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long per, int ctas_per_sample,
                                                     float* norms2) {
+    pgk_pdl_enter();
     __shared__ float sh[33];
     int n = blockIdx.x / ctas_per_sample, part = blockIdx.x % ctas_per_sample;
     const float* p = g + (long long)n * per;
@@ -902,6 +928,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 __global__ void gp_finalize_kernel(const float* __restrict__ g, int N, long long per, float lambda, float target,
                                    const float* __restrict__ d_real_loss, const float* __restrict__ d_fake_loss,
                                    const float* __restrict__ norms2, float* norms, float* gp, float* v0, float* cost) {
+    pgk_pdl_enter();
     const long long total = (long long)N * per;
     const float inv_n = 1.f / (float)N, t2 = target * target;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -925,12 +952,14 @@ __global__ void gp_finalize_kernel(const float* __restrict__ g, int N, long long
 }
 
 __global__ void fill_kernel(float* p, long long n, float v) {
+    pgk_pdl_enter();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         p[i] = v;
 }
 
 __global__ void pool_img_kernel(const float* __restrict__ img, long long planes, int H, int W, float scale,
                                 float* out) {
+    pgk_pdl_enter();
     const long long total = planes * H * W;  // H, W = output sizes
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -945,6 +974,7 @@ __global__ void pool_img_kernel(const float* __restrict__ img, long long planes,
 
 __global__ void unpool_img_add_kernel(const float* __restrict__ src, long long planes, int H, int W, float scale,
                                       int accumulate, float* dst) {
+    pgk_pdl_enter();
     const long long total = planes * H * W;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -980,7 +1010,7 @@ extern "C" int pgk_prep_weight(const float* w, float c, int kind, int cin, int c
     PGK_REQUIRE(kind == PGK_W_CONV ? (ks == 1 || ks == 3) : ks == 4, "pgk_prep_weight: bad ks %d for kind %d", ks, kind);
     PGK_REQUIRE(cin_stride >= cin, "pgk_prep_weight: cin_stride < cin");
     long long total = (long long)cout * cin * ks * ks;
-    prep_weight_kernel<<<grid_cap((total + 255) / 256), 256, 0, ST>>>(w, c, kind, cin, cin_stride, cout, ks, wf, wb);
+    pgk_launch(prep_weight_kernel, dim3(grid_cap((total + 255) / 256)), 256, 0, ST, w, c, kind, cin, cin_stride, cout, ks, wf, wb);
     PGK_LAUNCH_CHECK("pgk_prep_weight");
     return PGK_OK;
 }
@@ -989,7 +1019,7 @@ extern "C" int pgk_unprep_grad(const float* dwp, float c, int kind, int cin, int
                                float* dw, int accumulate, pgk_stream_t stream) {
     PGK_REQUIRE(kind >= 0 && kind <= 2, "pgk_unprep_grad: bad kind %d", kind);
     long long total = (long long)cout * cin * ks * ks;
-    unprep_grad_kernel<<<grid_cap((total + 255) / 256), 256, 0, ST>>>(dwp, c, kind, cin, cin_stride, cout, ks, dw,
+    pgk_launch(unprep_grad_kernel, dim3(grid_cap((total + 255) / 256)), 256, 0, ST, dwp, c, kind, cin, cin_stride, cout, ks, dw,
                                                                       accumulate);
     PGK_LAUNCH_CHECK("pgk_unprep_grad");
     return PGK_OK;
@@ -998,7 +1028,7 @@ extern "C" int pgk_unprep_grad(const float* dwp, float c, int kind, int cin, int
 extern "C" int pgk_prep_posbias(const float* w, float c, int cin_stride, int ch, int Cout, int H, int W, float* posT,
                                 pgk_stream_t stream) {
     int total = H * W * Cout;
-    prep_posbias_kernel<<<blocks_for(total, 256), 256, 0, ST>>>(w, c, cin_stride, ch, Cout, H, W, posT);
+    pgk_launch(prep_posbias_kernel, dim3(blocks_for(total, 256)), 256, 0, ST, w, c, cin_stride, ch, Cout, H, W, posT);
     PGK_LAUNCH_CHECK("pgk_prep_posbias");
     return PGK_OK;
 }
@@ -1007,7 +1037,7 @@ extern "C" int pgk_posbias_wgrad(const void* ua, long long ua_ps, int P, int N, 
                                  const float* coef, float c, int cin_stride, int ch, float* dw, pgk_stream_t stream) {
     int n_per = 16;
     dim3 grid(blocks_for(Cout, 128), 9, blocks_for(N, n_per));
-    posbias_wgrad_kernel<<<grid, 128, 0, ST>>>(make_planes(ua, ua_ps, P), N, H, W, Cout, coef, c, cin_stride, ch, dw,
+    pgk_launch(posbias_wgrad_kernel, grid, 128, 0, ST, make_planes(ua, ua_ps, P), N, H, W, Cout, coef, c, cin_stride, ch, dw,
                                                n_per);
     PGK_LAUNCH_CHECK("pgk_posbias_wgrad");
     return PGK_OK;
@@ -1019,7 +1049,7 @@ static int launch_expand(ExpandArgs& a, pgk_stream_t stream, const char* name) {
     size_t smem = sizeof(float) * a.C * a.K;
     PGK_REQUIRE(smem <= 48 * 1024, "%s: weight does not fit shared memory", name);
     long long total = (long long)a.N * a.H * a.W * (a.K >> 3);
-    rgb_expand_kernel<<<grid_cap((total + 255) / 256), 256, smem, ST>>>(a);
+    pgk_launch(rgb_expand_kernel, dim3(grid_cap((total + 255) / 256)), 256, smem, ST, a);
     PGK_LAUNCH_CHECK(name);
     return PGK_OK;
 }
@@ -1064,13 +1094,13 @@ static int launch_reduce(ReduceArgs& a, pgk_stream_t stream, const char* name) {
     // 8x its HBM time); per-pixel threads read the weights as broadcasts and store full 128-byte lines.
     if ((long long)a.N * a.H * a.W < (1ll << 31)) {
         const long long npix = (long long)a.N * a.H * a.W;
-        rgb_reduce_px_kernel<<<grid_cap((npix + 255) / 256), 256, smem + sizeof(float) * MAXC, ST>>>(a);
+        pgk_launch(rgb_reduce_px_kernel, dim3(grid_cap((npix + 255) / 256)), 256, smem + sizeof(float) * MAXC, ST, a);
         PGK_LAUNCH_CHECK(name);
         return PGK_OK;
     }
     a.L = lanes_for(maxch);
     long long threads = (long long)a.N * a.H * a.W * a.L;
-    rgb_reduce_kernel<<<grid_cap((threads + 255) / 256), 256, smem, ST>>>(a);
+    pgk_launch(rgb_reduce_kernel, dim3(grid_cap((threads + 255) / 256)), 256, smem, ST, a);
     PGK_LAUNCH_CHECK(name);
     return PGK_OK;
 }
@@ -1117,7 +1147,7 @@ extern "C" int pgk_rgb_wgrad(const float* img, int img_n0, const void* t, int P,
     if (ctas > cap) ctas = cap;
     if (ctas < 1) ctas = 1;
     a.r_per_cta = (a.R + ctas - 1) / ctas;
-    rgb_wgrad_kernel<<<(unsigned)ctas, 256, 0, ST>>>(a);
+    pgk_launch(rgb_wgrad_kernel, dim3((unsigned)ctas), 256, 0, ST, a);
     PGK_LAUNCH_CHECK("pgk_rgb_wgrad");
     return PGK_OK;
 }
@@ -1127,7 +1157,7 @@ extern "C" int pgk_pool2(const void* src, long long src_ps, int P, int N, int H,
                          pgk_stream_t stream) {
     PGK_REQUIRE(C % 8 == 0, "pgk_pool2: C must be a multiple of 8");
     long long total = (long long)N * H * W * (C >> 3);
-    pool2_kernel<<<grid_cap((total + 255) / 256), 256, 0, ST>>>(make_planes(src, src_ps, P), N, H, W, C,
+    pgk_launch(pool2_kernel, dim3(grid_cap((total + 255) / 256)), 256, 0, ST, make_planes(src, src_ps, P), N, H, W, C,
                                                                 avg ? 0.25f * a : a, make_planes(other, other_ps, P),
                                                                 other != nullptr, b, make_planes(out, out_ps, P));
     PGK_LAUNCH_CHECK("pgk_pool2");
@@ -1139,7 +1169,7 @@ extern "C" int pgk_mask_mul(const void* src, long long src_ps, int P, int N, int
     PGK_REQUIRE(C % 8 == 0, "pgk_mask_mul: C must be a multiple of 8");
     PGK_REQUIRE(!ups || (H % 2 == 0 && W % 2 == 0), "pgk_mask_mul: ups needs even H, W");
     long long total = (long long)N * H * W * (C >> 3);
-    mask_mul_kernel<<<grid_cap((total + 255) / 256), 256, 0, ST>>>(make_planes(src, src_ps, P), N, H, W, C, ups, scale,
+    pgk_launch(mask_mul_kernel, dim3(grid_cap((total + 255) / 256)), 256, 0, ST, make_planes(src, src_ps, P), N, H, W, C, ups, scale,
                                                                    make_planes(ref, ref_ps, P), ref != nullptr,
                                                                    make_planes(out, out_ps, P));
     PGK_LAUNCH_CHECK("pgk_mask_mul");
@@ -1149,7 +1179,7 @@ extern "C" int pgk_mask_mul(const void* src, long long src_ps, int P, int N, int
 extern "C" int pgk_axpby(const void* x, long long x_ps, float a, const void* y, long long y_ps, float b, int P,
                          long long count, void* out, long long out_ps, pgk_stream_t stream) {
     PGK_REQUIRE(count % 8 == 0, "pgk_axpby: count must be a multiple of 8");
-    axpby_kernel<<<grid_cap((count / 8 + 255) / 256), 256, 0, ST>>>(make_planes(x, x_ps, P), a, make_planes(y, y_ps, P),
+    pgk_launch(axpby_kernel, dim3(grid_cap((count / 8 + 255) / 256)), 256, 0, ST, make_planes(x, x_ps, P), a, make_planes(y, y_ps, P),
                                                                     y != nullptr, b, count, make_planes(out, out_ps, P));
     PGK_LAUNCH_CHECK("pgk_axpby");
     return PGK_OK;
@@ -1159,7 +1189,7 @@ extern "C" int pgk_pixelnorm(const void* h, long long h_ps, int P, long long npi
                              float* r, pgk_stream_t stream) {
     PGK_REQUIRE(C % 8 == 0 && C <= 1024, "pgk_pixelnorm: C must be a multiple of 8 and <= 1024");
     int L = lanes_for(C >> 3);
-    pixelnorm_kernel<<<grid_cap((npix * L + 255) / 256), 256, 0, ST>>>(make_planes(h, h_ps, P), npix, C, L,
+    pgk_launch(pixelnorm_kernel, dim3(grid_cap((npix * L + 255) / 256)), 256, 0, ST, make_planes(h, h_ps, P), npix, C, L,
                                                                        make_planes(y, y_ps, P), r);
     PGK_LAUNCH_CHECK("pgk_pixelnorm");
     return PGK_OK;
@@ -1169,7 +1199,7 @@ extern "C" int pgk_pixelnorm_bwd(const void* dy, long long dy_ps, const void* y,
                                  long long npix, int C, void* da, long long da_ps, pgk_stream_t stream) {
     PGK_REQUIRE(C % 8 == 0 && C <= 1024, "pgk_pixelnorm_bwd: C must be a multiple of 8 and <= 1024");
     int L = lanes_for(C >> 3);
-    pixelnorm_bwd_kernel<<<grid_cap((npix * L + 255) / 256), 256, 0, ST>>>(
+    pgk_launch(pixelnorm_bwd_kernel, dim3(grid_cap((npix * L + 255) / 256)), 256, 0, ST, 
         make_planes(dy, dy_ps, P), make_planes(y, y_ps, P), r, npix, C, L, make_planes(da, da_ps, P));
     PGK_LAUNCH_CHECK("pgk_pixelnorm_bwd");
     return PGK_OK;
@@ -1177,7 +1207,7 @@ extern "C" int pgk_pixelnorm_bwd(const void* dy, long long dy_ps, const void* y,
 
 extern "C" int pgk_latent_norm(const float* z, int N, int L, int normalize, void* out, int P, long long out_ps,
                                pgk_stream_t stream) {
-    latent_norm_kernel<<<N, 128, 0, ST>>>(z, L, normalize, make_planes(out, out_ps, P));
+    pgk_launch(latent_norm_kernel, N, 128, 0, ST, z, L, normalize, make_planes(out, out_ps, P));
     PGK_LAUNCH_CHECK("pgk_latent_norm");
     return PGK_OK;
 }
@@ -1185,7 +1215,7 @@ extern "C" int pgk_latent_norm(const float* z, int N, int L, int normalize, void
 extern "C" int pgk_stddev_stats(const void* h, long long h_ps, int P, int ngroups, long long group_count, float* stats,
                                 float* svec, int group_n, pgk_stream_t stream) {
     PGK_REQUIRE(group_count % 8 == 0, "pgk_stddev_stats: group size must be a multiple of 8");
-    stddev_stats_kernel<<<ngroups, 1024, 0, ST>>>(make_planes(h, h_ps, P), group_count, stats, svec, group_n);
+    pgk_launch(stddev_stats_kernel, ngroups, 1024, 0, ST, make_planes(h, h_ps, P), group_count, stats, svec, group_n);
     PGK_LAUNCH_CHECK("pgk_stddev_stats");
     return PGK_OK;
 }
@@ -1201,7 +1231,7 @@ extern "C" int pgk_group_dot_pos(const void* ua, long long ua_ps, int P, int ngr
     int per = (int)((count / 8 + 256 * 8 - 1) / (256 * 8));
     if (per < 1) per = 1;
     if (per > 64) per = 64;
-    group_dot_pos_kernel<<<ngroups * per, 256, 0, ST>>>(make_planes(ua, ua_ps, P), count, HW * C, posT, q, per);
+    pgk_launch(group_dot_pos_kernel, dim3(ngroups * per), 256, 0, ST, make_planes(ua, ua_ps, P), count, HW * C, posT, q, per);
     PGK_LAUNCH_CHECK("pgk_group_dot_pos");
     return PGK_OK;
 }
@@ -1209,7 +1239,7 @@ extern "C" int pgk_group_dot_pos(const void* ua, long long ua_ps, int P, int ngr
 extern "C" int pgk_stddev_bwd(const void* h, long long h_ps, const float* stats, const float* q, int P, int ngroups,
                               long long group_count, void* dh, long long dh_ps, pgk_stream_t stream) {
     long long total = group_count * ngroups / 8;
-    stddev_bwd_kernel<<<grid_cap((total + 255) / 256), 256, 0, ST>>>(make_planes(h, h_ps, P), stats, q, group_count,
+    pgk_launch(stddev_bwd_kernel, dim3(grid_cap((total + 255) / 256)), 256, 0, ST, make_planes(h, h_ps, P), stats, q, group_count,
                                                                      ngroups, make_planes(dh, dh_ps, P));
     PGK_LAUNCH_CHECK("pgk_stddev_bwd");
     return PGK_OK;
@@ -1226,10 +1256,10 @@ extern "C" int pgk_stddev_bwd2(const void* h, long long h_ps, const void* v, lon
     long long total = group_count / 8;
     unsigned nb = grid_cap((total + 255) / 256);
     if (nb > 128) nb = 128;
-    stddev_bwd2_reduce_kernel<<<nb, 256, 0, ST>>>(make_planes(h, h_ps, P), make_planes(v, v_ps, P), stats, group_count,
+    pgk_launch(stddev_bwd2_reduce_kernel, nb, 256, 0, ST, make_planes(h, h_ps, P), make_planes(v, v_ps, P), stats, group_count,
                                                   scratch);
     PGK_LAUNCH_CHECK("pgk_stddev_bwd2(reduce)");
-    stddev_bwd2_apply_kernel<<<grid_cap((total + 255) / 256), 256, 0, ST>>>(
+    pgk_launch(stddev_bwd2_apply_kernel, dim3(grid_cap((total + 255) / 256)), 256, 0, ST, 
         make_planes(h, h_ps, P), make_planes(v, v_ps, P), stats, q, scratch, group_count, ev, ev_n,
         make_planes(wh, wh_ps, P));
     PGK_LAUNCH_CHECK("pgk_stddev_bwd2(apply)");
@@ -1238,7 +1268,7 @@ extern "C" int pgk_stddev_bwd2(const void* h, long long h_ps, const void* v, lon
 
 extern "C" int pgk_linear_fwd(const void* h, long long h_ps, int P, int N, int K, const float* w, const float* b,
                               float* scores, pgk_stream_t stream) {
-    linear_fwd_kernel<<<blocks_for(N, 4), 128, 0, ST>>>(make_planes(h, h_ps, P), N, K, w, b, scores);
+    pgk_launch(linear_fwd_kernel, dim3(blocks_for(N, 4)), 128, 0, ST, make_planes(h, h_ps, P), N, K, w, b, scores);
     PGK_LAUNCH_CHECK("pgk_linear_fwd");
     return PGK_OK;
 }
@@ -1246,7 +1276,7 @@ extern "C" int pgk_linear_fwd(const void* h, long long h_ps, int P, int N, int K
 extern "C" int pgk_linear_bwd(const void* h, long long h_ps, int P, int N, int K, const float* w, const float* seed,
                               const float* wseed, void* ua, long long ua_ps, float* dw, float* db,
                               pgk_stream_t stream) {
-    linear_bwd_kernel<<<blocks_for(K / 8, 32), 32, 0, ST>>>(make_planes(h, h_ps, P), N, K, w, seed, wseed,
+    pgk_launch(linear_bwd_kernel, dim3(blocks_for(K / 8, 32)), 32, 0, ST, make_planes(h, h_ps, P), N, K, w, seed, wseed,
                                                             make_planes(ua, ua_ps, P), dw, db);
     PGK_LAUNCH_CHECK("pgk_linear_bwd");
     return PGK_OK;
@@ -1254,7 +1284,7 @@ extern "C" int pgk_linear_bwd(const void* h, long long h_ps, int P, int N, int K
 
 extern "C" int pgk_colsum(const void* v, long long v_ps, int P, int N, int K, float scale, float* dw,
                           pgk_stream_t stream) {
-    colsum_kernel<<<blocks_for(K / 8, 32), 32, 0, ST>>>(make_planes(v, v_ps, P), N, K, scale, dw);
+    pgk_launch(colsum_kernel, dim3(blocks_for(K / 8, 32)), 32, 0, ST, make_planes(v, v_ps, P), N, K, scale, dw);
     PGK_LAUNCH_CHECK("pgk_colsum");
     return PGK_OK;
 }
@@ -1262,14 +1292,14 @@ extern "C" int pgk_colsum(const void* v, long long v_ps, int P, int N, int K, fl
 extern "C" int pgk_interpolate(const float* real, const float* fake, const float* eps, int N, long long per,
                                float* mixed, pgk_stream_t stream) {
     long long total = (long long)N * per;
-    interpolate_kernel<<<grid_cap((total + 255) / 256), 256, 0, ST>>>(real, fake, eps, per, total, mixed);
+    pgk_launch(interpolate_kernel, dim3(grid_cap((total + 255) / 256)), 256, 0, ST, real, fake, eps, per, total, mixed);
     PGK_LAUNCH_CHECK("pgk_interpolate");
     return PGK_OK;
 }
 
 extern "C" int pgk_d_loss_seed(const float* scores, int N, float eps_drift, float* d_real_loss, float* d_fake_loss,
                                float* seed, float* wseed, pgk_stream_t stream) {
-    d_loss_seed_kernel<<<blocks_for(N, 128), 128, 0, ST>>>(scores, N, eps_drift, d_real_loss, d_fake_loss, seed,
+    pgk_launch(d_loss_seed_kernel, dim3(blocks_for(N, 128)), 128, 0, ST, scores, N, eps_drift, d_real_loss, d_fake_loss, seed,
                                                           wseed);
     PGK_LAUNCH_CHECK("pgk_d_loss_seed");
     return PGK_OK;
@@ -1277,7 +1307,7 @@ extern "C" int pgk_d_loss_seed(const float* scores, int N, float eps_drift, floa
 
 extern "C" int pgk_mean_scale(const float* x, int n, float scale, float* out, pgk_stream_t stream) {
     PGK_REQUIRE(n > 0, "pgk_mean_scale: empty input");
-    mean_scale_kernel<<<1, 256, 0, ST>>>(x, n, scale, out);
+    pgk_launch(mean_scale_kernel, 1, 256, 0, ST, x, n, scale, out);
     PGK_LAUNCH_CHECK("pgk_mean_scale");
     return PGK_OK;
 }
@@ -1295,17 +1325,17 @@ extern "C" int pgk_gp_penalty(const float* g, int N, long long per, float lambda
     int per_sample = (int)((per + 256 * 16 - 1) / (256 * 16));
     if (per_sample < 1) per_sample = 1;
     if (per_sample > 256) per_sample = 256;
-    sumsq_kernel<<<N * per_sample, 256, 0, ST>>>(g, per, per_sample, norms2);
+    pgk_launch(sumsq_kernel, dim3(N * per_sample), 256, 0, ST, g, per, per_sample, norms2);
     PGK_LAUNCH_CHECK("pgk_gp_penalty(sumsq)");
     long long total = (long long)N * per;
-    gp_finalize_kernel<<<grid_cap((total + 255) / 256), 256, 0, ST>>>(g, N, per, lambda, target, d_real_loss,
+    pgk_launch(gp_finalize_kernel, dim3(grid_cap((total + 255) / 256)), 256, 0, ST, g, N, per, lambda, target, d_real_loss,
                                                                       d_fake_loss, norms2, norms, gp, v0, cost);
     PGK_LAUNCH_CHECK("pgk_gp_penalty(finalize)");
     return PGK_OK;
 }
 
 extern "C" int pgk_fill(float* p, long long n, float v, pgk_stream_t stream) {
-    fill_kernel<<<grid_cap((n + 255) / 256), 256, 0, ST>>>(p, n, v);
+    pgk_launch(fill_kernel, dim3(grid_cap((n + 255) / 256)), 256, 0, ST, p, n, v);
     PGK_LAUNCH_CHECK("pgk_fill");
     return PGK_OK;
 }
@@ -1313,7 +1343,7 @@ extern "C" int pgk_fill(float* p, long long n, float v, pgk_stream_t stream) {
 extern "C" int pgk_pool_img(const float* img, int N, int C, int H, int W, int avg, float scale, float* out,
                             pgk_stream_t stream) {
     long long total = (long long)N * C * H * W;
-    pool_img_kernel<<<grid_cap((total + 255) / 256), 256, 0, ST>>>(img, (long long)N * C, H, W,
+    pgk_launch(pool_img_kernel, dim3(grid_cap((total + 255) / 256)), 256, 0, ST, img, (long long)N * C, H, W,
                                                                    avg ? 0.25f * scale : scale, out);
     PGK_LAUNCH_CHECK("pgk_pool_img");
     return PGK_OK;
@@ -1333,6 +1363,7 @@ __device__ __forceinline__ float radd(float a, float b) { return __fadd_rn(a, b)
 template <typename T, typename A>
 __global__ void real_prep_kernel(const T* __restrict__ src, long long planes, int H, int W, double one_minus_alpha_d,
                                  int fade, double min_in_d, double scale_d, double min_out_d, int rescale, float* out) {
+    pgk_pdl_enter();
     const long long total = planes * H * W;
     const A oma = (A)one_minus_alpha_d, min_in = (A)min_in_d, scale = (A)scale_d, min_out = (A)min_out_d;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -1363,10 +1394,10 @@ extern "C" int pgk_real_prep(const void* src, int src_is_u8, int N, int C, int H
     long long total = (long long)N * C * H * W;
     unsigned grid = grid_cap((total + 255) / 256);
     if (src_is_u8)
-        real_prep_kernel<unsigned char, double><<<grid, 256, 0, ST>>>((const unsigned char*)src, (long long)N * C, H, W,
+        pgk_launch(real_prep_kernel<unsigned char, double>, grid, 256, 0, ST, (const unsigned char*)src, (long long)N * C, H, W,
                                                               1.0 - alpha, fade, min_in, scale, min_out, rescale, out);
     else
-        real_prep_kernel<float, float><<<grid, 256, 0, ST>>>((const float*)src, (long long)N * C, H, W, 1.0 - alpha, fade, min_in,
+        pgk_launch(real_prep_kernel<float, float>, grid, 256, 0, ST, (const float*)src, (long long)N * C, H, W, 1.0 - alpha, fade, min_in,
                                                       scale, min_out, rescale, out);
     PGK_LAUNCH_CHECK("pgk_real_prep");
     return PGK_OK;
@@ -1376,6 +1407,7 @@ extern "C" int pgk_real_prep(const void* src, int src_is_u8, int N, int C, int H
 // One launch for every parameter that has a gradient.  table: n rows of 8 x 64-bit words
 //   {param ptr, grad ptr, exp_avg ptr, exp_avg_sq ptr, numel, step_size = lr/bc1 (float bits), 1/sqrt(bc2) (float bits), 0}
 __global__ void adam_multi_kernel(const unsigned long long* __restrict__ table, float beta1, float beta2, float eps) {
+    pgk_pdl_enter();
     const unsigned long long* e = table + 8ull * blockIdx.y;
     float* p = reinterpret_cast<float*>(e[0]);
     const float* g = reinterpret_cast<const float*>(e[1]);
@@ -1398,7 +1430,7 @@ extern "C" int pgk_adam_multi(const void* table, int ntensors, long long max_num
     long long bx = (max_numel + 1023) / 1024;   // 4 elements per thread at the largest tensor, grid-stride beyond
     if (bx > 2048) bx = 2048;
     dim3 grid((unsigned)bx, (unsigned)ntensors);
-    adam_multi_kernel<<<grid, 256, 0, ST>>>((const unsigned long long*)table, beta1, beta2, eps);
+    pgk_launch(adam_multi_kernel, grid, 256, 0, ST, (const unsigned long long*)table, beta1, beta2, eps);
     PGK_LAUNCH_CHECK("pgk_adam_multi");
     return PGK_OK;
 }
@@ -1406,7 +1438,7 @@ extern "C" int pgk_adam_multi(const void* table, int ntensors, long long max_num
 extern "C" int pgk_unpool_img_add(const float* src, int N, int C, int H, int W, float scale, int accumulate, float* dst,
                                   pgk_stream_t stream) {
     long long total = (long long)N * C * H * W;
-    unpool_img_add_kernel<<<grid_cap((total + 255) / 256), 256, 0, ST>>>(src, (long long)N * C, H, W, scale, accumulate,
+    pgk_launch(unpool_img_add_kernel, dim3(grid_cap((total + 255) / 256)), 256, 0, ST, src, (long long)N * C, H, W, scale, accumulate,
                                                                          dst);
     PGK_LAUNCH_CHECK("pgk_unpool_img_add");
     return PGK_OK;
@@ -1415,6 +1447,7 @@ extern "C" int pgk_unpool_img_add(const float* src, int N, int C, int H, int W, 
 // ---- fp16 two-plane copy of an activation (the forward operand of pgk_conv_fp16) ----------------------------------
 // dst planes {hi, lo} = {half(v), half(v - hi)} of v = the sum of the source's bf16 planes: 22 significand bits
 static __global__ void __launch_bounds__(256) cvt_fp16x2_kernel(Planes src, long long count8, __half* dst, long long dst_ps) {
+    pgk_pdl_enter();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count8;
          i += (long long)gridDim.x * blockDim.x) {
         float v[8];
@@ -1438,7 +1471,7 @@ extern "C" int pgk_cvt_fp16x2(const void* src, long long src_ps, int P, long lon
     PGK_REQUIRE(P >= 1 && P <= 3 && count > 0 && count % 8 == 0, "pgk_cvt_fp16x2: count must be a positive multiple of 8");
     PGK_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0 && (dst_ps * 2) % 16 == 0 && (P == 1 || (src_ps * 2) % 16 == 0),
                 "pgk_cvt_fp16x2: 16-byte alignment");
-    cvt_fp16x2_kernel<<<grid_cap((count / 8 + 255) / 256), 256, 0, ST>>>(make_planes(src, src_ps, P), count / 8,
+    pgk_launch(cvt_fp16x2_kernel, dim3(grid_cap((count / 8 + 255) / 256)), 256, 0, ST, make_planes(src, src_ps, P), count / 8,
                                                                          (__half*)dst, dst_ps);
     PGK_LAUNCH_CHECK("pgk_cvt_fp16x2");
     return PGK_OK;

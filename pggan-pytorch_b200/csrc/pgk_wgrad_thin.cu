@@ -133,6 +133,7 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     __syncthreads();
     fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tptr - raw));
+    pgk_pdl_enter();   // everything above touched shared / tensor memory and the kernel parameters only
 
     // busy polling by the two single-warp roles takes issue slots from the transposer warps of the same SM
     // sub-partitions; try_wait suspends instead
@@ -578,7 +579,7 @@ static int launch_wthin(const CUtensorMap& tmX, const CUtensorMap& tmG, WThinArg
     a.look = pl.raw == 8 ? 8 : pl.raw == 4 ? 4 : 1;
     int grid = pl.occ * pgk_num_sms();
     if (grid > a.total_units) grid = a.total_units;
-    kern<<<grid, kThreads, pl.smem, stream>>>(tmX, tmG, a);
+    pgk_launch(kern, grid, kThreads, pl.smem, stream, tmX, tmG, a);
     return PGK_OK;
 }
 

@@ -25,6 +25,22 @@ try:
     print('  dominant %s %s %.1f %s frac %.3f share %.2f tensor_pipe %s' % (r['kernel'].split(' ')[0], r['bound'], r['achieved'], r['unit'], r['frac'], r['share_of_step'], r['tensor_pipe']))
 except Exception as e: print(' failed', e)
 PY
+stamp "experimental: programmatic dependent launch (PGK_PDL=1): whole GPU suite, then step time A/B on c4 c3 c1 (with and without CUDA graphs)"
+PGK_PDL=1 timeout 1200 python -m pytest tests -x -q -m gpu > $OUT/pdl_pytest_gpu.log 2>&1; echo "rc=$?" >> $OUT/pdl_pytest_gpu.log; tail -3 $OUT/pdl_pytest_gpu.log
+for c in c4 c3 c1; do
+  for pdl in 0 1; do
+    for g in "" "--graphs"; do
+      PGK_PDL=$pdl timeout 300 python bench.py --config $c --steps 8 --warmup 3 --no-cpu-baseline $g > $OUT/bench_${c}_pdl${pdl}${g}.json 2> $OUT/bench_${c}_pdl${pdl}${g}.err
+      python - "$OUT/bench_${c}_pdl${pdl}${g}.json" "$c PGK_PDL=$pdl $g" <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(' %-24s ms/step %.2f  img/s %.1f  e2e %.1f' % (sys.argv[2], d['ms_per_step'], d['value'], d['e2e']['value']))
+except Exception as e: print(' failed', sys.argv[2], e)
+PY
+    done
+  done
+done
 stamp "hardware probe: swizzled row-shifted starts, cycles per MMA by layout / N / A-in-TMEM"
 (nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o /tmp/umma_probe tools/probes/umma_probe.cu && timeout 120 /tmp/umma_probe) > $OUT/umma_probe.txt 2>&1
 cat $OUT/umma_probe.txt
