@@ -26,6 +26,8 @@ try:
 except Exception as e: print(' failed', e)
 PY
 stamp "experimental: programmatic dependent launch (PGK_PDL=1): whole GPU suite, then step time A/B on c4 c3 c1 (with and without CUDA graphs)"
+# the default build compiles the PDL path out: rebuild with it (make PDL=1), A/B with the run-time switch, rebuild the default
+(make -C pggan-pytorch_b200/csrc clean && make -C pggan-pytorch_b200/csrc PDL=1 -j 16) > $OUT/pdl_build.log 2>&1; tail -1 $OUT/pdl_build.log
 PGK_PDL=1 timeout 1200 python -m pytest tests -x -q -m gpu > $OUT/pdl_pytest_gpu.log 2>&1; echo "rc=$?" >> $OUT/pdl_pytest_gpu.log; tail -3 $OUT/pdl_pytest_gpu.log
 for c in c4 c3 c1; do
   for pdl in 0 1; do
@@ -41,6 +43,7 @@ PY
     done
   done
 done
+(make -C pggan-pytorch_b200/csrc clean && make -C pggan-pytorch_b200/csrc -j 16) > $OUT/default_rebuild.log 2>&1; tail -1 $OUT/default_rebuild.log
 stamp "hardware probe: swizzled row-shifted starts, cycles per MMA by layout / N / A-in-TMEM"
 (nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o /tmp/umma_probe tools/probes/umma_probe.cu && timeout 120 /tmp/umma_probe) > $OUT/umma_probe.txt 2>&1
 cat $OUT/umma_probe.txt
