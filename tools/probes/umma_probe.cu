@@ -17,6 +17,15 @@
 //      thin weight gradient (one MMA per 16 pixels, N = 8..64: bound by exactly this) should write its transposed X
 //      rows to TMEM (tcgen05.st from the transposer warps) instead of shared memory.
 //
+//  (4) A FILLED BY tcgen05.cp.  The thin conv keeps image rows in shared memory as [pixel][8 channels] (16 bytes per
+//      pixel), and a tap's dx shift is a 16-byte shift of the start address.  tcgen05.cp .128x128b copies 128 rows x
+//      16 bytes -- exactly 128 pixels of one channel group, from any such start -- into four tensor-memory columns.
+//      Two neighbouring four-column slots are one K = 16 A operand, so an input row copied once per dx (3 copies of
+//      2 KB per channel group) serves the three output rows that use it, and the nine taps become MMAs whose A never
+//      touches the shared-memory port (8 cycles per MMA at N = 16 instead of 32+).  The probe checks the copy +
+//      MMA numerics for dx = 0..2 against the CPU (which also settles the ordering of tcgen05.cp -> tcgen05.mma issued
+//      by one thread) and times copy / MMA mixes per iteration.
+//
 // Build + run on the GPU box (nvcc is in the image):
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o /tmp/umma_probe tools/probes/umma_probe.cu && /tmp/umma_probe
 #include <cstdio>
@@ -59,6 +68,11 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                  "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// 128 rows x 16 bytes from shared memory (8-row core matrices of 128 contiguous bytes, SBO apart) -> 4 TMEM columns
+__device__ __forceinline__ void tmem_cp_128x128b(uint32_t taddr, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x128b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
 }
 
 __device__ __forceinline__ uint64_t make_desc(int layout, uint32_t tile_base, int r0, int kstep, int base_off_mode) {
@@ -162,6 +176,82 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const ProbeArgs a) {
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// ---- (4): pixel rows [256 pixels][8 channels] x 2 "image rows" in shared memory; slot j <- pixels dx .. dx+127 of row j
+struct CpArgs {
+    const bf16* A;   // [kRows][64]: row = pixel, k = 8 * j + c is channel c of image row j (only k < 16 is used)
+    const bf16* B;   // [kRows][64]: row = output channel n
+    float* D;
+    long long* cycles;
+    int N, dx, iters, ncp, nmma, variant;
+};
+
+__global__ void __launch_bounds__(128, 1) cp_probe_kernel(const CpArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t tR = base, tB = base + kTile, bar = base + 2 * kTile, tptr = bar + 16;
+    uint8_t* gen = smem_raw + (base - raw);
+    constexpr uint32_t kRowBuf = kRows * 16u;   // one image row: 256 pixels x 16 bytes
+    for (int i = threadIdx.x; i < kRows * 16; i += blockDim.x) {
+        const int p = i / 16, k = i % 16, j = k >> 3, c = k & 7;
+        *reinterpret_cast<bf16*>(gen + j * kRowBuf + p * 16 + c * 2) = a.A[p * kK + k];
+    }
+    for (int i = threadIdx.x; i < kRows * kK; i += blockDim.x) {
+        const int r = i / kK, k = i % kK;
+        *reinterpret_cast<bf16*>(gen + kTile + elem_off(SW128, r, k)) = a.B[i];
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tptr, 512);
+    fence_proxy_async();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tptr - raw));
+    const uint32_t idesc = idesc_bf16(a.N, 0, 0);
+    constexpr uint32_t kAcol = 448;   // A slots: 4 columns each, 16 slots
+    long long t0 = 0, t1 = 0;
+    if (warp == 0) {
+        // no swizzle, K-major: one 16-byte column, so LBO is unused; SBO = 128 bytes between 8-pixel groups
+        uint64_t rd[2];
+        // (variants 1, 2 only matter if variant 0 turns out wrong: other readings of the two offsets for this shape)
+        const uint32_t lbo = a.variant == 0 ? 16u : 128u, sbo = a.variant == 1 ? 16u : 128u;
+        for (int j = 0; j < 2; ++j) rd[j] = smem_desc(tR + j * kRowBuf + (uint32_t)a.dx * 16u, lbo, sbo, 0);
+        const uint64_t bd = make_desc(SW128, tB, 0, 0, 0);
+        __syncwarp();
+        t0 = clock64();
+        for (int it = 0; it < a.iters; ++it) {
+            if (elect_one()) {
+                for (int c = 0; c < a.ncp; ++c) tmem_cp_128x128b(tmem + kAcol + 4u * (c & 15), rd[c & 1]);
+                for (int m = 0; m < a.nmma; ++m)
+                    mma_bf16_ts(tmem, tmem + kAcol, bd, idesc, (it == 0 && m == 0) ? 0u : 1u);
+            }
+            __syncwarp();
+        }
+        if (elect_one()) mma_commit(bar);
+        __syncwarp();
+    }
+    mbar_wait(bar, 0);
+    fence_after();
+    if (warp == 0) {
+        t1 = clock64();
+        if (lane == 0) a.cycles[0] = t1 - t0;
+    }
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const int row = warp * 32 + lane;
+    for (int c = 0; c < a.N; c += 16) {
+        float v[16];
+        tmem_ld16(trow + c, v);
+        for (int j = 0; j < 16; ++j) a.D[row * 256 + c + j] = v[j];
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 #define CK(x)                                                                             \
     do {                                                                                  \
         cudaError_t e__ = (x);                                                            \
@@ -248,5 +338,39 @@ int main() {
                    e == 0.0 ? "yes" : "NO");
         }
     }
+
+    printf("== (4) A filled by tcgen05.cp.128x128b from [pixel][8 channel] rows (start shifted by dx pixels), K = 16 = two slots\n");
+    CK(cudaFuncSetAttribute(cp_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    auto run_cp = [&](int N, int dx, int iters, int ncp, int nmma, long long* cyc, int variant = 0) {
+        CpArgs a{dA, dB, dD, dC, N, dx, iters, ncp, nmma, variant};
+        CK(cudaMemset(dD, 0, sizeof(float) * 128 * 256));
+        cp_probe_kernel<<<1, 128, smem>>>(a);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(hD.data(), dD, sizeof(float) * 128 * 256, cudaMemcpyDeviceToHost));
+        if (cyc) CK(cudaMemcpy(cyc, dC, sizeof(long long), cudaMemcpyDeviceToHost));
+    };
+    for (int variant = 0; variant < 3; ++variant)
+    for (int dx = 0; dx <= 2; ++dx) {
+        run_cp(16, dx, 1, 2, 1, nullptr, variant);   // slots 0, 1 <- image rows 0, 1; one MMA over both
+        double worst = 0.0;
+        for (int m = 0; m < 128; ++m)
+            for (int n = 0; n < 16; ++n) {
+                double ref = 0.0;
+                for (int k = 0; k < 16; ++k) ref += (double)hA[(m + dx) * kK + k] * hB[n * kK + k];
+                const double e = fabs(ref - hD[m * 256 + n]);
+                if (e > worst) worst = e;
+            }
+        printf("   descriptor (LBO, SBO) = %s, dx %d: max |error| vs CPU %.1f %s\n",
+               variant == 0 ? "(16, 128)" : variant == 1 ? "(128, 16)" : "(128, 128)", dx, worst, worst == 0.0 ? "(exact)" : "(WRONG)");
+    }
+    printf("%5s %5s %6s %16s\n", "N", "ncp", "nmma", "cycles/iteration");
+    const int mixes[5][2] = {{0, 6}, {3, 0}, {3, 6}, {6, 6}, {3, 9}};
+    for (int N = 16; N <= 64; N *= 2)
+        for (int i = 0; i < 5; ++i) {
+            long long c = 0;
+            run_cp(N, 0, 512, mixes[i][0], mixes[i][1], &c);
+            printf("%5d %5d %6d %16.1f\n", N, mixes[i][0], mixes[i][1], c / 512.0);
+        }
     return 0;
 }
