@@ -446,7 +446,10 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int P>
+// XH = 1 (pgk_wgrad_fp16x, experimental): the activation operand is ONE IEEE-half plane (plane 0 of the copy
+// pgk_cvt_fp16x2 makes for the forward pass) against the P bf16 planes of g -- P products instead of P (P + 1) / 2;
+// only plane 0 of a stage holds X boxes then.
+template <int P, int XH>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
                 const WgradTcArgs a) {
@@ -524,10 +527,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 const int xn = a.xoff[grp] + smp, gn = a.goff[grp] + smp;
                 const uint32_t dst = sbase + s * stage_bytes;
                 if (elect_one()) {
-                    mbar_expect_tx(fb, stage_bytes);
+                    mbar_expect_tx(fb, XH ? stage_bytes - (P - 1) * 2 * S * box_bytes : stage_bytes);
                     for (int p = 0; p < P; ++p) {
                         const uint32_t pd = dst + p * plane_bytes;
-                        for (int b = 0; b < 2 * S; ++b)
+                        for (int b = 0; b < 2 * S && (!XH || p == 0); ++b)
                             tma_load_5d(pd + b * box_bytes, &tmX, fb, bc[b], x0 + bdx[b], y0 + bdy[b], xn, p);
                         for (int b = 0; b < gboxes; ++b)
                             tma_load_5d(pd + (2 * S + b) * box_bytes, &tmG, fb, co0 + b * 64, x0, y0, gn, p);
@@ -548,7 +551,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             }
         }
     } else if (warp == 5) {
-        const uint32_t idesc = idesc_bf16(a.NT, 1, 1);
+        const uint32_t idesc = XH ? idesc_f16(a.NT, 1, 1, 1, 0) : idesc_bf16(a.NT, 1, 1);
         const uint64_t dbase = smem_desc(0, box_bytes, 1024, 2);
         const uint32_t pl16 = plane_bytes >> 4, bx16 = box_bytes >> 4;
         int s = 0;
@@ -566,9 +569,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {   // PXS = 32 pixels = two K = 16 steps
 #pragma unroll
-                        for (int i = 0; i < P; ++i) {
+                        for (int i = 0; i < (XH ? 1 : P); ++i) {
 #pragma unroll
-                            for (int j = 0; j < P - i; ++j)
+                            for (int j = 0; j < (XH ? P : P - i); ++j)
                                 mma_bf16(d, ad_sl + (uint32_t)(i * pl16 + ks * 128), bd0 + (uint32_t)(j * pl16 + ks * 128),
                                          idesc, (ks == 0 && i + j == 0) ? later : 1u);
                         }
@@ -829,8 +832,9 @@ extern "C" int pgk_wgrad_tc_supported(int H, int W, int Cin, int Cout, int KS, i
 
 extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W,
                             int Cin, int Cout, int KS, int ngroups, int group_n, const int* xoff, const int* goff,
-                            float* dwp, pgk_stream_t stream) {
+                            float* dwp, pgk_stream_t stream, int x_fp16) {
     PGK_REQUIRE(pgk_wgrad_tc_supported(H, W, Cin, Cout, KS, 0, ngroups, group_n), "pgk_wgrad_tc: unsupported shape");
+    PGK_REQUIRE(!x_fp16 || Pr == 2, "pgk_wgrad_tc: the half-plane activation operand goes with two planes of g");
     PGK_REQUIRE(P >= 1 && P <= 3 && Pr >= 1 && Pr <= P, "pgk_wgrad_tc: need 1 <= Pr <= P <= 3");
     PGK_REQUIRE(ngroups >= 1 && ngroups <= 4, "pgk_wgrad_tc: 1..4 groups");
     WgradTcArgs a;
@@ -895,10 +899,11 @@ extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long l
 
     CUtensorMap tmX, tmG;
     {
+        // (a half-plane x is one plane deep: only plane 0 of it is ever read)
         unsigned long long dims[5] = {(unsigned long long)Cin, (unsigned long long)W, (unsigned long long)H,
-                                      (unsigned long long)(xmax + group_n), (unsigned long long)P};
+                                      (unsigned long long)(xmax + group_n), (unsigned long long)(x_fp16 ? 1 : P)};
         unsigned long long str[4] = {2ull * Cin, 2ull * Cin * W, 2ull * Cin * W * H,
-                                     P > 1 ? 2ull * x_ps : 2ull * Cin * W * H * (xmax + group_n)};
+                                     (P > 1 && !x_fp16) ? 2ull * x_ps : 2ull * Cin * W * H * (xmax + group_n)};
         unsigned box[5] = {64u, (unsigned)TW, (unsigned)TH, (unsigned)a.TN, 1u};
         int rc = pgk_make_tmap(&tmX, x, 5, dims, str, box, 128, "pgk_wgrad_tc(x)");
         if (rc) return rc;
@@ -914,15 +919,17 @@ extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long l
     }
     const int smem = a.stages * stage_bytes + 1024 + 256;
     typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const WgradTcArgs);
-    kern_t kern = Pr == 1 ? wgrad_tc_kernel<1> : Pr == 2 ? wgrad_tc_kernel<2> : wgrad_tc_kernel<3>;
-    static bool attr_done[3] = {};
-    if (!attr_done[Pr - 1]) {
+    kern_t kern = x_fp16 ? wgrad_tc_kernel<2, 1>
+                         : Pr == 1 ? wgrad_tc_kernel<1, 0> : Pr == 2 ? wgrad_tc_kernel<2, 0> : wgrad_tc_kernel<3, 0>;
+    static bool attr_done[4] = {};
+    const int ai = x_fp16 ? 3 : Pr - 1;
+    if (!attr_done[ai]) {
         cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e != cudaSuccess) {
             pgk_set_error("pgk_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return PGK_ERR_CUDA;
         }
-        attr_done[Pr - 1] = true;
+        attr_done[ai] = true;
     }
     dim3 grid((unsigned)sgroups, (unsigned)(Cout / a.NT), (unsigned)split);
     pgk_launch(kern, grid, kThreads, smem, (cudaStream_t)stream, tmX, tmG, a);

@@ -100,6 +100,18 @@ try:
     for k,v in r['families'].items(): print('   ',k,{a:round(b,3) for a,b in v.items()})
 except Exception as e: print(' failed', e)
 PY
+stamp "experimental follow-up: weight gradient with the half-plane activation operand (PGK_WGRAD_FP16X=1 on top of PGK_FWD_FP16=1)"
+timeout 300 python tools/tc_test.py wgrad16 > $OUT/wgrad_fp16x_kernel.txt 2>&1; tail -8 $OUT/wgrad_fp16x_kernel.txt
+PGK_FWD_FP16=1 PGK_WGRAD_FP16X=1 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_full_size.py -q -m gpu > $OUT/wgrad_fp16x_parity.log 2>&1; tail -5 $OUT/wgrad_fp16x_parity.log
+PGK_FWD_FP16=1 PGK_WGRAD_FP16X=1 timeout 600 python bench.py --config c2 --steps 8 --warmup 3 --no-cpu-baseline > $OUT/bench_c2_wgrad_fp16x.json 2> $OUT/bench_c2_wgrad_fp16x.err
+python - $OUT/bench_c2_wgrad_fp16x.json <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(' PGK_FWD_FP16=1 PGK_WGRAD_FP16X=1: ms/step %.2f  img/s %.1f  e2e %.1f' % (d['ms_per_step'], d['value'], d['e2e']['value']))
+    for k,v in d['roofline']['families'].items(): print('   ',k,{a:round(b,3) for a,b in v.items()})
+except Exception as e: print(' failed', e)
+PY
 stamp "GPU reference bar (PyTorch eager, fp32 and TF32)"
 timeout 900 python tests/dev/gpu_eager_bar.py c2 c3 c4 c5 --steps 3 --warmup 2 > $OUT/eager_bar.jsonl 2> $OUT/eager_bar.err
 cat $OUT/eager_bar.jsonl
