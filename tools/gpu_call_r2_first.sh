@@ -1,14 +1,26 @@
 #!/bin/bash
-# Round 2, first GPU call: re-validate the round-1 end state on a fresh box, then collect the two measurements the
-# round-1 sessions did not get to (no GPU minutes were left): the per-shape breakdown of every conv / weight-gradient
-# launch (tools/shape_profile.py) and the "GPU reference bar" of SURVEY.md 8(d) (the reference's arithmetic in PyTorch
-# eager on the GPU, tests/dev/gpu_eager_bar.py).     gpurun --timeout 1500 -- 'bash tools/gpu_call_r2_first.sh'
+# Round 2, GPU calls over the round-1 end state.  No GPU minutes were left when the last round-1 sessions wrote the
+# opt-in paths below, so each of them is first checked (single-kernel numerics, then the parity suite with the switch
+# on) and then timed against the default.  One gpurun call per PART (each is sized for ~10-20 minutes of box time):
+#
+#   gpurun --timeout 1500 -- 'bash tools/gpu_call_r2_first.sh A'   re-validation on a fresh box, then the three switches
+#                                                                    with the largest expected effect: fp16 forward
+#                                                                    operands (+ the half-plane weight gradient) on c2,
+#                                                                    programmatic dependent launch on c4 / c3 / c1
+#   gpurun --timeout 1500 -- 'bash tools/gpu_call_r2_first.sh B'   hardware probe (tcgen05 operand layouts, A in tensor
+#                                                                    memory, tcgen05.cp), thin weight gradient SW128,
+#                                                                    vector reductions, per-shape profiles of every config
+#   gpurun --timeout 1500 -- 'bash tools/gpu_call_r2_first.sh C'   tile-width / wave A/Bs, look-ahead H2D copy, and the
+#                                                                    "GPU reference bar" of SURVEY.md 8(d) (PyTorch eager)
+# Outputs land in gpurun_out/r2_<part>/.
 set -u
-OUT=gpurun_out/r2_first
+PART=${1:-A}
+OUT=gpurun_out/r2_$PART
 mkdir -p $OUT
 export PYTHONUNBUFFERED=1
 t0=$(date +%s)
 stamp() { echo "=== $1 (t+$(( $(date +%s) - t0 ))s)"; }
+part_validate() {
 stamp "full gpu test-suite"
 timeout 1200 python -m pytest tests -x -q -m gpu > $OUT/pytest_gpu.log 2>&1; echo "rc=$?" >> $OUT/pytest_gpu.log
 tail -3 $OUT/pytest_gpu.log
@@ -25,6 +37,8 @@ try:
     print('  dominant %s %s %.1f %s frac %.3f share %.2f tensor_pipe %s' % (r['kernel'].split(' ')[0], r['bound'], r['achieved'], r['unit'], r['frac'], r['share_of_step'], r['tensor_pipe']))
 except Exception as e: print(' failed', e)
 PY
+}
+part_pdl() {
 stamp "experimental: programmatic dependent launch (PGK_PDL=1): whole GPU suite, then step time A/B on c4 c3 c1 (with and without CUDA graphs)"
 # the default build compiles the PDL path out: rebuild with it (make PDL=1), A/B with the run-time switch, rebuild the default
 (make -C pggan-pytorch_b200/csrc clean && make -C pggan-pytorch_b200/csrc PDL=1 -j 16) > $OUT/pdl_build.log 2>&1; tail -1 $OUT/pdl_build.log
@@ -44,21 +58,31 @@ PY
   done
 done
 (make -C pggan-pytorch_b200/csrc clean && make -C pggan-pytorch_b200/csrc -j 16) > $OUT/default_rebuild.log 2>&1; tail -1 $OUT/default_rebuild.log
+}
+part_probe() {
 stamp "hardware probe: swizzled row-shifted starts, cycles per MMA by layout / N / A-in-TMEM"
 (nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o /tmp/umma_probe tools/probes/umma_probe.cu && timeout 120 /tmp/umma_probe) > $OUT/umma_probe.txt 2>&1
 cat $OUT/umma_probe.txt
+}
+part_sw128() {
 stamp "experimental: thin weight gradient with SWIZZLE_128B transposed tiles (PGK_WTHIN_SW128=1): numerics, then timing A/B"
 PGK_WTHIN_SW128=1 timeout 300 python tools/tc_test.py wthin > $OUT/wthin_sw128_numerics.txt 2>&1; tail -12 $OUT/wthin_sw128_numerics.txt
 for sw in 0 1; do
   PGK_WTHIN_SW128=$sw timeout 300 python tools/thin_bench.py 1 4 > $OUT/thin_bench_sw$sw.txt 2>&1; echo "-- PGK_WTHIN_SW128=$sw"; cat $OUT/thin_bench_sw$sw.txt
 done
+}
+part_red4() {
 stamp "experimental: 16-byte vector reductions in the wide weight gradient's flush (PGK_WGRAD_RED4=1): numerics"
 PGK_WGRAD_RED4=1 timeout 300 python tools/tc_test.py wgrad > $OUT/wgrad_red4_numerics.txt 2>&1; tail -9 $OUT/wgrad_red4_numerics.txt
+}
+part_shapes() {
 stamp "per-shape profiles c4 c3 c5 c2"
 for c in c4 c3 c5 c2; do
   timeout 300 python tools/shape_profile.py --config $c --steps 3 --warmup 2 --json $OUT/shapes_$c.json > $OUT/shapes_$c.txt 2>&1
   head -30 $OUT/shapes_$c.txt
 done
+}
+part_nt() {
 stamp "wave-quantisation A/B of the wide conv's channel-tile cap (c4, c3)"
 for nt in 64 128; do
   for c in c4 c3; do
@@ -66,12 +90,16 @@ for nt in 64 128; do
     head -1 $OUT/shapes_${c}_nt$nt.txt
   done
 done
+}
+part_switches() {
 stamp "A/B of the experimental switches on the step (c4, c3)"
 for c in c4 c3; do
   PGK_WGRAD_RED4=1 timeout 300 python tools/shape_profile.py --config $c --steps 3 --warmup 2 --json $OUT/shapes_${c}_red4.json > $OUT/shapes_${c}_red4.txt 2>&1; head -1 $OUT/shapes_${c}_red4.txt
   PGK_CONV_WAVE=1 timeout 300 python tools/shape_profile.py --config $c --steps 3 --warmup 2 --json $OUT/shapes_${c}_wave.json > $OUT/shapes_${c}_wave.txt 2>&1; head -1 $OUT/shapes_${c}_wave.txt
   PGK_WTHIN_SW128=1 timeout 300 python tools/shape_profile.py --config $c --steps 3 --warmup 2 --json $OUT/shapes_${c}_sw128.json > $OUT/shapes_${c}_sw128.txt 2>&1; head -1 $OUT/shapes_${c}_sw128.txt
 done
+}
+part_prefetch() {
 stamp "experimental: look-ahead H2D of the real batch (trainer.prefetch_reals): test, then e2e A/B on c4 and c2"
 PGK_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -k prefetched > $OUT/prefetch_test.log 2>&1; tail -2 $OUT/prefetch_test.log
 for c in c4 c2; do
@@ -86,6 +114,8 @@ except Exception as e: print(' failed', e)
 PY
   done
 done
+}
+part_fp16() {
 stamp "experimental: fp16 two-plane forward operands (PGK_FWD_FP16=1): kernel numerics, the whole parity suite, bench c2 A/B"
 timeout 300 python tools/tc_test.py fp16 > $OUT/fwd_fp16_kernel.txt 2>&1; tail -10 $OUT/fwd_fp16_kernel.txt
 PGK_FWD_FP16=1 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_full_size.py -q -m gpu > $OUT/fwd_fp16_parity.log 2>&1; tail -5 $OUT/fwd_fp16_parity.log
@@ -100,6 +130,8 @@ try:
     for k,v in r['families'].items(): print('   ',k,{a:round(b,3) for a,b in v.items()})
 except Exception as e: print(' failed', e)
 PY
+}
+part_wgrad16() {
 stamp "experimental follow-up: weight gradient with the half-plane activation operand (PGK_WGRAD_FP16X=1 on top of PGK_FWD_FP16=1)"
 timeout 300 python tools/tc_test.py wgrad16 > $OUT/wgrad_fp16x_kernel.txt 2>&1; tail -8 $OUT/wgrad_fp16x_kernel.txt
 PGK_FWD_FP16=1 PGK_WGRAD_FP16X=1 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_full_size.py -q -m gpu > $OUT/wgrad_fp16x_parity.log 2>&1; tail -5 $OUT/wgrad_fp16x_parity.log
@@ -112,7 +144,16 @@ try:
     for k,v in d['roofline']['families'].items(): print('   ',k,{a:round(b,3) for a,b in v.items()})
 except Exception as e: print(' failed', e)
 PY
+}
+part_eager() {
 stamp "GPU reference bar (PyTorch eager, fp32 and TF32)"
 timeout 900 python tests/dev/gpu_eager_bar.py c2 c3 c4 c5 --steps 3 --warmup 2 > $OUT/eager_bar.jsonl 2> $OUT/eager_bar.err
 cat $OUT/eager_bar.jsonl
+}
+case "$PART" in
+  A) part_validate; part_fp16; part_wgrad16; part_pdl ;;
+  B) part_probe; part_sw128; part_red4; part_shapes ;;
+  C) part_nt; part_switches; part_prefetch; part_eager ;;
+  *) echo "usage: $0 A|B|C"; exit 2 ;;
+esac
 stamp "done"
