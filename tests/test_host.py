@@ -272,3 +272,20 @@ def test_forward_conv_takes_the_fp16_operands_only_where_it_may(monkeypatch):
     x1, o1 = E.PT.empty(4, 8, 8, 64, 1, 'cpu'), E.PT.empty(4, 8, 8, 128, 1, 'cpu')
     E.conv(x1, (wf, wt, wh), 128, 3, o1, fwd=True)            # the bf16 mode has one plane: nothing to gain
     assert [c[0] for c in calls] == ['pgk_conv']
+
+
+def test_tiled_weight_relayout_index_logic_on_the_host(tmp_path):
+    """The shared-memory tiled flavour of pgk_prep_weight / pgk_unprep_grad (PGK_PREP_TILED=1) keeps its index logic in
+    host-callable functions (csrc/pgk_relayout.cuh); tests/relayout_host_check.cpp runs the kernels' two phases thread
+    by thread on the CPU and compares every element with the one-thread-per-element mapping."""
+    import shutil
+    import subprocess
+    gxx = shutil.which('g++')
+    if gxx is None:
+        pytest.skip('no g++ in this environment')
+    exe = str(tmp_path / 'relayout_check')
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'relayout_host_check.cpp')
+    subprocess.run([gxx, '-O1', '-std=c++17', '-o', exe, src], check=True)
+    r = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stdout
+    assert r.stdout.strip().endswith('0 bad')

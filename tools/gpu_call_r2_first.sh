@@ -75,6 +75,22 @@ part_red4() {
 stamp "experimental: 16-byte vector reductions in the wide weight gradient's flush (PGK_WGRAD_RED4=1): numerics"
 PGK_WGRAD_RED4=1 timeout 300 python tools/tc_test.py wgrad > $OUT/wgrad_red4_numerics.txt 2>&1; tail -9 $OUT/wgrad_red4_numerics.txt
 }
+part_relayout() {
+stamp "experimental: shared-memory tiled weight re-layout (PGK_PREP_TILED=1; index logic host-checked): parity suite, then step time A/B on c1 c4"
+PGK_PREP_TILED=1 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_kernels.py -q -m gpu > $OUT/prep_tiled_parity.log 2>&1; tail -3 $OUT/prep_tiled_parity.log
+for c in c1 c4; do
+  for t in 0 1; do
+    PGK_PREP_TILED=$t timeout 300 python bench.py --config $c --steps 8 --warmup 3 --no-cpu-baseline > $OUT/bench_${c}_tiled$t.json 2> $OUT/bench_${c}_tiled$t.err
+    python - "$OUT/bench_${c}_tiled$t.json" "$c PGK_PREP_TILED=$t" <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(' %-24s ms/step %.3f  img/s %.1f' % (sys.argv[2], d['ms_per_step'], d['value']))
+except Exception as e: print(' failed', sys.argv[2], e)
+PY
+  done
+done
+}
 part_shapes() {
 stamp "per-shape profiles c4 c3 c5 c2"
 for c in c4 c3 c5 c2; do
@@ -152,7 +168,7 @@ cat $OUT/eager_bar.jsonl
 }
 case "$PART" in
   A) part_validate; part_fp16; part_wgrad16; part_pdl ;;
-  B) part_probe; part_sw128; part_red4; part_shapes ;;
+  B) part_probe; part_sw128; part_red4; part_relayout; part_shapes ;;
   C) part_nt; part_switches; part_prefetch; part_eager ;;
   *) echo "usage: $0 A|B|C"; exit 2 ;;
 esac
