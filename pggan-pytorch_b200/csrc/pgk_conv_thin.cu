@@ -69,9 +69,36 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
     return v;
 }
 
-template <int CIN, int P, int SPLIT, int NPAD>
+// Tensor-memory columns of the ATM flavour's A ring: kATMRows input rows x slots of 4 columns (128 pixels x 8 channels
+// each).  Slots of a row: [dx][channel group] for Cin >= 16 -- a K = 16 step (tap, channel-group pair) is two
+// neighbouring slots; Cin = 8: [dx = 0, 1, 2, zero] -- the K = 16 steps are (dx 0, dx 1) and (dx 2, zero slot),
+// exactly the pairs pack_thin_kernel lays the weights out for.
+constexpr int kATMRows = 4;
+template <int CIN>
+struct ATMRing {
+    static constexpr int SLOTS = CIN == 8 ? 4 : 3 * (CIN / 8);
+    static constexpr int ROW_COLS = 4 * SLOTS;
+    static constexpr int COLS = kATMRows * ROW_COLS;
+};
+template <int CIN, int NPAD, int SPLIT, int ATM>
+struct ThinCols {
+    static constexpr int ACC = SPLIT ? 2 * NPAD : NPAD;
+    static constexpr int NEED = kAcc * ACC + (ATM ? ATMRing<CIN>::COLS : 0);
+    static constexpr unsigned N = NEED <= 64 ? 64u : NEED <= 128 ? 128u : NEED <= 256 ? 256u : 512u;
+};
+
+// ATM = 1 (PGK_THIN_ATM=1, experimental, bf16 mode only): the A operand of every MMA comes from TENSOR MEMORY.  Each
+// input row is copied once per dx from its shared-memory row buffer into the ring above (tcgen05.cp.128x128b: 128
+// pixels x 16 bytes from a start address shifted by dx pixels -- the tap shift the SS-mode descriptors express the same
+// way) and then serves the three output rows that use it; the MMAs read A at the tensor core's own rate instead of
+// streaming a 128-row tile through the shared-memory port per K = 16 step ("the thin conv with A in
+// tensor memory").  tcgen05.cp and tcgen05.mma of one thread execute in issue order, which is all the ring needs: a
+// slot is overwritten two output rows after its last reader was issued.  Same producer, weights, barriers and
+// epilogue; a shared-memory row is released as soon as its copies have completed.
+template <int CIN, int P, int SPLIT, int NPAD, int ATM>
 __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const ThinArgs a) {
+    static_assert(!ATM || (P == 1 && SPLIT == 0), "the tensor-memory A ring exists for the one-plane mode only");
     constexpr int CG = Steps<CIN>::CG, STEPS = Steps<CIN>::N;
     constexpr uint32_t plane_bytes = CG * kCgBytes;
     constexpr uint32_t row_bytes = P * plane_bytes;
@@ -112,14 +139,27 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
         }
         fence_barrier_init();
     }
-    constexpr int acc_cols = SPLIT ? 2 * NPAD : NPAD;
-    constexpr unsigned ncols = kAcc * acc_cols <= 64 ? 64u : kAcc * acc_cols <= 128 ? 128u : kAcc * acc_cols <= 256 ? 256u : 512u;
+    constexpr int acc_cols = ThinCols<CIN, NPAD, SPLIT, ATM>::ACC;
+    constexpr unsigned ncols = ThinCols<CIN, NPAD, SPLIT, ATM>::N;
     if (warp == 9) tmem_alloc(tptr, ncols);
     fence_proxy_async();   // generic-proxy writes (weights, zeroed ring) -> visible to the tensor core / TMA
     fence_before();
     __syncthreads();
     fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tptr - raw));
+    if constexpr (ATM != 0) {
+        // the A ring starts out as zeros: the zero slot of Cin = 8 is never written again, and no MMA may ever read
+        // a non-finite leftover (warps 0-3 own the four lane quarters)
+        if (warp < 4) {
+            const uint32_t t0 = tmem + kAcc * acc_cols + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+            for (int c = 0; c < ATMRing<CIN>::COLS; c += 8) tmem_zero8(t0 + c);
+            tmem_st_wait();
+        }
+        fence_before();
+        __syncthreads();
+        fence_after();
+    }
 
     // The two single-warp roles share their SM sub-partitions with epilogue warps: busy polling (test_wait) costs
     // those warps issue slots (12 % of all issued instructions in the ncu capture), try_wait suspends instead.
@@ -221,6 +261,65 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
         }
         cp_async_wait<0>();
         hand_over(g);
+    } else if (warp == 9 && ATM != 0) {
+        // ---- MMA issue, A from tensor memory (see the kernel header)
+        const uint32_t idesc = idesc_bf16(NPAD, 0, 0);
+        const uint64_t bdesc0 = smem_desc(w0, (uint32_t)NPAD * 16u, 128, 0);
+        constexpr uint32_t wstep16 = wstep >> 4;
+        // copy source: 128 pixels x 16 bytes, pixels 16 bytes apart (an 8-pixel core matrix is 128 contiguous bytes)
+        const uint64_t cdesc_hi = smem_desc(0, 16, 128, 0);
+        constexpr uint32_t kRowCols = ATMRing<CIN>::ROW_COLS;
+        const uint32_t tA = tmem + kAcc * acc_cols;
+        auto copy_row = [&](uint32_t gr) {   // input row gr: shared-memory slot gr mod ring -> ring row gr mod 4
+            const uint32_t src = (rows0 + (gr & (kRing - 1)) * row_bytes) >> 4;
+            const uint32_t dst = tA + (gr & (kATMRows - 1)) * kRowCols;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+                for (int cg = 0; cg < CG; ++cg)
+                    tmem_cp_128x128b(dst + (uint32_t)(dx * CG + cg) * 4u,
+                                     cdesc_hi | (uint64_t)(src + (uint32_t)(cg * kCgBytes + dx * 16) / 16u));
+            }
+        };
+        uint32_t g = 0, ti = 0;
+        for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
+            wait_bar(rfull(g & (kRing - 1)), (g >> kRingLog) & 1);
+            wait_bar(rfull((g + 1) & (kRing - 1)), ((g + 1) >> kRingLog) & 1);
+            fence_after();
+            if (elect_one()) {
+                copy_row(g);
+                copy_row(g + 1);
+                mma_commit(rempty(g & (kRing - 1)));
+                mma_commit(rempty((g + 1) & (kRing - 1)));
+            }
+            __syncwarp();
+            for (int i = 0; i < a.RC; ++i, ++g, ++ti) {
+                wait_bar(rfull((g + 2) & (kRing - 1)), ((g + 2) >> kRingLog) & 1);
+                const int b = ti & (kAcc - 1);
+                wait_bar(aempty(b), ((ti / kAcc) & 1) ^ 1);
+                fence_after();
+                if (elect_one()) {
+                    copy_row(g + 2);
+                    mma_commit(rempty((g + 2) & (kRing - 1)));
+                    const uint32_t d = tmem + b * acc_cols;
+#pragma unroll
+                    for (int st = 0; st < STEPS; ++st) {
+                        int dy, slot;
+                        if (CIN == 8) {
+                            dy = st >> 1, slot = (st & 1) * 2;          // (dx 0, dx 1) | (dx 2, zero slot)
+                        } else {
+                            const int tap = st / (CIN / 16), cgp = st % (CIN / 16);
+                            dy = tap / 3, slot = (tap % 3) * CG + 2 * cgp;
+                        }
+                        const uint32_t at = tA + ((g + dy) & (kATMRows - 1)) * kRowCols + (uint32_t)slot * 4u;
+                        mma_bf16_ts(d, at, bdesc0 + (uint32_t)(st * wstep16), idesc, st == 0 ? 0u : 1u);
+                    }
+                    mma_commit(afull(b));
+                }
+                __syncwarp();
+            }
+            g += 2;
+        }
     } else if (warp == 9) {
         // ---- MMA issue: per output row, STEPS x (products of planes) MMAs of 128 pixels x Npad x 16
         const uint32_t idesc = idesc_bf16(NPAD, 0, 0);
@@ -519,11 +618,11 @@ struct ThinPlan {
     int occ, ring, smem;
 };
 
-template <int CIN, int P, int SPLIT, int NPAD>
+template <int CIN, int P, int SPLIT, int NPAD, int ATM>
 static int launch_thin(const CUtensorMap& tmA, ThinArgs& a, cudaStream_t stream) {
     static bool attr = false;
     static ThinPlan plan;   // CTAs per SM, ring depth and shared memory of this instance
-    auto kern = conv_thin_kernel<CIN, P, SPLIT, NPAD>;
+    auto kern = conv_thin_kernel<CIN, P, SPLIT, NPAD, ATM>;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e != cudaSuccess) {
@@ -531,8 +630,7 @@ static int launch_thin(const CUtensorMap& tmA, ThinArgs& a, cudaStream_t stream)
             return PGK_ERR_CUDA;
         }
         constexpr int steps = Steps<CIN>::N;
-        constexpr int acc_cols = SPLIT ? 2 * NPAD : NPAD;
-        constexpr int ncols = kAcc * acc_cols <= 64 ? 64 : kAcc * acc_cols <= 128 ? 128 : kAcc * acc_cols <= 256 ? 256 : 512;
+        constexpr int ncols = (int)ThinCols<CIN, NPAD, SPLIT, ATM>::N;
         const int fixed = 128 + P * steps * NPAD * 32 + 16 + 16 * kMaxRing + 16 * kAcc + 32 + 4 * NPAD + 64;
         const int row = P * (CIN / 8) * kCgBytes;
         ThinPlan pl = {0, 0, 0};
@@ -555,8 +653,8 @@ static int launch_thin(const CUtensorMap& tmA, ThinArgs& a, cudaStream_t stream)
             cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, kern, kThinThreads, pl.smem);
             cudaFuncAttributes fa;
             cudaFuncGetAttributes(&fa, kern);
-            fprintf(stderr, "pgk_conv_thin<%d,%d,%d,%d>: plan occ %d ring %d smem %d | runtime says %d blocks/SM (%s), regs %d, "
-                            "static smem %zu, max dyn %d\n", CIN, P, SPLIT, NPAD, pl.occ, pl.ring, pl.smem, got,
+            fprintf(stderr, "pgk_conv_thin<%d,%d,%d,%d,%d>: plan occ %d ring %d smem %d | runtime says %d blocks/SM (%s), regs %d, "
+                            "static smem %zu, max dyn %d\n", CIN, P, SPLIT, NPAD, ATM, pl.occ, pl.ring, pl.smem, got,
                     cudaGetErrorString(oe), fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes);
             cudaGetLastError();
         }
@@ -597,7 +695,7 @@ static int launch_thin(const CUtensorMap& tmA, ThinArgs& a, cudaStream_t stream)
             const char* e = getenv("PGK_THIN_PAIR");
             pair = e ? atoi(e) != 0 : 1;
         }
-        a.pair = pair && best_pl.ring >= 8 && best_rc % 2 == 0;
+        a.pair = !ATM && pair && best_pl.ring >= 8 && best_rc % 2 == 0;
     }
     pgk_launch(kern, best_grid, kThinThreads, best_pl.smem, stream, tmA, a);
     return PGK_OK;
@@ -658,8 +756,20 @@ extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N
     }
     cudaStream_t st = (cudaStream_t)stream;
     int rc = PGK_ERR_ARG;
+    // PGK_THIN_ATM=1 (experimental, see the kernel header): A operands from tensor memory in the one-plane mode
+    static int atm = -1;
+    if (atm < 0) {
+        const char* e = getenv("PGK_THIN_ATM");
+        atm = e ? atoi(e) != 0 : 0;
+    }
+#define PGK_THIN_ATM_CASE(C_, N_) \
+    if (atm && Pr == 1 && Cin == C_ && a.Npad == N_) rc = launch_thin<C_, 1, 0, N_, 1>(tmA, a, st);
+    PGK_THIN_ATM_CASE(8, 16) PGK_THIN_ATM_CASE(8, 32) PGK_THIN_ATM_CASE(8, 64)
+    PGK_THIN_ATM_CASE(16, 16) PGK_THIN_ATM_CASE(16, 32) PGK_THIN_ATM_CASE(16, 64)
+    PGK_THIN_ATM_CASE(32, 16) PGK_THIN_ATM_CASE(32, 32) PGK_THIN_ATM_CASE(32, 64)
+#undef PGK_THIN_ATM_CASE
 #define PGK_THIN_CASE_N(C_, P_, S_, N_) \
-    if (Cin == C_ && Pr == P_ && a.split_acc == S_ && a.Npad == N_) rc = launch_thin<C_, P_, S_, N_>(tmA, a, st);
+    if (rc == PGK_ERR_ARG && Cin == C_ && Pr == P_ && a.split_acc == S_ && a.Npad == N_) rc = launch_thin<C_, P_, S_, N_, 0>(tmA, a, st);
 #define PGK_THIN_CASE(C_, P_, S_) PGK_THIN_CASE_N(C_, P_, S_, 16) PGK_THIN_CASE_N(C_, P_, S_, 32) PGK_THIN_CASE_N(C_, P_, S_, 64)
     PGK_THIN_CASE(8, 1, 0) PGK_THIN_CASE(16, 1, 0) PGK_THIN_CASE(32, 1, 0)
     PGK_THIN_CASE(8, 2, 0) PGK_THIN_CASE(16, 2, 0) PGK_THIN_CASE(32, 2, 0)

@@ -64,6 +64,17 @@ stamp "hardware probe: swizzled row-shifted starts, cycles per MMA by layout / N
 (nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o /tmp/umma_probe tools/probes/umma_probe.cu && timeout 120 /tmp/umma_probe) > $OUT/umma_probe.txt 2>&1
 cat $OUT/umma_probe.txt
 }
+part_atm() {
+stamp "experimental: thin conv with A in tensor memory (PGK_THIN_ATM=1; after the probe's part 4): numerics, kernel timing, c4 / c3 step A/B"
+timeout 300 python tools/tc_test.py thin1 > $OUT/thin1_default.txt 2>&1; tail -3 $OUT/thin1_default.txt
+PGK_THIN_ATM=1 PGK_THIN_DEBUG=1 timeout 300 python tools/tc_test.py thin1 > $OUT/thin1_atm.txt 2>&1; echo "rc=$?" >> $OUT/thin1_atm.txt; grep -v "^pgk_" $OUT/thin1_atm.txt | tail -18
+for atm in 0 1; do
+  PGK_THIN_ATM=$atm timeout 300 python tools/thin_bench.py 1 4 > $OUT/thin_bench_atm$atm.txt 2>&1; echo "-- PGK_THIN_ATM=$atm"; cat $OUT/thin_bench_atm$atm.txt
+done
+for c in c4 c3; do
+  PGK_THIN_ATM=1 timeout 300 python tools/shape_profile.py --config $c --steps 3 --warmup 2 --json $OUT/shapes_${c}_atm.json > $OUT/shapes_${c}_atm.txt 2>&1; head -1 $OUT/shapes_${c}_atm.txt
+done
+}
 part_sw128() {
 stamp "experimental: thin weight gradient with SWIZZLE_128B transposed tiles (PGK_WTHIN_SW128=1): numerics, then timing A/B"
 PGK_WTHIN_SW128=1 timeout 300 python tools/tc_test.py wthin > $OUT/wthin_sw128_numerics.txt 2>&1; tail -12 $OUT/wthin_sw128_numerics.txt
@@ -168,7 +179,7 @@ cat $OUT/eager_bar.jsonl
 }
 case "$PART" in
   A) part_validate; part_fp16; part_wgrad16; part_pdl ;;
-  B) part_probe; part_sw128; part_red4; part_relayout; part_shapes ;;
+  B) part_probe; part_shapes; part_atm; part_sw128; part_red4; part_relayout ;;
   C) part_nt; part_switches; part_prefetch; part_eager ;;
   *) echo "usage: $0 A|B|C"; exit 2 ;;
 esac

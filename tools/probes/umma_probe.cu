@@ -51,28 +51,13 @@ __host__ __device__ inline uint32_t elem_off(int layout, int r, int k) {
     return ((uint32_t)k >> 3) * (kRows * 16u) + (uint32_t)r * 16u + ((uint32_t)k & 7u) * 2u;
 }
 
-// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand comes from tensor memory (lane = row, one 32-bit column = two
-// consecutive K elements), which takes the 128-row A read off the shared-memory port
-__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
+// (mma_bf16_ts and tmem_cp_128x128b come from pgk_tc.cuh)
 // 32 lanes x 8 consecutive 32-bit columns from registers (lane = TMEM lane of this warp's quarter)
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
                  "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
-// 128 rows x 16 bytes from shared memory (8-row core matrices of 128 contiguous bytes, SBO apart) -> 4 TMEM columns
-__device__ __forceinline__ void tmem_cp_128x128b(uint32_t taddr, uint64_t sdesc) {
-    asm volatile("tcgen05.cp.cta_group::1.128x128b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
 }
 
 __device__ __forceinline__ uint64_t make_desc(int layout, uint32_t tile_base, int r0, int kstep, int base_off_mode) {

@@ -1,5 +1,5 @@
 """Development aid (GPU box): tensor-core kernels vs the CUDA-core kernels of the same library on random operands.
-   python tools/tc_test.py [conv|fp16|wgrad16|thin|wthin|wgrad|all]"""
+   python tools/tc_test.py [conv|fp16|wgrad16|thin|thin1|wthin|wgrad|all]"""
 import os
 import sys
 import time
@@ -260,6 +260,14 @@ def main():
         ok &= conv_case(1, 256, 256, 32, 64, 3, 3)
         ok &= conv_case(1, 512, 512, 16, 8, 3, 1, mask=True, act=0, fwd=False)
         ok &= conv_case(3, 128, 128, 32, 16, 3, 2)
+    if what in ('thin1', 'all'):
+        # every (Cin, Npad) instance of the thin conv in the one-plane mode (what PGK_THIN_ATM=1 replaces)
+        for cin in (8, 16, 32):
+            for cout in (8, 16, 32, 64):
+                ok &= conv_case(2, 32, 256, cin, cout, 3, 1)
+        ok &= conv_case(1, 64, 128, 8, 8, 3, 1, mask=True, act=0, bias=False, scale=0.25, fwd=False)
+        ok &= conv_case(3, 8, 128, 16, 32, 3, 1, mask=True)
+        ok &= conv_case(1, 1024, 1024, 8, 16, 3, 1)
     if what in ('wthin', 'all'):
         ok &= wgrad_case(1, 128, 128, 16, 16, 3, 1)
         ok &= wgrad_case(2, 256, 256, 16, 16, 3, 2, ngroups=2)
