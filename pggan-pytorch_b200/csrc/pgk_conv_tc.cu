@@ -113,7 +113,9 @@ struct ConvTcArgs {
 // P (planes read), KSTEPS (= bkb / 32) and SPLIT (separate correction accumulator) are compile-time: the MMA-issue
 // sequence of a k-slice unrolls to one descriptor add + one UTCHMMA per product.  (With run-time loop bounds the
 // dependent uniform-datapath address arithmetic cost ~350 cycles per MMA -- three times the MMA itself.)
-template <int P, int KSTEPS, int SPLIT>
+// F16 = 1 (pgk_conv_fp16): IEEE-half operand planes -- the operand formats come from the arguments and the accumulator
+// is scaled back before the bias.  F16 = 0 instances carry none of that (their machine code is the GPU-verified one).
+template <int P, int KSTEPS, int SPLIT, int F16>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmM, const ConvTcArgs a) {
@@ -214,7 +216,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp == 9) {
-        const uint32_t idesc = idesc_f16(a.NT, 0, 0, a.fp16_a, a.fp16_b);   // == idesc_bf16(NT, 0, 0) for bf16 planes
+        const uint32_t idesc = F16 ? idesc_f16(a.NT, 0, 0, a.fp16_a, a.fp16_b) : idesc_bf16(a.NT, 0, 0);
         // descriptor = constant high part | (address >> 4) in the low 14 bits: per MMA only an add
         const uint64_t dbase = smem_desc(0, 16, 8u * kBkb, KSTEPS == 4 ? 2u : 4u);
         constexpr uint32_t a16 = a_bytes >> 4;
@@ -347,7 +349,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] += w[j];
                         }
-                        if (a.acc_scale != 1.f) {   // fp16 weight operands are packed times a power of two
+                        if (F16) {   // fp16 weight operands are packed times a power of two
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] *= a.acc_scale;
                         }
@@ -449,7 +451,9 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 // XH = 1 (pgk_wgrad_fp16x, experimental): the activation operand is ONE IEEE-half plane (plane 0 of the copy
 // pgk_cvt_fp16x2 makes for the forward pass) against the P bf16 planes of g -- P products instead of P (P + 1) / 2;
 // only plane 0 of a stage holds X boxes then.
-template <int P, int XH>
+// RED4 = 1 (PGK_WGRAD_RED4=1, experimental): the flush uses 16-byte vector reductions, or plain read-add-write where
+// the pixel range is not split.  The <P, 0, 0> instances are the GPU-verified machine code.
+template <int P, int XH, int RED4>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
                 const WgradTcArgs a) {
@@ -596,7 +600,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 float v[16];
                 tmem_ld16(trow + sl * a.NT + c, v);
                 if (k < K) {
-                    if (a.red4) {
+                    if (RED4) {
                         if (gridDim.z == 1) {
                             // the pixel range is not split: this thread is the only writer of its row slice, so the
                             // accumulation into dwp needs no atomics at all
@@ -788,12 +792,14 @@ extern "C" int pgk_conv_tc(const void* x, int P, int Pr, long long x_ps, int N, 
     typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvTcArgs);
     kern_t kern = nullptr;
     const int ks = a.bkb / 32;
-#define PGK_CONV_CASE(P_, K_, S_) \
-    if (Pr == P_ && ks == K_ && a.split_acc == S_) kern = conv_tc_kernel<P_, K_, S_>;
-    PGK_CONV_CASE(1, 4, 0) PGK_CONV_CASE(1, 2, 0)
-    PGK_CONV_CASE(2, 4, 0) PGK_CONV_CASE(2, 2, 0)
-    PGK_CONV_CASE(2, 4, 1) PGK_CONV_CASE(2, 2, 1)
-    PGK_CONV_CASE(3, 4, 1) PGK_CONV_CASE(3, 2, 1)
+    const int f16 = (a.fp16_a || a.fp16_b) ? 1 : 0;
+    PGK_REQUIRE(!f16 || (a.fp16_a && a.fp16_b && Pr == 2), "pgk_conv_tc: half operands come as two planes of both x and w");
+#define PGK_CONV_CASE(P_, K_, S_, F_) \
+    if (Pr == P_ && ks == K_ && a.split_acc == S_ && f16 == F_) kern = conv_tc_kernel<P_, K_, S_, F_>;
+    PGK_CONV_CASE(1, 4, 0, 0) PGK_CONV_CASE(1, 2, 0, 0)
+    PGK_CONV_CASE(2, 4, 0, 0) PGK_CONV_CASE(2, 2, 0, 0)
+    PGK_CONV_CASE(2, 4, 1, 1) PGK_CONV_CASE(2, 2, 1, 1)
+    PGK_CONV_CASE(3, 4, 1, 0) PGK_CONV_CASE(3, 2, 1, 0)
 #undef PGK_CONV_CASE
     PGK_REQUIRE(kern != nullptr, "pgk_conv_tc: no kernel instance for Pr %d ksteps %d split %d", Pr, ks, a.split_acc);
     static bool attr_done[3][2][2] = {};
@@ -919,10 +925,15 @@ extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long l
     }
     const int smem = a.stages * stage_bytes + 1024 + 256;
     typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const WgradTcArgs);
-    kern_t kern = x_fp16 ? wgrad_tc_kernel<2, 1>
-                         : Pr == 1 ? wgrad_tc_kernel<1, 0> : Pr == 2 ? wgrad_tc_kernel<2, 0> : wgrad_tc_kernel<3, 0>;
-    static bool attr_done[4] = {};
-    const int ai = x_fp16 ? 3 : Pr - 1;
+    kern_t kern;
+    if (a.red4)
+        kern = x_fp16 ? wgrad_tc_kernel<2, 1, 1>
+                      : Pr == 1 ? wgrad_tc_kernel<1, 0, 1> : Pr == 2 ? wgrad_tc_kernel<2, 0, 1> : wgrad_tc_kernel<3, 0, 1>;
+    else
+        kern = x_fp16 ? wgrad_tc_kernel<2, 1, 0>
+                      : Pr == 1 ? wgrad_tc_kernel<1, 0, 0> : Pr == 2 ? wgrad_tc_kernel<2, 0, 0> : wgrad_tc_kernel<3, 0, 0>;
+    static bool attr_done[8] = {};
+    const int ai = (x_fp16 ? 3 : Pr - 1) + (a.red4 ? 4 : 0);
     if (!attr_done[ai]) {
         cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e != cudaSuccess) {

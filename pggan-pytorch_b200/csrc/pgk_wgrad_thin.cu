@@ -318,8 +318,9 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                         for (int pi = 0; pi < P; ++pi) {
 #pragma unroll
                             for (int pj = 0; pj < P - pi; ++pj)
-                                mma_bf16(d, dhi | (uint64_t)(xb[ky] + (pi * xt_plane) / 16 + kx16(ks)),
-                                         bd0 + (uint32_t)(pj * gtp16 + kg16(ks)), idesc,
+                                mma_bf16(d, dhi | (uint64_t)(SW ? xb[ky] + (pi * xt_plane) / 16 + kx16(ks)
+                                                                : xb[ky] + (pi * xt_plane + ks * 256) / 16),
+                                         bd0 + (uint32_t)(pj * gtp16 + (SW ? kg16(ks) : (uint32_t)(ks * 16))), idesc,
                                          (ks == 0 && pi + pj == 0) ? later : 1u);
                         }
                     };
@@ -331,8 +332,9 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                             for (int pi = 0; pi < P; ++pi) {
 #pragma unroll
                                 for (int pj = 0; pj < P - pi; ++pj)
-                                    mma_bf16(d, dhi | (uint64_t)(((xt0 + pi * (4u * xt_plane)) >> 4) + kx16(ks)),
-                                             bd0 + (uint32_t)(pj * gtp16 + kg16(ks)), idesc,
+                                    mma_bf16(d, dhi | (uint64_t)(SW ? ((xt0 + pi * (4u * xt_plane)) >> 4) + kx16(ks)
+                                                                    : (xt0 + pi * (4u * xt_plane) + ks * 256) >> 4),
+                                             bd0 + (uint32_t)(pj * gtp16 + (SW ? kg16(ks) : (uint32_t)(ks * 16))), idesc,
                                              (ks == 0 && pi + pj == 0) ? later4 : 1u);
                             }
                         }
