@@ -289,3 +289,47 @@ def test_tiled_weight_relayout_index_logic_on_the_host(tmp_path):
     r = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
     assert r.returncode == 0, r.stdout
     assert r.stdout.strip().endswith('0 bad')
+
+
+@pytest.mark.parametrize('fp16', [False, True])
+def test_python_sequencing_of_one_iteration_with_stubbed_kernels(monkeypatch, fp16):
+    """The host side of a D step and a G step (engine.py / wgan_gp_loss.py) runs end to end on CPU tensors when every
+    libpgk call is replaced by a recorder: no kernel runs, but every tensor is allocated, every launch is sequenced and
+    autograd receives the deposited gradients -- exactly the parameters of the active set get a .grad
+    (network.py:118-139, 225-240; inactive blocks keep None, as in the reference).  With fp16=True the same under the
+    two opt-in fp16 switches (their routing code is host logic too)."""
+    import collections
+    from importlib import import_module
+    E = import_module('pggan-pytorch_b200.engine')
+    L = import_module('pggan-pytorch_b200.wgan_gp_loss')
+    calls = collections.Counter()
+
+    def fake_call(name, *a):
+        calls[name] += 1
+    for m in (E, L, pg._lib):
+        monkeypatch.setattr(m, 'call', fake_call)
+    monkeypatch.setattr(E, 'FWD_FP16', fp16)
+    monkeypatch.setattr(E, 'WGRAD_FP16X', fp16)
+    for cls in (pg.Generator, pg.Discriminator):
+        monkeypatch.setattr(cls, '_input', lambda self, x: x.contiguous().float())
+    for depth, alpha, nd_expect, ng_expect in ((0, 1.0, 8, 6), (2, 0.5, 18, 16), (3, 1.0, 20, 18)):
+        G = pg.Generator((None, 3, 32, 32), fmap_base=1024, fmap_max=128, latent_size=64)
+        D = pg.Discriminator((None, 3, 32, 32), fmap_base=1024, fmap_max=128)
+        G.depth = D.depth = depth
+        G.alpha = D.alpha = alpha
+        r = 4 * 2 ** depth
+        calls.clear()
+        cost, d_real, d_fake = pg.wgan_gp_D_loss(D, G, torch.randn(4, 3, r, r), torch.randn(4, 64))
+        assert tuple(d_real.shape) == (4, 1) and tuple(d_fake.shape) == (4, 1) and cost.dim() == 0
+        cost.backward()
+        assert sum(p.grad is not None for p in D.parameters()) == nd_expect
+        assert all(p.grad is None for p in G.parameters())
+        assert calls['pgk_gp_penalty'] == 1 and calls['pgk_stddev_bwd2'] == 1
+        if fp16:
+            assert calls['pgk_conv_fp16'] > 0 and calls['pgk_cvt_fp16x2'] == calls['pgk_conv_fp16']
+            assert depth == 0 or calls['pgk_wgrad_fp16x'] > 0    # (depth 0, batch 4: too few pixels for the wide kernel)
+        else:
+            assert calls['pgk_conv_fp16'] == 0 and calls['pgk_wgrad_fp16x'] == 0 and calls['pgk_pack_operand_fp16'] == 0
+        gcost = pg.wgan_gp_G_loss(G, D, torch.randn(4, 64))
+        gcost.backward()
+        assert sum(p.grad is not None for p in G.parameters()) == ng_expect
