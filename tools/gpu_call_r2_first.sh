@@ -1,9 +1,9 @@
 #!/bin/bash
 # Round 2, GPU calls over the round-1 end state.  No GPU minutes were left when the last round-1 sessions wrote the
 # opt-in paths below, so each of them is first checked (single-kernel numerics, then the parity suite with the switch
-# on) and then timed against the default.  One gpurun call per PART (each is sized for ~10-20 minutes of box time):
+# on) and then timed against the default.  One gpurun call per PART (each is sized for ~15-30 minutes of box time; the parts are independent, and so are the part_* functions inside them):
 #
-#   gpurun --timeout 1500 -- 'bash tools/gpu_call_r2_first.sh A'   re-validation on a fresh box, then the three switches
+#   gpurun --timeout 2400 -- 'bash tools/gpu_call_r2_first.sh A'   re-validation on a fresh box, then the three switches
 #                                                                    with the largest expected effect: fp16 forward
 #                                                                    operands (+ the half-plane weight gradient) on c2,
 #                                                                    programmatic dependent launch on c4 / c3 / c1
