@@ -57,9 +57,19 @@ struct WThinArgs {
 // buffer = 128 bytes = 64 pixels, 16-byte chunk c of row m at (c ^ (m & 7)) * 16, the two 64-pixel halves of a row
 // ("atoms") `atom` bytes apart -- instead of un-swizzled 8 x 16-byte core matrices.  Same buffers, same sizes, same
 // barriers; only the stmatrix destinations and the MMA descriptors differ.
-template <int CIN, int P, int SW>
+//
+// ATM = 1 (PGK_WTHIN_ATM=1, experimental, Cin = 8 only): the stacked A operand lives in TENSOR MEMORY.  The four ring
+// slots of 32 accumulator rows are the four 32-lane quarters of tensor memory, and a quarter belongs to one warp: the
+// transposer warp (input row & 3) gathers its row straight from the raw [pixel][8 channels] buffer -- lane = (kx, ci)
+// reads X[p + kx][ci] for p = 0..127, conflict-free 16-bit loads -- packs pixel pairs and writes them with tcgen05.st
+// (64 columns per plane); the MMAs take [a_tmem] and no longer stream a 128-row A tile through the shared-memory port
+// per K = 16 step (~75 cycles each measured, 8 per image row, against ~180 cycles of HBM time per row).  Same rings,
+// barriers, accumulators and flush; no ldmatrix / stmatrix and no transposed tiles for X.  A slot is rewritten while
+// the MMAs of the current row still read its lanes as the don't-care ky -- those accumulator rows are never flushed.
+template <int CIN, int P, int SW, int ATM>
 __global__ void __launch_bounds__(kThreads, 2)
 wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WThinArgs a) {
+    static_assert(!ATM || (CIN == 8 && SW == 0), "the tensor-memory A operand exists for the stacked Cin = 8 flavour");
     // row groups of XT3: 3 * CG shifted copies + one group whose first row is all ones (the bias-gradient row)
     constexpr int CG = CIN / 8, XG = 3 * CG;
     constexpr uint32_t xt_plane = (XG + 1) * kGrp, xt_buf = P * xt_plane;
@@ -127,7 +137,9 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
     fence_proxy_async();
     const unsigned nacc = STACK ? 4u : 3u;
-    const unsigned ncols = nacc * a.Npad <= 64 ? 64u : nacc * a.Npad <= 128 ? 128u : 256u;
+    // ATM: the A operand (128 pixels = 64 columns per plane) sits after the accumulators
+    const unsigned ncols = ATM ? (nacc * a.Npad + 64u * P <= 128 ? 128u : nacc * a.Npad + 64u * P <= 256 ? 256u : 512u)
+                               : (nacc * a.Npad <= 64 ? 64u : nacc * a.Npad <= 128 ? 128u : 256u);
     if (warp == 5) tmem_alloc(tptr, ncols);
     fence_before();
     __syncthreads();
@@ -324,7 +336,20 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                                          (ks == 0 && pi + pj == 0) ? later : 1u);
                         }
                     };
-                    if (STACK) {
+                    if (STACK && ATM) {
+                        const uint32_t d = tmem + c4 * a.Npad, ta = tmem + 4u * a.Npad;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+                            for (int pi = 0; pi < P; ++pi) {
+#pragma unroll
+                                for (int pj = 0; pj < P - pi; ++pj)
+                                    mma_bf16_ts(d, ta + (uint32_t)(pi * 64 + ks * 8),
+                                                bd0 + (uint32_t)(pj * gtp16 + ks * 16), idesc,
+                                                (ks == 0 && pi + pj == 0) ? later4 : 1u);
+                            }
+                        }
+                    } else if (STACK) {
                         const uint32_t d = tmem + c4 * a.Npad;
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks) {
@@ -378,6 +403,35 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     mbar_wait(xfull(s), (gx >> kRawLog) & 1);
                     mbar_wait(xtempty(b), ((gx >> 2) & 1) ^ 1);
                     const uint32_t src0 = rawx0 + s * rawx_slot;
+                    if (ATM) {
+                        // the warp that owns ring slot b (= lane quarter b of tensor memory) writes the whole row:
+                        // lane = kx * 8 + ci gathers its channel of the kx-shifted pixels, lane 24 is the ones row
+                        if (warp == b) {
+                            const uint32_t ta = tmem + 4u * a.Npad + ((uint32_t)(warp * 32) << 16);
+                            const uint32_t lsrc = src0 + (uint32_t)(lane >> 3) * 16u + (uint32_t)(lane & 7) * 2u;
+                            for (int p = 0; p < P; ++p) {
+#pragma unroll
+                                for (int c = 0; c < 64; c += 8) {   // 8 columns = 16 pixels
+                                    uint32_t v[8];
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        uint32_t lo = 0, hi = 0;
+                                        if (lane < 24) {
+                                            const uint32_t ad = lsrc + p * rawx_plane + (uint32_t)(2 * (c + j)) * 16u;
+                                            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(lo) : "r"(ad));
+                                            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(hi) : "r"(ad + 16u));
+                                        }
+                                        v[j] = lane < 24 ? (lo | (hi << 16)) : (lane == 24 && p == 0) ? one16 : 0u;
+                                    }
+                                    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::
+                                                 "r"(ta + (uint32_t)(p * 64 + c)), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                                                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+                                }
+                            }
+                            tmem_st_wait();
+                            fence_before();
+                        }
+                    } else
                     // ops: (plane, kx, channel group, 32-pixel block)
                     for (int o = warp; o < P * 3 * CG * 4; o += 4) {
                         const int blk = o & 3;
@@ -392,7 +446,7 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                         else
                             stmatrix_x4(xt_at(b, p) + (kx * CG + cg) * kGrp + (blk * 4 + lj) * 128 + li * 16, v);
                     }
-                    if (warp == 0 && lane < 16) {   // the ones row (plane 0, row 0 of group XG), 16 pixel chunks
+                    if (!ATM && warp == 0 && lane < 16) {   // the ones row (plane 0, row 0 of group XG), 16 pixel chunks
                         const uint32_t dst = SW ? xt_sw(b, 0) + sw_off(xt_atom, XG * 8, lane) : xt_at(b, 0) + XG * kGrp + lane * 128;
                         st_shared_v4(dst, make_uint4(one16, one16, one16, one16));
                     }
@@ -525,9 +579,9 @@ struct WThinPlan {
     int occ, raw, smem;
 };
 
-template <int CIN, int P, int SW>
+template <int CIN, int P, int SW, int ATM>
 static int launch_wthin(const CUtensorMap& tmX, const CUtensorMap& tmG, WThinArgs& a, cudaStream_t stream) {
-    auto kern = wgrad_thin_kernel<CIN, P, SW>;
+    auto kern = wgrad_thin_kernel<CIN, P, SW, ATM>;
     static bool attr = false;
     static WThinPlan plans[4];   // by Cout / 8 -> index 0..3 (8, 16, 32, 64)
     static bool have[4] = {};
@@ -547,7 +601,8 @@ static int launch_wthin(const CUtensorMap& tmX, const CUtensorMap& tmG, WThinArg
         int cap = e ? atoi(e) : 2;
         cap = cap < 1 ? 1 : cap > 2 ? 2 : cap;
         const int nacc = CIN == 8 ? 4 : 3;
-        const int ncols = nacc * a.Npad <= 64 ? 64 : nacc * a.Npad <= 128 ? 128 : 256;
+        const int need = nacc * a.Npad + (ATM ? 64 * P : 0);
+        const int ncols = need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
         if (cap > 512 / ncols) cap = 512 / ncols;
         WThinPlan pl = {0, 0, 0};
         for (int occ = cap; occ >= 1 && pl.occ == 0; --occ) {
@@ -564,8 +619,8 @@ static int launch_wthin(const CUtensorMap& tmX, const CUtensorMap& tmG, WThinArg
             cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, kern, kThreads, pl.smem);
             cudaFuncAttributes fa;
             cudaFuncGetAttributes(&fa, kern);
-            fprintf(stderr, "pgk_wgrad_thin<%d,%d,%d> Cout %d: plan occ %d raw %d smem %d | runtime says %d blocks/SM (%s), regs %d\n",
-                    CIN, P, SW, a.Cout, pl.occ, pl.raw, pl.smem, got, cudaGetErrorString(oe), fa.numRegs);
+            fprintf(stderr, "pgk_wgrad_thin<%d,%d,%d,%d> Cout %d: plan occ %d raw %d smem %d | runtime says %d blocks/SM (%s), regs %d\n",
+                    CIN, P, SW, ATM, a.Cout, pl.occ, pl.raw, pl.smem, got, cudaGetErrorString(oe), fa.numRegs);
             cudaGetLastError();
         }
         if (pl.occ == 0) {
@@ -664,8 +719,17 @@ extern "C" int pgk_wgrad_thin(const void* x, long long x_ps, const void* g, long
         const char* e = getenv("PGK_WTHIN_SW128");
         sw128 = e ? atoi(e) != 0 : 0;
     }
+    // PGK_WTHIN_ATM=1 (experimental, see the kernel header): Cin = 8 with the stacked A operand in tensor memory
+    static int watm = -1;
+    if (watm < 0) {
+        const char* e = getenv("PGK_WTHIN_ATM");
+        watm = e ? atoi(e) != 0 : 0;
+    }
+    if (watm && Cin == 8 && Pr == 1) rc = launch_wthin<8, 1, 0, 1>(tmX, tmG, a, st);
+    if (watm && Cin == 8 && Pr == 2) rc = launch_wthin<8, 2, 0, 1>(tmX, tmG, a, st);
 #define PGK_WTHIN_CASE(C_, P_) \
-    if (Cin == C_ && Pr == P_) rc = sw128 ? launch_wthin<C_, P_, 1>(tmX, tmG, a, st) : launch_wthin<C_, P_, 0>(tmX, tmG, a, st);
+    if (rc == PGK_ERR_ARG && Cin == C_ && Pr == P_) \
+        rc = sw128 ? launch_wthin<C_, P_, 1, 0>(tmX, tmG, a, st) : launch_wthin<C_, P_, 0, 0>(tmX, tmG, a, st);
     PGK_WTHIN_CASE(8, 1) PGK_WTHIN_CASE(16, 1) PGK_WTHIN_CASE(32, 1)
     PGK_WTHIN_CASE(8, 2) PGK_WTHIN_CASE(16, 2) PGK_WTHIN_CASE(32, 2)
     PGK_WTHIN_CASE(8, 3) PGK_WTHIN_CASE(16, 3) PGK_WTHIN_CASE(32, 3)

@@ -75,6 +75,14 @@ for c in c4 c3; do
   PGK_THIN_ATM=1 timeout 300 python tools/shape_profile.py --config $c --steps 3 --warmup 2 --json $OUT/shapes_${c}_atm.json > $OUT/shapes_${c}_atm.txt 2>&1; head -1 $OUT/shapes_${c}_atm.txt
 done
 }
+part_watm() {
+stamp "experimental: stacked thin weight gradient (Cin = 8) with A in tensor memory (PGK_WTHIN_ATM=1): numerics, timing A/B"
+PGK_WTHIN_ATM=1 PGK_THIN_DEBUG=1 timeout 300 python tools/tc_test.py wthin > $OUT/wthin_atm_numerics.txt 2>&1; echo "rc=$?" >> $OUT/wthin_atm_numerics.txt; grep -v "^pgk_" $OUT/wthin_atm_numerics.txt | tail -12
+for w in 0 1; do
+  PGK_WTHIN_ATM=$w timeout 300 python tools/thin_bench.py 1 12 > $OUT/thin_bench_watm$w.txt 2>&1; echo "-- PGK_WTHIN_ATM=$w"; cat $OUT/thin_bench_watm$w.txt
+done
+PGK_WTHIN_ATM=1 timeout 300 python tools/shape_profile.py --config c4 --steps 3 --warmup 2 --json $OUT/shapes_c4_watm.json > $OUT/shapes_c4_watm.txt 2>&1; head -1 $OUT/shapes_c4_watm.txt
+}
 part_sw128() {
 stamp "experimental: thin weight gradient with SWIZZLE_128B transposed tiles (PGK_WTHIN_SW128=1): numerics, then timing A/B"
 PGK_WTHIN_SW128=1 timeout 300 python tools/tc_test.py wthin > $OUT/wthin_sw128_numerics.txt 2>&1; tail -12 $OUT/wthin_sw128_numerics.txt
@@ -179,7 +187,7 @@ cat $OUT/eager_bar.jsonl
 }
 case "$PART" in
   A) part_validate; part_fp16; part_wgrad16; part_pdl ;;
-  B) part_probe; part_shapes; part_atm; part_sw128; part_red4; part_relayout ;;
+  B) part_probe; part_shapes; part_atm; part_watm; part_sw128; part_red4; part_relayout ;;
   C) part_nt; part_switches; part_prefetch; part_eager ;;
   *) echo "usage: $0 A|B|C"; exit 2 ;;
 esac
