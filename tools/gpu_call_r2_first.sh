@@ -68,6 +68,7 @@ part_atm() {
 stamp "experimental: thin conv with A in tensor memory (PGK_THIN_ATM=1; after the probe's part 4): numerics, kernel timing, c4 / c3 step A/B"
 timeout 300 python tools/tc_test.py thin1 > $OUT/thin1_default.txt 2>&1; tail -3 $OUT/thin1_default.txt
 PGK_THIN_ATM=1 PGK_THIN_DEBUG=1 timeout 300 python tools/tc_test.py thin1 > $OUT/thin1_atm.txt 2>&1; echo "rc=$?" >> $OUT/thin1_atm.txt; grep -v "^pgk_" $OUT/thin1_atm.txt | tail -18
+PGK_THIN_ATM=1 timeout 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k "thin_conv or pixelnorm" > $OUT/thin_atm_pytest.log 2>&1; tail -3 $OUT/thin_atm_pytest.log
 for atm in 0 1; do
   PGK_THIN_ATM=$atm timeout 300 python tools/thin_bench.py 1 4 > $OUT/thin_bench_atm$atm.txt 2>&1; echo "-- PGK_THIN_ATM=$atm"; cat $OUT/thin_bench_atm$atm.txt
 done
@@ -78,6 +79,7 @@ done
 part_watm() {
 stamp "experimental: stacked thin weight gradient (Cin = 8) with A in tensor memory (PGK_WTHIN_ATM=1): numerics, timing A/B"
 PGK_WTHIN_ATM=1 PGK_THIN_DEBUG=1 timeout 300 python tools/tc_test.py wthin > $OUT/wthin_atm_numerics.txt 2>&1; echo "rc=$?" >> $OUT/wthin_atm_numerics.txt; grep -v "^pgk_" $OUT/wthin_atm_numerics.txt | tail -12
+PGK_WTHIN_ATM=1 timeout 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k "wgrad" > $OUT/wthin_atm_pytest.log 2>&1; tail -3 $OUT/wthin_atm_pytest.log
 for w in 0 1; do
   PGK_WTHIN_ATM=$w timeout 300 python tools/thin_bench.py 1 12 > $OUT/thin_bench_watm$w.txt 2>&1; echo "-- PGK_WTHIN_ATM=$w"; cat $OUT/thin_bench_watm$w.txt
 done
