@@ -384,6 +384,11 @@ def main():
         'clocks': clocks,
         'roofline': roof,
     }
+    switches = {k: v for k, v in sorted(os.environ.items()) if k.startswith('PGK_')}
+    if switches or args.graphs or args.prefetch:
+        # a line measured with non-default tuning switches says so (A/B runs; the driver's run has none)
+        out['config']['switches'] = dict(switches, **({'--graphs': '1'} if args.graphs else {}),
+                                         **({'--prefetch': '1'} if args.prefetch else {}))
     if not args.no_cpu_baseline and world == 1:      # the CPU leg is reported at N = 1 only
         base, _, _, _ = cpu_reference_leg(cfg, 3, 1, budget_s=20.0)
         out['cpu_baseline'] = base
