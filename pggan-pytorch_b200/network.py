@@ -115,7 +115,20 @@ class _EngineOwner(nn.Module):
     def __getstate__(self):
         st = self.__dict__.copy()
         st.pop('_engine', None)
+        st.pop('_param_list', None)
         return st
+
+    def zero_grad(self, set_to_none=True):
+        """The loss functions call this three times per iteration (reference wgan_gp_loss.py:42-43,69), and
+        nn.Module.zero_grad walks the whole module tree each time (~0.4 ms for these models, of an iteration whose host
+        side takes a few milliseconds).  The parameter set of these modules never changes: the list is built once."""
+        if not set_to_none:
+            return super().zero_grad(set_to_none=False)
+        ps = self.__dict__.get('_param_list')
+        if ps is None:
+            ps = self.__dict__['_param_list'] = list(self.parameters())
+        for p in ps:
+            p.grad = None
 
     @property
     def planes(self):
