@@ -58,7 +58,7 @@ struct WThinArgs {
 // ("atoms") `atom` bytes apart -- instead of un-swizzled 8 x 16-byte core matrices.  Same buffers, same sizes, same
 // barriers; only the stmatrix destinations and the MMA descriptors differ.
 //
-// ATM = 1 (PGK_WTHIN_ATM=1, experimental, Cin = 8 only): the stacked A operand lives in TENSOR MEMORY.  The four ring
+// ATM = 1 (PGK_WTHIN_ATM=1, experimental): the A operand lives in TENSOR MEMORY.  Cin = 8 (the stacked chain):  The four ring
 // slots of 32 accumulator rows are the four 32-lane quarters of tensor memory, and a quarter belongs to one warp: the
 // transposer warp (input row & 3) gathers its row straight from the raw [pixel][8 channels] buffer -- lane = (kx, ci)
 // reads X[p + kx][ci] for p = 0..127, conflict-free 16-bit loads -- packs pixel pairs and writes them with tcgen05.st
@@ -69,7 +69,12 @@ struct WThinArgs {
 template <int CIN, int P, int SW, int ATM>
 __global__ void __launch_bounds__(kThreads, 2)
 wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WThinArgs a) {
-    static_assert(!ATM || (CIN == 8 && SW == 0), "the tensor-memory A operand exists for the stacked Cin = 8 flavour");
+    // Cin = 16 / 32 with ATM (one plane only): every input row is one 128-lane A tile of its own (four of them, 64
+    // columns each, after the three accumulators), with the rows ordered (channel group, kx, channel): lane quarter cg
+    // = warp cg gathers from channel-group plane cg alone, conflict-free like the 8-channel case, and the flush maps
+    // lane -> (cg, kx, ci) back.  Lanes 24 (ones row, quarter 0) .. 31 of a quarter and the quarters beyond Cin / 8 hold
+    // zeros (written once at start-up).
+    static_assert(!ATM || (SW == 0 && (CIN == 8 || P == 1)), "tensor-memory A: no SW128, one plane for Cin >= 16");
     // row groups of XT3: 3 * CG shifted copies + one group whose first row is all ones (the bias-gradient row)
     constexpr int CG = CIN / 8, XG = 3 * CG;
     constexpr uint32_t xt_plane = (XG + 1) * kGrp, xt_buf = P * xt_plane;
@@ -138,7 +143,8 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     fence_proxy_async();
     const unsigned nacc = STACK ? 4u : 3u;
     // ATM: the A operand (128 pixels = 64 columns per plane) sits after the accumulators
-    const unsigned ncols = ATM ? (nacc * a.Npad + 64u * P <= 128 ? 128u : nacc * a.Npad + 64u * P <= 256 ? 256u : 512u)
+    constexpr unsigned kAtmCols = STACK ? 64u * P : 256u;   // stacked: one tile per plane; else four tiles (ring slots)
+    const unsigned ncols = ATM ? (nacc * a.Npad + kAtmCols <= 128 ? 128u : nacc * a.Npad + kAtmCols <= 256 ? 256u : 512u)
                                : (nacc * a.Npad <= 64 ? 64u : nacc * a.Npad <= 128 ? 128u : 256u);
     if (warp == 5) tmem_alloc(tptr, ncols);
     fence_before();
@@ -146,6 +152,18 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tptr - raw));
     pgk_pdl_enter();   // everything above touched shared / tensor memory and the kernel parameters only
+    if constexpr (ATM != 0 && !STACK) {
+        // the four A tiles start out as zeros: lanes that never receive data must still be finite for the MMAs
+        if (warp < 4) {
+            const uint32_t t0 = tmem + 3u * a.Npad + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+            for (int c = 0; c < 256; c += 8) tmem_zero8(t0 + c);
+            tmem_st_wait();
+        }
+        fence_before();
+        __syncthreads();
+        fence_after();
+    }
 
     // busy polling by the two single-warp roles takes issue slots from the transposer warps of the same SM
     // sub-partitions; try_wait suspends instead
@@ -326,6 +344,11 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     const uint32_t later = rows_done > 0 ? 1u : 0u;
                     auto issue = [&](int ky, int ks) {
                         const uint32_t d = tmem + ky * a.Npad;
+                        if constexpr (ATM != 0) {   // (Cin >= 16: one plane) A tile of input row gx + ky
+                            mma_bf16_ts(d, tmem + 3u * a.Npad + ((gx + ky) & 3u) * 64u + (uint32_t)(ks * 8),
+                                        bd0 + (uint32_t)(ks * 16), idesc, ks == 0 ? later : 1u);
+                            return;
+                        }
 #pragma unroll
                         for (int pi = 0; pi < P; ++pi) {
 #pragma unroll
@@ -406,9 +429,13 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     if (ATM) {
                         // the warp that owns ring slot b (= lane quarter b of tensor memory) writes the whole row:
                         // lane = kx * 8 + ci gathers its channel of the kx-shifted pixels, lane 24 is the ones row
-                        if (warp == b) {
-                            const uint32_t ta = tmem + 4u * a.Npad + ((uint32_t)(warp * 32) << 16);
-                            const uint32_t lsrc = src0 + (uint32_t)(lane >> 3) * 16u + (uint32_t)(lane & 7) * 2u;
+                        // stacked (Cin = 8): the warp that owns ring slot b writes the row into its lane quarter;
+                        // Cin >= 16: warp cg writes channel group cg of the row into tile b (columns b * 64 ..)
+                        if (STACK ? warp == b : warp < CG) {
+                            const uint32_t ta = STACK ? tmem + 4u * a.Npad + ((uint32_t)(warp * 32) << 16)
+                                                      : tmem + 3u * a.Npad + (uint32_t)b * 64u + ((uint32_t)(warp * 32) << 16);
+                            const uint32_t lsrc = src0 + (STACK ? 0u : (uint32_t)warp * kCgBytes) + (uint32_t)(lane >> 3) * 16u +
+                                                  (uint32_t)(lane & 7) * 2u;
                             for (int p = 0; p < P; ++p) {
 #pragma unroll
                                 for (int c = 0; c < 64; c += 8) {   // 8 columns = 16 pixels
@@ -421,7 +448,8 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                                             asm volatile("ld.shared.u16 %0, [%1];" : "=r"(lo) : "r"(ad));
                                             asm volatile("ld.shared.u16 %0, [%1];" : "=r"(hi) : "r"(ad + 16u));
                                         }
-                                        v[j] = lane < 24 ? (lo | (hi << 16)) : (lane == 24 && p == 0) ? one16 : 0u;
+                                        v[j] = lane < 24 ? (lo | (hi << 16))
+                                                         : (lane == 24 && p == 0 && (STACK || warp == 0)) ? one16 : 0u;
                                     }
                                     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::
                                                  "r"(ta + (uint32_t)(p * 64 + c)), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
@@ -512,11 +540,12 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             }
         } else {
             const int m = warp * 32 + lane;
-            const bool valid = m < 3 * CIN;
-            const int kx = m / CIN, ci = m - kx * CIN;
+            // ATM: rows are ordered (channel group = warp, kx, channel), 24 per lane quarter, row 24 of quarter 0 = ones
+            const bool valid = ATM ? (warp < CG && lane < 24) : m < 3 * CIN;
+            const int kx = ATM ? lane >> 3 : m / CIN, ci = ATM ? warp * 8 + (lane & 7) : m - kx * CIN;
             for (int ky = 0; ky < 3; ++ky) {
                 float* drow = a.dwp + (long long)((ky * 3 + kx) * a.cin_total + a.c0 + ci) * a.Cout;
-                const bool bias_row = a.db && ky == 1 && m == 3 * CIN;   // the ones row against G of the same row
+                const bool bias_row = a.db && ky == 1 && (ATM ? m == 24 : m == 3 * CIN);   // the ones row against G of the same row
                 for (int c = 0; c < a.Npad; c += 16) {
                     float v[16];
                     tmem_ld16(trow + ky * a.Npad + c, v);
@@ -601,7 +630,7 @@ static int launch_wthin(const CUtensorMap& tmX, const CUtensorMap& tmG, WThinArg
         int cap = e ? atoi(e) : 2;
         cap = cap < 1 ? 1 : cap > 2 ? 2 : cap;
         const int nacc = CIN == 8 ? 4 : 3;
-        const int need = nacc * a.Npad + (ATM ? 64 * P : 0);
+        const int need = nacc * a.Npad + (ATM ? (CIN == 8 ? 64 * P : 256) : 0);
         const int ncols = need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
         if (cap > 512 / ncols) cap = 512 / ncols;
         WThinPlan pl = {0, 0, 0};
@@ -727,6 +756,8 @@ extern "C" int pgk_wgrad_thin(const void* x, long long x_ps, const void* g, long
     }
     if (watm && Cin == 8 && Pr == 1) rc = launch_wthin<8, 1, 0, 1>(tmX, tmG, a, st);
     if (watm && Cin == 8 && Pr == 2) rc = launch_wthin<8, 2, 0, 1>(tmX, tmG, a, st);
+    if (watm && Cin == 16 && Pr == 1) rc = launch_wthin<16, 1, 0, 1>(tmX, tmG, a, st);
+    if (watm && Cin == 32 && Pr == 1) rc = launch_wthin<32, 1, 0, 1>(tmX, tmG, a, st);
 #define PGK_WTHIN_CASE(C_, P_) \
     if (rc == PGK_ERR_ARG && Cin == C_ && Pr == P_) \
         rc = sw128 ? launch_wthin<C_, P_, 1, 0>(tmX, tmG, a, st) : launch_wthin<C_, P_, 0, 0>(tmX, tmG, a, st);

@@ -144,3 +144,61 @@ def test_stacked_weight_gradient_tensor_memory_gather(cout):
             ref[(ky * 3 + kx) * cin:(ky * 3 + kx + 1) * cin] = np.einsum('hwc,hwo->co', xp[ky:ky + H, kx:kx + W], gy)
     assert np.array_equal(dw, ref)
     assert np.array_equal(db, gy.sum(axis=(0, 1)))
+
+
+@pytest.mark.parametrize('cin,cout', [(16, 16), (32, 32), (32, 64)])
+def test_wide_channel_weight_gradient_tensor_memory_row_order(cin, cout):
+    """Cin = 16 / 32 with PGK_WTHIN_ATM: one 128-lane A tile per input row, rows ordered (channel group, kx, channel) --
+    lane quarter cg is written by warp cg from channel-group plane cg -- three accumulators D[ky], flush lane -> (cg, kx,
+    ci)."""
+    rng = np.random.default_rng(cin + cout)
+    H, W, CG = 6, 128, cin // 8
+    x = rng.integers(-3, 4, size=(H, W, cin)).astype(np.float64)
+    gy = rng.integers(-2, 3, size=(H, W, cout)).astype(np.float64)
+    tiles = np.zeros((4, 128, 128))         # [ring slot][lane][pixel], zeroed once
+    acc = np.zeros((3, 128, cout))
+
+    def raw_row(j):                          # [cg][130 pixels][8]
+        y = j - 1
+        buf = np.zeros((CG, 130, 8))
+        if 0 <= y < H:
+            buf[:, 1:129, :] = x[y].reshape(W, CG, 8).transpose(1, 0, 2)
+        return buf
+
+    def write_tile(gx):
+        buf, b = raw_row(gx), gx & 3
+        for warp in range(CG):
+            for lane in range(32):
+                for p in range(128):
+                    if lane < 24:
+                        tiles[b, warp * 32 + lane, p] = buf[warp, p + (lane >> 3), lane & 7]
+                    else:
+                        tiles[b, warp * 32 + lane, p] = 1.0 if (lane == 24 and warp == 0) else 0.0
+
+    gx = 0
+    write_tile(0)
+    write_tile(1)
+    for i in range(H):
+        write_tile(gx + 2)
+        for ky in range(3):
+            acc[ky] += tiles[(gx + ky) & 3] @ gy[i]
+        gx += 1
+    dw = np.zeros((9 * cin, cout))
+    db = np.zeros(cout)
+    for warp in range(4):
+        for lane in range(32):
+            m = warp * 32 + lane
+            valid = warp < CG and lane < 24
+            kx, ci = lane >> 3, warp * 8 + (lane & 7)
+            for ky in range(3):
+                if valid:
+                    dw[(ky * 3 + kx) * cin + ci] += acc[ky, m]
+                elif ky == 1 and m == 24:
+                    db += acc[ky, m]
+    ref = np.zeros((9 * cin, cout))
+    xp = np.pad(x, ((1, 1), (1, 1), (0, 0)))
+    for ky in range(3):
+        for kx in range(3):
+            ref[(ky * 3 + kx) * cin:(ky * 3 + kx + 1) * cin] = np.einsum('hwc,hwo->co', xp[ky:ky + H, kx:kx + W], gy)
+    assert np.array_equal(dw, ref)
+    assert np.array_equal(db, gy.sum(axis=(0, 1)))
