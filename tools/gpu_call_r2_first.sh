@@ -7,9 +7,11 @@
 #                                                                    with the largest expected effect: fp16 forward
 #                                                                    operands (+ the half-plane weight gradient) on c2,
 #                                                                    programmatic dependent launch on c4 / c3 / c1
-#   gpurun --timeout 1500 -- 'bash tools/gpu_call_r2_first.sh B'   hardware probe (tcgen05 operand layouts, A in tensor
-#                                                                    memory, tcgen05.cp), thin weight gradient SW128,
-#                                                                    vector reductions, per-shape profiles of every config
+#   gpurun --timeout 2400 -- 'bash tools/gpu_call_r2_first.sh B'   hardware probe (tcgen05 operand layouts, A in tensor
+#                                                                    memory, tcgen05.cp), per-shape profiles of every
+#                                                                    config, then the thin kernels' flavours: A in tensor
+#                                                                    memory (conv, weight gradient), SW128, vector
+#                                                                    reductions, tiled weight re-layout
 #   gpurun --timeout 1500 -- 'bash tools/gpu_call_r2_first.sh C'   tile-width / wave A/Bs, look-ahead H2D copy, and the
 #                                                                    "GPU reference bar" of SURVEY.md 8(d) (PyTorch eager)
 # Outputs land in gpurun_out/r2_<part>/.
