@@ -20,9 +20,29 @@ class FusedAdam(torch.optim.Optimizer):
         if weight_decay != 0 or amsgrad:
             raise NotImplementedError('FusedAdam implements the reference configuration: no weight decay, no amsgrad')
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False))
-        self._host = None     # pinned staging for the pointer table
-        self._dev = None
+        # Pointer tables go host -> device asynchronously, and the host runs ahead of the GPU (no sync per step): a
+        # ring of pinned staging buffers, each guarded by an event recorded after its copy, so that a slot is never
+        # rewritten while the DMA that reads it is still pending.  The device table is allocated per launch from
+        # the caching allocator (stream-ordered reuse).
+        self._ring = []       # [pinned host table, copy-done event or None]
+        self._slot = 0
         self._keep = []       # gradient buffers of the launch in flight
+
+    RING = 8
+
+    def _stage(self, n):
+        """The next pinned staging table with room for n rows, safe to overwrite."""
+        if len(self._ring) < self.RING:
+            self._ring.append([torch.empty((max(64, n), 8), dtype=torch.int64).pin_memory(), None])
+            self._slot = len(self._ring) - 1
+        else:
+            self._slot = (self._slot + 1) % self.RING
+        host, done = self._ring[self._slot]
+        if done is not None:
+            done.synchronize()          # returns at once unless the host is more than RING launches ahead
+        if host.shape[0] < n:
+            host = self._ring[self._slot][0] = torch.empty((n, 8), dtype=torch.int64).pin_memory()
+        return host
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -32,7 +52,7 @@ class FusedAdam(torch.optim.Optimizer):
                 loss = closure()
         for group in self.param_groups:
             beta1, beta2 = group['betas']
-            rows, max_numel, dev, keep = [], 0, None, []
+            rows, max_numel, dev, keep, updated = [], 0, None, [], []
             for p in group['params']:
                 if p.grad is None:
                     continue
@@ -55,19 +75,23 @@ class FusedAdam(torch.optim.Optimizer):
                              struct.unpack('<I', struct.pack('<f', step_size))[0],
                              struct.unpack('<I', struct.pack('<f', inv_sqrt_bc2))[0], 0))
                 keep.append(g)       # the gradient buffer must outlive the asynchronous launch
+                updated.append(p)
                 max_numel = max(max_numel, p.numel())
                 dev = p.device
             if not rows:
                 continue
             _lib.check_device(dev)
             n = len(rows)
-            if self._host is None or self._host.shape[0] < n or self._dev.device != dev:
-                cap = max(64, n)
-                self._host = torch.empty((cap, 8), dtype=torch.int64).pin_memory()
-                self._dev = torch.empty((cap, 8), dtype=torch.int64, device=dev)
-            self._host[:n] = torch.from_numpy(np.array(rows, dtype=np.uint64).view(np.int64))
-            self._dev[:n].copy_(self._host[:n], non_blocking=True)
-            _lib.call('pgk_adam_multi', self._dev.data_ptr(), n, max_numel, float(beta1), float(beta2),
+            host = self._stage(n)
+            host[:n] = torch.from_numpy(np.array(rows, dtype=np.uint64).view(np.int64))
+            table = torch.empty((n, 8), dtype=torch.int64, device=dev)
+            table.copy_(host[:n], non_blocking=True)
+            self._ring[self._slot][1] = torch.cuda.Event()
+            self._ring[self._slot][1].record()
+            _lib.call('pgk_adam_multi', table.data_ptr(), n, max_numel, float(beta1), float(beta2),
                       float(group['eps']))
+            # the kernel writes through raw pointers: tell autograd (and every cache keyed on Tensor._version, e.g.
+            # engine.ConvW's re-laid weights) that the parameters changed
+            torch.autograd.graph.increment_version(updated)
             self._keep = keep
         return loss

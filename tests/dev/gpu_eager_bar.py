@@ -18,11 +18,16 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+sys.path.insert(0, os.path.join(ROOT, 'baseline'))
 import bench  # noqa: E402
 import pggan_oracle as O  # noqa: E402
+import ref_harness as R  # noqa: E402
 
 
 def run(cfg, steps, warmup, tf32, n, device='cuda'):
+    if R.available():      # the unmodified reference's own Trainer.train() (baseline/_ref)
+        ips, ms, _, _ = R.time_train(cfg['res'], cfg['ch'], cfg['depth'], cfg['alpha'], n, steps, warmup, device, tf32)
+        return ips, ms
     torch.backends.cudnn.allow_tf32 = tf32
     torch.backends.cuda.matmul.allow_tf32 = tf32
     torch.backends.cudnn.benchmark = True
@@ -91,7 +96,9 @@ def main():
             print(json.dumps({'tool': 'gpu_eager_bar', 'config': name, 'depth': cfg['depth'], 'alpha': cfg['alpha'],
                               'batch': n, 'config_batch': cfg['n'], 'precision': 'tf32' if tf32 else 'fp32',
                               'images_per_sec': ips, 'ms_per_step': ms,
-                              'what': "the reference's arithmetic (oracle) in PyTorch eager on the GPU"}), flush=True)
+                              'what': ("the unmodified reference's Trainer.train() (baseline/_ref) in PyTorch eager on the GPU"
+                                       if R.available() else
+                                       "the reference's arithmetic (oracle) in PyTorch eager on the GPU")}), flush=True)
             torch.cuda.empty_cache()
 
 

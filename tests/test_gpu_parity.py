@@ -63,16 +63,20 @@ def test_g_step_golden(gpu, case):
         assert rel_err(grads[k], v) < TOL, k
 
 
-def test_two_trainer_iterations_golden(gpu):
-    """Trainer.train() twice with torch Adam(betas=(0,.99)) -- parameters match the reference's after the same."""
+@pytest.mark.parametrize('fused', [False, True])
+def test_two_trainer_iterations_golden(gpu, fused):
+    """Trainer.train() twice with Adam(betas=(0,.99)) -- parameters match the reference's after the same.
+    fused=True: pg.FusedAdam, which updates the parameters through raw pointers -- the second iteration must see the
+    first one's update in every re-laid weight operand (engine.ConvW caches them by Tensor._version)."""
     g = load_trainer()
     pg = gpu['pg']
+    Adam = pg.FusedAdam if fused else torch.optim.Adam
     g2 = dict(g, pg=g['G0'], pd=g['D0'])
     G, D = gpu['build_pair'](g2)
     G.depth = D.depth = g['depth']
     G.alpha = D.alpha = g['alpha']
-    opt_g = torch.optim.Adam(G.parameters(), 1e-3, betas=(0.0, 0.99))
-    opt_d = torch.optim.Adam(D.parameters(), 1e-3, betas=(0.0, 0.99))
+    opt_g = Adam(G.parameters(), 1e-3, betas=(0.0, 0.99))
+    opt_d = Adam(D.parameters(), 1e-3, betas=(0.0, 0.99))
     lats = iter(list(g['latents']))
     t = pg.Trainer(D, G, pg.wgan_gp_D_loss, pg.wgan_gp_G_loss, opt_d, opt_g, None, iter(list(g['reals'])),
                    lambda: next(lats))
@@ -316,6 +320,35 @@ def test_fused_adam_matches_torch_adam(gpu):
     for a, b in zip(pa, pb):
         assert rel_err(b, a) < 1e-6
     assert ob.state[pb[2]]['step'] == oa.state[pa[2]]['step'] == 3
+
+
+def test_fused_adam_many_unsynchronised_steps(gpu):
+    """50 FusedAdam steps enqueued without a single host synchronisation (the host runs far ahead of the GPU: a slow
+    kernel is queued first), fresh gradient tensors and a different learning rate every step, against torch Adam.
+    The pointer / step-size table of step i must not be overwritten by step i+k before its copy has run."""
+    pg = gpu['pg']
+    torch.manual_seed(1)
+    shapes = [(128, 64, 3, 3), (128,), (3, 128, 1, 1), (1, 512)]
+    pa = [torch.nn.Parameter(torch.randn(s, device='cuda')) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa = torch.optim.Adam(pa, 1e-3, betas=(0.0, 0.99))
+    ob = pg.FusedAdam(pb, 1e-3, betas=(0.0, 0.99))
+    grads = [[torch.randn_like(a) * (1.0 + it) for a in pa] for it in range(50)]
+    big = torch.randn(8192, 8192, device='cuda')
+    torch.cuda.synchronize()
+    for _ in range(20):
+        big = big @ big * 1e-4            # ~20 x 1 ms of queued GPU work: every step below is enqueued behind it
+    for it in range(50):
+        for a, b, g in zip(pa, pb, grads[it]):
+            a.grad, b.grad = g, g.clone()
+        for o in (oa, ob):
+            o.param_groups[0]['lr'] = 1e-3 * (1 + it % 7)
+        oa.step()
+        ob.step()
+        assert all(b._version > 0 for b in pb)
+    torch.cuda.synchronize()
+    for a, b in zip(pa, pb):
+        assert rel_err(b, a) < 1e-6
 
 
 def test_cuda_graph_replay_equals_eager(gpu):

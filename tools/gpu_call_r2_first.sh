@@ -193,6 +193,7 @@ case "$PART" in
   A) part_validate; part_fp16; part_wgrad16; part_pdl ;;
   B) part_probe; part_shapes; part_atm; part_watm; part_sw128; part_red4; part_relayout ;;
   C) part_nt; part_switches; part_prefetch; part_eager ;;
-  *) echo "usage: $0 A|B|C"; exit 2 ;;
+  ALL) part_validate; part_eager; part_fp16; part_wgrad16; part_probe; part_shapes; part_red4; part_atm; part_watm; part_sw128; part_relayout ;;
+  *) echo "usage: $0 A|B|C|ALL"; exit 2 ;;
 esac
 stamp "done"
