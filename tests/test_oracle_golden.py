@@ -109,3 +109,68 @@ def test_real_preparation_matches_reference():
         for d, ref in zip(z['in%d' % i], z['out%d' % i]):
             got = O.prepare_real(d, float(alpha), rin, rout)
             assert got.dtype == np.float32 and np.array_equal(got, ref), i
+
+
+@pytest.mark.parametrize('name', ['d4_a05_n2', 'd5_c1_n2'])
+def test_oracle_at_baseline_widths_matches_reference(name):
+    """The oracle on BASELINE's own networks (full 1024x1024 model at depth 4 with its 512-channel K = 4608 layers;
+    the 1-channel 128x128 model at depth 5) against compact vectors of the reference executed at these widths
+    (tests/golden/make_golden_full.py): parameters / inputs regenerated from the same seeds, every loss and every
+    parameter gradient (norm + up to 2048 sampled entries per tensor)."""
+    import numpy as np
+    from _util import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    import make_golden_full as MF
+    z = np.load(os.path.join(GOLDEN, 'full_%s.npz' % name))
+    cfg = MF.CONFIGS[name]
+    res, ch, depth, alpha, n, seed = cfg
+    pgp, pdp = O.make_generator_params(res, ch, seed=MF.G_SEED), O.make_discriminator_params(res, ch, seed=MF.D_SEED)
+    z1, z2, real, mix = MF.inputs(cfg)
+    nb = O.n_blocks_for(res)
+    cost, rl, fl, gd = O.d_step_grads(pdp, pgp, real, z1, mix, depth, alpha, nb)
+    gcost, gg = O.g_step_grads(pgp, pdp, z2, depth, alpha, nb)
+    assert rel_err(cost, z['d_cost']) < TOL and rel_err(rl, z['d_real_loss']) < TOL and rel_err(fl, z['d_fake_loss']) < TOL
+    assert rel_err(gcost, z['g_cost']) < TOL
+
+    def check(prefix, grads):
+        keys = sorted(k[len(prefix):-5] for k in z.files if k.startswith(prefix) and k.endswith('/norm'))
+        assert set(keys) == set(grads)
+        for k in keys:
+            t = grads[k].reshape(-1)
+            key = prefix + k
+            assert rel_err(t[MF.sample_index(key, t.numel())], z[key + '/samples']) < 5e-4, key
+            assert abs(float(t.double().norm()) / float(z[key + '/norm']) - 1) < 5e-4, key
+    check('Dgrad.', gd)
+    check('Ggrad.', gg)
+
+
+def test_bf16_oracle_without_rounding_is_the_oracle():
+    """oracle/pggan_oracle_bf16.py restructures the forward graphs (folded c, split constant channel, rounding nodes
+    whose backward is again a rounding node).  With the roundings switched off it must BE the oracle: same losses and
+    gradients, including the penalty's double backward through the rounding nodes."""
+    import pggan_oracle_bf16 as B
+    for (res, ch, fb, fm, lat, n, depth, alpha) in [(16, 3, 128, 32, 32, 4, 2, 0.3), (16, 3, 128, 32, 32, 4, 0, 1.0),
+                                                    (32, 1, 256, 32, 32, 3, 3, 1.0)]:
+        pgp = O.make_generator_params(res, ch, fmap_base=fb, fmap_max=fm, latent_size=lat, seed=3)
+        pdp = O.make_discriminator_params(res, ch, fmap_base=fb, fmap_max=fm, seed=4)
+        nb, r = O.n_blocks_for(res), 4 * 2 ** depth
+        gen = torch.Generator().manual_seed(5)
+        z1, z2 = torch.randn(n, lat, generator=gen), torch.randn(n, lat, generator=gen)
+        real, mix = torch.randn(n, ch, r, r, generator=gen), torch.rand(n, 1, generator=gen)
+        c0, rl0, fl0, gd0 = O.d_step_grads(pdp, pgp, real, z1, mix, depth, alpha, nb)
+        gc0, gg0 = O.g_step_grads(pgp, pdp, z2, depth, alpha, nb)
+        B.ROUND = False
+        try:
+            c1, rl1, fl1, gd1, _ = B.d_step_grads(pdp, pgp, real, z1, mix, depth, alpha, nb)
+            gc1, gg1 = B.g_step_grads(pgp, pdp, z2, depth, alpha, nb)
+        finally:
+            B.ROUND = True
+        assert rel_err(c1, c0) < TOL and rel_err(gc1, gc0) < TOL and rel_err(rl1, rl0) < TOL and rel_err(fl1, fl0) < TOL
+        assert set(gd1) == set(gd0) and set(gg1) == set(gg0)
+        for k in gd0:
+            assert rel_err(gd1[k], gd0[k]) < TOL, k
+        for k in gg0:
+            assert rel_err(gg1[k], gg0[k]) < TOL, k
+        # and with them on it is a different (coarser) arithmetic
+        c2, _, _, gd2, _ = B.d_step_grads(pdp, pgp, real, z1, mix, depth, alpha, nb)
+        assert max(rel_err(gd2[k], gd0[k]) for k in gd0) > 1e-3
