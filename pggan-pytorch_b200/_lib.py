@@ -11,7 +11,8 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libpgk.so')
+# PGK_LIB: another build of the same library (A/B runs, e.g. the programmatic-dependent-launch build libpgk_pdl.so)
+LIB_PATH = os.environ.get('PGK_LIB') or os.path.join(_HERE, 'csrc', 'libpgk.so')
 
 P, I, L, F = c_void_p, c_int, c_longlong, c_float
 
