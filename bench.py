@@ -44,18 +44,7 @@ def nf(stage, fmap_base=4096, fmap_max=512):
 def flops_per_image(depth, ch, fade):
     """Algorithmic FLOPs of one iteration per image: 2*(14*MAC_D + 4*MAC_G) (SURVEY.md 8d / BASELINE.md 3), the
     4x4 first-G / last-D convs counted as the dense GEMMs they are."""
-    mac_g = nf(0) * nf(1) * 16 + 16 * nf(1) * nf(1) * 9
-    mac_d = 16 * nf(1) * nf(1) * 9 + 16 * nf(1) * nf(0) + nf(0)
-    for j in range(1, depth + 1):
-        px = (4 * 2 ** j) ** 2
-        mac_g += px * 9 * (nf(j) * nf(j + 1) + nf(j + 1) * nf(j + 1))
-        mac_d += px * 9 * (nf(j + 1) * nf(j + 1) + nf(j + 1) * nf(j))
-    px = (4 * 2 ** depth) ** 2
-    mac_g += px * nf(depth + 1) * ch
-    mac_d += px * nf(depth + 1) * ch
-    if fade:
-        mac_g += (px // 4) * nf(depth) * ch
-        mac_d += (px // 4) * nf(depth) * ch
+    mac_g, mac_d = flops_per_image_parts(depth, ch, fade)
     return 2.0 * (14 * mac_d + 4 * mac_g)
 
 
@@ -202,62 +191,99 @@ def assemble_roofline(config, cfg, fam, prod, ksteps, step_s, batch_overridden=F
     return roof
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=8)
-    ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
-    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--graphs', action='store_true', help='replay the losses as CUDA graphs (wgan_gp_loss.cuda_graphs)')
-    ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch of the config')
-    ap.add_argument('--prefetch', action='store_true',
-                    help='e2e leg: look-ahead H2D copy of the next real batch (trainer.prefetch_reals; not yet verified on a GPU)')
-    args = ap.parse_args()
-    cfg = dict(CONFIGS[args.config])
-    if args.batch:
-        cfg['n'] = args.batch
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    depth, alpha, n, ch = cfg['depth'], cfg['alpha'], cfg['n'], cfg['ch']
-    fade = depth > 0 and alpha < 1.0
+def d_step_flops_per_image(depth, ch, fade):
+    """Algorithmic FLOPs of the D step alone per image: 2*(12*MAC_D + MAC_G) (324.1 GFLOP at depth 8)."""
+    mac_g, mac_d = flops_per_image_parts(depth, ch, fade)
+    return 2.0 * (12 * mac_d + mac_g)
+
+
+def flops_per_image_parts(depth, ch, fade):
+    """(MAC_G, MAC_D) of one forward pass (the two terms of flops_per_image)."""
+    mac_g = nf(0) * nf(1) * 16 + 16 * nf(1) * nf(1) * 9
+    mac_d = 16 * nf(1) * nf(1) * 9 + 16 * nf(1) * nf(0) + nf(0)
+    for j in range(1, depth + 1):
+        px = (4 * 2 ** j) ** 2
+        mac_g += px * 9 * (nf(j) * nf(j + 1) + nf(j + 1) * nf(j + 1))
+        mac_d += px * 9 * (nf(j + 1) * nf(j + 1) + nf(j + 1) * nf(j))
+    px = (4 * 2 ** depth) ** 2
+    mac_g += px * nf(depth + 1) * ch
+    mac_d += px * nf(depth + 1) * ch
+    if fade:
+        mac_g += (px // 4) * nf(depth) * ch
+        mac_d += (px // 4) * nf(depth) * ch
+    return mac_g, mac_d
+
+
+def reference_leg_cpu(cfg, steps, warmup, budget_s):
+    """The reference arm / cpu_baseline: the UNMODIFIED reference's Trainer.train() (baseline/_ref, installed by
+    __graft_entry__.build()) on the host cores when it is there (kind "reference"), else the oracle port (kind "port").
+    The batch is a bounded sample of the config's: the largest power of two whose iteration stays near a second."""
+    sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+    import ref_harness as R
+    if not R.available():
+        return cpu_reference_leg(cfg, steps, warmup, budget_s)
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    depth, alpha, ch, res = cfg['depth'], cfg['alpha'], cfg['ch'], cfg['res']
+    n = max(1, min(cfg['n'], {0: 16, 1: 16, 2: 16, 3: 16, 4: 8, 5: 4, 6: 2}.get(depth, 1)))
+    ips, ms, k, w = R.time_train(res, ch, depth, alpha, n, steps, warmup, device='cpu', budget_s=budget_s)
     r = 4 * 2 ** depth
-    workload = {'workload': '%s: depth %d (%dx%d), alpha %g, batch %d/GPU, %s, D step (WGAN-GP) + G step + 2x Adam'
-                            % (args.config, depth, r, r, alpha, n, cfg['precision']),
-                'global_batch': n * max(world, 1), 'parallelism': 'dp%d' % max(world, 1),
-                'model_resolution': cfg['res'], 'channels': ch}
+    return dict(value=ips, unit='images/sec', cores=cores, kind='reference',
+                sample="%d timed iteration(s) of the unmodified reference's Trainer.train() (trainer.py:85-115), batch %d of the "
+                       "config's %d at depth %d (%dx%d), alpha %g, fp32, torch CPU ops on %d threads"
+                       % (k, n, cfg['n'], depth, r, r, alpha, cores)), ms * 1e-3, k, w
 
-    if args.impl == 'reference':
-        if rank != 0:
-            return
-        base, dt, k, w = cpu_reference_leg(cfg, args.steps, args.warmup, budget_s=60.0)
-        print(json.dumps({'impl': 'reference', 'metric': 'images/sec (G+D+GP step)', 'value': base['value'],
-                          'unit': 'images/sec', 'n_gpus': args.gpus, 'steps': k, 'warmup': w, 'ms_per_step': dt * 1e3,
-                          'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-                          'data': 'synthetic', 'config': workload, 'cpu_baseline': base,
-                          'note': 'host CPU only (rank 0); n_gpus names the launch this line pairs with',
-                          'e2e': {'value': base['value'], 'unit': 'images/sec', 'h2d_bytes_per_step': 0,
-                                  'd2h_bytes_per_step': 0}}))
-        return
 
+def gpu_eager_reference(cfg, steps=3, warmup=2):
+    """SURVEY.md 8(d) "GPU reference bar": the unmodified reference's Trainer.train() in PyTorch eager on this GPU at
+    the config's own batch, fp32 (cuDNN fp32 kernels) and with TF32 allowed -- the number the hand-written kernels
+    have to beat.  None when baseline/_ref is not installed."""
+    sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+    import ref_harness as R
+    import torch
+    if not R.available():
+        return None
+    out = {'what': "the unmodified reference's Trainer.train() (baseline/_ref: network.py, wgan_gp_loss.py, trainer.py:85-115), "
+                   "PyTorch eager + cuDNN on this GPU, inputs resident in HBM", 'batch': cfg['n'], 'steps': steps}
+    keep = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        for name, tf32 in (('fp32', False), ('tf32', True)):
+            n = cfg['n']
+            while True:
+                try:
+                    ips, ms, _, _ = R.time_train(cfg['res'], cfg['ch'], cfg['depth'], cfg['alpha'], n, steps, warmup,
+                                                 'cuda', tf32)
+                    break
+                except torch.OutOfMemoryError:
+                    torch.cuda.empty_cache()
+                    if n == 1:
+                        ips, ms = None, None
+                        break
+                    n //= 2
+            out[name] = {'images_per_sec': ips, 'ms_per_step': ms, 'batch': n}
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = keep
+    return out
+
+
+def run_config(name, cfg, args, rank, world, local_rank, steps, warmup, primary):
+    """Device-timed value, end-to-end value and the roofline of one BASELINE config.  Returns a dict (rank 0) or None."""
     import numpy as np
     import torch
     import torch.distributed as dist
     import pggan_b200 as pg
-
-    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU path)'
-    torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+    depth, alpha, n, ch = cfg['depth'], cfg['alpha'], cfg['n'], cfg['ch']
+    fade = depth > 0 and alpha < 1.0
+    r = 4 * 2 ** depth
     torch.manual_seed(1337)
     np.random.seed(1337 + rank)
     shape = (1000, ch, cfg['res'], cfg['res'])
     G, D = pg.Generator(shape).to(dev), pg.Discriminator(shape).to(dev)
     G.precision = D.precision = cfg['precision']
-    pg.wgan_gp_loss.cuda_graphs = args.graphs     # measured: no gain -- the step is GPU-bound at every config
+    pg.wgan_gp_loss.cuda_graphs = args.graphs
     G.depth = D.depth = depth
     G.alpha = D.alpha = alpha
     opt_g = pg.FusedAdam(G.parameters(), 1e-3, betas=(0.0, 0.99))      # train.py:148-149,195
@@ -267,11 +293,14 @@ def main():
     reals = [torch.randn(n, ch, r, r, device=dev, generator=gen) for _ in range(nbuf)]
     lats = [torch.randn(n, 512, device=dev, generator=gen) for _ in range(2 * nbuf)]
 
-    def step_device(i):
-        """inputs already resident in HBM"""
+    def d_step(i):
         cost, _, _ = pg.wgan_gp_D_loss(D, G, reals[i % nbuf], lats[(2 * i) % (2 * nbuf)])
         cost.backward()
         opt_d.step()
+
+    def step_device(i):
+        """inputs already resident in HBM"""
+        d_step(i)
         gcost = pg.wgan_gp_G_loss(G, D, lats[(2 * i + 1) % (2 * nbuf)])
         gcost.backward()
         opt_g.step()
@@ -296,22 +325,26 @@ def main():
         sync_all()
         return float(ms)
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         step_device(i)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
+    torch.cuda.reset_peak_memory_stats(dev)
     pg._lib.reset_launch_count()
-    ms = timed(step_device, args.steps)
+    ms = timed(step_device, steps)
     launches = pg._lib.launch_count()
     clocks = sampler.finish() if rank == 0 else None
     peak_mem = torch.cuda.max_memory_allocated(dev)
 
-    if os.environ.get('PGK_BENCH_MAIN_ONLY'):    # profiling runs (ncu): the device-resident leg only
+    if primary and os.environ.get('PGK_BENCH_MAIN_ONLY'):    # profiling runs (ncu): the device-resident leg only
         if rank == 0:
-            print(json.dumps({'ms_per_step': ms / args.steps, 'gpu_launches': launches, 'note': 'main leg only'}))
-        return
+            print(json.dumps({'ms_per_step': ms / steps, 'gpu_launches': launches, 'note': 'main leg only'}))
+        return None
+
+    # ---- the D step alone (the north star's 60 % tensor-pipe target is defined on the 1024^2 D step) ----------
+    ms_d = timed(d_step, steps) if (depth >= 8 or args.d_step) else None
 
     # ---- end to end: Trainer.train() fed from pinned host memory, loss read back every step ----------------
     host_reals = [torch.randn(n, ch, r, r).pin_memory() for _ in range(2)]
@@ -347,7 +380,7 @@ def main():
         heapq.heapify(q)
     for _ in range(2):
         tr.train()
-    ms_e2e = timed(lambda i: tr.train(), args.steps)
+    ms_e2e = timed(lambda i: tr.train(), steps)
     h2d = n * ch * r * r * 4 + 2 * n * 512 * 4
     d2h = 8
 
@@ -355,7 +388,7 @@ def main():
     pg._lib.prof_reset()
     pg._lib.prof_enable(True)
     sync_all()
-    ksteps = min(args.steps, 3)
+    ksteps = min(steps, 3)
     for i in range(ksteps):
         step_device(i)
     torch.cuda.synchronize()
@@ -363,38 +396,154 @@ def main():
     fam = {k: pg._lib.prof_read(k) for k in FAMILIES}
     prod = {k: pg._lib.prof_read_products(k) for k in FAMILIES}    # bf16 tensor-core FLOPs issued (1/3/6 per FLOP)
     pg._lib.prof_reset()
+    pg.wgan_gp_loss._graphs.clear()
+    del G, D, opt_g, opt_d, tr, reals, lats
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    step_s = ms / 1e3 / steps
+    roof = assemble_roofline(name, cfg, fam, prod, ksteps, step_s, bool(args.batch))
+    out = {'value': n * world / step_s, 'unit': 'images/sec', 'ms_per_step': step_s * 1e3, 'steps': steps,
+           'warmup': warmup, 'dtype': DTYPE[cfg['precision']],
+           'workload': '%s: depth %d (%dx%d), alpha %g, batch %d/GPU, %s, D step (WGAN-GP) + G step + 2x Adam'
+                       % (name, depth, r, r, alpha, n, cfg['precision']),
+           'e2e': {'value': n * world / (ms_e2e / 1e3 / steps), 'unit': 'images/sec', 'h2d_bytes_per_step': h2d,
+                   'd2h_bytes_per_step': d2h,
+                   'api': 'Trainer.train() with pinned host reals/latents' + (', real batches copied one step ahead' if args.prefetch else '')},
+           'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'peak_mem_gb': peak_mem / 1e9}
+    if ms_d is not None:
+        peak_tf = roof['peak'] if roof['bound'] == 'tensor' else None
+        try:
+            with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+                peak_tf = float(json.load(f).get('bf16_tflops_sustained', 1400.0))
+        except Exception:
+            peak_tf = peak_tf or 1400.0
+        fd = d_step_flops_per_image(depth, ch, fade)
+        d_s = ms_d / 1e3 / steps
+        out['d_step'] = {'ms': d_s * 1e3, 'gflop_per_image': fd / 1e9, 'achieved_tflops': fd * n / d_s / 1e12,
+                         'peak_tflops': peak_tf, 'tensor_frac': fd * n / d_s / 1e12 / peak_tf,
+                         'what': 'wgan_gp_D_loss + backward + Adam alone, device-timed; algorithmic FLOPs 2*(12*MAC_D + MAC_G) '
+                                 'per image against the measured sustained bf16 peak (north star: >= 0.6 at 1024x1024)'}
+    return out
 
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true',
+                    help='skip the secondary legs of the line (other BASELINE configs, GPU-eager reference)')
+    ap.add_argument('--d-step', action='store_true', help='time the D step alone at every config (default: depth 8 only)')
+    ap.add_argument('--graphs', action='store_true', help='replay the losses as CUDA graphs (wgan_gp_loss.cuda_graphs)')
+    ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch of the config')
+    ap.add_argument('--prefetch', action='store_true',
+                    help='e2e leg: look-ahead H2D copy of the next real batch (trainer.prefetch_reals)')
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.batch:
+        cfg['n'] = args.batch
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    depth, alpha, n, ch = cfg['depth'], cfg['alpha'], cfg['n'], cfg['ch']
+    r = 4 * 2 ** depth
+    workload = {'workload': '%s: depth %d (%dx%d), alpha %g, batch %d/GPU, %s, D step (WGAN-GP) + G step + 2x Adam'
+                            % (args.config, depth, r, r, alpha, n, cfg['precision']),
+                'global_batch': n * max(world, 1), 'parallelism': 'dp%d' % max(world, 1),
+                'model_resolution': cfg['res'], 'channels': ch}
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        base, dt, k, w = reference_leg_cpu(cfg, args.steps, args.warmup, budget_s=float(os.environ.get('PGK_CPU_BUDGET_S', '90')))
+        print(json.dumps({'impl': 'reference', 'metric': 'images/sec (G+D+GP step)', 'value': base['value'],
+                          'unit': 'images/sec', 'n_gpus': args.gpus, 'steps': k, 'warmup': w, 'ms_per_step': dt * 1e3,
+                          'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                          'data': 'synthetic', 'config': workload, 'cpu_baseline': base,
+                          'note': 'host CPU only (rank 0); n_gpus names the launch this line pairs with',
+                          'e2e': {'value': base['value'], 'unit': 'images/sec', 'h2d_bytes_per_step': 0,
+                                  'd2h_bytes_per_step': 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU path)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    main_res = run_config(args.config, cfg, args, rank, world, local_rank, args.steps, args.warmup, True)
+    if os.environ.get('PGK_BENCH_MAIN_ONLY'):
+        return
+    # ---- the other BASELINE configs on the same line: c4 is the north star's headline (depth 8), c3 / c5 the other
+    # bf16 configs; a few device-timed steps each, same legs (value, e2e, roofline; D step alone at depth 8) ----------
+    others = {}
+    if not args.no_extras and args.config == 'c2' and not args.batch:
+        for nm in (('c4', 'c3', 'c5') if world == 1 else ('c4',)):
+            res_o = run_config(nm, dict(CONFIGS[nm]), args, rank, world, local_rank, min(args.steps, 10), 3, False)
+            if res_o is not None:
+                others[nm] = res_o
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    step_s = ms / 1e3 / args.steps
-    value = n * world / step_s
-    roof = assemble_roofline(args.config, cfg, fam, prod, ksteps, step_s, bool(args.batch))
     out = {
-        'metric': 'images/sec (G+D+GP step)', 'value': value, 'unit': 'images/sec', 'n_gpus': world,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': step_s * 1e3, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': DTYPE[cfg['precision']], 'data': 'synthetic',
+        'metric': 'images/sec (G+D+GP step)', 'value': main_res['value'], 'unit': 'images/sec', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': main_res['ms_per_step'], 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': main_res['dtype'], 'data': 'synthetic',
         'config': dict(workload, l2='no flush needed: activations written per step (%.1f GB peak allocated) >> 126 MB L2'
-                       % (peak_mem / 1e9)),
-        'e2e': {'value': n * world / (ms_e2e / 1e3 / args.steps), 'unit': 'images/sec', 'h2d_bytes_per_step': h2d,
-                'd2h_bytes_per_step': d2h,
-                'api': 'Trainer.train() with pinned host reals/latents' + (', real batches copied one step ahead' if args.prefetch else '')},
-        'gpu_launches': launches,
-        'clocks': clocks,
-        'roofline': roof,
+                       % main_res['peak_mem_gb']),
+        'e2e': main_res['e2e'], 'gpu_launches': main_res['gpu_launches'], 'clocks': main_res['clocks'],
+        'roofline': main_res['roofline'],
     }
+    if 'd_step' in main_res:
+        out['d_step'] = main_res['d_step']
+    if others:
+        out['configs'] = others
     switches = {k: v for k, v in sorted(os.environ.items()) if k.startswith('PGK_')}
     if switches or args.graphs or args.prefetch:
         # a line measured with non-default tuning switches says so (A/B runs; the driver's run has none)
         out['config']['switches'] = dict(switches, **({'--graphs': '1'} if args.graphs else {}),
                                          **({'--prefetch': '1'} if args.prefetch else {}))
+    if world == 1 and not args.no_extras:
+        # the bar to beat: the reference itself in PyTorch eager on this GPU, for the line's config and the headline
+        try:
+            ge = {args.config: gpu_eager_reference(cfg)}
+            if 'c4' in others:
+                ge['c4'] = gpu_eager_reference(dict(CONFIGS['c4']), steps=2, warmup=1)
+            if ge[args.config] is not None:
+                out['gpu_eager_reference'] = ge
+        except Exception as e:           # a baseline leg must never take the line down
+            out['gpu_eager_reference'] = {'error': repr(e)[:300]}
     if not args.no_cpu_baseline and world == 1:      # the CPU leg is reported at N = 1 only
-        base, _, _, _ = cpu_reference_leg(cfg, 3, 1, budget_s=20.0)
-        out['cpu_baseline'] = base
+        torch.cuda.synchronize()
+        base = cpu_baseline_subprocess(args.config, args.batch)
+        if base is not None:
+            out['cpu_baseline'] = base
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def cpu_baseline_subprocess(config, batch):
+    """The CPU leg runs in a child process: loading the reference for the CPU replaces torch's .cuda() methods
+    process-wide (baseline/ref_harness.py), which must not happen in the process that drives the GPU."""
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--config', config, '--steps', '3',
+           '--warmup', '1']
+    if batch:
+        cmd += ['--batch', str(batch)]
+    try:
+        p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=240,
+                           env=dict(os.environ, CUDA_VISIBLE_DEVICES='', PGK_CPU_BUDGET_S='20'))
+        line = [l for l in p.stdout.splitlines() if l.startswith('{')][-1]
+        return json.loads(line)['cpu_baseline']
+    except Exception:
+        return None
 
 
 if __name__ == '__main__':
