@@ -51,6 +51,11 @@ long long pgk_launch_count(void);
 void pgk_reset_launch_count(void);
 /* add n to the counter: kernels replayed from a captured CUDA graph do not pass through the entry points */
 void pgk_count_launch(int n);
+/* Programmatic dependent launch: every kernel of the library is launched with the programmatic-stream-serialization
+ * attribute and runs griddepcontrol.wait before its first global read, so a kernel's prologue overlaps its predecessor's
+ * tail (the reference's default-stream ordering, trainer.py:85-115, is kept: nothing is read before the predecessor has
+ * completed).  set = 0 / 1 switches it off / on, set < 0 queries; returns the state.  Default: on unless PGK_PDL=0. */
+int pgk_pdl_state(int set);
 /* per-launch device timing of the GEMM-shaped kernels (bench.py's roofline): while enabled, pgk_conv / pgk_wgrad
  * bracket their launch with CUDA events on `stream`.  pgk_prof_read synchronises on the recorded events and returns
  * the summed algorithmic FLOPs (2*M*N*K of each launch), the summed algorithmic HBM bytes (operand planes read +
@@ -137,16 +142,6 @@ int pgk_conv_fp16(const void* xh, long long xh_ps, int N, int H, int W, int Cin,
                   long long out_ps, pgk_stream_t stream);
 /* 1 iff pgk_conv would run this shape on the wide tensor-core kernel (what pgk_conv_fp16 accepts) */
 int pgk_conv_tc_supported(int N, int H, int W, int Cin, int Cout, int KS, int ups);
-/* Weight gradient with the ACTIVATION operand read as one IEEE-half plane (experimental; follow-up of the forward
- * switch above): xh = plane 0 of what pgk_cvt_fp16x2 wrote for the layer's forward input (same N,H,W,C order; xoff
- * counts samples of xh), g = Pg (2 or 3) bf16 planes of which two are read; products xh*g0 + xh*g1 -- two instead of
- * three.  A weight gradient is an end result, so the 11-bit operand costs 1.4..2.4e-4 on it and nothing propagates
- * (tests/dev/precision_model_grad.py); groups whose x operand is itself a gradient (the penalty's (v, ua) term) must
- * stay on pgk_wgrad -- half precision does not cover their range.  Same groups / dwp semantics as pgk_wgrad; no bias
- * gradient (pgk_bias_grad); wide tensor-core shapes only: pgk_wgrad_fp16x_supported says which. */
-int pgk_wgrad_fp16x(const void* xh, const void* g, long long g_ps, int Pg, int H, int W, int Cin, int Cout, int KS,
-                    int ngroups, int group_n, const int* xoff, const int* goff, float* dwp, pgk_stream_t stream);
-int pgk_wgrad_fp16x_supported(int H, int W, int Cin, int Cout, int KS, int ngroups, int group_n);
 
 /* ---- weight gradient (cuDNN convolution_backward, weight part) --------------------------
  * dwp[tap*Cin+ci][co] += sum over the listed sample groups of X[..., ci] (shifted by tap) * g[..., co].

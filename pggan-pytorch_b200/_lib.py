@@ -26,7 +26,6 @@ SIGNATURES = {
     'pgk_cvt_fp16x2': [P, L, I, L, P, L],
     'pgk_pack_operand_fp16': [P, I, I, P, L, I],
     'pgk_conv_fp16': [P, L, I, I, I, I, I, I, P, L, P, P, P, I, P, I, L],
-    'pgk_wgrad_fp16x': [P, P, L, I, I, I, I, I, I, I, I, P, P, P],
     'pgk_wgrad': [P, L, P, L, I, I, I, I, I, I, I, I, I, I, P, P, P, P, ctypes.c_uint],
     'pgk_bias_grad': [P, L, I, I, I, I, I, P, F, P, I],
     'pgk_from_rgb': [P, I, I, I, I, I, P, F, P, I, P, L, P, I, L],
@@ -86,6 +85,8 @@ def load():
     lib.pgk_reset_launch_count.restype = None
     lib.pgk_count_launch.argtypes = [c_int]
     lib.pgk_count_launch.restype = None
+    lib.pgk_pdl_state.argtypes = [c_int]
+    lib.pgk_pdl_state.restype = c_int
     lib.pgk_prof_enable.argtypes = [c_int]
     lib.pgk_prof_enable.restype = None
     lib.pgk_prof_read.argtypes = [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
@@ -100,8 +101,6 @@ def load():
     lib.pgk_set_tc.restype = None
     lib.pgk_conv_tc_supported.argtypes = [c_int] * 7
     lib.pgk_conv_tc_supported.restype = c_int
-    lib.pgk_wgrad_fp16x_supported.argtypes = [c_int] * 7
-    lib.pgk_wgrad_fp16x_supported.restype = c_int
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = list(args) + [c_void_p]
@@ -112,9 +111,9 @@ def load():
 
 def exported_symbols():
     return ['pgk_version', 'pgk_last_error', 'pgk_arch_check', 'pgk_launch_count', 'pgk_reset_launch_count',
-            'pgk_count_launch',
+            'pgk_count_launch', 'pgk_pdl_state',
             'pgk_prof_enable', 'pgk_prof_read', 'pgk_prof_read_products', 'pgk_prof_reset', 'pgk_set_tc', 'pgk_pack_thin_plane_elems',
-            'pgk_conv_tc_supported', 'pgk_wgrad_fp16x_supported'] + list(SIGNATURES)
+            'pgk_conv_tc_supported'] + list(SIGNATURES)
 
 
 _checked_devices = set()
@@ -153,6 +152,11 @@ def launch_count():
 def add_launches(n):
     """Account for kernels launched by a replayed CUDA graph (they do not pass through the C entry points)."""
     load().pgk_count_launch(int(n))
+
+
+def pdl_state(on=None):
+    """Programmatic dependent launch (include/pgk.h): query (None) or switch; returns the state."""
+    return bool(load().pgk_pdl_state(-1 if on is None else int(bool(on))))
 
 
 def reset_launch_count():

@@ -24,7 +24,7 @@ extern "C" int pgk_conv_tc(const void* x, int P, int Pr, long long x_ps, int N, 
 extern "C" int pgk_wgrad_tc_supported(int H, int W, int Cin, int Cout, int KS, int ups, int ngroups, int group_n);
 extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W,
                             int Cin, int Cout, int KS, int ngroups, int group_n, const int* xoff, const int* goff,
-                            float* dwp, pgk_stream_t stream, int x_fp16);
+                            float* dwp, pgk_stream_t stream);
 
 extern "C" int pgk_conv_thin_supported(int N, int H, int W, int Cin, int Cout, int KS, int ups);
 extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N, int H, int W, int Cin, int Cout,
@@ -170,26 +170,6 @@ extern "C" int pgk_conv_fp16(const void* xh, long long xh_ps, int N, int H, int 
                        out, out_ps, stream, 1, 1, 1.0f / (float)(1 << PGK_FP16_WSHIFT));
 }
 
-// weight gradient with the activation operand as one IEEE-half plane (see include/pgk.h): the wide tensor-core kernel
-// with A = fp16, B = bf16 and the two products xh * g0, xh * g1
-extern "C" int pgk_wgrad_fp16x(const void* xh, const void* g, long long g_ps, int Pg, int H, int W, int Cin, int Cout,
-                               int KS, int ngroups, int group_n, const int* xoff, const int* goff, float* dwp,
-                               pgk_stream_t stream) {
-    PGK_REQUIRE(ngroups >= 1 && ngroups <= 4, "pgk_wgrad_fp16x: 1..4 groups");
-    PGK_REQUIRE(Pg >= 2 && Pg <= 3 && xh && g && dwp, "pgk_wgrad_fp16x: g has 2 or 3 bf16 planes (the fp32-faithful modes)");
-    PGK_REQUIRE(tc_enabled() && pgk_wgrad_tc_supported(H, W, Cin, Cout, KS, 0, ngroups, group_n),
-                "pgk_wgrad_fp16x: only shapes of the wide tensor-core weight gradient (see pgk_wgrad_fp16x_supported)");
-    const double flops = 2.0 * ngroups * group_n * H * W * (double)Cout * KS * KS * Cin;
-    const double bytes = 2.0 * ngroups * group_n * H * W * ((double)Cin + 2.0 * Cout);
-    ProfScope prof(PGK_PROF_WGRAD, flops, bytes, stream, 0);
-    prof.r.products = 2.0 * flops;
-    return pgk_wgrad_tc(xh, 0, g, g_ps, Pg, 2, H, W, Cin, Cout, KS, ngroups, group_n, xoff, goff, dwp, stream, 1);
-}
-
-extern "C" int pgk_wgrad_fp16x_supported(int H, int W, int Cin, int Cout, int KS, int ngroups, int group_n) {
-    return tc_enabled() && pgk_wgrad_tc_supported(H, W, Cin, Cout, KS, 0, ngroups, group_n);
-}
-
 extern "C" int pgk_wgrad(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W,
                          int Cin, int Cout, int KS, int ups, int ngroups, int group_n, const int* xoff, const int* goff,
                          float* dwp, float* db, unsigned bias_groups, pgk_stream_t stream) {
@@ -211,7 +191,7 @@ extern "C" int pgk_wgrad(const void* x, long long x_ps, const void* g, long long
     int rc;
     if (tc_enabled() && pgk_wgrad_tc_supported(H, W, Cin, Cout, KS, ups, ngroups, group_n)) {
         ProfScope prof(PGK_PROF_WGRAD, flops, bytes, stream, Pr);
-        rc = pgk_wgrad_tc(x, x_ps, g, g_ps, P, Pr, H, W, Cin, Cout, KS, ngroups, group_n, xoff, goff, dwp, stream, 0);
+        rc = pgk_wgrad_tc(x, x_ps, g, g_ps, P, Pr, H, W, Cin, Cout, KS, ngroups, group_n, xoff, goff, dwp, stream);
     } else {
         ProfScope prof(PGK_PROF_WGRAD_SIMT, flops, bytes, stream);
         rc = pgk_wgrad_simt(x, x_ps, g, g_ps, P, H, W, Cin, Cout, KS, ups, ngroups, group_n, xoff, goff, dwp, stream);

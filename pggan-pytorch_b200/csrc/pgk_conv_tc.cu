@@ -439,8 +439,6 @@ struct WgradTcArgs {
     int RG;               // 64-row groups in K = KS*KS*Cin / 64
     long long tiles_per_group, tiles_total, tiles_per_cta;
     float* dwp;
-    int red4;             // PGK_WGRAD_RED4=1 (experimental): flush with 16-byte vector reductions, or plain
-                          // read-add-write when the pixel range is not split, instead of scalar atomics
 };
 
 // four consecutive floats added to global memory in one reduction (sm_90+; the address must be 16-byte aligned)
@@ -448,12 +446,10 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// XH = 1 (pgk_wgrad_fp16x, experimental): the activation operand is ONE IEEE-half plane (plane 0 of the copy
-// pgk_cvt_fp16x2 makes for the forward pass) against the P bf16 planes of g -- P products instead of P (P + 1) / 2;
-// only plane 0 of a stage holds X boxes then.
-// RED4 = 1 (PGK_WGRAD_RED4=1, experimental): the flush uses 16-byte vector reductions, or plain read-add-write where
-// the pixel range is not split.  The <P, 0, 0> instances are the GPU-verified machine code.
-template <int P, int XH, int RED4>
+// The flush into dwp uses 16-byte vector reductions (SASS REDG.E.ADD.F32x4), or a plain read-add-write where the pixel
+// range is not split (this thread is then the only writer of its row slice): at batch 4 the flush of up to 147 CTAs x
+// 36 864 scalar atomics was the larger part of a 50-120 us launch (measured: -5 % of the depth-8 step, -3.5 % at depth 6).
+template <int P>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
                 const WgradTcArgs a) {
@@ -531,10 +527,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 const int xn = a.xoff[grp] + smp, gn = a.goff[grp] + smp;
                 const uint32_t dst = sbase + s * stage_bytes;
                 if (elect_one()) {
-                    mbar_expect_tx(fb, XH ? stage_bytes - (P - 1) * 2 * S * box_bytes : stage_bytes);
+                    mbar_expect_tx(fb, stage_bytes);
                     for (int p = 0; p < P; ++p) {
                         const uint32_t pd = dst + p * plane_bytes;
-                        for (int b = 0; b < 2 * S && (!XH || p == 0); ++b)
+                        for (int b = 0; b < 2 * S; ++b)
                             tma_load_5d(pd + b * box_bytes, &tmX, fb, bc[b], x0 + bdx[b], y0 + bdy[b], xn, p);
                         for (int b = 0; b < gboxes; ++b)
                             tma_load_5d(pd + (2 * S + b) * box_bytes, &tmG, fb, co0 + b * 64, x0, y0, gn, p);
@@ -555,7 +551,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             }
         }
     } else if (warp == 5) {
-        const uint32_t idesc = XH ? idesc_f16(a.NT, 1, 1, 1, 0) : idesc_bf16(a.NT, 1, 1);
+        const uint32_t idesc = idesc_bf16(a.NT, 1, 1);
         const uint64_t dbase = smem_desc(0, box_bytes, 1024, 2);
         const uint32_t pl16 = plane_bytes >> 4, bx16 = box_bytes >> 4;
         int s = 0;
@@ -573,9 +569,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {   // PXS = 32 pixels = two K = 16 steps
 #pragma unroll
-                        for (int i = 0; i < (XH ? 1 : P); ++i) {
+                        for (int i = 0; i < P; ++i) {
 #pragma unroll
-                            for (int j = 0; j < (XH ? P : P - i); ++j)
+                            for (int j = 0; j < P - i; ++j)
                                 mma_bf16(d, ad_sl + (uint32_t)(i * pl16 + ks * 128), bd0 + (uint32_t)(j * pl16 + ks * 128),
                                          idesc, (ks == 0 && i + j == 0) ? later : 1u);
                         }
@@ -600,24 +596,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 float v[16];
                 tmem_ld16(trow + sl * a.NT + c, v);
                 if (k < K) {
-                    if (RED4) {
-                        if (gridDim.z == 1) {
-                            // the pixel range is not split: this thread is the only writer of its row slice, so the
-                            // accumulation into dwp needs no atomics at all
+                    if (gridDim.z == 1) {
+                        // the pixel range is not split: this thread is the only writer of its row slice, so the
+                        // accumulation into dwp needs no atomics at all
 #pragma unroll
-                            for (int j = 0; j < 16; j += 4) {
-                                float4* p4 = reinterpret_cast<float4*>(drow + c + j);
-                                float4 o = *p4;
-                                o.x += v[j], o.y += v[j + 1], o.z += v[j + 2], o.w += v[j + 3];
-                                *p4 = o;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; j += 4) red_add_v4(drow + c + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        for (int j = 0; j < 16; j += 4) {
+                            float4* p4 = reinterpret_cast<float4*>(drow + c + j);
+                            float4 o = *p4;
+                            o.x += v[j], o.y += v[j + 1], o.z += v[j + 2], o.w += v[j + 3];
+                            *p4 = o;
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) atomicAdd(drow + c + j, v[j]);
+                        for (int j = 0; j < 16; j += 4) red_add_v4(drow + c + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
                     }
                 }
             }
@@ -707,20 +698,7 @@ extern "C" int pgk_conv_tc(const void* x, int P, int Pr, long long x_ps, int N, 
     // spread them over more CTAs with narrower channel slices
     {
         const int pixel_tiles = a.tiles_x * a.tiles_y * tiles_n, sms = pgk_num_sms();
-        // PGK_CONV_WAVE=1 (experimental): stop halving while the tiles still fit ONE wave.  The default rule halves
-        // until there are at least `sms` tiles, which lands between one and two waves (e.g. 24 pixel blocks x 512
-        // channels: 192 tiles of 64 channels = two rounds of the persistent loop, where 96 tiles of 128 channels
-        // are one round of tiles that cost well under twice as much).
-        static int wave = -1;
-        if (wave < 0) {
-            const char* e = getenv("PGK_CONV_WAVE");
-            wave = e ? atoi(e) != 0 : 0;
-        }
-        if (wave) {
-            while (a.NT > 32 && pixel_tiles * (Cout / (a.NT >> 1)) <= sms) a.NT >>= 1;
-        } else {
-            while (a.NT > 32 && pixel_tiles * (Cout / a.NT) < sms) a.NT >>= 1;
-        }
+        while (a.NT > 32 && pixel_tiles * (Cout / a.NT) < sms) a.NT >>= 1;
     }
     a.ntiles_n = Cout / a.NT;
     a.total_tiles = a.tiles_x * a.tiles_y * tiles_n * a.ntiles_n;
@@ -838,9 +816,9 @@ extern "C" int pgk_wgrad_tc_supported(int H, int W, int Cin, int Cout, int KS, i
 
 extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W,
                             int Cin, int Cout, int KS, int ngroups, int group_n, const int* xoff, const int* goff,
-                            float* dwp, pgk_stream_t stream, int x_fp16) {
+                            float* dwp, pgk_stream_t stream) {
     PGK_REQUIRE(pgk_wgrad_tc_supported(H, W, Cin, Cout, KS, 0, ngroups, group_n), "pgk_wgrad_tc: unsupported shape");
-    PGK_REQUIRE(!x_fp16 || Pr == 2, "pgk_wgrad_tc: the half-plane activation operand goes with two planes of g");
+    PGK_REQUIRE((((uintptr_t)dwp) & 15) == 0, "pgk_wgrad_tc: dwp must be 16-byte aligned (vector reductions)");
     PGK_REQUIRE(P >= 1 && P <= 3 && Pr >= 1 && Pr <= P, "pgk_wgrad_tc: need 1 <= Pr <= P <= 3");
     PGK_REQUIRE(ngroups >= 1 && ngroups <= 4, "pgk_wgrad_tc: 1..4 groups");
     WgradTcArgs a;
@@ -894,22 +872,13 @@ extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long l
     a.tiles_per_cta = (a.tiles_total + split - 1) / split;
     split = (a.tiles_total + a.tiles_per_cta - 1) / a.tiles_per_cta;
     a.dwp = dwp;
-    {
-        static int red4 = -1;
-        if (red4 < 0) {
-            const char* e = getenv("PGK_WGRAD_RED4");
-            red4 = e ? atoi(e) != 0 : 0;
-        }
-        a.red4 = red4 && (((uintptr_t)dwp) & 15) == 0;
-    }
 
     CUtensorMap tmX, tmG;
     {
-        // (a half-plane x is one plane deep: only plane 0 of it is ever read)
         unsigned long long dims[5] = {(unsigned long long)Cin, (unsigned long long)W, (unsigned long long)H,
-                                      (unsigned long long)(xmax + group_n), (unsigned long long)(x_fp16 ? 1 : P)};
+                                      (unsigned long long)(xmax + group_n), (unsigned long long)P};
         unsigned long long str[4] = {2ull * Cin, 2ull * Cin * W, 2ull * Cin * W * H,
-                                     (P > 1 && !x_fp16) ? 2ull * x_ps : 2ull * Cin * W * H * (xmax + group_n)};
+                                     P > 1 ? 2ull * x_ps : 2ull * Cin * W * H * (xmax + group_n)};
         unsigned box[5] = {64u, (unsigned)TW, (unsigned)TH, (unsigned)a.TN, 1u};
         int rc = pgk_make_tmap(&tmX, x, 5, dims, str, box, 128, "pgk_wgrad_tc(x)");
         if (rc) return rc;
@@ -925,15 +894,9 @@ extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long l
     }
     const int smem = a.stages * stage_bytes + 1024 + 256;
     typedef void (*kern_t)(const CUtensorMap, const CUtensorMap, const WgradTcArgs);
-    kern_t kern;
-    if (a.red4)
-        kern = x_fp16 ? wgrad_tc_kernel<2, 1, 1>
-                      : Pr == 1 ? wgrad_tc_kernel<1, 0, 1> : Pr == 2 ? wgrad_tc_kernel<2, 0, 1> : wgrad_tc_kernel<3, 0, 1>;
-    else
-        kern = x_fp16 ? wgrad_tc_kernel<2, 1, 0>
-                      : Pr == 1 ? wgrad_tc_kernel<1, 0, 0> : Pr == 2 ? wgrad_tc_kernel<2, 0, 0> : wgrad_tc_kernel<3, 0, 0>;
-    static bool attr_done[8] = {};
-    const int ai = (x_fp16 ? 3 : Pr - 1) + (a.red4 ? 4 : 0);
+    kern_t kern = Pr == 1 ? wgrad_tc_kernel<1> : Pr == 2 ? wgrad_tc_kernel<2> : wgrad_tc_kernel<3>;
+    static bool attr_done[3] = {};
+    const int ai = Pr - 1;
     if (!attr_done[ai]) {
         cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e != cudaSuccess) {

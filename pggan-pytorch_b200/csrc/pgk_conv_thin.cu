@@ -69,36 +69,34 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
     return v;
 }
 
-// Tensor-memory columns of the ATM flavour's A ring: kATMRows input rows x slots of 4 columns (128 pixels x 8 channels
-// each).  Slots of a row: [dx][channel group] for Cin >= 16 -- a K = 16 step (tap, channel-group pair) is two
-// neighbouring slots; Cin = 8: [dx = 0, 1, 2, zero] -- the K = 16 steps are (dx 0, dx 1) and (dx 2, zero slot),
-// exactly the pairs pack_thin_kernel lays the weights out for.
-constexpr int kATMRows = 4;
-template <int CIN>
-struct ATMRing {
-    static constexpr int SLOTS = CIN == 8 ? 4 : 3 * (CIN / 8);
-    static constexpr int ROW_COLS = 4 * SLOTS;
-    static constexpr int COLS = kATMRows * ROW_COLS;
+// STK = 1 (the one-plane mode): INPUT-ROW-STATIONARY issue.  A tcgen05.mma with M = 128, K = 16 costs ~66 cycles for any
+// N <= 64 (tools/probes/umma_probe.cu on B200: 66.5 / 70.0 / 78.2 / 104.6 / 168.6 cycles at N = 16 / 32 / 64 / 128 /
+// 256, swizzled or not -- the 128 x 32-byte A tile streams through the shared-memory port whatever N is; 42.8 with A
+// in tensor memory), so with one output row per accumulator the 8 -> 8 layer pays 6 x 66 cycles per 128-pixel row
+// against ~180 cycles of HBM time.  Here the three filter rows are stacked along N instead: an input row r is
+// multiplied ONCE per (dx, channel-group pair) by B = [ky = 2 | ky = 1 | ky = 0] (N = 3 * Npad) and accumulates into the
+// three neighbouring accumulator blocks of the output rows r-1, r, r+1 -- a ring of kStkBlocks blocks of Npad columns;
+// a window that wraps around the ring is issued as two instructions.  Three times fewer instructions (2 / 3 / 6 per
+// row for Cin 8 / 16 / 32), each input row is consumed by its own MMAs alone (released at once), and output row i is
+// complete when input row i+2 has been issued.  Every MMA accumulates: the epilogue warps, who own the lanes, zero a
+// block (tcgen05.st) after reading it and before handing it back.
+template <int NPAD>
+struct StkRing {
+    static constexpr int BLOCKS = NPAD == 64 ? 4 : 8;
 };
-template <int CIN, int NPAD, int SPLIT, int ATM>
+constexpr int kAccSlots = 8;        // accumulator barrier pairs laid out in shared memory (kAcc or StkRing::BLOCKS used)
+template <int CIN, int NPAD, int SPLIT, int STK>
 struct ThinCols {
     static constexpr int ACC = SPLIT ? 2 * NPAD : NPAD;
-    static constexpr int NEED = kAcc * ACC + (ATM ? ATMRing<CIN>::COLS : 0);
+    static constexpr int NEED = STK ? StkRing<NPAD>::BLOCKS * NPAD : kAcc * ACC;
     static constexpr unsigned N = NEED <= 64 ? 64u : NEED <= 128 ? 128u : NEED <= 256 ? 256u : 512u;
 };
 
-// ATM = 1 (PGK_THIN_ATM=1, experimental, bf16 mode only): the A operand of every MMA comes from TENSOR MEMORY.  Each
-// input row is copied once per dx from its shared-memory row buffer into the ring above (tcgen05.cp.128x128b: 128
-// pixels x 16 bytes from a start address shifted by dx pixels -- the tap shift the SS-mode descriptors express the same
-// way) and then serves the three output rows that use it; the MMAs read A at the tensor core's own rate instead of
-// streaming a 128-row tile through the shared-memory port per K = 16 step ("the thin conv with A in
-// tensor memory").  tcgen05.cp and tcgen05.mma of one thread execute in issue order, which is all the ring needs: a
-// slot is overwritten two output rows after its last reader was issued.  Same producer, weights, barriers and
-// epilogue; a shared-memory row is released as soon as its copies have completed.
-template <int CIN, int P, int SPLIT, int NPAD, int ATM>
+template <int CIN, int P, int SPLIT, int NPAD, int STK>
 __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const ThinArgs a) {
-    static_assert(!ATM || (P == 1 && SPLIT == 0), "the tensor-memory A ring exists for the one-plane mode only");
+    static_assert(!STK || (P == 1 && SPLIT == 0), "the input-row-stationary flavour exists for the one-plane mode only");
+    constexpr int NACC = STK ? StkRing<NPAD>::BLOCKS : kAcc;   // accumulator blocks in flight
     constexpr int CG = Steps<CIN>::CG, STEPS = Steps<CIN>::N;
     constexpr uint32_t plane_bytes = CG * kCgBytes;
     constexpr uint32_t row_bytes = P * plane_bytes;
@@ -114,15 +112,31 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
     auto rfull = [&](int s) { return bars + 8u * s; };
     auto rempty = [&](int s) { return bars + 8u * (kMaxRing + s); };
     auto afull = [&](int b) { return bars + 16u * kMaxRing + 8u * b; };
-    auto aempty = [&](int b) { return bars + 16u * kMaxRing + 8u * kAcc + 8u * b; };
-    const uint32_t tptr = bars + 16u * kMaxRing + 16u * kAcc;
+    auto aempty = [&](int b) { return bars + 16u * kMaxRing + 8u * kAccSlots + 8u * b; };
+    const uint32_t tptr = bars + 16u * kMaxRing + 16u * kAccSlots;
     float* bias_s = reinterpret_cast<float*>(smem_raw + (tptr + 16u - raw));
 
     // ---- one-time setup: zero the row ring (padding pixels must be finite), stage weights and bias
     for (uint32_t o = threadIdx.x * 16u; o < kRing * row_bytes; o += kThinThreads * 16u)
         st_shared_v4(rows0 + o, make_uint4(0, 0, 0, 0));
     pgk_pdl_enter();   // the weight operand and the bias are written by earlier launches of the stream
-    {
+    if constexpr (STK != 0) {
+        // the packed operand is [step = (ky, dx or dx-pair, channel-group pair)][K half][Npad][8]; staged here as
+        // [k step = (dx..., channel-group pair)][K half][ky = 2, 1, 0][Npad][8], i.e. the three filter rows side by side
+        // along N in the order of the output rows they feed (r-1, r, r+1)
+        const uint4* src = reinterpret_cast<const uint4*>(a.wpack);
+        for (uint32_t i = threadIdx.x; i < (uint32_t)(STEPS * 2 * NPAD); i += kThinThreads) {
+            const uint32_t n = i % NPAD, rr = i / NPAD, h = rr & 1u, st = rr >> 1;
+            uint32_t dy, ks;
+            if constexpr (CIN == 8) {
+                dy = st >> 1, ks = st & 1u;
+            } else {
+                const uint32_t tap = st / (CIN / 16), cgp = st % (CIN / 16);
+                dy = tap / 3, ks = (tap % 3) * (CIN / 16) + cgp;
+            }
+            st_shared_v4(w0 + ((((ks * 2 + h) * 3 + (2 - dy)) * NPAD) + n) * 16u, __ldg(src + i));
+        }
+    } else {
         const uint4* src = reinterpret_cast<const uint4*>(a.wpack);
         const uint32_t n16 = P * wplane / 16u;
         for (uint32_t i = threadIdx.x; i < n16; i += kThinThreads) st_shared_v4(w0 + i * 16u, __ldg(src + i));
@@ -133,27 +147,27 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
             mbar_init(rfull(s), 1);
             mbar_init(rempty(s), 1);
         }
-        for (int b = 0; b < kAcc; ++b) {
+        for (int b = 0; b < NACC; ++b) {
             mbar_init(afull(b), 1);
             mbar_init(aempty(b), 4);
         }
         fence_barrier_init();
     }
-    constexpr int acc_cols = ThinCols<CIN, NPAD, SPLIT, ATM>::ACC;
-    constexpr unsigned ncols = ThinCols<CIN, NPAD, SPLIT, ATM>::N;
+    constexpr int acc_cols = ThinCols<CIN, NPAD, SPLIT, STK>::ACC;
+    constexpr unsigned ncols = ThinCols<CIN, NPAD, SPLIT, STK>::N;
     if (warp == 9) tmem_alloc(tptr, ncols);
     fence_proxy_async();   // generic-proxy writes (weights, zeroed ring) -> visible to the tensor core / TMA
     fence_before();
     __syncthreads();
     fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tptr - raw));
-    if constexpr (ATM != 0) {
-        // the A ring starts out as zeros: the zero slot of Cin = 8 is never written again, and no MMA may ever read
-        // a non-finite leftover (warps 0-3 own the four lane quarters)
+    if constexpr (STK != 0) {
+        // every MMA of this flavour accumulates: the accumulator ring starts out as zeros (warps 0-3 own the four
+        // lane quarters) and each block is zeroed again by the epilogue that drains it
         if (warp < 4) {
-            const uint32_t t0 = tmem + kAcc * acc_cols + ((uint32_t)(warp * 32) << 16);
+            const uint32_t t0 = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
-            for (int c = 0; c < ATMRing<CIN>::COLS; c += 8) tmem_zero8(t0 + c);
+            for (int c = 0; c < NACC * NPAD; c += 8) tmem_zero8(t0 + c);
             tmem_st_wait();
         }
         fence_before();
@@ -261,64 +275,53 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
         }
         cp_async_wait<0>();
         hand_over(g);
-    } else if (warp == 9 && ATM != 0) {
-        // ---- MMA issue, A from tensor memory (see the kernel header)
-        const uint32_t idesc = idesc_bf16(NPAD, 0, 0);
-        const uint64_t bdesc0 = smem_desc(w0, (uint32_t)NPAD * 16u, 128, 0);
-        constexpr uint32_t wstep16 = wstep >> 4;
-        // copy source: 128 pixels x 16 bytes, pixels 16 bytes apart (an 8-pixel core matrix is 128 contiguous bytes)
-        const uint64_t cdesc_hi = smem_desc(0, 16, 128, 0);
-        constexpr uint32_t kRowCols = ATMRing<CIN>::ROW_COLS;
-        const uint32_t tA = tmem + kAcc * acc_cols;
-        auto copy_row = [&](uint32_t gr) {   // input row gr: shared-memory slot gr mod ring -> ring row gr mod 4
-            const uint32_t src = (rows0 + (gr & (kRing - 1)) * row_bytes) >> 4;
-            const uint32_t dst = tA + (gr & (kATMRows - 1)) * kRowCols;
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-#pragma unroll
-                for (int cg = 0; cg < CG; ++cg)
-                    tmem_cp_128x128b(dst + (uint32_t)(dx * CG + cg) * 4u,
-                                     cdesc_hi | (uint64_t)(src + (uint32_t)(cg * kCgBytes + dx * 16) / 16u));
-            }
-        };
+    } else if (warp == 9 && STK != 0) {
+        // ---- MMA issue, input-row stationary (see the kernel header)
+        constexpr int KSTEPS = STEPS / 3;
+        constexpr uint32_t kstep16 = (uint32_t)(6 * NPAD);            // one k step of the staged weights, in 16-byte units
+        const uint64_t adesc_hi = smem_desc(0, CIN == 8 ? 16u : (uint32_t)kCgBytes, 128, 0);
+        const uint64_t bdesc0 = smem_desc(w0, (uint32_t)(3 * NPAD) * 16u, 128, 0);
+        const uint32_t idesc0 = idesc_bf16(0, 0, 0);                  // N is filled in per instruction: (N >> 3) << 17
+        auto idesc_n = [&](int nb) { return idesc0 | ((uint32_t)(nb * NPAD >> 3) << 17); };
         uint32_t g = 0, ti = 0;
         for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
-            wait_bar(rfull(g & (kRing - 1)), (g >> kRingLog) & 1);
-            wait_bar(rfull((g + 1) & (kRing - 1)), ((g + 1) >> kRingLog) & 1);
-            fence_after();
-            if (elect_one()) {
-                copy_row(g);
-                copy_row(g + 1);
-                mma_commit(rempty(g & (kRing - 1)));
-                mma_commit(rempty((g + 1) & (kRing - 1)));
-            }
-            __syncwarp();
-            for (int i = 0; i < a.RC; ++i, ++g, ++ti) {
-                wait_bar(rfull((g + 2) & (kRing - 1)), ((g + 2) >> kRingLog) & 1);
-                const int b = ti & (kAcc - 1);
-                wait_bar(aempty(b), ((ti / kAcc) & 1) ^ 1);
+            for (int j = 0; j < a.RC + 2; ++j, ++g) {
+                const int s = g & (kRing - 1);
+                wait_bar(rfull(s), (g >> kRingLog) & 1);
+                if (j < a.RC) {      // the block of output row j is touched for the first time: its last reader is done
+                    const uint32_t tn = ti + (uint32_t)j;
+                    wait_bar(aempty(tn % NACC), ((tn / NACC) & 1) ^ 1);
+                }
                 fence_after();
+                // output rows [i_lo, i_hi] take this input row through ky = j - i; their blocks are neighbours in the ring
+                const int i_lo = j >= 2 ? j - 2 : 0, i_hi = j < a.RC ? j : a.RC - 1;
+                const int nb = i_hi - i_lo + 1;
+                const uint32_t kb0 = (uint32_t)(2 - j + i_lo);                   // first filter-row block of B
+                const uint32_t blk0 = (ti + (uint32_t)i_lo) % NACC;
+                const int nb_a = (int)blk0 + nb <= NACC ? nb : NACC - (int)blk0;  // blocks before the ring wraps
                 if (elect_one()) {
-                    copy_row(g + 2);
-                    mma_commit(rempty((g + 2) & (kRing - 1)));
-                    const uint32_t d = tmem + b * acc_cols;
+                    const uint32_t rowa = (rows0 + s * row_bytes) >> 4;
 #pragma unroll
-                    for (int st = 0; st < STEPS; ++st) {
-                        int dy, slot;
-                        if (CIN == 8) {
-                            dy = st >> 1, slot = (st & 1) * 2;          // (dx 0, dx 1) | (dx 2, zero slot)
+                    for (int ks = 0; ks < KSTEPS; ++ks) {
+                        uint32_t aoff;
+                        if constexpr (CIN == 8) {
+                            aoff = (uint32_t)(ks * 2 * 16) / 16u;                 // (dx -1, dx 0) | (dx +1, zero weights)
                         } else {
-                            const int tap = st / (CIN / 16), cgp = st % (CIN / 16);
-                            dy = tap / 3, slot = (tap % 3) * CG + 2 * cgp;
+                            const int dx = ks / (CIN / 16), cgp = ks % (CIN / 16);
+                            aoff = (uint32_t)(2 * cgp * kCgBytes + dx * 16) / 16u;
                         }
-                        const uint32_t at = tA + ((g + dy) & (kATMRows - 1)) * kRowCols + (uint32_t)slot * 4u;
-                        mma_bf16_ts(d, at, bdesc0 + (uint32_t)(st * wstep16), idesc, st == 0 ? 0u : 1u);
+                        const uint64_t ad = adesc_hi | (uint64_t)(rowa + aoff);
+                        const uint64_t bd = bdesc0 + (uint32_t)(ks * kstep16 + kb0 * NPAD);
+                        mma_bf16(tmem + blk0 * NPAD, ad, bd, idesc_n(nb_a), 1u);
+                        if (nb_a < nb)
+                            mma_bf16(tmem, ad, bd + (uint32_t)(nb_a * NPAD), idesc_n(nb - nb_a), 1u);
                     }
-                    mma_commit(afull(b));
+                    mma_commit(rempty(s));                                        // this input row is consumed
+                    if (j >= 2) mma_commit(afull((ti + (uint32_t)(j - 2)) % NACC));   // output row j - 2 is complete
                 }
                 __syncwarp();
             }
-            g += 2;
+            ti += (uint32_t)a.RC;
         }
     } else if (warp == 9) {
         // ---- MMA issue: per output row, STEPS x (products of planes) MMAs of 128 pixels x Npad x 16
@@ -458,8 +461,8 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
                 pix = base + (long long)ui * a.W;
                 if (a.has_mask) load_mask(pix);
             }
-            const int b = ti & (kAcc - 1);
-            mbar_wait(afull(b), (ti / kAcc) & 1);
+            const int b = (int)(ti % NACC);
+            mbar_wait(afull(b), (ti / NACC) & 1);
             fence_after();
             const uint32_t trow = tmem + b * acc_cols + trow_off;
             bool done_pn = false;
@@ -534,6 +537,12 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
                     }
                 }
             }
+            }
+            if constexpr (STK != 0) {
+                // hand the block back zeroed: the next output row that lands here accumulates from its first MMA on
+#pragma unroll
+                for (int c = 0; c < NPAD; c += 8) tmem_zero8(trow + c);
+                tmem_st_wait();
             }
             fence_before();
             __syncwarp();
@@ -618,11 +627,11 @@ struct ThinPlan {
     int occ, ring, smem;
 };
 
-template <int CIN, int P, int SPLIT, int NPAD, int ATM>
+template <int CIN, int P, int SPLIT, int NPAD, int STK>
 static int launch_thin(const CUtensorMap& tmA, ThinArgs& a, cudaStream_t stream) {
     static bool attr = false;
     static ThinPlan plan;   // CTAs per SM, ring depth and shared memory of this instance
-    auto kern = conv_thin_kernel<CIN, P, SPLIT, NPAD, ATM>;
+    auto kern = conv_thin_kernel<CIN, P, SPLIT, NPAD, STK>;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
         if (e != cudaSuccess) {
@@ -630,8 +639,8 @@ static int launch_thin(const CUtensorMap& tmA, ThinArgs& a, cudaStream_t stream)
             return PGK_ERR_CUDA;
         }
         constexpr int steps = Steps<CIN>::N;
-        constexpr int ncols = (int)ThinCols<CIN, NPAD, SPLIT, ATM>::N;
-        const int fixed = 128 + P * steps * NPAD * 32 + 16 + 16 * kMaxRing + 16 * kAcc + 32 + 4 * NPAD + 64;
+        constexpr int ncols = (int)ThinCols<CIN, NPAD, SPLIT, STK>::N;
+        const int fixed = 128 + P * steps * NPAD * 32 + 16 + 16 * kMaxRing + 16 * kAccSlots + 32 + 4 * NPAD + 64;
         const int row = P * (CIN / 8) * kCgBytes;
         ThinPlan pl = {0, 0, 0};
         const int cap = thin_occ_cap();
@@ -654,7 +663,7 @@ static int launch_thin(const CUtensorMap& tmA, ThinArgs& a, cudaStream_t stream)
             cudaFuncAttributes fa;
             cudaFuncGetAttributes(&fa, kern);
             fprintf(stderr, "pgk_conv_thin<%d,%d,%d,%d,%d>: plan occ %d ring %d smem %d | runtime says %d blocks/SM (%s), regs %d, "
-                            "static smem %zu, max dyn %d\n", CIN, P, SPLIT, NPAD, ATM, pl.occ, pl.ring, pl.smem, got,
+                            "static smem %zu, max dyn %d\n", CIN, P, SPLIT, NPAD, STK, pl.occ, pl.ring, pl.smem, got,
                     cudaGetErrorString(oe), fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes);
             cudaGetLastError();
         }
@@ -695,7 +704,7 @@ static int launch_thin(const CUtensorMap& tmA, ThinArgs& a, cudaStream_t stream)
             const char* e = getenv("PGK_THIN_PAIR");
             pair = e ? atoi(e) != 0 : 1;
         }
-        a.pair = !ATM && pair && best_pl.ring >= 8 && best_rc % 2 == 0;
+        a.pair = !STK && pair && best_pl.ring >= 8 && best_rc % 2 == 0;
     }
     pgk_launch(kern, best_grid, kThinThreads, best_pl.smem, stream, tmA, a);
     return PGK_OK;
@@ -756,18 +765,19 @@ extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N
     }
     cudaStream_t st = (cudaStream_t)stream;
     int rc = PGK_ERR_ARG;
-    // PGK_THIN_ATM=1 (experimental, see the kernel header): A operands from tensor memory in the one-plane mode
-    static int atm = -1;
-    if (atm < 0) {
-        const char* e = getenv("PGK_THIN_ATM");
-        atm = e ? atoi(e) != 0 : 0;
+    // one-plane mode: the input-row-stationary flavour (see the kernel header); PGK_THIN_STK=0 keeps the
+    // output-row-stationary issue order for A/B runs
+    static int stk = -1;
+    if (stk < 0) {
+        const char* e = getenv("PGK_THIN_STK");
+        stk = e ? atoi(e) != 0 : 1;
     }
-#define PGK_THIN_ATM_CASE(C_, N_) \
-    if (atm && Pr == 1 && Cin == C_ && a.Npad == N_) rc = launch_thin<C_, 1, 0, N_, 1>(tmA, a, st);
-    PGK_THIN_ATM_CASE(8, 16) PGK_THIN_ATM_CASE(8, 32) PGK_THIN_ATM_CASE(8, 64)
-    PGK_THIN_ATM_CASE(16, 16) PGK_THIN_ATM_CASE(16, 32) PGK_THIN_ATM_CASE(16, 64)
-    PGK_THIN_ATM_CASE(32, 16) PGK_THIN_ATM_CASE(32, 32) PGK_THIN_ATM_CASE(32, 64)
-#undef PGK_THIN_ATM_CASE
+#define PGK_THIN_STK_CASE(C_, N_) \
+    if (stk && Pr == 1 && P == 1 && Cin == C_ && a.Npad == N_) rc = launch_thin<C_, 1, 0, N_, 1>(tmA, a, st);
+    PGK_THIN_STK_CASE(8, 16) PGK_THIN_STK_CASE(8, 32) PGK_THIN_STK_CASE(8, 64)
+    PGK_THIN_STK_CASE(16, 16) PGK_THIN_STK_CASE(16, 32) PGK_THIN_STK_CASE(16, 64)
+    PGK_THIN_STK_CASE(32, 16) PGK_THIN_STK_CASE(32, 32) PGK_THIN_STK_CASE(32, 64)
+#undef PGK_THIN_STK_CASE
 #define PGK_THIN_CASE_N(C_, P_, S_, N_) \
     if (rc == PGK_ERR_ARG && Cin == C_ && Pr == P_ && a.split_acc == S_ && a.Npad == N_) rc = launch_thin<C_, P_, S_, N_, 0>(tmA, a, st);
 #define PGK_THIN_CASE(C_, P_, S_) PGK_THIN_CASE_N(C_, P_, S_, 16) PGK_THIN_CASE_N(C_, P_, S_, 32) PGK_THIN_CASE_N(C_, P_, S_, 64)

@@ -2,6 +2,7 @@
 // pooling / masks / pixel norm, minibatch-stddev (with first and second derivative), the head and the WGAN-GP
 // algebra.  All HBM-bound: 16-byte vector access on the channel-innermost planes, warp-shuffle reductions.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <cuda_fp16.h>
 
@@ -25,6 +26,16 @@ extern "C" const char* pgk_last_error(void) { return g_err; }
 extern "C" int pgk_version(void) { return 100; }
 extern "C" long long pgk_launch_count(void) { return g_launches; }
 extern "C" void pgk_reset_launch_count(void) { g_launches = 0; }
+// programmatic dependent launch (pgk_common.cuh): on unless PGK_PDL=0; pgk_pdl_state(0 / 1) switches it at run time
+extern "C" int pgk_pdl_state(int set) {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("PGK_PDL");
+        on = e ? atoi(e) != 0 : 1;
+    }
+    if (set >= 0) on = set != 0;
+    return on;
+}
 extern "C" int pgk_arch_check(int device) {
     int major = 0;
     cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
@@ -49,8 +60,7 @@ inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 
 // ------------------------------------------------------------------------------------------
 // weight re-layout
 // ------------------------------------------------------------------------------------------
-// weight_index() -- element (co, ci, ky, kx) -> its index in wf and in wb -- lives in pgk_relayout.cuh together with the
-// phases of the tiled kernels below, so that the host can run the same index logic (tests/relayout_host_check.cpp)
+// weight_index() -- element (co, ci, ky, kx) -> its index in wf and in wb -- lives in pgk_relayout.cuh
 
 __global__ void prep_weight_kernel(const float* __restrict__ w, float c, int kind, int cin, int cin_stride, int cout,
                                    int ks, float* __restrict__ wf, float* __restrict__ wb) {
@@ -90,32 +100,6 @@ __global__ void unprep_grad_kernel(const float* __restrict__ dwp, float c, int k
         float v = c * dwp[fi];
         dw[o] = accumulate ? dw[o] + v : v;
     }
-}
-
-// Tiled flavour (PGK_PREP_TILED=1, experimental): one (32 output channels x 32 / 16 input channels x taps) tile per
-// CTA through shared memory, so that both the PyTorch side and the operand side are read / written in runs of 64
-// bytes or more (pgk_relayout.cuh).  The one-thread-per-element kernels above write wf / wb 4 bytes at a time into
-// different sectors: 25 us for a 512 x 512 x 3 x 3 layer, ~1 TB/s, at batch 4 several per cent of an iteration.
-__global__ void __launch_bounds__(256) prep_weight_tiled_kernel(const float* __restrict__ w, float c, int kind, int cin,
-                                                                int cin_stride, int cout, int ks,
-                                                                float* __restrict__ wf, float* __restrict__ wb) {
-    pgk_pdl_enter();
-    extern __shared__ float relayout_tile_s[];
-    const RelayoutTile t = relayout_tile(kind, cin, cin_stride, cout, ks, blockIdx.x, blockIdx.y);
-    relayout_load_w(relayout_tile_s, w, c, t, threadIdx.x, blockDim.x);
-    __syncthreads();
-    relayout_store_fb(relayout_tile_s, wf, wb, t, threadIdx.x, blockDim.x);
-}
-
-__global__ void __launch_bounds__(256) unprep_grad_tiled_kernel(const float* __restrict__ dwp, float c, int kind, int cin,
-                                                                int cin_stride, int cout, int ks, float* __restrict__ dw,
-                                                                int accumulate) {
-    pgk_pdl_enter();
-    extern __shared__ float relayout_tile_s[];
-    const RelayoutTile t = relayout_tile(kind, cin, cin_stride, cout, ks, blockIdx.x, blockIdx.y);
-    relayout_load_dwp(relayout_tile_s, dwp, t, threadIdx.x, blockDim.x);
-    __syncthreads();
-    relayout_store_dw(relayout_tile_s, dw, c, accumulate, t, threadIdx.x, blockDim.x);
 }
 
 __global__ void prep_posbias_kernel(const float* __restrict__ w, float c, int cin_stride, int ch, int Cout, int H,
@@ -1017,28 +1001,11 @@ inline unsigned grid_cap(long long blocks) {
 
 #define ST (cudaStream_t) stream
 
-// PGK_PREP_TILED=1 (experimental): the shared-memory tiled weight re-layout kernels
-static bool relayout_tiled() {
-    static int on = -1;
-    if (on < 0) {
-        const char* e = getenv("PGK_PREP_TILED");
-        on = e ? atoi(e) != 0 : 0;
-    }
-    return on != 0;
-}
-
 extern "C" int pgk_prep_weight(const float* w, float c, int kind, int cin, int cin_stride, int cout, int ks, float* wf,
                                float* wb, pgk_stream_t stream) {
     PGK_REQUIRE(kind >= 0 && kind <= 2, "pgk_prep_weight: bad kind %d", kind);
     PGK_REQUIRE(kind == PGK_W_CONV ? (ks == 1 || ks == 3) : ks == 4, "pgk_prep_weight: bad ks %d for kind %d", ks, kind);
     PGK_REQUIRE(cin_stride >= cin, "pgk_prep_weight: cin_stride < cin");
-    if (relayout_tiled()) {
-        const dim3 grid((unsigned)((cin + relayout_tci(ks) - 1) / relayout_tci(ks)), (unsigned)((cout + kTileCo - 1) / kTileCo));
-        pgk_launch(prep_weight_tiled_kernel, grid, 256, sizeof(float) * relayout_tile_floats(ks), ST, w, c, kind, cin,
-                   cin_stride, cout, ks, wf, wb);
-        PGK_LAUNCH_CHECK("pgk_prep_weight(tiled)");
-        return PGK_OK;
-    }
     long long total = (long long)cout * cin * ks * ks;
     pgk_launch(prep_weight_kernel, dim3(grid_cap((total + 255) / 256)), 256, 0, ST, w, c, kind, cin, cin_stride, cout, ks, wf, wb);
     PGK_LAUNCH_CHECK("pgk_prep_weight");
@@ -1048,13 +1015,6 @@ extern "C" int pgk_prep_weight(const float* w, float c, int kind, int cin, int c
 extern "C" int pgk_unprep_grad(const float* dwp, float c, int kind, int cin, int cin_stride, int cout, int ks,
                                float* dw, int accumulate, pgk_stream_t stream) {
     PGK_REQUIRE(kind >= 0 && kind <= 2, "pgk_unprep_grad: bad kind %d", kind);
-    if (relayout_tiled()) {
-        const dim3 grid((unsigned)((cin + relayout_tci(ks) - 1) / relayout_tci(ks)), (unsigned)((cout + kTileCo - 1) / kTileCo));
-        pgk_launch(unprep_grad_tiled_kernel, grid, 256, sizeof(float) * relayout_tile_floats(ks), ST, dwp, c, kind, cin,
-                   cin_stride, cout, ks, dw, accumulate);
-        PGK_LAUNCH_CHECK("pgk_unprep_grad(tiled)");
-        return PGK_OK;
-    }
     long long total = (long long)cout * cin * ks * ks;
     pgk_launch(unprep_grad_kernel, dim3(grid_cap((total + 255) / 256)), 256, 0, ST, dwp, c, kind, cin, cin_stride, cout, ks, dw,
                                                                       accumulate);

@@ -53,12 +53,7 @@ struct WThinArgs {
     unsigned bias_mask;
 };
 
-// SW = 1 (PGK_WTHIN_SW128=1, experimental): the transposed rows are written as SWIZZLE_128B K-major tiles -- row m of a
-// buffer = 128 bytes = 64 pixels, 16-byte chunk c of row m at (c ^ (m & 7)) * 16, the two 64-pixel halves of a row
-// ("atoms") `atom` bytes apart -- instead of un-swizzled 8 x 16-byte core matrices.  Same buffers, same sizes, same
-// barriers; only the stmatrix destinations and the MMA descriptors differ.
-//
-// ATM = 1 (PGK_WTHIN_ATM=1, experimental): the A operand lives in TENSOR MEMORY.  Cin = 8 (the stacked chain):  The four ring
+// ATM = 1 (one-plane mode, 8 / 32 input channels; PGK_WTHIN_ATM=0 switches it off): the A operand lives in TENSOR MEMORY.  Cin = 8 (the stacked chain):  The four ring
 // slots of 32 accumulator rows are the four 32-lane quarters of tensor memory, and a quarter belongs to one warp: the
 // transposer warp (input row & 3) gathers its row straight from the raw [pixel][8 channels] buffer -- lane = (kx, ci)
 // reads X[p + kx][ci] for p = 0..127, conflict-free 16-bit loads -- packs pixel pairs and writes them with tcgen05.st
@@ -66,7 +61,7 @@ struct WThinArgs {
 // per K = 16 step (~75 cycles each measured, 8 per image row, against ~180 cycles of HBM time per row).  Same rings,
 // barriers, accumulators and flush; no ldmatrix / stmatrix and no transposed tiles for X.  A slot is rewritten while
 // the MMAs of the current row still read its lanes as the don't-care ky -- those accumulator rows are never flushed.
-template <int CIN, int P, int SW, int ATM>
+template <int CIN, int P, int ATM>
 __global__ void __launch_bounds__(kThreads, 2)
 wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WThinArgs a) {
     // Cin = 16 / 32 with ATM (one plane only): every input row is one 128-lane A tile of its own (four of them, 64
@@ -74,7 +69,7 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // = warp cg gathers from channel-group plane cg alone, conflict-free like the 8-channel case, and the flush maps
     // lane -> (cg, kx, ci) back.  Lanes 24 (ones row, quarter 0) .. 31 of a quarter and the quarters beyond Cin / 8 hold
     // zeros (written once at start-up).
-    static_assert(!ATM || (SW == 0 && (CIN == 8 || P == 1)), "tensor-memory A: no SW128, one plane for Cin >= 16");
+    static_assert(!ATM || (CIN == 8 || P == 1), "tensor-memory A: one plane for Cin >= 16");
     // row groups of XT3: 3 * CG shifted copies + one group whose first row is all ones (the bias-gradient row)
     constexpr int CG = CIN / 8, XG = 3 * CG;
     constexpr uint32_t xt_plane = (XG + 1) * kGrp, xt_buf = P * xt_plane;
@@ -96,17 +91,6 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // transposed X row buffers: [slot][plane] (three chains) or [plane][slot] (stacked)
     auto xt_at = [&](uint32_t buf, uint32_t p) {
         return STACK ? xt0 + p * (4u * xt_plane) + buf * xt_plane : xt0 + buf * xt_buf + p * xt_plane;
-    };
-    // SW: bytes between the two 64-pixel atoms of a transposed row buffer (X: all rows of the buffer -- of the four
-    // stacked slots when STACK; G: CGO * 8 rows), and the byte offset of (row m, 8-pixel chunk c) inside a buffer
-    constexpr uint32_t xt_atom = STACK ? 4u * (XG + 1) * 1024u : (XG + 1) * 1024u;
-    const uint32_t gt_atom = (uint32_t)a.CGO * 1024u;
-    auto sw_off = [](uint32_t atom, uint32_t m, uint32_t c) {
-        return (c >> 3) * atom + m * 128u + (((c & 7u) ^ (m & 7u)) << 4);
-    };
-    // base of the transposed X rows of slot `buf`, plane p, in the SW layout ([plane][atom][slot][rows] when STACK)
-    auto xt_sw = [&](uint32_t buf, uint32_t p) {
-        return STACK ? xt0 + p * (4u * xt_plane) + buf * ((XG + 1) * 1024u) : xt0 + buf * xt_buf + p * xt_plane;
     };
     const uint32_t bars = sbase + a.off_bars;
     const int kRaw = a.raw, kRawLog = a.raw_log2;
@@ -135,10 +119,7 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     for (uint32_t o = threadIdx.x * 16u; o < 4u * P * kGrp; o += kThreads * 16u) {
         const uint32_t buf = o / (P * kGrp), rem = o - buf * (P * kGrp);
         const uint32_t p = rem / kGrp, w = rem - p * kGrp;
-        if (SW)   // rows XG*8 .. XG*8+7 of both atoms (1024 bytes each)
-            st_shared_v4(xt_sw(buf, p) + (w >> 10) * xt_atom + XG * 1024u + (w & 1023u), make_uint4(0, 0, 0, 0));
-        else
-            st_shared_v4(xt_at(buf, p) + XG * kGrp + w, make_uint4(0, 0, 0, 0));
+        st_shared_v4(xt_at(buf, p) + XG * kGrp + w, make_uint4(0, 0, 0, 0));
     }
     fence_proxy_async();
     const unsigned nacc = STACK ? 4u : 3u;
@@ -319,12 +300,9 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     } else if (warp == 5) {
         // ---- MMA issue
         const uint32_t idesc = idesc_bf16(a.Npad, 0, 0);
-        // K-major, no swizzle: LBO = next 8 pixels, SBO = next 8 rows; SW: 128-byte rows, SBO = 8 rows, SWIZZLE_128B
-        const uint64_t dhi = SW ? smem_desc(0, 16, 1024, 2) : smem_desc(0, 128, kGrp, 0);
+        // K-major, no swizzle: LBO = next 8 pixels, SBO = next 8 rows
+        const uint64_t dhi = smem_desc(0, 128, kGrp, 0);
         const uint32_t gtp16 = gt_plane >> 4;
-        // K = 16 step ks of a 128-pixel row, in 16-byte units from the buffer base
-        auto kx16 = [&](int ks) { return SW ? (uint32_t)(((ks >> 2) * xt_atom + (ks & 3) * 32) >> 4) : (uint32_t)(ks * 16); };
-        auto kg16 = [&](int ks) { return SW ? (uint32_t)(((ks >> 2) * gt_atom + (ks & 3) * 32) >> 4) : (uint32_t)(ks * 16); };
         uint32_t gx = 0, gg = 0, rows_done = 0, used = 0;
         for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
             wait_bar(xtfull(gx & 3), (gx >> 2) & 1);
@@ -353,9 +331,8 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                         for (int pi = 0; pi < P; ++pi) {
 #pragma unroll
                             for (int pj = 0; pj < P - pi; ++pj)
-                                mma_bf16(d, dhi | (uint64_t)(SW ? xb[ky] + (pi * xt_plane) / 16 + kx16(ks)
-                                                                : xb[ky] + (pi * xt_plane + ks * 256) / 16),
-                                         bd0 + (uint32_t)(pj * gtp16 + (SW ? kg16(ks) : (uint32_t)(ks * 16))), idesc,
+                                mma_bf16(d, dhi | (uint64_t)(xb[ky] + (pi * xt_plane + ks * 256) / 16),
+                                         bd0 + (uint32_t)(pj * gtp16 + ks * 16), idesc,
                                          (ks == 0 && pi + pj == 0) ? later : 1u);
                         }
                     };
@@ -380,9 +357,8 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                             for (int pi = 0; pi < P; ++pi) {
 #pragma unroll
                                 for (int pj = 0; pj < P - pi; ++pj)
-                                    mma_bf16(d, dhi | (uint64_t)(SW ? ((xt0 + pi * (4u * xt_plane)) >> 4) + kx16(ks)
-                                                                    : (xt0 + pi * (4u * xt_plane) + ks * 256) >> 4),
-                                             bd0 + (uint32_t)(pj * gtp16 + (SW ? kg16(ks) : (uint32_t)(ks * 16))), idesc,
+                                    mma_bf16(d, dhi | (uint64_t)((xt0 + pi * (4u * xt_plane) + ks * 256) >> 4),
+                                             bd0 + (uint32_t)(pj * gtp16 + ks * 16), idesc,
                                              (ks == 0 && pi + pj == 0) ? later4 : 1u);
                             }
                         }
@@ -469,13 +445,10 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                         const int kx = r % 3, p = r / 3;
                         uint32_t v[4];
                         ldmatrix_x4_trans(src0 + p * rawx_plane + cg * kCgBytes + (blk * 32 + lj * 8 + li + kx) * 16, v);
-                        if (SW)
-                            stmatrix_x4(xt_sw(b, p) + sw_off(xt_atom, (kx * CG + cg) * 8 + li, blk * 4 + lj), v);
-                        else
-                            stmatrix_x4(xt_at(b, p) + (kx * CG + cg) * kGrp + (blk * 4 + lj) * 128 + li * 16, v);
+                        stmatrix_x4(xt_at(b, p) + (kx * CG + cg) * kGrp + (blk * 4 + lj) * 128 + li * 16, v);
                     }
                     if (!ATM && warp == 0 && lane < 16) {   // the ones row (plane 0, row 0 of group XG), 16 pixel chunks
-                        const uint32_t dst = SW ? xt_sw(b, 0) + sw_off(xt_atom, XG * 8, lane) : xt_at(b, 0) + XG * kGrp + lane * 128;
+                        const uint32_t dst = xt_at(b, 0) + XG * kGrp + lane * 128;
                         st_shared_v4(dst, make_uint4(one16, one16, one16, one16));
                     }
                     fence_proxy_async();
@@ -497,10 +470,7 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                         const int cg = r % a.CGO, p = r / a.CGO;
                         uint32_t v[4];
                         ldmatrix_x4_trans(src0 + p * rawg_plane + cg * kGrp + (blk * 32 + lj * 8 + li) * 16, v);
-                        if (SW)
-                            stmatrix_x4(dst0 + p * gt_plane + sw_off(gt_atom, cg * 8 + li, blk * 4 + lj), v);
-                        else
-                            stmatrix_x4(dst0 + p * gt_plane + cg * kGrp + (blk * 4 + lj) * 128 + li * 16, v);
+                        stmatrix_x4(dst0 + p * gt_plane + cg * kGrp + (blk * 4 + lj) * 128 + li * 16, v);
                     }
                     fence_proxy_async();
                     __syncwarp();
@@ -608,9 +578,9 @@ struct WThinPlan {
     int occ, raw, smem;
 };
 
-template <int CIN, int P, int SW, int ATM>
+template <int CIN, int P, int ATM>
 static int launch_wthin(const CUtensorMap& tmX, const CUtensorMap& tmG, WThinArgs& a, cudaStream_t stream) {
-    auto kern = wgrad_thin_kernel<CIN, P, SW, ATM>;
+    auto kern = wgrad_thin_kernel<CIN, P, ATM>;
     static bool attr = false;
     static WThinPlan plans[4];   // by Cout / 8 -> index 0..3 (8, 16, 32, 64)
     static bool have[4] = {};
@@ -648,8 +618,8 @@ static int launch_wthin(const CUtensorMap& tmX, const CUtensorMap& tmG, WThinArg
             cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, kern, kThreads, pl.smem);
             cudaFuncAttributes fa;
             cudaFuncGetAttributes(&fa, kern);
-            fprintf(stderr, "pgk_wgrad_thin<%d,%d,%d,%d> Cout %d: plan occ %d raw %d smem %d | runtime says %d blocks/SM (%s), regs %d\n",
-                    CIN, P, SW, ATM, a.Cout, pl.occ, pl.raw, pl.smem, got, cudaGetErrorString(oe), fa.numRegs);
+            fprintf(stderr, "pgk_wgrad_thin<%d,%d,%d> Cout %d: plan occ %d raw %d smem %d | runtime says %d blocks/SM (%s), regs %d\n",
+                    CIN, P, ATM, a.Cout, pl.occ, pl.raw, pl.smem, got, cudaGetErrorString(oe), fa.numRegs);
             cudaGetLastError();
         }
         if (pl.occ == 0) {
@@ -742,25 +712,19 @@ extern "C" int pgk_wgrad_thin(const void* x, long long x_ps, const void* g, long
     }
     cudaStream_t st = (cudaStream_t)stream;
     int rc = PGK_ERR_ARG;
-    // PGK_WTHIN_SW128=1 (experimental, see the kernel header): SWIZZLE_128B K-major transposed tiles
-    static int sw128 = -1;
-    if (sw128 < 0) {
-        const char* e = getenv("PGK_WTHIN_SW128");
-        sw128 = e ? atoi(e) != 0 : 0;
-    }
-    // PGK_WTHIN_ATM=1 (experimental, see the kernel header): Cin = 8 with the stacked A operand in tensor memory
+    // one-plane mode, 8 / 32 input channels: the A operand in tensor memory (see the kernel header).  Measured per
+    // shape at batch 12 (tools/thin_bench.py): 8 -> 8 0.345 -> 0.278 ms, 8 -> 16 0.346 -> 0.299, 32 -> 16 0.234 -> 0.169,
+    // 32 -> 32 0.108 -> 0.084, 32 -> 64 0.128 -> 0.112; the 16-channel flavour was slower (0.139 -> 0.160) and stays on
+    // shared-memory operands.  PGK_WTHIN_ATM=0 switches it off for A/B runs.
     static int watm = -1;
     if (watm < 0) {
         const char* e = getenv("PGK_WTHIN_ATM");
-        watm = e ? atoi(e) != 0 : 0;
+        watm = e ? atoi(e) != 0 : 1;
     }
-    if (watm && Cin == 8 && Pr == 1) rc = launch_wthin<8, 1, 0, 1>(tmX, tmG, a, st);
-    if (watm && Cin == 8 && Pr == 2) rc = launch_wthin<8, 2, 0, 1>(tmX, tmG, a, st);
-    if (watm && Cin == 16 && Pr == 1) rc = launch_wthin<16, 1, 0, 1>(tmX, tmG, a, st);
-    if (watm && Cin == 32 && Pr == 1) rc = launch_wthin<32, 1, 0, 1>(tmX, tmG, a, st);
+    if (watm && Cin == 8 && Pr == 1) rc = launch_wthin<8, 1, 1>(tmX, tmG, a, st);
+    if (watm && Cin == 32 && Pr == 1) rc = launch_wthin<32, 1, 1>(tmX, tmG, a, st);
 #define PGK_WTHIN_CASE(C_, P_) \
-    if (rc == PGK_ERR_ARG && Cin == C_ && Pr == P_) \
-        rc = sw128 ? launch_wthin<C_, P_, 1, 0>(tmX, tmG, a, st) : launch_wthin<C_, P_, 0, 0>(tmX, tmG, a, st);
+    if (rc == PGK_ERR_ARG && Cin == C_ && Pr == P_) rc = launch_wthin<C_, P_, 0>(tmX, tmG, a, st);
     PGK_WTHIN_CASE(8, 1) PGK_WTHIN_CASE(16, 1) PGK_WTHIN_CASE(32, 1)
     PGK_WTHIN_CASE(8, 2) PGK_WTHIN_CASE(16, 2) PGK_WTHIN_CASE(32, 2)
     PGK_WTHIN_CASE(8, 3) PGK_WTHIN_CASE(16, 3) PGK_WTHIN_CASE(32, 3)

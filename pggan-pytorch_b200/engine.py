@@ -30,10 +30,6 @@ W_CONV, W_GFIRST, W_DLAST = 0, 1, 2
 # planes"): forward convolutions that run on the wide tensor-core kernel read a two-plane fp16 copy of their input and
 # an fp16 packing of their weights -- three products per FLOP instead of six.  Not yet run on a GPU: default off.
 FWD_FP16 = os.environ.get('PGK_FWD_FP16', '0') == '1'
-# Experimental follow-up (PGK_WGRAD_FP16X=1, needs PGK_FWD_FP16=1): the fp16 copy a forward convolution made of its input
-# stays with the activation, and the layer's weight gradient reads its high plane as the activation operand -- two
-# products instead of three (include/pgk.h, pgk_wgrad_fp16x).  Not yet run on a GPU: default off.
-WGRAD_FP16X = FWD_FP16 and os.environ.get('PGK_WGRAD_FP16X', '0') == '1'
 
 
 def _ints(vals):
@@ -118,8 +114,6 @@ def conv(x, w, cout, ks, out, ups=0, bias=None, posT=None, pos_s=None, act=0, ma
         call('pgk_conv_fp16', xh.data_ptr(), xh.stride(0), out.N, out.H, out.W, x.C, cout, ks, w[2].data_ptr(),
              w[2].stride(0), None if bias is None else bias.data_ptr(), None if posT is None else posT.data_ptr(),
              None if pos_s is None else pos_s.data_ptr(), act, out.ptr, out.P, out.ps)
-        if WGRAD_FP16X:
-            x.aux['h16'] = (xh, x.off, x.N)     # samples [x.off, x.off + x.N) of the storage, for the weight gradient
         if pn_r is not None:
             call('pgk_pixelnorm', out.ptr, out.ps, out.P, out.N * out.H * out.W, out.C, out.ptr, out.ps,
                  pn_r.data_ptr())
@@ -134,22 +128,6 @@ def conv(x, w, cout, ks, out, ups=0, bias=None, posT=None, pos_s=None, act=0, ma
 def wgrad(x, g, H, W, cin, cout, ks, ups, groups, group_n, dwp, db=None, bias_goffs=()):
     """dwp += sum over the (x offset, g offset) sample groups; db (optional, zeroed by the caller) += the bias gradient
     over the groups whose g offset is listed in bias_goffs (fused into the same launch on the thin-layer path)."""
-    h16 = x.aux.get('h16') if WGRAD_FP16X else None
-    if h16 is not None and not ups and min(x.P, g.P) >= 2:
-        # groups whose activation samples the forward pass copied to fp16 take the two-product kernel; the others
-        # (the penalty's (v, ua) term: x is a gradient there) stay on bf16 planes
-        xh, h_off, h_n = h16
-        lo = lambda a: x.off + a - h_off
-        fast = [(a, b) for a, b in groups if lo(a) >= 0 and lo(a) + group_n <= h_n]
-        if fast and _lib.load().pgk_wgrad_fp16x_supported(H, W, cin, cout, ks, len(fast), group_n):
-            call('pgk_wgrad_fp16x', xh.data_ptr(), g.ptr, g.ps, g.P, H, W, cin, cout, ks, len(fast), group_n,
-                 _ints([lo(a) for a, _ in fast]), _ints([b for _, b in fast]), dwp.data_ptr())
-            bg = [b for _, b in fast if b in bias_goffs]
-            if db is not None and bg:
-                bias_grad(g, H * W, cout, bg, group_n, db, accumulate=1)
-            groups = [gr for gr in groups if gr not in fast]
-            if not groups:
-                return
     xoff, goff = _ints([a for a, _ in groups]), _ints([b for _, b in groups])
     mask = sum(1 << i for i, (_, go) in enumerate(groups) if go in bias_goffs)
     pg_ = min(x.P, g.P, GRAD_PLANES)

@@ -19,6 +19,9 @@ call = _lib.call
 mixing_factors_override = None
 # last step's auxiliary outputs (per-sample gradient norms, penalty) for monitoring / tests
 last_aux = {}
+# test hook: keep the tapes (stored activations) of the last D / G step in last_aux['d_tape'] / ['g_tape'], so that a test
+# can read the LeakyReLU decisions the kernels took (tests/test_gpu_baseline_widths.py imposes them on the oracle)
+keep_tapes = False
 
 
 class _Deposit(torch.autograd.Function):
@@ -83,11 +86,14 @@ def _run(key, body, inputs):
         g = torch.cuda.CUDAGraph()
         _run.epoch += 1
         engine.CAPTURE_EPOCH = _run.epoch   # the weight re-layout must be part of the graph whatever the cache says
+        pdl = _lib.pdl_state()
+        _lib.pdl_state(False)               # programmatic launch edges inside a graph measured slower than plain ones
         try:
             with torch.cuda.graph(g):
                 c.outputs = body(*c.inputs)
         finally:
             engine.CAPTURE_EPOCH = 0
+            _lib.pdl_state(pdl)
         c.launches = _lib.launch_count() - before
         c.graph = g
     else:
@@ -143,6 +149,8 @@ def _d_body(D, G, iwass_lambda, iwass_epsilon, iwass_target):
                        groups=[(0, 0), (n, n), (2 * n, 3 * n), (3 * n, 2 * n)], bias_goffs=[0, n, 3 * n],
                        head_groups=[(0, 0), (n, n), (3 * n, 2 * n)], head_bias_goffs=[0, n],
                        img_pairs=dict(top=top_pairs, low=low_pairs), ev_pair=(T.ev, 2 * n, 3 * n))
+        if keep_tapes:
+            last_aux['d_tape'] = T
         return cost, d_real_loss, d_fake_loss, gs, norms, gp
     return body
 
@@ -186,6 +194,8 @@ def _g_body(G, D):
         eg.backward(TG, dimg, gs)
         cost = torch.empty(1, dtype=torch.float32, device=dev)
         call('pgk_mean_scale', T.scores.data_ptr(), n, -1.0, cost.data_ptr())
+        if keep_tapes:
+            last_aux['g_tape'] = (TG, T)
         return cost, gs
     return body
 

@@ -62,3 +62,58 @@ def relu_margin(fn):
     finally:
         F.leaky_relu = orig
     return min(margins) if margins else float('inf')
+
+
+# ---- imposing the kernels' LeakyReLU decisions on the oracle ------------------------------------------------------
+def d_masks(T, group, n):
+    """The LeakyReLU decisions (stored activation > 0) of the CUDA D forward pass for sample group `group` of a tape,
+    in the order in which oracle.discriminator_forward calls leaky_relu (network.py:225-240)."""
+    sl = lambda t: (t.sl(group * n, (group + 1) * n).float() > 0).cpu()
+    out = [sl(T.t0)]
+    if T.depth > 0:
+        out += [sl(T.t1), sl(T.t2)]
+        if T.fade:
+            out.append(sl(T.f))
+        for rec in T.blocks:
+            out += [sl(rec.a), sl(rec.b)]
+    return out + [sl(T.l1), sl(T.l2)]
+
+
+def g_masks(TG):
+    """The same for the generator's tape (the pixel norm keeps the sign), in oracle.generator_forward's order."""
+    out = []
+    for _, _, a, b in TG.acts:
+        out += [(a.float() > 0).cpu(), (b.float() > 0).cpu()]
+    return out
+
+
+class ForcedMasks(object):
+    """Context manager: inside it the oracle's leaky_relu calls take their decisions from `queue` (one bool tensor per
+    call, None = decide for yourself) instead of from the sign of their input.  LeakyReLU makes every gradient a
+    discontinuous function of the forward values; with the decisions of the CUDA forward pass imposed, what is left
+    between the two sides is rounding alone.  Counts the units whose own decision differs (`flips` of `units`)."""
+
+    def __init__(self, queue):
+        self.queue, self.i, self.flips, self.units = list(queue), 0, 0, 0
+
+    def __enter__(self):
+        import torch.nn.functional as F
+        self.F, self.orig = F, F.leaky_relu
+
+        def hooked(x, negative_slope=0.01, *a, **k):
+            m = self.queue[self.i] if self.i < len(self.queue) else None
+            self.i += 1
+            if m is None:
+                return self.orig(x, negative_slope, *a, **k)
+            assert tuple(m.shape) == tuple(x.shape), (self.i, tuple(m.shape), tuple(x.shape))
+            self.flips += int(((x.detach() > 0) != m).sum())
+            self.units += m.numel()
+            one = torch.ones((), dtype=x.dtype)
+            return x * torch.where(m, one, one * negative_slope)
+
+        F.leaky_relu = hooked
+        return self
+
+    def __exit__(self, *exc):
+        self.F.leaky_relu = self.orig
+        return False

@@ -10,6 +10,12 @@ The full 1024x1024 networks have 18.4 M parameters each and the gradients are as
 * Of every result the file keeps: losses and scores in full; for the fake image and for every parameter gradient its
   L2 norm and its values at up to 2048 seeded positions (`sample_index`), all of it when it is smaller -- an unbiased sample
   of the per-tensor relative error ||a-b|| / ||b|| the tolerance is defined on.
+* Everything is stored twice: as the reference computes it (fp32, keys as above) and from the SAME reference modules
+  converted with .double() on the same inputs (keys prefixed 'f64/').  LeakyReLU makes every gradient a discontinuous
+  function of the forward values, so the reference's fp32 result has a noise floor of its own -- units whose
+  pre-activation lies within fp32 rounding of zero take the other slope under another summation order.  The distance
+  between the two copies, per tensor, IS that floor, measured on the reference itself; the GPU tests hold the CUDA
+  path to max(1e-3, 3 x floor) against the fp64 copy, and report both numbers.
 
 Files: tests/golden/full_<name>.npz (a few hundred KB each).
 """
@@ -55,10 +61,10 @@ def inputs(cfg):
     return z1, z2, real, mix
 
 
-def compact(out, key, t):
+def compact(out, key, t, prefix=''):
     t = t.detach().reshape(-1)
-    out[key + '/norm'] = np.float64(t.double().norm())
-    out[key + '/samples'] = t[sample_index(key, t.numel())].numpy()
+    out[prefix + key + '/norm'] = np.float64(t.double().norm())
+    out[prefix + key + '/samples'] = t[sample_index(key, t.numel())].numpy()
 
 
 def load_into(module, params):
@@ -69,49 +75,66 @@ def load_into(module, params):
             m.c = params[name + '.c'].clone()      # a 0-d fp32 tensor, as network.py:19 leaves it
 
 
-def make(name):
+def run_reference(cfg, dtype, out, prefix):
+    """The reference's modules (converted to `dtype`) on the seeded parameters / inputs; results into out[prefix + key]."""
     import network
     import wgan_gp_loss
     import pggan_oracle as O
-    cfg = CONFIGS[name]
     res, ch, depth, alpha, n, seed = cfg
     shape = (1000, ch, res, res)
     G, D = network.Generator(shape), network.Discriminator(shape)
     load_into(G, O.make_generator_params(res, ch, seed=G_SEED))
     load_into(D, O.make_discriminator_params(res, ch, seed=D_SEED))
+    G.to(dtype)
+    D.to(dtype)
     G.depth = D.depth = depth
     G.alpha = D.alpha = alpha
-    z1, z2, real, mix = inputs(cfg)
-    out = {'meta': np.array([res, ch, depth, n, seed, G_SEED, D_SEED], dtype=np.int64), 'alpha': np.float64(alpha)}
+    z1, z2, real, mix = [t.to(dtype) for t in inputs(cfg)]
     with torch.no_grad():
         fake = G(z1)
-        compact(out, 'fake', fake)
-        out['d_real_scores'] = D(real).numpy()
-        out['d_fake_scores'] = D(fake).numpy()
+        compact(out, 'fake', fake, prefix)
+        out[prefix + 'd_real_scores'] = D(real).numpy()
+        out[prefix + 'd_fake_scores'] = D(fake).numpy()
     # the reference draws the mixing factors with uniform_() into a module global (wgan_gp_loss.py:15-17): hand it a
-    # buffer whose uniform_() leaves our seeded factors in place
+    # buffer whose uniform_() leaves our seeded factors in place (and a seed gradient of the right dtype, :21-23)
     class Fixed(torch.Tensor):
         def uniform_(self, *a, **k):
             return self
     wgan_gp_loss.mixing_factors = mix.clone().as_subclass(Fixed)
-    wgan_gp_loss.grad_outputs = None
+    wgan_gp_loss.grad_outputs = torch.ones(n, 1, dtype=dtype)
     d_cost, d_real_loss, d_fake_loss = wgan_gp_loss.wgan_gp_D_loss(D, G, real, z1)
     assert torch.equal(torch.Tensor(wgan_gp_loss.mixing_factors), mix)
     d_cost.backward()
-    out['d_cost'] = d_cost.detach().numpy()
-    out['d_real_loss'] = d_real_loss.detach().numpy()
-    out['d_fake_loss'] = d_fake_loss.detach().numpy()
+    out[prefix + 'd_cost'] = d_cost.detach().numpy()
+    out[prefix + 'd_real_loss'] = d_real_loss.detach().numpy()
+    out[prefix + 'd_fake_loss'] = d_fake_loss.detach().numpy()
     for k, p_ in D.named_parameters():
         if p_.grad is not None:
-            compact(out, 'Dgrad.' + k, p_.grad)
+            compact(out, 'Dgrad.' + k, p_.grad, prefix)
     g_cost = wgan_gp_loss.wgan_gp_G_loss(G, D, z2)
     g_cost.backward()
-    out['g_cost'] = g_cost.detach().numpy()
+    out[prefix + 'g_cost'] = g_cost.detach().numpy()
     for k, p_ in G.named_parameters():
         if p_.grad is not None:
-            compact(out, 'Ggrad.' + k, p_.grad)
+            compact(out, 'Ggrad.' + k, p_.grad, prefix)
+    return float(d_cost), float(g_cost)
+
+
+def make(name):
+    cfg = CONFIGS[name]
+    res, ch, depth, alpha, n, seed = cfg
+    out = {'meta': np.array([res, ch, depth, n, seed, G_SEED, D_SEED], dtype=np.int64), 'alpha': np.float64(alpha)}
+    dc, gc = run_reference(cfg, torch.float32, out, '')
+    dc64, gc64 = run_reference(cfg, torch.float64, out, 'f64/')
+    keys = [k[:-5] for k in out if k.endswith('/norm') and not k.startswith('f64/')]
+    floor = {}
+    for k in keys:
+        a, b = out[k + '/samples'].astype(np.float64), out['f64/' + k + '/samples']
+        floor[k] = float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+    worst = max(floor, key=floor.get)
     np.savez_compressed(os.path.join(HERE, 'full_%s.npz' % name), **out)
-    print(name, 'd_cost', float(d_cost), 'g_cost', float(g_cost), 'keys', len(out), flush=True)
+    print(name, 'd_cost %.6f (f64 %.6f)  g_cost %.6f (f64 %.6f)  keys %d  fp32-vs-fp64 floor: median %.2e, worst %.2e (%s)'
+          % (dc, dc64, gc, gc64, len(out), float(np.median(list(floor.values()))), floor[worst], worst), flush=True)
 
 
 if __name__ == '__main__':

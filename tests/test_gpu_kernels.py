@@ -130,14 +130,3 @@ CONV_FP16 = [(2, 16, 16, 64, 64, 3, 3, False), (3, 4, 4, 512, 512, 3, 3, True), 
 def test_conv_on_half_operand_planes(T, case):
     n, h, w, ci, co, ks, p, pos = case
     assert T.conv_fp16_case(n, h, w, ci, co, ks, P=p, pos=pos)
-
-
-WGRAD_FP16X = [(4, 16, 16, 64, 64, 3, 3, 1), (16, 4, 4, 128, 64, 3, 3, 2), (2, 32, 32, 128, 256, 3, 3, 3),
-               (2, 64, 64, 256, 512, 3, 2, 1), (64, 1, 1, 8192, 512, 1, 3, 1)]
-
-
-@experimental
-@pytest.mark.parametrize('case', WGRAD_FP16X, ids=lambda c: 'N%dx%d_%dx%d_%d-%d_k%d_P%d' % (c[0], c[7], c[1], c[2], c[3], c[4], c[5], c[6]))
-def test_wgrad_with_half_plane_activations(T, case):
-    n, h, w, ci, co, ks, p, ng = case
-    assert T.wgrad_fp16x_case(n, h, w, ci, co, ks, P=p, ngroups=ng)

@@ -189,53 +189,6 @@ def test_integration_doc_names_every_entry_point():
     assert not missing, missing
 
 
-def test_weight_gradient_routes_sample_groups_by_their_fp16_copy(monkeypatch):
-    """engine.wgrad under PGK_WGRAD_FP16X (host logic only, kernels stubbed): sample groups whose activation samples
-    carry the fp16 copy left by the forward conv go to pgk_wgrad_fp16x with offsets relative to that copy, their bias
-    gradients to pgk_bias_grad; groups outside it (the penalty's (v, ua) term lives in the spare sample slots) stay on
-    pgk_wgrad with their own bias mask; without a copy nothing changes."""
-    from importlib import import_module
-    E = import_module('pggan-pytorch_b200.engine')
-    calls = []
-    monkeypatch.setattr(E, 'call', lambda name, *a: calls.append((name, a)))
-
-    class FakeLib(object):
-        @staticmethod
-        def pgk_wgrad_fp16x_supported(*a):
-            return 1
-    monkeypatch.setattr(E._lib, 'load', lambda: FakeLib)
-    monkeypatch.setattr(E, 'WGRAD_FP16X', True)
-    n, B, slots = 3, 9, 3
-    x = E.PT.empty(B + slots, 4, 4, 64, 3, 'cpu')
-    g = E.PT.empty(B + slots, 4, 4, 64, 2, 'cpu')
-    dwp, db = torch.zeros(9 * 64, 64), torch.zeros(64)
-    groups = [(0, 0), (3, 3), (6, 6), (9, 6)]       # real, fake, mixed-w, (v in the spare slots, ua of mixed)
-    # no copy: one pgk_wgrad call over all four groups
-    E.wgrad(x, g, 4, 4, 64, 64, 3, 0, groups, n, dwp, db, bias_goffs=[0, 3])
-    assert [c[0] for c in calls] == ['pgk_wgrad']
-    assert calls[0][1][12] == 4 and calls[0][1][-1] == 0b0011
-    # the forward conv of samples [0, B) left its copy (made through a slice: aux is shared with the parent)
-    calls.clear()
-    xh = torch.zeros((2, B * x.per), dtype=torch.float16)
-    x.sl(0, B).aux['h16'] = (xh, 0, B)
-    E.wgrad(x, g, 4, 4, 64, 64, 3, 0, groups, n, dwp, db, bias_goffs=[0, 3])
-    names = [c[0] for c in calls]
-    assert names == ['pgk_wgrad_fp16x', 'pgk_bias_grad', 'pgk_wgrad']
-    fast = calls[0][1]
-    assert fast[0] == xh.data_ptr() and fast[9] == 3 and fast[10] == n
-    assert list(fast[11])[:3] == [0, 3, 6] and list(fast[12])[:3] == [0, 3, 6]
-    assert calls[1][1][5] == 2 and list(calls[1][1][7])[:2] == [0, 3]       # bias gradient of the real and fake groups
-    rest = calls[2][1]
-    assert rest[12] == 1 and list(rest[14])[:1] == [9] and list(rest[15])[:1] == [6] and rest[-1] == 0
-    # a copy that starts at sample 3 of the storage: offsets are relative to it, sample 0 is not covered
-    calls.clear()
-    x.aux['h16'] = (xh, 3, 6)
-    E.wgrad(x, g, 4, 4, 64, 64, 3, 0, groups[:3], n, dwp)
-    assert [c[0] for c in calls] == ['pgk_wgrad_fp16x', 'pgk_wgrad']
-    assert list(calls[0][1][11])[:2] == [0, 3] and list(calls[0][1][12])[:2] == [3, 6]
-    assert list(calls[1][1][14])[:1] == [0]
-
-
 def test_forward_conv_takes_the_fp16_operands_only_where_it_may(monkeypatch):
     """engine.conv under PGK_FWD_FP16 (host logic only, kernels stubbed): a forward conv of the fp32-faithful mode on a
     wide-kernel shape makes the fp16 copy and runs pgk_conv_fp16 (pixel norm chained); gradient-chain convs (mask),
@@ -251,7 +204,6 @@ def test_forward_conv_takes_the_fp16_operands_only_where_it_may(monkeypatch):
             return int(cin % 64 == 0 and not ups)
     monkeypatch.setattr(E._lib, 'load', lambda: FakeLib)
     monkeypatch.setattr(E, 'FWD_FP16', True)
-    monkeypatch.setattr(E, 'WGRAD_FP16X', True)
     x3, o3 = E.PT.empty(4, 8, 8, 64, 3, 'cpu'), E.PT.empty(4, 8, 8, 128, 3, 'cpu')
     wf, wt, wh = torch.zeros(9 * 64 * 128), torch.zeros(3, 128, 9 * 64, dtype=torch.bfloat16), \
         torch.zeros(2, 128, 9 * 64, dtype=torch.float16)
@@ -259,9 +211,7 @@ def test_forward_conv_takes_the_fp16_operands_only_where_it_may(monkeypatch):
     E.conv(x3.sl(0, 3), (wf, wt, wh), 128, 3, o3.sl(0, 3), act=1, fwd=True, pn_r=r)
     assert [c[0] for c in calls] == ['pgk_cvt_fp16x2', 'pgk_conv_fp16', 'pgk_pixelnorm']
     assert calls[0][1][3] == 3 * x3.per                       # the copy covers the three samples of the slice
-    xh, off, n = x3.aux['h16']
-    assert (off, n) == (0, 3) and xh.dtype == torch.float16 and tuple(xh.shape) == (2, 3 * x3.per)
-    assert calls[1][1][0] == xh.data_ptr() and calls[1][1][8] == wh.data_ptr()
+    assert calls[1][1][8] == wh.data_ptr()
     for kw, w in ((dict(fwd=False, mask=o3), (wf, wt, wh)),      # a gradient-chain conv
                   (dict(fwd=True, scale=0.5), (wf, wt, wh)),     # scaled output
                   (dict(fwd=True), (wf, wt))):                   # no fp16 packing of the weights (thin layers)
@@ -273,22 +223,6 @@ def test_forward_conv_takes_the_fp16_operands_only_where_it_may(monkeypatch):
     E.conv(x1, (wf, wt, wh), 128, 3, o1, fwd=True)            # the bf16 mode has one plane: nothing to gain
     assert [c[0] for c in calls] == ['pgk_conv']
 
-
-def test_tiled_weight_relayout_index_logic_on_the_host(tmp_path):
-    """The shared-memory tiled flavour of pgk_prep_weight / pgk_unprep_grad (PGK_PREP_TILED=1) keeps its index logic in
-    host-callable functions (csrc/pgk_relayout.cuh); tests/relayout_host_check.cpp runs the kernels' two phases thread
-    by thread on the CPU and compares every element with the one-thread-per-element mapping."""
-    import shutil
-    import subprocess
-    gxx = shutil.which('g++')
-    if gxx is None:
-        pytest.skip('no g++ in this environment')
-    exe = str(tmp_path / 'relayout_check')
-    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'relayout_host_check.cpp')
-    subprocess.run([gxx, '-O1', '-std=c++17', '-o', exe, src], check=True)
-    r = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
-    assert r.returncode == 0, r.stdout
-    assert r.stdout.strip().endswith('0 bad')
 
 
 @pytest.mark.parametrize('fp16', [False, True])
@@ -309,7 +243,6 @@ def test_python_sequencing_of_one_iteration_with_stubbed_kernels(monkeypatch, fp
     for m in (E, L, pg._lib):
         monkeypatch.setattr(m, 'call', fake_call)
     monkeypatch.setattr(E, 'FWD_FP16', fp16)
-    monkeypatch.setattr(E, 'WGRAD_FP16X', fp16)
     for cls in (pg.Generator, pg.Discriminator):
         monkeypatch.setattr(cls, '_input', lambda self, x: x.contiguous().float())
     for depth, alpha, nd_expect, ng_expect in ((0, 1.0, 8, 6), (2, 0.5, 18, 16), (3, 1.0, 20, 18)):
@@ -327,9 +260,8 @@ def test_python_sequencing_of_one_iteration_with_stubbed_kernels(monkeypatch, fp
         assert calls['pgk_gp_penalty'] == 1 and calls['pgk_stddev_bwd2'] == 1
         if fp16:
             assert calls['pgk_conv_fp16'] > 0 and calls['pgk_cvt_fp16x2'] == calls['pgk_conv_fp16']
-            assert depth == 0 or calls['pgk_wgrad_fp16x'] > 0    # (depth 0, batch 4: too few pixels for the wide kernel)
         else:
-            assert calls['pgk_conv_fp16'] == 0 and calls['pgk_wgrad_fp16x'] == 0 and calls['pgk_pack_operand_fp16'] == 0
+            assert calls['pgk_conv_fp16'] == 0 and calls['pgk_pack_operand_fp16'] == 0
         gcost = pg.wgan_gp_G_loss(G, D, torch.randn(4, 64))
         gcost.backward()
         assert sum(p.grad is not None for p in G.parameters()) == ng_expect

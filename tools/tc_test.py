@@ -1,5 +1,5 @@
 """Development aid (GPU box): tensor-core kernels vs the CUDA-core kernels of the same library on random operands.
-   python tools/tc_test.py [conv|fp16|wgrad16|thin|thin1|wthin|wgrad|all]"""
+   python tools/tc_test.py [conv|fp16|thin|thin1|wthin|wgrad|all]"""
 import os
 import sys
 import time
@@ -179,43 +179,6 @@ def wgrad_case(N, H, W, Cin, Cout, KS, P, ngroups=1):
     return e_tc < tol
 
 
-def wgrad_fp16x_case(N, H, W, Cin, Cout, KS, P=3, ngroups=1):
-    """pgk_wgrad_fp16x (activation operand = the high half plane of pgk_cvt_fp16x2's copy, two products) against an fp64
-    reference, next to the three-product bf16 path on the same operands (expected: ~1e-4 against ~1e-5)."""
-    g = torch.Generator(device='cuda').manual_seed(N * 1000 + H + Cin + Cout + 7)
-    ntot = N * ngroups + 2
-    x = torch.randn(ntot, Cin, H, W, device='cuda', generator=g)
-    gg = torch.randn(ntot, Cout, H, W, device='cuda', generator=g) * 1e-3       # gradient-sized values
-    xp, gp = E.PT.from_float(x, P), E.PT.from_float(gg, P)
-    xh = torch.empty((2, xp.N * xp.per), dtype=torch.float16, device='cuda')
-    call('pgk_cvt_fp16x2', xp.ptr, xp.ps, xp.P, xp.N * xp.per, xh.data_ptr(), xh.stride(0))
-    K = KS * KS * Cin
-    groups = [(1 + i * N, (ngroups - 1 - i) * N) for i in range(ngroups)]
-    if not lib.pgk_wgrad_fp16x_supported(H, W, Cin, Cout, KS, ngroups, N):
-        print('--  wgrad_fp16x N%d x%d groups %dx%d %d->%d k%d: shape not served by the wide kernel' % (N, ngroups, H, W, Cin, Cout, KS))
-        return True
-    d16 = torch.zeros(K, Cout, device='cuda')
-    call('pgk_wgrad_fp16x', xh.data_ptr(), gp.ptr, gp.ps, gp.P, H, W, Cin, Cout, KS, ngroups, N,
-         E._ints([a for a, _ in groups]), E._ints([b for _, b in groups]), d16.data_ptr())
-    d3 = torch.zeros(K, Cout, device='cuda')
-    E.wgrad(xp, gp, H, W, Cin, Cout, KS, 0, groups, N, d3)
-    torch.cuda.synchronize()
-    xd, gd = xp.float().double(), gp.float().double()
-    ref = torch.zeros(K, Cout, dtype=torch.float64, device='cuda')
-    for xo, go in groups:
-        xs = torch.nn.functional.pad(xd[xo:xo + N], (KS // 2,) * 4)
-        gs = gd[go:go + N]
-        for ky in range(KS):
-            for kx in range(KS):
-                tap = ky * KS + kx
-                ref[tap * Cin:(tap + 1) * Cin] += torch.einsum('nchw,nohw->co', xs[:, :, ky:ky + H, kx:kx + W], gs)
-    e16, e3 = rel(d16, ref), rel(d3, ref)
-    ok = e16 < 5e-4
-    print('%s wgrad_fp16x N%d x%d groups %dx%d %d->%d k%d P%d: fp16 x bf16x2 %.2e | bf16x2 x bf16x2 %.2e'
-          % ('ok ' if ok else 'BAD', N, ngroups, H, W, Cin, Cout, KS, P, e16, e3))
-    return ok
-
-
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else 'all'
     ok = True
@@ -244,13 +207,6 @@ def main():
         ok &= conv_fp16_case(9, 1, 1, 512, 8192, 1)
         ok &= conv_fp16_case(5, 1, 1, 8192, 512, 1)
         ok &= conv_fp16_case(40, 16, 16, 512, 512, 3)
-    if what in ('wgrad16', 'all'):
-        ok &= wgrad_fp16x_case(4, 16, 16, 64, 64, 3)
-        ok &= wgrad_fp16x_case(16, 4, 4, 128, 64, 3, ngroups=2)
-        ok &= wgrad_fp16x_case(2, 32, 32, 128, 256, 3, ngroups=3)
-        ok &= wgrad_fp16x_case(2, 64, 64, 256, 512, 3, P=2)
-        ok &= wgrad_fp16x_case(64, 1, 1, 8192, 512, 1)
-        ok &= wgrad_fp16x_case(32, 1, 1, 512, 8192, 1, ngroups=2)
     if what in ('thin', 'all'):
         ok &= conv_case(1, 128, 128, 16, 16, 3, 1)
         ok &= conv_case(2, 256, 256, 16, 16, 3, 3)
@@ -261,7 +217,7 @@ def main():
         ok &= conv_case(1, 512, 512, 16, 8, 3, 1, mask=True, act=0, fwd=False)
         ok &= conv_case(3, 128, 128, 32, 16, 3, 2)
     if what in ('thin1', 'all'):
-        # every (Cin, Npad) instance of the thin conv in the one-plane mode (what PGK_THIN_ATM=1 replaces)
+        # every (Cin, Npad) instance of the thin conv in the one-plane mode (the input-row-stationary flavour)
         for cin in (8, 16, 32):
             for cout in (8, 16, 32, 64):
                 ok &= conv_case(2, 32, 256, cin, cout, 3, 1)
