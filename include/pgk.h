@@ -92,9 +92,42 @@ int pgk_pack_operand(const float* w, int K, int Nn, void* out, long long out_ps,
  * counts pgk_conv's `wt` must point to THIS packing (wt_ps = the plane size). */
 long long pgk_pack_thin_plane_elems(int Cin, int Cout);
 int pgk_pack_thin(const float* w, int Cin, int Cout, void* out, long long out_ps, int P, pgk_stream_t stream);
+/* All of the above for every conv layer of a network in ONE launch (what the engine calls after each optimizer step;
+ * the three entry points above stay for single layers / tools and define the result bit for bit):
+ *   w, c, kind, cin, cin_stride, cout, ks   as pgk_prep_weight
+ *   planes                                  bf16 planes written to F / B (1 = bf16 mode, 3 = fp32-faithful mode)
+ *   wf, wb                                  the fp32 operands of pgk_prep_weight, or NULL (only the CUDA-core kernels read them)
+ *   F, F_ps / B, B_ps                       pgk_pack_operand(wf) / pgk_pack_operand(wb), `planes` planes F_ps / B_ps elements
+ *                                           apart; thinF / thinB = 1: pgk_pack_thin's layout instead (the buffer's padding
+ *                                           entries must have been zeroed once: they are not written).  B may be NULL.
+ *   F16, F16_ps                             pgk_pack_operand_fp16(wf) (two half planes), or NULL */
+typedef struct PgkPrepLayer {
+    const float* w;
+    float c;
+    int kind, cin, cin_stride, cout, ks, planes;
+    float* wf;
+    float* wb;
+    void* F;
+    long long F_ps;
+    void* B;
+    long long B_ps;
+    void* F16;
+    long long F16_ps;
+    int thinF, thinB;
+} PgkPrepLayer;
+int pgk_prep_multi(const PgkPrepLayer* layers, int n, pgk_stream_t stream);
 /* inverse map for weight gradients: dw (PyTorch layout) (+)= c * dwp (wf layout). */
 int pgk_unprep_grad(const float* dwp, float c, int kind, int cin, int cin_stride, int cout, int ks,
                     float* dw, int accumulate, pgk_stream_t stream);
+/* the same for every layer of a network in one launch (the arguments of pgk_unprep_grad, one entry per layer) */
+typedef struct PgkUnprepLayer {
+    const float* dwp;
+    float c;
+    int kind, cin, cin_stride, cout, ks;
+    float* dw;
+    int accumulate;
+} PgkUnprepLayer;
+int pgk_unprep_multi(const PgkUnprepLayer* layers, int n, pgk_stream_t stream);
 
 /* ---- the convolution (network.py:34, F.conv2d through cuDNN) ---------------------------
  * out[n,y,x,co] = E( sum_{tap,ci} X[n, y+dy, x+dx, ci] * wf[tap*Cin+ci][co] ), zero padded, stride 1.

@@ -22,6 +22,8 @@ SIGNATURES = {
     'pgk_unprep_grad': [P, F, I, I, I, I, I, P, I],
     'pgk_pack_operand': [P, I, I, P, L, I],
     'pgk_pack_thin': [P, I, I, P, L, I],
+    'pgk_prep_multi': [P, I],
+    'pgk_unprep_multi': [P, I],
     'pgk_conv': [P, I, I, L, I, I, I, I, I, I, I, P, P, L, P, P, P, I, P, L, F, P, L, P],
     'pgk_cvt_fp16x2': [P, L, I, L, P, L],
     'pgk_pack_operand_fp16': [P, I, I, P, L, I],
@@ -59,6 +61,22 @@ SIGNATURES = {
                       ctypes.c_double, P],
     'pgk_adam_multi': [P, I, L, F, F, F],
 }
+
+
+
+class PrepLayer(ctypes.Structure):
+    """PgkPrepLayer of include/pgk.h (one conv layer of pgk_prep_multi's table)."""
+    _fields_ = [('w', c_void_p), ('c', c_float), ('kind', c_int), ('cin', c_int), ('cin_stride', c_int),
+                ('cout', c_int), ('ks', c_int), ('planes', c_int), ('wf', c_void_p), ('wb', c_void_p),
+                ('F', c_void_p), ('F_ps', c_longlong), ('B', c_void_p), ('B_ps', c_longlong), ('F16', c_void_p),
+                ('F16_ps', c_longlong), ('thinF', c_int), ('thinB', c_int)]
+
+
+class UnprepLayer(ctypes.Structure):
+    """PgkUnprepLayer of include/pgk.h."""
+    _fields_ = [('dwp', c_void_p), ('c', c_float), ('kind', c_int), ('cin', c_int), ('cin_stride', c_int),
+                ('cout', c_int), ('ks', c_int), ('dw', c_void_p), ('accumulate', c_int)]
+
 
 _lib = None
 

@@ -118,7 +118,8 @@ def conv(x, w, cout, ks, out, ups=0, bias=None, posT=None, pos_s=None, act=0, ma
             call('pgk_pixelnorm', out.ptr, out.ps, out.P, out.N * out.H * out.W, out.C, out.ptr, out.ps,
                  pn_r.data_ptr())
         return out
-    call('pgk_conv', x.ptr, x.P, x.P if fwd else min(x.P, GRAD_PLANES), x.ps, out.N, out.H, out.W, x.C, cout, ks, ups, wf.data_ptr(), wt.data_ptr(),
+    call('pgk_conv', x.ptr, x.P, x.P if fwd else min(x.P, GRAD_PLANES), x.ps, out.N, out.H, out.W, x.C, cout, ks, ups,
+         None if wf is None else wf.data_ptr(), wt.data_ptr(),
          wt.stride(0), None if bias is None else bias.data_ptr(), None if posT is None else posT.data_ptr(),
          None if pos_s is None else pos_s.data_ptr(), act, mp, mps, scale, out.ptr, out.ps,
          None if pn_r is None else pn_r.data_ptr())
@@ -182,17 +183,42 @@ def pool_img(img, avg=1, scale=1.0):
 # ---------------------------------------------------------------------------------------------
 # prepared weights
 # ---------------------------------------------------------------------------------------------
+def _tc_channels(cin, cout, ks):
+    """Do these channel counts run on the wide tensor-core kernel at every (power-of-two) resolution?  Then the fp32
+    [K][Cout] operands, which only the CUDA-core kernels read, need not be produced."""
+    if os.environ.get('PGK_TC', '1') == '0':
+        return False
+    return bool(_lib.load().pgk_conv_tc_supported(1, 8, 8, cin, cout, 1 if ks == 4 else ks, 0))
+
+
 class ConvW(object):
-    """Kernel-side operands of one equalised-LR conv (network.py:8-41): c folded in, re-laid for the GEMMs."""
+    """Kernel-side operands of one equalised-LR conv (network.py:8-41): c folded in, re-laid for the GEMMs.  All stale
+    layers of a network are refreshed together by ONE pgk_prep_multi launch (`prepare`)."""
 
     def __init__(self, mod, kind, cin, cout, ks, cin_stride=None, pos_hw=None, need_wb=True):
         self.mod, self.kind, self.cin, self.cout, self.ks = mod, kind, cin, cout, ks
         self.cin_stride = cin_stride if cin_stride is not None else cin
         self.pos_hw, self.need_wb = pos_hw, need_wb
         self.wf = self.wb = self.posT = self.bias16 = self.dwp = None
-        self.F = self.B = None   # (fp32 [K][N], bf16 planes [3][N][K]) operand pairs: forward / data gradient
+        self.F = self.B = None   # (fp32 [K][N] or None, bf16 planes [3][N][K]) operand pairs: forward / data gradient
         self.version = None
         self.cap_epoch = 0
+        taps = ks * ks
+        if kind == W_CONV:
+            self.geom = (taps * cin, cout, taps * cout, cin)           # kf, nf, kb, nb
+            gf, gb = (cin, cout, ks), (cout, cin, ks)
+        elif kind == W_GFIRST:
+            self.geom = (cin, 16 * cout, 16 * cout, cin)
+            gf, gb = (cin, 16 * cout, 1), (16 * cout, cin, 1)
+        else:
+            self.geom = (16 * cin, cout, cout, 16 * cin)
+            gf, gb = (16 * cin, cout, 1), (cout, 16 * cin, 1)
+        # thin layers (csrc/pgk_conv_thin.cu) take their own packing; the data-gradient operand swaps the roles
+        thin = lambda ci, co: kind == W_CONV and ks == 3 and ci in (8, 16, 32) and co in (8, 16, 32, 64)
+        self.thin_f, self.thin_b = thin(cin, cout), thin(cout, cin)
+        # the fp32 operands are read by the CUDA-core kernels only: shapes that always take a tensor-core kernel skip them
+        self.need_wf_f = not _tc_channels(*gf)
+        self.need_wf_b = need_wb and not _tc_channels(*gb)
 
     @property
     def weight(self):
@@ -202,78 +228,126 @@ class ConvW(object):
     def bias(self):
         return self.mod.conv.bias
 
-    def ensure(self):
+    def stale(self, planes):
         w = self.weight
-        ver = (w._version, w.data_ptr(), self.bias._version, self.mod.cf)
-        if ver == self.version and (CAPTURE_EPOCH == 0 or self.cap_epoch == CAPTURE_EPOCH):
-            return self
-        dev = w.device
+        ver = (w._version, w.data_ptr(), self.bias._version, self.mod.cf, planes)
+        return ver != self.version or (CAPTURE_EPOCH != 0 and self.cap_epoch != CAPTURE_EPOCH)
+
+    def _allocate(self, dev):
         n = self.cout * self.cin * self.ks * self.ks
-        if self.wf is None or self.wf.device != dev:
-            self.wf = torch.empty(n, dtype=torch.float32, device=dev)
-            self.wb = torch.empty(n, dtype=torch.float32, device=dev) if self.need_wb else None
-            if self.pos_hw is not None:
-                self.posT = torch.empty(self.pos_hw[0] * self.pos_hw[1] * self.cout, dtype=torch.float32, device=dev)
-        call('pgk_prep_weight', w.data_ptr(), self.mod.cf, self.kind, self.cin, self.cin_stride, self.cout, self.ks,
-             self.wf.data_ptr(), None if self.wb is None else self.wb.data_ptr())
-        # tensor-core operands: [plane][output channel][K], K-major
-        taps = self.ks * self.ks
-        if self.kind == W_CONV:
-            kf, nf_, kb, nb = taps * self.cin, self.cout, taps * self.cout, self.cin
-        elif self.kind == W_GFIRST:
-            kf, nf_, kb, nb = self.cin, 16 * self.cout, 16 * self.cout, self.cin
+        kf, nf_, kb, nb = self.geom
+        lib = _lib.load()
+        self.wf = torch.empty(n, dtype=torch.float32, device=dev) if self.need_wf_f else None
+        self.wb = torch.empty(n, dtype=torch.float32, device=dev) if self.need_wf_b else None
+        if self.pos_hw is not None:
+            self.posT = torch.empty(self.pos_hw[0] * self.pos_hw[1] * self.cout, dtype=torch.float32, device=dev)
+        # tensor-core operands: [plane][output channel][K], K-major (the thin packing has padding entries that are
+        # never written: zeroed once here)
+        if self.thin_f:
+            ft = torch.zeros((3, lib.pgk_pack_thin_plane_elems(self.cin, self.cout)), dtype=BF16, device=dev)
         else:
-            kf, nf_, kb, nb = 16 * self.cin, self.cout, self.cout, 16 * self.cin
-        # thin layers (csrc/pgk_conv_thin.cu) take their own packing; the data-gradient operand swaps the roles
-        thin = lambda ci, co: self.kind == W_CONV and self.ks == 3 and ci in (8, 16, 32) and co in (8, 16, 32, 64)
-        thin_f, thin_b = thin(self.cin, self.cout), thin(self.cout, self.cin)
-        if self.F is None or self.F[1].device != dev:
-            lib = _lib.load()
-            shp_f = (3, lib.pgk_pack_thin_plane_elems(self.cin, self.cout)) if thin_f else (3, nf_, kf)
-            shp_b = (3, lib.pgk_pack_thin_plane_elems(self.cout, self.cin)) if thin_b else (3, nb, kb)
-            self.F = (self.wf, torch.empty(shp_f, dtype=BF16, device=dev))
-            self.B = (self.wb, torch.empty(shp_b, dtype=BF16, device=dev)) if self.need_wb else None
-        if thin_f:
-            call('pgk_pack_thin', self.wf.data_ptr(), self.cin, self.cout, self.F[1].data_ptr(), self.F[1].stride(0), 3)
-        else:
-            call('pgk_pack_operand', self.wf.data_ptr(), kf, nf_, self.F[1].data_ptr(), self.F[1].stride(0), 3)
-        if FWD_FP16 and not thin_f:
+            ft = torch.empty((3, nf_, kf), dtype=BF16, device=dev)
+        self.F = (self.wf, ft)
+        if FWD_FP16 and not self.thin_f:
             # third element of the forward operand tuple: [2 planes][output channel][K] IEEE half, times 2^PGK_FP16_WSHIFT
-            if len(self.F) < 3 or self.F[2].device != dev:
-                self.F = (self.F[0], self.F[1], torch.empty((2, nf_, kf), dtype=torch.float16, device=dev))
-            call('pgk_pack_operand_fp16', self.wf.data_ptr(), kf, nf_, self.F[2].data_ptr(), self.F[2].stride(0), 2)
+            self.F = (self.wf, ft, torch.empty((2, nf_, kf), dtype=torch.float16, device=dev))
+        self.B = None
         if self.need_wb:
-            if thin_b:
-                call('pgk_pack_thin', self.wb.data_ptr(), self.cout, self.cin, self.B[1].data_ptr(),
-                     self.B[1].stride(0), 3)
+            if self.thin_b:
+                bt = torch.zeros((3, lib.pgk_pack_thin_plane_elems(self.cout, self.cin)), dtype=BF16, device=dev)
             else:
-                call('pgk_pack_operand', self.wb.data_ptr(), kb, nb, self.B[1].data_ptr(), self.B[1].stride(0), 3)
+                bt = torch.empty((3, nb, kb), dtype=BF16, device=dev)
+            self.B = (self.wb, bt)
+
+    def fill(self, d, planes):
+        """Fill one PgkPrepLayer (include/pgk.h) for this layer; allocates the operand buffers on first use."""
+        w = self.weight
+        if self.F is None or self.F[1].device != w.device:
+            self._allocate(w.device)
+        d.w, d.c, d.kind = w.data_ptr(), self.mod.cf, self.kind
+        d.cin, d.cin_stride, d.cout, d.ks, d.planes = self.cin, self.cin_stride, self.cout, self.ks, planes
+        d.wf = None if self.wf is None else self.wf.data_ptr()
+        d.wb = None if self.wb is None else self.wb.data_ptr()
+        d.F, d.F_ps, d.thinF = self.F[1].data_ptr(), self.F[1].stride(0), int(self.thin_f)
+        if self.B is not None:
+            d.B, d.B_ps, d.thinB = self.B[1].data_ptr(), self.B[1].stride(0), int(self.thin_b)
+        else:
+            d.B, d.B_ps, d.thinB = None, 0, 0
+        if len(self.F) > 2:
+            d.F16, d.F16_ps = self.F[2].data_ptr(), self.F[2].stride(0)
+        else:
+            d.F16, d.F16_ps = None, 0
+
+    def finish(self, planes):
+        """The per-layer extras after the batched launch, and the cache key."""
+        w = self.weight
         if self.pos_hw is not None:
             call('pgk_prep_posbias', w.data_ptr(), self.mod.cf, self.cin_stride, self.cin, self.cout, self.pos_hw[0],
                  self.pos_hw[1], self.posT.data_ptr())
         if self.kind == W_GFIRST:
             self.bias16 = self.bias.detach().repeat(16)
-        self.version = ver
+        self.version = (w._version, w.data_ptr(), self.bias._version, self.mod.cf, planes)
         self.cap_epoch = CAPTURE_EPOCH
+
+    def ensure(self, planes=3):
+        if self.stale(planes):
+            prepare([self], planes)
         return self
 
     def scratch(self):
-        if self.dwp is None or self.dwp.device != self.wf.device:
-            self.dwp = torch.empty_like(self.wf)
+        dev = self.weight.device
+        if self.dwp is None or self.dwp.device != dev:
+            self.dwp = torch.empty(self.cout * self.cin * self.ks * self.ks, dtype=torch.float32, device=dev)
         return self.dwp
 
-    def wgrad_into(self, grad, x, g, H, W, ups, groups, group_n, db=None, bias_goffs=()):
-        """grad (PyTorch layout, fp32) <- c * sum_groups x (*) g;  db (zero-initialised) += bias gradient."""
+    def wgrad_into(self, grad, x, g, H, W, ups, groups, group_n, db=None, bias_goffs=(), pending=None):
+        """grad (PyTorch layout, fp32) <- c * sum_groups x (*) g;  db (zero-initialised) += bias gradient.
+        pending (a list): the scratch was zeroed by the caller (zero_scratch) and the map back to the PyTorch layout is
+        left to one pgk_unprep_multi launch over all layers (unprep_all)."""
         dwp = self.scratch()
-        dwp.zero_()
+        if pending is None:
+            dwp.zero_()
         if self.kind == W_CONV:
             wgrad(x, g, H, W, self.cin, self.cout, self.ks, ups, groups, group_n, dwp, db, bias_goffs)
         elif self.kind == W_GFIRST:   # x: (n,1,1,cin), g: (n,1,1,16*cout)
             wgrad(x, g, 1, 1, self.cin, 16 * self.cout, 1, 0, groups, group_n, dwp)
         else:                          # x: (n,1,1,16*cin), g: (n,1,1,cout)
             wgrad(x, g, 1, 1, 16 * self.cin, self.cout, 1, 0, groups, group_n, dwp)
+        if pending is not None:
+            pending.append((self, grad))
+            return
         call('pgk_unprep_grad', dwp.data_ptr(), self.mod.cf, self.kind, self.cin, self.cin_stride, self.cout, self.ks,
              grad.data_ptr(), 0)
+
+
+def zero_scratch(convws):
+    """Zero the weight-gradient scratch of all these layers with one multi-tensor launch."""
+    torch._foreach_zero_([w.scratch() for w in convws])
+
+
+def unprep_all(pending):
+    """[(ConvW, grad)] -> one pgk_unprep_multi launch: grad (PyTorch layout) <- c * scratch ([K][Cout] layout)."""
+    if not pending:
+        return
+    table = (_lib.UnprepLayer * len(pending))()
+    for d, (w, grad) in zip(table, pending):
+        d.dwp, d.c, d.kind = w.dwp.data_ptr(), w.mod.cf, w.kind
+        d.cin, d.cin_stride, d.cout, d.ks = w.cin, w.cin_stride, w.cout, w.ks
+        d.dw, d.accumulate = grad.data_ptr(), 0
+    call('pgk_unprep_multi', ctypes.cast(table, ctypes.c_void_p), len(pending))
+
+
+def prepare(convws, planes):
+    """Refresh the operands of every stale layer of `convws` with one pgk_prep_multi launch (csrc/pgk_prep.cu)."""
+    todo = [w for w in convws if w.stale(planes)]
+    if not todo:
+        return
+    table = (_lib.PrepLayer * len(todo))()
+    for d, w in zip(table, todo):
+        w.fill(d, planes)
+    call('pgk_prep_multi', ctypes.cast(table, ctypes.c_void_p), len(todo))
+    for w in todo:
+        w.finish(planes)
 
 
 class GradSet(object):
@@ -307,12 +381,13 @@ class DEngine(object):
     def __init__(self, D):
         self.D = D
         self._cw = {}
+        self._P = 3
 
     def blk(self, k):
         """blocks[-k] (network.py:227,231,236)."""
         return self.D.blocks[len(self.D.blocks) - k]
 
-    def cw(self, mod, kind=W_CONV):
+    def _get(self, mod, kind=W_CONV):
         key = id(mod)
         if key not in self._cw:
             w = mod.conv.weight
@@ -323,7 +398,23 @@ class DEngine(object):
                 self._cw[key] = ConvW(mod, W_CONV, cin_stride - 1, cout, ks, cin_stride=cin_stride, pos_hw=(4, 4))
             else:
                 self._cw[key] = ConvW(mod, W_CONV, cin_stride, cout, ks)
-        return self._cw[key].ensure()
+        return self._cw[key]
+
+    def cw(self, mod, kind=W_CONV):
+        return self._get(mod, kind).ensure(self._P)
+
+    def prepare(self, depth, P):
+        """Refresh the operands of every conv layer active at `depth` in one launch (a no-op while they are current)."""
+        self._P = P
+        prepare(self.active_convs(depth), P)
+
+    def active_convs(self, depth):
+        ws = []
+        for k in range(depth + 1, 1, -1):
+            b = self.blk(k)
+            ws += [self._get(b.c1), self._get(b.c2)]
+        last = self.blk(1)
+        return ws + [self._get(last.c1), self._get(last.c2, W_DLAST)]
 
     def active_params(self, depth, fade):
         ps = []
@@ -352,6 +443,7 @@ class DEngine(object):
         assert B == ngroups * group_n and r == 4 * 2 ** depth, 'input resolution must match the current depth'
         T = SimpleNamespace(depth=depth, alpha=alpha, fade=fade, B=B, Bt=Bt, P=P, ngroups=ngroups, group_n=group_n,
                             ximg=ximg, blocks=[])
+        self.prepare(depth, P)
         new = lambda res, c: PT.empty(Bt, res, res, c, P, dev)
         top = self.blk(depth + 1)
         ctop = top.fromRGB.conv.weight.shape[0]
@@ -524,6 +616,8 @@ class DEngine(object):
         top = self.blk(depth + 1)
         C = T.ximg.shape[1]
         r = T.ximg.shape[-1]
+        pending = []
+        zero_scratch(self.active_convs(depth))
 
         def rgb(mod, t_ua, res, pairs_):
             gw, gb = gs[mod.conv.weight], gs[mod.conv.bias]
@@ -538,7 +632,7 @@ class DEngine(object):
         def conv_layer(mod, x, ua, res):
             w = self.cw(mod)
             w.wgrad_into(gs[mod.conv.weight], x, ua, res, res, 0, groups, n, db=gs[mod.conv.bias],
-                         bias_goffs=bias_goffs)
+                         bias_goffs=bias_goffs, pending=pending)
 
         if depth > 0:
             conv_layer(top.c1, T.t0, T.ua_t1, r)
@@ -549,7 +643,7 @@ class DEngine(object):
         last = self.blk(1)
         wl1, wl2 = self.cw(last.c1), self.cw(last.c2, W_DLAST)
         g1 = gs[last.c1.conv.weight]
-        wl1.wgrad_into(g1, T.hin, T.ua_l1, 4, 4, 0, head_groups, n)
+        wl1.wgrad_into(g1, T.hin, T.ua_l1, 4, 4, 0, head_groups, n, pending=pending)
         # the constant (stddev) input channel of c1: coefficient s_g for the ordinary terms, e for the v-chain
         for xo, go in head_groups:
             if ev_pair is not None and go == ev_pair[1] and xo == ev_pair[2]:
@@ -560,8 +654,10 @@ class DEngine(object):
             call('pgk_posbias_wgrad', u.ptr, u.ps, P, n, 4, 4, wl1.cout, coef.data_ptr(), last.c1.cf, wl1.cin_stride,
                  wl1.cin, g1.data_ptr())
         bias_grad(T.ua_l1, 16, wl1.cout, head_bias_goffs, n, gs[last.c1.conv.bias])
-        wl2.wgrad_into(gs[last.c2.conv.weight], T.l1.view(1, 1, 16 * wl1.cout), T.ua_l2, 1, 1, 0, head_groups, n)
+        wl2.wgrad_into(gs[last.c2.conv.weight], T.l1.view(1, 1, 16 * wl1.cout), T.ua_l2, 1, 1, 0, head_groups, n,
+                       pending=pending)
         bias_grad(T.ua_l2, 1, wl2.cout, head_bias_goffs, n, gs[last.c2.conv.bias])
+        unprep_all(pending)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -573,11 +669,12 @@ class GEngine(object):
     def __init__(self, G):
         self.G = G
         self._cw = {}
+        self._P = 3
 
     def block(self, i):
         return self.G.block0 if i == 0 else self.G.blocks[i - 1]
 
-    def cw(self, mod, kind=W_CONV):
+    def _get(self, mod, kind=W_CONV):
         key = id(mod)
         if key not in self._cw:
             w = mod.conv.weight
@@ -585,7 +682,22 @@ class GEngine(object):
                 self._cw[key] = ConvW(mod, W_GFIRST, w.shape[1], w.shape[0], 4, need_wb=False)
             else:
                 self._cw[key] = ConvW(mod, W_CONV, w.shape[1], w.shape[0], w.shape[2])
-        return self._cw[key].ensure()
+        return self._cw[key]
+
+    def cw(self, mod, kind=W_CONV):
+        return self._get(mod, kind).ensure(self._P)
+
+    def prepare(self, depth, P):
+        """Refresh the operands of every conv layer active at `depth` in one launch (a no-op while they are current)."""
+        self._P = P
+        prepare(self.active_convs(depth), P)
+
+    def active_convs(self, depth):
+        ws = [self._get(self.G.block0.c1, W_GFIRST), self._get(self.G.block0.c2)]
+        for i in range(1, depth + 1):
+            b = self.block(i)
+            ws += [self._get(b.c1), self._get(b.c2)]
+        return ws
 
     def active_params(self, depth, fade):
         ps = []
@@ -615,6 +727,7 @@ class GEngine(object):
         fade = depth > 0 and alpha < 1.0
         n, dev = z.shape[0], z.device
         T = SimpleNamespace(depth=depth, alpha=alpha, fade=fade, n=n, P=P, acts=[]) if tape else None
+        self.prepare(depth, P)
         zn = PT.empty(n, 1, 1, z.shape[1], P, dev)
         call('pgk_latent_norm', z.data_ptr(), n, z.shape[1], 1 if G.normalize_latents else 0, zn.ptr, P, zn.ps)
         b0 = G.block0
@@ -668,6 +781,8 @@ class GEngine(object):
         C = dimg.shape[1]
         res = dimg.shape[-1]
         groups = [(0, 0)]
+        pending = []
+        zero_scratch(self.active_convs(depth))
         hi = self.block(depth).toRGB
         hprev, _, u1, u2 = T.acts[depth]
         a_hi = 1.0 if depth == 0 else alpha
@@ -690,16 +805,18 @@ class GEngine(object):
             hprev, hup, u1, u2 = T.acts[i]
             w2 = self.cw(b.c2)
             da2 = self._act_bwd(d, u2, T, 'b%dc2' % i)
-            w2.wgrad_into(gs[b.c2.conv.weight], u1, da2, res, res, 0, groups, n, db=gs[b.c2.conv.bias], bias_goffs=[0])
+            w2.wgrad_into(gs[b.c2.conv.weight], u1, da2, res, res, 0, groups, n, db=gs[b.c2.conv.bias], bias_goffs=[0],
+                          pending=pending)
             d1 = conv(da2, w2.B, w2.cin, 3, PT.empty(n, res, res, w2.cin, P, dev))
             da1 = self._act_bwd(d1, u1, T, 'b%dc1' % i)
             if i == 0:
                 w1 = self.cw(b.c1, W_GFIRST)
-                w1.wgrad_into(gs[b.c1.conv.weight], T.zn, da1.view(1, 1, 16 * w1.cout), 1, 1, 0, groups, n)
+                w1.wgrad_into(gs[b.c1.conv.weight], T.zn, da1.view(1, 1, 16 * w1.cout), 1, 1, 0, groups, n, pending=pending)
                 bias_grad(da1, 16, w1.cout, [0], n, gs[b.c1.conv.bias])
                 break
             w1 = self.cw(b.c1)
-            w1.wgrad_into(gs[b.c1.conv.weight], hup, da1, res, res, 0, groups, n, db=gs[b.c1.conv.bias], bias_goffs=[0])
+            w1.wgrad_into(gs[b.c1.conv.weight], hup, da1, res, res, 0, groups, n, db=gs[b.c1.conv.bias], bias_goffs=[0],
+                          pending=pending)
             d_up = conv(da1, w1.B, w1.cin, 3, PT.empty(n, res, res, w1.cin, P, dev))
             res //= 2
             d = PT.empty(n, res, res, w1.cin, P, dev)
@@ -708,6 +825,7 @@ class GEngine(object):
                 d_lo = None
             else:
                 pool2(d_up, d, avg=0, a=1.0)
+        unprep_all(pending)
 
     def _act_bwd(self, d, y, T, name):
         """gradient w.r.t. the conv output given the gradient w.r.t. the (lrelu -> pixelnorm) output y."""

@@ -38,6 +38,7 @@ torch.Tensor.zero_ = lambda self: self
 torch.Tensor.copy_ = lambda self, src, non_blocking=False: self
 torch.Tensor.clone = lambda self, *a, **k: self
 torch._foreach_mul = lambda ts, s: list(ts)
+torch._foreach_zero_ = lambda ts: None
 torch.set_num_threads(1)
 
 

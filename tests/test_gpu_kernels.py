@@ -130,3 +130,79 @@ CONV_FP16 = [(2, 16, 16, 64, 64, 3, 3, False), (3, 4, 4, 512, 512, 3, 3, True), 
 def test_conv_on_half_operand_planes(T, case):
     n, h, w, ci, co, ks, p, pos = case
     assert T.conv_fp16_case(n, h, w, ci, co, ks, P=p, pos=pos)
+
+
+def test_prep_multi_is_the_single_layer_entry_points_bit_for_bit():
+    """pgk_prep_multi (csrc/pgk_prep.cu: every operand of every layer of a network in one launch, tiled through shared
+    memory) against the single-layer entry points that define the layouts -- pgk_prep_weight, pgk_pack_operand,
+    pgk_pack_thin, pgk_pack_operand_fp16 -- on a table that mixes every kind: wide and thin 3x3 layers, the 513-channel
+    stddev layer, widths that fill no tile, the dense 4x4 first-G / last-D layers; one and three planes."""
+    import ctypes
+    import torch
+    sys.path.insert(0, ROOT)
+    import pggan_b200 as pg
+    L = pg._lib
+    lib = L.load()
+    call = L.call
+    BF16 = torch.bfloat16
+    torch.manual_seed(0)
+    # (kind, cin, cin_stride, cout, ks, need_b)
+    specs = [(0, 64, 64, 128, 3, True), (0, 512, 513, 512, 3, True), (0, 8, 8, 16, 3, True), (0, 32, 32, 64, 3, True),
+             (0, 16, 16, 8, 3, True), (0, 64, 64, 32, 3, True), (0, 40, 40, 48, 3, True), (1, 512, 512, 512, 4, False),
+             (2, 512, 512, 512, 4, True), (0, 256, 256, 256, 3, True)]
+    thin = lambda ci, co, ks: ks == 3 and ci in (8, 16, 32) and co in (8, 16, 32, 64)
+    for planes in (1, 3):
+        table = (L.PrepLayer * len(specs))()
+        keep, expect = [], []
+        for d, (kind, cin, cs, cout, ks, need_b) in zip(table, specs):
+            taps = ks * ks
+            w = torch.randn(cout, cs, ks, ks, device='cuda')
+            c = 0.37 + 0.01 * cin
+            n = cout * cin * taps
+            if kind == 0:
+                kf, nf_, kb, nb = taps * cin, cout, taps * cout, cin
+            elif kind == 1:
+                kf, nf_, kb, nb = cin, 16 * cout, 16 * cout, cin
+            else:
+                kf, nf_, kb, nb = 16 * cin, cout, cout, 16 * cin
+            tf, tb = kind == 0 and thin(cin, cout, ks), kind == 0 and thin(cout, cin, ks)
+            new = lambda t, shape: (torch.zeros if t else torch.empty)(shape, dtype=BF16, device='cuda')
+            # the old path
+            wf, wb = torch.empty(n, device='cuda'), torch.empty(n, device='cuda')
+            call('pgk_prep_weight', w.data_ptr(), c, kind, cin, cs, cout, ks, wf.data_ptr(), wb.data_ptr() if need_b else None)
+            F0 = new(tf, (3, lib.pgk_pack_thin_plane_elems(cin, cout)) if tf else (3, nf_, kf))
+            B0 = new(tb, (3, lib.pgk_pack_thin_plane_elems(cout, cin)) if tb else (3, nb, kb)) if need_b else None
+            if tf:
+                call('pgk_pack_thin', wf.data_ptr(), cin, cout, F0.data_ptr(), F0.stride(0), planes)
+            else:
+                call('pgk_pack_operand', wf.data_ptr(), kf, nf_, F0.data_ptr(), F0.stride(0), planes)
+            if need_b:
+                if tb:
+                    call('pgk_pack_thin', wb.data_ptr(), cout, cin, B0.data_ptr(), B0.stride(0), planes)
+                else:
+                    call('pgk_pack_operand', wb.data_ptr(), kb, nb, B0.data_ptr(), B0.stride(0), planes)
+            H0 = None
+            if not tf:
+                H0 = torch.empty((2, nf_, kf), dtype=torch.float16, device='cuda')
+                call('pgk_pack_operand_fp16', wf.data_ptr(), kf, nf_, H0.data_ptr(), H0.stride(0), 2)
+            # the table entry
+            wf1, wb1 = torch.full_like(wf, float('nan')), torch.full_like(wb, float('nan'))
+            F1 = new(True, F0.shape) if tf else torch.full_like(F0, float('nan'))
+            B1 = None if B0 is None else (new(True, B0.shape) if tb else torch.full_like(B0, float('nan')))
+            H1 = None if H0 is None else torch.full_like(H0, float('nan'))
+            d.w, d.c, d.kind, d.cin, d.cin_stride, d.cout, d.ks, d.planes = w.data_ptr(), c, kind, cin, cs, cout, ks, planes
+            d.wf, d.wb = wf1.data_ptr(), wb1.data_ptr() if need_b else None
+            d.F, d.F_ps, d.thinF = F1.data_ptr(), F1.stride(0), int(tf)
+            d.B, d.B_ps, d.thinB = (B1.data_ptr(), B1.stride(0), int(tb)) if need_b else (None, 0, 0)
+            d.F16, d.F16_ps = (H1.data_ptr(), H1.stride(0)) if H1 is not None else (None, 0)
+            keep.append((w, wf, wb))
+            expect.append(((wf, wf1), (wb, wb1) if need_b else None, (F0[:planes], F1[:planes]),
+                           (B0[:planes], B1[:planes]) if need_b else None, (H0, H1) if H0 is not None else None))
+        call('pgk_prep_multi', ctypes.cast(table, ctypes.c_void_p), len(specs))
+        torch.cuda.synchronize()
+        for spec, pairs in zip(specs, expect):
+            for name, pair in zip(('wf', 'wb', 'F', 'B', 'F16'), pairs):
+                if pair is not None:
+                    a, b = pair
+                    assert torch.equal(a.view(torch.int16) if a.dtype != torch.float32 else a,
+                                       b.view(torch.int16) if b.dtype != torch.float32 else b), (planes, spec, name)
