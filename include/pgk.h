@@ -200,31 +200,40 @@ int pgk_from_rgb(const float* img, int N, int C, int H, int W, int Cout, const f
  * ups = 1: g has H/2 x W/2 and is read at (y/2, x/2) (the avg-pooled low-res branch, network.py:231-232). */
 int pgk_from_rgb_dgrad(const void* g, int P, long long g_ps, int N, int C, int H, int W, int Cout, const float* w,
                        float c, float scale, int ups, int accumulate, float* dimg, pgk_stream_t stream);
+/* DEVICE-SIDE FADE-IN SCALARS.  DepthManager changes alpha every iteration of a transition phase (plugins.py:57-81), and
+ * alpha enters five entry points as a host scalar (the lerps of network.py:131-138, 230-233 and their derivatives).  So
+ * that ONE captured CUDA graph can be replayed over a whole phase, each of them also takes optional device pointers
+ * d_*: when non-NULL the corresponding host scalar is multiplied by the float they point to at execution time (the
+ * caller passes the alpha-free part as the host scalar and keeps {alpha, 1 - alpha} in a two-float device buffer that
+ * it rewrites before every replay).  NULL = the host scalar alone, as before. */
 /* toRGB (network.py:49,65) with the generator's fade-in (network.py:131-138):
  * img[n,c,y,x] = a_hi * (sum_k c_hi*w_hi[c][k]*h[n,y,x,k] + b_hi[c])
  *              + a_lo * (sum_k c_lo*w_lo[c][k]*h_lo[n,y/2,x/2,k] + b_lo[c])     (second term iff h_lo != NULL) */
 int pgk_to_rgb(const void* h, int P, long long h_ps, int N, int H, int W, int Cin, const float* w_hi, float c_hi,
                const float* b_hi, float a_hi, const void* h_lo, long long hlo_ps, int Cin_lo, const float* w_lo,
-               float c_lo, const float* b_lo, float a_lo, int C, float* img, pgk_stream_t stream);
+               float c_lo, const float* b_lo, float a_lo, int C, float* img, const float* d_a_hi, const float* d_a_lo,
+               pgk_stream_t stream);
 /* data gradient of toRGB: dh[n,y,x,k] = scale * sum_c c*w[c][k] * dimg(n,c,y,x); pool = 1: dimg is summed over the
  * 2x2 block (2y..2y+1, 2x..2x+1) of a 2H x 2W image (the backward of toRGB_prev(upsample(h))). */
 int pgk_to_rgb_dgrad(const float* dimg, int N, int C, int H, int W, int Cin, const float* w, float c, float scale,
-                     int pool, void* dh, int P, long long dh_ps, pgk_stream_t stream);
+                     int pool, void* dh, int P, long long dh_ps, const float* d_scale, pgk_stream_t stream);
 /* weight/bias gradients of both 1x1 families in one pass over pixels:
  * dw[a*sa + k*sk] += scale_w * sum_{n,pix} IMG(n,a,pix) * t[n,pix,k];  d_colsum[k] += scale_b*sum t;  d_imgsum[a] += scale_b*sum IMG
  * IMG = img, or its 2x2 block sum when pool = 1 (img is then 2H x 2W).  Any output pointer may be NULL. */
 int pgk_rgb_wgrad(const float* img, int img_n0, const void* t, int P, long long t_ps, int t_n0, int N, int C, int H,
                   int W, int K, int pool, float scale_w, float scale_b, float* dw, int sa, int sk, float* d_colsum,
-                  float* d_imgsum, pgk_stream_t stream);
+                  float* d_imgsum, const float* d_scale, pgk_stream_t stream);
 
 /* ---- elementwise / reductions on planes ------------------------------------------------- */
 /* out = a * pool2x2(src) [+ b * other]; avg = 1: mean of the block (F.avg_pool2d, network.py:229,238),
  * avg = 0: sum (backward of the nearest upsample).  src is N x 2H x 2W x C, out/other N x H x W x C. */
 int pgk_pool2(const void* src, long long src_ps, int P, int N, int H, int W, int C, int avg, float a,
-              const void* other, long long other_ps, float b, void* out, long long out_ps, pgk_stream_t stream);
+              const void* other, long long other_ps, float b, void* out, long long out_ps, const float* d_a,
+              const float* d_b, pgk_stream_t stream);
 /* out[n,y,x,c] = scale * src[n, y>>ups, x>>ups, c] * lrelu'(ref[n,y,x,c]) (ref optional) */
 int pgk_mask_mul(const void* src, long long src_ps, int P, int N, int H, int W, int C, int ups, float scale,
-                 const void* ref, long long ref_ps, void* out, long long out_ps, pgk_stream_t stream);
+                 const void* ref, long long ref_ps, void* out, long long out_ps, const float* d_scale,
+                 pgk_stream_t stream);
 /* out = a*x + b*y (y optional) on planes with `count` elements per plane */
 int pgk_axpby(const void* x, long long x_ps, float a, const void* y, long long y_ps, float b, int P, long long count,
               void* out, long long out_ps, pgk_stream_t stream);

@@ -155,6 +155,7 @@ struct ExpandArgs {
     const float* w;
     int sc, sk;  // weight element (c,k) at w[c*sc + k*sk]
     float wscale;
+    const float* dmul;   // optional device scalar multiplied into wscale (the fade-in factor of a replayed CUDA graph)
     const float* bias;
     int act;
     Planes mask;
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(256) rgb_expand_kernel(ExpandArgs a) {
     extern __shared__ float wsm[];  // [C][K]
     for (int i = threadIdx.x; i < a.C * a.K; i += blockDim.x) {
         int c = i / a.K, k = i - c * a.K;
-        wsm[i] = a.wscale * a.w[(long long)c * a.sc + (long long)k * a.sk];
+        wsm[i] = a.wscale * (a.dmul ? __ldg(a.dmul) : 1.f) * a.w[(long long)c * a.sc + (long long)k * a.sk];
     }
     __syncthreads();
     const int nch = a.K >> 3;
@@ -229,6 +230,7 @@ struct ReduceSrc {
     float wscale;
     const float* bias;
     float a;
+    const float* da;   // optional device scalar multiplied into a
 };
 struct ReduceArgs {
     ReduceSrc s[2];
@@ -242,6 +244,8 @@ struct ReduceArgs {
 __global__ void __launch_bounds__(256) rgb_reduce_kernel(ReduceArgs a) {
     pgk_pdl_enter();
     extern __shared__ float wsm[];  // source 0: [C][K0], then source 1: [C][K1]
+    float sa[2];
+    for (int s = 0; s < 2; ++s) sa[s] = a.s[s].a * ((s < a.nsrc && a.s[s].da) ? __ldg(a.s[s].da) : 1.f);
     int off1 = a.C * a.s[0].K;
     for (int s = 0; s < a.nsrc; ++s) {
         int K = a.s[s].K;
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(256) rgb_reduce_kernel(ReduceArgs a) {
                     }
             }
 #pragma unroll
-            for (int c = 0; c < MAXC; ++c) acc[c] = fmaf(S.a, part[c], acc[c]);
+            for (int c = 0; c < MAXC; ++c) acc[c] = fmaf(sa[s], part[c], acc[c]);
         }
         for (int o = L >> 1; o > 0; o >>= 1) {
 #pragma unroll
@@ -295,7 +299,7 @@ __global__ void __launch_bounds__(256) rgb_reduce_kernel(ReduceArgs a) {
             for (int c = 0; c < a.C; ++c) {
                 float v = acc[c];
                 for (int s = 0; s < a.nsrc; ++s)
-                    if (a.s[s].bias) v = fmaf(a.s[s].a, __ldg(a.s[s].bias + c), v);
+                    if (a.s[s].bias) v = fmaf(sa[s], __ldg(a.s[s].bias + c), v);
                 long long o = ((long long)n * a.C + c) * HW + r;
                 a.img[o] = a.accumulate ? a.img[o] + v : v;
             }
@@ -312,19 +316,21 @@ __global__ void __launch_bounds__(256) rgb_reduce_px_kernel(ReduceArgs a) {
     extern __shared__ __align__(16) float wsm[];  // source 0: [C][K0], source 1: [C][K1], then bsum[MAXC]
     const int off1 = a.C * a.s[0].K;
     const int offb = off1 + (a.nsrc > 1 ? a.C * a.s[1].K : 0);
+    float sa[2];
+    for (int s = 0; s < 2; ++s) sa[s] = a.s[s].a * ((s < a.nsrc && a.s[s].da) ? __ldg(a.s[s].da) : 1.f);
     for (int s = 0; s < a.nsrc; ++s) {
         const int K = a.s[s].K;
         float* dst = wsm + (s ? off1 : 0);
         for (int i = threadIdx.x; i < a.C * K; i += blockDim.x) {
             const int c = i / K, k = i - c * K;
-            dst[i] = a.s[s].a * a.s[s].wscale * a.s[s].w[(long long)c * a.s[s].sc + (long long)k * a.s[s].sk];
+            dst[i] = sa[s] * a.s[s].wscale * a.s[s].w[(long long)c * a.s[s].sc + (long long)k * a.s[s].sk];
         }
     }
     if (threadIdx.x < MAXC) {
         float b = 0.f;
         if ((int)threadIdx.x < a.C)
             for (int s = 0; s < a.nsrc; ++s)
-                if (a.s[s].bias) b = fmaf(a.s[s].a, a.s[s].bias[threadIdx.x], b);
+                if (a.s[s].bias) b = fmaf(sa[s], a.s[s].bias[threadIdx.x], b);
         wsm[offb + threadIdx.x] = b;
     }
     __syncthreads();
@@ -374,6 +380,7 @@ struct RgbWgradArgs {
     int t_n0;
     int N, C, H, W, K, pool;
     float scale, scale_b;
+    const float* dmul;   // optional device scalar multiplied into both
     float* dw;
     int sa, sk;
     float* colsum;
@@ -383,6 +390,8 @@ struct RgbWgradArgs {
 
 __global__ void __launch_bounds__(256) rgb_wgrad_kernel(RgbWgradArgs a) {
     pgk_pdl_enter();
+    const float dm = a.dmul ? __ldg(a.dmul) : 1.f;
+    const float a_scale = a.scale * dm, a_scale_b = a.scale_b * dm;
     __shared__ float red[256][MAXC * 8 + 8 + 1];
     __shared__ float isum[MAXC];
     const int nch = a.K >> 3;
@@ -472,9 +481,9 @@ __global__ void __launch_bounds__(256) rgb_wgrad_kernel(RgbWgradArgs a) {
             for (int w = 0; w < 8; ++w) tot += red[w * 32 + chn][q];
             const int j = q & 7, c = q >> 3;
             if (c < MAXC) {
-                if (c < a.C && a.dw) atomicAdd(a.dw + (long long)c * a.sa + (long long)(chn * 8 + j) * a.sk, a.scale * tot);
+                if (c < a.C && a.dw) atomicAdd(a.dw + (long long)c * a.sa + (long long)(chn * 8 + j) * a.sk, a_scale * tot);
             } else if (a.colsum) {
-                atomicAdd(a.colsum + chn * 8 + j, a.scale_b * tot);
+                atomicAdd(a.colsum + chn * 8 + j, a_scale_b * tot);
             }
         }
     } else {
@@ -487,26 +496,27 @@ __global__ void __launch_bounds__(256) rgb_wgrad_kernel(RgbWgradArgs a) {
                 for (int l = 0; l < lanes; ++l) tot += red[l * nch + t][q];
                 int j = q & 7, c = q >> 3;
                 if (c < MAXC) {
-                    if (c < a.C && a.dw) atomicAdd(a.dw + (long long)c * a.sa + (long long)(t * 8 + j) * a.sk, a.scale * tot);
+                    if (c < a.C && a.dw) atomicAdd(a.dw + (long long)c * a.sa + (long long)(t * 8 + j) * a.sk, a_scale * tot);
                 } else if (a.colsum) {
-                    atomicAdd(a.colsum + t * 8 + j, a.scale_b * tot);
+                    atomicAdd(a.colsum + t * 8 + j, a_scale_b * tot);
                 }
             }
         }
     }
     __syncthreads();
-    if (t < a.C && a.imgsum) atomicAdd(a.imgsum + t, a.scale_b * isum[t]);
+    if (t < a.C && a.imgsum) atomicAdd(a.imgsum + t, a_scale_b * isum[t]);
 }
 
 // ------------------------------------------------------------------------------------------
 // planes elementwise
 // ------------------------------------------------------------------------------------------
 __global__ void pool2_kernel(Planes src, int N, int H, int W, int C, float a, Planes other, int has_other, float b,
-                             Planes out) {
+                             Planes out, const float* da, const float* db) {
     pgk_pdl_enter();
     const int nch = C >> 3;
     const long long total = (long long)N * H * W * nch;
-    const float sa = a;
+    const float sa = a * (da ? __ldg(da) : 1.f);
+    b *= db ? __ldg(db) : 1.f;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         int chunk = (int)(idx % nch);
@@ -535,8 +545,9 @@ __global__ void pool2_kernel(Planes src, int N, int H, int W, int C, float a, Pl
 }
 
 __global__ void mask_mul_kernel(Planes src, int N, int H, int W, int C, int ups, float scale, Planes ref, int has_ref,
-                                Planes out) {
+                                Planes out, const float* dscale) {
     pgk_pdl_enter();
+    scale *= dscale ? __ldg(dscale) : 1.f;
     const int nch = C >> 3;
     const long long total = (long long)N * H * W * nch;
     const int Hs = H >> ups, Ws = W >> ups;
@@ -1056,7 +1067,7 @@ extern "C" int pgk_from_rgb(const float* img, int N, int C, int H, int W, int Co
                             long long out_ps, pgk_stream_t stream) {
     ExpandArgs a;
     a.img = img, a.N = N, a.C = C, a.H = H, a.W = W, a.K = Cout;
-    a.w = w, a.sc = 1, a.sk = C, a.wscale = c, a.bias = bias, a.act = act;
+    a.w = w, a.sc = 1, a.sk = C, a.wscale = c, a.dmul = nullptr, a.bias = bias, a.act = act;
     a.mask = make_planes(mask_ref, mask_ps, P);
     a.has_mask = mask_ref != nullptr;
     a.pool = 0;
@@ -1065,10 +1076,11 @@ extern "C" int pgk_from_rgb(const float* img, int N, int C, int H, int W, int Co
 }
 
 extern "C" int pgk_to_rgb_dgrad(const float* dimg, int N, int C, int H, int W, int Cin, const float* w, float c,
-                                float scale, int pool, void* dh, int P, long long dh_ps, pgk_stream_t stream) {
+                                float scale, int pool, void* dh, int P, long long dh_ps, const float* d_scale,
+                                pgk_stream_t stream) {
     ExpandArgs a;
     a.img = dimg, a.N = N, a.C = C, a.H = H, a.W = W, a.K = Cin;
-    a.w = w, a.sc = Cin, a.sk = 1, a.wscale = c * scale, a.bias = nullptr, a.act = 0;
+    a.w = w, a.sc = Cin, a.sk = 1, a.wscale = c * scale, a.dmul = d_scale, a.bias = nullptr, a.act = 0;
     a.mask = make_planes(nullptr, 0, P);
     a.has_mask = 0;
     a.pool = pool;
@@ -1105,13 +1117,13 @@ static int launch_reduce(ReduceArgs& a, pgk_stream_t stream, const char* name) {
 extern "C" int pgk_to_rgb(const void* h, int P, long long h_ps, int N, int H, int W, int Cin, const float* w_hi,
                           float c_hi, const float* b_hi, float a_hi, const void* h_lo, long long hlo_ps, int Cin_lo,
                           const float* w_lo, float c_lo, const float* b_lo, float a_lo, int C, float* img,
-                          pgk_stream_t stream) {
+                          const float* d_a_hi, const float* d_a_lo, pgk_stream_t stream) {
     ReduceArgs a;
     a.nsrc = h_lo ? 2 : 1;
     a.s[0].t = make_planes(h, h_ps, P), a.s[0].K = Cin, a.s[0].ups = 0, a.s[0].w = w_hi, a.s[0].sc = Cin, a.s[0].sk = 1;
-    a.s[0].wscale = c_hi, a.s[0].bias = b_hi, a.s[0].a = a_hi;
+    a.s[0].wscale = c_hi, a.s[0].bias = b_hi, a.s[0].a = a_hi, a.s[0].da = d_a_hi;
     a.s[1].t = make_planes(h_lo, hlo_ps, P), a.s[1].K = Cin_lo, a.s[1].ups = 1, a.s[1].w = w_lo, a.s[1].sc = Cin_lo;
-    a.s[1].sk = 1, a.s[1].wscale = c_lo, a.s[1].bias = b_lo, a.s[1].a = a_lo;
+    a.s[1].sk = 1, a.s[1].wscale = c_lo, a.s[1].bias = b_lo, a.s[1].a = a_lo, a.s[1].da = d_a_lo;
     a.N = N, a.C = C, a.H = H, a.W = W, a.accumulate = 0, a.img = img;
     PGK_REQUIRE(!h_lo || (H % 2 == 0 && W % 2 == 0), "pgk_to_rgb: fade-in needs even H, W");
     return launch_reduce(a, stream, "pgk_to_rgb");
@@ -1123,7 +1135,7 @@ extern "C" int pgk_from_rgb_dgrad(const void* g, int P, long long g_ps, int N, i
     ReduceArgs a;
     a.nsrc = 1;
     a.s[0].t = make_planes(g, g_ps, P), a.s[0].K = Cout, a.s[0].ups = ups, a.s[0].w = w, a.s[0].sc = 1, a.s[0].sk = C;
-    a.s[0].wscale = c, a.s[0].bias = nullptr, a.s[0].a = scale;
+    a.s[0].wscale = c, a.s[0].bias = nullptr, a.s[0].a = scale, a.s[0].da = nullptr;
     a.s[1] = a.s[0];
     a.N = N, a.C = C, a.H = H, a.W = W, a.accumulate = accumulate, a.img = dimg;
     return launch_reduce(a, stream, "pgk_from_rgb_dgrad");
@@ -1131,12 +1143,12 @@ extern "C" int pgk_from_rgb_dgrad(const void* g, int P, long long g_ps, int N, i
 
 extern "C" int pgk_rgb_wgrad(const float* img, int img_n0, const void* t, int P, long long t_ps, int t_n0, int N,
                              int C, int H, int W, int K, int pool, float scale_w, float scale_b, float* dw, int sa,
-                             int sk, float* d_colsum, float* d_imgsum, pgk_stream_t stream) {
+                             int sk, float* d_colsum, float* d_imgsum, const float* d_scale, pgk_stream_t stream) {
     PGK_REQUIRE(C >= 1 && C <= MAXC, "pgk_rgb_wgrad: image channels must be 1..%d", MAXC);
     PGK_REQUIRE(K % 8 == 0 && K / 8 <= 256, "pgk_rgb_wgrad: K must be a multiple of 8 and <= 2048");
     RgbWgradArgs a;
     a.img = img, a.img_n0 = img_n0, a.t = make_planes(t, t_ps, P), a.t_n0 = t_n0;
-    a.N = N, a.C = C, a.H = H, a.W = W, a.K = K, a.pool = pool, a.scale = scale_w, a.scale_b = scale_b;
+    a.N = N, a.C = C, a.H = H, a.W = W, a.K = K, a.pool = pool, a.scale = scale_w, a.scale_b = scale_b, a.dmul = d_scale;
     a.dw = dw, a.sa = sa, a.sk = sk, a.colsum = d_colsum, a.imgsum = d_imgsum;
     a.R = (long long)N * H * W;
     long long ctas = (a.R + 255) / 256;
@@ -1150,25 +1162,26 @@ extern "C" int pgk_rgb_wgrad(const float* img, int img_n0, const void* t, int P,
 }
 
 extern "C" int pgk_pool2(const void* src, long long src_ps, int P, int N, int H, int W, int C, int avg, float a,
-                         const void* other, long long other_ps, float b, void* out, long long out_ps,
-                         pgk_stream_t stream) {
+                         const void* other, long long other_ps, float b, void* out, long long out_ps, const float* d_a,
+                         const float* d_b, pgk_stream_t stream) {
     PGK_REQUIRE(C % 8 == 0, "pgk_pool2: C must be a multiple of 8");
     long long total = (long long)N * H * W * (C >> 3);
     pgk_launch(pool2_kernel, dim3(grid_cap((total + 255) / 256)), 256, 0, ST, make_planes(src, src_ps, P), N, H, W, C,
                                                                 avg ? 0.25f * a : a, make_planes(other, other_ps, P),
-                                                                other != nullptr, b, make_planes(out, out_ps, P));
+                                                                other != nullptr, b, make_planes(out, out_ps, P), d_a, d_b);
     PGK_LAUNCH_CHECK("pgk_pool2");
     return PGK_OK;
 }
 
 extern "C" int pgk_mask_mul(const void* src, long long src_ps, int P, int N, int H, int W, int C, int ups, float scale,
-                            const void* ref, long long ref_ps, void* out, long long out_ps, pgk_stream_t stream) {
+                            const void* ref, long long ref_ps, void* out, long long out_ps, const float* d_scale,
+                            pgk_stream_t stream) {
     PGK_REQUIRE(C % 8 == 0, "pgk_mask_mul: C must be a multiple of 8");
     PGK_REQUIRE(!ups || (H % 2 == 0 && W % 2 == 0), "pgk_mask_mul: ups needs even H, W");
     long long total = (long long)N * H * W * (C >> 3);
     pgk_launch(mask_mul_kernel, dim3(grid_cap((total + 255) / 256)), 256, 0, ST, make_planes(src, src_ps, P), N, H, W, C, ups, scale,
                                                                    make_planes(ref, ref_ps, P), ref != nullptr,
-                                                                   make_planes(out, out_ps, P));
+                                                                   make_planes(out, out_ps, P), d_scale);
     PGK_LAUNCH_CHECK("pgk_mask_mul");
     return PGK_OK;
 }

@@ -63,60 +63,82 @@ __global__ void __launch_bounds__(256) prep_multi_kernel(const __grid_constant__
     const int co0 = (tl / tiles_ci) * kTileCo, ci0 = (tl % tiles_ci) * tci;
     const int nco = min(kTileCo, L.cout - co0), nci = min(tci, L.cin - ci0);
     // ---- load: for every output channel of the tile one contiguous run of nci * taps floats
+    // (element r of a run sits at ci_l * tp + tap = r + ci_l * (tp - taps): the padding is 0 for 1 / 9 taps, 1 for 16)
     const int run = nci * taps;
-    for (int e = threadIdx.x; e < nco * run; e += blockDim.x) {
-        const int co_l = e / run, r = e - co_l * run;
-        const int ci_l = r / taps, tap = r - ci_l * taps;
-        tile[co_l * row + ci_l * tp + tap] =
-            L.c * L.w[((long long)(co0 + co_l) * L.cin_stride + ci0) * taps + r];
+    for (int co_l = threadIdx.x >> 5; co_l < nco; co_l += blockDim.x >> 5) {
+        const float* src = L.w + ((long long)(co0 + co_l) * L.cin_stride + ci0) * taps;
+        for (int r = threadIdx.x & 31; r < run; r += 32)
+            tile[co_l * row + r + (taps == 16 ? (r >> 4) : 0)] = L.c * src[r];
     }
     __syncthreads();
     // operand geometry (engine.ConvW): forward [nf][kf], data gradient [nb][kb]
-    int kf, nf_, kb, nb;
-    if (L.kind == PGK_W_CONV) kf = taps * L.cin, nf_ = L.cout, kb = taps * L.cout, nb = L.cin;
-    else if (L.kind == PGK_W_GFIRST) kf = L.cin, nf_ = 16 * L.cout, kb = 16 * L.cout, nb = L.cin;
-    else kf = 16 * L.cin, nf_ = L.cout, kb = L.cout, nb = 16 * L.cin;
+    int kf, kb;
+    if (L.kind == PGK_W_CONV) kf = taps * L.cin, kb = taps * L.cout;
+    else if (L.kind == PGK_W_GFIRST) kf = L.cin, kb = 16 * L.cout;
+    else kf = 16 * L.cin, kb = L.cout;
     const int npad_f = L.cout < 16 ? 16 : L.cout, npad_b = L.cin < 16 ? 16 : L.cin;
-    // ---- pass 1, input channel fastest: forward operand (+ half packing), wb
-    for (int e = threadIdx.x; e < nco * taps * nci; e += blockDim.x) {
-        const int ci_l = e % nci, r = e / nci;
-        const int tap = r % taps, co_l = r / taps;
-        const float v = tile[co_l * row + ci_l * tp + tap];
-        const int co = co0 + co_l, ci = ci0 + ci_l, ky = tap / L.ks, kx = tap - ky * L.ks;
-        long long fi, bi;
-        weight_index(L.kind, L.cin, L.cout, L.ks, co, ci, ky, kx, fi, bi);
-        const int k_f = (int)(fi / nf_), n_f = (int)(fi - (long long)k_f * nf_);
-        if (L.F) {
-            const long long idx = L.thinF ? thin_index(k_f, n_f, L.cin, npad_f) : (long long)n_f * kf + k_f;
-            store_planes((bf16*)L.F, L.F_ps, L.planes, idx, v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    // ---- pass 1, a warp per (output channel, tap) row, lanes = input channels: forward operand (+ half packing), wb.
+    // Every destination is contiguous in ci: per row one base index, no division per element.
+    for (int r = warp; r < nco * taps; r += nwarps) {
+        const int co_l = r / taps, tap = r - co_l * taps;
+        const int co = co0 + co_l;
+        long long fbase, bbase;      // index of (co, ci0, tap) in F (standard layout) and in wb
+        if (L.kind == PGK_W_CONV) {
+            const int tapf = taps - 1 - tap;
+            fbase = (long long)co * kf + (long long)tap * L.cin + ci0;
+            bbase = ((long long)tapf * L.cout + co) * L.cin + ci0;
+        } else if (L.kind == PGK_W_GFIRST) {
+            fbase = ((long long)(15 - tap) * L.cout + co) * L.cin + ci0;
+            bbase = fbase;
+        } else {
+            fbase = (long long)co * kf + (long long)tap * L.cin + ci0;
+            bbase = fbase;
         }
-        if (L.F16) {
-            __half* o = (__half*)L.F16;
-            float s = v * (float)(1 << PGK_FP16_WSHIFT);
-            const long long idx = (long long)n_f * kf + k_f;
-            for (int p = 0; p < 2; ++p) {
-                const __half h = __float2half_rn(s);
-                o[p * L.F16_ps + idx] = h;
-                s -= __half2float(h);
+        if (lane < nci) {
+            const float v = tile[co_l * row + lane * tp + tap];
+            if (L.F) {
+                const long long idx = L.thinF ? thin_index(tap * L.cin + ci0 + lane, co, L.cin, npad_f) : fbase + lane;
+                store_planes((bf16*)L.F, L.F_ps, L.planes, idx, v);
             }
+            if (L.F16) {
+                __half* o = (__half*)L.F16;
+                float sv = v * (float)(1 << PGK_FP16_WSHIFT);
+                for (int p = 0; p < 2; ++p) {
+                    const __half h = __float2half_rn(sv);
+                    o[p * L.F16_ps + fbase + lane] = h;
+                    sv -= __half2float(h);
+                }
+            }
+            if (L.wb) L.wb[bbase + lane] = v;
         }
-        if (L.wb) L.wb[bi] = v;
     }
-    // ---- pass 2, output channel fastest: data-gradient operand, wf
+    // ---- pass 2, a warp per (input channel, tap) row, lanes = output channels: data-gradient operand, wf
     if (L.B || L.wf) {
-        for (int e = threadIdx.x; e < nci * taps * nco; e += blockDim.x) {
-            const int co_l = e % nco, r = e / nco;
-            const int tap = r % taps, ci_l = r / taps;
-            const float v = tile[co_l * row + ci_l * tp + tap];
-            const int co = co0 + co_l, ci = ci0 + ci_l, ky = tap / L.ks, kx = tap - ky * L.ks;
-            long long fi, bi;
-            weight_index(L.kind, L.cin, L.cout, L.ks, co, ci, ky, kx, fi, bi);
-            if (L.B) {
-                const int k_b = (int)(bi / nb), n_b = (int)(bi - (long long)k_b * nb);
-                const long long idx = L.thinB ? thin_index(k_b, n_b, L.cout, npad_b) : (long long)n_b * kb + k_b;
-                store_planes((bf16*)L.B, L.B_ps, L.planes, idx, v);
+        for (int r = warp; r < nci * taps; r += nwarps) {
+            const int ci_l = r / taps, tap = r - ci_l * taps;
+            const int ci = ci0 + ci_l;
+            long long fibase, bidx;     // index of (co0, ci, tap) in wf and in B (standard layout)
+            if (L.kind == PGK_W_CONV) {
+                const int tapf = taps - 1 - tap;
+                fibase = ((long long)tap * L.cin + ci) * L.cout + co0;
+                bidx = (long long)ci * kb + (long long)tapf * L.cout + co0;
+            } else if (L.kind == PGK_W_GFIRST) {
+                fibase = (long long)ci * (16 * L.cout) + (long long)(15 - tap) * L.cout + co0;
+                bidx = 0;               // (the first generator layer has no data-gradient operand)
+            } else {
+                fibase = ((long long)tap * L.cin + ci) * L.cout + co0;
+                bidx = fibase;
             }
-            if (L.wf) L.wf[fi] = v;
+            if (lane < nco) {
+                const float v = tile[lane * row + ci_l * tp + tap];
+                if (L.B) {
+                    const long long idx = L.thinB ? thin_index((taps - 1 - tap) * L.cout + co0 + lane, ci, L.cout, npad_b)
+                                                  : bidx + lane;
+                    store_planes((bf16*)L.B, L.B_ps, L.planes, idx, v);
+                }
+                if (L.wf) L.wf[fibase + lane] = v;
+            }
         }
     }
 }
@@ -140,24 +162,25 @@ __global__ void __launch_bounds__(256) unprep_multi_kernel(const __grid_constant
     const int tl = (int)blockIdx.x - t.tile0[li];
     const int co0 = (tl / tiles_ci) * kTileCo, ci0 = (tl % tiles_ci) * tci;
     const int nco = min(kTileCo, L.cout - co0), nci = min(tci, L.cin - ci0);
-    // ---- load, output channel fastest: dwp is [K][Cout] (the forward operand's layout)
-    for (int e = threadIdx.x; e < nci * taps * nco; e += blockDim.x) {
-        const int co_l = e % nco, r = e / nco;
-        const int tap = r % taps, ci_l = r / taps;
-        const int ky = tap / L.ks, kx = tap - ky * L.ks;
-        long long fi, bi;
-        weight_index(L.kind, L.cin, L.cout, L.ks, co0 + co_l, ci0 + ci_l, ky, kx, fi, bi);
-        tile[co_l * row + ci_l * tp + tap] = L.c * L.dwp[fi];
+    // ---- load, a warp per (input channel, tap) row, lanes = output channels: dwp is [K][Cout] (wf's layout)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int r = warp; r < nci * taps; r += nwarps) {
+        const int ci_l = r / taps, tap = r - ci_l * taps;
+        const int ci = ci0 + ci_l;
+        long long fibase;
+        if (L.kind == PGK_W_GFIRST) fibase = (long long)ci * (16 * L.cout) + (long long)(15 - tap) * L.cout + co0;
+        else fibase = ((long long)tap * L.cin + ci) * L.cout + co0;
+        if (lane < nco) tile[lane * row + ci_l * tp + tap] = L.c * L.dwp[fibase + lane];
     }
     __syncthreads();
     // ---- store: for every output channel one contiguous run of nci * taps floats of the PyTorch layout
     const int run = nci * taps;
-    for (int e = threadIdx.x; e < nco * run; e += blockDim.x) {
-        const int co_l = e / run, r = e - co_l * run;
-        const int ci_l = r / taps, tap = r - ci_l * taps;
-        const long long o = ((long long)(co0 + co_l) * L.cin_stride + ci0) * taps + r;
-        const float v = tile[co_l * row + ci_l * tp + tap];
-        L.dw[o] = L.accumulate ? L.dw[o] + v : v;
+    for (int co_l = warp; co_l < nco; co_l += nwarps) {
+        float* dst = L.dw + ((long long)(co0 + co_l) * L.cin_stride + ci0) * taps;
+        for (int r = lane; r < run; r += 32) {
+            const float v = tile[co_l * row + r + (taps == 16 ? (r >> 4) : 0)];
+            dst[r] = L.accumulate ? dst[r] + v : v;
+        }
     }
 }
 

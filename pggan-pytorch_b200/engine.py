@@ -94,6 +94,34 @@ def _mask(m):
     return (m.ptr, m.ps) if m is not None else (None, 0)
 
 
+class Fade(object):
+    """The fade-in factors alpha and 1 - alpha as the kernels take them: (host scalar, device pointer or None).
+    Eager mode: the host scalar carries everything.  CUDA-graph mode (wgan_gp_loss.cuda_graphs): the host scalar is the
+    alpha-free part and the kernel multiplies by the float at the device pointer, which the loss function rewrites
+    before every replay -- alpha changes every iteration of a transition phase (plugins.py:57-81), the graph does not."""
+    __slots__ = ('alpha', 'dev')
+
+    def __init__(self, alpha, dev=None):
+        self.alpha, self.dev = float(alpha), dev
+
+    def a(self, k=1.0):
+        return (k, self.dev.data_ptr()) if self.dev is not None else (k * self.alpha, None)
+
+    def b(self, k=1.0):
+        return (k, self.dev.data_ptr() + 4) if self.dev is not None else (k * (1.0 - self.alpha), None)
+
+    def write(self):
+        """(graph mode) put the current factors where the captured kernels read them"""
+        if self.dev is not None:
+            call('pgk_fill', self.dev.data_ptr(), 1, self.alpha)
+            call('pgk_fill', self.dev.data_ptr() + 4, 1, 1.0 - self.alpha)
+
+
+def _sc(v):
+    """scalar argument -> (host scalar, device multiplier pointer or None)"""
+    return v if isinstance(v, tuple) else (float(v), None)
+
+
 # ---------------------------------------------------------------------------------------------
 # thin op wrappers (argument marshalling only)
 # ---------------------------------------------------------------------------------------------
@@ -155,21 +183,24 @@ def from_rgb_dgrad(g, mod, dimg, scale=1.0, ups=0, accumulate=0):
          accumulate, dimg.data_ptr())
 
 
-def rgb_wgrad(img, img_n0, t, n, c, h, w, pool, scale_w, scale_b, dw, sa, sk, colsum, imgsum):
+def rgb_wgrad(img, img_n0, t, n, c, h, w, pool, scale_w, scale_b, dw, sa, sk, colsum, imgsum, dscale=None):
     call('pgk_rgb_wgrad', img.data_ptr(), img_n0, t.ptr, t.P, t.ps, 0, n, c, h, w, t.C, pool, scale_w, scale_b,
          None if dw is None else dw.data_ptr(), sa, sk, None if colsum is None else colsum.data_ptr(),
-         None if imgsum is None else imgsum.data_ptr())
+         None if imgsum is None else imgsum.data_ptr(), dscale)
 
 
 def pool2(src, out, avg=1, a=1.0, other=None, b=0.0):
     op, ops = _mask(other)
-    call('pgk_pool2', src.ptr, src.ps, src.P, out.N, out.H, out.W, out.C, avg, a, op, ops, b, out.ptr, out.ps)
+    (a, da), (b, db) = _sc(a), _sc(b)
+    call('pgk_pool2', src.ptr, src.ps, src.P, out.N, out.H, out.W, out.C, avg, a, op, ops, b, out.ptr, out.ps, da, db)
     return out
 
 
 def mask_mul(src, out, ref=None, ups=0, scale=1.0):
     rp, rps = _mask(ref)
-    call('pgk_mask_mul', src.ptr, src.ps, src.P, out.N, out.H, out.W, out.C, ups, scale, rp, rps, out.ptr, out.ps)
+    scale, dscale = _sc(scale)
+    call('pgk_mask_mul', src.ptr, src.ps, src.P, out.N, out.H, out.W, out.C, ups, scale, rp, rps, out.ptr, out.ps,
+         dscale)
     return out
 
 
@@ -382,6 +413,7 @@ class DEngine(object):
         self.D = D
         self._cw = {}
         self._P = 3
+        self.fade_dev = None    # two floats on the device (alpha, 1 - alpha) in CUDA-graph mode, see Fade
 
     def blk(self, k):
         """blocks[-k] (network.py:227,231,236)."""
@@ -442,7 +474,7 @@ class DEngine(object):
         r = ximg.shape[-1]
         assert B == ngroups * group_n and r == 4 * 2 ** depth, 'input resolution must match the current depth'
         T = SimpleNamespace(depth=depth, alpha=alpha, fade=fade, B=B, Bt=Bt, P=P, ngroups=ngroups, group_n=group_n,
-                            ximg=ximg, blocks=[])
+                            ximg=ximg, blocks=[], fd=Fade(alpha, self.fade_dev if fade else None))
         self.prepare(depth, P)
         new = lambda res, c: PT.empty(Bt, res, res, c, P, dev)
         top = self.blk(depth + 1)
@@ -462,7 +494,7 @@ class DEngine(object):
                 T.xlow = pool_img(ximg)
                 T.f = new(r // 2, w2.cout)
                 from_rgb(T.xlow, self.blk(depth).fromRGB, T.f.sl(0, B))
-                pool2(T.t2.sl(0, B), h.sl(0, B), avg=1, a=alpha, other=T.f.sl(0, B), b=1.0 - alpha)
+                pool2(T.t2.sl(0, B), h.sl(0, B), avg=1, a=T.fd.a(), other=T.f.sl(0, B), b=T.fd.b())
             else:
                 pool2(T.t2.sl(0, B), h.sl(0, B), avg=1)
             res = r // 2
@@ -545,11 +577,11 @@ class DEngine(object):
                 d_h = conv(ua_a, w1.B, w1.cin, 3, PT.empty(n, rec.res, rec.res, w1.cin, P, dev))
             w1, w2 = self.cw(top.c1), self.cw(top.c2)
             ua_t2 = mask_mul(d_h, ua_of('ua_t2', T.t2), ref=T.t2.sl(n0, n1), ups=1,
-                             scale=0.25 * (alpha if fade else 1.0))
+                             scale=T.fd.a(0.25) if fade else 0.25)
             ua_t1 = conv(ua_t2, w2.B, w1.cout, 3, ua_of('ua_t1', T.t1), mask=T.t1.sl(n0, n1))
             ua_t0 = conv(ua_t1, w1.B, w1.cin, 3, ua_of('ua_t0', T.t0), mask=T.t0.sl(n0, n1))
             if fade:
-                ua_f = mask_mul(d_h, ua_of('ua_f', T.f), ref=T.f.sl(n0, n1), scale=1.0 - alpha)
+                ua_f = mask_mul(d_h, ua_of('ua_f', T.f), ref=T.f.sl(n0, n1), scale=T.fd.b())
 
     def image_grad(self, T, g0, n, dimg):
         """dimg (fp32 n,C,r,r) <- gradient w.r.t. the input image from the ua tensors at sample offset g0
@@ -582,7 +614,7 @@ class DEngine(object):
                 T.v0low = pool_img(v0)
                 from_rgb(T.v0low, self.blk(depth).fromRGB, v(T.f), act=0, bias=False, mask=m(T.f))
                 dst = T.blocks[0].hin if T.blocks else T.hin
-                pool2(v(T.t2), v(dst), avg=1, a=alpha, other=v(T.f), b=1.0 - alpha)
+                pool2(v(T.t2), v(dst), avg=1, a=T.fd.a(), other=v(T.f), b=T.fd.b())
             else:
                 dst = T.blocks[0].hin if T.blocks else T.hin
                 pool2(v(T.t2), v(dst), avg=1)
@@ -670,6 +702,7 @@ class GEngine(object):
         self.G = G
         self._cw = {}
         self._P = 3
+        self.fade_dev = None
 
     def block(self, i):
         return self.G.block0 if i == 0 else self.G.blocks[i - 1]
@@ -726,7 +759,8 @@ class GEngine(object):
         depth, alpha = int(G.depth), float(G.alpha)
         fade = depth > 0 and alpha < 1.0
         n, dev = z.shape[0], z.device
-        T = SimpleNamespace(depth=depth, alpha=alpha, fade=fade, n=n, P=P, acts=[]) if tape else None
+        fd = Fade(alpha, self.fade_dev if fade else None)
+        T = SimpleNamespace(depth=depth, alpha=alpha, fade=fade, n=n, P=P, acts=[], fd=fd) if tape else None
         self.prepare(depth, P)
         zn = PT.empty(n, 1, 1, z.shape[1], P, dev)
         call('pgk_latent_norm', z.data_ptr(), n, z.shape[1], 1 if G.normalize_latents else 0, zn.ptr, P, zn.ps)
@@ -763,14 +797,15 @@ class GEngine(object):
         hi = self.block(depth).toRGB
         if fade:
             lo = self.block(depth - 1).toRGB
+            (a_hi, d_hi), (a_lo, d_lo) = fd.a(), fd.b()
             call('pgk_to_rgb', h.ptr, P, h.ps, n, res, res, h.C, hi.conv.weight.data_ptr(), hi.cf,
-                 hi.conv.bias.data_ptr(), alpha, hprev.ptr, hprev.ps, hprev.C, lo.conv.weight.data_ptr(), lo.cf,
-                 lo.conv.bias.data_ptr(), 1.0 - alpha, C, img.data_ptr())
+                 hi.conv.bias.data_ptr(), a_hi, hprev.ptr, hprev.ps, hprev.C, lo.conv.weight.data_ptr(), lo.cf,
+                 lo.conv.bias.data_ptr(), a_lo, C, img.data_ptr(), d_hi, d_lo)
         else:
             # depth 0 returns toRGB(h); depth > 0 with alpha >= 1 returns 0*(1-alpha) + ult*alpha (network.py:136-138)
             a_hi = 1.0 if depth == 0 else alpha
             call('pgk_to_rgb', h.ptr, P, h.ps, n, res, res, h.C, hi.conv.weight.data_ptr(), hi.cf,
-                 hi.conv.bias.data_ptr(), a_hi, None, 0, 0, None, 0.0, None, 0.0, C, img.data_ptr())
+                 hi.conv.bias.data_ptr(), a_hi, None, 0, 0, None, 0.0, None, 0.0, C, img.data_ptr(), None, None)
         return img, T
 
     def backward(self, T, dimg, gs):
@@ -785,21 +820,23 @@ class GEngine(object):
         zero_scratch(self.active_convs(depth))
         hi = self.block(depth).toRGB
         hprev, _, u1, u2 = T.acts[depth]
-        a_hi = 1.0 if depth == 0 else alpha
-        # toRGB (network.py:49,65) and the fade-in lerp (network.py:138)
-        rgb_wgrad(dimg, 0, u2, n, C, res, res, 0, hi.cf * a_hi, a_hi, gs[hi.conv.weight], u2.C, 1, None,
-                  gs[hi.conv.bias])
+        # toRGB (network.py:49,65) and the fade-in lerp (network.py:138): factor alpha on the new level's branch (1 at
+        # depth 0), 1 - alpha on the previous level's
+        k_hi, d_hi = T.fd.a() if fade else ((1.0 if depth == 0 else alpha), None)
+        rgb_wgrad(dimg, 0, u2, n, C, res, res, 0, hi.cf * k_hi, k_hi, gs[hi.conv.weight], u2.C, 1, None,
+                  gs[hi.conv.bias], dscale=d_hi)
         d = PT.empty(n, res, res, u2.C, P, dev)
-        call('pgk_to_rgb_dgrad', dimg.data_ptr(), n, C, res, res, u2.C, hi.conv.weight.data_ptr(), hi.cf, a_hi, 0,
-             d.ptr, P, d.ps)
+        call('pgk_to_rgb_dgrad', dimg.data_ptr(), n, C, res, res, u2.C, hi.conv.weight.data_ptr(), hi.cf, k_hi, 0,
+             d.ptr, P, d.ps, d_hi)
         d_lo = None
         if fade:
             lo = self.block(depth - 1).toRGB
-            rgb_wgrad(dimg, 0, hprev, n, C, res // 2, res // 2, 1, lo.cf * (1.0 - alpha), 1.0 - alpha,
-                      gs[lo.conv.weight], hprev.C, 1, None, gs[lo.conv.bias])
+            k_lo, dp_lo = T.fd.b()
+            rgb_wgrad(dimg, 0, hprev, n, C, res // 2, res // 2, 1, lo.cf * k_lo, k_lo,
+                      gs[lo.conv.weight], hprev.C, 1, None, gs[lo.conv.bias], dscale=dp_lo)
             d_lo = PT.empty(n, res // 2, res // 2, hprev.C, P, dev)
             call('pgk_to_rgb_dgrad', dimg.data_ptr(), n, C, res // 2, res // 2, hprev.C, lo.conv.weight.data_ptr(),
-                 lo.cf, 1.0 - alpha, 1, d_lo.ptr, P, d_lo.ps)
+                 lo.cf, k_lo, 1, d_lo.ptr, P, d_lo.ps, dp_lo)
         for i in range(depth, -1, -1):
             b = self.block(i)
             hprev, hup, u1, u2 = T.acts[i]

@@ -50,11 +50,13 @@ def _allreduce(gs):
 
 
 # ---- CUDA graphs -----------------------------------------------------------------------------
-# cuda_graphs = True: the kernel sequence of a loss is captured once per (networks, depth, alpha, batch shape,
-# precision, loss constants) and replayed afterwards: ~10^3 launches per step become one graph launch, which is what
-# bounds the low-resolution phases.  alpha is baked into the captured launches, so replay pays off in the
-# stabilisation phases (alpha constant); while a level fades in, alpha changes every iteration and the loss runs eagerly
-# (a key is captured only on its third use).  Parameters must keep their storage (Adam updates in place).
+# cuda_graphs = True: the kernel sequence of a loss is captured once per (networks, depth, fading or not, batch shape,
+# precision, loss constants) and replayed afterwards: several hundred launches per step become one graph launch, which
+# is what bounds the low-resolution phases.  alpha is NOT part of the key: while a level fades in it changes every
+# iteration (plugins.py:57-81), so the five kernels it enters read it from a two-float device buffer of the engine
+# (engine.Fade, include/pgk.h "device-side fade-in scalars") that is rewritten before every replay -- one graph serves
+# the whole transition phase.  A key is captured on its third use.  Parameters must keep their storage (Adam updates
+# in place).
 cuda_graphs = False
 _graphs = {}
 
@@ -66,14 +68,34 @@ class _Captured(object):
         self.uses, self.graph, self.inputs, self.outputs, self.launches = 0, None, None, None, 0
 
 
+def _fade_scalars(*models):
+    """Graph mode: give every engine its device-side (alpha, 1 - alpha) pair and write the current values into it (two
+    tiny launches per engine, outside the graph).  Eager mode: no device scalars, alpha travels as a kernel argument."""
+    from .engine import Fade
+    for m in models:
+        e = m.engine
+        if not cuda_graphs:
+            e.fade_dev = None
+            continue
+        if e.fade_dev is None or e.fade_dev.device != next(m.parameters()).device:
+            e.fade_dev = torch.empty(2, dtype=torch.float32, device=next(m.parameters()).device)
+        Fade(float(m.alpha), e.fade_dev).write()
+
+
+def _phase(m):
+    """what a captured graph depends on: the depth and whether the level is fading in -- not alpha itself"""
+    return int(m.depth), bool(int(m.depth) > 0 and float(m.alpha) < 1.0)
+
+
 def _run(key, body, inputs):
     """body(*inputs) -> tuple of tensors / objects.  Eager for the first two uses of a key, then captured + replayed."""
     if not cuda_graphs:
         return body(*inputs)
     c = _graphs.get(key)
     if c is None:
-        if len(_graphs) > 16:
-            _graphs.clear()            # bounded cache: phases change only a handful of times per run
+        if len(_graphs) > 16:           # bounded cache: phases change only a handful of times per run
+            for k in [k for k, v in _graphs.items() if v.graph is None] or list(_graphs):
+                del _graphs[k]
         c = _graphs[key] = _Captured()
     c.uses += 1
     if c.uses <= 2:
@@ -166,7 +188,8 @@ def wgan_gp_D_loss(D, G, real_images_in, fake_latents_in, iwass_lambda=10.0, iwa
         eps = mixing_factors_override.to(dev, torch.float32).contiguous().view(-1)
     else:
         eps = torch.rand(n, device=dev, dtype=torch.float32)       # wgan_gp_loss.py:15-17
-    key = ('D', id(D), id(G), int(D.depth), float(D.alpha), int(G.depth), float(G.alpha), tuple(real.shape),
+    _fade_scalars(D, G)
+    key = ('D', id(D), id(G), _phase(D), _phase(G), tuple(real.shape),
            tuple(z.shape), D.precision, G.precision, float(iwass_lambda), float(iwass_epsilon), float(iwass_target))
     cost, d_real_loss, d_fake_loss, gs, norms, gp = _run(
         key, _d_body(D, G, iwass_lambda, iwass_epsilon, iwass_target), (real, z, eps))
@@ -203,8 +226,8 @@ def _g_body(G, D):
 def wgan_gp_G_loss(G, D, fake_latents_in):
     G.zero_grad()
     z = G._input(fake_latents_in)
-    key = ('G', id(G), id(D), int(D.depth), float(D.alpha), int(G.depth), float(G.alpha), tuple(z.shape), D.precision,
-           G.precision)
+    _fade_scalars(D, G)
+    key = ('G', id(G), id(D), _phase(D), _phase(G), tuple(z.shape), D.precision, G.precision)
     cost, gs = _run(key, _g_body(G, D), (z,))
     _allreduce(gs)
     return _deposit(cost.view(()), gs)

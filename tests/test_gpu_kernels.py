@@ -206,3 +206,32 @@ def test_prep_multi_is_the_single_layer_entry_points_bit_for_bit():
                     a, b = pair
                     assert torch.equal(a.view(torch.int16) if a.dtype != torch.float32 else a,
                                        b.view(torch.int16) if b.dtype != torch.float32 else b), (planes, spec, name)
+
+
+def test_unprep_multi_is_unprep_grad_bit_for_bit():
+    """pgk_unprep_multi (all layers in one tiled launch) against pgk_unprep_grad layer by layer."""
+    import ctypes
+    import torch
+    sys.path.insert(0, ROOT)
+    import pggan_b200 as pg
+    L = pg._lib
+    call = L.call
+    torch.manual_seed(1)
+    specs = [(0, 64, 64, 128, 3), (0, 512, 513, 512, 3), (0, 8, 8, 16, 3), (0, 40, 40, 48, 3), (1, 512, 512, 512, 4),
+             (2, 512, 512, 512, 4), (0, 32, 32, 64, 3)]
+    table = (L.UnprepLayer * len(specs))()
+    pairs = []
+    for d, (kind, cin, cs, cout, ks) in zip(table, specs):
+        n = cout * cin * ks * ks
+        dwp = torch.randn(n, device='cuda')
+        c = 0.11 + 0.001 * cin
+        ref = torch.full((cout, cs, ks, ks), 7.0, device='cuda')
+        got = ref.clone()
+        call('pgk_unprep_grad', dwp.data_ptr(), c, kind, cin, cs, cout, ks, ref.data_ptr(), 0)
+        d.dwp, d.c, d.kind, d.cin, d.cin_stride, d.cout, d.ks = dwp.data_ptr(), c, kind, cin, cs, cout, ks
+        d.dw, d.accumulate = got.data_ptr(), 0
+        pairs.append((dwp, ref, got))
+    call('pgk_unprep_multi', ctypes.cast(table, ctypes.c_void_p), len(specs))
+    torch.cuda.synchronize()
+    for spec, (_, ref, got) in zip(specs, pairs):
+        assert torch.equal(ref, got), spec

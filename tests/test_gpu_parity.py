@@ -351,9 +351,12 @@ def test_fused_adam_many_unsynchronised_steps(gpu):
         assert rel_err(b, a) < 1e-6
 
 
-def test_cuda_graph_replay_equals_eager(gpu):
+@pytest.mark.parametrize('fading', [False, True])
+def test_cuda_graph_replay_equals_eager(gpu, fading):
     """wgan_gp_loss.cuda_graphs: the captured + replayed kernel sequence gives the eager results, including after the
-    optimizer changed the weights (the weight re-layout kernels are part of the graph)."""
+    optimizer changed the weights (the weight re-layout kernels are part of the graph).  fading=True: alpha changes
+    EVERY iteration, as DepthManager does during a transition phase (plugins.py:57-81) -- one graph serves them all,
+    the kernels read alpha from the engine's device-side scalar pair."""
     pg = gpu['pg']
     g = load_step('tiny3_d2_a03')
 
@@ -365,7 +368,9 @@ def test_cuda_graph_replay_equals_eager(gpu):
         pg.wgan_gp_loss._graphs.clear()
         out = []
         try:
-            for it in range(5):
+            for it in range(6):
+                if fading:
+                    G.alpha = D.alpha = 0.0 if it == 3 else 0.1 + 0.17 * it      # (0.0: the first iteration of a level)
                 gen = torch.Generator().manual_seed(100 + it)
                 real = torch.randn(g['n'], g['channels'], g['real'].shape[-1], g['real'].shape[-1], generator=gen).cuda()
                 z1 = torch.randn(g['n'], g['latent'], generator=gen).cuda()
