@@ -107,3 +107,37 @@ class LRScheduler(Plugin):
     def iteration(self, *args):
         self.lrs_d.step(self.trainer.cur_nimg)
         self.lrs_g.step(self.trainer.cur_nimg)
+
+
+class AsyncLossMonitor(Plugin):
+    """EfficientLossMonitor (plugins.py:102-111) without the device synchronisation it costs every iteration: the
+    reference reads `val.data[0]` on the host after each iteration (four monitors = four D2H syncs per iteration, which
+    stop the host from running ahead of the GPU).  Here the running sum stays on the device and the host reads one mean
+    per epoch (tick).  Same arguments (`loss_no`: 0 G loss, 1 D cost, 2 D real loss, 3 D fake loss; `stat_name`), same
+    `trainer.stats[stat_name]` fields `last` / `epoch_mean` as torch.utils.trainer's LossMonitor wrote; `last` is filled at
+    the epoch boundary only."""
+
+    def __init__(self, loss_no, stat_name):
+        super().__init__([(1, 'iteration'), (1, 'epoch')])
+        self.loss_no, self.stat_name = loss_no, stat_name
+        self._sum = None
+        self._last = None
+        self._count = 0
+
+    def register(self, trainer):
+        self.trainer = trainer
+        trainer.stats.setdefault(self.stat_name, {'log_format': ':.4f', 'log_epoch_fields': ['{epoch_mean:.4f}']})
+
+    def iteration(self, iteration, *args):
+        val = args[self.loss_no]
+        val = val.detach() if self.loss_no < 2 else val.detach().mean()
+        self._sum = val.clone() if self._sum is None else self._sum.add_(val)      # enqueued on the stream: no sync
+        self._last = val
+        self._count += 1
+
+    def epoch(self, epoch_index):
+        st = self.trainer.stats[self.stat_name]
+        if self._count:
+            st['epoch_mean'] = float(self._sum) / self._count       # the one device read of the tick
+            st['last'] = float(self._last)
+        self._sum, self._last, self._count = None, None, 0

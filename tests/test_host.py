@@ -265,3 +265,32 @@ def test_python_sequencing_of_one_iteration_with_stubbed_kernels(monkeypatch, fp
         gcost = pg.wgan_gp_G_loss(G, D, torch.randn(4, 64))
         gcost.backward()
         assert sum(p.grad is not None for p in G.parameters()) == ng_expect
+
+
+def test_async_loss_monitor_reads_once_per_epoch():
+    """AsyncLossMonitor: running sums stay tensors during the iterations; `trainer.stats` gets the epoch mean and the
+    last value at the epoch boundary, with EfficientLossMonitor's conventions (plugins.py:102-111: losses 0 / 1 are
+    scalars, 2 / 3 are (N,1) tensors whose mean is logged)."""
+    class T(object):
+        stats = {}
+    m0, m2 = pg.AsyncLossMonitor(0, 'G_loss'), pg.AsyncLossMonitor(2, 'D_real')
+    t = T()
+    m0.register(t), m2.register(t)
+    for it in range(1, 4):
+        args = (torch.tensor(float(it)), torch.tensor(0.0), torch.full((4, 1), 2.0 * it), torch.zeros(4, 1))
+        m0.iteration(it, *args), m2.iteration(it, *args)
+        assert 'epoch_mean' not in t.stats['G_loss']
+    m0.epoch(1), m2.epoch(1)
+    assert t.stats['G_loss']['epoch_mean'] == 2.0 and t.stats['G_loss']['last'] == 3.0
+    assert t.stats['D_real']['epoch_mean'] == 4.0 and t.stats['D_real']['last'] == 6.0
+    m0.epoch(2)     # an epoch without iterations leaves the stats alone
+    assert t.stats['G_loss']['epoch_mean'] == 2.0
+
+
+def test_device_random_latents_has_the_shape_and_statistics_of_random_latents():
+    draw = pg.device_random_latents(64, 512, device='cpu', seed=3)
+    a, b = draw(), draw()
+    assert tuple(a.shape) == (64, 512) and a.dtype == torch.float32 and not torch.equal(a, b)
+    assert abs(float(a.mean())) < 0.05 and abs(float(a.std()) - 1.0) < 0.05
+    ref = pg.random_latents(64, 512)
+    assert tuple(ref.shape) == tuple(a.shape) and ref.dtype == a.dtype
