@@ -409,7 +409,7 @@ def run_config(name, cfg, args, rank, world, local_rank, steps, warmup, primary)
                        % (name, depth, r, r, alpha, n, cfg['precision']),
            'e2e': {'value': n * world / (ms_e2e / 1e3 / steps), 'unit': 'images/sec', 'h2d_bytes_per_step': h2d,
                    'd2h_bytes_per_step': d2h,
-                   'api': 'Trainer.train() with pinned host reals/latents' + (', real batches copied one step ahead' if args.prefetch else '')},
+                   'api': 'Trainer.train() with pinned host reals/latents' + (', Trainer.prefetch_reals = True (the next real batch is copied on a copy stream under the running iteration)' if args.prefetch else '')},
            'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'peak_mem_gb': peak_mem / 1e9}
     if ms_d is not None:
         peak_tf = roof['peak'] if roof['bound'] == 'tensor' else None
@@ -440,8 +440,8 @@ def main():
     ap.add_argument('--d-step', action='store_true', help='time the D step alone at every config (default: depth 8 only)')
     ap.add_argument('--graphs', action='store_true', help='replay the losses as CUDA graphs (wgan_gp_loss.cuda_graphs)')
     ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch of the config')
-    ap.add_argument('--prefetch', action='store_true',
-                    help='e2e leg: look-ahead H2D copy of the next real batch (trainer.prefetch_reals)')
+    ap.add_argument('--no-prefetch', dest='prefetch', action='store_false',
+                    help='e2e leg: without the look-ahead H2D copy of the next real batch (Trainer.prefetch_reals)')
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.batch:
@@ -506,10 +506,10 @@ def main():
     if others:
         out['configs'] = others
     switches = {k: v for k, v in sorted(os.environ.items()) if k.startswith('PGK_')}
-    if switches or args.graphs or args.prefetch:
+    if switches or args.graphs or not args.prefetch:
         # a line measured with non-default tuning switches says so (A/B runs; the driver's run has none)
         out['config']['switches'] = dict(switches, **({'--graphs': '1'} if args.graphs else {}),
-                                         **({'--prefetch': '1'} if args.prefetch else {}))
+                                         **({'--no-prefetch': '1'} if not args.prefetch else {}))
     if world == 1 and not args.no_extras:
         # the bar to beat: the reference itself in PyTorch eager on this GPU, for the line's config and the headline
         try:

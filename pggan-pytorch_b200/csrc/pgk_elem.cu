@@ -510,21 +510,53 @@ __global__ void __launch_bounds__(256) rgb_wgrad_kernel(RgbWgradArgs a) {
 // ------------------------------------------------------------------------------------------
 // planes elementwise
 // ------------------------------------------------------------------------------------------
-__global__ void pool2_kernel(Planes src, int N, int H, int W, int C, float a, Planes other, int has_other, float b,
-                             Planes out, const float* da, const float* db) {
+// Index arithmetic of the two kernels below: one work item = 8 channels of one output pixel.  C / 8, W and H are powers of
+// two for every layer of the reference's networks (network.py:94-95), so the item -> (n, y, x, chunk) split is shifts
+// and masks (P2 = true, 32-bit); the generic flavour divides in 64 bits, which alone held these kernels at ~40 % of
+// the HBM bandwidth (three 64-bit divisions per 16-byte store).
+template <bool P2>
+struct PixSplit {
+    int nch, W, H, lnch, lw, lh;
+    __device__ __forceinline__ void operator()(long long idx, int& chunk, int& x, int& y, int& n, long long& pix) const {
+        if (P2) {
+            const unsigned i = (unsigned)idx;
+            chunk = (int)(i & (unsigned)(nch - 1));
+            const unsigned p = i >> lnch;
+            x = (int)(p & (unsigned)(W - 1));
+            const unsigned r = p >> lw;
+            y = (int)(r & (unsigned)(H - 1));
+            n = (int)(r >> lh);
+            pix = p;
+        } else {
+            chunk = (int)(idx % nch);
+            pix = idx / nch;
+            x = (int)(pix % W);
+            const long long r = pix / W;
+            y = (int)(r % H);
+            n = (int)(r / H);
+        }
+    }
+};
+static inline int log2_exact(int v) {
+    if (v <= 0 || (v & (v - 1))) return -1;
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return l;
+}
+
+template <bool P2>
+__global__ void __launch_bounds__(256) pool2_kernel(Planes src, int N, PixSplit<P2> sp, int C, float a, Planes other,
+                                                    int has_other, float b, Planes out, const float* da, const float* db) {
     pgk_pdl_enter();
-    const int nch = C >> 3;
-    const long long total = (long long)N * H * W * nch;
+    const int H = sp.H, W = sp.W;
+    const long long total = (long long)N * H * W * sp.nch;
     const float sa = a * (da ? __ldg(da) : 1.f);
     b *= db ? __ldg(db) : 1.f;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        int chunk = (int)(idx % nch);
-        long long pix = idx / nch;
-        int x = (int)(pix % W);
-        long long r = pix / W;
-        int y = (int)(r % H);
-        int n = (int)(r / H);
+        int chunk, x, y, n;
+        long long pix;
+        sp(idx, chunk, x, y, n, pix);
         long long b00 = ((((long long)n * 2 * H + 2 * y) * 2 * W) + 2 * x) * C + chunk * 8;
         float f0[8], f1[8], f2[8], f3[8], v[8];
         ld8(src, b00, f0);
@@ -544,21 +576,19 @@ __global__ void pool2_kernel(Planes src, int N, int H, int W, int C, float a, Pl
     }
 }
 
-__global__ void mask_mul_kernel(Planes src, int N, int H, int W, int C, int ups, float scale, Planes ref, int has_ref,
-                                Planes out, const float* dscale) {
+template <bool P2>
+__global__ void __launch_bounds__(256) mask_mul_kernel(Planes src, int N, PixSplit<P2> sp, int C, int ups, float scale,
+                                                       Planes ref, int has_ref, Planes out, const float* dscale) {
     pgk_pdl_enter();
     scale *= dscale ? __ldg(dscale) : 1.f;
-    const int nch = C >> 3;
-    const long long total = (long long)N * H * W * nch;
+    const int H = sp.H, W = sp.W;
+    const long long total = (long long)N * H * W * sp.nch;
     const int Hs = H >> ups, Ws = W >> ups;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        int chunk = (int)(idx % nch);
-        long long pix = idx / nch;
-        int x = (int)(pix % W);
-        long long r = pix / W;
-        int y = (int)(r % H);
-        int n = (int)(r / H);
+        int chunk, x, y, n;
+        long long pix;
+        sp(idx, chunk, x, y, n, pix);
         float f[8];
         ld8(src, ((((long long)n * Hs + (y >> ups)) * Ws) + (x >> ups)) * C + chunk * 8, f);
         long long o = pix * C + chunk * 8;
@@ -1166,9 +1196,18 @@ extern "C" int pgk_pool2(const void* src, long long src_ps, int P, int N, int H,
                          const float* d_b, pgk_stream_t stream) {
     PGK_REQUIRE(C % 8 == 0, "pgk_pool2: C must be a multiple of 8");
     long long total = (long long)N * H * W * (C >> 3);
-    pgk_launch(pool2_kernel, dim3(grid_cap((total + 255) / 256)), 256, 0, ST, make_planes(src, src_ps, P), N, H, W, C,
-                                                                avg ? 0.25f * a : a, make_planes(other, other_ps, P),
-                                                                other != nullptr, b, make_planes(out, out_ps, P), d_a, d_b);
+    const int lnch = log2_exact(C >> 3), lw = log2_exact(W), lh = log2_exact(H);
+    const dim3 grid(grid_cap((total + 255) / 256));
+    const float sa = avg ? 0.25f * a : a;
+    if (lnch >= 0 && lw >= 0 && lh >= 0 && total < (1ll << 31)) {
+        PixSplit<true> sp = {C >> 3, W, H, lnch, lw, lh};
+        pgk_launch(pool2_kernel<true>, grid, 256, 0, ST, make_planes(src, src_ps, P), N, sp, C, sa,
+                   make_planes(other, other_ps, P), other != nullptr, b, make_planes(out, out_ps, P), d_a, d_b);
+    } else {
+        PixSplit<false> sp = {C >> 3, W, H, 0, 0, 0};
+        pgk_launch(pool2_kernel<false>, grid, 256, 0, ST, make_planes(src, src_ps, P), N, sp, C, sa,
+                   make_planes(other, other_ps, P), other != nullptr, b, make_planes(out, out_ps, P), d_a, d_b);
+    }
     PGK_LAUNCH_CHECK("pgk_pool2");
     return PGK_OK;
 }
@@ -1179,9 +1218,17 @@ extern "C" int pgk_mask_mul(const void* src, long long src_ps, int P, int N, int
     PGK_REQUIRE(C % 8 == 0, "pgk_mask_mul: C must be a multiple of 8");
     PGK_REQUIRE(!ups || (H % 2 == 0 && W % 2 == 0), "pgk_mask_mul: ups needs even H, W");
     long long total = (long long)N * H * W * (C >> 3);
-    pgk_launch(mask_mul_kernel, dim3(grid_cap((total + 255) / 256)), 256, 0, ST, make_planes(src, src_ps, P), N, H, W, C, ups, scale,
-                                                                   make_planes(ref, ref_ps, P), ref != nullptr,
-                                                                   make_planes(out, out_ps, P), d_scale);
+    const int lnch = log2_exact(C >> 3), lw = log2_exact(W), lh = log2_exact(H);
+    const dim3 grid(grid_cap((total + 255) / 256));
+    if (lnch >= 0 && lw >= 0 && lh >= 0 && total < (1ll << 31)) {
+        PixSplit<true> sp = {C >> 3, W, H, lnch, lw, lh};
+        pgk_launch(mask_mul_kernel<true>, grid, 256, 0, ST, make_planes(src, src_ps, P), N, sp, C, ups, scale,
+                   make_planes(ref, ref_ps, P), ref != nullptr, make_planes(out, out_ps, P), d_scale);
+    } else {
+        PixSplit<false> sp = {C >> 3, W, H, 0, 0, 0};
+        pgk_launch(mask_mul_kernel<false>, grid, 256, 0, ST, make_planes(src, src_ps, P), N, sp, C, ups, scale,
+                   make_planes(ref, ref_ps, P), ref != nullptr, make_planes(out, out_ps, P), d_scale);
+    }
     PGK_LAUNCH_CHECK("pgk_mask_mul");
     return PGK_OK;
 }

@@ -115,17 +115,11 @@ def test_conv_pixelnorm(T, case):
     assert T.pixelnorm_case(*case)
 
 
-# ---- opt-in paths written at the end of round 1 without a GPU: run with PGK_TEST_EXPERIMENTAL=1 until they have been
-# verified once (the env-switched kernel flavours -- PGK_THIN_ATM, PGK_WTHIN_ATM, PGK_WTHIN_SW128, PGK_WGRAD_RED4,
-# PGK_PREP_TILED -- are read once per process: run this whole file with the switch set, tools/gpu_call_r2_first.sh)
-experimental = pytest.mark.skipif(os.environ.get('PGK_TEST_EXPERIMENTAL') != '1',
-                                  reason='opt-in path not yet run on a GPU (PGK_TEST_EXPERIMENTAL=1 enables it)')
-
+# ---- the forward conv on two IEEE-half operand planes (the default forward path of the fp32-faithful mode)
 CONV_FP16 = [(2, 16, 16, 64, 64, 3, 3, False), (3, 4, 4, 512, 512, 3, 3, True), (2, 64, 64, 128, 256, 3, 3, False),
              (1, 128, 128, 64, 128, 3, 2, False), (9, 1, 1, 512, 8192, 1, 3, False), (5, 1, 1, 8192, 512, 1, 3, False)]
 
 
-@experimental
 @pytest.mark.parametrize('case', CONV_FP16, ids=lambda c: 'N%d_%dx%d_%d-%d_k%d_P%d' % c[:7])
 def test_conv_on_half_operand_planes(T, case):
     n, h, w, ci, co, ks, p, pos = case

@@ -109,8 +109,6 @@ def test_two_trainer_iterations_golden(gpu, fused):
             assert float(upd.norm()) == 0, k
 
 
-@pytest.mark.skipif(os.environ.get('PGK_TEST_EXPERIMENTAL') != '1',
-                    reason='opt-in path not yet run on a GPU (PGK_TEST_EXPERIMENTAL=1 enables it)')
 def test_prefetched_reals_give_the_same_parameters(gpu):
     """trainer.prefetch_reals = True (look-ahead H2D copy of pinned real batches on a copy stream) must not change a
     single bit of what two Trainer.train() iterations do."""
