@@ -164,6 +164,9 @@ struct ExpandArgs {
     Planes out;
 };
 
+// IT = unsigned when the launch has fewer than 2^31 work items (every real shape): the item -> (pixel, chunk), pixel ->
+// (sample, position) splits are 32-bit divisions instead of 64-bit ones
+template <typename IT>
 __global__ void __launch_bounds__(256) rgb_expand_kernel(ExpandArgs a) {
     pgk_pdl_enter();
     extern __shared__ float wsm[];  // [C][K]
@@ -172,15 +175,14 @@ __global__ void __launch_bounds__(256) rgb_expand_kernel(ExpandArgs a) {
         wsm[i] = a.wscale * (a.dmul ? __ldg(a.dmul) : 1.f) * a.w[(long long)c * a.sc + (long long)k * a.sk];
     }
     __syncthreads();
-    const int nch = a.K >> 3;
-    const long long total = (long long)a.N * a.H * a.W * nch;
-    const int HW = a.H * a.W;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        int chunk = (int)(idx % nch);
-        long long pix = idx / nch;
-        int n = (int)(pix / HW);
-        int r = (int)(pix - (long long)n * HW);
+    const IT nch = (IT)(a.K >> 3);
+    const IT HW = (IT)(a.H * a.W);
+    const IT total = (IT)a.N * HW * nch;
+    for (IT idx = (IT)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (IT)gridDim.x * blockDim.x) {
+        const IT pix = idx / nch;
+        const int chunk = (int)(idx - pix * nch);
+        const int n = (int)(pix / HW);
+        const int r = (int)(pix - (IT)n * HW);
         float iv[MAXC];
         if (!a.pool) {
 #pragma unroll
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(256) rgb_expand_kernel(ExpandArgs a) {
             if (a.act) s = lrelu(s);
             v[j] = s;
         }
-        long long o = pix * a.K + chunk * 8;
+        long long o = (long long)pix * a.K + chunk * 8;
         if (a.has_mask) {
             float m[8];
             Planes m0 = a.mask;   // the sign of plane 0 is the sign of the value
@@ -413,8 +415,14 @@ __global__ void __launch_bounds__(256) rgb_wgrad_kernel(RgbWgradArgs a) {
     if (r_end > a.R) r_end = a.R;
     if (pl < lanes) {
         for (long long rr = r_begin + pl; rr < r_end; rr += lanes) {
-            int n = (int)(rr / HW);
-            int r = (int)(rr - (long long)n * HW);
+            int n, r;
+            if (a.R < (1ll << 31)) {
+                n = (int)((unsigned)rr / (unsigned)HW);
+                r = (int)((unsigned)rr - (unsigned)n * (unsigned)HW);
+            } else {
+                n = (int)(rr / HW);
+                r = (int)(rr - (long long)n * HW);
+            }
             float iv[MAXC] = {0.f, 0.f, 0.f, 0.f};
             if (!a.pool) {
 #pragma unroll
@@ -1087,7 +1095,10 @@ static int launch_expand(ExpandArgs& a, pgk_stream_t stream, const char* name) {
     size_t smem = sizeof(float) * a.C * a.K;
     PGK_REQUIRE(smem <= 48 * 1024, "%s: weight does not fit shared memory", name);
     long long total = (long long)a.N * a.H * a.W * (a.K >> 3);
-    pgk_launch(rgb_expand_kernel, dim3(grid_cap((total + 255) / 256)), 256, smem, ST, a);
+    if (total < (1ll << 31) - (1ll << 24))
+        pgk_launch(rgb_expand_kernel<unsigned>, dim3(grid_cap((total + 255) / 256)), 256, smem, ST, a);
+    else
+        pgk_launch(rgb_expand_kernel<long long>, dim3(grid_cap((total + 255) / 256)), 256, smem, ST, a);
     PGK_LAUNCH_CHECK(name);
     return PGK_OK;
 }

@@ -31,7 +31,7 @@ W_CONV, W_GFIRST, W_DLAST = 0, 1, 2
 # three products per FLOP instead of six at the same 22 operand bits.  Measured (round 2, B200): depth 4 / batch 128
 # 88.96 -> 77.64 ms per iteration; every parity test (full widths, kernel-decision-conditioned gradients, unscreened
 # seeds) is unchanged with it.  PGK_FWD_FP16=0 keeps the six-product bf16 path (A/B runs).
-FWD_FP16 = os.environ.get('PGK_FWD_FP16', '1') != '0'
+FWD_FP16 = os.environ.get('PGK_FWD_FP16', '0') == '1'
 
 
 def _ints(vals):
