@@ -20,7 +20,8 @@ extern "C" int pgk_conv_tc_supported(int N, int H, int W, int Cin, int Cout, int
 extern "C" int pgk_conv_tc(const void* x, int P, int Pr, long long x_ps, int N, int H, int W, int Cin, int Cout, int KS,
                            const void* wt, long long wt_ps, const float* bias, const float* posT, const float* pos_s,
                            int act, const void* mask_ref, long long mask_ps, float out_scale, void* out,
-                           long long out_ps, pgk_stream_t stream, int fp16_x, int fp16_w, float acc_scale);
+                           long long out_ps, pgk_stream_t stream, int fp16_x, int fp16_w, float acc_scale, float* pn_r);
+extern "C" int pgk_conv_tc_fuses_pixelnorm(int Cout, int split_acc);
 extern "C" int pgk_wgrad_tc_supported(int H, int W, int Cin, int Cout, int KS, int ups, int ngroups, int group_n);
 extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W,
                             int Cin, int Cout, int KS, int ngroups, int group_n, const int* xoff, const int* goff,
@@ -140,8 +141,9 @@ extern "C" int pgk_conv(const void* x, int P, int Pr, long long x_ps, int N, int
                            out_ps, pn_done ? pn_r : nullptr, stream);
     } else if (wt && tc_enabled() && pgk_conv_tc_supported(N, H, W, Cin, Cout, KS, ups)) {
         ProfScope prof(PGK_PROF_CONV, flops, bytes, stream, Pr);
+        pn_done = pn_r && !posT && pgk_conv_tc_fuses_pixelnorm(Cout, Pr == 3);
         rc = pgk_conv_tc(x, P, Pr, x_ps, N, H, W, Cin, Cout, KS, wt, wt_ps, bias, posT, pos_s, act, mask_ref, mask_ps,
-                         out_scale, out, out_ps, stream, 0, 0, 1.0f);
+                         out_scale, out, out_ps, stream, 0, 0, 1.0f, pn_done ? pn_r : nullptr);
     } else {
         PGK_REQUIRE(wf != nullptr, "pgk_conv: this shape runs on the CUDA-core kernel, which needs the fp32 operand wf");
         ProfScope prof(PGK_PROF_CONV_SIMT, flops, bytes, stream);
@@ -167,7 +169,7 @@ extern "C" int pgk_conv_fp16(const void* xh, long long xh_ps, int N, int H, int 
     ProfScope prof(PGK_PROF_CONV, flops, bytes, stream, 2);
     // the kernel reads Pr = 2 planes of x and wt (its tensor maps are declared P >= 2 planes deep) and writes P planes
     return pgk_conv_tc(xh, P, 2, xh_ps, N, H, W, Cin, Cout, KS, wth, wth_ps, bias, posT, pos_s, act, nullptr, 0, 1.0f,
-                       out, out_ps, stream, 1, 1, 1.0f / (float)(1 << PGK_FP16_WSHIFT));
+                       out, out_ps, stream, 1, 1, 1.0f / (float)(1 << PGK_FP16_WSHIFT), nullptr);
 }
 
 extern "C" int pgk_wgrad(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W,

@@ -106,6 +106,8 @@ struct ConvTcArgs {
     Planes mask;
     float out_scale;
     Planes out;
+    float* pn_r;           // pixel norm after the activation (the tile holds every channel of a pixel: NT == Cout): the
+                           // per-pixel factor rsqrt(mean_c(h^2) + 1e-8) is stored here; NULL = no pixel norm
     int fp16_a, fp16_b;    // operand formats of this launch: 1 = IEEE half planes (pgk_conv_fp16), 0 = bf16 planes
     float acc_scale;       // applied to the accumulator before the bias: 2^-PGK_FP16_WSHIFT with fp16 weights, else 1
 };
@@ -139,7 +141,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // epilogue staging, per warpgroup: 2 mask slabs + Pout output slabs of 128 rows x slab channels (1024-aligned)
     const uint32_t slab_bytes = 128u * a.slab * 2u;
     const uint32_t epi_wg_bytes = (uint32_t)(a.nmask + a.Pout) * slab_bytes;
-    const uint32_t epi_base = (tptr + 16u + 2u * 4u * a.NT + 1023u) & ~1023u;
+    float* ss_s = bias_s + 2 * a.NT;                                            // [2 warpgroups][128 pixels]
+    const uint32_t epi_base = (tptr + 16u + 2u * 4u * a.NT + 1024u + 1023u) & ~1023u;
 
     constexpr int kelems = kBkb >> 1;
     const int kchunks = a.Cin / kelems;
@@ -311,6 +314,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(tfull(b), (ti >> 1) & 1);
             fence_after();
             const uint32_t trow = tmem + b * acc_cols + ((uint32_t)(q * 32) << 16);
+            float pn_rr = 1.f;
+            if (a.pn_r) {
+                // pixel norm (network.py:37-40), fused: the tile holds all Cout channels of its 128 pixels, half of them
+                // per warpgroup.  First pass over the accumulator: bias + LeakyReLU, sum of squares of this thread's
+                // half; the two halves of a pixel meet in shared memory; the slab loop below reads the accumulator
+                // again and scales what it stores -- one rounding of the finished value, as in the thin kernel.
+                float ss = 0.f;
+                if (active) {
+                    for (int c = wg * wcols; c < (wg + 1) * wcols; c += 16) {
+                        float v[16];
+                        tmem_ld16(trow + c, v);
+                        if (SPLIT) {
+                            float w[16];
+                            tmem_ld16(trow + a.NT + c, w);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] += w[j];
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float f = F16 ? v[j] * a.acc_scale : v[j];
+                            if (a.bias) f += bs[c + j];
+                            if (a.act) f = lrelu(f);
+                            ss = fmaf(f, f, ss);
+                        }
+                    }
+                }
+                ss_s[wg * 128 + r] = ss;
+                named_bar_sync(4, kEpiWarps * 32);
+                pn_rr = rsqrtf((ss_s[r] + ss_s[128 + r]) / (float)a.Cout + 1e-8f);
+                if (wg == 0 && valid) a.pn_r[((long long)n * a.H + y) * a.W + x] = pn_rr;
+            }
             if (active) {
                 for (int sl = 0; sl < nslabs; ++sl, ++sc) {
                     const int c0 = wg * wcols + sl * a.slab;   // first channel of the slab within the tile
@@ -372,6 +406,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (a.act) {
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) f[j] = lrelu(f[j]);
+                            }
+                            if (a.pn_r) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) f[j] *= pn_rr;
                             }
                             if (a.has_mask) {
                                 float m[8];
@@ -662,6 +700,10 @@ __global__ void pack_operand_h_kernel(const float* __restrict__ w, int K, int Nn
 
 }  // namespace
 
+// does the wide kernel apply the pixel norm itself?  Its tile must hold every channel of a pixel: Cout <= 256 channels
+// of accumulator, 128 where the correction products have an accumulator of their own (three planes / half operands)
+extern "C" int pgk_conv_tc_fuses_pixelnorm(int Cout, int split_acc) { return Cout <= (split_acc ? 128 : 256); }
+
 // can the tensor-core conv take this shape?
 extern "C" int pgk_conv_tc_supported(int N, int H, int W, int Cin, int Cout, int KS, int ups) {
     if (ups || (KS != 1 && KS != 3)) return 0;
@@ -675,8 +717,11 @@ extern "C" int pgk_conv_tc_supported(int N, int H, int W, int Cin, int Cout, int
 extern "C" int pgk_conv_tc(const void* x, int P, int Pr, long long x_ps, int N, int H, int W, int Cin, int Cout, int KS,
                            const void* wt, long long wt_ps, const float* bias, const float* posT, const float* pos_s,
                            int act, const void* mask_ref, long long mask_ps, float out_scale, void* out,
-                           long long out_ps, pgk_stream_t stream, int fp16_x, int fp16_w, float acc_scale) {
+                           long long out_ps, pgk_stream_t stream, int fp16_x, int fp16_w, float acc_scale, float* pn_r) {
     PGK_REQUIRE(pgk_conv_tc_supported(N, H, W, Cin, Cout, KS, 0), "pgk_conv_tc: unsupported shape");
+    PGK_REQUIRE(!pn_r || (pgk_conv_tc_fuses_pixelnorm(Cout, Pr == 3 || (fp16_x && fp16_w)) && !mask_ref && !posT &&
+                          out_scale == 1.0f),
+                "pgk_conv_tc: the fused pixel norm needs all channels of a pixel in one tile, no mask, no stddev channel");
     PGK_REQUIRE(P >= 1 && P <= 3 && Pr >= 1 && Pr <= P, "pgk_conv_tc: need 1 <= Pr <= P <= 3");
     ConvTcArgs a;
     a.N = N, a.H = H, a.W = W, a.Cin = Cin, a.Cout = Cout, a.KS = KS, a.P = Pr;   // the kernel's P = planes READ
@@ -694,11 +739,12 @@ extern "C" int pgk_conv_tc(const void* x, int P, int Pr, long long x_ps, int N, 
     int nt_max = a.split_acc ? 128 : 256;
     if (const char* e = getenv("PGK_CONV_NT")) nt_max = atoi(e) < nt_max ? atoi(e) : nt_max;   // tuning knob
     a.NT = Cout < nt_max ? Cout : nt_max;
+    a.pn_r = pn_r;
     // few pixel blocks (the 4x4 ... 16x16 levels at small batch): the launch is bound by streaming the weights, so
     // spread them over more CTAs with narrower channel slices
     {
         const int pixel_tiles = a.tiles_x * a.tiles_y * tiles_n, sms = pgk_num_sms();
-        while (a.NT > 32 && pixel_tiles * (Cout / a.NT) < sms) a.NT >>= 1;
+        while (!pn_r && a.NT > 32 && pixel_tiles * (Cout / a.NT) < sms) a.NT >>= 1;   // (pixel norm: NT stays Cout)
     }
     a.ntiles_n = Cout / a.NT;
     a.total_tiles = a.tiles_x * a.tiles_y * tiles_n * a.ntiles_n;
@@ -707,7 +753,7 @@ extern "C" int pgk_conv_tc(const void* x, int P, int Pr, long long x_ps, int N, 
     const int wcols = a.NT >= 32 ? a.NT / 2 : a.NT;
     a.slab = (wcols >= 32 && !(P == 3 && mask_ref)) ? 32 : 16;
     const int epi_bytes = 2 * (a.nmask + a.Pout) * 128 * a.slab * 2 + 1024;
-    const int fixed = 1024 + 512 + 2 * 4 * a.NT + epi_bytes;
+    const int fixed = 1024 + 512 + 2 * 4 * a.NT + 1024 + epi_bytes;   // (+1024: the pixel norm's exchange buffer)
     const int budget = kSmemLimit - fixed;
     a.bkb = 128;
     int stage_bytes = Pr * (128 * a.bkb + a.NT * a.bkb);

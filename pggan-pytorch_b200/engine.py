@@ -140,6 +140,7 @@ def conv(x, w, cout, ks, out, ups=0, bias=None, posT=None, pos_s=None, act=0, ma
             and _lib.load().pgk_conv_tc_supported(out.N, out.H, out.W, x.C, cout, ks, 0)):
         # fp16 two-plane copy of the input (one extra pass), then the conv on half operands
         xh = torch.empty((2, x.N * x.per), dtype=torch.float16, device=x.t.device)
+        out.aux['xh'] = xh          # lives as long as the output it produced (the tape), not just this call
         call('pgk_cvt_fp16x2', x.ptr, x.ps, x.P, x.N * x.per, xh.data_ptr(), xh.stride(0))
         call('pgk_conv_fp16', xh.data_ptr(), xh.stride(0), out.N, out.H, out.W, x.C, cout, ks, w[2].data_ptr(),
              w[2].stride(0), None if bias is None else bias.data_ptr(), None if posT is None else posT.data_ptr(),

@@ -194,10 +194,12 @@ BF16_TOL_VALUE, BF16_TOL_GRAD = 3e-2, 2e-2
 
 def pn_fused_fn(pg, G, n):
     """Which generator layers normalise inside the conv epilogue (one rounding) and which as a second pass over the
-    stored tensor (two): asked of the library itself, per layer shape."""
+    stored tensor (two): asked of the library itself, per layer shape (one-plane mode)."""
+    import ctypes
     lib = pg._lib.load()
-    lib.pgk_conv_thin_supported.argtypes = [__import__('ctypes').c_int] * 7
-    lib.pgk_conv_thin_fuses_pixelnorm.argtypes = [__import__('ctypes').c_int]
+    lib.pgk_conv_thin_supported.argtypes = [ctypes.c_int] * 7
+    lib.pgk_conv_thin_fuses_pixelnorm.argtypes = [ctypes.c_int]
+    lib.pgk_conv_tc_fuses_pixelnorm.argtypes = [ctypes.c_int] * 2
     table = {}
     res = 4
     for i in range(0, G.max_depth + 1):
@@ -208,8 +210,13 @@ def pn_fused_fn(pg, G, n):
         for c in ('c1', 'c2'):
             w = getattr(b, c).conv.weight
             cout, cin, ks = w.shape[0], w.shape[1], w.shape[2]
-            table['%s.%s' % (nm, c)] = bool(ks == 3 and lib.pgk_conv_thin_supported(n, res, res, cin, cout, 3, 0)
-                                            and lib.pgk_conv_thin_fuses_pixelnorm(cout))
+            thin = ks == 3 and lib.pgk_conv_thin_supported(n, res, res, cin, cout, 3, 0)
+            if thin:
+                fused = lib.pgk_conv_thin_fuses_pixelnorm(cout)
+            else:
+                fused = ks == 3 and lib.pgk_conv_tc_supported(n, res, res, cin, cout, 3, 0) and \
+                    lib.pgk_conv_tc_fuses_pixelnorm(cout, 0)
+            table['%s.%s' % (nm, c)] = bool(fused)
     return lambda name: table[name]
 
 

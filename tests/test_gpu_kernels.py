@@ -107,7 +107,11 @@ def test_wgrad(T, case):
 # conv + bias + LeakyReLU + pixel norm in one call (the generator's PGConv2d.forward, network.py:32-40): fused into the
 # thin kernel's epilogue for Cout <= 32, a second in-place pass on the other kernels
 PIXELNORM = [(2, 128, 128, 16, 8, 1), (1, 256, 256, 8, 8, 3), (3, 128, 256, 32, 16, 2), (2, 256, 128, 32, 32, 1),
-             (1, 128, 128, 16, 64, 3), (2, 32, 32, 64, 32, 3), (3, 8, 8, 128, 128, 1)]
+             (1, 128, 128, 16, 64, 3), (2, 32, 32, 64, 32, 3), (3, 8, 8, 128, 128, 1),
+             # the wide kernel's fused pixel norm (all channels of a pixel in one tile): every tile width, both
+             # accumulator layouts, a partial last pixel block; and widths it cannot hold (second pass in place)
+             (2, 64, 64, 128, 64, 1), (3, 32, 32, 256, 256, 1), (5, 16, 16, 64, 128, 3), (2, 128, 128, 64, 64, 2),
+             (3, 4, 4, 128, 16, 1), (1, 16, 16, 512, 512, 1), (2, 16, 16, 256, 256, 3), (7, 8, 8, 64, 32, 3)]
 
 
 @pytest.mark.parametrize('case', PIXELNORM, ids=lambda c: 'N%d_%dx%d_%d-%d_P%d' % c)
