@@ -451,18 +451,33 @@ class DEngine(object):
         last = self.blk(1)
         return ws + [self._get(last.c1), self._get(last.c2, W_DLAST)]
 
+    # Parameters (= order of the flat gradient buffer) and weight gradients go LOW RESOLUTION FIRST: the 4x4 ... 32x32
+    # blocks hold ~90 % of the gradient bytes (512-channel layers) and their weight gradients are short, the 64x64-and-up
+    # blocks hold few bytes and their weight gradients are the long ones.  Under data parallelism the all-reduce of the
+    # first bucket therefore runs underneath the weight gradients of the second (wgan_gp_loss._d_body).
+    BUCKET_LEVELS = 4       # blocks[-1] .. blocks[-4] (4x4 .. 32x32) + linear form the first bucket
+
     def active_params(self, depth, fade):
-        ps = []
+        ps = [self.D.linear.weight, self.D.linear.bias]
+        for k in range(1, depth + 2):
+            b = self.blk(k)
+            ps += [b.c1.conv.weight, b.c1.conv.bias, b.c2.conv.weight, b.c2.conv.bias]
         top = self.blk(depth + 1)
         ps += [top.fromRGB.conv.weight, top.fromRGB.conv.bias]
         if fade:
             lo = self.blk(depth)
             ps += [lo.fromRGB.conv.weight, lo.fromRGB.conv.bias]
-        for k in range(depth + 1, 0, -1):
-            b = self.blk(k)
-            ps += [b.c1.conv.weight, b.c1.conv.bias, b.c2.conv.weight, b.c2.conv.bias]
-        ps += [self.D.linear.weight, self.D.linear.bias]
         return ps
+
+    def first_bucket_elems(self, depth):
+        """elements of the flat gradient buffer that belong to the first bucket (0 = no split worth making)"""
+        if depth + 1 <= self.BUCKET_LEVELS:
+            return 0
+        n = self.D.linear.weight.numel() + self.D.linear.bias.numel()
+        for k in range(1, self.BUCKET_LEVELS + 1):
+            b = self.blk(k)
+            n += sum(p.numel() for p in (b.c1.conv.weight, b.c1.conv.bias, b.c2.conv.weight, b.c2.conv.bias))
+        return n
 
     # -- forward ---------------------------------------------------------------------------
     def forward(self, ximg, ngroups, group_n, P, slots=0):
@@ -642,10 +657,13 @@ class DEngine(object):
         conv(v(T.l1).view(1, 1, 16 * wl1.cout), wl2.F, wl2.cout, 1, v(T.l2), mask=m(T.l2))
 
     # -- parameter gradients -------------------------------------------------------------------
-    def param_grads(self, T, gs, groups, bias_goffs, head_groups, head_bias_goffs, img_pairs, ev_pair=None):
+    def param_grads(self, T, gs, groups, bias_goffs, head_groups, head_bias_goffs, img_pairs, ev_pair=None,
+                    first_bucket_done=None):
         """groups: (x sample offset, ua sample offset) pairs of group_n samples each for the layers below the last
         block; head_groups: the same for the last block's c1 / c2.  img_pairs: (image tensor, img_n0, ua offset)
-        triples for fromRGB.  ev_pair = (coef vector (n), ua offset) adds the v-chain's extra-channel term."""
+        triples for fromRGB.  ev_pair = (coef vector (n), ua offset) adds the v-chain's extra-channel term.
+        Order: low resolution first (see active_params); first_bucket_done() is called once the gradients of the first
+        bucket are final in gs (the caller starts their all-reduce there)."""
         n, P = T.group_n, min(T.P, GRAD_PLANES)
         depth, alpha, fade = T.depth, T.alpha, T.fade
         top = self.blk(depth + 1)
@@ -654,27 +672,12 @@ class DEngine(object):
         pending = []
         zero_scratch(self.active_convs(depth))
 
-        def rgb(mod, t_ua, res, pairs_):
-            gw, gb = gs[mod.conv.weight], gs[mod.conv.bias]
-            for img, img_n0, goff, with_bias in pairs_:
-                rgb_wgrad(img, img_n0, t_ua.sl(goff, goff + n), n, C, res, res, 0, mod.cf, 1.0, gw, 1, C,
-                          gb if with_bias else None, None)
-
-        rgb(top.fromRGB, T.ua_t0, r, img_pairs['top'])
-        if fade:
-            rgb(self.blk(depth).fromRGB, T.ua_f, r // 2, img_pairs['low'])
-
         def conv_layer(mod, x, ua, res):
             w = self.cw(mod)
             w.wgrad_into(gs[mod.conv.weight], x, ua, res, res, 0, groups, n, db=gs[mod.conv.bias],
                          bias_goffs=bias_goffs, pending=pending)
 
-        if depth > 0:
-            conv_layer(top.c1, T.t0, T.ua_t1, r)
-            conv_layer(top.c2, T.t1, T.ua_t2, r)
-            for i, rec in enumerate(T.blocks):
-                conv_layer(rec.mod.c1, rec.hin, getattr(T, 'ua_blk%da' % i), rec.res)
-                conv_layer(rec.mod.c2, rec.a, getattr(T, 'ua_blk%db' % i), rec.res)
+        # ---- the last block (4x4) and the linear head (its gradients were written by backward_head / pgk_colsum)
         last = self.blk(1)
         wl1, wl2 = self.cw(last.c1), self.cw(last.c2, W_DLAST)
         g1 = gs[last.c1.conv.weight]
@@ -692,6 +695,37 @@ class DEngine(object):
         wl2.wgrad_into(gs[last.c2.conv.weight], T.l1.view(1, 1, 16 * wl1.cout), T.ua_l2, 1, 1, 0, head_groups, n,
                        pending=pending)
         bias_grad(T.ua_l2, 1, wl2.cout, head_bias_goffs, n, gs[last.c2.conv.bias])
+        # ---- blocks[-2] (8x8) upwards; T.blocks runs from the block below the top one down to blocks[-2]
+        level = 1
+
+        def close_bucket():
+            unprep_all(pending)
+            del pending[:]
+            if first_bucket_done is not None:
+                first_bucket_done()
+
+        for i in range(len(T.blocks) - 1, -1, -1):
+            if level == self.BUCKET_LEVELS:
+                close_bucket()
+            rec = T.blocks[i]
+            conv_layer(rec.mod.c1, rec.hin, getattr(T, 'ua_blk%da' % i), rec.res)
+            conv_layer(rec.mod.c2, rec.a, getattr(T, 'ua_blk%db' % i), rec.res)
+            level += 1
+        if depth > 0:
+            if level == self.BUCKET_LEVELS:
+                close_bucket()
+            conv_layer(top.c1, T.t0, T.ua_t1, r)
+            conv_layer(top.c2, T.t1, T.ua_t2, r)
+
+        def rgb(mod, t_ua, res, pairs_):
+            gw, gb = gs[mod.conv.weight], gs[mod.conv.bias]
+            for img, img_n0, goff, with_bias in pairs_:
+                rgb_wgrad(img, img_n0, t_ua.sl(goff, goff + n), n, C, res, res, 0, mod.cf, 1.0, gw, 1, C,
+                          gb if with_bias else None, None)
+
+        rgb(top.fromRGB, T.ua_t0, r, img_pairs['top'])
+        if fade:
+            rgb(self.blk(depth).fromRGB, T.ua_f, r // 2, img_pairs['low'])
         unprep_all(pending)
 
 

@@ -294,3 +294,28 @@ def test_device_random_latents_has_the_shape_and_statistics_of_random_latents():
     assert abs(float(a.mean())) < 0.05 and abs(float(a.std()) - 1.0) < 0.05
     ref = pg.random_latents(64, 512)
     assert tuple(ref.shape) == tuple(a.shape) and ref.dtype == a.dtype
+
+
+def test_first_gradient_bucket_is_a_prefix_of_the_flat_buffer():
+    """DEngine orders parameters (= the flat gradient buffer) low resolution first, and first_bucket_elems() is the
+    size of a PREFIX of it: linear + blocks[-1..-4] -- what the D step all-reduces while the high-resolution weight
+    gradients still run.  The active set itself is unchanged (same parameters as the reference gives a gradient)."""
+    D = pg.Discriminator((None, 3, 1024, 1024))
+    e = D.engine
+    for depth in range(0, 9):
+        for fade in (False, True):
+            if fade and depth == 0:
+                continue
+            ps = e.active_params(depth, fade)
+            assert len({id(p) for p in ps}) == len(ps) == 2 + 4 * (depth + 1) + 2 + (2 if fade else 0)
+            split = e.first_bucket_elems(depth)
+            if depth < 4:
+                assert split == 0
+                continue
+            first = [D.linear.weight, D.linear.bias]
+            for k in range(1, 5):
+                b = D.blocks[len(D.blocks) - k]
+                first += [b.c1.conv.weight, b.c1.conv.bias, b.c2.conv.weight, b.c2.conv.bias]
+            assert [id(p) for p in ps[:len(first)]] == [id(p) for p in first]
+            assert split == sum(p.numel() for p in first)
+            assert split > 0.85 * sum(p.numel() for p in ps)       # the 512-channel layers: most of the bytes
