@@ -57,14 +57,15 @@ def test_reference_arm_prints_the_contract_line():
     assert line['config']['workload'].startswith('c1:')
 
 
-def test_committed_traffic_figure_is_what_the_committed_capture_says():
+@pytest.mark.parametrize('cfg,family', [('c2', 'conv_tc_kernel'), ('c4', 'conv_thin_kernel')])
+def test_committed_traffic_figure_is_what_the_committed_capture_says(cfg, family):
     with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
-        entry = json.load(f)['c2']['conv_tc_kernel']
+        entry = json.load(f)[cfg][family]
     per = {}
-    with open(os.path.join(ROOT, 'profiles', 'r1e_traffic_c2.csv')) as f:
+    with open(os.path.join(ROOT, 'profiles', 'r2_traffic_%s.csv' % cfg)) as f:
         rows = csv.DictReader([l for l in f if not l.startswith('==')])
         for row in rows:
-            if 'conv_tc_kernel' not in row['Kernel Name'] or not row['Metric Name'].startswith('dram__bytes'):
+            if family not in row['Kernel Name'] or not row['Metric Name'].startswith('dram__bytes'):
                 continue
             scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[row['Metric Unit']]
             per[int(row['ID'])] = per.get(int(row['ID']), 0.0) + float(row['Metric Value'].replace(',', '')) * scale
