@@ -34,11 +34,12 @@ def _shell_class(name):
 
 
 class _RefUnpickler(pickle.Unpickler):
-    """network.<Class> -> an nn.Module shell of the same name; everything else (torch tensors, nn.Conv2d,
-    nn.LeakyReLU, collections ...) resolves normally."""
+    """network.<Class> (the reference's top-level module, train.py:11) -> an nn.Module shell of the same name;
+    everything else (torch tensors, nn.Conv2d, nn.LeakyReLU, collections, and this package's own
+    `pggan-pytorch_b200.network` classes) resolves normally."""
 
     def find_class(self, module, name):
-        if module == 'network' or module.endswith('.network'):
+        if module == 'network':
             return _shell_class(name)
         return super().find_class(module, name)
 
@@ -104,6 +105,8 @@ def from_reference(ref, device=None):
     out.set_wscale({n: float(getattr(m, 'c', 1.0)) for n, m in convs.items()})
     out.depth = int(getattr(ref, 'depth', 0))
     out.alpha = float(getattr(ref, 'alpha', 1.0))
+    if getattr(ref, 'precision', None) in ('fp32', 'bf16x2', 'bf16'):     # (a pggan_b200 module passed through here)
+        out.precision = ref.precision
     if device is not None:
         out.to(device)
     return out

@@ -777,9 +777,12 @@ extern "C" int pgk_conv_tc(const void* x, int P, int Pr, long long x_ps, int N, 
     a.acc_scale = acc_scale;
 
     CUtensorMap tmA, tmB;
+    // (half operands come as exactly two planes: their tensor maps must not declare a third one behind the allocation)
+    static const bool tmap3 = getenv("PGK_FP16_TMAP3") != nullptr;   // (diagnostic: the round-1 declaration)
+    const unsigned long long planes_x = (fp16_x && !tmap3) ? 2ull : (unsigned long long)P, planes_w = (fp16_w && !tmap3) ? 2ull : 3ull;
     {
         unsigned long long dims[5] = {(unsigned long long)Cin, (unsigned long long)W, (unsigned long long)H,
-                                      (unsigned long long)N, (unsigned long long)P};
+                                      (unsigned long long)N, planes_x};
         unsigned long long str[4] = {2ull * Cin, 2ull * Cin * W, 2ull * Cin * W * H,
                                      P > 1 ? 2ull * x_ps : 2ull * Cin * W * H * N};
         unsigned box[5] = {(unsigned)(a.bkb / 2), (unsigned)TW, (unsigned)TH, (unsigned)a.TN, 1u};
@@ -788,7 +791,7 @@ extern "C" int pgk_conv_tc(const void* x, int P, int Pr, long long x_ps, int N, 
     }
     {
         const unsigned long long K = (unsigned long long)KS * KS * Cin;
-        unsigned long long dims[3] = {K, (unsigned long long)Cout, 3ull};
+        unsigned long long dims[3] = {K, (unsigned long long)Cout, planes_w};
         unsigned long long str[2] = {2ull * K, 2ull * wt_ps};
         unsigned box[3] = {(unsigned)(a.bkb / 2), (unsigned)a.NT, 1u};
         int rc = pgk_make_tmap(&tmB, wt, 3, dims, str, box, a.bkb, "pgk_conv_tc(w)");

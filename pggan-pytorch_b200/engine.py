@@ -32,6 +32,10 @@ W_CONV, W_GFIRST, W_DLAST = 0, 1, 2
 # 88.96 -> 77.64 ms per iteration; every parity test (full widths, kernel-decision-conditioned gradients, unscreened
 # seeds) is unchanged with it.  PGK_FWD_FP16=0 keeps the six-product bf16 path (A/B runs).
 FWD_FP16 = os.environ.get('PGK_FWD_FP16', '0') == '1'
+# diagnostic knobs of the fault hunt
+_FP16_NOPOS = os.environ.get('PGK_FP16_NOPOS', '0') == '1'
+_FP16_MINPIX = int(os.environ.get('PGK_FP16_MINPIX', '0'))
+_FP16_PAD = int(os.environ.get('PGK_FP16_PAD', '0'))
 
 
 def _ints(vals):
@@ -137,9 +141,10 @@ def conv(x, w, cout, ks, out, ups=0, bias=None, posT=None, pos_s=None, act=0, ma
     mp, mps = _mask(mask)
     wf, wt = w[0], w[1]
     if (FWD_FP16 and fwd and len(w) > 2 and w[2] is not None and x.P >= 2 and mask is None and not ups and scale == 1.0
+            and not (_FP16_NOPOS and posT is not None) and out.N * out.H * out.W >= _FP16_MINPIX
             and _lib.load().pgk_conv_tc_supported(out.N, out.H, out.W, x.C, cout, ks, 0)):
         # fp16 two-plane copy of the input (one extra pass), then the conv on half operands
-        xh = torch.empty((2, x.N * x.per), dtype=torch.float16, device=x.t.device)
+        xh = torch.empty((2, x.N * x.per + _FP16_PAD), dtype=torch.float16, device=x.t.device)
         out.aux['xh'] = xh          # lives as long as the output it produced (the tape), not just this call
         call('pgk_cvt_fp16x2', x.ptr, x.ps, x.P, x.N * x.per, xh.data_ptr(), xh.stride(0))
         call('pgk_conv_fp16', xh.data_ptr(), xh.stride(0), out.N, out.H, out.W, x.C, cout, ks, w[2].data_ptr(),
