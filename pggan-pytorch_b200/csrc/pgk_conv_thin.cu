@@ -45,6 +45,8 @@ struct ThinArgs {
     int pair;                   // MMA warp interleaves the K steps of two output rows (two accumulators)
     int tma;                    // producer: 1 = TMA boxes (16-byte inner extent), 0 = cp.async chunks
     int spin;                   // producer / MMA warps poll their barriers (1) or suspend in try_wait (0)
+    int dbg;                    // PGK_THIN_DBG knock-outs for stage timing (results are wrong): 1 no MMAs, 2 no stores /
+                                // mask loads, 8 no loads
     float* pn_r;                // pixel norm after the activation (NPAD <= 32): per-pixel factor stored here, or NULL
     int total_units;
     int Pout, split_acc;
@@ -204,6 +206,8 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
                 wait_bar(rempty(s), ((g >> kRingLog) & 1) ^ 1);
                 if (elect_one()) {
                     const uint32_t fb = rfull(s);
+                    if (a.dbg & 8) mbar_arrive(fb);
+                    else {
                     mbar_expect_tx(fb, tx_bytes);
                     const uint32_t dst = rows0 + s * row_bytes;
 #pragma unroll
@@ -211,6 +215,7 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
 #pragma unroll
                         for (int cg = 0; cg < CG; ++cg)
                             tma_load_5d(dst + p * plane_bytes + cg * kCgBytes, &tmA, fb, cg * 8, x0 - 1, ya - 1 + j, n, p);
+                    }
                     }
                 }
                 __syncwarp();
@@ -302,7 +307,7 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
                 if (elect_one()) {
                     const uint32_t rowa = (rows0 + s * row_bytes) >> 4;
 #pragma unroll
-                    for (int ks = 0; ks < KSTEPS; ++ks) {
+                    for (int ks = 0; ks < KSTEPS && !(a.dbg & 1); ++ks) {
                         uint32_t aoff;
                         if constexpr (CIN == 8) {
                             aoff = (uint32_t)(ks * 2 * 16) / 16u;                 // (dx -1, dx 0) | (dx +1, zero weights)
@@ -437,7 +442,7 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
             const uint4* mp = reinterpret_cast<const uint4*>(a.mask.p + pix * a.Cout);
 #pragma unroll
             for (int k = 0; k < NV; ++k)
-                if (k * 8 < a.Cout) mk[k] = ldg_nc_v4(mp + k);
+                if (k * 8 < a.Cout && !(a.dbg & 2)) mk[k] = ldg_nc_v4(mp + k);
         };
         const float s_pos = a.out_scale, s_neg = a.act ? PGK_LRELU * a.out_scale : a.out_scale;
         uint32_t ti = (uint32_t)wg;
@@ -497,7 +502,7 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
                         if (8 * h < a.Cout) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[8 * h + j] *= rr;
-                            split_store8(a.out, o + 8 * h, v + 8 * h);
+                            if (!(a.dbg & 2)) split_store8(a.out, o + 8 * h, v + 8 * h);
                         }
                     }
                     done_pn = true;
@@ -533,7 +538,7 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
 #pragma unroll
                             for (int j = 0; j < 8; ++j) f[j] *= lrelu_grad(m[j]);
                         }
-                        split_store8(a.out, o + c + 8 * h, f);
+                        if (!(a.dbg & 2)) split_store8(a.out, o + c + 8 * h, f);
                     }
                 }
             }
@@ -746,6 +751,10 @@ extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N
         use_tma = e ? atoi(e) != 0 : 1;
     }
     a.tma = use_tma;
+    {
+        const char* e = getenv("PGK_THIN_DBG");
+        a.dbg = e ? atoi(e) : 0;
+    }
     static int spin = -1;
     if (spin < 0) {
         const char* e = getenv("PGK_THIN_SPIN");

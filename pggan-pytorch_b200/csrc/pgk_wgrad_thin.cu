@@ -41,6 +41,8 @@ struct WThinArgs {
     int tma;                  // producer: 1 = TMA boxes, 0 = cp.async chunks
     int spin;                 // producer / MMA warps poll their barriers (1) or suspend in try_wait (0)
     int ks_major;             // MMA issue order: 1 = the three ky accumulators interleaved per K step
+    int dbg;                  // PGK_WTHIN_DBG knock-outs for stage timing (results are wrong): 1 no MMAs, 2 no X
+                              // transposition, 4 no G transposition, 8 no loads
     int H, W, Cout, Npad, CGO;
     int RC, chunks_y, strips;
     int ngroups, group_n;
@@ -179,6 +181,8 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     wait_bar(xempty(s), ((gx >> kRawLog) & 1) ^ 1);
                     if (elect_one()) {
                         const uint32_t fb = xfull(s);
+                        if (a.dbg & 8) mbar_arrive(fb);
+                        else {
                         mbar_expect_tx(fb, P * CG * 130 * 16);
                         const uint32_t dst = rawx0 + s * rawx_slot;
 #pragma unroll
@@ -186,6 +190,7 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
                             for (int cg = 0; cg < CG; ++cg)
                                 tma_load_5d(dst + p * rawx_plane + cg * kCgBytes, &tmX, fb, a.c0 + cg * 8, x0 - 1, ya - 1 + j, xn, p);
+                        }
                         }
                     }
                     __syncwarp();
@@ -196,12 +201,15 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     wait_bar(gempty(s), ((gg >> kRawLog) & 1) ^ 1);
                     if (elect_one()) {
                         const uint32_t fb = gfull(s);
+                        if (a.dbg & 8) mbar_arrive(fb);
+                        else {
                         mbar_expect_tx(fb, P * a.CGO * 128 * 16);
                         const uint32_t dst = rawg0 + s * rawg_slot;
 #pragma unroll
                         for (int p = 0; p < P; ++p)
                             for (int cg = 0; cg < a.CGO; ++cg)
                                 tma_load_5d(dst + p * rawg_plane + cg * kGrp, &tmG, fb, cg * 8, x0, ya + j - 2, gn, p);
+                        }
                     }
                     __syncwarp();
                     ++gg;
@@ -320,6 +328,7 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 used |= 1u << c4;
                 if (elect_one()) {
                     const uint32_t later = rows_done > 0 ? 1u : 0u;
+                    if (!(a.dbg & 1)) {
                     auto issue = [&](int ky, int ks) {
                         const uint32_t d = tmem + ky * a.Npad;
                         if constexpr (ATM != 0) {   // (Cin >= 16: one plane) A tile of input row gx + ky
@@ -375,6 +384,7 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                             for (int ks = 0; ks < 8; ++ks) issue(ky, ks);
                         }
                     }
+                    }
                     mma_commit(gtempty(gg & 1));
                     mma_commit(xtempty(gx & 3));
                     if (i == a.RC - 1) {
@@ -402,7 +412,8 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     mbar_wait(xfull(s), (gx >> kRawLog) & 1);
                     mbar_wait(xtempty(b), ((gx >> 2) & 1) ^ 1);
                     const uint32_t src0 = rawx0 + s * rawx_slot;
-                    if (ATM) {
+                    if (a.dbg & 2) {
+                    } else if (ATM) {
                         // the warp that owns ring slot b (= lane quarter b of tensor memory) writes the whole row:
                         // lane = kx * 8 + ci gathers its channel of the kx-shifted pixels, lane 24 is the ones row
                         // stacked (Cin = 8): the warp that owns ring slot b writes the row into its lane quarter;
@@ -464,7 +475,7 @@ wgrad_thin_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     mbar_wait(gfull(s), (gg >> kRawLog) & 1);
                     mbar_wait(gtempty(t), ((gg >> 1) & 1) ^ 1);
                     const uint32_t src0 = rawg0 + s * rawg_slot, dst0 = gt0 + t * gt_slot;
-                    for (int o = warp; o < P * a.CGO * 4; o += 4) {
+                    for (int o = warp; o < P * a.CGO * 4 && !(a.dbg & 4); o += 4) {
                         const int blk = o & 3;
                         const int r = o >> 2;
                         const int cg = r % a.CGO, p = r / a.CGO;
@@ -673,6 +684,10 @@ extern "C" int pgk_wgrad_thin(const void* x, long long x_ps, const void* g, long
         ks_major = e ? atoi(e) != 0 : 0;
     }
     a.tma = use_tma, a.ks_major = ks_major;
+    {
+        const char* e = getenv("PGK_WTHIN_DBG");
+        a.dbg = e ? atoi(e) : 0;
+    }
     {
         static int spin = -1;
         if (spin < 0) {

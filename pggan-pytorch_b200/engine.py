@@ -30,8 +30,9 @@ W_CONV, W_GFIRST, W_DLAST = 0, 1, 2
 # their input and an fp16 packing of their weights (include/pgk.h "forward convolution on IEEE-half operand planes"):
 # three products per FLOP instead of six at the same 22 operand bits.  Measured (round 2, B200): depth 4 / batch 128
 # 88.96 -> 77.64 ms per iteration; every parity test (full widths, kernel-decision-conditioned gradients, unscreened
-# seeds) is unchanged with it.  PGK_FWD_FP16=0 keeps the six-product bf16 path (A/B runs).
-FWD_FP16 = os.environ.get('PGK_FWD_FP16', '0') == '1'
+# seeds) is unchanged with it.  Default since the fault of its first version was found (the tensor maps declared a third
+# operand plane behind the two-plane allocations: DESIGN.md 7c-4); PGK_FWD_FP16=0 keeps the six-product bf16 path (A/B).
+FWD_FP16 = os.environ.get('PGK_FWD_FP16', '1') == '1'
 # diagnostic knobs of the fault hunt
 _FP16_NOPOS = os.environ.get('PGK_FP16_NOPOS', '0') == '1'
 _FP16_MINPIX = int(os.environ.get('PGK_FP16_MINPIX', '0'))
