@@ -45,6 +45,7 @@ struct ThinArgs {
     int pair;                   // MMA warp interleaves the K steps of two output rows (two accumulators)
     int tma;                    // producer: 1 = TMA boxes (16-byte inner extent), 0 = cp.async chunks
     int spin;                   // producer / MMA warps poll their barriers (1) or suspend in try_wait (0)
+    int tstore;                 // epilogue stores through shared memory + TMA (one plane out, Cout >= 16): see the epilogue
     int dbg;                    // PGK_THIN_DBG knock-outs for stage timing (results are wrong): 1 no MMAs, 2 no stores /
                                 // mask loads, 8 no loads
     float* pn_r;                // pixel norm after the activation (NPAD <= 32): per-pixel factor stored here, or NULL
@@ -96,6 +97,7 @@ struct ThinCols {
 
 template <int CIN, int P, int SPLIT, int NPAD, int STK>
 __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                    const __grid_constant__ CUtensorMap tmO,
                                                                     const ThinArgs a) {
     static_assert(!STK || (P == 1 && SPLIT == 0), "the input-row-stationary flavour exists for the one-plane mode only");
     constexpr int NACC = STK ? StkRing<NPAD>::BLOCKS : kAcc;   // accumulator blocks in flight
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
     auto aempty = [&](int b) { return bars + 16u * kMaxRing + 8u * kAccSlots + 8u * b; };
     const uint32_t tptr = bars + 16u * kMaxRing + 16u * kAccSlots;
     float* bias_s = reinterpret_cast<float*>(smem_raw + (tptr + 16u - raw));
+    const uint32_t stage0 = (tptr + 16u + 4u * NPAD + 1023u) & ~1023u;   // store staging: 8 warps x 32 pixels x Cout bf16
 
     // ---- one-time setup: zero the row ring (padding pixels must be finite), stage weights and bias
     for (uint32_t o = threadIdx.x * 16u; o < kRing * row_bytes; o += kThinThreads * 16u)
@@ -445,6 +448,23 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
                 if (k * 8 < a.Cout && !(a.dbg & 2)) mk[k] = ldg_nc_v4(mp + k);
         };
         const float s_pos = a.out_scale, s_neg = a.act ? PGK_LRELU * a.out_scale : a.out_scale;
+        // tstore (one output plane, Cout >= 16): a lane's Cout * 2 bytes are not contiguous with its neighbour's in one
+        // 16-byte store instruction (stride Cout * 2): every such instruction occupies the LSU for 32 partial sectors,
+        // measured as about half of the kernel at Cout >= 32 (PGK_THIN_DBG=2).  Instead the warp's 32 pixels x Cout
+        // channels go to a staging tile in shared memory, written in the 32 / 64 / 128-byte swizzle pattern of the
+        // output tensor map (conflict-free 16-byte stores), and leave as ONE bulk tensor store per warp and tile.
+        const uint32_t cb = (uint32_t)a.Cout * 2u;
+        const uint32_t stg = stage0 + (uint32_t)warp * 32u * cb, my_row = stg + (uint32_t)lane * cb;
+        const uint32_t my_sw = (my_row >> 7) & (cb / 16u - 1u);
+        auto emit8 = [&](long long o, int h, const float* f) {   // channels 8h .. 8h+7 of this thread's pixel
+            if (a.tstore) {
+                uint4 q;
+                q.x = pack2(f[0], f[1]), q.y = pack2(f[2], f[3]), q.z = pack2(f[4], f[5]), q.w = pack2(f[6], f[7]);
+                st_shared_v4(my_row + (((uint32_t)h ^ my_sw) << 4), q);
+            } else if (!(a.dbg & 2)) {
+                split_store8(a.out, o + 8 * h, f);
+            }
+        };
         uint32_t ti = (uint32_t)wg;
         // (uk, ui): unit and row of the NEXT tile this warpgroup will prefetch for; base = pixel of row 0 of unit uk
         uint32_t uk = ti / (uint32_t)a.RC, ui = ti - uk * (uint32_t)a.RC;
@@ -470,6 +490,10 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
             mbar_wait(afull(b), (ti / NACC) & 1);
             fence_after();
             const uint32_t trow = tmem + b * acc_cols + trow_off;
+            if (a.tstore) {   // the previous tile's bulk store has finished reading the staging tile
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+            }
             bool done_pn = false;
             if constexpr (NPAD <= 32) {
                 if (a.pn_r) {
@@ -502,7 +526,7 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
                         if (8 * h < a.Cout) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[8 * h + j] *= rr;
-                            if (!(a.dbg & 2)) split_store8(a.out, o + 8 * h, v + 8 * h);
+                            emit8(o, h, v + 8 * h);
                         }
                     }
                     done_pn = true;
@@ -538,10 +562,18 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
 #pragma unroll
                             for (int j = 0; j < 8; ++j) f[j] *= lrelu_grad(m[j]);
                         }
-                        if (!(a.dbg & 2)) split_store8(a.out, o + c + 8 * h, f);
+                        emit8(o, c / 8 + h, f);
                     }
                 }
             }
+            }
+            if (a.tstore) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0 && !(a.dbg & 2)) {
+                    tma_store_2d(&tmO, stg, 0, (int)(pcur - lane));
+                    tma_store_commit();
+                }
             }
             if constexpr (STK != 0) {
                 // hand the block back zeroed: the next output row that lands here accumulates from its first MMA on
@@ -553,6 +585,7 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
             __syncwarp();
             if (lane == 0) mbar_arrive(aempty(b));
         }
+        if (a.tstore && lane == 0) tma_store_wait_all();
     }
     fence_before();
     __syncthreads();
@@ -633,7 +666,7 @@ struct ThinPlan {
 };
 
 template <int CIN, int P, int SPLIT, int NPAD, int STK>
-static int launch_thin(const CUtensorMap& tmA, ThinArgs& a, cudaStream_t stream) {
+static int launch_thin(const CUtensorMap& tmA, const CUtensorMap& tmO, ThinArgs& a, cudaStream_t stream) {
     static bool attr = false;
     static ThinPlan plan;   // CTAs per SM, ring depth and shared memory of this instance
     auto kern = conv_thin_kernel<CIN, P, SPLIT, NPAD, STK>;
@@ -645,7 +678,8 @@ static int launch_thin(const CUtensorMap& tmA, ThinArgs& a, cudaStream_t stream)
         }
         constexpr int steps = Steps<CIN>::N;
         constexpr int ncols = (int)ThinCols<CIN, NPAD, SPLIT, STK>::N;
-        const int fixed = 128 + P * steps * NPAD * 32 + 16 + 16 * kMaxRing + 16 * kAccSlots + 32 + 4 * NPAD + 64;
+        const int fixed = 128 + P * steps * NPAD * 32 + 16 + 16 * kMaxRing + 16 * kAccSlots + 32 + 4 * NPAD + 64 +
+                          (P == 1 ? 1024 + 8 * 32 * NPAD * 2 : 0);   // (+ the store staging tiles of the one-plane mode)
         const int row = P * (CIN / 8) * kCgBytes;
         ThinPlan pl = {0, 0, 0};
         const int cap = thin_occ_cap();
@@ -653,9 +687,13 @@ static int launch_thin(const CUtensorMap& tmA, ThinArgs& a, cudaStream_t stream)
         // Residency is computed here -- shared memory (+1 KB reserved per CTA) against the 228 KB of an SM, 512 TMEM
         // columns, and registers through __launch_bounds__(kThinThreads, 2).
         const int occ_max = cap < 512 / ncols ? cap : 512 / ncols;
+        // (a ring of 4 rows with two CTAs per SM keeps as many rows in flight per SM as 8 rows with one, and the second
+        // CTA overlaps epilogues with MMAs; the output-row-stationary flavours need 8 rows for their MMA window + look-ahead)
+        const int min_ring2 = STK ? 4 : 8;
         for (int pass = 0; pass < 2 && pl.occ == 0; ++pass) {
             for (int occ = occ_max > 2 ? 2 : occ_max; occ >= 1 && pl.occ == 0; --occ) {
-                for (int ring = pass == 0 ? 16 : 4; ring >= (pass == 0 ? 8 : 4) && pl.occ == 0; ring >>= 1) {
+                const int lo = pass == 0 ? (occ >= 2 ? min_ring2 : 8) : 4;
+                for (int ring = pass == 0 ? 16 : 4; ring >= lo && pl.occ == 0; ring >>= 1) {
                     const int smem = fixed + ring * row;
                     if (smem > kSmemLimit || occ * (smem + 1024) > 228 * 1024) continue;
                     pl.occ = occ, pl.ring = ring, pl.smem = smem;
@@ -711,7 +749,8 @@ static int launch_thin(const CUtensorMap& tmA, ThinArgs& a, cudaStream_t stream)
         }
         a.pair = !STK && pair && best_pl.ring >= 8 && best_rc % 2 == 0;
     }
-    pgk_launch(kern, best_grid, kThinThreads, best_pl.smem, stream, tmA, a);
+    if (P != 1) a.tstore = 0;   // (staging tiles are planned for the one-plane instances only)
+    pgk_launch(kern, best_grid, kThinThreads, best_pl.smem, stream, tmA, tmO, a);
     return PGK_OK;
 }
 
@@ -772,6 +811,22 @@ extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N
         int rc = pgk_make_tmap(&tmA, x, 5, dims, str, box, 0, "pgk_conv_thin(x)");
         if (rc) return rc;
     }
+    // the output as a 2-D tensor [pixel][Cout] for the epilogue's bulk stores (box = one warp's 32 pixels)
+    CUtensorMap tmO;
+    memset(&tmO, 0, sizeof(tmO));
+    static int use_tstore = -1;
+    if (use_tstore < 0) {
+        const char* e = getenv("PGK_THIN_TSTORE");
+        use_tstore = e ? atoi(e) != 0 : 1;
+    }
+    a.tstore = use_tstore && P == 1 && Pr == 1 && Cout >= 16 && (long long)N * H * W < (1ll << 31) && (((uintptr_t)out) & 15) == 0;
+    if (a.tstore) {
+        unsigned long long dims[2] = {(unsigned long long)Cout, (unsigned long long)N * H * W};
+        unsigned long long str[1] = {2ull * Cout};
+        unsigned box[2] = {(unsigned)Cout, 32u};
+        int rc = pgk_make_tmap(&tmO, out, 2, dims, str, box, 2 * Cout, "pgk_conv_thin(out)");
+        if (rc) return rc;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     int rc = PGK_ERR_ARG;
     // one-plane mode: the input-row-stationary flavour (see the kernel header); PGK_THIN_STK=0 keeps the
@@ -782,13 +837,13 @@ extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N
         stk = e ? atoi(e) != 0 : 1;
     }
 #define PGK_THIN_STK_CASE(C_, N_) \
-    if (stk && Pr == 1 && P == 1 && Cin == C_ && a.Npad == N_) rc = launch_thin<C_, 1, 0, N_, 1>(tmA, a, st);
+    if (stk && Pr == 1 && P == 1 && Cin == C_ && a.Npad == N_) rc = launch_thin<C_, 1, 0, N_, 1>(tmA, tmO, a, st);
     PGK_THIN_STK_CASE(8, 16) PGK_THIN_STK_CASE(8, 32) PGK_THIN_STK_CASE(8, 64)
     PGK_THIN_STK_CASE(16, 16) PGK_THIN_STK_CASE(16, 32) PGK_THIN_STK_CASE(16, 64)
     PGK_THIN_STK_CASE(32, 16) PGK_THIN_STK_CASE(32, 32) PGK_THIN_STK_CASE(32, 64)
 #undef PGK_THIN_STK_CASE
 #define PGK_THIN_CASE_N(C_, P_, S_, N_) \
-    if (rc == PGK_ERR_ARG && Cin == C_ && Pr == P_ && a.split_acc == S_ && a.Npad == N_) rc = launch_thin<C_, P_, S_, N_, 0>(tmA, a, st);
+    if (rc == PGK_ERR_ARG && Cin == C_ && Pr == P_ && a.split_acc == S_ && a.Npad == N_) rc = launch_thin<C_, P_, S_, N_, 0>(tmA, tmO, a, st);
 #define PGK_THIN_CASE(C_, P_, S_) PGK_THIN_CASE_N(C_, P_, S_, 16) PGK_THIN_CASE_N(C_, P_, S_, 32) PGK_THIN_CASE_N(C_, P_, S_, 64)
     PGK_THIN_CASE(8, 1, 0) PGK_THIN_CASE(16, 1, 0) PGK_THIN_CASE(32, 1, 0)
     PGK_THIN_CASE(8, 2, 0) PGK_THIN_CASE(16, 2, 0) PGK_THIN_CASE(32, 2, 0)

@@ -117,6 +117,11 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, uint32_t src,
                  "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m), "r"(src), "r"(c0),
+                 "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the bulk groups committed by this thread have finished READING shared memory
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

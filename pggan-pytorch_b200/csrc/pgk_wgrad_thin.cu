@@ -650,6 +650,11 @@ static int launch_wthin(const CUtensorMap& tmX, const CUtensorMap& tmG, WThinArg
     return PGK_OK;
 }
 
+// the transposer-free one-plane flavour (pgk_wgrad_direct.cu)
+int pgk_wgrad_thin_direct(const void* x, const void* g, int H, int W, int Cin, int cin_total, int c0, int Cout,
+                          int ngroups, int group_n, const int* xoff, const int* goff, float* dwp, float* db,
+                          unsigned bias_mask, pgk_stream_t stream);
+
 // Cin: channels handled by this launch (8, 16 or 32), starting at channel c0 of an x tensor with cin_total channels
 // (a 64-channel input is two launches).  db (optional): fused bias gradient over the groups in bias_mask; db and dwp
 // are accumulated into (the caller zeroes them).
@@ -659,9 +664,27 @@ extern "C" int pgk_wgrad_thin(const void* x, long long x_ps, const void* g, long
     PGK_REQUIRE(pgk_wgrad_thin_supported(H, W, Cin, Cout, 3, 0, ngroups, group_n, Pr), "pgk_wgrad_thin: unsupported shape");
     PGK_REQUIRE(c0 >= 0 && c0 % 8 == 0 && c0 + Cin <= cin_total, "pgk_wgrad_thin: bad channel window");
     PGK_REQUIRE(P >= Pr && P <= 3 && ngroups >= 1 && ngroups <= 4, "pgk_wgrad_thin: bad planes / groups");
+    PGK_REQUIRE((((uintptr_t)x | (uintptr_t)g) & 15) == 0 && (Pr == 1 || ((x_ps | g_ps) * 2) % 16 == 0),
+                "pgk_wgrad_thin: x and g must be 16-byte aligned");
+    {
+        // one-plane mode: rows are read as MN-major operands where TMA put them (no transposition stage);
+        // PGK_WTHIN_DIRECT=0 keeps the transposing kernel below for A/B runs
+        static int direct = -1;
+        if (direct < 0) {
+            const char* e = getenv("PGK_WTHIN_DIRECT");
+            direct = e ? atoi(e) != 0 : 1;
+        }
+        if (direct && P == 1 && Pr == 1) {
+            int rc = pgk_wgrad_thin_direct(x, g, H, W, Cin, cin_total, c0, Cout, ngroups, group_n, xoff, goff, dwp, db,
+                                           bias_mask, stream);
+            if (rc) return rc;
+            PGK_LAUNCH_CHECK("pgk_wgrad(thin tcgen05, direct)");
+            return PGK_OK;
+        }
+    }
     WThinArgs a;
     a.H = H, a.W = W, a.Cout = Cout, a.Npad = Cout < 16 ? 16 : Cout, a.CGO = Cout / 8;
-    a.RC = H >= 32 ? 32 : H;
+    a.RC = H < 32 ? H : H % 32 == 0 ? 32 : H % 16 == 0 ? 16 : 8;   // (H is a multiple of 8)
     a.chunks_y = H / a.RC;
     a.strips = W / 128;
     a.ngroups = ngroups, a.group_n = group_n;

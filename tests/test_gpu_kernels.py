@@ -84,6 +84,21 @@ WGRAD = [
     (2, 256, 256, 64, 32, 1, 2),
     (1, 128, 128, 64, 16, 2, 1),
     (3, 512, 512, 8, 8, 1, 4),
+    # every (Cin, Cout) instance of the transposer-free one-plane kernel, several units per CTA, ring wrap-around
+    (1, 128, 128, 8, 16, 1, 1),
+    (1, 128, 128, 8, 32, 1, 2),
+    (1, 128, 256, 8, 64, 1, 1),
+    (1, 128, 128, 16, 32, 1, 1),
+    (2, 128, 128, 16, 64, 1, 2),
+    (1, 128, 128, 32, 8, 1, 1),
+    (1, 256, 128, 32, 16, 1, 3),
+    (6, 512, 512, 16, 16, 1, 2),
+    (5, 256, 256, 32, 32, 1, 1),
+    (3, 512, 256, 32, 64, 1, 1),
+    (2, 8, 128, 16, 32, 1, 1),
+    (2, 24, 128, 32, 32, 1, 1),
+    (1, 40, 128, 16, 16, 1, 1),
+    (1, 40, 128, 16, 16, 2, 1),
     (4, 16, 16, 64, 64, 1, 1),
     (4, 16, 16, 64, 64, 3, 1),
     (16, 4, 4, 128, 64, 3, 2),
