@@ -33,7 +33,8 @@ CONFIGS = {
     'c4': dict(depth=8, alpha=0.3, n=4, precision='bf16', res=1024, ch=3),
     'c5': dict(depth=5, alpha=1.0, n=64, precision='bf16', res=128, ch=1),
 }
-DTYPE = {'fp32': 'bf16x3 (three bf16 planes = 24 mantissa bits, fp32 accumulate; fp32-faithful)',
+DTYPE = {'fp32': 'bf16x3 (fp32-faithful: tensors as three bf16 planes = 24 mantissa bits; wide forward convs read two '
+                 'fp16 planes = 22 bits; fp32 accumulate)',
          'bf16': 'bf16 (fp32 accumulate)'}
 
 
@@ -186,8 +187,9 @@ def assemble_roofline(config, cfg, fam, prod, ksteps, step_s, batch_overridden=F
                 step_algorithmic={'gflop_per_image': fimg / 1e9, 'achieved': fimg * n / step_s / 1e12,
                                   'frac': fimg * n / step_s / 1e12 / peak_tf})
     if cfg['precision'] == 'fp32':
-        roof['note'] = ('fp32-faithful mode: every algorithmic FLOP costs 6 (forward) or 3 (gradient chains) bf16 '
-                        'tensor-core products, so frac <= 1/6 .. 1/3 by construction; tensor_pipe counts the products')
+        roof['note'] = ('fp32-faithful mode: every algorithmic FLOP costs 3 tensor-core products (forward: two fp16 '
+                        'planes; gradient chains: two bf16 planes; 6 with PGK_FWD_FP16=0), so frac <= 1/3 by '
+                        'construction; tensor_pipe counts the products')
     return roof
 
 

@@ -46,6 +46,7 @@ struct ThinArgs {
     int tma;                    // producer: 1 = TMA boxes (16-byte inner extent), 0 = cp.async chunks
     int spin;                   // producer / MMA warps poll their barriers (1) or suspend in try_wait (0)
     int tstore;                 // epilogue stores through shared memory + TMA (one plane out, Cout >= 16): see the epilogue
+    int mload;                  // backward masks loaded warp-coalesced and redistributed through the staging tile
     int dbg;                    // PGK_THIN_DBG knock-outs for stage timing (results are wrong): 1 no MMAs, 2 no stores /
                                 // mask loads, 8 no loads
     float* pn_r;                // pixel norm after the activation (NPAD <= 32): per-pixel factor stored here, or NULL
@@ -442,6 +443,16 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
 #pragma unroll
         for (int k = 0; k < NV; ++k) mk[k] = make_uint4(0, 0, 0, 0);
         auto load_mask = [&](long long pix) {   // plane 0 only: its sign is the sign of the value
+            if (a.mload) {
+                // the warp's 32 pixels x Cout channels are 32 * Cout * 2 contiguous bytes: lane takes the 16-byte chunks
+                // lane, lane + 32, ... (full lines per instruction); they reach their pixel's thread through the
+                // staging tile when the tile is processed (below)
+                const uint4* mp = reinterpret_cast<const uint4*>(a.mask.p + (pix - lane) * a.Cout) + lane;
+#pragma unroll
+                for (int k = 0; k < NV; ++k)
+                    if (!(a.dbg & 2)) mk[k] = ldg_nc_v4(mp + k * 32);
+                return;
+            }
             const uint4* mp = reinterpret_cast<const uint4*>(a.mask.p + pix * a.Cout);
 #pragma unroll
             for (int k = 0; k < NV; ++k)
@@ -492,6 +503,19 @@ __global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid
             const uint32_t trow = tmem + b * acc_cols + trow_off;
             if (a.tstore) {   // the previous tile's bulk store has finished reading the staging tile
                 if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+            }
+            if (a.mload) {
+                // chunk c = 32 k + lane of the warp's block belongs to pixel c / NV, channels 8 (c % NV) ..: written in
+                // the tile's swizzle (512 contiguous bytes per instruction), read back by the pixel's own thread
+#pragma unroll
+                for (int k = 0; k < NV; ++k) {
+                    const uint32_t c = (uint32_t)(k * 32 + lane), row = stg + (c / NV) * cb;
+                    st_shared_v4(row + (((c % NV) ^ ((row >> 7) & (cb / 16u - 1u))) << 4), mc[k]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < NV; ++k) mc[k] = ld_shared_v4(my_row + (((uint32_t)k ^ my_sw) << 4));
                 __syncwarp();
             }
             bool done_pn = false;
@@ -749,7 +773,7 @@ static int launch_thin(const CUtensorMap& tmA, const CUtensorMap& tmO, ThinArgs&
         }
         a.pair = !STK && pair && best_pl.ring >= 8 && best_rc % 2 == 0;
     }
-    if (P != 1) a.tstore = 0;   // (staging tiles are planned for the one-plane instances only)
+    if (P != 1) a.tstore = a.mload = 0;   // (staging tiles are planned for the one-plane instances only)
     pgk_launch(kern, best_grid, kThinThreads, best_pl.smem, stream, tmA, tmO, a);
     return PGK_OK;
 }
@@ -819,7 +843,13 @@ extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N
         const char* e = getenv("PGK_THIN_TSTORE");
         use_tstore = e ? atoi(e) != 0 : 1;
     }
+    static int use_mload = -1;
+    if (use_mload < 0) {
+        const char* e = getenv("PGK_THIN_MLOAD");
+        use_mload = e ? atoi(e) != 0 : 1;
+    }
     a.tstore = use_tstore && P == 1 && Pr == 1 && Cout >= 16 && (long long)N * H * W < (1ll << 31) && (((uintptr_t)out) & 15) == 0;
+    a.mload = a.tstore && use_mload && mask_ref != nullptr && (((uintptr_t)mask_ref) & 15) == 0;
     if (a.tstore) {
         unsigned long long dims[2] = {(unsigned long long)Cout, (unsigned long long)N * H * W};
         unsigned long long str[1] = {2ull * Cout};
