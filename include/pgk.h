@@ -314,9 +314,14 @@ int pgk_real_prep(const void* src, int src_is_u8, int N, int C, int H, int W, do
 
 /* ---- optimizer (the step just after the path) ----------------------------------------------------
  * torch.optim.Adam as wired by train.py:148-149,195 for every parameter with a gradient, in ONE launch.
- * table (device): ntensors rows of 8 x 64-bit words {param ptr, grad ptr, exp_avg ptr, exp_avg_sq ptr, numel,
- * float bits of lr / (1 - beta1^t), float bits of 1 / sqrt(1 - beta2^t), 0}; all tensors fp32 contiguous. */
-int pgk_adam_multi(const void* table, int ntensors, long long max_numel, float beta1, float beta2, float eps,
+ * table (device): ntensors (<= 1024) rows of 8 x 64-bit words {param ptr, grad ptr, exp_avg ptr, exp_avg_sq ptr, numel,
+ * float bits of lr / (1 - beta1^t), float bits of 1 / sqrt(1 - beta2^t), first block}; all tensors fp32 contiguous.
+ * Block b of the one-dimensional grid updates PGK_ADAM_CHUNK elements of the tensor whose block range holds it:
+ * first block of row 0 = 0, of row i+1 = first block of row i + ceil(numel_i / PGK_ADAM_CHUNK); total_blocks = the sum.
+ * pgk_adam_chunk() returns PGK_ADAM_CHUNK. */
+#define PGK_ADAM_CHUNK 4096
+int pgk_adam_chunk(void);
+int pgk_adam_multi(const void* table, int ntensors, long long total_blocks, float beta1, float beta2, float eps,
                    pgk_stream_t stream);
 
 #ifdef __cplusplus

@@ -119,6 +119,8 @@ def load():
     lib.pgk_set_tc.restype = None
     lib.pgk_conv_tc_supported.argtypes = [c_int] * 7
     lib.pgk_conv_tc_supported.restype = c_int
+    lib.pgk_adam_chunk.argtypes = []
+    lib.pgk_adam_chunk.restype = c_int
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = list(args) + [c_void_p]
@@ -131,7 +133,7 @@ def exported_symbols():
     return ['pgk_version', 'pgk_last_error', 'pgk_arch_check', 'pgk_launch_count', 'pgk_reset_launch_count',
             'pgk_count_launch', 'pgk_pdl_state',
             'pgk_prof_enable', 'pgk_prof_read', 'pgk_prof_read_products', 'pgk_prof_reset', 'pgk_set_tc', 'pgk_pack_thin_plane_elems',
-            'pgk_conv_tc_supported'] + list(SIGNATURES)
+            'pgk_conv_tc_supported', 'pgk_adam_chunk'] + list(SIGNATURES)
 
 
 _checked_devices = set()
@@ -170,6 +172,11 @@ def launch_count():
 def add_launches(n):
     """Account for kernels launched by a replayed CUDA graph (they do not pass through the C entry points)."""
     load().pgk_count_launch(int(n))
+
+
+def adam_chunk():
+    """Elements one block of pgk_adam_multi updates (include/pgk.h: PGK_ADAM_CHUNK)."""
+    return int(load().pgk_adam_chunk())
 
 
 def pdl_state(on=None):

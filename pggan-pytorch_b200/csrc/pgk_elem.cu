@@ -145,6 +145,11 @@ __global__ void posbias_wgrad_kernel(Planes ua, int N, int H, int W, int Cout, c
     atomicAdd(dw + (((long long)co * cin_stride + ch) * 3 + ky) * 3 + kx, c * s);
 }
 
+// items per thread and pass in the 1x1 image kernels (1 = the round-1 loops; A/B builds: make EXTRA=-DPGK_RGB_UN=1)
+#ifndef PGK_RGB_UN
+#define PGK_RGB_UN 4
+#endif
+
 // ------------------------------------------------------------------------------------------
 // 1x1 convs against the image surface
 // ------------------------------------------------------------------------------------------
@@ -178,47 +183,66 @@ __global__ void __launch_bounds__(256) rgb_expand_kernel(ExpandArgs a) {
     const IT nch = (IT)(a.K >> 3);
     const IT HW = (IT)(a.H * a.W);
     const IT total = (IT)a.N * HW * nch;
-    for (IT idx = (IT)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (IT)gridDim.x * blockDim.x) {
-        const IT pix = idx / nch;
-        const int chunk = (int)(idx - pix * nch);
-        const int n = (int)(pix / HW);
-        const int r = (int)(pix - (IT)n * HW);
-        float iv[MAXC];
-        if (!a.pool) {
+    // UN items per thread and pass, every load of the pass issued before the first use: one item keeps 12-28 bytes in
+    // flight per thread, which left these launches at a third of the copy bandwidth (latency bound)
+    constexpr int UN = PGK_RGB_UN;
+    const IT stride = (IT)gridDim.x * blockDim.x;
+    for (IT idx0 = (IT)blockIdx.x * blockDim.x + threadIdx.x; idx0 < total; idx0 += UN * stride) {
+        float iv[UN][MAXC];
+        float m[UN][8];
+        long long o[UN];
+        int chunk[UN];
+        bool ok[UN];
 #pragma unroll
-            for (int c = 0; c < MAXC; ++c)
-                if (c < a.C) iv[c] = __ldg(a.img + ((long long)n * a.C + c) * HW + r);
-        } else {
-            int y = r / a.W, x = r - y * a.W;
-            int W2 = a.W * 2;
+        for (int u = 0; u < UN; ++u) {
+            const IT idx = idx0 + (IT)u * stride;
+            ok[u] = idx < total;
+            if (!ok[u]) continue;
+            const IT pix = idx / nch;
+            chunk[u] = (int)(idx - pix * nch);
+            const int n = (int)(pix / HW);
+            const int r = (int)(pix - (IT)n * HW);
+            if (!a.pool) {
 #pragma unroll
-            for (int c = 0; c < MAXC; ++c)
-                if (c < a.C) {
-                    const float* p = a.img + (((long long)n * a.C + c) * (a.H * 2) + 2 * y) * W2 + 2 * x;
-                    iv[c] = (__ldg(p) + __ldg(p + 1)) + (__ldg(p + W2) + __ldg(p + W2 + 1));
-                }
+                for (int c = 0; c < MAXC; ++c)
+                    if (c < a.C) iv[u][c] = __ldg(a.img + ((long long)n * a.C + c) * HW + r);
+            } else {
+                int y = r / a.W, x = r - y * a.W;
+                int W2 = a.W * 2;
+#pragma unroll
+                for (int c = 0; c < MAXC; ++c)
+                    if (c < a.C) {
+                        const float* p = a.img + (((long long)n * a.C + c) * (a.H * 2) + 2 * y) * W2 + 2 * x;
+                        iv[u][c] = (__ldg(p) + __ldg(p + 1)) + (__ldg(p + W2) + __ldg(p + W2 + 1));
+                    }
+            }
+            o[u] = (long long)pix * a.K + chunk[u] * 8;
+            if (a.has_mask) {
+                Planes m0 = a.mask;   // the sign of plane 0 is the sign of the value
+                m0.P = 1;
+                ld8(m0, o[u], m[u]);
+            }
         }
-        float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float s = 0.f;
+        for (int u = 0; u < UN; ++u) {
+            if (!ok[u]) continue;
+            float v[8];
 #pragma unroll
-            for (int c = 0; c < MAXC; ++c)
-                if (c < a.C) s = fmaf(iv[c], wsm[c * a.K + chunk * 8 + j], s);
-            if (a.bias) s += __ldg(a.bias + chunk * 8 + j);
-            if (a.act) s = lrelu(s);
-            v[j] = s;
+            for (int j = 0; j < 8; ++j) {
+                float s = 0.f;
+#pragma unroll
+                for (int c = 0; c < MAXC; ++c)
+                    if (c < a.C) s = fmaf(iv[u][c], wsm[c * a.K + chunk[u] * 8 + j], s);
+                if (a.bias) s += __ldg(a.bias + chunk[u] * 8 + j);
+                if (a.act) s = lrelu(s);
+                v[j] = s;
+            }
+            if (a.has_mask) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] *= lrelu_grad(m[u][j]);
+            }
+            split_store8(a.out, o[u], v);
         }
-        long long o = (long long)pix * a.K + chunk * 8;
-        if (a.has_mask) {
-            float m[8];
-            Planes m0 = a.mask;   // the sign of plane 0 is the sign of the value
-            m0.P = 1;
-            ld8(m0, o, m);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] *= lrelu_grad(m[j]);
-        }
-        split_store8(a.out, o, v);
     }
 }
 
@@ -309,6 +333,72 @@ __global__ void __launch_bounds__(256) rgb_reduce_kernel(ReduceArgs a) {
     }
 }
 
+// UN pixels per thread and pass, MCH chunks of 8 channels per source at most; one-plane tensors (raw 16-byte loads are
+// kept packed until they are used)
+template <int UN, int MCH>
+__device__ __forceinline__ void reduce_px_narrow(const ReduceArgs& a, const float* wsm, int off1, int offb, unsigned npix,
+                                                 unsigned HW, unsigned W, unsigned stride) {
+    for (unsigned pix0 = blockIdx.x * blockDim.x + threadIdx.x; pix0 < npix; pix0 += UN * stride) {
+        uint4 q[UN][2][MCH];
+        unsigned nn[UN], rr[UN];
+        bool ok[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const unsigned pix = pix0 + u * stride;
+            ok[u] = pix < npix;
+            if (!ok[u]) continue;
+            const unsigned n = pix / HW, r = pix - n * HW;
+            const unsigned y = r / W, x = r - y * W;
+            nn[u] = n, rr[u] = r;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (s >= a.nsrc) continue;
+                const ReduceSrc& S = a.s[s];
+                const unsigned Hs = a.H >> S.ups, Ws = a.W >> S.ups;
+                const long long base = ((long long)(n * Hs + (y >> S.ups)) * Ws + (x >> S.ups)) * S.K;
+#pragma unroll
+                for (int ch = 0; ch < MCH; ++ch)
+                    if (ch < (S.K >> 3)) q[u][s][ch] = __ldg(reinterpret_cast<const uint4*>(S.t.p + base + ch * 8));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            if (!ok[u]) continue;
+            float acc[MAXC];
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) acc[c] = wsm[offb + c];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (s >= a.nsrc) continue;
+                const int K = a.s[s].K;
+                const float* wm = wsm + (s ? off1 : 0);
+#pragma unroll
+                for (int ch = 0; ch < MCH; ++ch) {
+                    if (ch >= (K >> 3)) continue;
+                    float g[8];
+                    unpack8(q[u][s][ch], g);
+#pragma unroll
+                    for (int c = 0; c < MAXC; ++c)
+                        if (c < a.C) {
+                            const float4 w0 = *reinterpret_cast<const float4*>(wm + c * K + ch * 8);
+                            const float4 w1 = *reinterpret_cast<const float4*>(wm + c * K + ch * 8 + 4);
+                            float t = acc[c];
+                            t = fmaf(g[0], w0.x, t), t = fmaf(g[1], w0.y, t), t = fmaf(g[2], w0.z, t), t = fmaf(g[3], w0.w, t);
+                            t = fmaf(g[4], w1.x, t), t = fmaf(g[5], w1.y, t), t = fmaf(g[6], w1.z, t), t = fmaf(g[7], w1.w, t);
+                            acc[c] = t;
+                        }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c)
+                if (c < a.C) {
+                    const long long o = ((long long)nn[u] * a.C + c) * HW + rr[u];
+                    a.img[o] = a.accumulate ? a.img[o] + acc[c] : acc[c];
+                }
+        }
+    }
+}
+
 // The same reduction with one thread per output pixel -- full-warp coalesced image stores, no idle lanes or shuffles,
 // 32-bit index arithmetic, weights read from shared memory as float4 broadcasts, the bias terms folded into one
 // constant per image channel.  (A lane reads its pixel's K channels 16 bytes at a time; the other half of every
@@ -337,7 +427,19 @@ __global__ void __launch_bounds__(256) rgb_reduce_px_kernel(ReduceArgs a) {
     }
     __syncthreads();
     const unsigned npix = (unsigned)a.N * a.H * a.W, HW = (unsigned)a.H * a.W, W = (unsigned)a.W;
-    for (unsigned pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
+    const unsigned stride = gridDim.x * blockDim.x;
+    // narrow one-plane layers (the 256^2 ... 1024^2 levels): one pixel is 16-64 bytes of loads, so several pixels per
+    // thread and pass with their loads issued first; wide layers keep one pixel (K / 8 independent loads already)
+    const int kmax = (a.nsrc > 1 && a.s[1].K > a.s[0].K) ? a.s[1].K : a.s[0].K;
+    if (PGK_RGB_UN > 1 && a.s[0].t.P == 1 && kmax <= 16) {
+        reduce_px_narrow<4, 2>(a, wsm, off1, offb, npix, HW, W, stride);
+        return;
+    }
+    if (PGK_RGB_UN > 1 && a.s[0].t.P == 1 && kmax <= 32) {
+        reduce_px_narrow<2, 4>(a, wsm, off1, offb, npix, HW, W, stride);
+        return;
+    }
+    for (unsigned pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += stride) {
         const unsigned n = pix / HW, r = pix - n * HW;
         const unsigned y = r / W, x = r - y * W;
         float acc[MAXC];
@@ -414,41 +516,56 @@ __global__ void __launch_bounds__(256) rgb_wgrad_kernel(RgbWgradArgs a) {
     long long r_begin = (long long)blockIdx.x * a.r_per_cta, r_end = r_begin + a.r_per_cta;
     if (r_end > a.R) r_end = a.R;
     if (pl < lanes) {
-        for (long long rr = r_begin + pl; rr < r_end; rr += lanes) {
-            int n, r;
-            if (a.R < (1ll << 31)) {
-                n = (int)((unsigned)rr / (unsigned)HW);
-                r = (int)((unsigned)rr - (unsigned)n * (unsigned)HW);
-            } else {
-                n = (int)(rr / HW);
-                r = (int)(rr - (long long)n * HW);
+        // four pixels per pass, loads first (same pixels, same order per thread as one at a time: identical sums)
+        constexpr int UN = PGK_RGB_UN;
+        for (long long rr0 = r_begin + pl; rr0 < r_end; rr0 += (long long)UN * lanes) {
+            float iv[UN][MAXC];
+            float f[UN][8];
+            bool ok[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const long long rr = rr0 + (long long)u * lanes;
+                ok[u] = rr < r_end;
+#pragma unroll
+                for (int c = 0; c < MAXC; ++c) iv[u][c] = 0.f;
+                if (!ok[u]) continue;
+                int n, r;
+                if (a.R < (1ll << 31)) {
+                    n = (int)((unsigned)rr / (unsigned)HW);
+                    r = (int)((unsigned)rr - (unsigned)n * (unsigned)HW);
+                } else {
+                    n = (int)(rr / HW);
+                    r = (int)(rr - (long long)n * HW);
+                }
+                if (!a.pool) {
+#pragma unroll
+                    for (int c = 0; c < MAXC; ++c)
+                        if (c < a.C) iv[u][c] = __ldg(a.img + ((long long)(a.img_n0 + n) * a.C + c) * HW + r);
+                } else {
+                    int y = r / a.W, x = r - y * a.W;
+                    int W2 = a.W * 2;
+#pragma unroll
+                    for (int c = 0; c < MAXC; ++c)
+                        if (c < a.C) {
+                            const float* p = a.img + (((long long)(a.img_n0 + n) * a.C + c) * (a.H * 2) + 2 * y) * W2 + 2 * x;
+                            iv[u][c] = (__ldg(p) + __ldg(p + 1)) + (__ldg(p + W2) + __ldg(p + W2 + 1));
+                        }
+                }
+                ld8(a.t, ((long long)(a.t_n0 + n) * HW + r) * a.K + ch * 8, f[u]);
             }
-            float iv[MAXC] = {0.f, 0.f, 0.f, 0.f};
-            if (!a.pool) {
 #pragma unroll
-                for (int c = 0; c < MAXC; ++c)
-                    if (c < a.C) iv[c] = __ldg(a.img + ((long long)(a.img_n0 + n) * a.C + c) * HW + r);
-            } else {
-                int y = r / a.W, x = r - y * a.W;
-                int W2 = a.W * 2;
+            for (int u = 0; u < UN; ++u) {
+                if (!ok[u]) continue;
 #pragma unroll
-                for (int c = 0; c < MAXC; ++c)
-                    if (c < a.C) {
-                        const float* p = a.img + (((long long)(a.img_n0 + n) * a.C + c) * (a.H * 2) + 2 * y) * W2 + 2 * x;
-                        iv[c] = (__ldg(p) + __ldg(p + 1)) + (__ldg(p + W2) + __ldg(p + W2 + 1));
-                    }
-            }
-            float f[8];
-            ld8(a.t, ((long long)(a.t_n0 + n) * HW + r) * a.K + ch * 8, f);
+                for (int j = 0; j < 8; ++j) {
+                    cs[j] += f[u][j];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                cs[j] += f[j];
+                    for (int c = 0; c < MAXC; ++c) acc[c][j] = fmaf(iv[u][c], f[u][j], acc[c][j]);
+                }
+                if (ch == 0) {
 #pragma unroll
-                for (int c = 0; c < MAXC; ++c) acc[c][j] = fmaf(iv[c], f[j], acc[c][j]);
-            }
-            if (ch == 0) {
-#pragma unroll
-                for (int c = 0; c < MAXC; ++c) is[c] += iv[c];
+                    for (int c = 0; c < MAXC; ++c) is[c] += iv[u][c];
+                }
             }
         }
     }
@@ -1473,32 +1590,87 @@ extern "C" int pgk_real_prep(const void* src, int src_is_u8, int N, int C, int H
 
 // multi-tensor Adam (torch.optim.Adam as wired by train.py:148-149,195: betas (0, 0.99), eps 1e-8, no weight decay).
 // One launch for every parameter that has a gradient.  table: n rows of 8 x 64-bit words
-//   {param ptr, grad ptr, exp_avg ptr, exp_avg_sq ptr, numel, step_size = lr/bc1 (float bits), 1/sqrt(bc2) (float bits), 0}
-__global__ void adam_multi_kernel(const unsigned long long* __restrict__ table, float beta1, float beta2, float eps) {
+//   {param ptr, grad ptr, exp_avg ptr, exp_avg_sq ptr, numel, step_size = lr/bc1 (float bits), 1/sqrt(bc2) (float bits),
+//    first block}
+// The grid is one-dimensional: block b works on PGK_ADAM_CHUNK elements of the tensor whose [first block, next first
+// block) range holds b (rows in ascending first-block order), so that the many small tensors (biases) cost one block
+// each instead of a grid row of empty blocks; 16-byte accesses where the four pointers allow, every load of a thread's
+// four vectors issued before the first store.
+constexpr int kAdamChunk = PGK_ADAM_CHUNK;
+__device__ __forceinline__ float adam_one(float gi, float& mi, float& vi, float beta1, float beta2, float step_size,
+                                          float inv_sqrt_bc2, float eps) {
+    mi = beta1 * mi + (1.f - beta1) * gi;
+    vi = beta2 * vi + (1.f - beta2) * gi * gi;
+    return step_size * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
+}
+__global__ void __launch_bounds__(256) adam_multi_kernel(const unsigned long long* __restrict__ table, int ntensors,
+                                                         float beta1, float beta2, float eps) {
     pgk_pdl_enter();
-    const unsigned long long* e = table + 8ull * blockIdx.y;
+    __shared__ unsigned long long first[1024];
+    for (int i = threadIdx.x; i < ntensors; i += blockDim.x) first[i] = table[8ull * i + 7];
+    __syncthreads();
+    int lo = 0, hi = ntensors - 1;
+    const unsigned long long bid = blockIdx.x;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (first[mid] <= bid) lo = mid;
+        else hi = mid - 1;
+    }
+    const unsigned long long* e = table + 8ull * lo;
     float* p = reinterpret_cast<float*>(e[0]);
     const float* g = reinterpret_cast<const float*>(e[1]);
     float* m = reinterpret_cast<float*>(e[2]);
     float* v = reinterpret_cast<float*>(e[3]);
     const long long n = (long long)e[4];
     const float step_size = __uint_as_float((unsigned)e[5]), inv_sqrt_bc2 = __uint_as_float((unsigned)e[6]);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const float gi = g[i];
-        const float mi = beta1 * m[i] + (1.f - beta1) * gi;
-        const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    const long long i0 = (long long)(bid - first[lo]) * kAdamChunk;
+    long long i1 = i0 + kAdamChunk;
+    if (i1 > n) i1 = n;
+    if (i0 >= n) return;
+    const bool vec = ((e[0] | e[1] | e[2] | e[3]) & 15ull) == 0;
+    long long done = i0;
+    if (vec) {
+        constexpr int UN = kAdamChunk / 1024;   // float4 per thread
+        float4 gq[UN], mq[UN], vq[UN], pq[UN];
+        bool ok[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const long long i = i0 + 4ll * (threadIdx.x + 256 * u);
+            ok[u] = i + 3 < i1;
+            if (ok[u]) {
+                gq[u] = *reinterpret_cast<const float4*>(g + i), mq[u] = *reinterpret_cast<const float4*>(m + i);
+                vq[u] = *reinterpret_cast<const float4*>(v + i), pq[u] = *reinterpret_cast<const float4*>(p + i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            if (!ok[u]) continue;
+            const long long i = i0 + 4ll * (threadIdx.x + 256 * u);
+            pq[u].x -= adam_one(gq[u].x, mq[u].x, vq[u].x, beta1, beta2, step_size, inv_sqrt_bc2, eps);
+            pq[u].y -= adam_one(gq[u].y, mq[u].y, vq[u].y, beta1, beta2, step_size, inv_sqrt_bc2, eps);
+            pq[u].z -= adam_one(gq[u].z, mq[u].z, vq[u].z, beta1, beta2, step_size, inv_sqrt_bc2, eps);
+            pq[u].w -= adam_one(gq[u].w, mq[u].w, vq[u].w, beta1, beta2, step_size, inv_sqrt_bc2, eps);
+            *reinterpret_cast<float4*>(m + i) = mq[u], *reinterpret_cast<float4*>(v + i) = vq[u];
+            *reinterpret_cast<float4*>(p + i) = pq[u];
+        }
+        done = i0 + ((i1 - i0) & ~3ll);
+    }
+    for (long long i = done + threadIdx.x; i < i1; i += blockDim.x) {
+        float mi = m[i], vi = v[i];
+        const float d = adam_one(g[i], mi, vi, beta1, beta2, step_size, inv_sqrt_bc2, eps);
         m[i] = mi, v[i] = vi;
-        p[i] -= step_size * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
+        p[i] -= d;
     }
 }
 
-extern "C" int pgk_adam_multi(const void* table, int ntensors, long long max_numel, float beta1, float beta2, float eps,
+extern "C" int pgk_adam_chunk() { return kAdamChunk; }
+
+extern "C" int pgk_adam_multi(const void* table, int ntensors, long long total_blocks, float beta1, float beta2, float eps,
                               pgk_stream_t stream) {
-    PGK_REQUIRE(ntensors > 0 && ntensors <= 65535 && max_numel > 0, "pgk_adam_multi: bad table size");
-    long long bx = (max_numel + 1023) / 1024;   // 4 elements per thread at the largest tensor, grid-stride beyond
-    if (bx > 2048) bx = 2048;
-    dim3 grid((unsigned)bx, (unsigned)ntensors);
-    pgk_launch(adam_multi_kernel, grid, 256, 0, ST, (const unsigned long long*)table, beta1, beta2, eps);
+    PGK_REQUIRE(ntensors > 0 && ntensors <= 1024 && total_blocks > 0 && total_blocks < (1ll << 31),
+                "pgk_adam_multi: bad table size (1..1024 tensors)");
+    pgk_launch(adam_multi_kernel, dim3((unsigned)total_blocks), 256, 0, ST, (const unsigned long long*)table, ntensors, beta1,
+               beta2, eps);
     PGK_LAUNCH_CHECK("pgk_adam_multi");
     return PGK_OK;
 }

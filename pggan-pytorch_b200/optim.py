@@ -52,7 +52,8 @@ class FusedAdam(torch.optim.Optimizer):
                 loss = closure()
         for group in self.param_groups:
             beta1, beta2 = group['betas']
-            rows, max_numel, dev, keep, updated = [], 0, None, [], []
+            rows, nblocks, dev, keep, updated = [], 0, None, [], []
+            chunk = _lib.adam_chunk()
             for p in group['params']:
                 if p.grad is None:
                     continue
@@ -73,10 +74,10 @@ class FusedAdam(torch.optim.Optimizer):
                 inv_sqrt_bc2 = 1.0 / math.sqrt(1.0 - beta2 ** t)
                 rows.append((p.data_ptr(), g.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(), p.numel(),
                              struct.unpack('<I', struct.pack('<f', step_size))[0],
-                             struct.unpack('<I', struct.pack('<f', inv_sqrt_bc2))[0], 0))
+                             struct.unpack('<I', struct.pack('<f', inv_sqrt_bc2))[0], nblocks))
+                nblocks += (p.numel() + chunk - 1) // chunk     # (include/pgk.h: one block per PGK_ADAM_CHUNK elements)
                 keep.append(g)       # the gradient buffer must outlive the asynchronous launch
                 updated.append(p)
-                max_numel = max(max_numel, p.numel())
                 dev = p.device
             if not rows:
                 continue
@@ -88,7 +89,7 @@ class FusedAdam(torch.optim.Optimizer):
             table.copy_(host[:n], non_blocking=True)
             self._ring[self._slot][1] = torch.cuda.Event()
             self._ring[self._slot][1].record()
-            _lib.call('pgk_adam_multi', table.data_ptr(), n, max_numel, float(beta1), float(beta2),
+            _lib.call('pgk_adam_multi', table.data_ptr(), n, nblocks, float(beta1), float(beta2),
                       float(group['eps']))
             # the kernel writes through raw pointers: tell autograd (and every cache keyed on Tensor._version, e.g.
             # engine.ConvW's re-laid weights) that the parameters changed

@@ -57,6 +57,8 @@ def main():
     ap.add_argument('--batch', type=int, default=0)
     ap.add_argument('--top', type=int, default=40)
     ap.add_argument('--json', default='', help='also write the table to this file')
+    ap.add_argument('--others', action='store_true',
+                    help='second table: every other libpgk entry point by (name, small integer arguments)')
     args = ap.parse_args()
     cfg = dict(bench.CONFIGS[args.config])
     if args.batch:
@@ -100,9 +102,20 @@ def main():
     records = []
     real_call = pg._lib.call
 
+    others = []
+
     def timed_call(name, *a):
         if name not in ('pgk_conv', 'pgk_wgrad', 'pgk_conv_fp16'):
-            return real_call(name, *a)
+            if not args.others:
+                return real_call(name, *a)
+            # signature: the integer arguments that are sizes / flags (pointers and strides are huge or None)
+            sig = (name,) + tuple(v for v in a if isinstance(v, int) and not isinstance(v, bool) and 0 <= v < (1 << 16))
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = real_call(name, *a)
+            e.record()
+            others.append((sig, s, e))
+            return r
         sig, fl, by = signature(name, a)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
@@ -154,6 +167,17 @@ def main():
     print("(* = under 12 us per launch: the ~2-3 us gap between back-to-back launches is part of the figure;"
           " f_tens counts issued bf16 products against %.0f TF/s, f_hbm algorithmic bytes against %.0f GB/s)"
           % (peak_tf, peak_gb))
+    if args.others:
+        oa = collections.OrderedDict()
+        for sig, s_, e_ in others:
+            t = oa.setdefault(sig, [0, 0.0])
+            t[0] += 1
+            t[1] += s_.elapsed_time(e_)
+        orows = sorted(oa.items(), key=lambda kv: -kv[1][1])
+        print('other entry points: %.2f ms / iteration' % (sum(v[1] for v in oa.values()) / args.steps))
+        print('%-70s %6s %9s %9s' % ('entry point + small integer arguments (include/pgk.h order)', 'n/step', 'ms/step', 'us/launch'))
+        for sig, (cnt, ms) in orows[:args.top]:
+            print('%-70s %6.1f %9.3f %9.1f' % (' '.join(str(v) for v in sig), cnt / args.steps, ms / args.steps, 1e3 * ms / cnt))
     if args.json:
         with open(args.json, 'w') as f:
             json.dump({'config': args.config, 'step_ms': step_ms, 'rows': rows}, f, indent=1)
