@@ -145,9 +145,11 @@ __global__ void posbias_wgrad_kernel(Planes ua, int N, int H, int W, int Cout, c
     atomicAdd(dw + (((long long)co * cin_stride + ch) * 3 + ky) * 3 + kx, c * s);
 }
 
-// items per thread and pass in the 1x1 image kernels (1 = the round-1 loops; A/B builds: make EXTRA=-DPGK_RGB_UN=1)
+// items per thread and pass in the 1x1 image kernels.  Measured (c4, round 2): 4 items with the loads first is SLOWER
+// than 1 (from_rgb 126 -> 181 us, from_rgb_dgrad 77 -> 124: 100-127 registers halve the resident threads, and these
+// kernels are bound by instruction issue, not by bytes in flight).  A/B builds: make EXTRA=-DPGK_RGB_UN=4
 #ifndef PGK_RGB_UN
-#define PGK_RGB_UN 4
+#define PGK_RGB_UN 1
 #endif
 
 // ------------------------------------------------------------------------------------------
@@ -1163,6 +1165,215 @@ inline unsigned grid_cap(long long blocks) {
     return (unsigned)blocks;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// narrow one-plane layers (8 / 16 / 32 feature channels: the 256^2 ... 1024^2 levels)
+// ------------------------------------------------------------------------------------------
+// On these shapes the generic kernels above are bound by instruction issue, not by memory (c4, round 2: from_rgb at
+// 1024^2 2.8 TB/s, to_rgb 2.0, from_rgb_dgrad 1.7, pixelnorm_bwd 1.8 against 5+ for mask_mul / pool2): two integer
+// divisions, a scalar shared-memory weight read per multiply, run-time plane / layout branches -- ~140 instructions
+// per 16-byte store.  These flavours take one sample per blockIdx.y (no divisions; W is a power of two), read weights
+// as float4 broadcasts, know their channel count at compile time and keep loads packed until they are used.  Same
+// arithmetic, in the same order, as the generic kernels.
+
+template <int NCH>   // K = 8 * NCH feature channels
+__global__ void __launch_bounds__(256) rgb_expand_narrow_kernel(ExpandArgs a, int lw) {
+    pgk_pdl_enter();
+    constexpr int K = 8 * NCH;
+    __shared__ __align__(16) float wsm[MAXC * K + K];   // [c][k] weights, then the bias
+    for (int i = threadIdx.x; i < a.C * K; i += blockDim.x) {
+        const int c = i / K, k = i - c * K;
+        wsm[i] = a.wscale * (a.dmul ? __ldg(a.dmul) : 1.f) * a.w[(long long)c * a.sc + (long long)k * a.sk];
+    }
+    for (int i = threadIdx.x; i < K; i += blockDim.x) wsm[MAXC * K + i] = a.bias ? __ldg(a.bias + i) : 0.f;
+    __syncthreads();
+    const unsigned HW = (unsigned)a.H * a.W, W = (unsigned)a.W;
+    const long long n = blockIdx.y;
+    const float* img = a.img + n * a.C * (a.pool ? 4ll * HW : (long long)HW);
+    bf16* out = a.out.p + n * HW * K;
+    const bf16* mk = a.mask.p + n * HW * K;
+    for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < HW; r += gridDim.x * blockDim.x) {
+        float iv[MAXC];
+        if (!a.pool) {
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c)
+                if (c < a.C) iv[c] = __ldg(img + (long long)c * HW + r);
+        } else {
+            const unsigned y = r >> lw, x = r & (W - 1), W2 = 2 * W;
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c)
+                if (c < a.C) {
+                    const float* p = img + ((long long)c * (2 * a.H) + 2 * y) * W2 + 2 * x;
+                    iv[c] = (__ldg(p) + __ldg(p + 1)) + (__ldg(p + W2) + __ldg(p + W2 + 1));
+                }
+        }
+        uint4 mq[NCH];
+        if (a.has_mask) {
+#pragma unroll
+            for (int h = 0; h < NCH; ++h) mq[h] = __ldg(reinterpret_cast<const uint4*>(mk + (long long)r * K + 8 * h));
+        }
+#pragma unroll
+        for (int h = 0; h < NCH; ++h) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 0.f;
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c)
+                if (c < a.C) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(wsm + c * K + 8 * h);
+                    const float4 w1 = *reinterpret_cast<const float4*>(wsm + c * K + 8 * h + 4);
+                    v[0] = fmaf(iv[c], w0.x, v[0]), v[1] = fmaf(iv[c], w0.y, v[1]), v[2] = fmaf(iv[c], w0.z, v[2]);
+                    v[3] = fmaf(iv[c], w0.w, v[3]), v[4] = fmaf(iv[c], w1.x, v[4]), v[5] = fmaf(iv[c], w1.y, v[5]);
+                    v[6] = fmaf(iv[c], w1.z, v[6]), v[7] = fmaf(iv[c], w1.w, v[7]);
+                }
+            if (a.bias) {
+                const float4 b0 = *reinterpret_cast<const float4*>(wsm + MAXC * K + 8 * h);
+                const float4 b1 = *reinterpret_cast<const float4*>(wsm + MAXC * K + 8 * h + 4);
+                v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w, v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
+            }
+            if (a.act) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = lrelu(v[j]);
+            }
+            if (a.has_mask) {
+                float m[8];
+                unpack8(mq[h], m);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] *= lrelu_grad(m[j]);
+            }
+            uint4 q;
+            q.x = pack2(v[0], v[1]), q.y = pack2(v[2], v[3]), q.z = pack2(v[4], v[5]), q.w = pack2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(out + (long long)r * K + 8 * h) = q;
+        }
+    }
+}
+
+// sources of NCH0 (+ optionally NCH1, at half resolution when its `ups` is set) chunks of 8 channels -> image
+template <int NCH0, int NCH1>
+__global__ void __launch_bounds__(256) rgb_reduce_narrow_kernel(ReduceArgs a, int lw) {
+    pgk_pdl_enter();
+    constexpr int K0 = 8 * NCH0, K1 = 8 * NCH1;
+    __shared__ __align__(16) float wsm[MAXC * (K0 + K1) + MAXC];   // source 0: [c][K0], source 1: [c][K1], then bsum
+    constexpr int off1 = MAXC * K0, offb = MAXC * (K0 + K1);
+    float sa[2];
+    for (int s = 0; s < 2; ++s) sa[s] = a.s[s].a * ((s < a.nsrc && a.s[s].da) ? __ldg(a.s[s].da) : 1.f);
+    for (int s = 0; s < (NCH1 ? 2 : 1); ++s) {
+        const int K = s ? K1 : K0;
+        float* dst = wsm + (s ? off1 : 0);
+        for (int i = threadIdx.x; i < a.C * K; i += blockDim.x) {
+            const int c = i / K, k = i - c * K;
+            dst[i] = sa[s] * a.s[s].wscale * a.s[s].w[(long long)c * a.s[s].sc + (long long)k * a.s[s].sk];
+        }
+    }
+    if (threadIdx.x < MAXC) {
+        float b = 0.f;
+        if ((int)threadIdx.x < a.C)
+            for (int s = 0; s < a.nsrc; ++s)
+                if (a.s[s].bias) b = fmaf(sa[s], a.s[s].bias[threadIdx.x], b);
+        wsm[offb + threadIdx.x] = b;
+    }
+    __syncthreads();
+    const unsigned HW = (unsigned)a.H * a.W, W = (unsigned)a.W;
+    const long long n = blockIdx.y;
+    const int u0 = a.s[0].ups, u1 = NCH1 ? a.s[1].ups : 0;
+    const bf16* t0 = a.s[0].t.p + n * (long long)(HW >> (2 * u0)) * K0;
+    const bf16* t1 = NCH1 ? a.s[1].t.p + n * (long long)(HW >> (2 * u1)) * K1 : nullptr;
+    float* img = a.img + n * a.C * (long long)HW;
+    for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < HW; r += gridDim.x * blockDim.x) {
+        const unsigned y = r >> lw, x = r & (W - 1);
+        uint4 q0[NCH0], q1[NCH1 ? NCH1 : 1];
+        {
+            const long long b0 = ((long long)(y >> u0) * (W >> u0) + (x >> u0)) * K0;
+#pragma unroll
+            for (int h = 0; h < NCH0; ++h) q0[h] = __ldg(reinterpret_cast<const uint4*>(t0 + b0 + 8 * h));
+        }
+        if (NCH1) {
+            const long long b1 = ((long long)(y >> u1) * (W >> u1) + (x >> u1)) * K1;
+#pragma unroll
+            for (int h = 0; h < NCH1; ++h) q1[h] = __ldg(reinterpret_cast<const uint4*>(t1 + b1 + 8 * h));
+        }
+        float old[MAXC];
+        if (a.accumulate) {
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c)
+                if (c < a.C) old[c] = img[(long long)c * HW + r];
+        }
+        float acc[MAXC];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) acc[c] = wsm[offb + c];
+        auto add = [&](const uint4& q, const float* wm, int K, int h) {
+            float g[8];
+            unpack8(q, g);
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c)
+                if (c < a.C) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(wm + c * K + h * 8);
+                    const float4 w1 = *reinterpret_cast<const float4*>(wm + c * K + h * 8 + 4);
+                    float t = acc[c];
+                    t = fmaf(g[0], w0.x, t), t = fmaf(g[1], w0.y, t), t = fmaf(g[2], w0.z, t), t = fmaf(g[3], w0.w, t);
+                    t = fmaf(g[4], w1.x, t), t = fmaf(g[5], w1.y, t), t = fmaf(g[6], w1.z, t), t = fmaf(g[7], w1.w, t);
+                    acc[c] = t;
+                }
+        };
+#pragma unroll
+        for (int h = 0; h < NCH0; ++h) add(q0[h], wsm, K0, h);
+        if (NCH1) {
+#pragma unroll
+            for (int h = 0; h < NCH1; ++h) add(q1[h], wsm + off1, K1, h);
+        }
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c)
+            if (c < a.C) img[(long long)c * HW + r] = a.accumulate ? old[c] + acc[c] : acc[c];
+    }
+}
+
+// one thread per pixel, NCH chunks of 8 channels (C = 8 * NCH <= 32)
+template <int NCH>
+__global__ void __launch_bounds__(256) pixelnorm_bwd_narrow_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y,
+                                                                   const float* __restrict__ r, unsigned npix,
+                                                                   bf16* __restrict__ da) {
+    pgk_pdl_enter();
+    constexpr int C = 8 * NCH;
+    for (unsigned pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
+        uint4 gq[NCH], vq[NCH];
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+            gq[i] = __ldg(reinterpret_cast<const uint4*>(dy + (long long)pix * C + 8 * i));
+            vq[i] = __ldg(reinterpret_cast<const uint4*>(y + (long long)pix * C + 8 * i));
+        }
+        const float rs = __ldg(r + pix);
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+            float g[8], v[8];
+            unpack8(gq[i], g), unpack8(vq[i], v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dot = fmaf(g[j], v[j], dot);
+        }
+        const float mean = dot / (float)C;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+            float g[8], v[8], o[8];
+            unpack8(gq[i], g), unpack8(vq[i], v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = rs * (g[j] - v[j] * mean) * lrelu_grad(v[j]);
+            uint4 q;
+            q.x = pack2(o[0], o[1]), q.y = pack2(o[2], o[3]), q.z = pack2(o[4], o[5]), q.w = pack2(o[6], o[7]);
+            *reinterpret_cast<uint4*>(da + (long long)pix * C + 8 * i) = q;
+        }
+    }
+}
+
+// blocks along x for the one-sample-per-blockIdx.y kernels: enough to fill the machine 16 deep
+static unsigned narrow_gx(long long HW, int N) {
+    long long gx = (HW + 255) / 256, cap = (16ll * pgk_num_sms() + N - 1) / N;
+    if (gx > cap) gx = cap;
+    return (unsigned)(gx < 1 ? 1 : gx);
+}
+static int narrow_enabled() {   // (read per launch: tests switch it inside one process)
+    const char* e = getenv("PGK_NARROW");
+    return e ? atoi(e) != 0 : 1;
+}
 }  // namespace
 
 #define ST (cudaStream_t) stream
@@ -1212,6 +1423,15 @@ static int launch_expand(ExpandArgs& a, pgk_stream_t stream, const char* name) {
     size_t smem = sizeof(float) * a.C * a.K;
     PGK_REQUIRE(smem <= 48 * 1024, "%s: weight does not fit shared memory", name);
     long long total = (long long)a.N * a.H * a.W * (a.K >> 3);
+    const int lw = log2_exact(a.W);
+    if (narrow_enabled() && (a.K == 8 || a.K == 16) && a.out.P == 1 && lw >= 0 && (long long)a.H * a.W < (1ll << 30) &&
+        a.N <= 65535) {
+        const dim3 grid(narrow_gx((long long)a.H * a.W, a.N), (unsigned)a.N);
+        if (a.K == 8) pgk_launch(rgb_expand_narrow_kernel<1>, grid, 256, 0, ST, a, lw);
+        else pgk_launch(rgb_expand_narrow_kernel<2>, grid, 256, 0, ST, a, lw);
+        PGK_LAUNCH_CHECK(name);
+        return PGK_OK;
+    }
     if (total < (1ll << 31) - (1ll << 24))
         pgk_launch(rgb_expand_kernel<unsigned>, dim3(grid_cap((total + 255) / 256)), 256, smem, ST, a);
     else
@@ -1259,6 +1479,25 @@ static int launch_reduce(ReduceArgs& a, pgk_stream_t stream, const char* name) {
     // One thread per pixel for every width: the lanes-per-pixel kernel below spends its time in shuffles, conflicting
     // shared-memory weight reads and 8-byte image stores (measured 527 us on the 128-channel 64^2 level at batch 128,
     // 8x its HBM time); per-pixel threads read the weights as broadcasts and store full 128-byte lines.
+    {
+        const int lw = log2_exact(a.W), k0 = a.s[0].K, k1 = a.nsrc > 1 ? a.s[1].K : 0;
+        const bool p1 = a.s[0].t.P == 1 && (a.nsrc < 2 || a.s[1].t.P == 1);
+        if (narrow_enabled() && p1 && lw >= 0 && (long long)a.H * a.W < (1ll << 30) && a.N <= 65535 &&
+            (a.s[0].ups == 0 || (a.H % 2 == 0 && a.W % 2 == 0)) && (a.nsrc < 2 || (a.H % 2 == 0 && a.W % 2 == 0))) {
+            const dim3 grid(narrow_gx((long long)a.H * a.W, a.N), (unsigned)a.N);
+            bool done = true;
+            if (k0 == 8 && k1 == 0) pgk_launch(rgb_reduce_narrow_kernel<1, 0>, grid, 256, 0, ST, a, lw);
+            else if (k0 == 16 && k1 == 0) pgk_launch(rgb_reduce_narrow_kernel<2, 0>, grid, 256, 0, ST, a, lw);
+            else if (k0 == 32 && k1 == 0) pgk_launch(rgb_reduce_narrow_kernel<4, 0>, grid, 256, 0, ST, a, lw);
+            else if (k0 == 8 && k1 == 16) pgk_launch(rgb_reduce_narrow_kernel<1, 2>, grid, 256, 0, ST, a, lw);
+            else if (k0 == 16 && k1 == 32) pgk_launch(rgb_reduce_narrow_kernel<2, 4>, grid, 256, 0, ST, a, lw);
+            else done = false;
+            if (done) {
+                PGK_LAUNCH_CHECK(name);
+                return PGK_OK;
+            }
+        }
+    }
     if ((long long)a.N * a.H * a.W < (1ll << 31)) {
         const long long npix = (long long)a.N * a.H * a.W;
         pgk_launch(rgb_reduce_px_kernel, dim3(grid_cap((npix + 255) / 256)), 256, smem + sizeof(float) * MAXC, ST, a);
@@ -1383,6 +1622,15 @@ extern "C" int pgk_pixelnorm(const void* h, long long h_ps, int P, long long npi
 extern "C" int pgk_pixelnorm_bwd(const void* dy, long long dy_ps, const void* y, long long y_ps, const float* r, int P,
                                  long long npix, int C, void* da, long long da_ps, pgk_stream_t stream) {
     PGK_REQUIRE(C % 8 == 0 && C <= 1024, "pgk_pixelnorm_bwd: C must be a multiple of 8 and <= 1024");
+    if (narrow_enabled() && P == 1 && C <= 32 && (C == 8 || C == 16 || C == 32) && npix < (1ll << 31)) {
+        const dim3 grid(grid_cap((npix + 255) / 256));
+        const bf16 *d = (const bf16*)dy, *yy = (const bf16*)y;
+        if (C == 8) pgk_launch(pixelnorm_bwd_narrow_kernel<1>, grid, 256, 0, ST, d, yy, r, (unsigned)npix, (bf16*)da);
+        else if (C == 16) pgk_launch(pixelnorm_bwd_narrow_kernel<2>, grid, 256, 0, ST, d, yy, r, (unsigned)npix, (bf16*)da);
+        else pgk_launch(pixelnorm_bwd_narrow_kernel<4>, grid, 256, 0, ST, d, yy, r, (unsigned)npix, (bf16*)da);
+        PGK_LAUNCH_CHECK("pgk_pixelnorm_bwd");
+        return PGK_OK;
+    }
     int L = lanes_for(C >> 3);
     pgk_launch(pixelnorm_bwd_kernel, dim3(grid_cap((npix * L + 255) / 256)), 256, 0, ST, 
         make_planes(dy, dy_ps, P), make_planes(y, y_ps, P), r, npix, C, L, make_planes(da, da_ps, P));

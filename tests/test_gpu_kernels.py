@@ -248,3 +248,76 @@ def test_unprep_multi_is_unprep_grad_bit_for_bit():
     torch.cuda.synchronize()
     for spec, (_, ref, got) in zip(specs, pairs):
         assert torch.equal(ref, got), spec
+
+
+@pytest.mark.parametrize('K', [8, 16])
+@pytest.mark.parametrize('C', [1, 3])
+def test_narrow_image_kernels_are_the_generic_ones_bit_for_bit(K, C):
+    """The narrow one-plane flavours of the 1x1 image kernels and of the pixel-norm backward pass (csrc/pgk_elem.cu,
+    PGK_NARROW) against the generic kernels on the same inputs: same arithmetic in the same order, so equal bits."""
+    import torch
+    sys.path.insert(0, ROOT)
+    import pggan_b200 as pg
+    E = importlib.import_module('pggan-pytorch_b200.engine')
+    call = pg._lib.call
+    torch.manual_seed(K * 10 + C)
+    n, H, W = 3, 32, 64
+    dev = 'cuda'
+    img = torch.randn(n, C, H, W, device=dev)
+    img2 = torch.randn(n, C, 2 * H, 2 * W, device=dev)
+    w = torch.randn(K, C, 1, 1, device=dev)            # fromRGB layout [K][C]
+    wt = torch.randn(C, K, 1, 1, device=dev)           # toRGB layout [C][K]
+    wt2 = torch.randn(C, 2 * K, 1, 1, device=dev)
+    bias = torch.randn(K, device=dev)
+    bias_c, bias_c2 = torch.randn(C, device=dev), torch.randn(C, device=dev)
+    mask = E.PT.empty(n, H, W, K, 1, dev)
+    mask.t.normal_()
+    h = E.PT.empty(n, H, W, K, 1, dev)
+    h.t.normal_()
+    hlo = E.PT.empty(n, H // 2, W // 2, 2 * K, 1, dev)
+    hlo.t.normal_()
+    r = torch.rand(n * H * W, device=dev) + 0.5
+    dsc = torch.tensor([0.37, 0.63], device=dev)
+
+    def run():
+        outs = []
+        o = E.PT.empty(n, H, W, K, 1, dev)
+        call('pgk_from_rgb', img.data_ptr(), n, C, H, W, K, w.data_ptr(), 0.7, bias.data_ptr(), 1, None, 0, o.ptr, 1, o.ps)
+        outs.append(o.t.clone())
+        call('pgk_from_rgb', img.data_ptr(), n, C, H, W, K, w.data_ptr(), 0.7, None, 0, mask.ptr, mask.ps, o.ptr, 1, o.ps)
+        outs.append(o.t.clone())
+        call('pgk_to_rgb_dgrad', img.data_ptr(), n, C, H, W, K, wt.data_ptr(), 0.9, 0.3, 0, o.ptr, 1, o.ps, dsc.data_ptr())
+        outs.append(o.t.clone())
+        call('pgk_to_rgb_dgrad', img2.data_ptr(), n, C, H, W, K, wt.data_ptr(), 0.9, 0.3, 1, o.ptr, 1, o.ps, None)
+        outs.append(o.t.clone())
+        im = torch.full((n, C, H, W), 3.0, device=dev)
+        call('pgk_to_rgb', h.ptr, 1, h.ps, n, H, W, K, wt.data_ptr(), 0.8, bias_c.data_ptr(), 0.6, None, 0, 0, None, 0.0,
+             None, 0.0, C, im.data_ptr(), None, None)
+        outs.append(im.clone())
+        call('pgk_to_rgb', h.ptr, 1, h.ps, n, H, W, K, wt.data_ptr(), 0.8, bias_c.data_ptr(), 0.6, hlo.ptr, hlo.ps, 2 * K,
+             wt2.data_ptr(), 0.5, bias_c2.data_ptr(), 0.4, C, im.data_ptr(), dsc[:1].data_ptr(), dsc[1:].data_ptr())
+        outs.append(im.clone())
+        call('pgk_from_rgb_dgrad', h.ptr, 1, h.ps, n, C, H, W, K, w.data_ptr(), 0.7, 1.3, 0, 0, im.data_ptr())
+        outs.append(im.clone())
+        im2 = torch.full((n, C, 2 * H, 2 * W), 1.0, device=dev)
+        call('pgk_from_rgb_dgrad', h.ptr, 1, h.ps, n, C, 2 * H, 2 * W, K, w.data_ptr(), 0.7, 0.25, 1, 1, im2.data_ptr())
+        outs.append(im2.clone())
+        call('pgk_pixelnorm_bwd', h.ptr, h.ps, mask.ptr, mask.ps, r.data_ptr(), 1, n * H * W, K, o.ptr, o.ps)
+        outs.append(o.t.clone())
+        torch.cuda.synchronize()
+        return outs
+
+    old = os.environ.get('PGK_NARROW')
+    try:
+        os.environ['PGK_NARROW'] = '0'
+        ref = run()
+        os.environ['PGK_NARROW'] = '1'
+        got = run()
+    finally:
+        if old is None:
+            os.environ.pop('PGK_NARROW', None)
+        else:
+            os.environ['PGK_NARROW'] = old
+    for i, (a, b) in enumerate(zip(ref, got)):
+        a, b = (a.view(torch.int16), b.view(torch.int16)) if a.dtype == torch.bfloat16 else (a, b)
+        assert torch.equal(a, b), 'output %d differs' % i
