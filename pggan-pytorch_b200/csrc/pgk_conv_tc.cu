@@ -627,26 +627,75 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         fence_after();
         const int K = a.KS * a.KS * a.Cin;
         const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        // A thread owns one accumulator row (lane = row), i.e. one row of dW: written directly, a warp's 16-byte access
+        // touches 32 rows -- 32 partial sectors per instruction, and this flush was the larger part of the small
+        // launches (4 x 32^2 pixels, 512 -> 256: 6 us of MMAs in a 144 us launch).  The stage ring is idle by now: each
+        // warp turns its 32 rows x 32 columns through it (row pitch 36 floats: both directions conflict free) so that
+        // every global access covers 4 rows x 128 contiguous bytes.
+        constexpr uint32_t kPitch = 144u;
+        const bool staged = (uint32_t)a.stages * stage_bytes >= 4u * 32u * kPitch;
+        const uint32_t fl = sbase + (uint32_t)warp * (32u * kPitch);
         for (int sl = 0; sl < S; ++sl) {
-            const int k = (slab0 + sl) * 128 + warp * 32 + lane;
-            float* drow = a.dwp + (long long)k * a.Cout + co0;
-            for (int c = 0; c < a.NT; c += 16) {
-                float v[16];
+            const int kw = (slab0 + sl) * 128 + warp * 32;     // first row of this warp
+            for (int c = 0; c < a.NT; c += 32) {
+                float v[32];
                 tmem_ld16(trow + sl * a.NT + c, v);
-                if (k < K) {
-                    if (gridDim.z == 1) {
-                        // the pixel range is not split: this thread is the only writer of its row slice, so the
-                        // accumulation into dwp needs no atomics at all
+                tmem_ld16(trow + sl * a.NT + c + 16, v + 16);
+                if (staged) {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            float4* p4 = reinterpret_cast<float4*>(drow + c + j);
-                            float4 o = *p4;
-                            o.x += v[j], o.y += v[j + 1], o.z += v[j + 2], o.w += v[j + 3];
-                            *p4 = o;
+                    for (int j = 0; j < 8; ++j)
+                        st_shared_v4(fl + (uint32_t)lane * kPitch + 16u * j,
+                                     make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                                __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
+                    __syncwarp();
+                    const int q = lane & 7, r0 = lane >> 3;
+                    float* dcol = a.dwp + co0 + c + 4 * q;
+                    if (gridDim.z == 1) {
+                        // the pixel range is not split: this CTA is the only writer of its tile, no atomics
+                        float4 o[8];
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int k = kw + it * 4 + r0;
+                            if (k < K) o[it] = *reinterpret_cast<const float4*>(dcol + (long long)k * a.Cout);
+                        }
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int k = kw + it * 4 + r0;
+                            if (k < K) {
+                                const uint4 x = ld_shared_v4(fl + (uint32_t)(it * 4 + r0) * kPitch + 16u * q);
+                                o[it].x += __uint_as_float(x.x), o[it].y += __uint_as_float(x.y);
+                                o[it].z += __uint_as_float(x.z), o[it].w += __uint_as_float(x.w);
+                                *reinterpret_cast<float4*>(dcol + (long long)k * a.Cout) = o[it];
+                            }
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) red_add_v4(drow + c + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        for (int it = 0; it < 8; ++it) {
+                            const int k = kw + it * 4 + r0;
+                            if (k < K) {
+                                const uint4 x = ld_shared_v4(fl + (uint32_t)(it * 4 + r0) * kPitch + 16u * q);
+                                red_add_v4(dcol + (long long)k * a.Cout, __uint_as_float(x.x), __uint_as_float(x.y),
+                                           __uint_as_float(x.z), __uint_as_float(x.w));
+                            }
+                        }
+                    }
+                    __syncwarp();
+                } else {
+                    const int k = kw + lane;
+                    float* drow = a.dwp + (long long)k * a.Cout + co0 + c;
+                    if (k < K) {
+                        if (gridDim.z == 1) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                float4* p4 = reinterpret_cast<float4*>(drow + j);
+                                float4 o = *p4;
+                                o.x += v[j], o.y += v[j + 1], o.z += v[j + 2], o.w += v[j + 3];
+                                *p4 = o;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) red_add_v4(drow + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        }
                     }
                 }
             }
@@ -887,36 +936,110 @@ extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long l
         if (a.xoff[i] > xmax) xmax = a.xoff[i];
         if (a.goff[i] > gmax) gmax = a.goff[i];
     }
-    a.NT = Cout < 256 ? Cout : 256;
     a.RG = KS * KS * Cin / 64;
     const int slabs = (a.RG + 1) / 2;
-    const int smax = 512 / a.NT;
-    const int sgroups = (slabs + smax - 1) / smax;
-    a.S = (slabs + sgroups - 1) / sgroups;
     const int box_bytes = a.PXS * 128;
+    a.tiles_per_group = (long long)group_n * H * W / a.PXS;
+    a.tiles_total = a.tiles_per_group * ngroups;
+    const int sms = pgk_num_sms();
+    const long long max_split = (a.tiles_total + 15) / 16;
+    // ---- plan: channel tile NT, slabs per CTA S, pixel split.  The round-1 rule (widest tile, S * NT = 512 columns,
+    // pixel range split to one or two waves) is right when the reduction is long; with few pixels (the 4x4 ... 32x32
+    // levels at batch 4) its CTAs run a few microseconds of MMAs and then push `split` copies of dW through atomics,
+    // which was the larger part of those launches.  A cost model in cycles (MMA issue at max(130, 0.66 NT) per
+    // MN-major instruction, operand boxes at ~48 bytes / cycle per SM, flush: ~8 floats / cycle per SM direct, ~96 / cycle
+    // chip-wide through atomics) ranks the alternatives; it replaces the round-1 plan only when it predicts at
+    // least 25 % less, so the long-reduction shapes (c2, c3) keep the plans they were measured with.
+    struct WPlan {
+        int NT, S, sgroups, occ;
+        long long split;
+        double cost;
+    };
+    const double prods = Pr * (Pr + 1) / 2;
+    auto occ_of = [&](int NT, int S) {
+        const int stage_bytes = Pr * (2 * S + NT / 64) * box_bytes;
+        int occ = 512 / (int)tmem_cols(S * NT);
+        if (occ > 4) occ = 4;
+        while (occ > 1 && (kSmemLimit / occ - 2048) / stage_bytes < 3) --occ;
+        return occ;
+    };
+    auto eval = [&](int NT, int S, long long split) {
+        WPlan pl;
+        pl.NT = NT, pl.S = S, pl.split = split;
+        pl.sgroups = (slabs + S - 1) / S;
+        pl.occ = occ_of(NT, S);
+        const long long ctas = (long long)pl.sgroups * (Cout / NT) * split;
+        const long long per_cta = (a.tiles_total + split - 1) / split;
+        const double mma = (double)per_cta * S * 2 * prods * (0.66 * NT > 130.0 ? 0.66 * NT : 130.0);
+        const double load = (double)per_cta * (2 * S + NT / 64) * Pr * box_bytes / 48.0;
+        const long long resident = (long long)pl.occ * sms;
+        const long long waves = (ctas + resident - 1) / resident;
+        long long per_sm = (ctas + sms - 1) / sms;
+        if (per_sm > pl.occ) per_sm = pl.occ;
+        const double body = (mma > load ? mma : load) * per_sm + 4000.0;
+        const double flush_cta = (double)S * 128 * NT / 8.0 * per_sm;
+        const double flush_chip = split > 1 ? (double)ctas * S * 128 * NT / 96.0 : 0.0;
+        pl.cost = waves * (body + flush_cta) + flush_chip;
+        return pl;
+    };
+    WPlan legacy;
+    {
+        const int NT = Cout < 256 ? Cout : 256;
+        const int smax = 512 / NT;
+        const int sgroups = (slabs + smax - 1) / smax;
+        const int S = (slabs + sgroups - 1) / sgroups;
+        // split the pixel range so that the grid is (just under) one or two full waves of the SMs
+        const int base = sgroups * (Cout / NT);
+        long long split = 1;
+        double best = -1.0;
+        for (int w = 1; w <= 2; ++w) {
+            long long sp = (long long)w * sms / base;
+            if (sp < 1) sp = 1;
+            if (sp > max_split) sp = max_split;
+            const long long ctas = sp * base;
+            const double util = (double)ctas / (double)(((ctas + sms - 1) / sms) * sms);
+            if (util > best + 0.02) best = util, split = sp;
+        }
+        legacy = eval(NT, S, split);
+    }
+    WPlan plan = legacy;
+    {
+        static int model = -1;
+        if (model < 0) {
+            const char* e = getenv("PGK_WGRAD_PLAN");
+            model = e ? atoi(e) != 0 : 1;
+        }
+        WPlan bestp = legacy;
+        for (int NT = 256; model && NT >= 64; NT >>= 1) {
+            if (NT > Cout || Cout % NT) continue;
+            for (int S = 512 / NT; S >= 1; --S) {
+                if (S > slabs) continue;
+                const int sgroups = (slabs + S - 1) / S;
+                if ((slabs + sgroups - 1) / sgroups != S) continue;   // (the same grouping with a smaller S exists)
+                const long long base = (long long)sgroups * (Cout / NT), resident = (long long)occ_of(NT, S) * sms;
+                for (int w = 0; w <= 4; ++w) {
+                    long long sp = w == 0 ? 1 : (long long)w * resident / base;
+                    if (sp < 1) sp = 1;
+                    if (sp > max_split) sp = max_split;
+                    const WPlan c = eval(NT, S, sp);
+                    if (c.cost < bestp.cost) bestp = c;
+                }
+            }
+        }
+        if (bestp.cost < 0.75 * legacy.cost) plan = bestp;
+    }
+    a.NT = plan.NT, a.S = plan.S;
+    const int sgroups = plan.sgroups;
+    long long split = plan.split;
     const int stage_bytes = Pr * (2 * a.S + a.NT / 64) * box_bytes;
-    int ctas = 512 / (int)tmem_cols(a.S * a.NT);
-    if (ctas > 4) ctas = 4;
-    while (ctas > 1 && (kSmemLimit / ctas - 2048) / stage_bytes < 3) --ctas;
+    const int ctas = plan.occ;
     a.stages = (kSmemLimit / ctas - 2048) / stage_bytes;
     if (a.stages > 8) a.stages = 8;
     PGK_REQUIRE(a.stages >= 1, "pgk_wgrad_tc: stage does not fit in shared memory");
-    a.tiles_per_group = (long long)group_n * H * W / a.PXS;
-    a.tiles_total = a.tiles_per_group * ngroups;
-    // split the pixel range so that the grid is (just under) one or two full waves of the SMs
-    const int base = sgroups * (Cout / a.NT);
-    const int sms = pgk_num_sms();
-    long long max_split = (a.tiles_total + 15) / 16;
-    long long split = 1;
-    double best = -1.0;
-    for (int w = 1; w <= 2; ++w) {
-        long long sp = (long long)w * sms / base;
-        if (sp < 1) sp = 1;
-        if (sp > max_split) sp = max_split;
-        const long long ctas = sp * base;
-        const double util = (double)ctas / (double)(((ctas + sms - 1) / sms) * sms);
-        if (util > best + 0.02) best = util, split = sp;
-    }
+    if (getenv("PGK_WGRAD_PLAN_DEBUG"))
+        fprintf(stderr, "pgk_wgrad_tc %dx%d n %d %d->%d Pr %d: NT %d S %d split %lld (model %.0f kcycles; round-1 plan NT %d S %d split %lld %.0f)\n",
+                H, W, ngroups * group_n, Cin, Cout, Pr, plan.NT, plan.S, plan.split, plan.cost / 1e3, legacy.NT, legacy.S,
+                legacy.split, legacy.cost / 1e3);
     if (split > 65535) split = 65535;
     a.tiles_per_cta = (a.tiles_total + split - 1) / split;
     split = (a.tiles_total + a.tiles_per_cta - 1) / a.tiles_per_cta;

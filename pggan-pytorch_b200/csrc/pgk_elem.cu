@@ -494,7 +494,10 @@ struct RgbWgradArgs {
     long long R, r_per_cta;
 };
 
-__global__ void __launch_bounds__(256) rgb_wgrad_kernel(RgbWgradArgs a) {
+// NARROW: one-plane tensors, power-of-two H * W and W, fewer than 2^31 pixels -- shifts instead of divisions, packed
+// loads, and the next pixel's loads issued before the current one is accumulated (same sums in the same order)
+template <bool NARROW>
+__global__ void __launch_bounds__(256, NARROW ? 3 : 1) rgb_wgrad_kernel(RgbWgradArgs a, int lhw, int lw) {
     pgk_pdl_enter();
     const float dm = a.dmul ? __ldg(a.dmul) : 1.f;
     const float a_scale = a.scale * dm, a_scale_b = a.scale_b * dm;
@@ -517,7 +520,54 @@ __global__ void __launch_bounds__(256) rgb_wgrad_kernel(RgbWgradArgs a) {
     if (t < MAXC) isum[t] = 0.f;
     long long r_begin = (long long)blockIdx.x * a.r_per_cta, r_end = r_begin + a.r_per_cta;
     if (r_end > a.R) r_end = a.R;
-    if (pl < lanes) {
+    if (NARROW) {
+        if (pl < lanes) {
+            const unsigned W = (unsigned)a.W, W2 = 2 * W, HWu = (unsigned)HW;
+            float iv[MAXC], ivn[MAXC];
+            uint4 q = make_uint4(0, 0, 0, 0), qn = make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) iv[c] = ivn[c] = 0.f;
+            auto load = [&](unsigned rr, float* v, uint4& qq) {
+                const unsigned n = rr >> lhw, r = rr & (HWu - 1);
+                if (!a.pool) {
+#pragma unroll
+                    for (int c = 0; c < MAXC; ++c)
+                        if (c < a.C) v[c] = __ldg(a.img + ((long long)(a.img_n0 + n) * a.C + c) * HW + r);
+                } else {
+                    const unsigned y = r >> lw, x = r & (W - 1);
+#pragma unroll
+                    for (int c = 0; c < MAXC; ++c)
+                        if (c < a.C) {
+                            const float* p = a.img + (((long long)(a.img_n0 + n) * a.C + c) * (a.H * 2) + 2 * y) * W2 + 2 * x;
+                            v[c] = (__ldg(p) + __ldg(p + 1)) + (__ldg(p + W2) + __ldg(p + W2 + 1));
+                        }
+                }
+                qq = __ldg(reinterpret_cast<const uint4*>(a.t.p + ((long long)(a.t_n0 + n) * HW + r) * a.K + ch * 8));
+            };
+            unsigned rr = (unsigned)r_begin + pl;
+            const unsigned rend = (unsigned)r_end;
+            if (rr < rend) load(rr, iv, q);
+            for (; rr < rend; rr += lanes) {
+                const unsigned nx = rr + lanes;
+                if (nx < rend) load(nx, ivn, qn);
+                float f[8];
+                unpack8(q, f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    cs[j] += f[j];
+#pragma unroll
+                    for (int c = 0; c < MAXC; ++c) acc[c][j] = fmaf(iv[c], f[j], acc[c][j]);
+                }
+                if (ch == 0) {
+#pragma unroll
+                    for (int c = 0; c < MAXC; ++c) is[c] += iv[c];
+                }
+                q = qn;
+#pragma unroll
+                for (int c = 0; c < MAXC; ++c) iv[c] = ivn[c];
+            }
+        }
+    } else if (pl < lanes) {
         // four pixels per pass, loads first (same pixels, same order per thread as one at a time: identical sums)
         constexpr int UN = PGK_RGB_UN;
         for (long long rr0 = r_begin + pl; rr0 < r_end; rr0 += (long long)UN * lanes) {
@@ -1549,11 +1599,14 @@ extern "C" int pgk_rgb_wgrad(const float* img, int img_n0, const void* t, int P,
     a.dw = dw, a.sa = sa, a.sk = sk, a.colsum = d_colsum, a.imgsum = d_imgsum;
     a.R = (long long)N * H * W;
     long long ctas = (a.R + 255) / 256;
-    long long cap = 4ll * pgk_num_sms();
+    const int lhw = log2_exact(H * W), lw = log2_exact(W);
+    const bool narrow = narrow_enabled() && P == 1 && K <= 32 && lhw >= 0 && lw >= 0 && a.R < (1ll << 31);
+    long long cap = (narrow ? 3ll : 4ll) * pgk_num_sms();
     if (ctas > cap) ctas = cap;
     if (ctas < 1) ctas = 1;
     a.r_per_cta = (a.R + ctas - 1) / ctas;
-    pgk_launch(rgb_wgrad_kernel, dim3((unsigned)ctas), 256, 0, ST, a);
+    if (narrow) pgk_launch(rgb_wgrad_kernel<true>, dim3((unsigned)ctas), 256, 0, ST, a, lhw, lw);
+    else pgk_launch(rgb_wgrad_kernel<false>, dim3((unsigned)ctas), 256, 0, ST, a, lhw, lw);
     PGK_LAUNCH_CHECK("pgk_rgb_wgrad");
     return PGK_OK;
 }

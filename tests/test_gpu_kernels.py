@@ -304,6 +304,12 @@ def test_narrow_image_kernels_are_the_generic_ones_bit_for_bit(K, C):
         outs.append(im2.clone())
         call('pgk_pixelnorm_bwd', h.ptr, h.ps, mask.ptr, mask.ps, r.data_ptr(), 1, n * H * W, K, o.ptr, o.ps)
         outs.append(o.t.clone())
+        # weight / bias gradients of the 1x1 convs: atomics across CTAs, compared with a tolerance below
+        for pool, im_ in ((0, img), (1, img2)):
+            dw, cs, isum = torch.zeros(C, K, device=dev), torch.zeros(K, device=dev), torch.zeros(C, device=dev)
+            call('pgk_rgb_wgrad', im_.data_ptr(), 1, h.ptr, 1, h.ps, 0, n - 1, C, H, W, K, pool, 0.7, 0.9, dw.data_ptr(), K, 1,
+                 cs.data_ptr(), isum.data_ptr(), dsc[:1].data_ptr())
+            outs.append(torch.cat([dw.flatten(), cs, isum]))
         torch.cuda.synchronize()
         return outs
 
@@ -319,5 +325,8 @@ def test_narrow_image_kernels_are_the_generic_ones_bit_for_bit(K, C):
         else:
             os.environ['PGK_NARROW'] = old
     for i, (a, b) in enumerate(zip(ref, got)):
+        if i >= len(ref) - 2:
+            assert torch.allclose(a, b, rtol=2e-5, atol=2e-5 * float(a.abs().max())), 'gradient %d differs' % i
+            continue
         a, b = (a.view(torch.int16), b.view(torch.int16)) if a.dtype == torch.bfloat16 else (a, b)
         assert torch.equal(a, b), 'output %d differs' % i
