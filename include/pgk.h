@@ -190,12 +190,16 @@ int pgk_wgrad(const void* x, long long x_ps, const void* g, long long g_ps, int 
 int pgk_bias_grad(const void* g, long long g_ps, int P, int HW, int Cout, int ngroups, int group_n, const int* goff,
                   float scale, float* db, int accumulate, pgk_stream_t stream);
 
+/* out16 / y16 (optional, NULL = off) of pgk_from_rgb, pgk_pool2, pgk_mask_mul and pgk_pixelnorm: a second output, the
+ * two IEEE-half planes (out16_ps elements apart) that pgk_cvt_fp16x2 would derive from the bf16 planes just stored --
+ * bit for bit -- for the wide forward conv that reads this tensor next (pgk_conv_fp16); saves the conversion pass. */
+
 /* ---- 1x1 convs against the image surface ------------------------------------------------
  * fromRGB (network.py:145,160): out[n,y,x,co] = E(sum_c c*w[co][c] * img[n,c,y,x]); E as in pgk_conv
  * (bias, act, mask_ref).  w is the PyTorch (Cout, C, 1, 1) tensor, scale c applied here. */
 int pgk_from_rgb(const float* img, int N, int C, int H, int W, int Cout, const float* w, float c, const float* bias,
-                 int act, const void* mask_ref, long long mask_ps, void* out, int P, long long out_ps,
-                 pgk_stream_t stream);
+                 int act, const void* mask_ref, long long mask_ps, void* out, int P, long long out_ps, void* out16,
+                 long long out16_ps, pgk_stream_t stream);
 /* data gradient of fromRGB to the image: dimg[n,c,y,x] (+)= scale * sum_co c*w[co][c] * g[n,y,x,co];
  * ups = 1: g has H/2 x W/2 and is read at (y/2, x/2) (the avg-pooled low-res branch, network.py:231-232). */
 int pgk_from_rgb_dgrad(const void* g, int P, long long g_ps, int N, int C, int H, int W, int Cout, const float* w,
@@ -229,17 +233,17 @@ int pgk_rgb_wgrad(const float* img, int img_n0, const void* t, int P, long long 
  * avg = 0: sum (backward of the nearest upsample).  src is N x 2H x 2W x C, out/other N x H x W x C. */
 int pgk_pool2(const void* src, long long src_ps, int P, int N, int H, int W, int C, int avg, float a,
               const void* other, long long other_ps, float b, void* out, long long out_ps, const float* d_a,
-              const float* d_b, pgk_stream_t stream);
+              const float* d_b, void* out16, long long out16_ps, pgk_stream_t stream);
 /* out[n,y,x,c] = scale * src[n, y>>ups, x>>ups, c] * lrelu'(ref[n,y,x,c]) (ref optional) */
 int pgk_mask_mul(const void* src, long long src_ps, int P, int N, int H, int W, int C, int ups, float scale,
-                 const void* ref, long long ref_ps, void* out, long long out_ps, const float* d_scale,
-                 pgk_stream_t stream);
+                 const void* ref, long long ref_ps, void* out, long long out_ps, const float* d_scale, void* out16,
+                 long long out16_ps, pgk_stream_t stream);
 /* out = a*x + b*y (y optional) on planes with `count` elements per plane */
 int pgk_axpby(const void* x, long long x_ps, float a, const void* y, long long y_ps, float b, int P, long long count,
               void* out, long long out_ps, pgk_stream_t stream);
 /* pixel norm (network.py:37-40): y = h * r, r = rsqrt(mean_c(h^2) + 1e-8); in place allowed; r (fp32 per pixel) stored. */
 int pgk_pixelnorm(const void* h, long long h_ps, int P, long long npix, int C, void* y, long long y_ps, float* r,
-                  pgk_stream_t stream);
+                  void* y16, long long y16_ps, pgk_stream_t stream);
 /* backward of LeakyReLU -> pixel norm: da = r * (dy - y * mean_c(dy*y)) * lrelu'(y)  */
 int pgk_pixelnorm_bwd(const void* dy, long long dy_ps, const void* y, long long y_ps, const float* r, int P,
                       long long npix, int C, void* da, long long da_ps, pgk_stream_t stream);

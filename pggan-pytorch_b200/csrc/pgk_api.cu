@@ -152,7 +152,7 @@ extern "C" int pgk_conv(const void* x, int P, int Pr, long long x_ps, int N, int
     }
     if (rc || !pn_r || pn_done) return rc;
     // kernels whose tile does not hold every channel of a pixel: the pixel norm as a second pass, in place
-    return pgk_pixelnorm(out, out_ps, P, (long long)N * H * W, Cout, out, out_ps, pn_r, stream);
+    return pgk_pixelnorm(out, out_ps, P, (long long)N * H * W, Cout, out, out_ps, pn_r, nullptr, 0, stream);
 }
 
 // forward convolution on IEEE-half operand planes (see include/pgk.h): the wide tensor-core kernel with fp16 A and B

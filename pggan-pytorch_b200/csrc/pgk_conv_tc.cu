@@ -947,9 +947,11 @@ extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long l
     // pixel range split to one or two waves) is right when the reduction is long; with few pixels (the 4x4 ... 32x32
     // levels at batch 4) its CTAs run a few microseconds of MMAs and then push `split` copies of dW through atomics,
     // which was the larger part of those launches.  A cost model in cycles (MMA issue at max(130, 0.66 NT) per
-    // MN-major instruction, operand boxes at ~48 bytes / cycle per SM, flush: ~8 floats / cycle per SM direct, ~96 / cycle
+    // MN-major instruction, operand boxes at ~20 bytes / cycle per SM, flush: ~8 floats / cycle per SM direct, ~96 / cycle
     // chip-wide through atomics) ranks the alternatives; it replaces the round-1 plan only when it predicts at
-    // least 25 % less, so the long-reduction shapes (c2, c3) keep the plans they were measured with.
+    // least 25 % less.  OPT-IN (PGK_WGRAD_PLAN=1): its first calibration (48 bytes / cycle) chose un-split plans that
+    // measured slower (c4 wgrad_tc 0.66 -> 0.87 ms per iteration, c3 3.14 -> 3.36); the staged flush below is what
+    // helped the short reductions.
     struct WPlan {
         int NT, S, sgroups, occ;
         long long split;
@@ -971,7 +973,7 @@ extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long l
         const long long ctas = (long long)pl.sgroups * (Cout / NT) * split;
         const long long per_cta = (a.tiles_total + split - 1) / split;
         const double mma = (double)per_cta * S * 2 * prods * (0.66 * NT > 130.0 ? 0.66 * NT : 130.0);
-        const double load = (double)per_cta * (2 * S + NT / 64) * Pr * box_bytes / 48.0;
+        const double load = (double)per_cta * (2 * S + NT / 64) * Pr * box_bytes / 20.0;
         const long long resident = (long long)pl.occ * sms;
         const long long waves = (ctas + resident - 1) / resident;
         long long per_sm = (ctas + sms - 1) / sms;
@@ -1007,7 +1009,7 @@ extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long l
         static int model = -1;
         if (model < 0) {
             const char* e = getenv("PGK_WGRAD_PLAN");
-            model = e ? atoi(e) != 0 : 1;
+            model = e ? atoi(e) != 0 : 0;
         }
         WPlan bestp = legacy;
         for (int NT = 256; model && NT >= 64; NT >>= 1) {

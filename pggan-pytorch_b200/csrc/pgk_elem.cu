@@ -55,6 +55,51 @@ namespace {
 
 constexpr int MAXC = 4;  // image channels supported by the 1x1 image-surface kernels
 
+// optional second output of the kernels whose result a wide forward conv of the fp32-faithful mode reads next: the two
+// IEEE-half planes pgk_cvt_fp16x2 would derive from the stored bf16 planes (bit for bit: the value is rebuilt from the
+// planes exactly as ld8 reads them back), which saves that pass -- a read of 6 and a write of 4 bytes per element
+struct H16Out {
+    __half* p;
+    long long ps;
+};
+__device__ __forceinline__ void split_store8_h16(const Planes& t, long long i, const float* f, const H16Out& h16) {
+    if (!h16.p) {
+        split_store8(t, i, f);
+        return;
+    }
+    float res[8], back[3][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) res[j] = f[j];
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+        if (pl < t.P) {
+            uint4 q;
+            q.x = pack2(res[0], res[1]), q.y = pack2(res[2], res[3]), q.z = pack2(res[4], res[5]), q.w = pack2(res[6], res[7]);
+            *reinterpret_cast<uint4*>(t.p + pl * t.ps + i) = q;
+            unpack8(q, back[pl]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) res[j] -= back[pl][j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) back[pl][j] = 0.f;
+        }
+    }
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = t.P == 1 ? back[0][j] : back[0][j] + (t.P == 3 ? back[1][j] + back[2][j] : back[1][j]);
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const __half2 hh = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+        const float2 b = __half22float2(hh);
+        const __half2 l = __floats2half2_rn(v[2 * j] - b.x, v[2 * j + 1] - b.y);
+        hi[j] = *reinterpret_cast<const uint32_t*>(&hh);
+        lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    *reinterpret_cast<uint4*>(h16.p + i) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(h16.p + h16.ps + i) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
 inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 1) / per); }
 
 // ------------------------------------------------------------------------------------------
@@ -169,6 +214,7 @@ struct ExpandArgs {
     int has_mask;
     int pool;  // IMG = 2x2 block sum of a 2H x 2W image
     Planes out;
+    H16Out h16;
 };
 
 // IT = unsigned when the launch has fewer than 2^31 work items (every real shape): the item -> (pixel, chunk), pixel ->
@@ -243,7 +289,7 @@ __global__ void __launch_bounds__(256) rgb_expand_kernel(ExpandArgs a) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] *= lrelu_grad(m[u][j]);
             }
-            split_store8(a.out, o[u], v);
+            split_store8_h16(a.out, o[u], v, a.h16);
         }
     }
 }
@@ -723,7 +769,7 @@ static inline int log2_exact(int v) {
 
 template <bool P2>
 __global__ void __launch_bounds__(256) pool2_kernel(Planes src, int N, PixSplit<P2> sp, int C, float a, Planes other,
-                                                    int has_other, float b, Planes out, const float* da, const float* db) {
+                                                    int has_other, float b, Planes out, const float* da, const float* db, H16Out h16) {
     pgk_pdl_enter();
     const int H = sp.H, W = sp.W;
     const long long total = (long long)N * H * W * sp.nch;
@@ -749,13 +795,13 @@ __global__ void __launch_bounds__(256) pool2_kernel(Planes src, int N, PixSplit<
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = fmaf(b, g[j], v[j]);
         }
-        split_store8(out, o, v);
+        split_store8_h16(out, o, v, h16);
     }
 }
 
 template <bool P2>
 __global__ void __launch_bounds__(256) mask_mul_kernel(Planes src, int N, PixSplit<P2> sp, int C, int ups, float scale,
-                                                       Planes ref, int has_ref, Planes out, const float* dscale) {
+                                                       Planes ref, int has_ref, Planes out, const float* dscale, H16Out h16) {
     pgk_pdl_enter();
     scale *= dscale ? __ldg(dscale) : 1.f;
     const int H = sp.H, W = sp.W;
@@ -780,7 +826,7 @@ __global__ void __launch_bounds__(256) mask_mul_kernel(Planes src, int N, PixSpl
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] *= scale;
         }
-        split_store8(out, o, f);
+        split_store8_h16(out, o, f, h16);
     }
 }
 
@@ -805,7 +851,7 @@ __global__ void axpby_kernel(Planes x, float a, Planes y, int has_y, float b, lo
 }
 
 // pixel norm: L lanes per pixel, each lane owns up to 4 chunks of 8 channels
-__global__ void __launch_bounds__(256) pixelnorm_kernel(Planes h, long long npix, int C, int L, Planes y, float* r) {
+__global__ void __launch_bounds__(256) pixelnorm_kernel(Planes h, long long npix, int C, int L, Planes y, float* r, H16Out h16) {
     pgk_pdl_enter();
     const int nch = C >> 3;
     const int sub = threadIdx.x & (L - 1);
@@ -833,7 +879,7 @@ __global__ void __launch_bounds__(256) pixelnorm_kernel(Planes h, long long npix
             if (valid && ch < nch) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[i][j] *= rs;
-                split_store8(y, pix * C + ch * 8, f[i]);
+                split_store8_h16(y, pix * C + ch * 8, f[i], h16);
             }
         }
         if (sub == 0 && valid && r) r[pix] = rs;
@@ -1474,7 +1520,7 @@ static int launch_expand(ExpandArgs& a, pgk_stream_t stream, const char* name) {
     PGK_REQUIRE(smem <= 48 * 1024, "%s: weight does not fit shared memory", name);
     long long total = (long long)a.N * a.H * a.W * (a.K >> 3);
     const int lw = log2_exact(a.W);
-    if (narrow_enabled() && (a.K == 8 || a.K == 16) && a.out.P == 1 && lw >= 0 && (long long)a.H * a.W < (1ll << 30) &&
+    if (narrow_enabled() && !a.h16.p && (a.K == 8 || a.K == 16) && a.out.P == 1 && lw >= 0 && (long long)a.H * a.W < (1ll << 30) &&
         a.N <= 65535) {
         const dim3 grid(narrow_gx((long long)a.H * a.W, a.N), (unsigned)a.N);
         if (a.K == 8) pgk_launch(rgb_expand_narrow_kernel<1>, grid, 256, 0, ST, a, lw);
@@ -1492,8 +1538,9 @@ static int launch_expand(ExpandArgs& a, pgk_stream_t stream, const char* name) {
 
 extern "C" int pgk_from_rgb(const float* img, int N, int C, int H, int W, int Cout, const float* w, float c,
                             const float* bias, int act, const void* mask_ref, long long mask_ps, void* out, int P,
-                            long long out_ps, pgk_stream_t stream) {
+                            long long out_ps, void* out16, long long out16_ps, pgk_stream_t stream) {
     ExpandArgs a;
+    a.h16.p = (__half*)out16, a.h16.ps = out16_ps;
     a.img = img, a.N = N, a.C = C, a.H = H, a.W = W, a.K = Cout;
     a.w = w, a.sc = 1, a.sk = C, a.wscale = c, a.dmul = nullptr, a.bias = bias, a.act = act;
     a.mask = make_planes(mask_ref, mask_ps, P);
@@ -1507,6 +1554,7 @@ extern "C" int pgk_to_rgb_dgrad(const float* dimg, int N, int C, int H, int W, i
                                 float scale, int pool, void* dh, int P, long long dh_ps, const float* d_scale,
                                 pgk_stream_t stream) {
     ExpandArgs a;
+    a.h16.p = nullptr, a.h16.ps = 0;
     a.img = dimg, a.N = N, a.C = C, a.H = H, a.W = W, a.K = Cin;
     a.w = w, a.sc = Cin, a.sk = 1, a.wscale = c * scale, a.dmul = d_scale, a.bias = nullptr, a.act = 0;
     a.mask = make_planes(nullptr, 0, P);
@@ -1613,7 +1661,8 @@ extern "C" int pgk_rgb_wgrad(const float* img, int img_n0, const void* t, int P,
 
 extern "C" int pgk_pool2(const void* src, long long src_ps, int P, int N, int H, int W, int C, int avg, float a,
                          const void* other, long long other_ps, float b, void* out, long long out_ps, const float* d_a,
-                         const float* d_b, pgk_stream_t stream) {
+                         const float* d_b, void* out16, long long out16_ps, pgk_stream_t stream) {
+    const H16Out h16 = {(__half*)out16, out16_ps};
     PGK_REQUIRE(C % 8 == 0, "pgk_pool2: C must be a multiple of 8");
     long long total = (long long)N * H * W * (C >> 3);
     const int lnch = log2_exact(C >> 3), lw = log2_exact(W), lh = log2_exact(H);
@@ -1622,11 +1671,11 @@ extern "C" int pgk_pool2(const void* src, long long src_ps, int P, int N, int H,
     if (lnch >= 0 && lw >= 0 && lh >= 0 && total < (1ll << 31)) {
         PixSplit<true> sp = {C >> 3, W, H, lnch, lw, lh};
         pgk_launch(pool2_kernel<true>, grid, 256, 0, ST, make_planes(src, src_ps, P), N, sp, C, sa,
-                   make_planes(other, other_ps, P), other != nullptr, b, make_planes(out, out_ps, P), d_a, d_b);
+                   make_planes(other, other_ps, P), other != nullptr, b, make_planes(out, out_ps, P), d_a, d_b, h16);
     } else {
         PixSplit<false> sp = {C >> 3, W, H, 0, 0, 0};
         pgk_launch(pool2_kernel<false>, grid, 256, 0, ST, make_planes(src, src_ps, P), N, sp, C, sa,
-                   make_planes(other, other_ps, P), other != nullptr, b, make_planes(out, out_ps, P), d_a, d_b);
+                   make_planes(other, other_ps, P), other != nullptr, b, make_planes(out, out_ps, P), d_a, d_b, h16);
     }
     PGK_LAUNCH_CHECK("pgk_pool2");
     return PGK_OK;
@@ -1634,7 +1683,8 @@ extern "C" int pgk_pool2(const void* src, long long src_ps, int P, int N, int H,
 
 extern "C" int pgk_mask_mul(const void* src, long long src_ps, int P, int N, int H, int W, int C, int ups, float scale,
                             const void* ref, long long ref_ps, void* out, long long out_ps, const float* d_scale,
-                            pgk_stream_t stream) {
+                            void* out16, long long out16_ps, pgk_stream_t stream) {
+    const H16Out h16 = {(__half*)out16, out16_ps};
     PGK_REQUIRE(C % 8 == 0, "pgk_mask_mul: C must be a multiple of 8");
     PGK_REQUIRE(!ups || (H % 2 == 0 && W % 2 == 0), "pgk_mask_mul: ups needs even H, W");
     long long total = (long long)N * H * W * (C >> 3);
@@ -1643,11 +1693,11 @@ extern "C" int pgk_mask_mul(const void* src, long long src_ps, int P, int N, int
     if (lnch >= 0 && lw >= 0 && lh >= 0 && total < (1ll << 31)) {
         PixSplit<true> sp = {C >> 3, W, H, lnch, lw, lh};
         pgk_launch(mask_mul_kernel<true>, grid, 256, 0, ST, make_planes(src, src_ps, P), N, sp, C, ups, scale,
-                   make_planes(ref, ref_ps, P), ref != nullptr, make_planes(out, out_ps, P), d_scale);
+                   make_planes(ref, ref_ps, P), ref != nullptr, make_planes(out, out_ps, P), d_scale, h16);
     } else {
         PixSplit<false> sp = {C >> 3, W, H, 0, 0, 0};
         pgk_launch(mask_mul_kernel<false>, grid, 256, 0, ST, make_planes(src, src_ps, P), N, sp, C, ups, scale,
-                   make_planes(ref, ref_ps, P), ref != nullptr, make_planes(out, out_ps, P), d_scale);
+                   make_planes(ref, ref_ps, P), ref != nullptr, make_planes(out, out_ps, P), d_scale, h16);
     }
     PGK_LAUNCH_CHECK("pgk_mask_mul");
     return PGK_OK;
@@ -1663,11 +1713,12 @@ extern "C" int pgk_axpby(const void* x, long long x_ps, float a, const void* y, 
 }
 
 extern "C" int pgk_pixelnorm(const void* h, long long h_ps, int P, long long npix, int C, void* y, long long y_ps,
-                             float* r, pgk_stream_t stream) {
+                             float* r, void* y16, long long y16_ps, pgk_stream_t stream) {
+    const H16Out h16 = {(__half*)y16, y16_ps};
     PGK_REQUIRE(C % 8 == 0 && C <= 1024, "pgk_pixelnorm: C must be a multiple of 8 and <= 1024");
     int L = lanes_for(C >> 3);
     pgk_launch(pixelnorm_kernel, dim3(grid_cap((npix * L + 255) / 256)), 256, 0, ST, make_planes(h, h_ps, P), npix, C, L,
-                                                                       make_planes(y, y_ps, P), r);
+                                                                       make_planes(y, y_ps, P), r, h16);
     PGK_LAUNCH_CHECK("pgk_pixelnorm");
     return PGK_OK;
 }

@@ -33,6 +33,9 @@ W_CONV, W_GFIRST, W_DLAST = 0, 1, 2
 # seeds) is unchanged with it.  Default since the fault of its first version was found (the tensor maps declared a third
 # operand plane behind the two-plane allocations: DESIGN.md 7c-4); PGK_FWD_FP16=0 keeps the six-product bf16 path (A/B).
 FWD_FP16 = os.environ.get('PGK_FWD_FP16', '1') == '1'
+# Producers of a tensor that such a conv reads next (from_rgb, pool2, the materialised upsample, the pixel norm) write
+# the fp16 planes themselves (include/pgk.h: out16), which saves the pgk_cvt_fp16x2 pass; PGK_FUSE_CVT=0 for A/B runs.
+FUSE_CVT = os.environ.get('PGK_FUSE_CVT', '1') == '1'
 # diagnostic knobs of the fault hunt
 _FP16_NOPOS = os.environ.get('PGK_FP16_NOPOS', '0') == '1'
 _FP16_MINPIX = int(os.environ.get('PGK_FP16_MINPIX', '0'))
@@ -101,6 +104,26 @@ def _mask(m):
     return (m.ptr, m.ps) if m is not None else (None, 0)
 
 
+def _h16_out(out, want):
+    """(pointer, plane stride) of the IEEE-half companion a producer kernel fills next to `out`, or (None, 0).  The
+    companion covers the whole storage (2 planes x ntot samples); aux['h16_range'] remembers which samples are valid."""
+    if not (want and FWD_FP16 and FUSE_CVT and out.P >= 2 and out.C % 64 == 0):
+        return None, 0
+    h = out.aux.get('h16')
+    if h is None or h.shape[1] != out.ntot * out.per:
+        h = out.aux['h16'] = torch.empty((2, out.ntot * out.per), dtype=torch.float16, device=out.t.device)
+    out.aux['h16_range'] = (out.off, out.off + out.N)
+    return h.data_ptr() + 2 * out.off * out.per, out.ntot * out.per
+
+
+def _h16_in(x):
+    """(pointer, plane stride) of a valid companion of x, or None."""
+    h, rng = x.aux.get('h16'), x.aux.get('h16_range')
+    if h is None or rng is None or x.off < rng[0] or x.off + x.N > rng[1] or h.shape[1] != x.ntot * x.per:
+        return None
+    return h.data_ptr() + 2 * x.off * x.per, x.ntot * x.per
+
+
 class Fade(object):
     """The fade-in factors alpha and 1 - alpha as the kernels take them: (host scalar, device pointer or None).
     Eager mode: the host scalar carries everything.  CUDA-graph mode (wgan_gp_loss.cuda_graphs): the host scalar is the
@@ -135,25 +158,35 @@ def _sc(v):
 
 
 def conv(x, w, cout, ks, out, ups=0, bias=None, posT=None, pos_s=None, act=0, mask=None, scale=1.0, fwd=False,
-         pn_r=None):
+         pn_r=None, out_h16=False):
     """out <- pgk_conv(x); H, W are taken from `out`.  w = (fp32 [K][Cout] operand, bf16 planes [3][Cout][K] operand).
     fwd=True: a forward pass whose values decide LeakyReLU masks -- all planes are read.
-    pn_r: fp32 (N*H*W) tensor -- apply the pixel norm after the activation and store its per-pixel factor there."""
+    pn_r: fp32 (N*H*W) tensor -- apply the pixel norm after the activation and store its per-pixel factor there.
+    out_h16: the next reader of `out` is a wide forward conv: let the pixel-norm pass write its fp16 planes too."""
     mp, mps = _mask(mask)
     wf, wt = w[0], w[1]
     if (FWD_FP16 and fwd and len(w) > 2 and w[2] is not None and x.P >= 2 and mask is None and not ups and scale == 1.0
             and not (_FP16_NOPOS and posT is not None) and out.N * out.H * out.W >= _FP16_MINPIX
             and _lib.load().pgk_conv_tc_supported(out.N, out.H, out.W, x.C, cout, ks, 0)):
         # fp16 two-plane copy of the input (one extra pass), then the conv on half operands
-        xh = torch.empty((2, x.N * x.per + _FP16_PAD), dtype=torch.float16, device=x.t.device)
-        out.aux['xh'] = xh          # lives as long as the output it produced (the tape), not just this call
-        call('pgk_cvt_fp16x2', x.ptr, x.ps, x.P, x.N * x.per, xh.data_ptr(), xh.stride(0))
-        call('pgk_conv_fp16', xh.data_ptr(), xh.stride(0), out.N, out.H, out.W, x.C, cout, ks, w[2].data_ptr(),
+        comp = _h16_in(x)
+        if comp is not None:
+            xh_ptr, xh_ps = comp             # written by the kernel that produced x
+        else:
+            xh = torch.empty((2, x.N * x.per + _FP16_PAD), dtype=torch.float16, device=x.t.device)
+            call('pgk_cvt_fp16x2', x.ptr, x.ps, x.P, x.N * x.per, xh.data_ptr(), xh.stride(0))
+            xh_ptr, xh_ps = xh.data_ptr(), xh.stride(0)
+        call('pgk_conv_fp16', xh_ptr, xh_ps, out.N, out.H, out.W, x.C, cout, ks, w[2].data_ptr(),
              w[2].stride(0), None if bias is None else bias.data_ptr(), None if posT is None else posT.data_ptr(),
              None if pos_s is None else pos_s.data_ptr(), act, out.ptr, out.P, out.ps)
+        # the half planes have one reader: hand them back to the (stream-ordered) caching allocator now rather than
+        # when the tape dies
+        x.aux.pop('h16', None)
+        x.aux.pop('h16_range', None)
         if pn_r is not None:
+            o16, o16_ps = _h16_out(out, out_h16)
             call('pgk_pixelnorm', out.ptr, out.ps, out.P, out.N * out.H * out.W, out.C, out.ptr, out.ps,
-                 pn_r.data_ptr())
+                 pn_r.data_ptr(), o16, o16_ps)
         return out
     call('pgk_conv', x.ptr, x.P, x.P if fwd else min(x.P, GRAD_PLANES), x.ps, out.N, out.H, out.W, x.C, cout, ks, ups,
          None if wf is None else wf.data_ptr(), wt.data_ptr(),
@@ -178,11 +211,12 @@ def bias_grad(g, hw, cout, goffs, group_n, db, scale=1.0, accumulate=0):
          accumulate)
 
 
-def from_rgb(img, mod, out, act=1, bias=True, mask=None):
+def from_rgb(img, mod, out, act=1, bias=True, mask=None, h16=False):
     n, c, h, w = img.shape
     mp, mps = _mask(mask)
+    o16, o16_ps = _h16_out(out, h16)
     call('pgk_from_rgb', img.data_ptr(), n, c, h, w, out.C, mod.conv.weight.data_ptr(), mod.cf,
-         mod.conv.bias.data_ptr() if bias else None, act, mp, mps, out.ptr, out.P, out.ps)
+         mod.conv.bias.data_ptr() if bias else None, act, mp, mps, out.ptr, out.P, out.ps, o16, o16_ps)
     return out
 
 
@@ -198,18 +232,21 @@ def rgb_wgrad(img, img_n0, t, n, c, h, w, pool, scale_w, scale_b, dw, sa, sk, co
          None if imgsum is None else imgsum.data_ptr(), dscale)
 
 
-def pool2(src, out, avg=1, a=1.0, other=None, b=0.0):
+def pool2(src, out, avg=1, a=1.0, other=None, b=0.0, h16=False):
     op, ops = _mask(other)
     (a, da), (b, db) = _sc(a), _sc(b)
-    call('pgk_pool2', src.ptr, src.ps, src.P, out.N, out.H, out.W, out.C, avg, a, op, ops, b, out.ptr, out.ps, da, db)
+    o16, o16_ps = _h16_out(out, h16)
+    call('pgk_pool2', src.ptr, src.ps, src.P, out.N, out.H, out.W, out.C, avg, a, op, ops, b, out.ptr, out.ps, da, db,
+         o16, o16_ps)
     return out
 
 
-def mask_mul(src, out, ref=None, ups=0, scale=1.0):
+def mask_mul(src, out, ref=None, ups=0, scale=1.0, h16=False):
     rp, rps = _mask(ref)
     scale, dscale = _sc(scale)
+    o16, o16_ps = _h16_out(out, h16)
     call('pgk_mask_mul', src.ptr, src.ps, src.P, out.N, out.H, out.W, out.C, ups, scale, rp, rps, out.ptr, out.ps,
-         dscale)
+         dscale, o16, o16_ps)
     return out
 
 
@@ -504,7 +541,7 @@ class DEngine(object):
         top = self.blk(depth + 1)
         ctop = top.fromRGB.conv.weight.shape[0]
         T.t0 = new(r, ctop)
-        from_rgb(ximg, top.fromRGB, T.t0.sl(0, B))
+        from_rgb(ximg, top.fromRGB, T.t0.sl(0, B), h16=True)
         if depth == 0:
             hin = T.t0
         else:
@@ -518,9 +555,9 @@ class DEngine(object):
                 T.xlow = pool_img(ximg)
                 T.f = new(r // 2, w2.cout)
                 from_rgb(T.xlow, self.blk(depth).fromRGB, T.f.sl(0, B))
-                pool2(T.t2.sl(0, B), h.sl(0, B), avg=1, a=T.fd.a(), other=T.f.sl(0, B), b=T.fd.b())
+                pool2(T.t2.sl(0, B), h.sl(0, B), avg=1, a=T.fd.a(), other=T.f.sl(0, B), b=T.fd.b(), h16=True)
             else:
-                pool2(T.t2.sl(0, B), h.sl(0, B), avg=1)
+                pool2(T.t2.sl(0, B), h.sl(0, B), avg=1, h16=True)
             res = r // 2
             for k in range(depth, 1, -1):
                 b = self.blk(k)
@@ -530,7 +567,7 @@ class DEngine(object):
                 b_ = new(res, w2.cout)
                 conv(a_.sl(0, B), w2.F, w2.cout, 3, b_.sl(0, B), bias=w2.bias, act=1, fwd=True)
                 hn = new(res // 2, w2.cout)
-                pool2(b_.sl(0, B), hn.sl(0, B), avg=1)
+                pool2(b_.sl(0, B), hn.sl(0, B), avg=1, h16=True)
                 T.blocks.append(SimpleNamespace(mod=b, hin=h, a=a_, b=b_, res=res))
                 h, res = hn, res // 2
             hin = h
@@ -813,7 +850,7 @@ class GEngine(object):
         conv(zn, w1.F, 16 * w1.cout, 1, h1.view(1, 1, 16 * w1.cout), bias=w1.bias16, act=1, fwd=True)
         r = self._pn(h1, T, 'b0c1')   # the dense first layer: its 16 output pixels sit side by side in one GEMM row
         if r is not None:
-            call('pgk_pixelnorm', h1.ptr, h1.ps, h1.P, h1.N * h1.H * h1.W, h1.C, h1.ptr, h1.ps, r.data_ptr())
+            call('pgk_pixelnorm', h1.ptr, h1.ps, h1.P, h1.N * h1.H * h1.W, h1.C, h1.ptr, h1.ps, r.data_ptr(), None, 0)
         h2 = PT.empty(n, 4, 4, w2.cout, P, dev)
         conv(h1, w2.F, w2.cout, 3, h2, bias=w2.bias, act=1, fwd=True, pn_r=self._pn(h2, T, 'b0c2'))
         if tape:
@@ -827,9 +864,9 @@ class GEngine(object):
             res *= 2
             # nearest-neighbour 2x upsample (network.py:127,129), materialised once: the tensor-core conv and the
             # weight gradient both read it through plain TMA boxes
-            hu = mask_mul(h, PT.empty(n, res, res, h.C, P, dev), ups=1)
+            hu = mask_mul(h, PT.empty(n, res, res, h.C, P, dev), ups=1, h16=True)
             u1 = PT.empty(n, res, res, w1.cout, P, dev)
-            conv(hu, w1.F, w1.cout, 3, u1, bias=w1.bias, act=1, fwd=True, pn_r=self._pn(u1, T, 'b%dc1' % i))
+            conv(hu, w1.F, w1.cout, 3, u1, bias=w1.bias, act=1, fwd=True, pn_r=self._pn(u1, T, 'b%dc1' % i), out_h16=True)
             u2 = PT.empty(n, res, res, w2.cout, P, dev)
             conv(u1, w2.F, w2.cout, 3, u2, bias=w2.bias, act=1, fwd=True, pn_r=self._pn(u2, T, 'b%dc2' % i))
             if tape:

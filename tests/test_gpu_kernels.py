@@ -282,9 +282,9 @@ def test_narrow_image_kernels_are_the_generic_ones_bit_for_bit(K, C):
     def run():
         outs = []
         o = E.PT.empty(n, H, W, K, 1, dev)
-        call('pgk_from_rgb', img.data_ptr(), n, C, H, W, K, w.data_ptr(), 0.7, bias.data_ptr(), 1, None, 0, o.ptr, 1, o.ps)
+        call('pgk_from_rgb', img.data_ptr(), n, C, H, W, K, w.data_ptr(), 0.7, bias.data_ptr(), 1, None, 0, o.ptr, 1, o.ps, None, 0)
         outs.append(o.t.clone())
-        call('pgk_from_rgb', img.data_ptr(), n, C, H, W, K, w.data_ptr(), 0.7, None, 0, mask.ptr, mask.ps, o.ptr, 1, o.ps)
+        call('pgk_from_rgb', img.data_ptr(), n, C, H, W, K, w.data_ptr(), 0.7, None, 0, mask.ptr, mask.ps, o.ptr, 1, o.ps, None, 0)
         outs.append(o.t.clone())
         call('pgk_to_rgb_dgrad', img.data_ptr(), n, C, H, W, K, wt.data_ptr(), 0.9, 0.3, 0, o.ptr, 1, o.ps, dsc.data_ptr())
         outs.append(o.t.clone())

@@ -394,3 +394,50 @@ def test_cuda_graph_replay_equals_eager(gpu, fading):
         assert rel_err(r1, r0) < 1e-5 and rel_err(f1, f0) < 1e-5
     for a, b in zip(pe, pgr):
         assert rel_err(b, a) < 1e-5      # atomics make the last bits of the weight gradients order dependent
+
+
+@pytest.mark.parametrize('depth,alpha', [(2, 1.0), (3, 0.4)])
+def test_fused_half_planes_equal_the_conversion_pass(gpu, depth, alpha):
+    """fp32-faithful mode with fp16 forward operands: the half planes written by from_rgb / pool2 / the upsample / the
+    pixel norm (include/pgk.h: out16) against those of the separate pgk_cvt_fp16x2 pass -- the forward results (no
+    atomics on that path) must be equal bit for bit, at the reference's channel widths (512: the wide kernel)."""
+    import importlib
+    pg = gpu['pg']
+    E = importlib.import_module('pggan-pytorch_b200.engine')
+    if not E.FWD_FP16:
+        pytest.skip('PGK_FWD_FP16=0')
+    torch.manual_seed(7)
+    shape = (1000, 3, 1024, 1024)
+    G, D = pg.Generator(shape).cuda(), pg.Discriminator(shape).cuda()
+    G.depth = D.depth = depth
+    G.alpha = D.alpha = alpha
+    n, r = 4, 4 * 2 ** depth
+    z = torch.randn(n, 512, device='cuda')
+    x = torch.randn(n, 3, r, r, device='cuda')
+    seen = []
+    real_call = E.call
+
+    def spy(name, *a):
+        seen.append(name)
+        return real_call(name, *a)
+
+    def run(fuse):
+        old = E.FUSE_CVT
+        E.FUSE_CVT = fuse
+        E.call = spy
+        del seen[:]
+        try:
+            with torch.no_grad():
+                img = G(z).clone()
+                score = D(x).clone()
+            torch.cuda.synchronize()
+        finally:
+            E.FUSE_CVT = old
+            E.call = real_call
+        return img, score, seen.count('pgk_cvt_fp16x2'), seen.count('pgk_conv_fp16')
+
+    img0, s0, cvt0, conv0 = run(False)
+    img1, s1, cvt1, conv1 = run(True)
+    assert conv0 == conv1 and conv0 > 0 and cvt0 == conv0        # without fusion: one conversion per half-operand conv
+    assert cvt1 < cvt0                                           # with it: only conv -> conv links still convert
+    assert torch.equal(img0, img1) and torch.equal(s0, s1)
