@@ -80,8 +80,10 @@ __global__ void __launch_bounds__(256) prep_multi_kernel(const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     // ---- pass 1, a warp per (output channel, tap) row, lanes = input channels: forward operand (+ half packing), wb.
     // Every destination is contiguous in ci: per row one base index, no division per element.
-    for (int r = warp; r < nco * taps; r += nwarps) {
-        const int co_l = r / taps, tap = r - co_l * taps;
+    // (a warp walks the taps of its output channels: no division per row -- the per-row index arithmetic was the larger
+    // part of this kernel's instructions)
+    for (int co_l = warp; co_l < nco; co_l += nwarps)
+    for (int tap = 0; tap < taps; ++tap) {
         const int co = co0 + co_l;
         long long fbase, bbase;      // index of (co, ci0, tap) in F (standard layout) and in wb
         if (L.kind == PGK_W_CONV) {
@@ -115,8 +117,8 @@ __global__ void __launch_bounds__(256) prep_multi_kernel(const __grid_constant__
     }
     // ---- pass 2, a warp per (input channel, tap) row, lanes = output channels: data-gradient operand, wf
     if (L.B || L.wf) {
-        for (int r = warp; r < nci * taps; r += nwarps) {
-            const int ci_l = r / taps, tap = r - ci_l * taps;
+        for (int ci_l = warp; ci_l < nci; ci_l += nwarps)
+        for (int tap = 0; tap < taps; ++tap) {
             const int ci = ci0 + ci_l;
             long long fibase, bidx;     // index of (co0, ci, tap) in wf and in B (standard layout)
             if (L.kind == PGK_W_CONV) {
@@ -164,8 +166,8 @@ __global__ void __launch_bounds__(256) unprep_multi_kernel(const __grid_constant
     const int nco = min(kTileCo, L.cout - co0), nci = min(tci, L.cin - ci0);
     // ---- load, a warp per (input channel, tap) row, lanes = output channels: dwp is [K][Cout] (wf's layout)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int r = warp; r < nci * taps; r += nwarps) {
-        const int ci_l = r / taps, tap = r - ci_l * taps;
+    for (int ci_l = warp; ci_l < nci; ci_l += nwarps)
+    for (int tap = 0; tap < taps; ++tap) {
         const int ci = ci0 + ci_l;
         long long fibase;
         if (L.kind == PGK_W_GFIRST) fibase = (long long)ci * (16 * L.cout) + (long long)(15 - tap) * L.cout + co0;

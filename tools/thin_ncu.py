@@ -1,5 +1,5 @@
 """Development aid: one launch of each thin-layer kernel shape of interest, for `ncu --set full` captures.
-   ncu --set full --clock-control none --import-source on -k regex:'conv_thin|wgrad_thin' -o gpurun_out/thin python tools/thin_ncu.py"""
+   ncu --set full --clock-control none --import-source on -k regex:'conv_thin|wgrad_direct|wgrad_thin' -o gpurun_out/thin python tools/thin_ncu.py"""
 import os
 import sys
 
