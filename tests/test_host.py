@@ -259,7 +259,9 @@ def test_python_sequencing_of_one_iteration_with_stubbed_kernels(monkeypatch, fp
         assert all(p.grad is None for p in G.parameters())
         assert calls['pgk_gp_penalty'] == 1 and calls['pgk_stddev_bwd2'] == 1
         if fp16:
-            assert calls['pgk_conv_fp16'] > 0 and calls['pgk_cvt_fp16x2'] == calls['pgk_conv_fp16']
+            # (inputs written by from_rgb / pool2 / the upsample / the pixel norm arrive with their half planes: fewer
+            # conversion passes than half-operand convs)
+            assert calls['pgk_conv_fp16'] > 0 and 0 < calls['pgk_cvt_fp16x2'] < calls['pgk_conv_fp16']
         else:
             assert calls['pgk_conv_fp16'] == 0 and calls['pgk_pack_operand_fp16'] == 0
         gcost = pg.wgan_gp_G_loss(G, D, torch.randn(4, 64))
