@@ -25,7 +25,7 @@ extern "C" int pgk_conv_tc_fuses_pixelnorm(int Cout, int split_acc);
 extern "C" int pgk_wgrad_tc_supported(int H, int W, int Cin, int Cout, int KS, int ups, int ngroups, int group_n);
 extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W,
                             int Cin, int Cout, int KS, int ngroups, int group_n, const int* xoff, const int* goff,
-                            float* dwp, pgk_stream_t stream);
+                            float* dwp, float* db, unsigned bias_mask, pgk_stream_t stream);
 
 extern "C" int pgk_conv_thin_supported(int N, int H, int W, int Cin, int Cout, int KS, int ups);
 extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N, int H, int W, int Cin, int Cout,
@@ -193,7 +193,16 @@ extern "C" int pgk_wgrad(const void* x, long long x_ps, const void* g, long long
     int rc;
     if (tc_enabled() && pgk_wgrad_tc_supported(H, W, Cin, Cout, KS, ups, ngroups, group_n)) {
         ProfScope prof(PGK_PROF_WGRAD, flops, bytes, stream, Pr);
-        rc = pgk_wgrad_tc(x, x_ps, g, g_ps, P, Pr, H, W, Cin, Cout, KS, ngroups, group_n, xoff, goff, dwp, stream);
+        // the bias gradient rides along in the same launch (PGK_WGRAD_BIAS_FUSE=0: the separate pass below, for A/B runs)
+        static int fuse = -1;
+        if (fuse < 0) {
+            const char* e = getenv("PGK_WGRAD_BIAS_FUSE");
+            fuse = e ? atoi(e) != 0 : 1;
+        }
+        const bool fused = fuse && db && bias_groups && P == Pr;
+        rc = pgk_wgrad_tc(x, x_ps, g, g_ps, P, Pr, H, W, Cin, Cout, KS, ngroups, group_n, xoff, goff, dwp,
+                          fused ? db : nullptr, bias_groups, stream);
+        if (rc || fused) return rc;
     } else {
         ProfScope prof(PGK_PROF_WGRAD_SIMT, flops, bytes, stream);
         rc = pgk_wgrad_simt(x, x_ps, g, g_ps, P, H, W, Cin, Cout, KS, ups, ngroups, group_n, xoff, goff, dwp, stream);

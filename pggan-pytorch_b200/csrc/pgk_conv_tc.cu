@@ -477,6 +477,8 @@ struct WgradTcArgs {
     int RG;               // 64-row groups in K = KS*KS*Cin / 64
     long long tiles_per_group, tiles_total, tiles_per_cta;
     float* dwp;
+    float* db;            // optional fused bias gradient: db[co] += sum over the pixels of the groups in bias_mask of G
+    unsigned bias_mask;
 };
 
 // four consecutive floats added to global memory in one reduction (sm_90+; the address must be 16-byte aligned)
@@ -513,11 +515,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const int ntiles = (int)(t_end - t_begin);   // >= 1 by construction of the grid
     const int pad = a.KS >> 1;
     const int cchunks = a.Cin / 64;
+    // the bias gradient (column sums of G) rides along in the CTAs of the first slab group: warps 0-3, idle until the
+    // flush, add up every G tile from the stage ring while the MMAs of that stage run
+    const bool do_bias = a.db != nullptr && blockIdx.x == 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.stages; ++s) {
             mbar_init(full(s), 1);
-            mbar_init(empty(s), 1);
+            mbar_init(empty(s), do_bias ? 5 : 1);   // the MMA commit (+ the four bias-gradient warps)
         }
         mbar_init(tfull, 1);
         fence_barrier_init();
@@ -623,6 +628,57 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         if (elect_one()) mma_commit(tfull);
         __syncwarp();
     } else {
+        if (do_bias) {
+            // thread = (16-byte chunk c of the 128-byte pixel row, pixel group pg): pixels pg and pg + 16 of every box;
+            // SWIZZLE_128B: chunk c of pixel row px sits at chunk position c ^ (px & 7)
+            const int t = warp * 32 + lane, c = t & 7, pg = t >> 3;
+            float acc[4][8];
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[b][j] = 0.f;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int it = 0; it < ntiles; ++it) {
+                mbar_wait(full(s), ph);
+                const int grp = (int)((t_begin + it) / a.tiles_per_group);
+                if ((a.bias_mask >> grp) & 1) {
+                    const uint32_t g0 = sbase + s * stage_bytes + 2 * S * box_bytes;
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            if (b < gboxes) {
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    const uint32_t px = (uint32_t)(pg + 16 * h);
+                                    float f[8];
+                                    unpack8(ld_shared_v4(g0 + p * plane_bytes + b * box_bytes + px * 128u +
+                                                         ((uint32_t)(c ^ (int)(px & 7u)) << 4)), f);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) acc[b][j] += f[j];
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty(s));
+                if (++s == a.stages) s = 0, ph ^= 1;
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                if (b < gboxes) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float v = acc[b][j];
+                        v += __shfl_xor_sync(0xffffffffu, v, 8);
+                        v += __shfl_xor_sync(0xffffffffu, v, 16);
+                        if (lane < 8 && v != 0.f) atomicAdd(a.db + co0 + b * 64 + c * 8 + j, v);
+                    }
+                }
+            }
+        }
         mbar_wait(tfull, 0);
         fence_after();
         const int K = a.KS * a.KS * a.Cin;
@@ -914,7 +970,7 @@ extern "C" int pgk_wgrad_tc_supported(int H, int W, int Cin, int Cout, int KS, i
 
 extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W,
                             int Cin, int Cout, int KS, int ngroups, int group_n, const int* xoff, const int* goff,
-                            float* dwp, pgk_stream_t stream) {
+                            float* dwp, float* db, unsigned bias_mask, pgk_stream_t stream) {
     PGK_REQUIRE(pgk_wgrad_tc_supported(H, W, Cin, Cout, KS, 0, ngroups, group_n), "pgk_wgrad_tc: unsupported shape");
     PGK_REQUIRE((((uintptr_t)dwp) & 15) == 0, "pgk_wgrad_tc: dwp must be 16-byte aligned (vector reductions)");
     PGK_REQUIRE(P >= 1 && P <= 3 && Pr >= 1 && Pr <= P, "pgk_wgrad_tc: need 1 <= Pr <= P <= 3");
@@ -1046,6 +1102,7 @@ extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long l
     a.tiles_per_cta = (a.tiles_total + split - 1) / split;
     split = (a.tiles_total + a.tiles_per_cta - 1) / a.tiles_per_cta;
     a.dwp = dwp;
+    a.db = db, a.bias_mask = bias_mask;
 
     CUtensorMap tmX, tmG;
     {

@@ -1520,11 +1520,12 @@ static int launch_expand(ExpandArgs& a, pgk_stream_t stream, const char* name) {
     PGK_REQUIRE(smem <= 48 * 1024, "%s: weight does not fit shared memory", name);
     long long total = (long long)a.N * a.H * a.W * (a.K >> 3);
     const int lw = log2_exact(a.W);
-    if (narrow_enabled() && !a.h16.p && (a.K == 8 || a.K == 16) && a.out.P == 1 && lw >= 0 && (long long)a.H * a.W < (1ll << 30) &&
+    if (narrow_enabled() && !a.h16.p && (a.K == 8 || a.K == 16 || a.K == 32) && a.out.P == 1 && lw >= 0 && (long long)a.H * a.W < (1ll << 30) &&
         a.N <= 65535) {
         const dim3 grid(narrow_gx((long long)a.H * a.W, a.N), (unsigned)a.N);
         if (a.K == 8) pgk_launch(rgb_expand_narrow_kernel<1>, grid, 256, 0, ST, a, lw);
-        else pgk_launch(rgb_expand_narrow_kernel<2>, grid, 256, 0, ST, a, lw);
+        else if (a.K == 16) pgk_launch(rgb_expand_narrow_kernel<2>, grid, 256, 0, ST, a, lw);
+        else pgk_launch(rgb_expand_narrow_kernel<4>, grid, 256, 0, ST, a, lw);
         PGK_LAUNCH_CHECK(name);
         return PGK_OK;
     }

@@ -250,7 +250,7 @@ def test_unprep_multi_is_unprep_grad_bit_for_bit():
         assert torch.equal(ref, got), spec
 
 
-@pytest.mark.parametrize('K', [8, 16])
+@pytest.mark.parametrize('K', [8, 16, 32])
 @pytest.mark.parametrize('C', [1, 3])
 def test_narrow_image_kernels_are_the_generic_ones_bit_for_bit(K, C):
     """The narrow one-plane flavours of the 1x1 image kernels and of the pixel-norm backward pass (csrc/pgk_elem.cu,

@@ -62,7 +62,7 @@ def test_committed_traffic_figure_is_what_the_committed_capture_says(cfg, family
     with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
         entry = json.load(f)[cfg][family]
     per = {}
-    with open(os.path.join(ROOT, 'profiles', 'r2_traffic_%s.csv' % cfg)) as f:
+    with open(os.path.join(ROOT, 'profiles', 'r2b_traffic_%s.csv' % cfg)) as f:
         rows = csv.DictReader([l for l in f if not l.startswith('==')])
         for row in rows:
             if family not in row['Kernel Name'] or not row['Metric Name'].startswith('dram__bytes'):
