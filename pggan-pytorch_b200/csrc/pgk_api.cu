@@ -25,7 +25,7 @@ extern "C" int pgk_conv_tc_fuses_pixelnorm(int Cout, int split_acc);
 extern "C" int pgk_wgrad_tc_supported(int H, int W, int Cin, int Cout, int KS, int ups, int ngroups, int group_n);
 extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W,
                             int Cin, int Cout, int KS, int ngroups, int group_n, const int* xoff, const int* goff,
-                            float* dwp, float* db, unsigned bias_mask, pgk_stream_t stream);
+                            float* dwp, float* db, unsigned bias_mask, int* bias_fused, pgk_stream_t stream);
 
 extern "C" int pgk_conv_thin_supported(int N, int H, int W, int Cin, int Cout, int KS, int ups);
 extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N, int H, int W, int Cin, int Cout,
@@ -199,9 +199,9 @@ extern "C" int pgk_wgrad(const void* x, long long x_ps, const void* g, long long
             const char* e = getenv("PGK_WGRAD_BIAS_FUSE");
             fuse = e ? atoi(e) != 0 : 1;
         }
-        const bool fused = fuse && db && bias_groups && P == Pr;
+        int fused = 0;
         rc = pgk_wgrad_tc(x, x_ps, g, g_ps, P, Pr, H, W, Cin, Cout, KS, ngroups, group_n, xoff, goff, dwp,
-                          fused ? db : nullptr, bias_groups, stream);
+                          (fuse && P == Pr) ? db : nullptr, bias_groups, &fused, stream);
         if (rc || fused) return rc;
     } else {
         ProfScope prof(PGK_PROF_WGRAD_SIMT, flops, bytes, stream);

@@ -970,7 +970,7 @@ extern "C" int pgk_wgrad_tc_supported(int H, int W, int Cin, int Cout, int KS, i
 
 extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W,
                             int Cin, int Cout, int KS, int ngroups, int group_n, const int* xoff, const int* goff,
-                            float* dwp, float* db, unsigned bias_mask, pgk_stream_t stream) {
+                            float* dwp, float* db, unsigned bias_mask, int* bias_fused, pgk_stream_t stream) {
     PGK_REQUIRE(pgk_wgrad_tc_supported(H, W, Cin, Cout, KS, 0, ngroups, group_n), "pgk_wgrad_tc: unsupported shape");
     PGK_REQUIRE((((uintptr_t)dwp) & 15) == 0, "pgk_wgrad_tc: dwp must be 16-byte aligned (vector reductions)");
     PGK_REQUIRE(P >= 1 && P <= 3 && Pr >= 1 && Pr <= P, "pgk_wgrad_tc: need 1 <= Pr <= P <= 3");
@@ -1102,7 +1102,13 @@ extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long l
     a.tiles_per_cta = (a.tiles_total + split - 1) / split;
     split = (a.tiles_total + a.tiles_per_cta - 1) / a.tiles_per_cta;
     a.dwp = dwp;
-    a.db = db, a.bias_mask = bias_mask;
+    // The bias gradient rides along (idle warps sum the G tiles of the first slab group's CTAs) where that measured a
+    // gain: one-plane mode with long reductions (c3 19.90 -> 19.63 ms, c5 25.74 -> 25.34).  In the fp32-faithful mode
+    // the extra shared-memory reads slow those CTAs' MMAs by what the separate pass cost (c2: +-0), and on the short
+    // reductions of depth 8 / batch 4 it lost 0.4 ms per iteration: there the caller runs pgk_bias_grad.
+    const bool fuse_bias = db && bias_mask && Pr == 1 && a.tiles_per_cta >= 64;
+    a.db = fuse_bias ? db : nullptr, a.bias_mask = bias_mask;
+    if (bias_fused) *bias_fused = fuse_bias ? 1 : 0;
 
     CUtensorMap tmX, tmG;
     {
