@@ -230,17 +230,14 @@ int pgk_rgb_wgrad(const float* img, int img_n0, const void* t, int P, long long 
 
 /* ---- elementwise / reductions on planes ------------------------------------------------- */
 /* out = a * pool2x2(src) [+ b * other]; avg = 1: mean of the block (F.avg_pool2d, network.py:229,238),
- * avg = 0: sum (backward of the nearest upsample).  src is N x 2H x 2W x C, out/other N x H x W x C.
- * src_bits (optional, N*H*W*C/8 32-bit words): side output for the backward pass -- per output pixel and group of 8
- * channels the LeakyReLU decisions (plane 0 > 0) of the four source pixels, byte q = pixel (q >> 1, q & 1) of the block;
- * pgk_mask_mul(ups = 1) takes it as ref_bits in place of ref (4 bytes read where the reference tensor costs 64). */
+ * avg = 0: sum (backward of the nearest upsample).  src is N x 2H x 2W x C, out/other N x H x W x C. */
 int pgk_pool2(const void* src, long long src_ps, int P, int N, int H, int W, int C, int avg, float a,
               const void* other, long long other_ps, float b, void* out, long long out_ps, const float* d_a,
-              const float* d_b, void* out16, long long out16_ps, void* src_bits, pgk_stream_t stream);
-/* out[n,y,x,c] = scale * src[n, y>>ups, x>>ups, c] * lrelu'(ref[n,y,x,c]) (ref optional; ref_bits: see pgk_pool2) */
+              const float* d_b, void* out16, long long out16_ps, pgk_stream_t stream);
+/* out[n,y,x,c] = scale * src[n, y>>ups, x>>ups, c] * lrelu'(ref[n,y,x,c]) (ref optional) */
 int pgk_mask_mul(const void* src, long long src_ps, int P, int N, int H, int W, int C, int ups, float scale,
                  const void* ref, long long ref_ps, void* out, long long out_ps, const float* d_scale, void* out16,
-                 long long out16_ps, const void* ref_bits, pgk_stream_t stream);
+                 long long out16_ps, pgk_stream_t stream);
 /* out = a*x + b*y (y optional) on planes with `count` elements per plane */
 int pgk_axpby(const void* x, long long x_ps, float a, const void* y, long long y_ps, float b, int P, long long count,
               void* out, long long out_ps, pgk_stream_t stream);

@@ -35,8 +35,8 @@ SIGNATURES = {
     'pgk_to_rgb': [P, I, L, I, I, I, I, P, F, P, F, P, L, I, P, F, P, F, I, P, P, P],
     'pgk_to_rgb_dgrad': [P, I, I, I, I, I, P, F, F, I, P, I, L, P],
     'pgk_rgb_wgrad': [P, I, P, I, L, I, I, I, I, I, I, I, F, F, P, I, I, P, P, P],
-    'pgk_pool2': [P, L, I, I, I, I, I, I, F, P, L, F, P, L, P, P, P, L, P],
-    'pgk_mask_mul': [P, L, I, I, I, I, I, I, F, P, L, P, L, P, P, L, P],
+    'pgk_pool2': [P, L, I, I, I, I, I, I, F, P, L, F, P, L, P, P, P, L],
+    'pgk_mask_mul': [P, L, I, I, I, I, I, I, F, P, L, P, L, P, P, L],
     'pgk_axpby': [P, L, F, P, L, F, I, L, P, L],
     'pgk_pixelnorm': [P, L, I, L, I, P, L, P, P, L],
     'pgk_pixelnorm_bwd': [P, L, P, L, P, I, L, I, P, L],

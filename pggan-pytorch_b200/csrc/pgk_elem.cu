@@ -737,20 +737,6 @@ __global__ void __launch_bounds__(256, NARROW ? 3 : 1) rgb_wgrad_kernel(RgbWgrad
 // two for every layer of the reference's networks (network.py:94-95), so the item -> (n, y, x, chunk) split is shifts
 // and masks (P2 = true, 32-bit); the generic flavour divides in 64 bits, which alone held these kernels at ~40 % of
 // the HBM bandwidth (three 64-bit divisions per 16-byte store).
-// bit j = (element j of 8 packed bf16 values > 0): what lrelu_grad decides on
-__device__ __forceinline__ uint32_t positive_bits8(const uint4& q) {
-    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-    uint32_t m = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t lo = w[k] & 0xFFFFu, hi = w[k] >> 16;
-        // (v > 0: sign clear, magnitude non-zero and not a NaN -- exactly `v > 0.f`)
-        m |= (uint32_t)(lo != 0 && lo <= 0x7F80u) << (2 * k);
-        m |= (uint32_t)(hi != 0 && hi <= 0x7F80u) << (2 * k + 1);
-    }
-    return m;
-}
-
 template <bool P2>
 struct PixSplit {
     int nch, W, H, lnch, lw, lh;
@@ -783,8 +769,7 @@ static inline int log2_exact(int v) {
 
 template <bool P2>
 __global__ void __launch_bounds__(256) pool2_kernel(Planes src, int N, PixSplit<P2> sp, int C, float a, Planes other,
-                                                    int has_other, float b, Planes out, const float* da, const float* db, H16Out h16,
-                                                    uint32_t* __restrict__ bits) {
+                                                    int has_other, float b, Planes out, const float* da, const float* db, H16Out h16) {
     pgk_pdl_enter();
     const int H = sp.H, W = sp.W;
     const long long total = (long long)N * H * W * sp.nch;
@@ -801,16 +786,6 @@ __global__ void __launch_bounds__(256) pool2_kernel(Planes src, int N, PixSplit<
         ld8(src, b00 + C, f1);
         ld8(src, b00 + (long long)2 * W * C, f2);
         ld8(src, b00 + (long long)2 * W * C + C, f3);
-        if (bits) {
-            // side output for the backward pass: the sign decisions of the four source pixels (plane 0, as every mask
-            // reader takes them), 8 channels x 4 pixels = one word per output element group -- the backward chain's
-            // "unpool x mask" then reads 4 bytes where it read 64 (pgk_mask_mul: bits_ref)
-            const uint4* s0 = reinterpret_cast<const uint4*>(src.p + b00);
-            const uint4* s2 = reinterpret_cast<const uint4*>(src.p + b00 + (long long)2 * W * C);
-            bits[idx] = positive_bits8(__ldg(s0)) | (positive_bits8(__ldg(reinterpret_cast<const uint4*>(src.p + b00 + C))) << 8) |
-                        (positive_bits8(__ldg(s2)) << 16) |
-                        (positive_bits8(__ldg(reinterpret_cast<const uint4*>(src.p + b00 + (long long)2 * W * C + C))) << 24);
-        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = sa * ((f0[j] + f1[j]) + (f2[j] + f3[j]));
         long long o = pix * C + chunk * 8;
@@ -826,8 +801,7 @@ __global__ void __launch_bounds__(256) pool2_kernel(Planes src, int N, PixSplit<
 
 template <bool P2>
 __global__ void __launch_bounds__(256) mask_mul_kernel(Planes src, int N, PixSplit<P2> sp, int C, int ups, float scale,
-                                                       Planes ref, int has_ref, Planes out, const float* dscale, H16Out h16,
-                                                       const uint32_t* __restrict__ bits) {
+                                                       Planes ref, int has_ref, Planes out, const float* dscale, H16Out h16) {
     pgk_pdl_enter();
     scale *= dscale ? __ldg(dscale) : 1.f;
     const int H = sp.H, W = sp.W;
@@ -841,14 +815,7 @@ __global__ void __launch_bounds__(256) mask_mul_kernel(Planes src, int N, PixSpl
         float f[8];
         ld8(src, ((((long long)n * Hs + (y >> ups)) * Ws) + (x >> ups)) * C + chunk * 8, f);
         long long o = pix * C + chunk * 8;
-        if (bits) {
-            // (ups = 1) the reference's sign decisions as pgk_pool2 packed them: word of the parent pixel, byte of this
-            // pixel's quadrant
-            const uint32_t wd = __ldg(bits + ((((long long)n * Hs + (y >> 1)) * Ws) + (x >> 1)) * sp.nch + chunk);
-            const uint32_t mb = wd >> (8 * (((y & 1) << 1) | (x & 1)));
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] *= scale * (((mb >> j) & 1u) ? 1.f : PGK_LRELU);
-        } else if (has_ref) {
+        if (has_ref) {
             float m[8];
             Planes r0 = ref;   // the sign of plane 0 is the sign of the value
             r0.P = 1;
@@ -1695,9 +1662,8 @@ extern "C" int pgk_rgb_wgrad(const float* img, int img_n0, const void* t, int P,
 
 extern "C" int pgk_pool2(const void* src, long long src_ps, int P, int N, int H, int W, int C, int avg, float a,
                          const void* other, long long other_ps, float b, void* out, long long out_ps, const float* d_a,
-                         const float* d_b, void* out16, long long out16_ps, void* src_bits, pgk_stream_t stream) {
+                         const float* d_b, void* out16, long long out16_ps, pgk_stream_t stream) {
     const H16Out h16 = {(__half*)out16, out16_ps};
-    PGK_REQUIRE(!src_bits || (((uintptr_t)src & 15) == 0 && (P == 1 || (src_ps * 2) % 16 == 0)), "pgk_pool2: src alignment");
     PGK_REQUIRE(C % 8 == 0, "pgk_pool2: C must be a multiple of 8");
     long long total = (long long)N * H * W * (C >> 3);
     const int lnch = log2_exact(C >> 3), lw = log2_exact(W), lh = log2_exact(H);
@@ -1706,13 +1672,11 @@ extern "C" int pgk_pool2(const void* src, long long src_ps, int P, int N, int H,
     if (lnch >= 0 && lw >= 0 && lh >= 0 && total < (1ll << 31)) {
         PixSplit<true> sp = {C >> 3, W, H, lnch, lw, lh};
         pgk_launch(pool2_kernel<true>, grid, 256, 0, ST, make_planes(src, src_ps, P), N, sp, C, sa,
-                   make_planes(other, other_ps, P), other != nullptr, b, make_planes(out, out_ps, P), d_a, d_b, h16,
-                   (uint32_t*)src_bits);
+                   make_planes(other, other_ps, P), other != nullptr, b, make_planes(out, out_ps, P), d_a, d_b, h16);
     } else {
         PixSplit<false> sp = {C >> 3, W, H, 0, 0, 0};
         pgk_launch(pool2_kernel<false>, grid, 256, 0, ST, make_planes(src, src_ps, P), N, sp, C, sa,
-                   make_planes(other, other_ps, P), other != nullptr, b, make_planes(out, out_ps, P), d_a, d_b, h16,
-                   (uint32_t*)src_bits);
+                   make_planes(other, other_ps, P), other != nullptr, b, make_planes(out, out_ps, P), d_a, d_b, h16);
     }
     PGK_LAUNCH_CHECK("pgk_pool2");
     return PGK_OK;
@@ -1720,10 +1684,9 @@ extern "C" int pgk_pool2(const void* src, long long src_ps, int P, int N, int H,
 
 extern "C" int pgk_mask_mul(const void* src, long long src_ps, int P, int N, int H, int W, int C, int ups, float scale,
                             const void* ref, long long ref_ps, void* out, long long out_ps, const float* d_scale,
-                            void* out16, long long out16_ps, const void* ref_bits, pgk_stream_t stream) {
+                            void* out16, long long out16_ps, pgk_stream_t stream) {
     const H16Out h16 = {(__half*)out16, out16_ps};
     PGK_REQUIRE(C % 8 == 0, "pgk_mask_mul: C must be a multiple of 8");
-    PGK_REQUIRE(!ref_bits || ups, "pgk_mask_mul: ref_bits are the words pgk_pool2 wrote (ups = 1 only)");
     PGK_REQUIRE(!ups || (H % 2 == 0 && W % 2 == 0), "pgk_mask_mul: ups needs even H, W");
     long long total = (long long)N * H * W * (C >> 3);
     const int lnch = log2_exact(C >> 3), lw = log2_exact(W), lh = log2_exact(H);
@@ -1731,13 +1694,11 @@ extern "C" int pgk_mask_mul(const void* src, long long src_ps, int P, int N, int
     if (lnch >= 0 && lw >= 0 && lh >= 0 && total < (1ll << 31)) {
         PixSplit<true> sp = {C >> 3, W, H, lnch, lw, lh};
         pgk_launch(mask_mul_kernel<true>, grid, 256, 0, ST, make_planes(src, src_ps, P), N, sp, C, ups, scale,
-                   make_planes(ref, ref_ps, P), ref != nullptr, make_planes(out, out_ps, P), d_scale, h16,
-                   (const uint32_t*)ref_bits);
+                   make_planes(ref, ref_ps, P), ref != nullptr, make_planes(out, out_ps, P), d_scale, h16);
     } else {
         PixSplit<false> sp = {C >> 3, W, H, 0, 0, 0};
         pgk_launch(mask_mul_kernel<false>, grid, 256, 0, ST, make_planes(src, src_ps, P), N, sp, C, ups, scale,
-                   make_planes(ref, ref_ps, P), ref != nullptr, make_planes(out, out_ps, P), d_scale, h16,
-                   (const uint32_t*)ref_bits);
+                   make_planes(ref, ref_ps, P), ref != nullptr, make_planes(out, out_ps, P), d_scale, h16);
     }
     PGK_LAUNCH_CHECK("pgk_mask_mul");
     return PGK_OK;

@@ -232,28 +232,12 @@ def rgb_wgrad(img, img_n0, t, n, c, h, w, pool, scale_w, scale_b, dw, sa, sk, co
          None if imgsum is None else imgsum.data_ptr(), dscale)
 
 
-# The backward chain's "unpool x 0.25 x LeakyReLU mask" reads the sign decisions of a D block's output as one 32-bit word
-# per 8 channels x 2x2 pixels, written by the forward pool2 that reads that output anyway (include/pgk.h: src_bits /
-# ref_bits), instead of the full-resolution tensor; PGK_MASK_BITS=0 for A/B runs.
-MASK_BITS = os.environ.get('PGK_MASK_BITS', '1') == '1'
-
-
-def pool2(src, out, avg=1, a=1.0, other=None, b=0.0, h16=False, bits=False):
-    """bits=True: also store src's sign decisions in src.aux['bits'] (int32, one word per output element group of the
-    whole storage; valid for the samples this call covers) for mask_mul(..., ref=src, ups=1)."""
+def pool2(src, out, avg=1, a=1.0, other=None, b=0.0, h16=False):
     op, ops = _mask(other)
     (a, da), (b, db) = _sc(a), _sc(b)
     o16, o16_ps = _h16_out(out, h16)
-    bp = None
-    if bits and MASK_BITS:
-        words = out.per // 8
-        t = src.aux.get('bits')
-        if t is None or t.numel() != src.ntot * words:
-            t = src.aux['bits'] = torch.empty(src.ntot * words, dtype=torch.int32, device=src.t.device)
-        src.aux['bits_range'] = (src.off, src.off + src.N)
-        bp = t.data_ptr() + 4 * src.off * words
     call('pgk_pool2', src.ptr, src.ps, src.P, out.N, out.H, out.W, out.C, avg, a, op, ops, b, out.ptr, out.ps, da, db,
-         o16, o16_ps, bp)
+         o16, o16_ps)
     return out
 
 
@@ -261,15 +245,8 @@ def mask_mul(src, out, ref=None, ups=0, scale=1.0, h16=False):
     rp, rps = _mask(ref)
     scale, dscale = _sc(scale)
     o16, o16_ps = _h16_out(out, h16)
-    bp = None
-    if ref is not None and ups and MASK_BITS:
-        t, rng = ref.aux.get('bits'), ref.aux.get('bits_range')
-        words = ref.per // 32                      # one word per 8 channels of a 2x2 block
-        if t is not None and rng is not None and rng[0] <= ref.off and ref.off + ref.N <= rng[1] \
-                and t.numel() == ref.ntot * words:
-            bp = t.data_ptr() + 4 * ref.off * words
     call('pgk_mask_mul', src.ptr, src.ps, src.P, out.N, out.H, out.W, out.C, ups, scale, rp, rps, out.ptr, out.ps,
-         dscale, o16, o16_ps, bp)
+         dscale, o16, o16_ps)
     return out
 
 
@@ -578,9 +555,9 @@ class DEngine(object):
                 T.xlow = pool_img(ximg)
                 T.f = new(r // 2, w2.cout)
                 from_rgb(T.xlow, self.blk(depth).fromRGB, T.f.sl(0, B))
-                pool2(T.t2.sl(0, B), h.sl(0, B), avg=1, a=T.fd.a(), other=T.f.sl(0, B), b=T.fd.b(), h16=True, bits=True)
+                pool2(T.t2.sl(0, B), h.sl(0, B), avg=1, a=T.fd.a(), other=T.f.sl(0, B), b=T.fd.b(), h16=True)
             else:
-                pool2(T.t2.sl(0, B), h.sl(0, B), avg=1, h16=True, bits=True)
+                pool2(T.t2.sl(0, B), h.sl(0, B), avg=1, h16=True)
             res = r // 2
             for k in range(depth, 1, -1):
                 b = self.blk(k)
@@ -590,7 +567,7 @@ class DEngine(object):
                 b_ = new(res, w2.cout)
                 conv(a_.sl(0, B), w2.F, w2.cout, 3, b_.sl(0, B), bias=w2.bias, act=1, fwd=True)
                 hn = new(res // 2, w2.cout)
-                pool2(b_.sl(0, B), hn.sl(0, B), avg=1, h16=True, bits=True)
+                pool2(b_.sl(0, B), hn.sl(0, B), avg=1, h16=True)
                 T.blocks.append(SimpleNamespace(mod=b, hin=h, a=a_, b=b_, res=res))
                 h, res = hn, res // 2
             hin = h

@@ -335,39 +335,3 @@ def test_narrow_image_kernels_are_the_generic_ones_bit_for_bit(K, C):
             continue
         a, b = (a.view(torch.int16), b.view(torch.int16)) if a.dtype == torch.bfloat16 else (a, b)
         assert torch.equal(a, b), 'output %d differs' % i
-
-
-@pytest.mark.parametrize('P,C,H,W', [(1, 8, 16, 32), (3, 64, 8, 8), (1, 32, 12, 24), (2, 16, 6, 10)])
-def test_mask_bits_equal_the_reference_tensor(P, C, H, W):
-    """pgk_pool2's side output (the LeakyReLU decisions of its source, one word per 8 channels x 2x2 pixels) read by
-    pgk_mask_mul(ups=1) against the same call reading the full-resolution reference tensor: equal bits, including
-    zeros and negative zeros in the reference (lrelu'(0) = 0.2)."""
-    import torch
-    sys.path.insert(0, ROOT)
-    import pggan_b200  # noqa: F401
-    E = importlib.import_module('pggan-pytorch_b200.engine')
-    torch.manual_seed(P * 100 + C)
-    n, dev = 5, 'cuda'
-    v = torch.randn(n, C, 2 * H, 2 * W, device=dev)
-    v[torch.rand_like(v) < 0.1] = 0.0
-    v[torch.rand_like(v) < 0.05] = -0.0
-    src = E.PT.from_float(v, P)
-    store = E.PT.empty(n + 2, 2 * H, 2 * W, C, P, dev)       # a slice of a larger storage, as the tape's tensors are
-    store.t.zero_()
-    store.sl(1, 1 + n).t.view(P, n + 2, -1)[:, 1:1 + n] = src.t.view(P, n, -1)
-    ref = store.sl(1, 1 + n)
-    pooled = E.PT.empty(n, H, W, C, P, dev)
-    old = E.MASK_BITS
-    try:
-        E.MASK_BITS = True
-        E.pool2(ref, pooled, avg=1, bits=True)
-        assert 'bits' in ref.aux
-        d = E.PT.from_float(torch.randn(3, C, H, W, device=dev), min(P, 2))
-        sub = store.sl(2, 5)                                 # samples 1..3 of the pooled range
-        out_bits = E.mask_mul(d, E.PT.empty(3, 2 * H, 2 * W, C, min(P, 2), dev), ref=sub, ups=1, scale=0.25)
-        E.MASK_BITS = False
-        out_ref = E.mask_mul(d, E.PT.empty(3, 2 * H, 2 * W, C, min(P, 2), dev), ref=sub, ups=1, scale=0.25)
-    finally:
-        E.MASK_BITS = old
-    torch.cuda.synchronize()
-    assert torch.equal(out_bits.t.view(torch.int16), out_ref.t.view(torch.int16))
