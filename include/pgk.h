@@ -154,6 +154,14 @@ int pgk_conv(const void* x, int P, int Pr, long long x_ps, int N, int H, int W, 
              const float* pos_s, int act, const void* mask_ref, long long mask_ps, float out_scale, void* out,
              long long out_ps, float* pn_r, pgk_stream_t stream);
 
+/* The row-streaming thin-layer kernel called directly (pgk_conv dispatches to it for Cin in {8, 16, 32}).  Additionally,
+ * in the one-plane mode (P = Pr = 1), Cin = 64 with Cout in {32, 64}: layers that pgk_conv gives to the wide kernel, where
+ * an MMA of N = 32 ... 64 runs at a quarter of the tensor rate; here the three filter rows are stacked along N.  wpack:
+ * pgk_pack_thin's packing (wpack_ps = pgk_pack_thin_plane_elems(Cin, Cout)); arguments otherwise as pgk_conv's. */
+int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N, int H, int W, int Cin, int Cout, const void* wpack,
+                  long long wpack_ps, const float* bias, int act, const void* mask_ref, long long mask_ps, float out_scale,
+                  void* out, long long out_ps, float* pn_r, pgk_stream_t stream);
+
 /* ---- forward convolution on IEEE-half operand planes (experimental; fp32-faithful modes only) ----------------------
  * The fp32-faithful mode pays six bf16 products per forward FLOP (three planes, i + j <= 2) because two bf16 planes
  * (16 bits) flip too many LeakyReLU units.  Two fp16 planes carry 22 bits, so the three products hi*hi, hi*lo, lo*hi

@@ -22,6 +22,7 @@ SIGNATURES = {
     'pgk_unprep_grad': [P, F, I, I, I, I, I, P, I],
     'pgk_pack_operand': [P, I, I, P, L, I],
     'pgk_pack_thin': [P, I, I, P, L, I],
+    'pgk_conv_thin': [P, I, I, L, I, I, I, I, I, P, L, P, I, P, L, F, P, L, P],
     'pgk_prep_multi': [P, I],
     'pgk_unprep_multi': [P, I],
     'pgk_conv': [P, I, I, L, I, I, I, I, I, I, I, P, P, L, P, P, P, I, P, L, F, P, L, P],

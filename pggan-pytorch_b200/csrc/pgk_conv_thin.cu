@@ -97,7 +97,7 @@ struct ThinCols {
 };
 
 template <int CIN, int P, int SPLIT, int NPAD, int STK>
-__global__ void __launch_bounds__(kThinThreads, 2) conv_thin_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(kThinThreads, CIN == 64 ? 1 : 2) conv_thin_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const __grid_constant__ CUtensorMap tmO,
                                                                     const ThinArgs a) {
     static_assert(!STK || (P == 1 && SPLIT == 0), "the input-row-stationary flavour exists for the one-plane mode only");
@@ -660,7 +660,7 @@ extern "C" long long pgk_pack_thin_plane_elems(int Cin, int Cout) {
 
 extern "C" int pgk_pack_thin(const float* w, int Cin, int Cout, void* out, long long out_ps, int P,
                              pgk_stream_t stream) {
-    PGK_REQUIRE((Cin == 8 || Cin == 16 || Cin == 32) && Cout % 8 == 0 && Cout >= 8 && Cout <= 64 && P >= 1 && P <= 3,
+    PGK_REQUIRE((Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64) && Cout % 8 == 0 && Cout >= 8 && Cout <= 64 && P >= 1 && P <= 3,
                 "pgk_pack_thin: unsupported shape (Cin %d Cout %d)", Cin, Cout);
     const int npad = Cout < 16 ? 16 : Cout;
     const int steps = Cin == 8 ? 6 : 9 * (Cin / 16);
@@ -788,7 +788,12 @@ extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N
                              pgk_stream_t stream) {
     PGK_REQUIRE(!pn_r || (pgk_conv_thin_fuses_pixelnorm(Cout) && !mask_ref && out_scale == 1.0f),
                 "pgk_conv_thin: the fused pixel norm needs Cout <= 32, no mask and out_scale 1");
-    PGK_REQUIRE(pgk_conv_thin_supported(N, H, W, Cin, Cout, 3, 0), "pgk_conv_thin: unsupported shape");
+    // 64 input channels (one-plane mode, Cout 32 / 64): not part of pgk_conv's dispatch -- those layers belong to the wide
+    // kernel's channel counts, where a tcgen05.mma of N = 32 ... 64 runs at a quarter of the tensor rate (c3: 0.26-0.44 of
+    // the peak); the row-streaming kernel stacks the three filter rows along N and is bound by HBM instead.  The caller
+    // asks for it explicitly with an operand packed by pgk_pack_thin.
+    const bool wide64 = Cin == 64 && P == 1 && Pr == 1 && (Cout == 32 || Cout == 64) && W % 128 == 0 && H >= 8 && H % 8 == 0 && N > 0;
+    PGK_REQUIRE(wide64 || pgk_conv_thin_supported(N, H, W, Cin, Cout, 3, 0), "pgk_conv_thin: unsupported shape");
     PGK_REQUIRE(P >= 1 && P <= 3 && Pr >= 1 && Pr <= P, "pgk_conv_thin: need 1 <= Pr <= P <= 3");
     ThinArgs a;
     a.N = N, a.H = H, a.W = W, a.Cout = Cout;
@@ -871,6 +876,7 @@ extern "C" int pgk_conv_thin(const void* x, int P, int Pr, long long x_ps, int N
     PGK_THIN_STK_CASE(8, 16) PGK_THIN_STK_CASE(8, 32) PGK_THIN_STK_CASE(8, 64)
     PGK_THIN_STK_CASE(16, 16) PGK_THIN_STK_CASE(16, 32) PGK_THIN_STK_CASE(16, 64)
     PGK_THIN_STK_CASE(32, 16) PGK_THIN_STK_CASE(32, 32) PGK_THIN_STK_CASE(32, 64)
+    PGK_THIN_STK_CASE(64, 32) PGK_THIN_STK_CASE(64, 64)
 #undef PGK_THIN_STK_CASE
 #define PGK_THIN_CASE_N(C_, P_, S_, N_) \
     if (rc == PGK_ERR_ARG && Cin == C_ && Pr == P_ && a.split_acc == S_ && a.Npad == N_) rc = launch_thin<C_, P_, S_, N_, 0>(tmA, tmO, a, st);

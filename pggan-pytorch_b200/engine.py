@@ -36,6 +36,12 @@ FWD_FP16 = os.environ.get('PGK_FWD_FP16', '1') == '1'
 # Producers of a tensor that such a conv reads next (from_rgb, pool2, the materialised upsample, the pixel norm) write
 # the fp16 planes themselves (include/pgk.h: out16), which saves the pgk_cvt_fp16x2 pass; PGK_FUSE_CVT=0 for A/B runs.
 FUSE_CVT = os.environ.get('PGK_FUSE_CVT', '1') == '1'
+# 3x3 layers with 64 input channels and 32 / 64 output channels at W >= 128 (the 256^2 / 512^2 levels' 64 -> 32 and the
+# 128^2 / 256^2 levels' 64 -> 64 convs and data gradients), one-plane mode: the wide kernel runs them at a quarter of
+# the tensor rate (a tcgen05.mma of N = 32 ... 64 costs what one of N = 128 does; c3: 0.26-0.44 of the peak), the
+# row-streaming thin kernel stacks the three filter rows along N and is bound by HBM.  Fourth element of the operand
+# tuples: the layer's pgk_pack_thin packing.  PGK_THIN64=0 for A/B runs.
+THIN64 = os.environ.get('PGK_THIN64', '1') == '1'
 # diagnostic knobs of the fault hunt
 _FP16_NOPOS = os.environ.get('PGK_FP16_NOPOS', '0') == '1'
 _FP16_MINPIX = int(os.environ.get('PGK_FP16_MINPIX', '0'))
@@ -188,6 +194,16 @@ def conv(x, w, cout, ks, out, ups=0, bias=None, posT=None, pos_s=None, act=0, ma
             call('pgk_pixelnorm', out.ptr, out.ps, out.P, out.N * out.H * out.W, out.C, out.ptr, out.ps,
                  pn_r.data_ptr(), o16, o16_ps)
         return out
+    if (len(w) > 3 and w[3] is not None and x.P == 1 and out.P == 1 and x.C == 64 and ks == 3 and not ups and posT is None
+            and out.W % 128 == 0 and out.H % 8 == 0 and out.H >= 8 and (mask is None or mask.P == 1)):
+        fuse_pn = pn_r is not None and cout <= 32 and mask is None and scale == 1.0
+        call('pgk_conv_thin', x.ptr, 1, 1, x.ps, out.N, out.H, out.W, 64, cout, w[3].data_ptr(), w[3].stride(0),
+             None if bias is None else bias.data_ptr(), act, mp, mps, scale, out.ptr, out.ps,
+             pn_r.data_ptr() if fuse_pn else None)
+        if pn_r is not None and not fuse_pn:
+            call('pgk_pixelnorm', out.ptr, out.ps, out.P, out.N * out.H * out.W, out.C, out.ptr, out.ps, pn_r.data_ptr(),
+                 None, 0)
+        return out
     call('pgk_conv', x.ptr, x.P, x.P if fwd else min(x.P, GRAD_PLANES), x.ps, out.N, out.H, out.W, x.C, cout, ks, ups,
          None if wf is None else wf.data_ptr(), wt.data_ptr(),
          wt.stride(0), None if bias is None else bias.data_ptr(), None if posT is None else posT.data_ptr(),
@@ -293,9 +309,13 @@ class ConvW(object):
         # thin layers (csrc/pgk_conv_thin.cu) take their own packing; the data-gradient operand swaps the roles
         thin = lambda ci, co: kind == W_CONV and ks == 3 and ci in (8, 16, 32) and co in (8, 16, 32, 64)
         self.thin_f, self.thin_b = thin(cin, cout), thin(cout, cin)
-        # the fp32 operands are read by the CUDA-core kernels only: shapes that always take a tensor-core kernel skip them
-        self.need_wf_f = not _tc_channels(*gf)
-        self.need_wf_b = need_wb and not _tc_channels(*gb)
+        # 64-input-channel layers the thin kernel takes over in the one-plane mode (THIN64): a second, thin packing
+        t64 = lambda ci, co: THIN64 and kind == W_CONV and ks == 3 and ci == 64 and co in (32, 64)
+        self.t64_f, self.t64_b = t64(cin, cout), need_wb and t64(cout, cin)
+        # the fp32 operands are read by the CUDA-core kernels only: shapes that always take a tensor-core kernel skip
+        # them (the thin packing of the 64-channel layers is made from them)
+        self.need_wf_f = self.t64_f or not _tc_channels(*gf)
+        self.need_wf_b = need_wb and (self.t64_b or not _tc_channels(*gb))
 
     @property
     def weight(self):
@@ -328,6 +348,9 @@ class ConvW(object):
         if FWD_FP16 and not self.thin_f:
             # third element of the forward operand tuple: [2 planes][output channel][K] IEEE half, times 2^PGK_FP16_WSHIFT
             self.F = (self.wf, ft, torch.empty((2, nf_, kf), dtype=torch.float16, device=dev))
+        if self.t64_f:
+            f64 = torch.zeros((1, lib.pgk_pack_thin_plane_elems(self.cin, self.cout)), dtype=BF16, device=dev)
+            self.F = (self.F + (None,))[:3] + (f64,)
         self.B = None
         if self.need_wb:
             if self.thin_b:
@@ -335,6 +358,9 @@ class ConvW(object):
             else:
                 bt = torch.empty((3, nb, kb), dtype=BF16, device=dev)
             self.B = (self.wb, bt)
+            if self.t64_b:
+                b64 = torch.zeros((1, lib.pgk_pack_thin_plane_elems(self.cout, self.cin)), dtype=BF16, device=dev)
+                self.B = (self.wb, bt, None, b64)
 
     def fill(self, d, planes):
         """Fill one PgkPrepLayer (include/pgk.h) for this layer; allocates the operand buffers on first use."""
@@ -350,7 +376,7 @@ class ConvW(object):
             d.B, d.B_ps, d.thinB = self.B[1].data_ptr(), self.B[1].stride(0), int(self.thin_b)
         else:
             d.B, d.B_ps, d.thinB = None, 0, 0
-        if len(self.F) > 2 and planes >= 2:      # (the half packing is read by the fp32-faithful mode only)
+        if len(self.F) > 2 and self.F[2] is not None and planes >= 2:   # (the half packing: fp32-faithful mode only)
             d.F16, d.F16_ps = self.F[2].data_ptr(), self.F[2].stride(0)
         else:
             d.F16, d.F16_ps = None, 0
@@ -363,6 +389,11 @@ class ConvW(object):
                  self.pos_hw[1], self.posT.data_ptr())
         if self.kind == W_GFIRST:
             self.bias16 = self.bias.detach().repeat(16)
+        if planes == 1:      # (the thin packing of the 64-channel layers is read by the one-plane mode only)
+            if self.t64_f:
+                call('pgk_pack_thin', self.wf.data_ptr(), self.cin, self.cout, self.F[3].data_ptr(), self.F[3].stride(0), 1)
+            if self.t64_b:
+                call('pgk_pack_thin', self.wb.data_ptr(), self.cout, self.cin, self.B[3].data_ptr(), self.B[3].stride(0), 1)
         self.version = (w._version, w.data_ptr(), self.bias._version, self.mod.cf, planes)
         self.cap_epoch = CAPTURE_EPOCH
 

@@ -27,6 +27,7 @@ What is compared with what, and why there are two kinds of gradient test:
 `PGK_PARITY_REPORT=<file>` appends the measured numbers as JSON lines.
 """
 import json
+import importlib
 import os
 import sys
 
@@ -211,6 +212,9 @@ def pn_fused_fn(pg, G, n):
             w = getattr(b, c).conv.weight
             cout, cin, ks = w.shape[0], w.shape[1], w.shape[2]
             thin = ks == 3 and lib.pgk_conv_thin_supported(n, res, res, cin, cout, 3, 0)
+            # (engine.THIN64: 64 -> 32 / 64 layers of the one-plane mode run on the thin kernel at W >= 128)
+            E_ = importlib.import_module('pggan-pytorch_b200.engine')
+            thin = thin or (E_.THIN64 and ks == 3 and cin == 64 and cout in (32, 64) and res % 128 == 0)
             if thin:
                 fused = lib.pgk_conv_thin_fuses_pixelnorm(cout)
             else:

@@ -41,6 +41,12 @@ THIN_CONV = [
     (2, 8, 128, 8, 32, 1, dict(mask=True)),
     (1, 24, 384, 16, 64, 3, {}),
     (9, 64, 128, 32, 8, 2, dict(mask=True, fwd=False)),
+    # 64 input channels on the thin kernel (one-plane mode; engine.THIN64)
+    (2, 128, 128, 64, 32, 1, {}),
+    (3, 256, 256, 64, 32, 1, dict(mask=True, act=0, bias=False, fwd=False)),
+    (2, 128, 256, 64, 64, 1, {}),
+    (5, 128, 128, 64, 64, 1, dict(mask=True, act=0, bias=False, scale=0.25, fwd=False)),
+    (1, 8, 128, 64, 32, 1, dict(mask=True)),
 ]
 
 

@@ -35,6 +35,12 @@ def conv_case(N, H, W, Cin, Cout, KS, P, act=1, mask=False, bias=True, scale=1.0
     else:
         wt = torch.empty(3, Cout, K, dtype=BF16, device='cuda')
         call('pgk_pack_operand', wf.data_ptr(), K, Cout, wt.data_ptr(), wt.stride(0), 3)
+    w_tc = (wf, wt)
+    if KS == 3 and Cin == 64 and Cout in (32, 64) and P == 1 and W % 128 == 0:
+        # the one-plane mode's 64-channel layers on the thin kernel (engine.THIN64): fourth element = thin packing
+        w64 = torch.zeros(1, lib.pgk_pack_thin_plane_elems(Cin, Cout), dtype=BF16, device='cuda')
+        call('pgk_pack_thin', wf.data_ptr(), Cin, Cout, w64.data_ptr(), w64.stride(0), 1)
+        w_tc = (wf, wt, None, w64)
     b = torch.randn(Cout, device='cuda', generator=g) if bias else None
     xp = E.PT.from_float(x, P)
     m = E.PT.from_float(torch.randn(N, Cout, H, W, device='cuda', generator=g), P) if mask else None
@@ -45,7 +51,8 @@ def conv_case(N, H, W, Cin, Cout, KS, P, act=1, mask=False, bias=True, scale=1.0
         lib.pgk_set_tc(tcon)
         o = E.PT.empty(N, H, W, Cout, P, 'cuda')
         o.t.fill_(float('nan'))
-        E.conv(xp, (wf, wt), Cout, KS, o, bias=b, posT=posT, pos_s=pos_s, act=act, mask=m, scale=scale, fwd=fwd)
+        E.conv(xp, w_tc if tcon else (wf, wt), Cout, KS, o, bias=b, posT=posT, pos_s=pos_s, act=act, mask=m, scale=scale,
+               fwd=fwd)
         torch.cuda.synchronize()
         outs.append(o.float())
     lib.pgk_set_tc(1)
