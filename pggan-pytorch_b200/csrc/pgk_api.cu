@@ -36,6 +36,9 @@ extern "C" int pgk_conv_thin_fuses_pixelnorm(int Cout);
 
 extern "C" int pgk_wgrad_thin_supported(int H, int W, int Cin, int Cout, int KS, int ups, int ngroups, int group_n,
                                         int Pr);
+int pgk_wgrad_thin_direct(const void* x, const void* g, int H, int W, int Cin, int cin_total, int c0, int Cout,
+                          int cout_total, int co0, int ngroups, int group_n, const int* xoff, const int* goff, float* dwp,
+                          float* db, unsigned bias_mask, pgk_stream_t stream);
 extern "C" int pgk_wgrad_thin(const void* x, long long x_ps, const void* g, long long g_ps, int P, int Pr, int H, int W,
                               int Cin, int cin_total, int c0, int Cout, int ngroups, int group_n, const int* xoff,
                               const int* goff, float* dwp, float* db, unsigned bias_mask, pgk_stream_t stream);
@@ -178,6 +181,28 @@ extern "C" int pgk_wgrad(const void* x, long long x_ps, const void* g, long long
     PGK_REQUIRE(ngroups >= 1 && ngroups <= 4, "pgk_wgrad: 1..4 groups");
     const double flops = 2.0 * ngroups * group_n * H * W * (double)Cout * KS * KS * Cin;
     const double bytes = 2.0 * ngroups * group_n * H * W * ((double)Cin / (ups ? 4 : 1) + Cout) * Pr;
+    // one-plane mode, 64 input channels at W >= 128: the transposer-free thin kernel reads every X row once, where the
+    // wide kernel re-loads a shifted box per tap (9 x the X traffic: 0.35-0.40 of the tensor peak on these shapes, bound by
+    // L2 bandwidth).  Output channels in windows of 64 (PGK_WGRAD64=0: the wide kernel, for A/B runs).
+    {
+        static int w64 = -1;
+        if (w64 < 0) {
+            const char* e = getenv("PGK_WGRAD64");
+            w64 = e ? atoi(e) != 0 : 1;
+        }
+        if (w64 && tc_enabled() && Cin == 64 && P == 1 && Pr == 1 && KS == 3 && !ups && (Cout == 32 || Cout == 64 || Cout == 128) &&
+            W % 128 == 0 && H >= 8 && H % 8 == 0 && (((uintptr_t)x | (uintptr_t)g) & 15) == 0) {
+            ProfScope prof(PGK_PROF_WGRAD_THIN, flops, bytes, stream, Pr);
+            const int cw = Cout == 32 ? 32 : 64;
+            for (int co0 = 0; co0 < Cout; co0 += cw) {
+                int rc = pgk_wgrad_thin_direct(x, g, H, W, 64, 64, 0, cw, Cout, co0, ngroups, group_n, xoff, goff, dwp, db,
+                                               bias_groups, stream);
+                if (rc) return rc;
+                PGK_LAUNCH_CHECK("pgk_wgrad(thin tcgen05, direct, 64 channels)");
+            }
+            return PGK_OK;
+        }
+    }
     // thin layers: the bias gradient rides along as one more accumulator row (a 64-channel input = two launches)
     const int thin_cin = Cin == 64 ? 32 : Cin;
     if (tc_enabled() && (Cin != 64 || Cout < 64) &&

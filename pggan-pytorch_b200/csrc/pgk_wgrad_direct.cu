@@ -42,6 +42,7 @@ struct WDirArgs {
     int rx, rx_log2, rg, rg_log2;   // ring depths (powers of two); the G ring has two mirror slots behind it
     uint32_t off_g, off_bars;       // byte offsets from the 1024-aligned base (the X ring starts at 0)
     int cin_total, c0;              // this launch handles input channels [c0, c0 + CIN) of cin_total
+    int cout_total, co0;            // ... and output channels [co0, co0 + COUT) of cout_total (a.Cout = cout_total)
     float* dwp;
     float* db;                      // optional fused bias gradient over the groups in bias_mask
     unsigned bias_mask;
@@ -77,7 +78,7 @@ wgrad_direct_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     constexpr int N = 3 * CIN;
     constexpr int M0 = COUT <= 16 ? 64 : 128;      // first MMA: 8 / 4 / 4 / 2 slots of 8 / 16 / 32 / 64 channels
     constexpr bool TWO = COUT == 64;               // second MMA (M = 64): the third slot of the window
-    constexpr uint32_t acc_cols = N <= 32 ? 32u : N <= 64 ? 64u : 128u;
+    constexpr uint32_t acc_cols = N <= 32 ? 32u : N <= 64 ? 64u : N <= 128 ? 128u : 256u;
     constexpr uint32_t ncols = TWO ? 2u * acc_cols : acc_cols;
     extern __shared__ uint8_t smem_raw[];
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
@@ -139,8 +140,8 @@ wgrad_direct_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                             mbar_arrive(fb);
                         } else {
                             mbar_expect_tx(fb, (s < 2 ? 2u : 1u) * gslot);
-                            tma_load_5d(gr0 + s * gslot, &tmG, fb, 0, x0, ya - 1 + j, gn, 0);
-                            if (s < 2) tma_load_5d(gr0 + (RG + s) * gslot, &tmG, fb, 0, x0, ya - 1 + j, gn, 0);
+                            tma_load_5d(gr0 + s * gslot, &tmG, fb, a.co0, x0, ya - 1 + j, gn, 0);
+                            if (s < 2) tma_load_5d(gr0 + (RG + s) * gslot, &tmG, fb, a.co0, x0, ya - 1 + j, gn, 0);
                         }
                     }
                     __syncwarp();
@@ -235,7 +236,7 @@ wgrad_direct_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 float v = bsum[c];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0 && v != 0.f) atomicAdd(a.db + c, v);
+                if (lane == 0 && v != 0.f) atomicAdd(a.db + a.co0 + c, v);
             }
         }
         // ---- flush: accumulator row m = slot * Cout + co (ky = 2 - slot), column n = kx * Cin + ci.  An M = 64
@@ -259,7 +260,7 @@ wgrad_direct_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                         const int n = c + jn;
                         if (n < N) {
                             const int kx = n / CIN, ci = n % CIN;
-                            atomicAdd(a.dwp + (long long)((ky * 3 + kx) * a.cin_total + a.c0 + ci) * a.Cout + co, v[jn]);
+                            atomicAdd(a.dwp + (long long)((ky * 3 + kx) * a.cin_total + a.c0 + ci) * a.Cout + a.co0 + co, v[jn]);
                         }
                     }
                 }
@@ -341,10 +342,11 @@ static int launch_wdir(const CUtensorMap& tmX, const CUtensorMap& tmG, WDirArgs&
 
 // The one-plane (Pr = 1) flavour of pgk_wgrad_thin: same arguments and meaning (pgk_wgrad_thin.cu), called from there.
 int pgk_wgrad_thin_direct(const void* x, const void* g, int H, int W, int Cin, int cin_total, int c0, int Cout,
-                          int ngroups, int group_n, const int* xoff, const int* goff, float* dwp, float* db,
-                          unsigned bias_mask, pgk_stream_t stream) {
+                          int cout_total, int co0, int ngroups, int group_n, const int* xoff, const int* goff, float* dwp,
+                          float* db, unsigned bias_mask, pgk_stream_t stream) {
     WDirArgs a;
-    a.H = H, a.W = W, a.Cout = Cout;
+    a.H = H, a.W = W, a.Cout = cout_total;
+    a.cout_total = cout_total, a.co0 = co0;
     a.RC = H < 32 ? H : H % 32 == 0 ? 32 : H % 16 == 0 ? 16 : 8;   // (H is a multiple of 8)
     a.chunks_y = H / a.RC;
     a.strips = W / 128;
@@ -379,9 +381,10 @@ int pgk_wgrad_thin_direct(const void* x, const void* g, int H, int W, int Cin, i
         if (rc) return rc;
     }
     {
-        unsigned long long dims[5] = {(unsigned long long)Cout, (unsigned long long)W, (unsigned long long)H,
+        const unsigned long long Ct = (unsigned long long)cout_total;
+        unsigned long long dims[5] = {Ct, (unsigned long long)W, (unsigned long long)H,
                                       (unsigned long long)(gmax + group_n), 1ull};
-        unsigned long long str[4] = {2ull * Cout, 2ull * Cout * W, 2ull * Cout * W * H, 2ull * Cout * W * H * (gmax + group_n)};
+        unsigned long long str[4] = {2ull * Ct, 2ull * Ct * W, 2ull * Ct * W * H, 2ull * Ct * W * H * (gmax + group_n)};
         unsigned box[5] = {(unsigned)Cout, 128u, 1u, 1u, 1u};
         int rc = pgk_make_tmap(&tmG, g, 5, dims, str, box, Cout == 8 ? 0 : 2 * Cout, "pgk_wgrad_thin(direct, g)");
         if (rc) return rc;
@@ -394,6 +397,7 @@ int pgk_wgrad_thin_direct(const void* x, const void* g, int H, int W, int Cin, i
     PGK_WDIR_CASE(8, 8) PGK_WDIR_CASE(8, 16) PGK_WDIR_CASE(8, 32) PGK_WDIR_CASE(8, 64)
     PGK_WDIR_CASE(16, 8) PGK_WDIR_CASE(16, 16) PGK_WDIR_CASE(16, 32) PGK_WDIR_CASE(16, 64)
     PGK_WDIR_CASE(32, 8) PGK_WDIR_CASE(32, 16) PGK_WDIR_CASE(32, 32) PGK_WDIR_CASE(32, 64)
+    PGK_WDIR_CASE(64, 32) PGK_WDIR_CASE(64, 64)
 #undef PGK_WDIR_CASE
     if (!matched) pgk_set_error("pgk_wgrad_thin(direct): no kernel instance for Cin %d Cout %d", Cin, Cout);
     return rc;

@@ -652,8 +652,8 @@ static int launch_wthin(const CUtensorMap& tmX, const CUtensorMap& tmG, WThinArg
 
 // the transposer-free one-plane flavour (pgk_wgrad_direct.cu)
 int pgk_wgrad_thin_direct(const void* x, const void* g, int H, int W, int Cin, int cin_total, int c0, int Cout,
-                          int ngroups, int group_n, const int* xoff, const int* goff, float* dwp, float* db,
-                          unsigned bias_mask, pgk_stream_t stream);
+                          int cout_total, int co0, int ngroups, int group_n, const int* xoff, const int* goff, float* dwp,
+                          float* db, unsigned bias_mask, pgk_stream_t stream);
 
 // Cin: channels handled by this launch (8, 16 or 32), starting at channel c0 of an x tensor with cin_total channels
 // (a 64-channel input is two launches).  db (optional): fused bias gradient over the groups in bias_mask; db and dwp
@@ -675,8 +675,8 @@ extern "C" int pgk_wgrad_thin(const void* x, long long x_ps, const void* g, long
             direct = e ? atoi(e) != 0 : 1;
         }
         if (direct && P == 1 && Pr == 1) {
-            int rc = pgk_wgrad_thin_direct(x, g, H, W, Cin, cin_total, c0, Cout, ngroups, group_n, xoff, goff, dwp, db,
-                                           bias_mask, stream);
+            int rc = pgk_wgrad_thin_direct(x, g, H, W, Cin, cin_total, c0, Cout, Cout, 0, ngroups, group_n, xoff, goff, dwp,
+                                           db, bias_mask, stream);
             if (rc) return rc;
             PGK_LAUNCH_CHECK("pgk_wgrad(thin tcgen05, direct)");
             return PGK_OK;

@@ -104,6 +104,11 @@ WGRAD = [
     (2, 8, 128, 16, 32, 1, 1),
     (2, 24, 128, 32, 32, 1, 1),
     (1, 40, 128, 16, 16, 1, 1),
+    # 64 input channels, one plane: the direct kernel in output-channel windows of 64 (pgk_api.cu)
+    (2, 128, 128, 64, 32, 1, 2),
+    (1, 256, 128, 64, 64, 1, 1),
+    (3, 128, 256, 64, 128, 1, 3),
+    (5, 128, 128, 64, 64, 1, 1),
     (1, 40, 128, 16, 16, 2, 1),
     (4, 16, 16, 64, 64, 1, 1),
     (4, 16, 16, 64, 64, 3, 1),
