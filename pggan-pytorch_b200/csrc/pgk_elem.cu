@@ -549,7 +549,11 @@ __global__ void __launch_bounds__(256, NARROW ? 3 : 1) rgb_wgrad_kernel(RgbWgrad
     const float a_scale = a.scale * dm, a_scale_b = a.scale_b * dm;
     __shared__ float red[256][MAXC * 8 + 8 + 1];
     __shared__ float isum[MAXC];
-    const int nch = a.K >> 3;
+    // wide layers (K > 64 channels, the low-resolution levels): blockIdx.y takes a tile of 8 chunks, so that a 4x4 level
+    // at batch 16 is 64 CTAs and not one thread block walking 256 pixels four at a time (70 us per launch at depth 0)
+    const int nch_all = a.K >> 3;
+    const int nch = nch_all > 8 && (nch_all & 7) == 0 ? 8 : nch_all;
+    const int ch0 = (int)blockIdx.y * nch;
     const int t = threadIdx.x;
     const int lanes = 256 / nch;
     const int ch = t % nch, pl = t / nch;
@@ -588,7 +592,7 @@ __global__ void __launch_bounds__(256, NARROW ? 3 : 1) rgb_wgrad_kernel(RgbWgrad
                             v[c] = (__ldg(p) + __ldg(p + 1)) + (__ldg(p + W2) + __ldg(p + W2 + 1));
                         }
                 }
-                qq = __ldg(reinterpret_cast<const uint4*>(a.t.p + ((long long)(a.t_n0 + n) * HW + r) * a.K + ch * 8));
+                qq = __ldg(reinterpret_cast<const uint4*>(a.t.p + ((long long)(a.t_n0 + n) * HW + r) * a.K + (ch0 + ch) * 8));
             };
             unsigned rr = (unsigned)r_begin + pl;
             const unsigned rend = (unsigned)r_end;
@@ -604,7 +608,7 @@ __global__ void __launch_bounds__(256, NARROW ? 3 : 1) rgb_wgrad_kernel(RgbWgrad
 #pragma unroll
                     for (int c = 0; c < MAXC; ++c) acc[c][j] = fmaf(iv[c], f[j], acc[c][j]);
                 }
-                if (ch == 0) {
+                if (ch0 + ch == 0) {
 #pragma unroll
                     for (int c = 0; c < MAXC; ++c) is[c] += iv[c];
                 }
@@ -649,7 +653,7 @@ __global__ void __launch_bounds__(256, NARROW ? 3 : 1) rgb_wgrad_kernel(RgbWgrad
                             iv[u][c] = (__ldg(p) + __ldg(p + 1)) + (__ldg(p + W2) + __ldg(p + W2 + 1));
                         }
                 }
-                ld8(a.t, ((long long)(a.t_n0 + n) * HW + r) * a.K + ch * 8, f[u]);
+                ld8(a.t, ((long long)(a.t_n0 + n) * HW + r) * a.K + (ch0 + ch) * 8, f[u]);
             }
 #pragma unroll
             for (int u = 0; u < UN; ++u) {
@@ -660,7 +664,7 @@ __global__ void __launch_bounds__(256, NARROW ? 3 : 1) rgb_wgrad_kernel(RgbWgrad
 #pragma unroll
                     for (int c = 0; c < MAXC; ++c) acc[c][j] = fmaf(iv[u][c], f[u][j], acc[c][j]);
                 }
-                if (ch == 0) {
+                if (ch0 + ch == 0) {
 #pragma unroll
                     for (int c = 0; c < MAXC; ++c) is[c] += iv[u][c];
                 }
@@ -694,7 +698,7 @@ __global__ void __launch_bounds__(256, NARROW ? 3 : 1) rgb_wgrad_kernel(RgbWgrad
     }
     __syncthreads();
     if (fast) {
-        if (lane == 0 && a.imgsum) {
+        if (lane == 0 && a.imgsum && ch0 == 0) {
             for (int c = 0; c < a.C; ++c) atomicAdd(&isum[c], is[c]);
         }
         for (int o = t; o < nch * (MAXC * 8 + 8); o += 256) {
@@ -704,13 +708,13 @@ __global__ void __launch_bounds__(256, NARROW ? 3 : 1) rgb_wgrad_kernel(RgbWgrad
             for (int w = 0; w < 8; ++w) tot += red[w * 32 + chn][q];
             const int j = q & 7, c = q >> 3;
             if (c < MAXC) {
-                if (c < a.C && a.dw) atomicAdd(a.dw + (long long)c * a.sa + (long long)(chn * 8 + j) * a.sk, a_scale * tot);
+                if (c < a.C && a.dw) atomicAdd(a.dw + (long long)c * a.sa + (long long)((ch0 + chn) * 8 + j) * a.sk, a_scale * tot);
             } else if (a.colsum) {
-                atomicAdd(a.colsum + chn * 8 + j, a_scale_b * tot);
+                atomicAdd(a.colsum + (ch0 + chn) * 8 + j, a_scale_b * tot);
             }
         }
     } else {
-        if (ch == 0 && pl < lanes && a.imgsum) {
+        if (ch0 + ch == 0 && pl < lanes && a.imgsum) {
             for (int c = 0; c < a.C; ++c) atomicAdd(&isum[c], is[c]);
         }
         if (t < nch) {
@@ -719,15 +723,15 @@ __global__ void __launch_bounds__(256, NARROW ? 3 : 1) rgb_wgrad_kernel(RgbWgrad
                 for (int l = 0; l < lanes; ++l) tot += red[l * nch + t][q];
                 int j = q & 7, c = q >> 3;
                 if (c < MAXC) {
-                    if (c < a.C && a.dw) atomicAdd(a.dw + (long long)c * a.sa + (long long)(t * 8 + j) * a.sk, a_scale * tot);
+                    if (c < a.C && a.dw) atomicAdd(a.dw + (long long)c * a.sa + (long long)((ch0 + t) * 8 + j) * a.sk, a_scale * tot);
                 } else if (a.colsum) {
-                    atomicAdd(a.colsum + t * 8 + j, a_scale_b * tot);
+                    atomicAdd(a.colsum + (ch0 + t) * 8 + j, a_scale_b * tot);
                 }
             }
         }
     }
     __syncthreads();
-    if (t < a.C && a.imgsum) atomicAdd(a.imgsum + t, a_scale_b * isum[t]);
+    if (t < a.C && a.imgsum && ch0 == 0) atomicAdd(a.imgsum + t, a_scale_b * isum[t]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1505,7 +1509,7 @@ extern "C" int pgk_prep_posbias(const float* w, float c, int cin_stride, int ch,
 
 extern "C" int pgk_posbias_wgrad(const void* ua, long long ua_ps, int P, int N, int H, int W, int Cout,
                                  const float* coef, float c, int cin_stride, int ch, float* dw, pgk_stream_t stream) {
-    int n_per = 16;
+    int n_per = 2;    // (16 samples per CTA left a depth-0 launch at 36 CTAs of 256 dependent 2-byte loads each: 81 us)
     dim3 grid(blocks_for(Cout, 128), 9, blocks_for(N, n_per));
     pgk_launch(posbias_wgrad_kernel, grid, 128, 0, ST, make_planes(ua, ua_ps, P), N, H, W, Cout, coef, c, cin_stride, ch, dw,
                                                n_per);
@@ -1597,7 +1601,9 @@ static int launch_reduce(ReduceArgs& a, pgk_stream_t stream, const char* name) {
             }
         }
     }
-    if ((long long)a.N * a.H * a.W < (1ll << 31)) {
+    // (few pixels and many channels -- the 4x4 ... 16x16 levels at small batch: one thread per pixel leaves a single CTA
+    // walking 64 chunks; the lanes-per-pixel kernel below spreads them)
+    if ((long long)a.N * a.H * a.W < (1ll << 31) && !((long long)a.N * a.H * a.W <= 8192 && maxch >= 16)) {
         const long long npix = (long long)a.N * a.H * a.W;
         pgk_launch(rgb_reduce_px_kernel, dim3(grid_cap((npix + 255) / 256)), 256, smem + sizeof(float) * MAXC, ST, a);
         PGK_LAUNCH_CHECK(name);
@@ -1654,8 +1660,10 @@ extern "C" int pgk_rgb_wgrad(const float* img, int img_n0, const void* t, int P,
     if (ctas > cap) ctas = cap;
     if (ctas < 1) ctas = 1;
     a.r_per_cta = (a.R + ctas - 1) / ctas;
-    if (narrow) pgk_launch(rgb_wgrad_kernel<true>, dim3((unsigned)ctas), 256, 0, ST, a, lhw, lw);
-    else pgk_launch(rgb_wgrad_kernel<false>, dim3((unsigned)ctas), 256, 0, ST, a, lhw, lw);
+    const int nch_all = K >> 3;
+    const unsigned gy = nch_all > 8 && (nch_all & 7) == 0 ? (unsigned)(nch_all / 8) : 1u;
+    if (narrow) pgk_launch(rgb_wgrad_kernel<true>, dim3((unsigned)ctas, gy), 256, 0, ST, a, lhw, lw);
+    else pgk_launch(rgb_wgrad_kernel<false>, dim3((unsigned)ctas, gy), 256, 0, ST, a, lhw, lw);
     PGK_LAUNCH_CHECK("pgk_rgb_wgrad");
     return PGK_OK;
 }
