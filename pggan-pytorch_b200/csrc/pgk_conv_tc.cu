@@ -883,8 +883,7 @@ extern "C" int pgk_conv_tc(const void* x, int P, int Pr, long long x_ps, int N, 
 
     CUtensorMap tmA, tmB;
     // (half operands come as exactly two planes: their tensor maps must not declare a third one behind the allocation)
-    static const bool tmap3 = getenv("PGK_FP16_TMAP3") != nullptr;   // (diagnostic: the round-1 declaration)
-    const unsigned long long planes_x = (fp16_x && !tmap3) ? 2ull : (unsigned long long)P, planes_w = (fp16_w && !tmap3) ? 2ull : 3ull;
+    const unsigned long long planes_x = fp16_x ? 2ull : (unsigned long long)P, planes_w = fp16_w ? 2ull : 3ull;
     {
         unsigned long long dims[5] = {(unsigned long long)Cin, (unsigned long long)W, (unsigned long long)H,
                                       (unsigned long long)N, planes_x};
@@ -999,105 +998,35 @@ extern "C" int pgk_wgrad_tc(const void* x, long long x_ps, const void* g, long l
     a.tiles_total = a.tiles_per_group * ngroups;
     const int sms = pgk_num_sms();
     const long long max_split = (a.tiles_total + 15) / 16;
-    // ---- plan: channel tile NT, slabs per CTA S, pixel split.  The round-1 rule (widest tile, S * NT = 512 columns,
-    // pixel range split to one or two waves) is right when the reduction is long; with few pixels (the 4x4 ... 32x32
-    // levels at batch 4) its CTAs run a few microseconds of MMAs and then push `split` copies of dW through atomics,
-    // which was the larger part of those launches.  A cost model in cycles (MMA issue at max(130, 0.66 NT) per
-    // MN-major instruction, operand boxes at ~20 bytes / cycle per SM, flush: ~8 floats / cycle per SM direct, ~96 / cycle
-    // chip-wide through atomics) ranks the alternatives; it replaces the round-1 plan only when it predicts at
-    // least 25 % less.  OPT-IN (PGK_WGRAD_PLAN=1): its first calibration (48 bytes / cycle) chose un-split plans that
-    // measured slower (c4 wgrad_tc 0.66 -> 0.87 ms per iteration, c3 3.14 -> 3.36); the staged flush below is what
-    // helped the short reductions.
-    struct WPlan {
-        int NT, S, sgroups, occ;
-        long long split;
-        double cost;
-    };
-    const double prods = Pr * (Pr + 1) / 2;
-    auto occ_of = [&](int NT, int S) {
-        const int stage_bytes = Pr * (2 * S + NT / 64) * box_bytes;
-        int occ = 512 / (int)tmem_cols(S * NT);
-        if (occ > 4) occ = 4;
-        while (occ > 1 && (kSmemLimit / occ - 2048) / stage_bytes < 3) --occ;
-        return occ;
-    };
-    auto eval = [&](int NT, int S, long long split) {
-        WPlan pl;
-        pl.NT = NT, pl.S = S, pl.split = split;
-        pl.sgroups = (slabs + S - 1) / S;
-        pl.occ = occ_of(NT, S);
-        const long long ctas = (long long)pl.sgroups * (Cout / NT) * split;
-        const long long per_cta = (a.tiles_total + split - 1) / split;
-        const double mma = (double)per_cta * S * 2 * prods * (0.66 * NT > 130.0 ? 0.66 * NT : 130.0);
-        const double load = (double)per_cta * (2 * S + NT / 64) * Pr * box_bytes / 20.0;
-        const long long resident = (long long)pl.occ * sms;
-        const long long waves = (ctas + resident - 1) / resident;
-        long long per_sm = (ctas + sms - 1) / sms;
-        if (per_sm > pl.occ) per_sm = pl.occ;
-        const double body = (mma > load ? mma : load) * per_sm + 4000.0;
-        const double flush_cta = (double)S * 128 * NT / 8.0 * per_sm;
-        const double flush_chip = split > 1 ? (double)ctas * S * 128 * NT / 96.0 : 0.0;
-        pl.cost = waves * (body + flush_cta) + flush_chip;
-        return pl;
-    };
-    WPlan legacy;
+    // ---- plan: widest channel tile, S * NT = 512 accumulator columns, the pixel range split to one or two waves.
+    // (A cost model that avoided splitting short reductions was tried in round 2b and measured slower twice -- c4
+    // wgrad_tc 0.66 -> 0.87 / 0.80 ms per iteration: un-split plans re-load X per tap from L2 -- and was removed; the
+    // staged flush below is what helped those shapes.)
+    a.NT = Cout < 256 ? Cout : 256;
+    const int smax = 512 / a.NT;
+    const int sgroups = (slabs + smax - 1) / smax;
+    a.S = (slabs + sgroups - 1) / sgroups;
+    const int stage_bytes = Pr * (2 * a.S + a.NT / 64) * box_bytes;
+    int ctas = 512 / (int)tmem_cols(a.S * a.NT);
+    if (ctas > 4) ctas = 4;
+    while (ctas > 1 && (kSmemLimit / ctas - 2048) / stage_bytes < 3) --ctas;
+    a.stages = (kSmemLimit / ctas - 2048) / stage_bytes;
+    if (a.stages > 8) a.stages = 8;
+    PGK_REQUIRE(a.stages >= 1, "pgk_wgrad_tc: stage does not fit in shared memory");
+    // split the pixel range so that the grid is (just under) one or two full waves of the SMs
+    const int base = sgroups * (Cout / a.NT);
+    long long split = 1;
     {
-        const int NT = Cout < 256 ? Cout : 256;
-        const int smax = 512 / NT;
-        const int sgroups = (slabs + smax - 1) / smax;
-        const int S = (slabs + sgroups - 1) / sgroups;
-        // split the pixel range so that the grid is (just under) one or two full waves of the SMs
-        const int base = sgroups * (Cout / NT);
-        long long split = 1;
         double best = -1.0;
         for (int w = 1; w <= 2; ++w) {
             long long sp = (long long)w * sms / base;
             if (sp < 1) sp = 1;
             if (sp > max_split) sp = max_split;
-            const long long ctas = sp * base;
-            const double util = (double)ctas / (double)(((ctas + sms - 1) / sms) * sms);
+            const long long nctas = sp * base;
+            const double util = (double)nctas / (double)(((nctas + sms - 1) / sms) * sms);
             if (util > best + 0.02) best = util, split = sp;
         }
-        legacy = eval(NT, S, split);
     }
-    WPlan plan = legacy;
-    {
-        static int model = -1;
-        if (model < 0) {
-            const char* e = getenv("PGK_WGRAD_PLAN");
-            model = e ? atoi(e) != 0 : 0;
-        }
-        WPlan bestp = legacy;
-        for (int NT = 256; model && NT >= 64; NT >>= 1) {
-            if (NT > Cout || Cout % NT) continue;
-            for (int S = 512 / NT; S >= 1; --S) {
-                if (S > slabs) continue;
-                const int sgroups = (slabs + S - 1) / S;
-                if ((slabs + sgroups - 1) / sgroups != S) continue;   // (the same grouping with a smaller S exists)
-                const long long base = (long long)sgroups * (Cout / NT), resident = (long long)occ_of(NT, S) * sms;
-                for (int w = 0; w <= 4; ++w) {
-                    long long sp = w == 0 ? 1 : (long long)w * resident / base;
-                    if (sp < 1) sp = 1;
-                    if (sp > max_split) sp = max_split;
-                    const WPlan c = eval(NT, S, sp);
-                    if (c.cost < bestp.cost) bestp = c;
-                }
-            }
-        }
-        if (bestp.cost < 0.75 * legacy.cost) plan = bestp;
-    }
-    a.NT = plan.NT, a.S = plan.S;
-    const int sgroups = plan.sgroups;
-    long long split = plan.split;
-    const int stage_bytes = Pr * (2 * a.S + a.NT / 64) * box_bytes;
-    const int ctas = plan.occ;
-    a.stages = (kSmemLimit / ctas - 2048) / stage_bytes;
-    if (a.stages > 8) a.stages = 8;
-    PGK_REQUIRE(a.stages >= 1, "pgk_wgrad_tc: stage does not fit in shared memory");
-    if (getenv("PGK_WGRAD_PLAN_DEBUG"))
-        fprintf(stderr, "pgk_wgrad_tc %dx%d n %d %d->%d Pr %d: NT %d S %d split %lld (model %.0f kcycles; round-1 plan NT %d S %d split %lld %.0f)\n",
-                H, W, ngroups * group_n, Cin, Cout, Pr, plan.NT, plan.S, plan.split, plan.cost / 1e3, legacy.NT, legacy.S,
-                legacy.split, legacy.cost / 1e3);
     if (split > 65535) split = 65535;
     a.tiles_per_cta = (a.tiles_total + split - 1) / split;
     split = (a.tiles_total + a.tiles_per_cta - 1) / a.tiles_per_cta;

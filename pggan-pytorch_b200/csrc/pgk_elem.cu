@@ -381,72 +381,6 @@ __global__ void __launch_bounds__(256) rgb_reduce_kernel(ReduceArgs a) {
     }
 }
 
-// UN pixels per thread and pass, MCH chunks of 8 channels per source at most; one-plane tensors (raw 16-byte loads are
-// kept packed until they are used)
-template <int UN, int MCH>
-__device__ __forceinline__ void reduce_px_narrow(const ReduceArgs& a, const float* wsm, int off1, int offb, unsigned npix,
-                                                 unsigned HW, unsigned W, unsigned stride) {
-    for (unsigned pix0 = blockIdx.x * blockDim.x + threadIdx.x; pix0 < npix; pix0 += UN * stride) {
-        uint4 q[UN][2][MCH];
-        unsigned nn[UN], rr[UN];
-        bool ok[UN];
-#pragma unroll
-        for (int u = 0; u < UN; ++u) {
-            const unsigned pix = pix0 + u * stride;
-            ok[u] = pix < npix;
-            if (!ok[u]) continue;
-            const unsigned n = pix / HW, r = pix - n * HW;
-            const unsigned y = r / W, x = r - y * W;
-            nn[u] = n, rr[u] = r;
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                if (s >= a.nsrc) continue;
-                const ReduceSrc& S = a.s[s];
-                const unsigned Hs = a.H >> S.ups, Ws = a.W >> S.ups;
-                const long long base = ((long long)(n * Hs + (y >> S.ups)) * Ws + (x >> S.ups)) * S.K;
-#pragma unroll
-                for (int ch = 0; ch < MCH; ++ch)
-                    if (ch < (S.K >> 3)) q[u][s][ch] = __ldg(reinterpret_cast<const uint4*>(S.t.p + base + ch * 8));
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < UN; ++u) {
-            if (!ok[u]) continue;
-            float acc[MAXC];
-#pragma unroll
-            for (int c = 0; c < MAXC; ++c) acc[c] = wsm[offb + c];
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                if (s >= a.nsrc) continue;
-                const int K = a.s[s].K;
-                const float* wm = wsm + (s ? off1 : 0);
-#pragma unroll
-                for (int ch = 0; ch < MCH; ++ch) {
-                    if (ch >= (K >> 3)) continue;
-                    float g[8];
-                    unpack8(q[u][s][ch], g);
-#pragma unroll
-                    for (int c = 0; c < MAXC; ++c)
-                        if (c < a.C) {
-                            const float4 w0 = *reinterpret_cast<const float4*>(wm + c * K + ch * 8);
-                            const float4 w1 = *reinterpret_cast<const float4*>(wm + c * K + ch * 8 + 4);
-                            float t = acc[c];
-                            t = fmaf(g[0], w0.x, t), t = fmaf(g[1], w0.y, t), t = fmaf(g[2], w0.z, t), t = fmaf(g[3], w0.w, t);
-                            t = fmaf(g[4], w1.x, t), t = fmaf(g[5], w1.y, t), t = fmaf(g[6], w1.z, t), t = fmaf(g[7], w1.w, t);
-                            acc[c] = t;
-                        }
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < MAXC; ++c)
-                if (c < a.C) {
-                    const long long o = ((long long)nn[u] * a.C + c) * HW + rr[u];
-                    a.img[o] = a.accumulate ? a.img[o] + acc[c] : acc[c];
-                }
-        }
-    }
-}
-
 // The same reduction with one thread per output pixel -- full-warp coalesced image stores, no idle lanes or shuffles,
 // 32-bit index arithmetic, weights read from shared memory as float4 broadcasts, the bias terms folded into one
 // constant per image channel.  (A lane reads its pixel's K channels 16 bytes at a time; the other half of every
@@ -476,17 +410,6 @@ __global__ void __launch_bounds__(256) rgb_reduce_px_kernel(ReduceArgs a) {
     __syncthreads();
     const unsigned npix = (unsigned)a.N * a.H * a.W, HW = (unsigned)a.H * a.W, W = (unsigned)a.W;
     const unsigned stride = gridDim.x * blockDim.x;
-    // narrow one-plane layers (the 256^2 ... 1024^2 levels): one pixel is 16-64 bytes of loads, so several pixels per
-    // thread and pass with their loads issued first; wide layers keep one pixel (K / 8 independent loads already)
-    const int kmax = (a.nsrc > 1 && a.s[1].K > a.s[0].K) ? a.s[1].K : a.s[0].K;
-    if (PGK_RGB_UN > 1 && a.s[0].t.P == 1 && kmax <= 16) {
-        reduce_px_narrow<4, 2>(a, wsm, off1, offb, npix, HW, W, stride);
-        return;
-    }
-    if (PGK_RGB_UN > 1 && a.s[0].t.P == 1 && kmax <= 32) {
-        reduce_px_narrow<2, 4>(a, wsm, off1, offb, npix, HW, W, stride);
-        return;
-    }
     for (unsigned pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += stride) {
         const unsigned n = pix / HW, r = pix - n * HW;
         const unsigned y = r / W, x = r - y * W;

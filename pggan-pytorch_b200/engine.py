@@ -42,10 +42,6 @@ FUSE_CVT = os.environ.get('PGK_FUSE_CVT', '1') == '1'
 # row-streaming thin kernel stacks the three filter rows along N and is bound by HBM.  Fourth element of the operand
 # tuples: the layer's pgk_pack_thin packing.  PGK_THIN64=0 for A/B runs.
 THIN64 = os.environ.get('PGK_THIN64', '1') == '1'
-# diagnostic knobs of the fault hunt
-_FP16_NOPOS = os.environ.get('PGK_FP16_NOPOS', '0') == '1'
-_FP16_MINPIX = int(os.environ.get('PGK_FP16_MINPIX', '0'))
-_FP16_PAD = int(os.environ.get('PGK_FP16_PAD', '0'))
 
 
 def _ints(vals):
@@ -172,14 +168,13 @@ def conv(x, w, cout, ks, out, ups=0, bias=None, posT=None, pos_s=None, act=0, ma
     mp, mps = _mask(mask)
     wf, wt = w[0], w[1]
     if (FWD_FP16 and fwd and len(w) > 2 and w[2] is not None and x.P >= 2 and mask is None and not ups and scale == 1.0
-            and not (_FP16_NOPOS and posT is not None) and out.N * out.H * out.W >= _FP16_MINPIX
             and _lib.load().pgk_conv_tc_supported(out.N, out.H, out.W, x.C, cout, ks, 0)):
         # fp16 two-plane copy of the input (one extra pass), then the conv on half operands
         comp = _h16_in(x)
         if comp is not None:
             xh_ptr, xh_ps = comp             # written by the kernel that produced x
         else:
-            xh = torch.empty((2, x.N * x.per + _FP16_PAD), dtype=torch.float16, device=x.t.device)
+            xh = torch.empty((2, x.N * x.per), dtype=torch.float16, device=x.t.device)
             call('pgk_cvt_fp16x2', x.ptr, x.ps, x.P, x.N * x.per, xh.data_ptr(), xh.stride(0))
             xh_ptr, xh_ps = xh.data_ptr(), xh.stride(0)
         call('pgk_conv_fp16', xh_ptr, xh_ps, out.N, out.H, out.W, x.C, cout, ks, w[2].data_ptr(),
