@@ -190,15 +190,19 @@ extern "C" int pgk_wgrad(const void* x, long long x_ps, const void* g, long long
             const char* e = getenv("PGK_WGRAD64");
             w64 = e ? atoi(e) != 0 : 1;
         }
-        if (w64 && tc_enabled() && Cin == 64 && P == 1 && Pr == 1 && KS == 3 && !ups && (Cout == 32 || Cout == 64 || Cout == 128) &&
+        // (128 input channels -- the generator's first conv of a level reads the previous level's width: two windows of 64)
+        const bool in_ok = Cin == 64 || (Cin == 128 && Cout <= 64);
+        if (w64 && tc_enabled() && in_ok && P == 1 && Pr == 1 && KS == 3 && !ups && (Cout == 32 || Cout == 64 || Cout == 128) &&
             W % 128 == 0 && H >= 8 && H % 8 == 0 && (((uintptr_t)x | (uintptr_t)g) & 15) == 0) {
             ProfScope prof(PGK_PROF_WGRAD_THIN, flops, bytes, stream, Pr);
             const int cw = Cout == 32 ? 32 : 64;
-            for (int co0 = 0; co0 < Cout; co0 += cw) {
-                int rc = pgk_wgrad_thin_direct(x, g, H, W, 64, 64, 0, cw, Cout, co0, ngroups, group_n, xoff, goff, dwp, db,
-                                               bias_groups, stream);
-                if (rc) return rc;
-                PGK_LAUNCH_CHECK("pgk_wgrad(thin tcgen05, direct, 64 channels)");
+            for (int c0 = 0; c0 < Cin; c0 += 64) {
+                for (int co0 = 0; co0 < Cout; co0 += cw) {
+                    int rc = pgk_wgrad_thin_direct(x, g, H, W, 64, Cin, c0, cw, Cout, co0, ngroups, group_n, xoff, goff, dwp,
+                                                   c0 == 0 ? db : nullptr, bias_groups, stream);
+                    if (rc) return rc;
+                    PGK_LAUNCH_CHECK("pgk_wgrad(thin tcgen05, direct, 64-channel windows)");
+                }
             }
             return PGK_OK;
         }

@@ -109,6 +109,8 @@ WGRAD = [
     (1, 256, 128, 64, 64, 1, 1),
     (3, 128, 256, 64, 128, 1, 3),
     (5, 128, 128, 64, 64, 1, 1),
+    (2, 128, 128, 128, 64, 1, 2),
+    (1, 128, 256, 128, 32, 1, 1),
     (1, 40, 128, 16, 16, 2, 1),
     (4, 16, 16, 64, 64, 1, 1),
     (4, 16, 16, 64, 64, 3, 1),
