@@ -305,7 +305,8 @@ class ConvW(object):
         thin = lambda ci, co: kind == W_CONV and ks == 3 and ci in (8, 16, 32) and co in (8, 16, 32, 64)
         self.thin_f, self.thin_b = thin(cin, cout), thin(cout, cin)
         # 64-input-channel layers the thin kernel takes over in the one-plane mode (THIN64): a second, thin packing
-        t64 = lambda ci, co: THIN64 and kind == W_CONV and ks == 3 and ci == 64 and co in (32, 64)
+        t64 = lambda ci, co: (THIN64 and os.environ.get('PGK_TC', '1') != '0' and kind == W_CONV and ks == 3 and ci == 64
+                              and co in (32, 64))
         self.t64_f, self.t64_b = t64(cin, cout), need_wb and t64(cout, cin)
         # the fp32 operands are read by the CUDA-core kernels only: shapes that always take a tensor-core kernel skip
         # them (the thin packing of the 64-channel layers is made from them)
